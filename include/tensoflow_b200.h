@@ -1,0 +1,153 @@
+/*
+ * tensoflow_b200 -- C ABI of the B200-native TensoFlow hot path.
+ *
+ * The reference (fudan-zvg/tensoflow) has no plugin registry: its operator
+ * boundary is a set of third-party native ops called from PyTorch modules.
+ * Each entry point below names the reference call site(s) it replaces
+ * (paths relative to the reference tree).  Conventions:
+ *   - every pointer is a DEVICE pointer to contiguous fp32 (int32 where said),
+ *     owned by the caller; the library never allocates, frees or retains them
+ *     (exception: the BVH handle, created/destroyed explicitly);
+ *   - gradient outputs are ACCUMULATED into (caller zero-initialises);
+ *   - all work is enqueued on `stream` (a cudaStream_t); no implicit syncs;
+ *   - return 0 on success, non-zero otherwise, message via tf_last_error();
+ *   - re-entrant: backward entry points are called from autograd worker threads.
+ *   - there is no CPU fallback.
+ */
+#ifndef TENSOFLOW_B200_H
+#define TENSOFLOW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TF_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define TF_API __attribute__((visibility("default")))
+#else
+#define TF_API
+#endif
+
+typedef void* tf_stream_t; /* cudaStream_t */
+
+/* A VM-decomposed (3 planes x 3 lines) tensorial field.
+ * Reference storage: nn.Parameter [1,C,H,W] / [1,C,G,1] (network/fields.py:101-111).
+ * Here the same logical tensors are held channels-last, i.e. plane i is
+ * [H][W][C] and line i is [G][C] in memory, so one texel's C channels are
+ * contiguous (16-byte vector loads / reductions).  Mip levels 1..L-1 (2x2 box
+ * filter, what nvdiffrast builds internally) live in one buffer per texture,
+ * level after level.  plane i is addressed with u = x[m0] along W and
+ * v = x[m1] along H, (m0,m1) = (0,1),(0,2),(1,2); line i with x[2-i] along G
+ * (network/fields.py:28-29,268-288). */
+typedef struct {
+    const float* plane[3];
+    const float* plane_mip[3]; /* may be NULL when n_levels == 1 */
+    const float* line[3];
+    const float* line_mip[3];
+    int32_t plane_h[3], plane_w[3], line_g[3];
+    int32_t n_comp;   /* C, multiple of 4 */
+    int32_t n_levels; /* L >= 1 */
+    float aabb_min[3], aabb_max[3];
+} tf_vm_field_t;
+
+/* Mutable twin (mip outputs / gradient accumulators), same layouts. */
+typedef struct {
+    float* plane[3];
+    float* plane_mip[3];
+    float* line[3];
+    float* line_mip[3];
+} tf_vm_mut_t;
+
+/* Decoder MLP of TensoSDF: Linear(3C+3,H) -> Softplus(beta=100) -> Linear(H,1+A)
+ * (network/fields.py:78-91).  PyTorch layouts: W0 [H][3C+3], W1 [1+A][H]. */
+typedef struct {
+    const float* W0; const float* b0; const float* W1; const float* b1;
+    int32_t hidden;  /* H, multiple of 32 */
+    int32_t app_dim; /* A, multiple of 4, <= 128 */
+} tf_sdf_mlp_t;
+
+typedef struct { float* W0; float* b0; float* W1; float* b1; } tf_sdf_mlp_grad_t;
+
+TF_API int tf_abi_version(void);
+TF_API const char* tf_last_error(void);
+/* number of kernels this library has launched in this process (bench.py reports it) */
+TF_API long long tf_launch_count(void);
+
+/* ---- VM field ------------------------------------------------------------ */
+
+/* Rebuild mip levels 1..L-1 from level 0 (nvdiffrast does this inside every
+ * dr.texture call: network/fields.py:276-288). */
+TF_API int tf_vm_build_mips(const tf_vm_field_t* f, const tf_vm_mut_t* out, tf_stream_t stream);
+
+/* Fold gradients accumulated on levels 1..L-1 into level 0 (x1/4 per level,
+ * x1/2 for lines) -- the mip part of dr.texture's backward. */
+TF_API int tf_vm_fold_mip_grads(const tf_vm_field_t* f, const tf_vm_mut_t* g, tf_stream_t stream);
+
+/* feat[n, 3C] = concat_i plane_i(x) * line_i(x): the 6 dr.texture calls + product of
+ * network/fields.py:272-293, :786-806 and network/flow.py:719-740.
+ * level may be NULL (level 0 only). */
+TF_API int tf_vm_feature_fwd(const tf_vm_field_t* f, const float* xyz, const float* level, int64_t n,
+                      float* feat, tf_stream_t stream);
+TF_API int tf_vm_feature_bwd(const tf_vm_field_t* f, const float* xyz, const float* level, int64_t n,
+                      const float* d_feat, const tf_vm_mut_t* g, tf_stream_t stream);
+
+/* ---- fused TensoSDF stencil ------------------------------------------------
+ * One call = TensoSDF.forward (network/fields.py:262-299) at the sample plus the
+ * six finite-difference taps of TensoSDF.gradient (network/fields.py:227-260):
+ *   sdf7[n,7] : SDF at (centre, +x, -x, +y, -y, +z, -z), taps at +-units[k]
+ *   feat[n,A] : appearance features (decoder outputs 1..A) at the centre
+ *   grad[n,3] : central differences          hess[n] : (g.h)/(|g|^2+1e-5)
+ * feat / grad / hess may be NULL.  level may be NULL. */
+TF_API size_t tf_sdf_stencil_fwd_workspace(const tf_vm_field_t* f, const tf_sdf_mlp_t* m);
+TF_API int tf_sdf_stencil_fwd(const tf_vm_field_t* f, const tf_sdf_mlp_t* m, const float* xyz,
+                       const float* level, int64_t n, const float units[3], float* sdf7,
+                       float* feat, float* grad, float* hess, void* workspace, size_t ws_bytes,
+                       tf_stream_t stream);
+
+/* SDF only (TensoSDF.sdf, network/fields.py:148) -- the hierarchical sampler's query. */
+TF_API int tf_sdf_only_fwd(const tf_vm_field_t* f, const tf_sdf_mlp_t* m, const float* xyz,
+                    const float* level, int64_t n, float* sdf, void* workspace, size_t ws_bytes,
+                    tf_stream_t stream);
+
+/* Backward of tf_sdf_stencil_fwd.  g_sdf[n], g_feat[n,A], g_grad[n,3], g_hess[n] are the
+ * upstream gradients (each may be NULL = zero); sdf7 is the forward output.
+ * Any workspace size >= tf_sdf_stencil_bwd_workspace(.., 1) works; larger is faster
+ * (the call processes the n samples in slices that fit). */
+TF_API size_t tf_sdf_stencil_bwd_workspace(const tf_vm_field_t* f, const tf_sdf_mlp_t* m, int64_t n_slice);
+TF_API int tf_sdf_stencil_bwd(const tf_vm_field_t* f, const tf_sdf_mlp_t* m, const float* xyz,
+                       const float* level, int64_t n, const float units[3], const float* sdf7,
+                       const float* g_sdf, const float* g_feat, const float* g_grad,
+                       const float* g_hess, const tf_vm_mut_t* g_field,
+                       const tf_sdf_mlp_grad_t* g_mlp, void* workspace, size_t ws_bytes,
+                       tf_stream_t stream);
+
+/* ---- NeuS alpha + compositing ------------------------------------------------
+ * Replaces ShapeRenderer.compute_sdf_alpha's tail (network/shapeRenderer.py:1004-1024),
+ * nerfacc.render_weight_from_alpha and the nerfacc.accumulate_along_rays calls
+ * (network/shapeRenderer.py:1166-1206).  Samples are packed ray after ray;
+ * ray_offsets[r]..ray_offsets[r+1] (int32, n_rays+1 entries) replaces int64 ray_indices.
+ *   variance : device scalar, inv_s = clip(exp(10*variance),1e-6,1e6)
+ *   vals[n,D]: per-sample values to accumulate (colour, gradient, radiance, ...), D <= 16
+ * outputs: alpha[n], weights[n], acc[r], out[r,D] = sum_i w_i vals_i. */
+TF_API int tf_neus_composite_fwd(const float* sdf, const float* grad, const float* dists,
+                          const float* dirs, const int32_t* ray_offsets, int32_t n_rays,
+                          const float* variance, float cos_anneal, const float* vals, int32_t D,
+                          float* alpha, float* weights, float* acc, float* out,
+                          tf_stream_t stream);
+/* g_weights may be NULL.  d_variance is a device scalar accumulated atomically
+ * (pass NULL when inv_s is frozen: network/shapeRenderer.py:1007-1008). */
+TF_API int tf_neus_composite_bwd(const float* sdf, const float* grad, const float* dists,
+                          const float* dirs, const int32_t* ray_offsets, int32_t n_rays,
+                          const float* variance, float cos_anneal, const float* vals, int32_t D,
+                          const float* alpha, const float* weights, const float* g_acc,
+                          const float* g_out, const float* g_weights, float* d_sdf,
+                          float* d_grad, float* d_vals, float* d_variance, tf_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TENSOFLOW_B200_H */

@@ -1,0 +1,327 @@
+"""torch.autograd.Function layer over the C ABI (include/tensoflow_b200.h).
+
+PyTorch is plumbing here: it owns device memory and streams; all arithmetic of the
+hot path runs in the hand-written sm_100a kernels of libtensoflow_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import VMField, VMMut, SdfMlp, SdfMlpGrad, check, ptr, stream_ptr
+
+BWD_WORKSPACE_BYTES = 4 << 30   # upper bound for the stencil-backward scratch
+
+
+class KernelTimers:
+    """Optional CUDA-event timing of the C-ABI calls (bench.py turns it on for the timed
+    region; events are recorded on the launching stream)."""
+    enabled = False
+    events = {}
+
+    @classmethod
+    def reset(cls, enabled: bool):
+        cls.enabled = enabled
+        cls.events = {}
+
+    @classmethod
+    def totals_ms(cls):
+        return {k: (sum(a.elapsed_time(b) for a, b in v), len(v)) for k, v in cls.events.items()}
+
+
+class _timed:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if KernelTimers.enabled:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if KernelTimers.enabled:
+            self.b.record()
+            KernelTimers.events.setdefault(self.name, []).append((self.a, self.b))
+        return False
+
+
+def _nhwc(p: torch.Tensor) -> torch.Tensor:
+    """[1,C,H,W] parameter -> contiguous [H,W,C] tensor (a view when the parameter is
+    stored channels-last, which is how tensoflow_b200 modules hold it)."""
+    v = p.detach()[0].permute(1, 2, 0)
+    return v if v.is_contiguous() else v.contiguous()
+
+
+def mip_sizes(h: int, w: int, n_levels: int):
+    out = []
+    for _ in range(1, n_levels):
+        h = h // 2 if h > 1 else 1
+        w = w // 2 if w > 1 else 1
+        out.append((h, w))
+    return out
+
+
+class VMDesc:
+    """Owns the C descriptor of a VM field plus the tensors it points to."""
+
+    def __init__(self, planes: Sequence[torch.Tensor], lines: Sequence[torch.Tensor], aabb: torch.Tensor,
+                 n_levels: int, build_mips: bool):
+        self.planes = [_nhwc(p) for p in planes]          # [H,W,C]
+        self.lines = [_nhwc(l)[:, 0, :] for l in lines]   # [G,C]
+        self.lines = [l if l.is_contiguous() else l.contiguous() for l in self.lines]
+        self.n_levels = int(n_levels)
+        self.C = int(self.planes[0].shape[-1])
+        dev = self.planes[0].device
+        self.device = dev
+        f = VMField()
+        self.plane_mips: List[Optional[torch.Tensor]] = [None] * 3
+        self.line_mips: List[Optional[torch.Tensor]] = [None] * 3
+        ab = aabb.detach().float().cpu()
+        for i in range(3):
+            H, W, _ = self.planes[i].shape
+            G = self.lines[i].shape[0]
+            f.plane[i] = self.planes[i].data_ptr()
+            f.line[i] = self.lines[i].data_ptr()
+            f.plane_h[i], f.plane_w[i], f.line_g[i] = H, W, G
+            f.aabb_min[i] = float(ab[0, i])
+            f.aabb_max[i] = float(ab[1, i])
+            if self.n_levels > 1 and build_mips:
+                npl = sum(h * w for h, w in mip_sizes(H, W, self.n_levels))
+                nln = sum(h for h, _ in mip_sizes(G, 1, self.n_levels))
+                self.plane_mips[i] = torch.empty(npl * self.C, device=dev, dtype=torch.float32)
+                self.line_mips[i] = torch.empty(nln * self.C, device=dev, dtype=torch.float32)
+                f.plane_mip[i] = self.plane_mips[i].data_ptr()
+                f.line_mip[i] = self.line_mips[i].data_ptr()
+        f.n_comp = self.C
+        f.n_levels = self.n_levels
+        self.c = f
+        if self.n_levels > 1 and build_mips:
+            out = VMMut()
+            for i in range(3):
+                out.plane_mip[i] = self.plane_mips[i].data_ptr()
+                out.line_mip[i] = self.line_mips[i].data_ptr()
+            check(_lib.load().tf_vm_build_mips(C.byref(f), C.byref(out), stream_ptr()), "tf_vm_build_mips")
+
+    def new_grads(self, with_mips: bool):
+        """Zeroed gradient accumulators with the same layouts; returns (VMMut, tensors)."""
+        g = VMMut()
+        gp = [torch.zeros_like(p) for p in self.planes]
+        gl = [torch.zeros_like(l) for l in self.lines]
+        gpm: List[Optional[torch.Tensor]] = [None] * 3
+        glm: List[Optional[torch.Tensor]] = [None] * 3
+        for i in range(3):
+            g.plane[i] = gp[i].data_ptr()
+            g.line[i] = gl[i].data_ptr()
+            if with_mips and self.n_levels > 1:
+                gpm[i] = torch.zeros_like(self.plane_mips[i])
+                glm[i] = torch.zeros_like(self.line_mips[i])
+                g.plane_mip[i] = gpm[i].data_ptr()
+                g.line_mip[i] = glm[i].data_ptr()
+        return g, gp, gl, gpm, glm
+
+    def finish_grads(self, g, gp, gl, with_mips: bool):
+        """Fold mip gradients into level 0 and return grads shaped like the parameters."""
+        if with_mips and self.n_levels > 1:
+            check(_lib.load().tf_vm_fold_mip_grads(C.byref(self.c), C.byref(g), stream_ptr()), "tf_vm_fold_mip_grads")
+        planes = [t.permute(2, 0, 1).unsqueeze(0) for t in gp]                 # [1,C,H,W] (channels-last strides)
+        lines = [t.permute(1, 0).unsqueeze(0).unsqueeze(-1) for t in gl]       # [1,C,G,1]
+        return planes, lines
+
+
+def _f32c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    t = t.detach()
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _mlp_desc(W0, b0, W1, b1):
+    m = SdfMlp()
+    ws = [_f32c(W0), _f32c(b0), _f32c(W1), _f32c(b1)]
+    m.W0, m.b0, m.W1, m.b1 = (w.data_ptr() for w in ws)
+    m.hidden = int(W0.shape[0])
+    m.app_dim = int(W1.shape[0]) - 1
+    return m, ws
+
+
+def _units_arr(units) -> C.Array:
+    u = [float(x) for x in units]
+    return (C.c_float * 3)(*u)
+
+
+class SdfStencilFunction(torch.autograd.Function):
+    """TensoSDF.forward at x plus the six FD taps of TensoSDF.gradient
+    (reference network/fields.py:262-299, 227-260) in one fused kernel.
+
+    inputs : xyz [N,3], level [N] or None, units (3 floats), aabb [2,3], n_levels,
+             W0,b0,W1,b1, plane0..2, line0..2
+    outputs: sdf [N], feat [N,A], grad [N,3], hess [N]
+    No gradient flows to xyz / level (the reference detaches uv and never asks for d level).
+    """
+
+    @staticmethod
+    def forward(ctx, xyz, level, units, aabb, n_levels, W0, b0, W1, b1, *factors):
+        lib = _lib.load()
+        planes, lines = factors[:3], factors[3:6]
+        xyz_c = _f32c(xyz.reshape(-1, 3))
+        lvl_c = None if level is None else _f32c(level.reshape(-1))
+        n = xyz_c.shape[0]
+        vm = VMDesc(planes, lines, aabb, n_levels, build_mips=lvl_c is not None)
+        m, mlp_keep = _mlp_desc(W0, b0, W1, b1)
+        A = m.app_dim
+        dev = xyz_c.device
+        sdf7 = torch.empty(n, 7, device=dev, dtype=torch.float32)
+        feat = torch.empty(n, A, device=dev, dtype=torch.float32)
+        grad = torch.empty(n, 3, device=dev, dtype=torch.float32)
+        hess = torch.empty(n, device=dev, dtype=torch.float32)
+        wsb = lib.tf_sdf_stencil_fwd_workspace(C.byref(vm.c), C.byref(m))
+        if wsb == 0:
+            check(1, "tf_sdf_stencil_fwd_workspace")
+        ws = torch.empty(wsb // 4, device=dev, dtype=torch.float32)
+        u = _units_arr(units)
+        with _timed("sdf_stencil_fwd"):
+            check(lib.tf_sdf_stencil_fwd(C.byref(vm.c), C.byref(m), ptr(xyz_c), ptr(lvl_c), n, u, ptr(sdf7), ptr(feat),
+                                         ptr(grad), ptr(hess), ptr(ws), wsb, stream_ptr()), "tf_sdf_stencil_fwd")
+        ctx.save_for_backward(xyz_c, lvl_c, sdf7, aabb, W0, b0, W1, b1, *factors)
+        ctx.units = [float(x) for x in units]
+        ctx.n_levels = n_levels
+        sdf = sdf7[:, 0].contiguous()
+        return sdf, feat, grad, hess
+
+    @staticmethod
+    def backward(ctx, g_sdf, g_feat, g_grad, g_hess):
+        lib = _lib.load()
+        xyz_c, lvl_c, sdf7, aabb, W0, b0, W1, b1, *factors = ctx.saved_tensors
+        planes, lines = factors[:3], factors[3:6]
+        n = xyz_c.shape[0]
+        with_mips = lvl_c is not None
+        vm = VMDesc(planes, lines, aabb, ctx.n_levels, build_mips=with_mips)
+        m, mlp_keep = _mlp_desc(W0, b0, W1, b1)
+        g, gp, gl, gpm, glm = vm.new_grads(with_mips)
+        dW0 = torch.zeros_like(mlp_keep[0]); db0 = torch.zeros_like(mlp_keep[1])
+        dW1 = torch.zeros_like(mlp_keep[2]); db1 = torch.zeros_like(mlp_keep[3])
+        mg = SdfMlpGrad()
+        mg.W0, mg.b0, mg.W1, mg.b1 = dW0.data_ptr(), db0.data_ptr(), dW1.data_ptr(), db1.data_ptr()
+        need_all = lib.tf_sdf_stencil_bwd_workspace(C.byref(vm.c), C.byref(m), max(n, 1))
+        wsb = min(need_all, max(BWD_WORKSPACE_BYTES, lib.tf_sdf_stencil_bwd_workspace(C.byref(vm.c), C.byref(m), 16)))
+        ws = torch.empty(wsb // 4, device=xyz_c.device, dtype=torch.float32)
+        gs, gf, gg, gh = _f32c(g_sdf), _f32c(g_feat), _f32c(g_grad), _f32c(g_hess)
+        with _timed("sdf_stencil_bwd"):
+            check(lib.tf_sdf_stencil_bwd(C.byref(vm.c), C.byref(m), ptr(xyz_c), ptr(lvl_c), n, _units_arr(ctx.units), ptr(sdf7),
+                                         ptr(gs), ptr(gf), ptr(gg), ptr(gh), C.byref(g), C.byref(mg), ptr(ws), wsb, stream_ptr()),
+                  "tf_sdf_stencil_bwd")
+        d_planes, d_lines = vm.finish_grads(g, gp, gl, with_mips)
+        return (None, None, None, None, None, dW0, db0, dW1, db1, *d_planes, *d_lines)
+
+
+def sdf_only(xyz, level, aabb, n_levels, W0, b0, W1, b1, planes, lines) -> torch.Tensor:
+    """TensoSDF.sdf (reference network/fields.py:148) without autograd -> [N]."""
+    lib = _lib.load()
+    xyz_c = _f32c(xyz.reshape(-1, 3))
+    lvl_c = None if level is None else _f32c(level.reshape(-1))
+    n = xyz_c.shape[0]
+    vm = VMDesc(planes, lines, aabb, n_levels, build_mips=lvl_c is not None)
+    m, keep = _mlp_desc(W0, b0, W1, b1)
+    out = torch.empty(n, device=xyz_c.device, dtype=torch.float32)
+    wsb = lib.tf_sdf_stencil_fwd_workspace(C.byref(vm.c), C.byref(m))
+    if wsb == 0:
+        check(1, "tf_sdf_stencil_fwd_workspace")
+    ws = torch.empty(wsb // 4, device=xyz_c.device, dtype=torch.float32)
+    check(lib.tf_sdf_only_fwd(C.byref(vm.c), C.byref(m), ptr(xyz_c), ptr(lvl_c), n, ptr(out), ptr(ws), wsb, stream_ptr()),
+          "tf_sdf_only_fwd")
+    return out
+
+
+class VMFeatureFunction(torch.autograd.Function):
+    """feat[N,3C] = concat_i plane_i(x)*line_i(x) (reference network/fields.py:776-806,
+    network/flow.py:709-740).  inputs: xyz, level|None, aabb, n_levels, plane0..2, line0..2."""
+
+    @staticmethod
+    def forward(ctx, xyz, level, aabb, n_levels, *factors):
+        lib = _lib.load()
+        planes, lines = factors[:3], factors[3:6]
+        xyz_c = _f32c(xyz.reshape(-1, 3))
+        lvl_c = None if level is None else _f32c(level.reshape(-1))
+        n = xyz_c.shape[0]
+        vm = VMDesc(planes, lines, aabb, n_levels, build_mips=lvl_c is not None)
+        feat = torch.empty(n, 3 * vm.C, device=xyz_c.device, dtype=torch.float32)
+        check(lib.tf_vm_feature_fwd(C.byref(vm.c), ptr(xyz_c), ptr(lvl_c), n, ptr(feat), stream_ptr()), "tf_vm_feature_fwd")
+        ctx.save_for_backward(xyz_c, lvl_c, aabb, *factors)
+        ctx.n_levels = n_levels
+        return feat
+
+    @staticmethod
+    def backward(ctx, g_feat):
+        lib = _lib.load()
+        xyz_c, lvl_c, aabb, *factors = ctx.saved_tensors
+        planes, lines = factors[:3], factors[3:6]
+        with_mips = lvl_c is not None
+        vm = VMDesc(planes, lines, aabb, ctx.n_levels, build_mips=with_mips)
+        g, gp, gl, gpm, glm = vm.new_grads(with_mips)
+        gf = _f32c(g_feat)
+        check(lib.tf_vm_feature_bwd(C.byref(vm.c), ptr(xyz_c), ptr(lvl_c), xyz_c.shape[0], ptr(gf), C.byref(g), stream_ptr()),
+              "tf_vm_feature_bwd")
+        d_planes, d_lines = vm.finish_grads(g, gp, gl, with_mips)
+        return (None, None, None, None, *d_planes, *d_lines)
+
+
+class NeusCompositeFunction(torch.autograd.Function):
+    """NeuS alpha + transmittance + per-ray accumulation (reference
+    network/shapeRenderer.py:1004-1024, 1166-1206).
+
+    inputs : sdf [N], grad [N,3], dists [N], dirs [R,3], ray_offsets int32 [R+1],
+             variance (0-d), cos_anneal (float), vals [N,D], train_variance (bool)
+    outputs: alpha [N], weights [N], acc [R], out [R,D]
+    """
+
+    @staticmethod
+    def forward(ctx, sdf, grad, dists, dirs, ray_offsets, variance, cos_anneal, vals, train_variance=True):
+        lib = _lib.load()
+        sdf_c, grad_c, dists_c, dirs_c = _f32c(sdf), _f32c(grad), _f32c(dists), _f32c(dirs)
+        vals_c = _f32c(vals)
+        var_c = _f32c(variance.reshape(1))
+        offs = ray_offsets.contiguous()
+        assert offs.dtype == torch.int32
+        n, R = sdf_c.shape[0], dirs_c.shape[0]
+        D = 0 if vals_c is None else int(vals_c.shape[1])
+        dev = sdf_c.device
+        alpha = torch.empty(n, device=dev, dtype=torch.float32)
+        weights = torch.empty(n, device=dev, dtype=torch.float32)
+        acc = torch.empty(R, device=dev, dtype=torch.float32)
+        out = torch.empty(R, D, device=dev, dtype=torch.float32)
+        with _timed("neus_composite_fwd"):
+          check(lib.tf_neus_composite_fwd(ptr(sdf_c), ptr(grad_c), ptr(dists_c), ptr(dirs_c), ptr(offs), R, ptr(var_c),
+                                        float(cos_anneal), ptr(vals_c), D, ptr(alpha), ptr(weights), ptr(acc), ptr(out),
+                                        stream_ptr()), "tf_neus_composite_fwd")
+        ctx.save_for_backward(sdf_c, grad_c, dists_c, dirs_c, offs, var_c, vals_c, alpha, weights)
+        ctx.cos_anneal = float(cos_anneal)
+        ctx.train_variance = bool(train_variance)
+        ctx.var_shape = variance.shape
+        ctx.mark_non_differentiable(alpha)
+        return alpha, weights, acc, out
+
+    @staticmethod
+    def backward(ctx, _g_alpha, g_weights, g_acc, g_out):
+        lib = _lib.load()
+        sdf_c, grad_c, dists_c, dirs_c, offs, var_c, vals_c, alpha, weights = ctx.saved_tensors
+        n, R = sdf_c.shape[0], dirs_c.shape[0]
+        D = 0 if vals_c is None else int(vals_c.shape[1])
+        dev = sdf_c.device
+        d_sdf = torch.zeros(n, device=dev, dtype=torch.float32)
+        d_grad = torch.zeros(n, 3, device=dev, dtype=torch.float32)
+        d_vals = torch.zeros(n, D, device=dev, dtype=torch.float32) if D > 0 else None
+        d_var = torch.zeros(1, device=dev, dtype=torch.float32) if ctx.train_variance else None
+        with _timed("neus_composite_bwd"):
+          check(lib.tf_neus_composite_bwd(ptr(sdf_c), ptr(grad_c), ptr(dists_c), ptr(dirs_c), ptr(offs), R, ptr(var_c),
+                                        ctx.cos_anneal, ptr(vals_c), D, ptr(alpha), ptr(weights), ptr(_f32c(g_acc)),
+                                        ptr(_f32c(g_out)), ptr(_f32c(g_weights)), ptr(d_sdf), ptr(d_grad), ptr(d_vals),
+                                        ptr(d_var), stream_ptr()), "tf_neus_composite_bwd")
+        dv = None if d_var is None else d_var.reshape(ctx.var_shape)
+        return d_sdf, d_grad, None, None, None, dv, None, d_vals, None

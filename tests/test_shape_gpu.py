@@ -1,0 +1,238 @@
+"""GPU parity tests of the shape-stage kernels (through the C ABI) against the oracle.
+
+Tolerances follow BASELINE.json's north star: colour / SDF / alpha within 1e-4 relative,
+parameter gradients within 1e-3 relative, where relative error = max|a-b| / max|b|
+(conftest.rel_err).  The fp64 oracle is the arbiter; finite-difference outputs
+(normals, hessian) are ill-conditioned in fp32 (division by units ~ 1/G), so for those the
+bar is "no worse than a small multiple of the fp32 oracle's own error against fp64".
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+from oracle import torch_oracle as O  # noqa: E402
+
+
+def _cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def close_as_fp32(got, o64, o32, tol, what, slack=4.0):
+    e_got = rel_err(got, o64)
+    e_ref = rel_err(o32, o64)
+    assert e_got <= max(tol, slack * e_ref), f"{what}: rel err {e_got:.3e} (fp32 oracle {e_ref:.3e}, tol {tol:.1e})"
+    return e_got
+
+
+def make_fields(C, H, A, G0, ups, seed=0, noise=0.05):
+    """Oracle fp32 / fp64 TensoSDF and the CUDA module with identical parameters."""
+    from tensoflow_b200.fields import TensoSDF
+    from tensoflow_b200 import synthetic
+    dev = _cuda()
+    torch.manual_seed(seed)
+    aabb = [[-1.0, -1.0, -1.0], [1.0, 1.0, 1.0]]
+    o32 = O.TensoSDF([G0] * 3, aabb, sdf_n_comp=C, sdf_dim=H, app_dim=A, init_n_levels=1)
+    for r in ups:
+        o32.upsample_volume_grid(torch.tensor([r] * 3))
+    synthetic.perturb_field(o32, seed=seed + 1, noise=noise)
+    with torch.no_grad():   # move the hidden pre-activations off the softplus linear branch
+        o32.sdf_mat[0].weight.mul_(0.05)
+        o32.sdf_mat[0].bias.add_(0.01 * torch.randn_like(o32.sdf_mat[0].bias))
+        o32.sdf_mat[2].weight[1:].add_(0.1 * torch.randn_like(o32.sdf_mat[2].weight[1:]))
+    o64 = O.TensoSDF([G0] * 3, aabb, sdf_n_comp=C, sdf_dim=H, app_dim=A, init_n_levels=1, dtype=torch.float64)
+    for r in ups:
+        o64.upsample_volume_grid(torch.tensor([r] * 3))
+    synthetic.copy_field_params(o32, o64)
+    cu = TensoSDF(torch.tensor([G0] * 3), torch.tensor(aabb), device=dev, sdf_n_comp=C, sdf_dim=H, app_dim=A,
+                  init_n_levels=1, sdf_multires=0)
+    for r in ups:
+        cu.upsample_volume_grid(torch.tensor([r] * 3))
+    synthetic.copy_field_params(o32, cu)
+    assert cu.n_levels == o32.n_levels and list(cu.gridSize) == list(o32.gridSize)
+    return o32, o64, cu
+
+
+def points(n, seed, with_level, n_levels):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(n, 3, generator=g) * 2.1 - 1.05          # a few points outside the aabb (clamp)
+    lv = (torch.rand(n, 1, generator=g) * (n_levels + 1.5) - 1.0) if with_level else None
+    return x, lv
+
+
+CONFIGS = [
+    # C,  H,   A,  G0, ups,        N
+    (8, 32, 16, 16, [32, 64], 1003),      # small, 3 mip levels, ragged tile
+    (16, 128, 128, 128, [], 4099),         # BASELINE config 1 dims (128^3, 48 comps), L=1
+    (36, 256, 128, 16, [32, 64], 2050),    # BASELINE config 2 dims on a small grid, L=3
+]
+
+
+@pytest.mark.parametrize("C,H,A,G0,ups,N", CONFIGS)
+@pytest.mark.parametrize("with_level", [True, False])
+def test_vm_feature(C, H, A, G0, ups, N, with_level):
+    from tensoflow_b200 import ops
+    o32, o64, cu = make_fields(C, H, A, G0, ups)
+    dev = _cuda()
+    x, lv = points(N, 3, with_level, o32.n_levels)
+    f64 = O.vm_feature(o64.sdf_plane, o64.sdf_line, x.double(), None if lv is None else lv.double(), o64.aabb, o64.n_levels)
+    f32 = O.vm_feature(o32.sdf_plane, o32.sdf_line, x, lv, o32.aabb, o32.n_levels)
+    got = ops.VMFeatureFunction.apply(x.to(dev), None if lv is None else lv.to(dev), cu.aabb, cu.n_levels,
+                                      *cu.sdf_plane, *cu.sdf_line)
+    close_as_fp32(got, f64, f32, 1e-5, "vm feature")
+    gup = torch.randn(N, 3 * C, generator=torch.Generator().manual_seed(5))
+    (f64 * gup.double()).sum().backward()
+    (got * gup.to(dev)).sum().backward()
+    for name in ("sdf_plane", "sdf_line"):
+        for i in range(3):
+            e = rel_err(getattr(cu, name)[i].grad, getattr(o64, name)[i].grad)
+            assert e < 1e-4, f"{name}[{i}] grad rel err {e:.3e}"
+
+
+@pytest.mark.parametrize("C,H,A,G0,ups,N", CONFIGS)
+@pytest.mark.parametrize("with_level", [True, False])
+def test_stencil_forward(C, H, A, G0, ups, N, with_level):
+    o32, o64, cu = make_fields(C, H, A, G0, ups)
+    dev = _cuda()
+    x, lv = points(N, 7, with_level, o32.n_levels)
+    with torch.no_grad():
+        r64 = o64(x.double(), None if lv is None else lv.double())
+        g64, h64 = o64.gradient(x.double(), None if lv is None else lv.double(), training=True, sdf=r64[:, :1])
+        r32 = o32(x, lv)
+        g32, h32 = o32.gradient(x, lv, training=True, sdf=r32[:, :1])
+        sdf, feat, grad, hess = cu.stencil(x.to(dev), None if lv is None else lv.to(dev))
+        only = cu.sdf(x.to(dev), None if lv is None else lv.to(dev))
+        full = cu(x.to(dev), None if lv is None else lv.to(dev))
+    close_as_fp32(sdf, r64[:, 0], r32[:, 0], 1e-5, "sdf")
+    close_as_fp32(only[:, 0], r64[:, 0], r32[:, 0], 1e-5, "sdf (sdf-only kernel)")
+    close_as_fp32(feat, r64[:, 1:], r32[:, 1:], 1e-5, "appearance features")
+    close_as_fp32(full, r64, r32, 1e-5, "TensoSDF.forward")
+    close_as_fp32(grad, g64, g32, 1e-4, "FD gradient")
+    close_as_fp32(hess, h64, h32, 1e-4, "normal hessian")
+
+
+@pytest.mark.parametrize("C,H,A,G0,ups,N", CONFIGS)
+@pytest.mark.parametrize("with_level", [True, False])
+def test_stencil_backward(C, H, A, G0, ups, N, with_level, monkeypatch):
+    from tensoflow_b200 import ops
+    o32, o64, cu = make_fields(C, H, A, G0, ups)
+    dev = _cuda()
+    if N > 2000:   # force the sliced-workspace path
+        monkeypatch.setattr(ops, "BWD_WORKSPACE_BYTES", 48 << 20)
+    x, lv = points(N, 11, with_level, o32.n_levels)
+    g = torch.Generator().manual_seed(13)
+    u_sdf, u_feat = torch.randn(N, generator=g), torch.randn(N, A, generator=g)
+    u_grad, u_hess = torch.randn(N, 3, generator=g), torch.randn(N, generator=g) * 1e-2
+
+    def oracle_loss(f, dt):
+        r = f(x.to(dt), None if lv is None else lv.to(dt))
+        gr, he = f.gradient(x.to(dt), None if lv is None else lv.to(dt), training=True, sdf=r[:, :1])
+        return (r[:, 0] * u_sdf.to(dt)).sum() + (r[:, 1:] * u_feat.to(dt)).sum() + (gr * u_grad.to(dt)).sum() + (he * u_hess.to(dt)).sum()
+
+    oracle_loss(o64, torch.float64).backward()
+    oracle_loss(o32, torch.float32).backward()
+    sdf, feat, grad, hess = cu.stencil(x.to(dev), None if lv is None else lv.to(dev))
+    ((sdf * u_sdf.to(dev)).sum() + (feat * u_feat.to(dev)).sum() + (grad * u_grad.to(dev)).sum() + (hess * u_hess.to(dev)).sum()).backward()
+    for (name, p64), (_, p32), (_, pc) in zip(o64.named_parameters(), o32.named_parameters(), cu.named_parameters()):
+        assert pc.grad is not None, name
+        close_as_fp32(pc.grad, p64.grad, p32.grad, 1e-3, f"d {name}")
+
+
+def _composite_inputs(n_rays, max_s, seed):
+    g = torch.Generator().manual_seed(seed)
+    counts = torch.randint(0, max_s + 1, (n_rays,), generator=g)
+    counts[0] = 0
+    counts[-1] = max_s
+    idx = torch.repeat_interleave(torch.arange(n_rays), counts)
+    n = int(counts.sum())
+    sdf = torch.randn(n, generator=g) * 0.05
+    grad = F.normalize(torch.randn(n, 3, generator=g), dim=-1) * (1 + 0.1 * torch.randn(n, 1, generator=g))
+    dists = torch.rand(n, generator=g) * 0.02 + 0.002
+    dirs = F.normalize(torch.randn(n_rays, 3, generator=g), dim=-1)
+    vals = torch.rand(n, 7, generator=g)
+    return idx, sdf, grad, dists, dirs, vals
+
+
+@pytest.mark.parametrize("cos_anneal", [0.0, 0.4, 1.0])
+def test_neus_composite(cos_anneal):
+    from tensoflow_b200 import ops
+    from tensoflow_b200.shape_renderer import ray_offsets_from_indices
+    dev = _cuda()
+    n_rays = 333
+    idx, sdf, grad, dists, dirs, vals = _composite_inputs(n_rays, 100, 21)
+    g = torch.Generator().manual_seed(22)
+    u_acc, u_out = torch.randn(n_rays, generator=g), torch.randn(n_rays, 7, generator=g)
+    u_w = torch.randn(sdf.shape[0], generator=g) * 0.1
+
+    def run_oracle(dt):
+        s, gr, va = sdf.to(dt).requires_grad_(), grad.to(dt).requires_grad_(), vals.to(dt).requires_grad_()
+        var = torch.tensor(0.3, dtype=dt, requires_grad=True)
+        alpha, _ = O.neus_alpha(s, gr, dists.to(dt), dirs.to(dt)[idx], var, cos_anneal)
+        w, _ = O.render_weight_from_alpha(alpha, idx, n_rays)
+        acc = O.accumulate_along_rays(w, None, idx, n_rays)[:, 0]
+        out = O.accumulate_along_rays(w, va, idx, n_rays)
+        ((acc * u_acc.to(dt)).sum() + (out * u_out.to(dt)).sum() + (w * u_w.to(dt)).sum()).backward()
+        return alpha, w, acc, out, s.grad, gr.grad, va.grad, var.grad
+
+    r64, r32 = run_oracle(torch.float64), run_oracle(torch.float32)
+    s, gr, va = sdf.to(dev).requires_grad_(), grad.to(dev).requires_grad_(), vals.to(dev).requires_grad_()
+    var = torch.tensor(0.3, device=dev, requires_grad=True)
+    offs = ray_offsets_from_indices(idx.to(dev), n_rays)
+    alpha, w, acc, out = ops.NeusCompositeFunction.apply(s, gr, dists.to(dev), dirs.to(dev), offs, var, cos_anneal, va, True)
+    ((acc * u_acc.to(dev)).sum() + (out * u_out.to(dev)).sum() + (w * u_w.to(dev)).sum()).backward()
+    got = (alpha, w, acc, out, s.grad, gr.grad, va.grad, var.grad)
+    names = ("alpha", "weights", "acc", "out", "d sdf", "d grad", "d vals", "d variance")
+    tols = (1e-4, 1e-4, 1e-4, 1e-4, 1e-3, 1e-3, 1e-3, 1e-3)
+    for a, b64, b32, nm, tol in zip(got, r64, r32, names, tols):
+        close_as_fp32(a, b64, b32, tol, nm)
+
+
+def test_neus_composite_empty():
+    from tensoflow_b200 import ops
+    dev = _cuda()
+    z = torch.zeros(0, device=dev)
+    offs = torch.zeros(5, dtype=torch.int32, device=dev)
+    alpha, w, acc, out = ops.NeusCompositeFunction.apply(z, torch.zeros(0, 3, device=dev), z, torch.ones(4, 3, device=dev), offs,
+                                                         torch.tensor(0.3, device=dev), 1.0, torch.zeros(0, 6, device=dev), True)
+    assert acc.shape == (4,) and float(acc.abs().sum()) == 0.0 and float(out.abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("C,H,A,G0,ups,R,S", [(16, 128, 128, 128, [], 256, 64), (36, 256, 128, 32, [64, 128], 128, 48)])
+def test_render_core_end_to_end(C, H, A, G0, ups, R, S):
+    """field -> alpha -> composite -> charbonnier + 0.1 eikonal, fwd + bwd, vs the oracle."""
+    from tensoflow_b200 import synthetic
+    from tensoflow_b200.shape_renderer import render_core, charbonnier
+    o32, o64, cu = make_fields(C, H, A, G0, ups, noise=0.01)
+    dev = _cuda()
+    rays = synthetic.make_rays(R, seed=0)
+    t0, t1, idx = synthetic.uniform_samples(rays["rays_o"], rays["dirs"], o32.aabb, S)
+
+    def run_oracle(f, dt):
+        var = torch.tensor(0.3, dtype=dt, requires_grad=True)
+        r = O.shape_render_core(f, var, rays["rays_o"].to(dt), rays["dirs"].to(dt), rays["radiis"].to(dt), rays["rays_cos"].to(dt),
+                                t0.to(dt), t1.to(dt), idx, synthetic.simple_color_fn, cos_anneal_ratio=0.7)
+        loss = O.charbonnier(r["ray_rgb"], rays["rgbs"].to(dt)).mean() + 0.1 * r["gradient_error"].mean() \
+            + 0.01 * r["loss_sparse"] + 1e-4 * r["loss_hessian"]
+        loss.backward()
+        return r, loss, var
+
+    r64, l64, v64 = run_oracle(o64, torch.float64)
+    r32, l32, v32 = run_oracle(o32, torch.float32)
+    var = torch.tensor(0.3, device=dev, requires_grad=True)
+    rc = render_core(cu, var, synthetic.simple_color_fn, rays["rays_o"].to(dev), rays["dirs"].to(dev), rays["radiis"].to(dev),
+                     rays["rays_cos"].to(dev), t0.to(dev), t1.to(dev), idx.to(dev), cos_anneal_ratio=0.7)
+    loss = charbonnier(rc["ray_rgb"], rays["rgbs"].to(dev)).mean() + 0.1 * rc["gradient_error"].mean() \
+        + 0.01 * rc["loss_sparse"] + 1e-4 * rc["loss_hessian"]
+    loss.backward()
+    for k in ("ray_rgb", "acc", "sdf", "alpha", "weights"):
+        close_as_fp32(rc[k], r64[k], r32[k], 1e-4, k)
+    close_as_fp32(rc["normal"], r64["normal"], r32["normal"], 1e-4, "normal")
+    close_as_fp32(loss, l64, l32, 1e-4, "loss")
+    close_as_fp32(var.grad, v64.grad, v32.grad, 1e-3, "d variance")
+    for (name, p64), (_, p32), (_, pc) in zip(o64.named_parameters(), o32.named_parameters(), cu.named_parameters()):
+        close_as_fp32(pc.grad, p64.grad, p32.grad, 1e-3, f"d {name}")
