@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""Benchmark of the TensoFlow hot path on B200 (see the contract in DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload shape|material]
+
+Default workload = BASELINE.json configs[1]: shape stage, VM field 512^3 (C=36, H=256,
+A=128, 3 mip levels), 8192-ray batch x 512 samples, forward + backward
+(field stencil -> NeuS alpha -> compositing -> charbonnier + eikonal loss).
+One "step" = one such pass over one synthetic ray batch.  Under torchrun every rank runs
+its own 8192-ray batch (weak scaling) and the VM-factor / MLP gradients are summed with one
+flat-bucket NCCL allreduce inside the timed region.
+
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+SHAPE_CFG = dict(G=512, C=36, H=256, A=128, L=3, rays=8192, samples=512)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf=d["bf16_tflops_sustained"], tf_burst=d["bf16_tflops"], src="measured")
+    return dict(hbm=6650.0, tf=1400.0, tf_burst=1590.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(index), "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def shape_algorithmic(cfg, n_samples, n_rays):
+    """algorithmic bytes and decoder FLOPs of one shape-stage step."""
+    C, H, A, G, L = cfg["C"], cfg["H"], cfg["A"], cfg["G"], cfg["L"]
+    K = 3 * C + 3
+    p_vm = 3 * C * 4 * sum((G >> l) ** 2 + (G >> l) for l in range(L))
+    by = n_samples * 1128 + n_rays * 120 + 3 * p_vm
+    fwd_flops = n_samples * (2 * (K * H + H * (1 + A)) + 6 * 2 * (K * H + H))
+    return by, fwd_flops
+
+
+def build_shape(cfg, device, seed=0):
+    from tensoflow_b200.fields import TensoSDF
+    from tensoflow_b200 import synthetic
+    torch.manual_seed(6033)   # reference trainer seed (train/trainer_inv.py:42)
+    aabb = torch.tensor([[-1.0] * 3, [1.0] * 3])
+    G0 = cfg["G"] >> (cfg["L"] - 1)
+    field = TensoSDF(torch.tensor([G0] * 3), aabb, device=device, sdf_n_comp=cfg["C"], sdf_dim=cfg["H"], app_dim=cfg["A"],
+                     init_n_levels=1, sdf_multires=0)
+    for l in range(1, cfg["L"]):   # bilinear upsampling exactly as the reference schedule does
+        field.upsample_volume_grid(torch.tensor([G0 << l] * 3))
+    synthetic.perturb_field(field, seed=seed + 1, noise=1e-2)
+    variance = torch.nn.Parameter(torch.tensor(0.3, device=device))
+    return field, variance
+
+
+def shape_step(field, variance, rays, cfg, loss_scale=1.0):
+    """fwd + bwd of the shape-stage hot path on one ray batch (already on the device)."""
+    from tensoflow_b200 import synthetic
+    from tensoflow_b200.shape_renderer import render_core, charbonnier
+    t0, t1, idx = synthetic.uniform_samples(rays["rays_o"], rays["dirs"], field.aabb, cfg["samples"])
+    out = render_core(field, variance, synthetic.simple_color_fn, rays["rays_o"], rays["dirs"], rays["radiis"], rays["rays_cos"],
+                      t0, t1, idx, cos_anneal_ratio=1.0)
+    loss = charbonnier(out["ray_rgb"], rays["rgbs"]).mean() + 0.1 * out["gradient_error"].mean()
+    (loss * loss_scale).backward()
+    return loss.detach(), int(idx.shape[0])
+
+
+def cpu_baseline_shape(cfg, n_rays, iters, threads):
+    """The oracle port of the reference path, timed on the host cores (fwd + bwd)."""
+    from oracle import torch_oracle as O
+    from tensoflow_b200 import synthetic
+    torch.set_num_threads(threads)
+    torch.manual_seed(6033)
+    aabb = [[-1.0] * 3, [1.0] * 3]
+    G0 = cfg["G"] >> (cfg["L"] - 1)
+    f = O.TensoSDF([G0] * 3, aabb, sdf_n_comp=cfg["C"], sdf_dim=cfg["H"], app_dim=cfg["A"], init_n_levels=1)
+    for l in range(1, cfg["L"]):
+        f.upsample_volume_grid(torch.tensor([G0 << l] * 3))
+    synthetic.perturb_field(f, seed=1, noise=1e-2)
+    var = torch.tensor(0.3, requires_grad=True)
+    rays = synthetic.make_rays(n_rays, seed=0)
+    times = []
+    for it in range(iters + 1):
+        t = time.perf_counter()
+        t0, t1, idx = synthetic.uniform_samples(rays["rays_o"], rays["dirs"], f.aabb, cfg["samples"])
+        r = O.shape_render_core(f, var, rays["rays_o"], rays["dirs"], rays["radiis"], rays["rays_cos"], t0, t1, idx,
+                                synthetic.simple_color_fn, cos_anneal_ratio=1.0)
+        loss = O.charbonnier(r["ray_rgb"], rays["rgbs"]).mean() + 0.1 * r["gradient_error"].mean()
+        for p in f.parameters():
+            p.grad = None
+        loss.backward()
+        if it > 0:
+            times.append(time.perf_counter() - t)
+    return n_rays / statistics.median(times), times
+
+
+def workload_name(cfg):
+    return (f"shape stage: TensoSDF VM field {cfg['G']}^3 (C={cfg['C']}, H={cfg['H']}, A={cfg['A']}, {cfg['L']} mip levels), "
+            f"{cfg['rays']}-ray batch x {cfg['samples']} samples, fwd+bwd")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = dict(SHAPE_CFG)
+    threads = len(os.sched_getaffinity(0))
+    n_rays = args.ref_rays
+    from oracle import torch_oracle as O  # noqa: F401
+    t_all = time.perf_counter()
+    rps, times = cpu_baseline_shape(cfg, n_rays, max(1, args.steps + args.warmup - 1), threads)
+    times = times[max(0, args.warmup - 1):] or times
+    ms = 1e3 * statistics.median(times)
+    val = n_rays / (ms / 1e3)
+    line = {
+        "impl": "reference", "metric": "train rays/sec (fwd+bwd)", "value": val, "unit": "rays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(cfg), "sample": f"{n_rays} rays x {cfg['samples']} samples per step"},
+        "cpu_baseline": {"value": val, "unit": "rays/s", "cores": threads, "kind": "port",
+                         "sample": f"oracle/torch_oracle.py (PyTorch CPU restatement of the reference path), {n_rays} rays x "
+                                   f"{cfg['samples']} samples per step, median of {len(times)} steps"},
+        "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.perf_counter() - t_all,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from tensoflow_b200 import build as tb
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: tensoflow_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    if rank == 0:
+        tb.build()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()
+    from tensoflow_b200 import _lib, ops, synthetic
+    _lib.load()
+    cfg = dict(SHAPE_CFG)
+    if args.rays:
+        cfg["rays"] = args.rays
+    if args.samples:
+        cfg["samples"] = args.samples
+    field, variance = build_shape(cfg, dev)
+    params = list(field.parameters()) + [variance]
+    # rank-specific synthetic ray batches in pinned host memory (the reference keeps its rays on the CPU too,
+    # network/shapeRenderer.py:780)
+    n_batches = 4
+    host = [{k: v.pin_memory() for k, v in synthetic.make_rays(cfg["rays"], seed=1000 * rank + b).items()} for b in range(n_batches)]
+    h2d = sum(v.numel() * v.element_size() for v in host[0].values())
+    flat = None
+    if world > 1:
+        flat = torch.zeros(sum(p.numel() for p in params), device=dev)
+
+    def zero_grads():
+        for p in params:
+            p.grad = None
+
+    def allreduce_grads():
+        if world == 1:
+            return
+        off = 0
+        views = []
+        for p in params:
+            g = p.grad
+            v = g.permute(0, 2, 3, 1).reshape(-1) if g.dim() == 4 else g.reshape(-1)
+            flat[off:off + v.numel()].copy_(v)
+            views.append((p, off, v.numel()))
+            off += v.numel()
+        dist.all_reduce(flat)
+
+    def step_device(b):
+        rays = {k: v.to(dev, non_blocking=True) for k, v in host[b % n_batches].items()}
+        return rays
+
+    resident = [{k: v.to(dev) for k, v in h.items()} for h in host]
+    n_samples = 0
+    # ---- warm-up ----
+    for i in range(max(args.warmup, 3)):
+        zero_grads()
+        _, n_samples = shape_step(field, variance, resident[i % n_batches], cfg, 1.0 / world)
+        allreduce_grads()
+    torch.cuda.synchronize()
+
+    def timed(run_step, timers):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ops.KernelTimers.reset(timers)
+        l0 = _lib.launch_count()
+        sampler = ClockSampler(local) if rank == 0 else None
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(args.steps):
+            run_step(i)
+        b.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = a.elapsed_time(b)
+        clocks = sampler.stop() if sampler else None
+        launches = _lib.launch_count() - l0
+        tot = ops.KernelTimers.totals_ms()
+        ops.KernelTimers.reset(False)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms, clocks, launches, tot
+
+    # ---- device-resident timing (value) ----
+    def step_resident(i):
+        zero_grads()
+        shape_step(field, variance, resident[i % n_batches], cfg, 1.0 / world)
+        allreduce_grads()
+
+    ms, clocks, launches, ktimes = timed(step_resident, True)
+
+    # ---- end-to-end timing: pinned host rays -> H2D -> step -> D2H loss ----
+    losses = []
+
+    def step_e2e(i):
+        zero_grads()
+        rays = step_device(i)
+        loss, _ = shape_step(field, variance, rays, cfg, 1.0 / world)
+        allreduce_grads()
+        losses.append(float(loss.cpu()))   # D2H read of the step's result
+
+    ms_e2e, _, _, _ = timed(step_e2e, False)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    rays_total = cfg["rays"] * world
+    value = rays_total * args.steps / (ms / 1e3)
+    e2e = rays_total * args.steps / (ms_e2e / 1e3)
+    by, fwd_flops = shape_algorithmic(cfg, n_samples, cfg["rays"])
+    # dominant kernel = the fused stencil (fwd: 1x, bwd: 2x the minimal decoder FLOPs)
+    kt = {k: v[0] / max(v[1], 1) for k, v in ktimes.items()}
+    dom = max(kt, key=kt.get) if kt else None
+    roof = None
+    if dom is not None:
+        flops = fwd_flops * (2 if dom.endswith("bwd") else 1) if "stencil" in dom else 0
+        ach = flops / (kt[dom] / 1e3) / 1e12
+        roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": pk["tf"], "unit": "TFLOP/s", "frac": ach / pk["tf"],
+                "traffic": None, "peak_source": f"{pk['src']} bf16 sustained", "ms_per_launch": kt[dom],
+                "share_of_step": kt[dom] * ktimes[dom][1] / ms,
+                "note": "algorithmic decoder FLOPs (fp32-exact; v1 runs them as FFMA, not yet tcgen05)",
+                "calls_ms": {k: round(v, 3) for k, v in kt.items()},
+                "hbm_algorithmic": {"bytes_per_step": by, "GBps_at_step_rate": by / (ms / args.steps / 1e3) / 1e9,
+                                    "frac_of_hbm_peak": by / (ms / args.steps / 1e3) / 1e9 / pk["hbm"]}}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = len(os.sched_getaffinity(0))
+        rps, times = cpu_baseline_shape(cfg, args.ref_rays, 2, threads)
+        cpu = {"value": rps, "unit": "rays/s", "cores": threads, "kind": "port",
+               "sample": f"oracle port, {args.ref_rays} of {cfg['rays']} rays x {cfg['samples']} samples, fwd+bwd, median of {len(times)}"}
+    line = {
+        "metric": "train rays/sec (fwd+bwd)", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(cfg), "samples_per_step_per_gpu": n_samples,
+                   "colour": "synthetic.simple_color_fn (shading network not in this workload)",
+                   "l2": "working set per step (>= 2 GB of per-sample tensors) exceeds the 126 MB L2; no explicit flush",
+                   "parallelism": f"dp{world} (ray sharding + flat fp32 gradient allreduce)" if world > 1 else "single GPU"},
+        "roofline": roof, "cpu_baseline": cpu,
+        "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches, "clocks": clocks, "loss": losses[-1] if losses else None,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rays", type=int, default=0, help="override rays per GPU per step (parity/debug only)")
+    ap.add_argument("--samples", type=int, default=0, help="override samples per ray (parity/debug only)")
+    ap.add_argument("--ref-rays", type=int, default=32, help="rays per CPU-baseline step (bounded sample)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

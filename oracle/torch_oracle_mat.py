@@ -209,3 +209,206 @@ def specular_cubemap(cubemap: torch.Tensor, roughness: float, cutoff: float = 0.
         w = torch.where(LdV >= cos_cut, w, torch.zeros_like(w))
         outs.append((w @ flat) / w.sum(-1, keepdim=True))
     return torch.cat(outs, 0).reshape(cubemap.shape)
+
+
+# --------------------------------------------------------------------------
+# TensoFlow sampler (network/flow.py): prior, piecewise-quadratic coupling, VM feature
+# --------------------------------------------------------------------------
+from . import torch_oracle as _O  # noqa: E402
+import torch.nn as nn  # noqa: E402
+
+
+def sphere_prior_angles(num_samples: int, dtype=torch.float32) -> torch.Tensor:
+    """SphereSampler.set_angle (network/flow.py:62-76): the last `num_samples` points of a
+    Fibonacci sphere above 1 degree elevation, as (phi/2pi, theta/(pi/2)); built in float32
+    like the reference, then cast."""
+    ratio = (1 + 90) / 180
+    num_points = int(num_samples // (1 - ratio))
+    g = (np.sqrt(5) - 1.0) / 2.0
+    phis, thetas = [], []
+    for n in range(num_points - num_samples, num_points):
+        z = 2.0 * n / num_points - 1.0
+        phis.append(2 * np.pi * n * g % (2 * np.pi))
+        thetas.append(np.arcsin(z))
+    phi = torch.tensor(phis, dtype=torch.float32) / (2 * np.pi)
+    theta = torch.tensor(thetas, dtype=torch.float32) / (0.5 * np.pi)
+    return torch.stack([phi, theta], -1).to(dtype)
+
+
+def sphere_prior_sample(pn: int, sn: int, phi_shift: Optional[torch.Tensor], dtype=torch.float32, device="cpu"):
+    """SphereSampler.forward (flow.py:82-90).  phi_shift [pn,sn,1] stands for the
+    torch.rand_like draw of training mode (None = eval)."""
+    x = sphere_prior_angles(sn, dtype).to(device).expand(pn, sn, 2)
+    if phi_shift is not None:
+        x = torch.cat([(x[..., :1] + phi_shift) % 1, x[..., 1:]], -1)
+    x = x.clamp(1e-6, 1 - 1e-6)
+    logj = -torch.cos(x[..., 1:] * (0.5 * np.pi)).log()
+    return x, logj
+
+
+def _pwq_common(wv_tilde: torch.Tensor, clamp_w: bool):
+    """wv_tilde [N,21] -> w [N,10], wsum [N,10], wsum_shift [N,11], v [N,11], vw [N,11]."""
+    nv = int(np.ceil(wv_tilde.shape[-1] / 2))
+    v_t, w_t = wv_tilde[:, :nv], wv_tilde[:, nv:]
+    w = torch.exp(w_t)
+    if clamp_w:
+        w = w.clamp_min(1e-6)                                              # flow.py:343
+    wsum = torch.cumsum(w, -1)
+    wn = wsum[:, -1:]
+    w = w / wn
+    if clamp_w:
+        w = w.clamp_min(1e-6)                                              # flow.py:346
+    wsum = wsum / wn
+    wsum_shift = torch.cat([torch.zeros_like(wsum[:, :1]), wsum], -1)
+    v = torch.exp(v_t)
+    v = (v / ((v[:, :-1] + v[:, 1:]) / 2 * w).sum(-1, keepdim=True)).clamp_min(1e-6)   # flow.py:166-168,350
+    vw = torch.cat([torch.zeros_like(wsum[:, :1]), torch.cumsum((v[:, :-1] + v[:, 1:]) / 2 * w, -1)], -1)
+    return w, wsum, wsum_shift, v, vw
+
+
+def pwquad_forward(x: torch.Tensor, wv_tilde: torch.Tensor):
+    """ElementWisePWQuadraticTransform.flow_inv (flow.py:332-413) for one coordinate:
+    x [N] in (0,1) -> (out [N], logj [N]); used for density evaluation."""
+    w, wsum, wsum_shift, v, vw = _pwq_common(wv_tilde, True)
+    b = w.shape[-1]
+    eps = torch.finfo(wsum.dtype).eps
+    finder = torch.where(wsum > x[:, None], torch.zeros_like(wsum), torch.ones_like(wsum))
+    mx = torch.argmax(torch.cat([torch.full_like(wsum[:, :1], eps), finder * wsum], -1), -1).clamp(0, b - 1)[:, None]
+    wb, vb, vb1 = w.gather(-1, mx)[:, 0], v.gather(-1, mx)[:, 0], v.gather(-1, mx + 1)[:, 0]
+    alphas = ((x - wsum_shift.gather(-1, mx)[:, 0]) / wb).clamp(0, 1)
+    out = alphas ** 2 / 2 * ((vb1 - vb) * wb) + alphas * vb * wb + vw.gather(-1, mx)[:, 0]
+    out = out.clamp(min=eps, max=1.0 - eps)
+    logj = torch.log(torch.lerp(vb, vb1, alphas))
+    return out, logj
+
+
+def pwquad_inverse(y: torch.Tensor, wv_tilde: torch.Tensor):
+    """ElementWisePWQuadraticTransform.flow (flow.py:415-525): y [N] -> (x [N], logj [N]);
+    used for sampling."""
+    w, wsum, wsum_shift, v, vw = _pwq_common(wv_tilde, False)
+    b = w.shape[-1]
+    eps = torch.finfo(vw.dtype).eps
+    finder = torch.where(vw > y[:, None], torch.zeros_like(vw), torch.ones_like(vw))
+    mx = torch.argmax(torch.cat([torch.full_like(vw[:, :1], eps), finder * (vw + 1)], -1), -1) - 1
+    e = mx.clamp(0, b - 1)[:, None]
+    wb, vb, vb1 = w.gather(-1, e)[:, 0], v.gather(-1, e)[:, 0], v.gather(-1, e + 1)[:, 0]
+    a = (vb1 - vb) * wb
+    bb = vb * wb
+    c = vw.gather(-1, e)[:, 0] - y
+    a = torch.where(a.abs() < eps, eps * torch.ones_like(a), a)
+    d = (bb ** 2 - 2 * a * c).clamp_min(0)
+    sol1 = (-bb - torch.sqrt(d)) / a
+    sol2 = (-bb + torch.sqrt(d)) / a
+    sol = torch.where((sol1 >= 0) & (sol1 < 1), sol1, sol2).clamp(min=eps, max=1.0 - eps)
+    x = (wb * sol + wsum_shift.gather(-1, e)[:, 0]).clamp(min=eps, max=1.0 - eps)
+    logj = -torch.log(torch.lerp(vb, vb1, sol))
+    return x, logj
+
+
+class FlowBlock(nn.Module):
+    """network/flow.py:549-641 (Block) with the pwquad defaults: PE(y_n) (7) + feature (37)
+    -> Reshift -> 3x(Linear 64 + LeakyReLU) -> Linear 21 -> spline on the other coordinate.
+    Parameter names match the reference (`nn.1`, `nn.3`, `nn.5`, `nn.7`; `nn.0` = Reshift)."""
+
+    class Reshift(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.scale = nn.Parameter(torch.scalar_tensor(2.0), requires_grad=False)
+            self.offset = nn.Parameter(torch.scalar_tensor(-1.0), requires_grad=False)
+
+        def forward(self, x):
+            return x * self.scale + self.offset
+
+    def __init__(self, cond_index: int, feature_dim: int = 37, d_hidden: int = 64, n_bins: int = 21, multires: int = 3):
+        super().__init__()
+        self.cond = cond_index                 # coordinate that conditions (mask == True)
+        self.embed, d_in = _O.get_embedder(multires, 1)
+        layers = [FlowBlock.Reshift()]
+        last = d_in + feature_dim
+        for _ in range(3):
+            layers += [nn.Linear(last, d_hidden), nn.LeakyReLU()]
+            last = d_hidden
+        layers.append(nn.Linear(last, n_bins))
+        self.nn = nn.Sequential(*layers)
+
+    def _st(self, y, feature):
+        y_n = y[:, self.cond:self.cond + 1]
+        return self.nn(torch.cat([self.embed(y_n), feature], -1))
+
+    def flow(self, y, logj, feature):           # sampling direction (flow.py:600-616)
+        st = self._st(y, feature)
+        t = 1 - self.cond
+        xt, lj = pwquad_inverse(y[:, t], st)
+        x = torch.zeros_like(y)
+        x[:, self.cond] = y[:, self.cond]
+        x[:, t] = xt
+        return x, logj + lj[:, None]
+
+    def flow_inv(self, y, logj, feature):       # density direction (flow.py:623-641)
+        st = self._st(y, feature)
+        t = 1 - self.cond
+        xt, lj = pwquad_forward(y[:, t], st)
+        x = torch.zeros_like(y)
+        x[:, self.cond] = y[:, self.cond]
+        x[:, t] = xt
+        return x, logj + lj[:, None]
+
+
+class TensoFlow(nn.Module):
+    """network/flow.py:643-855 with flow='pwquad' (every shipped config)."""
+
+    def __init__(self, aabb, gridSize=(512, 512, 512), nis_n_comp=12, nis_dim=64, nis_feature_dim=16, dtype=torch.float32):
+        super().__init__()
+        self.register_buffer("aabb", torch.as_tensor(aabb, dtype=dtype).clone())
+        self.gridSize = [int(g) for g in gridSize]
+        self.n_levels = 3
+        planes, lines = [], []
+        for i in range(3):                                                    # flow.py:755-764
+            m0, m1 = _O.MAT_MODE[i]
+            planes.append(nn.Parameter(1e-4 * (2 * torch.rand(1, nis_n_comp, self.gridSize[m0], self.gridSize[m1], dtype=dtype) - 1)))
+            lines.append(nn.Parameter(torch.full((1, nis_n_comp, self.gridSize[_O.VEC_MODE[i]], 1), 1.0 / (nis_n_comp * 3), dtype=dtype)))
+        self.nis_plane = nn.ParameterList(planes)
+        self.nis_line = nn.ParameterList(lines)
+        self.embed_xyz, xyz_ch = _O.get_embedder(3, 3)
+        self.nis_mat = nn.Sequential(nn.Linear(3 * nis_n_comp + xyz_ch, nis_dim), nn.Softplus(beta=100),
+                                     nn.Linear(nis_dim, nis_feature_dim)).to(dtype)
+        self.embed_refl, refl_ch = _O.get_embedder(3, 2)
+        self.embed_rough, rough_ch = _O.get_embedder(3, 1)
+        fdim = nis_feature_dim + refl_ch + rough_ch
+        self.flows = nn.ModuleList([FlowBlock(0, fdim), FlowBlock(1, fdim)]).to(dtype)   # masks [T,F], [F,T]: flow.py:668-674
+
+    def tenso_feature(self, pts):                                             # flow.py:709-744
+        feat = _O.vm_feature(self.nis_plane, self.nis_line, pts, None, self.aabb, self.n_levels)
+        return self.nis_mat(torch.cat([feat, self.embed_xyz(pts)], -1))
+
+    def condition(self, pts, reflections, roughness):                         # flow.py:803-815 / 836-848
+        rough = torch.zeros_like(self.embed_rough(roughness))                 # computed then zeroed (flow.py:814,847)
+        return torch.cat([self.tenso_feature(pts), self.embed_refl(reflections), rough], -1)
+
+    def sample(self, pts, reflections, roughness, n_samples, phi_shift=None):
+        """flow.py:833-855 -> angles [pn,sn,2], logj [pn,sn,1] (= -log q)."""
+        pn = pts.shape[0]
+        x, logj = sphere_prior_sample(pn, n_samples, phi_shift, pts.dtype, pts.device)
+        feature = self.condition(pts, reflections, roughness)
+        feature = feature[:, None, :].expand(-1, n_samples, -1).reshape(pn * n_samples, -1)
+        x, logj = x.reshape(-1, 2), logj.reshape(-1, 1)
+        for f in self.flows:
+            x, logj = f.flow(x, logj, feature)
+        return x.reshape(pn, n_samples, 2), logj.reshape(pn, n_samples, 1)
+
+    def forward(self, pts, reflections, roughness, x, rays_id=None):
+        """flow.py:801-831 -> z, log q(x); x [pn,sn,2] or ragged [M,2] with rays_id."""
+        x = x.clamp(1e-6, 1 - 1e-6)
+        feature = self.condition(pts, reflections, roughness)
+        if rays_id is not None:
+            feature = feature[rays_id]
+        pre = x.shape[:-1]
+        if x.dim() == 3:
+            feature = feature[:, None, :].expand(-1, x.shape[1], -1)
+        x = x.reshape(-1, 2)
+        feature = feature.reshape(-1, feature.shape[-1])
+        logj = torch.zeros(x.shape[0], 1, dtype=x.dtype, device=x.device)
+        for f in list(self.flows)[::-1]:
+            x, logj = f.flow_inv(x, logj, feature)
+        logq = logj + torch.cos(x[:, 1:] * (0.5 * np.pi)).log()              # + prior log-prob (flow.py:78-80,825)
+        return x.reshape(*pre, 2), logq.reshape(*pre, 1)

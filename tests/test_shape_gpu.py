@@ -170,7 +170,7 @@ def test_neus_composite(cos_anneal):
     u_w = torch.randn(sdf.shape[0], generator=g) * 0.1
 
     def run_oracle(dt):
-        s, gr, va = sdf.to(dt).requires_grad_(), grad.to(dt).requires_grad_(), vals.to(dt).requires_grad_()
+        s, gr, va = (t.detach().clone().to(dt).requires_grad_() for t in (sdf, grad, vals))
         var = torch.tensor(0.3, dtype=dt, requires_grad=True)
         alpha, _ = O.neus_alpha(s, gr, dists.to(dt), dirs.to(dt)[idx], var, cos_anneal)
         w, _ = O.render_weight_from_alpha(alpha, idx, n_rays)
@@ -180,7 +180,7 @@ def test_neus_composite(cos_anneal):
         return alpha, w, acc, out, s.grad, gr.grad, va.grad, var.grad
 
     r64, r32 = run_oracle(torch.float64), run_oracle(torch.float32)
-    s, gr, va = sdf.to(dev).requires_grad_(), grad.to(dev).requires_grad_(), vals.to(dev).requires_grad_()
+    s, gr, va = (t.detach().clone().to(dev).requires_grad_() for t in (sdf, grad, vals))
     var = torch.tensor(0.3, device=dev, requires_grad=True)
     offs = ray_offsets_from_indices(idx.to(dev), n_rays)
     alpha, w, acc, out = ops.NeusCompositeFunction.apply(s, gr, dists.to(dev), dirs.to(dev), offs, var, cos_anneal, va, True)
