@@ -147,6 +147,34 @@ TF_API int tf_neus_composite_bwd(const float* sdf, const float* grad, const floa
                           const float* g_out, const float* g_weights, float* d_sdf,
                           float* d_grad, float* d_vals, float* d_variance, tf_stream_t stream);
 
+/* ---- small MLP layers (tall-skinny fused linear) -------------------------------
+ * Y[M,N] = act(X[M,K] W[N,K]^T + b[N]) -- one nn.Linear + activation of the reference's
+ * predictor stacks (network/other_field.py:20-121), coupling-layer conditioners
+ * (network/flow.py:577-598) and TensoFlow.nis_mat (network/flow.py:694-697).
+ * act: 0 none, 1 ReLU, 2 LeakyReLU(0.01), 3 Softplus(beta=100), 4 Sigmoid,
+ *      5 exp(min(x, act_param)) (ExpActivation, network/other_field.py:12-18).
+ * Row-major contiguous X, W, Y.  b may be NULL. */
+TF_API int tf_linear_fwd(const float* X, const float* W, const float* b, int64_t M, int32_t K,
+                         int32_t N, int32_t act, float act_param, float* Y, tf_stream_t stream);
+/* dpre[M,N] = dY * act'(Y) (written; must not alias dY); dX[M,K] = dpre W (dX may be NULL);
+ * dW[N,K] += dpre^T X and db[N] += colsum(dpre) (each may be NULL). */
+TF_API int tf_linear_bwd(const float* X, const float* W, const float* Y, const float* dY,
+                         float* dpre, int64_t M, int32_t K, int32_t N, int32_t act,
+                         float act_param, float* dX, float* dW, float* db, tf_stream_t stream);
+
+/* ---- TensoFlow sampler: piecewise-quadratic coupling transform -------------------
+ * ElementWisePWQuadraticTransform of the reference (network/flow.py:314-525), one
+ * coordinate per row, K = 10 bins from st[M,21] = (11 vertex heights, 10 bin widths).
+ *   inverse = 0: forward spline (`flow_inv`, density evaluation, flow.py:332-413)
+ *   inverse = 1: inverse spline (`flow`, sampling, flow.py:415-525)
+ * y[M] in (0,1) -> x[M], logj[M]. */
+TF_API int tf_pwquad_fwd(const float* y, const float* st, int64_t M, int32_t inverse, float* x,
+                         float* logj, tf_stream_t stream);
+/* Backward of the forward spline (inverse = 0 only: the sampling copies are frozen,
+ * network/fields.py:1050-1065): given g_x[M], g_logj[M] -> d_y[M], d_st[M,21]. */
+TF_API int tf_pwquad_bwd(const float* y, const float* st, int64_t M, const float* g_x,
+                         const float* g_logj, float* d_y, float* d_st, tf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

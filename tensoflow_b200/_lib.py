@@ -62,8 +62,14 @@ _SIGNATURES = {
                                         _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
 }
 
-# filled in by later sections of the ABI (flow sampler, MC shading, BVH)
-_OPTIONAL_SIGNATURES = {}
+# later sections of the ABI (small MLP layers, flow sampler, MC shading, BVH)
+_OPTIONAL_SIGNATURES = {
+    "tf_linear_fwd": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_float, _P, _P]),
+    "tf_linear_bwd": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+                                _P, _P, _P, _P]),
+    "tf_pwquad_fwd": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, _P, _P]),
+    "tf_pwquad_bwd": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P, _P, _P]),
+}
 
 
 def exported_symbols():

@@ -1,0 +1,260 @@
+// Tall-skinny fused linear layers (M = 10^5..10^7 rows, K,N <= 256): the small MLPs of the
+// hot path -- coupling-layer conditioners (network/flow.py:577-598), indirect-light and
+// material predictors (network/other_field.py:20-121), shading heads (network/fields.py:395-417).
+//   fwd      : Y = act(X W^T + b)                       (nn.Linear + activation, one pass)
+//   bwd-data : dPre = dY * act'(Y);  dX = dPre W        (dPre is written back for bwd-weight)
+//   bwd-wgt  : dW += dPre^T X (xty),  db += colsum(dPre)
+// v1 arithmetic is fp32 FFMA (128x64 CTA tile, 8x4 register tile); see DESIGN.md.
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 64, BK = 16, BMP = BM + 4, BNP = BN + 4;
+
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2, ACT_SOFTPLUS100 = 3, ACT_SIGMOID = 4, ACT_EXP = 5 };
+
+__device__ __forceinline__ float act_fwd(float x, int act, float p) {
+    switch (act) {
+        case ACT_RELU: return fmaxf(x, 0.f);
+        case ACT_LEAKY: return x > 0.f ? x : 0.01f * x;
+        case ACT_SOFTPLUS100: return softplus100(x);
+        case ACT_SIGMOID: return 1.f / (1.f + expf(-x));
+        case ACT_EXP: return expf(fminf(x, p));          // ExpActivation (other_field.py:12-18)
+        default: return x;
+    }
+}
+// derivative expressed through the OUTPUT y (so only Y has to be kept for backward)
+__device__ __forceinline__ float act_bwd(float y, int act, float p) {
+    switch (act) {
+        case ACT_RELU: return y > 0.f ? 1.f : 0.f;
+        case ACT_LEAKY: return y > 0.f ? 1.f : 0.01f;
+        case ACT_SOFTPLUS100: return 1.f - expf(-100.f * y);
+        case ACT_SIGMOID: return y * (1.f - y);
+        case ACT_EXP: return y < expf(p) ? y : 0.f;
+        default: return 1.f;
+    }
+}
+
+// out[M][Nout] = epi( A[M][Kred] * B ),  B[kk][j] = TRANS_W ? W[kk*ldw + j] : W[j*ldw + kk]
+// BWD: A element = dY * act'(Y) (and stored to dpre by the blockIdx.y == 0 column of CTAs)
+template <bool TRANS_W, bool BWD>
+__global__ void __launch_bounds__(256, 2) linear_kernel(const float* __restrict__ A, int lda, const float* __restrict__ Yact,
+                                                        float* __restrict__ dpre, const float* __restrict__ W, int ldw,
+                                                        const float* __restrict__ bias, int64_t M, int Kred, int Nout, int act,
+                                                        float act_p, float* __restrict__ out, int ldo) {
+    __shared__ __align__(16) float As[BK][BMP];
+    __shared__ __align__(16) float Bs[BK][BNP];
+    const int64_t r0 = (int64_t)blockIdx.x * BM;
+    const int c0 = blockIdx.y * BN;
+    const int ty = threadIdx.x / 16, tx = threadIdx.x % 16;
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+    for (int k0 = 0; k0 < Kred; k0 += BK) {
+        // A tile -> As[k][row]
+#pragma unroll
+        for (int i = 0; i < BM / 16; ++i) {
+            const int row = ty + 16 * i, k = tx;
+            const int64_t r = r0 + row;
+            float v = 0.f;
+            if (r < M && k0 + k < Kred) {
+                v = A[r * lda + k0 + k];
+                if (BWD) {
+                    v *= act_bwd(Yact[r * lda + k0 + k], act, act_p);
+                    if (blockIdx.y == 0) dpre[r * lda + k0 + k] = v;
+                }
+            }
+            As[k][row] = v;
+        }
+        // B tile -> Bs[k][col]
+#pragma unroll
+        for (int i = 0; i < (BK * BN) / 256; ++i) {
+            const int idx = threadIdx.x + 256 * i;
+            int k, j;
+            if (TRANS_W) { k = idx / BN; j = idx % BN; } else { j = idx / BK; k = idx % BK; }
+            float v = 0.f;
+            if (k0 + k < Kred && c0 + j < Nout) v = TRANS_W ? __ldg(W + (size_t)(k0 + k) * ldw + c0 + j) : __ldg(W + (size_t)(c0 + j) * ldw + k0 + k);
+            Bs[k][j] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                acc[i][0] = fmaf(a[i], b.x, acc[i][0]); acc[i][1] = fmaf(a[i], b.y, acc[i][1]);
+                acc[i][2] = fmaf(a[i], b.z, acc[i][2]); acc[i][3] = fmaf(a[i], b.w, acc[i][3]);
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int64_t r = r0 + ty * 8 + i;
+        if (r >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = c0 + tx * 4 + j;
+            if (c >= Nout) continue;
+            float v = acc[i][j];
+            if (!BWD) {
+                if (bias) v += __ldg(bias + c);
+                v = act_fwd(v, act, act_p);
+            }
+            out[r * ldo + c] = v;
+        }
+    }
+}
+
+// ---- weight-gradient GEMM: out[m][n] (ld = ldo) += sum_r X[r][m] * Y[r][n] ---------------
+constexpr int XT_M = 128, XT_N = 128, XT_R = 16;
+__global__ void __launch_bounds__(256) xty_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ Y, int ldy,
+                                                  int64_t rows, int M, int N, float* __restrict__ out, int ldo,
+                                                  int64_t rows_per_cta) {
+    __shared__ __align__(16) float Xs[XT_R][XT_M];
+    __shared__ __align__(16) float Ys[XT_R][XT_N];
+    const int m0 = blockIdx.x * XT_M, n0 = blockIdx.y * XT_N;
+    const int64_t r_begin = (int64_t)blockIdx.z * rows_per_cta;
+    const int64_t r_end = r_begin + rows_per_cta < rows ? r_begin + rows_per_cta : rows;
+    const int ty = threadIdx.x / 16, tx = threadIdx.x % 16;
+    const bool vec = (ldx % 4 == 0) && (ldy % 4 == 0) && (((uintptr_t)X & 15) == 0) && (((uintptr_t)Y & 15) == 0);
+    float acc[8][8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
+    for (int64_t r0 = r_begin; r0 < r_end; r0 += XT_R) {
+        for (int i = threadIdx.x; i < XT_R * (XT_M / 4); i += 256) {
+            const int rr = i / (XT_M / 4), m = (i % (XT_M / 4)) * 4;
+            float4 v = f4_zero();
+            if (r0 + rr < r_end) {
+                const float* src = X + (size_t)(r0 + rr) * ldx + m0 + m;
+                if (vec && m0 + m + 3 < ldx) { if (m0 + m < M) v = ldg4(src); }
+                else {
+                    if (m0 + m + 0 < M) v.x = __ldg(src + 0);
+                    if (m0 + m + 1 < M) v.y = __ldg(src + 1);
+                    if (m0 + m + 2 < M) v.z = __ldg(src + 2);
+                    if (m0 + m + 3 < M) v.w = __ldg(src + 3);
+                }
+            }
+            *reinterpret_cast<float4*>(&Xs[rr][m]) = v;
+        }
+        for (int i = threadIdx.x; i < XT_R * (XT_N / 4); i += 256) {
+            const int rr = i / (XT_N / 4), nn = (i % (XT_N / 4)) * 4;
+            float4 v = f4_zero();
+            if (r0 + rr < r_end) {
+                const float* src = Y + (size_t)(r0 + rr) * ldy + n0 + nn;
+                if (vec && n0 + nn + 3 < ldy) { if (n0 + nn < N) v = ldg4(src); }
+                else {
+                    if (n0 + nn + 0 < N) v.x = __ldg(src + 0);
+                    if (n0 + nn + 1 < N) v.y = __ldg(src + 1);
+                    if (n0 + nn + 2 < N) v.z = __ldg(src + 2);
+                    if (n0 + nn + 3 < N) v.w = __ldg(src + 3);
+                }
+            }
+            *reinterpret_cast<float4*>(&Ys[rr][nn]) = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int rr = 0; rr < XT_R; ++rr) {
+            const float4 xa = *reinterpret_cast<const float4*>(&Xs[rr][ty * 4]);
+            const float4 xb = *reinterpret_cast<const float4*>(&Xs[rr][64 + ty * 4]);
+            const float4 ya = *reinterpret_cast<const float4*>(&Ys[rr][tx * 4]);
+            const float4 yb = *reinterpret_cast<const float4*>(&Ys[rr][64 + tx * 4]);
+            const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+            const float yv[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int b = 0; b < 8; ++b) acc[a][b] = fmaf(xv[a], yv[b], acc[a][b]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        const int m = m0 + (a < 4 ? ty * 4 + a : 64 + ty * 4 + a - 4);
+        if (m >= M) continue;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int nn = n0 + (b < 4 ? tx * 4 + b : 64 + tx * 4 + b - 4);
+            if (nn < N && acc[a][b] != 0.f) atomicAdd(out + (size_t)m * ldo + nn, acc[a][b]);
+        }
+    }
+}
+
+// column sums: out[c] += sum_r X[r][c]
+__global__ void colsum_kernel(const float* __restrict__ X, int ldx, int64_t rows, int cols, float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    float acc = 0.f;
+    for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) acc += X[r * ldx + c];
+    if (acc != 0.f) atomicAdd(out + c, acc);
+}
+
+}  // namespace
+
+// internal entry points shared with the other translation units
+int tf_internal_xty(const float* X, int ldx, const float* Y, int ldy, int64_t rows, int M, int N, float* out, int ldo,
+                    cudaStream_t stream) {
+    if (rows == 0 || M == 0 || N == 0) return 0;
+    dim3 grid((M + XT_M - 1) / XT_M, (N + XT_N - 1) / XT_N, 1);
+    const int tiles = grid.x * grid.y;
+    int64_t slices = (2 * (int64_t)tf_num_sms() + tiles - 1) / tiles;
+    int64_t rpc = (rows + slices - 1) / slices;
+    rpc = ((rpc + XT_R - 1) / XT_R) * XT_R;
+    if (rpc < 256) rpc = 256;
+    grid.z = (unsigned)((rows + rpc - 1) / rpc);
+    xty_kernel<<<grid, 256, 0, stream>>>(X, ldx, Y, ldy, rows, M, N, out, ldo, rpc);
+    tf_count_launches(1);
+    return 0;
+}
+
+int tf_internal_colsum(const float* X, int ldx, int64_t rows, int cols, float* out, cudaStream_t stream) {
+    if (rows == 0 || cols == 0) return 0;
+    int gy = (int)(rows < 256 ? rows : 256);
+    dim3 cg((cols + 127) / 128, gy);
+    colsum_kernel<<<cg, 128, 0, stream>>>(X, ldx, rows, cols, out);
+    tf_count_launches(1);
+    return 0;
+}
+
+extern "C" TF_API int tf_linear_fwd(const float* X, const float* W, const float* b, int64_t M, int32_t K, int32_t N, int32_t act,
+                                    float act_param, float* Y, tf_stream_t stream) {
+    if (M == 0) return 0;
+    TF_REQUIRE(X && W && Y, "tf_linear_fwd: NULL pointer");
+    TF_REQUIRE(K > 0 && N > 0 && act >= 0 && act <= 5, "tf_linear_fwd: bad K/N/act (%d,%d,%d)", K, N, act);
+    dim3 grid((unsigned)((M + BM - 1) / BM), (N + BN - 1) / BN);
+    linear_kernel<false, false><<<grid, 256, 0, (cudaStream_t)stream>>>(X, K, nullptr, nullptr, W, K, b, M, K, N, act, act_param, Y, N);
+    tf_count_launches(1);
+    TF_CHECK_LAUNCH("tf_linear_fwd");
+    return 0;
+}
+
+extern "C" TF_API int tf_linear_bwd(const float* X, const float* W, const float* Y, const float* dY, float* dpre, int64_t M,
+                                    int32_t K, int32_t N, int32_t act, float act_param, float* dX, float* dW, float* db,
+                                    tf_stream_t stream_) {
+    if (M == 0) return 0;
+    TF_REQUIRE(X && W && Y && dY && dpre && dY != dpre, "tf_linear_bwd: NULL pointer (or dY aliases dpre)");
+    TF_REQUIRE(K > 0 && N > 0 && act >= 0 && act <= 5, "tf_linear_bwd: bad K/N/act (%d,%d,%d)", K, N, act);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    // dPre = dY * act'(Y) and dX = dPre W.  dX may be NULL (first layer): then a one-column
+    // launch still materialises dPre.
+    float* scratch_dx = dX;
+    int kcols = K;
+    if (!dX) { kcols = 0; }
+    if (dX) {
+        dim3 grid((unsigned)((M + BM - 1) / BM), (K + BN - 1) / BN);
+        linear_kernel<true, true><<<grid, 256, 0, stream>>>(dY, N, Y, dpre, W, K, nullptr, M, N, K, act, act_param, scratch_dx, K);
+    } else {
+        dim3 grid((unsigned)((M + BM - 1) / BM), 1);
+        linear_kernel<true, true><<<grid, 256, 0, stream>>>(dY, N, Y, dpre, W, K, nullptr, M, N, kcols, act, act_param, nullptr, K);
+    }
+    tf_count_launches(1);
+    if (dW) tf_internal_xty(dpre, N, X, K, M, N, K, dW, K, stream);
+    if (db) tf_internal_colsum(dpre, N, M, N, db, stream);
+    TF_CHECK_LAUNCH("tf_linear_bwd");
+    return 0;
+}

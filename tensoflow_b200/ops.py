@@ -296,6 +296,12 @@ class NeusCompositeFunction(torch.autograd.Function):
         weights = torch.empty(n, device=dev, dtype=torch.float32)
         acc = torch.empty(R, device=dev, dtype=torch.float32)
         out = torch.empty(R, D, device=dev, dtype=torch.float32)
+        if n == 0:   # no samples at all: every ray composites to zero
+            acc.zero_(); out.zero_()
+            ctx.save_for_backward(sdf_c, grad_c, dists_c, dirs_c, offs, var_c, vals_c, alpha, weights)
+            ctx.cos_anneal, ctx.train_variance, ctx.var_shape = float(cos_anneal), bool(train_variance), variance.shape
+            ctx.mark_non_differentiable(alpha)
+            return alpha, weights, acc, out
         with _timed("neus_composite_fwd"):
           check(lib.tf_neus_composite_fwd(ptr(sdf_c), ptr(grad_c), ptr(dists_c), ptr(dirs_c), ptr(offs), R, ptr(var_c),
                                         float(cos_anneal), ptr(vals_c), D, ptr(alpha), ptr(weights), ptr(acc), ptr(out),
@@ -318,6 +324,9 @@ class NeusCompositeFunction(torch.autograd.Function):
         d_grad = torch.zeros(n, 3, device=dev, dtype=torch.float32)
         d_vals = torch.zeros(n, D, device=dev, dtype=torch.float32) if D > 0 else None
         d_var = torch.zeros(1, device=dev, dtype=torch.float32) if ctx.train_variance else None
+        if n == 0:
+            dv = None if d_var is None else d_var.reshape(ctx.var_shape)
+            return d_sdf, d_grad, None, None, None, dv, None, d_vals, None
         with _timed("neus_composite_bwd"):
           check(lib.tf_neus_composite_bwd(ptr(sdf_c), ptr(grad_c), ptr(dists_c), ptr(dirs_c), ptr(offs), R, ptr(var_c),
                                         ctx.cos_anneal, ptr(vals_c), D, ptr(alpha), ptr(weights), ptr(_f32c(g_acc)),
@@ -325,3 +334,81 @@ class NeusCompositeFunction(torch.autograd.Function):
                                         ptr(d_var), stream_ptr()), "tf_neus_composite_bwd")
         dv = None if d_var is None else d_var.reshape(ctx.var_shape)
         return d_sdf, d_grad, None, None, None, dv, None, d_vals, None
+
+
+ACT = {"none": 0, "relu": 1, "leaky": 2, "softplus100": 3, "sigmoid": 4, "exp": 5}
+
+
+class LinearFunction(torch.autograd.Function):
+    """Y = act(X W^T + b): one nn.Linear + activation of the reference's small MLPs
+    (network/other_field.py:20-121, network/flow.py:577-598) as one fused kernel.
+    X [M,K], W [N,K], b [N] or None, act in ACT, act_param (max for 'exp')."""
+
+    @staticmethod
+    def forward(ctx, X, W, b, act, act_param=0.0):
+        lib = _lib.load()
+        Xc, Wc, bc = _f32c(X), _f32c(W), _f32c(b)
+        M, K = Xc.shape
+        N = Wc.shape[0]
+        Y = torch.empty(M, N, device=Xc.device, dtype=torch.float32)
+        with _timed("linear_fwd"):
+            check(lib.tf_linear_fwd(ptr(Xc), ptr(Wc), ptr(bc), M, K, N, ACT[act], float(act_param), ptr(Y), stream_ptr()),
+                  "tf_linear_fwd")
+        ctx.save_for_backward(Xc, Wc, Y)
+        ctx.act, ctx.act_param, ctx.has_bias = act, float(act_param), b is not None
+        return Y
+
+    @staticmethod
+    def backward(ctx, gY):
+        lib = _lib.load()
+        Xc, Wc, Y = ctx.saved_tensors
+        M, K = Xc.shape
+        N = Wc.shape[0]
+        gYc = _f32c(gY)
+        dpre = torch.empty_like(Y)
+        need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
+        dX = torch.empty(M, K, device=Xc.device, dtype=torch.float32) if need_x else None
+        dW = torch.zeros_like(Wc) if need_w else None
+        db = torch.zeros(N, device=Xc.device, dtype=torch.float32) if need_b else None
+        with _timed("linear_bwd"):
+            check(lib.tf_linear_bwd(ptr(Xc), ptr(Wc), ptr(Y), ptr(gYc), ptr(dpre), M, K, N, ACT[ctx.act], ctx.act_param,
+                                    ptr(dX), ptr(dW), ptr(db), stream_ptr()), "tf_linear_bwd")
+        return dX, dW, db, None, None
+
+
+def linear(X, W, b=None, act="none", act_param=0.0):
+    if X.shape[0] == 0:
+        return X.new_zeros(0, W.shape[0])
+    return LinearFunction.apply(X, W, b, act, act_param)
+
+
+class PwquadFunction(torch.autograd.Function):
+    """Piecewise-quadratic coupling transform (reference network/flow.py:314-525).
+    y [M], st [M,21] -> x [M], logj [M].  inverse=True is the sampling direction (no grad)."""
+
+    @staticmethod
+    def forward(ctx, y, st, inverse):
+        lib = _lib.load()
+        yc, stc = _f32c(y), _f32c(st)
+        M = yc.shape[0]
+        x = torch.empty_like(yc)
+        logj = torch.empty_like(yc)
+        with _timed("pwquad_fwd"):
+            check(lib.tf_pwquad_fwd(ptr(yc), ptr(stc), M, 1 if inverse else 0, ptr(x), ptr(logj), stream_ptr()), "tf_pwquad_fwd")
+        ctx.save_for_backward(yc, stc)
+        ctx.inverse = bool(inverse)
+        return x, logj
+
+    @staticmethod
+    def backward(ctx, g_x, g_logj):
+        if ctx.inverse:
+            raise RuntimeError("the inverse (sampling) spline has no backward: the reference samples from frozen flow copies")
+        lib = _lib.load()
+        yc, stc = ctx.saved_tensors
+        M = yc.shape[0]
+        d_y = torch.empty_like(yc)
+        d_st = torch.empty_like(stc)
+        with _timed("pwquad_bwd"):
+            check(lib.tf_pwquad_bwd(ptr(yc), ptr(stc), M, ptr(_f32c(g_x)), ptr(_f32c(g_logj)), ptr(d_y), ptr(d_st), stream_ptr()),
+                  "tf_pwquad_bwd")
+        return d_y, d_st, None
