@@ -101,7 +101,7 @@ class Block(nn.Module):
         h = ops.linear(h, self.nn[5].weight, self.nn[5].bias, "leaky")
         return ops.linear(h, self.nn[7].weight, self.nn[7].bias, "none")
 
-    def _apply(self, y, logj, feature, inverse):
+    def _couple(self, y, logj, feature, inverse):
         st = self._st(y, feature)
         t = 1 - self.cond
         xt, lj = ops.PwquadFunction.apply(y[:, t], st, inverse)
@@ -111,10 +111,10 @@ class Block(nn.Module):
         return torch.stack(cols, -1), logj + lj[:, None]
 
     def flow(self, y, logj, feature, return_jacobian=True):          # sampling direction
-        return self._apply(y, logj, feature, True)
+        return self._couple(y, logj, feature, True)
 
     def flow_inv(self, y, logj, feature, return_jacobian=True):      # density direction
-        return self._apply(y, logj, feature, False)
+        return self._couple(y, logj, feature, False)
 
 
 class TensoFlow(nn.Module):
