@@ -175,6 +175,57 @@ TF_API int tf_pwquad_fwd(const float* y, const float* st, int64_t M, int32_t inv
 TF_API int tf_pwquad_bwd(const float* y, const float* st, int64_t M, const float* g_x,
                          const float* g_logj, float* d_y, float* d_st, tf_stream_t stream);
 
+/* ---- triangle-mesh ray tracer ---------------------------------------------------------
+ * Replaces the un-vendored `_raytracing` extension behind raytracing/raytracer.py:8-54
+ * (`create_raytracer(vertices, triangles)` / `impl.trace(o, d, positions, normals, depth)`).
+ * tf_bvh_create takes HOST arrays (like the reference, which builds from numpy) and uploads a
+ * BVH to the current device; the handle owns that device memory until tf_bvh_destroy.
+ * trace: closest hit with t > 0; writes position = o + t d, UNIT face normal (e1 x e2, the
+ * reference renderer flips it: network/materialRenderer.py:256-257) and depth = t;
+ * a miss writes depth = 10 (the sentinel of materialRenderer.py:261), normal = 0. */
+typedef struct tf_bvh_opaque tf_bvh_t;
+TF_API int tf_bvh_create(const float* vertices_host, int64_t n_vertices, const int32_t* triangles_host,
+                         int64_t n_triangles, tf_bvh_t** out);
+TF_API void tf_bvh_destroy(tf_bvh_t* handle);
+TF_API int tf_bvh_trace(const tf_bvh_t* handle, const float* rays_o, const float* rays_d, int64_t n,
+                        float* positions, float* face_normals, float* depth, tf_stream_t stream);
+
+/* ---- material-stage Monte-Carlo integral (network/fields.py:1075-1335) -----------------
+ * tf_mc_directions builds one direction set per surface point and its pdf:
+ *   mode 0: flow samples in the half-vector parametrisation (fields.py:1085-1108,1164-1188)
+ *           src = angles [pn,sn,2] in (0,1)^2, aux = logj [pn,sn]
+ *   mode 1: fixed cosine set (fields.py:824-847): src = table [sn,2] (az/2pi, el),
+ *           aux = per-point azimuth shift in [0,1) [pn] or NULL
+ *   mode 2: fixed GGX set (fields.py:858-895): as mode 1 plus roughness [pn]
+ * Outputs go to dirs[(p*out_stride + out_offset + s)*3], prob[p*out_stride + out_offset + s]
+ * so several sets can share one [pn, D] buffer.  normals / view_dirs must be unit length. */
+TF_API int tf_mc_directions(int32_t mode, const float* normals, const float* view_dirs, const float* src,
+                            const float* aux, const float* roughness, int64_t n_points, int32_t n_dirs,
+                            float* dirs, float* prob, int32_t out_stride, int32_t out_offset,
+                            tf_stream_t stream);
+/* EnvLight.direct_light (network/light.py:125-162): out[n,3] = exp(seamless bilinear lookup of the
+ * log-radiance cubemap base[6,R,R,3]) where mask[n] != 0 (NULL = all), 0 elsewhere; bwd scatters
+ * g_out * out into d_base (accumulated). */
+TF_API int tf_cube_light_fwd(const float* base, int32_t res, const float* dirs, const uint8_t* mask,
+                             int64_t n, float* out, tf_stream_t stream);
+TF_API int tf_cube_light_bwd(int32_t res, const float* dirs, const uint8_t* mask, int64_t n,
+                             const float* out, const float* g_out, float* d_base, tf_stream_t stream);
+/* BRDF weights + estimators per surface point over D = n_diffuse + n_specular directions
+ * (fields.py:1146-1157, 1208-1234).  out[pn,16] = diffuse estimate (3), specular estimate (3),
+ * mean diffuse light (3), mean specular light (3), visibility (1), indirect light (3).
+ * bwd: g_out[pn,16] -> d_albedo[pn,3], d_metallic[pn], d_roughness[pn], d_lights[pn,D,3]. */
+TF_API int tf_mc_estimate_fwd(const float* normals, const float* view_dirs, const float* albedo,
+                              const float* metallic, const float* roughness, const float* dirs,
+                              const float* prob, const float* lights, const uint8_t* hit,
+                              int64_t n_points, int32_t n_diffuse, int32_t n_specular, float* out,
+                              tf_stream_t stream);
+TF_API int tf_mc_estimate_bwd(const float* normals, const float* view_dirs, const float* albedo,
+                              const float* metallic, const float* roughness, const float* dirs,
+                              const float* prob, const float* lights, const uint8_t* hit,
+                              int64_t n_points, int32_t n_diffuse, int32_t n_specular,
+                              const float* g_out, float* d_albedo, float* d_metallic,
+                              float* d_roughness, float* d_lights, tf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

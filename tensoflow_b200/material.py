@@ -1,0 +1,415 @@
+"""Material stage (reference network/fields.py:618-1595 MCShadingNetwork, network/light.py
+EnvLight, network/materialRenderer.py) on the sm_100a kernels.
+
+In-scope branches: shade_mixed, use_nis_diffuse + use_nis_specular with the
+half-vector parametrisation, outer_light_version='envlight', geometry_type='schlick', no
+human lights.  Parameter names follow the reference so its checkpoints load
+(`mat_plane.*`, `mat_line.*`, `*_predictor.*`, `outer_light.base`, `inner_light.*`,
+`flow_{diffuse,specular}[_copy].*`); the reference's dead weights (`feats_network`,
+`mat_n_comp_mat`) are not instantiated.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Dict, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops, mc_ops
+from .fields import _cl, MAT_MODE, VEC_MODE, TVLoss
+from .flow import TensoFlow, posenc
+
+EPS = 1e-6   # reference network/fields.py:18
+
+
+def linear_to_srgb(linear):
+    """reference utils/raw_utils.py:4-10"""
+    eps = torch.finfo(torch.float32).eps
+    srgb0 = 323 / 25 * linear
+    srgb1 = (211 * torch.clamp(linear, min=eps) ** (5 / 12) - 11) / 200
+    return torch.where(linear <= 0.0031308, srgb0, srgb1)
+
+
+def saturate_dot(a, b):
+    return torch.clamp(torch.sum(a * b, dim=-1, keepdim=True), min=0.0, max=1.0)
+
+
+def sample_sphere(num_samples, begin_elevation=0):
+    """reference utils/base_utils.py:869-882"""
+    ratio = (begin_elevation + 90) / 180
+    num_points = int(num_samples // (1 - ratio))
+    phi = (np.sqrt(5) - 1.0) / 2.
+    az, el = [], []
+    for n in range(num_points - num_samples, num_points):
+        z = 2. * n / num_points - 1.
+        az.append(2 * np.pi * n * phi % (2 * np.pi))
+        el.append(np.arcsin(z))
+    return np.array(az), np.array(el)
+
+
+# ---- integrated directional encoding (reference utils/ref_utils.py:8-117), kappa_inv = 0 ----
+def _ide_tables(deg_view=5):
+    ml = []
+    for i in range(deg_view):
+        l = 2 ** i
+        for m in range(l + 1):
+            ml.append((m, l))
+    ml = np.array(ml).T
+    l_max = 2 ** (deg_view - 1)
+
+    def gbc(a, k):
+        return np.prod(a - np.arange(k)) / math.factorial(k)
+
+    mat = np.zeros((l_max + 1, ml.shape[1]))
+    for i, (m, l) in enumerate(ml.T):
+        for k in range(l - m + 1):
+            alc = ((-1) ** m * 2 ** l * math.factorial(l) / math.factorial(k) / math.factorial(l - k - m)
+                   * gbc(0.5 * (l + k + m - 1.0), l))
+            mat[k, i] = np.sqrt((2.0 * l + 1.0) * math.factorial(l - m) / (4.0 * np.pi * math.factorial(l + m))) * alc
+    return ml, mat.astype(np.float32)
+
+
+_IDE_CACHE = {}
+
+
+def ide_encode(xyz: torch.Tensor) -> torch.Tensor:
+    """generate_ide_fn(5)(xyz, 0) -> [N,72] with real arithmetic: (x+iy)^m by recurrence."""
+    key = xyz.device
+    if key not in _IDE_CACHE:
+        ml, mat = _ide_tables(5)
+        _IDE_CACHE[key] = (torch.from_numpy(ml[0].astype(np.int64)).to(xyz.device), torch.from_numpy(mat).to(xyz.device))
+    m_idx, mat = _IDE_CACHE[key]
+    x, y, z = xyz[:, 0:1], xyz[:, 1:2], xyz[:, 2:3]
+    n_pow = mat.shape[0]
+    zs = [torch.ones_like(z)]
+    re, im = [torch.ones_like(x)], [torch.zeros_like(x)]
+    for _ in range(1, n_pow):
+        zs.append(zs[-1] * z)
+        re_n = re[-1] * x - im[-1] * y
+        im_n = re[-1] * y + im[-1] * x
+        re.append(re_n)
+        im.append(im_n)
+    vmz = torch.cat(zs, -1)
+    re, im = torch.cat(re, -1)[:, m_idx], torch.cat(im, -1)[:, m_idx]
+    poly = vmz @ mat
+    return torch.cat([re * poly, im * poly], -1)
+
+
+def make_predictor(n_layers, feats_dim, output_dim, run_dim=None):
+    """weight-norm Linear stacks of reference network/other_field.py:20-121 (activations are
+    applied by the fused linear kernels)."""
+    run_dim = run_dim or (256 if n_layers == 4 else 128)
+    wn = nn.utils.parametrizations.weight_norm
+    layers, last = [], feats_dim
+    for _ in range(n_layers - 1):
+        layers += [wn(nn.Linear(last, run_dim)), nn.ReLU()]
+        last = run_dim
+    layers += [wn(nn.Linear(last, output_dim)), nn.Identity()]
+    return nn.Sequential(*layers)
+
+
+def run_predictor(seq: nn.Sequential, x, final_act: str, act_param: float = 0.0):
+    n = len(seq) // 2
+    for i in range(n):
+        lin = seq[2 * i]
+        x = ops.linear(x, lin.weight, lin.bias, "relu" if i < n - 1 else final_act, act_param)
+    return x
+
+
+class EnvLight(nn.Module):
+    """reference network/light.py:8-31: trainable log-radiance cubemap; `direct_light`
+    (light.py:125-162) is the lookup the MC shader uses."""
+
+    def __init__(self, path=None, device='cuda', scale=1.0, min_res=16, start_res=16, max_res=512, min_roughness=0.08,
+                 max_roughness=0.5, trainable=False):
+        super().__init__()
+        self.max_res, self.min_res = max_res, min_res
+        self.base = nn.Parameter(torch.full((6, max_res, max_res, 3), math.log(0.5), dtype=torch.float32, device=device),
+                                 requires_grad=trainable)
+        self.level = max(0, int(np.log2(max_res / start_res)) + 0.5)
+
+    def upsample(self):
+        if self.level > 0:
+            self.level = max(self.level - 1, 0)
+
+    def build_mips_direct(self, cutoff=0.99):
+        """reference light.py:66-70 (average-pool chain; unused by direct_light)."""
+        self.base_mip = [self.base]
+        while self.base_mip[-1].shape[1] > self.min_res:
+            self.base_mip.append(F.avg_pool2d(self.base_mip[-1].permute(0, 3, 1, 2), (2, 2)).permute(0, 2, 3, 1).contiguous())
+
+    def direct_light(self, l, roughness=None, mask=None):
+        return mc_ops.CubeLightFunction.apply(self.base, l, mask)
+
+
+def get_orthogonal_directions(d):
+    """reference fields.py:812-822"""
+    x, y, z = torch.split(d, 1, dim=-1)
+    o0 = torch.cat([y, -x, torch.zeros_like(x)], -1)
+    o1 = torch.cat([-z, torch.zeros_like(x), x], -1)
+    mask0 = (torch.norm(o0, dim=-1) > torch.norm(o1, dim=-1))[:, None]
+    return F.normalize(torch.where(mask0, o0, o1), dim=-1)
+
+
+def direction_to_angle(normals, directions):
+    """reference fields.py:1035-1048"""
+    z = normals
+    x = get_orthogonal_directions(normals)
+    y = torch.cross(z, x, dim=-1)
+    cx = torch.sum(x.unsqueeze(1) * directions, -1, keepdim=True)
+    cy = torch.sum(y.unsqueeze(1) * directions, -1, keepdim=True)
+    cz = torch.sum(z.unsqueeze(1) * directions, -1, keepdim=True).clamp(-1 + EPS, 1 - EPS)
+    phi = (torch.atan2(cy, cx) + 2 * np.pi) % (2 * np.pi)
+    return torch.cat([phi, torch.acos(cz)], dim=-1)
+
+
+class MCShadingNetwork(nn.Module):
+    default_cfg = {
+        'diffuse_sample_num': 512, 'specular_sample_num': 256, 'human_lights': False, 'light_exp_max': 5.0,
+        'inner_light_exp_max': 5.0, 'outer_light_version': 'envlight', 'geometry_type': 'schlick', 'random_azimuth': True,
+        'shade_fn': 'shade_mixed', 'use_nis_diffuse': True, 'use_nis_specular': True, 'gridSize': [512, 512, 512],
+        'nis_diffuse_sample_num': 64, 'nis_specular_sample_num': 32, 'nis_start_iter_diffuse': 1000,
+        'nis_start_iter_specular': 1000, 'nis_loss_iter_diffuse': 500, 'nis_loss_iter_specular': 500,
+        'nis_update_interval_diffuse': 1000, 'nis_update_interval_specular': 1000, 'flow_diffuse': 'pwquad',
+        'flow_specular': 'pwquad', 'use_half_diffuse': True, 'use_half_specular': True, 'light_upsample_interval': 1000,
+        'light_reso': 128, 'reg_min_max': True, 'mat_grid': 512, 'device': 'cuda',
+    }
+
+    def __init__(self, cfg, ray_trace_fun: Callable, aabb):
+        super().__init__()
+        self.cfg = {**self.default_cfg, **cfg}
+        c = self.cfg
+        if c['outer_light_version'] != 'envlight' or c['human_lights'] or c['shade_fn'] != 'shade_mixed' \
+                or c['geometry_type'] != 'schlick' or not (c['use_half_diffuse'] and c['use_half_specular']):
+            raise NotImplementedError("tensoflow_b200 implements the shipped material configuration "
+                                      "(envlight, shade_mixed, half-vector flows, schlick geometry)")
+        dev = c['device']
+        self.aabb = torch.as_tensor(aabb, dtype=torch.float32).to(dev)
+        self.use_nis = True
+        self.mat_n_comp, self.n_levels, self.nplane = 36, 3, 3
+        G = int(c['mat_grid'])      # the reference hard-codes 512 (fields.py:676-684)
+        self.gridSize = torch.tensor([G, G, G])
+        planes, lines = [], []
+        for i in range(3):          # reference fields.py:765-774
+            planes.append(nn.Parameter(_cl((1e-4 * (2 * torch.rand(1, self.mat_n_comp, G, G) - 1)).to(dev))))
+            lines.append(nn.Parameter(_cl(torch.full((1, self.mat_n_comp, G, 1), 1. / (self.mat_n_comp * 3), device=dev))))
+        self.mat_plane, self.mat_line = nn.ParameterList(planes), nn.ParameterList(lines)
+        self.mat_feature_dim = self.mat_n_comp * self.n_levels
+        self.tv_reg = TVLoss()
+        self.metallic_predictor = make_predictor(2, self.mat_feature_dim, 1).to(dev)
+        self.roughness_predictor = make_predictor(2, self.mat_feature_dim, 1).to(dev)
+        self.albedo_predictor = make_predictor(2, self.mat_feature_dim, 3).to(dev)
+        self.outer_light = EnvLight(trainable=True, max_res=c['light_reso'], device=dev)
+        self.inner_light = make_predictor(4, 51 + 72, 3).to(dev)
+        nn.init.constant_(self.inner_light[-2].bias, np.log(0.5))
+        for name, n in (('diffuse_direction_samples', c['diffuse_sample_num']), ('specular_direction_samples', c['specular_sample_num'])):
+            az, el = sample_sphere(n, 0)            # reference fields.py:734-742
+            az, el = az * 0.5 / np.pi, 1 - 2 * el / np.pi
+            setattr(self, name, torch.from_numpy(np.stack([az, el], -1).astype(np.float32)).to(dev))
+        self.ray_trace_fun = ray_trace_fun
+        self.use_flow_diffuse_copy = False
+        self.use_flow_specular_copy = False
+        mk = lambda: TensoFlow(d=2, aabb=self.aabb, gridSize=c['gridSize'], device=dev, flow='pwquad')
+        self.flow_diffuse, self.flow_diffuse_copy = mk(), mk()
+        self.flow_specular, self.flow_specular_copy = mk(), mk()
+
+    # ---- bookkeeping --------------------------------------------------------------------
+    def get_optparam_groups(self, lr_init_spatialxyz=0.02, lr_init_network=0.001, lr_init_env=0.1):
+        g = [{'params': self.mat_line, 'lr': lr_init_spatialxyz}, {'params': self.mat_plane, 'lr': lr_init_spatialxyz},
+             {'params': self.outer_light.parameters(), 'lr': lr_init_env},
+             {'params': list(self.albedo_predictor.parameters()) + list(self.metallic_predictor.parameters())
+              + list(self.roughness_predictor.parameters()) + list(self.inner_light.parameters()), 'lr': lr_init_network}]
+        g += self.flow_diffuse.get_optparam_groups(lr_init_spatialxyz, lr_init_network)
+        g += self.flow_specular.get_optparam_groups(lr_init_spatialxyz, lr_init_network)
+        return g
+
+    def update_step(self, step):
+        """reference fields.py:1050-1068: periodic refresh of the frozen sampling copies."""
+        c = self.cfg
+        for kind in ('diffuse', 'specular'):
+            if (step + 1) >= c[f'nis_start_iter_{kind}'] and (step + 1 - c[f'nis_start_iter_{kind}']) % c[f'nis_update_interval_{kind}'] == 0:
+                setattr(self, f'use_flow_{kind}_copy', True)
+                copy = getattr(self, f'flow_{kind}_copy')
+                copy.load_state_dict(getattr(self, f'flow_{kind}').state_dict())
+                for p in copy.parameters():
+                    p.requires_grad = False
+        if (step + 1) % c['light_upsample_interval'] == 0:
+            self.outer_light.upsample()
+
+    # ---- materials (reference fields.py:776-810, 1010-1017) ------------------------------------
+    def tenso_feature(self, xyz_sampled, level_vol=None):
+        return ops.VMFeatureFunction.apply(xyz_sampled, level_vol, self.aabb, self.n_levels, *self.mat_plane, *self.mat_line)
+
+    def predict_materials(self, pts):
+        feats = self.tenso_feature(pts)
+        metallic = run_predictor(self.metallic_predictor, feats, "sigmoid")
+        roughness = run_predictor(self.roughness_predictor, feats, "sigmoid") * (1.0 - 0.04 ** 2) + 0.04 ** 2
+        albedo = run_predictor(self.albedo_predictor, feats, "sigmoid")
+        return metallic, roughness, albedo
+
+    def TV_loss(self):
+        total = 0
+        for i in range(3):
+            total = total + self.tv_reg(self.mat_plane[i]) + self.tv_reg(self.mat_line[i])
+        return total
+
+    def material_regularization(self, pts, normals, metallic, roughness, albedo, step):
+        """reference fields.py:1547-1578"""
+        reg = self.TV_loss() * 0.1
+        if self.cfg['reg_min_max'] and step is not None and step < 2000:
+            reg = reg + torch.sum(torch.clamp(roughness - 0.9 ** 2, min=0)) + torch.sum(torch.clamp(0.1 ** 2 - roughness, min=0))
+            reg = reg + torch.sum(torch.clamp(metallic - 0.98, min=0)) + torch.sum(torch.clamp(0.02 - metallic, min=0))
+        return reg
+
+    # ---- lights (reference fields.py:905-975) -----------------------------------------------------
+    def get_lights(self, pts, dirs):
+        """pts [pn,3], dirs [pn,D,3] -> lights [pn,D,3] (autograd), hit [pn,D] bool, inters [pn,D,3]"""
+        pn, D, _ = dirs.shape
+        eps = 1e-5
+        with torch.no_grad():
+            o = (pts[:, None, :] + dirs * eps).reshape(-1, 3)
+            inters, hit_normals, depth, hit = self.ray_trace_fun(o, dirs.reshape(-1, 3))
+            hit = hit.reshape(-1)
+            near = (depth.reshape(-1, 1) > eps).to(torch.float32)
+        lights = self.outer_light.direct_light(dirs.reshape(-1, 3), None, ~hit)
+        idx = torch.nonzero(hit)[:, 0]
+        if idx.numel() > 0:                                           # occluded directions: indirect-light MLP
+            p, v, n = inters[idx], -dirs.reshape(-1, 3)[idx], F.normalize(hit_normals[idx], dim=-1)
+            refl = torch.sum(v * n, -1, keepdim=True) * n * 2 - v
+            enc = torch.cat([posenc(p, 8), ide_encode(refl)], -1)
+            inner = run_predictor(self.inner_light, enc, "exp", self.cfg['inner_light_exp_max'])
+            lights = lights.index_add(0, idx, inner)
+        lights = lights * near
+        return lights.reshape(pn, D, 3), hit.reshape(pn, D), inters.reshape(pn, D, 3)
+
+    # ---- shade_mixed (reference fields.py:1075-1335) -------------------------------------------------
+    def shade_mixed(self, pts, normals, view_dirs, reflections, metallic, roughness, albedo, human_poses, is_train, step=None,
+                    nis_sample=None, noise: Optional[Dict[str, torch.Tensor]] = None):
+        c = self.cfg
+        noise = noise or {}
+        pn, dev = pts.shape[0], pts.device
+        use_fd = c['use_nis_diffuse'] and ((nis_sample is not None and nis_sample) or (nis_sample is None and self.use_flow_diffuse_copy))
+        use_fs = c['use_nis_specular'] and ((nis_sample is not None and nis_sample) or (nis_sample is None and self.use_flow_specular_copy))
+        nd, ns = c['nis_diffuse_sample_num'], c['nis_specular_sample_num']
+        Dd = c['diffuse_sample_num'] + (nd if use_fd else 0)
+        Ds = ns if use_fs else c['specular_sample_num']
+        rand_az = is_train and c['random_azimuth']
+        with torch.no_grad():
+            view_angles = direction_to_angle(normals, view_dirs.unsqueeze(1)).squeeze(1)
+            view_angles = view_angles / torch.tensor([2 * np.pi, 0.5 * np.pi], device=dev)
+            dirs = torch.empty(pn, Dd + Ds, 3, device=dev)
+            prob = torch.empty(pn, Dd + Ds, device=dev)
+            rough_d = roughness.detach()
+            ang_d = ang_s = None
+            off = 0
+            if use_fd:
+                self.flow_diffuse_copy.train(is_train)
+                ang_d, lj = self.flow_diffuse_copy.sample(pts, view_angles, rough_d, nd, return_jacobian=True, phi_shift=noise.get('phi_diffuse'))
+                mc_ops.mc_directions(0, normals, view_dirs, ang_d, lj.reshape(pn, nd), None, nd, dirs, prob, 0)
+                off = nd
+            az = noise.get('az_diffuse')
+            if az is None and rand_az:
+                az = torch.rand(pn, 1, 1, device=dev)
+            mc_ops.mc_directions(1, normals, view_dirs, self.diffuse_direction_samples, None if az is None else az.reshape(pn), None,
+                                 c['diffuse_sample_num'], dirs, prob, off)
+            if use_fs:
+                self.flow_specular_copy.train(is_train)
+                ang_s, lj = self.flow_specular_copy.sample(pts, view_angles, rough_d, ns, return_jacobian=True, phi_shift=noise.get('phi_specular'))
+                mc_ops.mc_directions(0, normals, view_dirs, ang_s, lj.reshape(pn, ns), None, ns, dirs, prob, Dd)
+            else:
+                az = noise.get('az_specular')
+                if az is None and rand_az:
+                    az = torch.rand(pn, 1, 1, device=dev)
+                mc_ops.mc_directions(2, normals, view_dirs, self.specular_direction_samples, None if az is None else az.reshape(pn),
+                                     rough_d.reshape(pn), Ds, dirs, prob, Dd)
+        lights, hit, inters = self.get_lights(pts, dirs)
+        est = mc_ops.McEstimateFunction.apply(normals, view_dirs, albedo, metallic, roughness, dirs, prob, lights, hit, Dd)
+        diffuse_colors, specular_colors = est[:, 0:3], est[:, 3:6]
+        colors = linear_to_srgb(diffuse_colors + specular_colors)
+        outputs = {
+            'albedo': albedo, 'normal': (normals + 1) / 2, 'roughness': roughness, 'metallic': metallic,
+            'diffuse_light': torch.clamp(linear_to_srgb(est[:, 6:9]), min=0, max=1),
+            'specular_light': torch.clamp(linear_to_srgb(est[:, 9:12]), min=0, max=1),
+            'diffuse_color': torch.clamp(linear_to_srgb(diffuse_colors), min=0, max=1),
+            'specular_color': torch.clamp(linear_to_srgb(specular_colors), min=0, max=1),
+            'visibility': est[:, 12:13], 'indirect_light': est[:, 13:16],
+            'human_lights': torch.zeros(1, 3, device=dev),
+        }
+        zero = torch.zeros((), device=dev)
+        # ---- neural-importance-sampling losses (reference fields.py:1254-1333) ----
+        if use_fd and step is not None and step >= c['nis_loss_iter_diffuse']:
+            d1, L1, p1 = dirs[:, :nd], lights[:, :nd], prob[:, :nd, None].clamp_min(EPS)
+            fx = albedo.unsqueeze(1) * (1 - metallic.unsqueeze(1)) * (saturate_dot(d1, normals.unsqueeze(1)) / np.pi) * L1
+            H = F.normalize(view_dirs.unsqueeze(1) + d1, dim=-1)
+            HoV = torch.clamp(torch.sum(H * view_dirs.unsqueeze(1), dim=-1, keepdim=True), min=0.0, max=1.0)
+            phi, theta = ang_d[..., :1] * (2 * np.pi), ang_d[..., 1:2] * (0.5 * np.pi)
+            x = torch.cat([phi / (2 * np.pi), theta / (0.5 * np.pi)], -1).clamp(EPS, 1 - EPS)
+            _, logq_ = self.flow_diffuse(pts, view_angles, roughness, x, return_jacobian=True)
+            logq = logq_ - (4 * np.pi ** 2 * HoV * torch.sin(theta)).clamp_min(EPS).log()
+            outputs['loss_nis_diffuse'] = -(fx * logq / p1).mean()
+        else:
+            outputs['loss_nis_diffuse'] = zero
+        if use_fs and step is not None and step >= c['nis_loss_iter_specular']:
+            d2, L2, p2 = dirs[:, Dd:], lights[:, Dd:], prob[:, Dd:, None].clamp_min(EPS)
+            valid = (torch.sum(d2 * normals.unsqueeze(1), dim=-1, keepdim=True) > 0).to(torch.float32)
+            H = F.normalize(view_dirs.unsqueeze(1) + d2, dim=-1)
+            HoV = torch.clamp(torch.sum(H * view_dirs.unsqueeze(1), dim=-1, keepdim=True), min=0.0, max=1.0)
+            F0 = (0.04 * (1 - metallic) + metallic * albedo).unsqueeze(1)
+            fres = F0 + (1.0 - F0) * torch.clamp(1.0 - HoV, min=0.0, max=1.0) ** 5.0
+            NoV = saturate_dot(normals, view_dirs).unsqueeze(1)
+            NoL = saturate_dot(normals.unsqueeze(1), d2)
+            k = roughness.unsqueeze(1) / 2
+            geo = (NoV / (NoV * (1 - k) + k + 1e-5)) * (NoL / (NoL * (1 - k) + k + 1e-5))
+            NoH = saturate_dot(normals.unsqueeze(1), H)
+            a2 = roughness.unsqueeze(1) ** 2
+            dist = a2 / (np.pi * (NoH ** 2 * (a2 - 1.0) + 1.0) ** 2).clamp_min(EPS)
+            fxs = dist * fres * geo / (4 * NoV).clamp_min(EPS) * L2
+            phi, theta = ang_s[..., :1] * (2 * np.pi), ang_s[..., 1:2] * (0.5 * np.pi)
+            x = torch.cat([phi / (2 * np.pi), theta / (0.5 * np.pi)], -1).clamp(EPS, 1 - EPS)
+            _, logq_ = self.flow_specular(pts, view_angles, roughness, x, return_jacobian=True)
+            logq = logq_ - (4 * np.pi ** 2 * HoV * torch.sin(theta)).clamp_min(EPS).log()
+            # the reference compacts the N.L > 0 pairs and takes the mean over them (fields.py:1209-1214,1321)
+            outputs['loss_nis_specular'] = -((fxs * logq / p2) * valid).sum() / (valid.sum() * 3).clamp_min(1.0)
+        else:
+            outputs['loss_nis_specular'] = zero
+        outputs['loss_nis'] = outputs['loss_nis_diffuse'] + outputs['loss_nis_specular']
+        return colors, outputs
+
+    def forward(self, pts, view_dirs, normals, human_poses, step, is_train, noise=None):
+        """reference fields.py:1453-1473"""
+        view_dirs, normals = F.normalize(view_dirs, dim=-1), F.normalize(normals, dim=-1)
+        metallic, roughness, albedo = self.predict_materials(pts)
+        reflections = torch.sum(view_dirs * normals, -1, keepdim=True) * normals * 2 - view_dirs
+        if step is not None:
+            return self.shade_mixed(pts, normals, view_dirs, reflections, metallic, roughness, albedo, human_poses, is_train, step,
+                                    noise=noise)
+        colors, outputs = self.shade_mixed(pts, normals, view_dirs, reflections, metallic, roughness, albedo, human_poses, is_train,
+                                           step, nis_sample=False, noise=noise)
+        colors_nis, outputs_nis = self.shade_mixed(pts, normals, view_dirs, reflections, metallic, roughness, albedo, human_poses,
+                                                   is_train, nis_sample=True, noise=noise)
+        outputs_nis['rgb_pr'] = colors_nis
+        outputs.update({k + '_nis': v for k, v in outputs_nis.items()})
+        return colors, outputs
+
+
+class MeshTracer:
+    """MaterialRenderer.trace (reference network/materialRenderer.py:253-263) over the BVH kernel:
+    flipped + normalised face normals, hit = depth < 10.  `offset` is the 2*unit_size push the
+    renderer applies to secondary rays (materialRenderer.py:223)."""
+
+    def __init__(self, vertices, triangles, offset: float = 0.0):
+        self.ray_tracer = mc_ops.RayTracer(vertices, triangles)
+        self.offset = float(offset)
+
+    def trace(self, rays_o, rays_d):
+        inters, normals, depth = self.ray_tracer.trace(rays_o, rays_d)
+        depth = depth.reshape(*depth.shape, 1)
+        normals = F.normalize(-normals, dim=-1)
+        hit_mask = ~(depth >= 10)
+        return inters, normals, depth, hit_mask
+
+    def __call__(self, o, d):
+        return self.trace(o + self.offset * d, d)
