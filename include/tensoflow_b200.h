@@ -226,6 +226,16 @@ TF_API int tf_mc_estimate_bwd(const float* normals, const float* view_dirs, cons
                               const float* g_out, float* d_albedo, float* d_metallic,
                               float* d_roughness, float* d_lights, tf_stream_t stream);
 
+/* ---- cubemap prefilter (EnvLight.build_mips, network/light.py:52-64) -----------------------
+ * The reference's diffuse / specular prefilter kernels (network/renderutils/c_src/cubemap.cu:
+ * 110-350) are linear maps of the cubemap with weights that depend only on (resolution,
+ * roughness, cutoff).  The host builds that operator once as CSR and these entry points apply
+ * it to a 3-channel cubemap x[n_cols,3]: y[n_rows,3] = W x, and gx[n_cols,3] += W^T gy. */
+TF_API int tf_csr_spmm3_fwd(const int32_t* rowptr, const int32_t* col, const float* val, const float* x,
+                            int32_t n_rows, float* y, tf_stream_t stream);
+TF_API int tf_csr_spmm3_bwd(const int32_t* rowptr, const int32_t* col, const float* val, const float* gy,
+                            int32_t n_rows, float* gx, tf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

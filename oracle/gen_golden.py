@@ -154,13 +154,41 @@ def gen_mcshade():
           grads=_np({k: p.grad for k, p in ref.named_parameters() if p.grad is not None and 'feats_network' not in k}))
 
 
+def gen_shader():
+    import network.fields as RF
+    import network.light as RL
+    torch.manual_seed(3)
+    ref = RF.ShapeShadingNetwork(dict(has_radiance_field=True, radiance_field_step=0))
+    ref.envlight = RL.EnvLight(trainable=True, max_res=16, min_res=4)     # the shader hard-codes 128 (fields.py:359)
+    with torch.no_grad():
+        ref.envlight.base.add_(0.5 * torch.randn_like(ref.envlight.base))
+    n = 257
+    pts = torch.rand(n, 3) * 1.6 - 0.8
+    nrm = torch.randn(n, 3, requires_grad=True)
+    view = torch.randn(n, 3)
+    feat = torch.randn(n, 128, requires_grad=True)
+    ref.envlight.build_mips()
+    color, rad, occ = ref(pts, nrm, view, feat, None, step=10)
+    u = torch.randn_like(color)
+    ((color * u).sum() + rad.sum() + occ['occ_prob'].sum()).backward()
+    sd = {k: v for k, v in ref.state_dict().items() if not k.startswith('outer_light') and k != 'FG_LUT'}
+    grads = {k: p.grad for k, p in ref.named_parameters() if p.grad is not None and not k.startswith('outer_light')}
+    grads['__normals'] = nrm.grad
+    grads['__features'] = feat.grad
+    _save("shader.npz", state=_np(sd), inputs=_np({"points": pts, "normals": nrm, "view_dirs": view, "features": feat, "u": u}),
+          outputs=_np({"color": color, "radiance": rad, "occ_prob": occ['occ_prob'], "roughness": occ['roughness'],
+                       "reflective": occ['reflective'], "diffuse": ref.envlight.diffuse,
+                       **{f"specular{i}": s for i, s in enumerate(ref.envlight.specular)}}),
+          grads=_np(grads))
+
+
 def main():
     sys.path.insert(0, ROOT)
     from oracle import ref_shim
     ref_shim.install()
-    gen_tensosdf()
-    gen_tensoflow()
-    gen_mcshade()
+    which = sys.argv[1:] or ["tensosdf", "tensoflow", "mcshade", "shader"]
+    for name in which:
+        globals()[f"gen_{name}"]()
 
 
 if __name__ == "__main__":

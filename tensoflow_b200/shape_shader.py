@@ -1,0 +1,378 @@
+"""Shape-stage shader (reference network/fields.py:320-575 ShapeShadingNetwork) and its
+prefiltered environment light (reference network/light.py:8-122).
+
+Round-1 structure: the MLP stacks (material / indirect light / occlusion / radiance heads) run
+on the fused linear kernels, the cubemap prefilter on the cached CSR operator kernel; the
+per-sample encodings and the (direction- and level-differentiable) cube / LUT lookups are
+tensor arithmetic on the device with autograd (next: fold them into one per-sample kernel,
+see DESIGN.md).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib, ops
+from ._lib import check, ptr, stream_ptr
+from .flow import posenc
+from .material import make_predictor, run_predictor, linear_to_srgb, _ide_tables
+
+
+# ---- cube geometry (reference network/light_utils.py:24-31, renderutils/c_src/cubemap.cu:32-60) ----
+def cube_to_dir_t(face: torch.Tensor, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    one = torch.ones_like(x)
+    opts = [(one, -y, -x), (-one, -y, x), (x, one, y), (x, -one, -y), (x, -y, one), (-x, -y, -one)]
+    out = torch.stack(opts[5], -1)
+    for s in range(4, -1, -1):
+        out = torch.where((face == s).unsqueeze(-1), torch.stack(opts[s], -1), out)
+    return out
+
+
+def dir_to_face_xy(d: torch.Tensor):
+    ax = d.abs()
+    dx, dy, dz = d[..., 0], d[..., 1], d[..., 2]
+    is_x = (ax[..., 0] >= ax[..., 1]) & (ax[..., 0] >= ax[..., 2])
+    is_y = (~is_x) & (ax[..., 1] >= ax[..., 2])
+    face = torch.where(is_x, torch.where(dx >= 0, 0, 1), torch.where(is_y, torch.where(dy >= 0, 2, 3), torch.where(dz >= 0, 4, 5)))
+    m = torch.where(is_x, ax[..., 0], torch.where(is_y, ax[..., 1], ax[..., 2])).clamp_min(1e-30)
+    xs = [-dz, dz, dx, dx, dx, -dx]
+    ys = [-dy, -dy, dz, -dz, -dy, -dy]
+    x, y = xs[5], ys[5]
+    for s in range(4, -1, -1):
+        x = torch.where(face == s, xs[s], x)
+        y = torch.where(face == s, ys[s], y)
+    return face, x / m, y / m
+
+
+def cube_sample(tex: torch.Tensor, d: torch.Tensor) -> torch.Tensor:
+    """Seamless bilinear lookup (dr.texture(..., boundary_mode='cube'), reference light.py:107,135):
+    tex [6,R,R,C], d [N,3] -> [N,C]; differentiable in tex and d.  Taps that leave the face fold onto
+    the neighbouring face, the tap leaving in both axes is dropped and the weights renormalised."""
+    R = tex.shape[1]
+    face, x, y = dir_to_face_xy(d)
+    u = (x + 1.0) * 0.5 * R - 0.5
+    v = (y + 1.0) * 0.5 * R - 0.5
+    u0, v0 = torch.floor(u), torch.floor(v)
+    fu, fv = (u - u0).unsqueeze(-1), (v - v0).unsqueeze(-1)
+    u0, v0 = u0.long(), v0.long()
+    flat = tex.reshape(-1, tex.shape[-1])
+    major = face // 2
+    out, wsum = 0, 0
+    for du, dv in ((0, 0), (1, 0), (0, 1), (1, 1)):
+        iu, iv = u0 + du, v0 + dv
+        w = (fu if du else 1 - fu) * (fv if dv else 1 - fv)
+        ou, ov = (iu < 0) | (iu >= R), (iv < 0) | (iv >= R)
+        fx = 2.0 * (iu.to(d.dtype) + 0.5) / R - 1.0
+        fy = 2.0 * (iv.to(d.dtype) + 0.5) / R - 1.0
+        p = cube_to_dir_t(face, fx, fy)
+        ex = (p.abs() - 1.0).clamp_min(0.0)
+        ar = torch.arange(3, device=d.device)
+        is_major = ar[None, :] == major[:, None]
+        ex = torch.where(is_major, torch.zeros_like(ex), ex)
+        e = ex.sum(-1, keepdim=True)
+        q = torch.where(ex > 0, torch.sign(p), p)
+        q = torch.where(is_major, torch.sign(p) * (1.0 - e), q)
+        f2, x2, y2 = dir_to_face_xy(q)
+        iu2 = torch.floor((x2 + 1.0) * 0.5 * R).long().clamp(0, R - 1)
+        iv2 = torch.floor((y2 + 1.0) * 0.5 * R).long().clamp(0, R - 1)
+        fold = ou ^ ov
+        f_use = torch.where(fold, f2, face)
+        iu_use = torch.where(fold, iu2, iu.clamp(0, R - 1))
+        iv_use = torch.where(fold, iv2, iv.clamp(0, R - 1))
+        w = torch.where((ou & ov).unsqueeze(-1), torch.zeros_like(w), w)
+        out = out + flat[(f_use * R + iv_use) * R + iu_use] * w
+        wsum = wsum + w
+    return out / wsum
+
+
+def cube_sample_mip(stack: List[torch.Tensor], d: torch.Tensor, level: torch.Tensor) -> torch.Tensor:
+    """linear-mipmap-linear over a user-supplied stack (reference light.py:111-118); differentiable in
+    the textures, the direction and the level."""
+    n = len(stack)
+    lv = level.reshape(-1).clamp(0.0, float(n - 1))
+    l0 = torch.floor(lv)
+    f = (lv - l0).unsqueeze(-1)
+    l0 = l0.long()
+    l1 = (l0 + 1).clamp(max=n - 1)
+    out = 0
+    for l in range(n):
+        w = (l0 == l).unsqueeze(-1) * (1 - f) + ((l1 == l) & (l0 != l)).unsqueeze(-1) * f
+        out = out + cube_sample(stack[l], d) * w
+    return out
+
+
+def texture2d_linear_clamp(tex: torch.Tensor, uv: torch.Tensor) -> torch.Tensor:
+    """dr.texture(tex[None], uv, filter_mode='linear', boundary_mode='clamp') (reference fields.py:522):
+    tex [H,W,C], uv [N,2]; differentiable in uv."""
+    H, W, _ = tex.shape
+    x, y = uv[:, 0] * W - 0.5, uv[:, 1] * H - 0.5
+    x0, y0 = torch.floor(x), torch.floor(y)
+    fx, fy = (x - x0).unsqueeze(-1), (y - y0).unsqueeze(-1)
+    x0i, x1i = x0.long().clamp(0, W - 1), (x0.long() + 1).clamp(0, W - 1)
+    y0i, y1i = y0.long().clamp(0, H - 1), (y0.long() + 1).clamp(0, H - 1)
+    return (tex[y0i, x0i] * (1 - fx) * (1 - fy) + tex[y0i, x1i] * fx * (1 - fy)
+            + tex[y1i, x0i] * (1 - fx) * fy + tex[y1i, x1i] * fx * fy)
+
+
+_IDE = {}
+
+
+def ide_encode_rough(xyz: torch.Tensor, kappa_inv: torch.Tensor) -> torch.Tensor:
+    """Integrated directional encoding (reference utils/ref_utils.py:53-117) -> [N,72]."""
+    if xyz.device not in _IDE:
+        ml, mat = _ide_tables(5)
+        _IDE[xyz.device] = (torch.from_numpy(ml[0].astype(np.int64)).to(xyz.device), torch.from_numpy(mat).to(xyz.device),
+                            torch.from_numpy((0.5 * ml[1] * (ml[1] + 1)).astype(np.float32)).to(xyz.device))
+    m_idx, mat, sigma = _IDE[xyz.device]
+    x, y, z = xyz[:, 0:1], xyz[:, 1:2], xyz[:, 2:3]
+    zs, re, im = [torch.ones_like(z)], [torch.ones_like(x)], [torch.zeros_like(x)]
+    for _ in range(1, mat.shape[0]):
+        zs.append(zs[-1] * z)
+        re_n, im_n = re[-1] * x - im[-1] * y, re[-1] * y + im[-1] * x
+        re.append(re_n)
+        im.append(im_n)
+    vmz = torch.cat(zs, -1)
+    re, im = torch.cat(re, -1)[:, m_idx], torch.cat(im, -1)[:, m_idx]
+    att = (vmz @ mat) * torch.exp(-sigma * kappa_inv)
+    return torch.cat([re * att, im * att], -1)
+
+
+# ---- cubemap prefilter operators (reference renderutils/c_src/cubemap.cu:17-60,110-350) ----------------
+def _texel_dirs(N, device):
+    c = 2.0 * ((torch.arange(N, device=device, dtype=torch.float32) + 0.5) / N) - 1.0
+    fy, fx = torch.meshgrid(c, c, indexing="ij")
+    face = torch.arange(6, device=device)[:, None, None].expand(6, N, N)
+    return F.normalize(cube_to_dir_t(face, fx.expand(6, N, N), fy.expand(6, N, N)), dim=-1).reshape(-1, 3)
+
+
+def _pixel_area(N, device):
+    if N <= 1:
+        return torch.ones(6, device=device)
+    H = N // 2
+    i = (torch.arange(N, device=device) - H).abs().float()
+    dx = torch.atan((i + 1) / H) - torch.atan(i / H)
+    return (dx[None, :] * dx[:, None]).reshape(1, -1).repeat(6, 1).reshape(-1)
+
+
+def _ndf_cutoff(roughness: float, cutoff: float) -> float:
+    """reference renderutils/ops.py:427-438"""
+    a2 = roughness ** 4
+    ct = np.cos(np.linspace(0, np.pi / 2.0, 1000000))
+    c = np.clip(ct, 0.0, 1.0)
+    dd = (c * a2 - c) * c + 1.0
+    D = np.cumsum(a2 / (dd * dd * np.pi))
+    return float(ct[np.argmax(D >= D[-1] * cutoff)])
+
+
+class PrefilterOp:
+    """CSR operator of one prefilter pass, built once per (res, kind, roughness, cutoff)."""
+    _cache: Dict[Tuple, "PrefilterOp"] = {}
+
+    def __init__(self, res: int, kind: str, roughness: float, cutoff: float, device, chunk: int = 4096):
+        dirs = _texel_dirs(res, device)
+        area = _pixel_area(res, device)
+        rows, cols, vals = [], [], []
+        if kind == "specular":
+            cos_cut = _ndf_cutoff(roughness, cutoff)
+            a2 = (roughness * roughness) ** 2
+        for i in range(0, dirs.shape[0], chunk):
+            V = dirs[i:i + chunk]
+            LdV = V @ dirs.T
+            if kind == "diffuse":
+                w = LdV.clamp(0.0, 0.999) * area[None, :] / 3.141592
+                keep = w > 0
+            else:
+                Hh = F.normalize(dirs[None, :, :] + V[:, None, :], dim=-1, eps=1e-20)
+                VdH = (Hh * V[:, None, :]).sum(-1).clamp(0.0, 1.0)
+                dd = (VdH * a2 - VdH) * VdH + 1.0
+                w = LdV.clamp_min(0.0) * (a2 / (dd * dd * math.pi)) * area[None, :] / 4.0
+                keep = LdV >= cos_cut
+                w = torch.where(keep, w, torch.zeros_like(w))
+                w = w / w.sum(-1, keepdim=True)
+            r, c = torch.nonzero(keep, as_tuple=True)
+            rows.append(r + i); cols.append(c); vals.append(w[r, c])
+        rows, cols, vals = torch.cat(rows), torch.cat(cols), torch.cat(vals)
+        n = dirs.shape[0]
+        counts = torch.bincount(rows, minlength=n)
+        self.rowptr = torch.cat([torch.zeros(1, dtype=torch.long, device=device), torch.cumsum(counts, 0)]).to(torch.int32)
+        self.col = cols.to(torch.int32).contiguous()
+        self.val = vals.float().contiguous()
+        self.n = n
+
+    @classmethod
+    def get(cls, res, kind, roughness, cutoff, device):
+        key = (res, kind, float(roughness), float(cutoff), str(device))
+        if key not in cls._cache:
+            cls._cache[key] = PrefilterOp(res, kind, roughness, cutoff, device)
+        return cls._cache[key]
+
+
+class PrefilterFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cubemap, op: PrefilterOp):
+        x = cubemap.detach().contiguous().reshape(-1, 3)
+        y = torch.empty_like(x)
+        check(_lib.load().tf_csr_spmm3_fwd(ptr(op.rowptr), ptr(op.col), ptr(op.val), ptr(x), op.n, ptr(y), stream_ptr()), "tf_csr_spmm3_fwd")
+        ctx.op = op
+        return y.reshape(cubemap.shape)
+
+    @staticmethod
+    def backward(ctx, g):
+        op = ctx.op
+        gy = g.contiguous().reshape(-1, 3)
+        gx = torch.zeros_like(gy)
+        check(_lib.load().tf_csr_spmm3_bwd(ptr(op.rowptr), ptr(op.col), ptr(op.val), ptr(gy), op.n, ptr(gx), stream_ptr()), "tf_csr_spmm3_bwd")
+        return gx.reshape(g.shape), None
+
+
+def diffuse_cubemap(cubemap):
+    return PrefilterFunction.apply(cubemap, PrefilterOp.get(cubemap.shape[1], "diffuse", 0.0, 0.0, cubemap.device))
+
+
+def specular_cubemap(cubemap, roughness, cutoff=0.99):
+    return PrefilterFunction.apply(cubemap, PrefilterOp.get(cubemap.shape[1], "specular", roughness, cutoff, cubemap.device))
+
+
+class CubemapMip(torch.autograd.Function):
+    """reference network/light_utils.py:66-82: 2x2 average pool forward; the backward is a seamless
+    bilinear cube lookup of dout/4 at the fine texel centres (kept as the reference defines it)."""
+
+    @staticmethod
+    def forward(ctx, cubemap):
+        return F.avg_pool2d(cubemap.permute(0, 3, 1, 2), (2, 2)).permute(0, 2, 3, 1).contiguous()
+
+    @staticmethod
+    def backward(ctx, dout):
+        res = dout.shape[1] * 2
+        c = torch.linspace(-1.0 + 1.0 / res, 1.0 - 1.0 / res, res, device=dout.device)
+        gy, gx = torch.meshgrid(c, c, indexing="ij")
+        face = torch.arange(6, device=dout.device)[:, None, None].expand(6, res, res)
+        v = F.normalize(cube_to_dir_t(face, gx.expand(6, res, res), gy.expand(6, res, res)), dim=-1, eps=1e-20)
+        return cube_sample(dout * 0.25, v.reshape(-1, 3)).reshape(6, res, res, -1)
+
+
+class ShadingEnvLight(nn.Module):
+    """reference network/light.py:8-122 (the prefiltered split-sum light of the shape stage)"""
+
+    def __init__(self, device='cuda', min_res=16, max_res=128, min_roughness=0.08, max_roughness=0.5, trainable=True):
+        super().__init__()
+        self.min_res, self.max_res = min_res, max_res
+        self.min_roughness, self.max_roughness = min_roughness, max_roughness
+        self.base = nn.Parameter(torch.full((6, max_res, max_res, 3), math.log(0.5), dtype=torch.float32, device=device),
+                                 requires_grad=trainable)
+
+    def build_mips(self, cutoff=0.99):
+        self.specular = [self.base]
+        while self.specular[-1].shape[1] > self.min_res:
+            self.specular.append(CubemapMip.apply(self.specular[-1]))
+        self.diffuse = diffuse_cubemap(self.specular[-1])
+        n = len(self.specular)
+        for idx in range(n - 1):
+            r = (idx / (n - 2)) * (self.max_roughness - self.min_roughness) + self.min_roughness
+            self.specular[idx] = specular_cubemap(self.specular[idx], r, cutoff)
+        self.specular[-1] = specular_cubemap(self.specular[-1], 1.0, cutoff)
+
+    def get_mip(self, roughness):
+        n = len(self.specular)
+        lo = (torch.clamp(roughness, self.min_roughness, self.max_roughness) - self.min_roughness) / \
+            (self.max_roughness - self.min_roughness) * (n - 2)
+        hi = (torch.clamp(roughness, self.max_roughness, 1.0) - self.max_roughness) / (1.0 - self.max_roughness) + n - 2
+        return torch.where(roughness < self.max_roughness, lo, hi)
+
+    def forward(self, l, roughness=None):
+        if roughness is None:
+            return torch.exp(cube_sample(self.diffuse, l))
+        return torch.exp(cube_sample_mip(self.specular, l, self.get_mip(roughness)[..., 0]))
+
+
+def load_fg_lut(device):
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets", "fg_lut_256.npz")
+    return torch.from_numpy(np.load(p)["fg"]).to(device)
+
+
+class ShapeShadingNetwork(nn.Module):
+    default_cfg = {'human_light': False, 'sphere_direction': False, 'light_pos_freq': 8, 'inner_init': -0.95, 'light_exp_max': 0.0,
+                   'app_feats_dim': 128, 'has_radiance_field': False, 'radiance_field_step': 0, 'mat_pos_multires': -1,
+                   'device': 'cuda', 'env_res': 128, 'env_min_res': 16}
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = {**self.default_cfg, **cfg}
+        c = self.cfg
+        if c['human_light'] or c['mat_pos_multires'] != -1 or c['light_pos_freq'] != 8:
+            raise NotImplementedError("tensoflow_b200 implements the shipped shape-shader configuration")
+        dev, fd = c['device'], c['app_feats_dim']
+        if c['has_radiance_field']:
+            self.rad_mlp = make_predictor(3, fd + 3 + 27 + 3, 3, run_dim=128).to(dev)
+        self.mat_mlp = make_predictor(3, fd, 5, run_dim=128).to(dev)
+        self.register_buffer('FG_LUT', load_fg_lut(dev)[None])
+        self.envlight = ShadingEnvLight(device=dev, max_res=c['env_res'], min_res=c['env_min_res'])
+        self.inner_light = make_predictor(3, 51 + 72, 3, run_dim=128).to(dev)
+        nn.init.constant_(self.inner_light[-2].bias, np.log(0.5))
+        self.inner_weight = make_predictor(3, 51 + 39, 1, run_dim=128).to(dev)
+        nn.init.constant_(self.inner_weight[-2].bias, c['inner_init'])
+
+    def get_optparam_groups(self, lr_init_network, lr_init_envlight):
+        return [{'params': self.envlight.parameters(), 'lr': lr_init_envlight},
+                {'params': [p for n, p in self.named_parameters() if 'envlight' not in n], 'lr': lr_init_network}]
+
+    def predict_materials(self, points, feature_vectors):
+        mat = run_predictor(self.mat_mlp, feature_vectors, "sigmoid")
+        return mat[..., 4:], mat[..., 3:4], mat[..., :3]
+
+    def forward(self, points, normals, view_dirs, feature_vectors, human_poses=None, inter_results=False, step=None):
+        c = self.cfg
+        with_rad = c['has_radiance_field'] and step is not None and step > c['radiance_field_step']
+        dev = points.device
+        if points.shape[0] == 0:
+            occ_info = {'reflective': torch.zeros(0, 1, device=dev), 'occ_prob': torch.zeros(0, 1, device=dev), 'roughness': torch.zeros(0, 1, device=dev)}
+            return torch.zeros(0, 3, device=dev), (torch.zeros(0, 3, device=dev) if with_rad else None), occ_info
+        normals = F.normalize(normals, dim=-1)
+        bad = normals[:, :2].sum(dim=-1) == 0.
+        normals = torch.where(bad[:, None], torch.tensor([0.0, 1e-6, 1.0], device=dev), normals)
+        view_dirs = F.normalize(view_dirs, dim=-1)
+        reflective = torch.sum(view_dirs * normals, -1, keepdim=True) * normals * 2 - view_dirs
+        NoV = torch.sum(normals * view_dirs, -1, keepdim=True)
+        mat = run_predictor(self.mat_mlp, feature_vectors, "sigmoid")
+        albedo, roughness, metallic = mat[..., :3] * 0.77 + 0.03, mat[..., 3:4] * 0.9 + 0.09, mat[..., 4:]
+        radiance = None
+        if with_rad:
+            radiance = run_predictor(self.rad_mlp, torch.cat([feature_vectors, points, posenc(view_dirs, 4), normals], -1), "sigmoid")
+        diffuse_albedo = (1 - metallic) * albedo
+        diffuse_light = self.envlight(normals)
+        diffuse_color = diffuse_albedo * diffuse_light
+        specular_albedo = 0.04 * (1 - metallic) + metallic * albedo
+        ref_roughness = ide_encode_rough(reflective, roughness)
+        direct_light = self.envlight(reflective, roughness)
+        pts = posenc(points, 8)
+        indirect_light = run_predictor(self.inner_light, torch.cat([pts, ref_roughness], -1), "exp", c['light_exp_max'])
+        occ_prob = run_predictor(self.inner_weight, torch.cat([pts.detach(), posenc(reflective, 6).detach()], -1), "none") * 0.5 + 0.5
+        occ_ = torch.clamp(occ_prob, min=0, max=1)
+        specular_light = indirect_light * occ_ + direct_light * (1 - occ_)
+        indirect = indirect_light * occ_
+        fg_uv = torch.cat([torch.clamp(NoV, min=0.0, max=1.0), torch.clamp(roughness, min=0.0, max=1.0)], -1)
+        fg = texture2d_linear_clamp(self.FG_LUT[0], fg_uv)
+        specular_ref = specular_albedo * fg[:, 0:1] + fg[:, 1:2]
+        specular_color = specular_ref * specular_light
+        color = torch.clamp(linear_to_srgb(diffuse_color + specular_color), min=0.0, max=1.0)
+        occ_info = {'reflective': reflective, 'occ_prob': occ_prob, 'roughness': roughness}
+        if inter_results:
+            inter = {
+                'specular_albedo': specular_albedo, 'specular_ref': torch.clamp(specular_ref, min=0.0, max=1.0),
+                'specular_direct_light': direct_light,
+                'specular_light': torch.clamp(linear_to_srgb(specular_light), min=0.0, max=1.0),
+                'specular_color': torch.clamp(linear_to_srgb(specular_color), min=0.0, max=1.0),
+                'diffuse_albedo': diffuse_albedo, 'diffuse_light': torch.clamp(linear_to_srgb(diffuse_light), min=0.0, max=1.0),
+                'diffuse_color': torch.clamp(linear_to_srgb(diffuse_color), min=0.0, max=1.0),
+                'metallic': metallic, 'roughness': roughness, 'albedo': albedo,
+                'occ_prob': torch.clamp(occ_prob, max=1.0, min=0.0), 'indirect_light': indirect,
+            }
+            return color, occ_info, inter
+        return color, radiance, occ_info

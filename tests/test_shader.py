@@ -1,0 +1,83 @@
+"""Shape-stage shader + prefiltered env light: oracle vs reference golden (CPU) and the CUDA
+product vs the same reference outputs (GPU).  Fixture: tests/golden/shader.npz, produced by
+oracle/gen_golden.py from the reference's own ShapeShadingNetwork / EnvLight."""
+import pytest
+import torch
+
+from conftest import rel_err
+from test_golden import load
+from oracle import torch_oracle_shader as SH
+
+
+def _oracle(g, dtype=torch.float32):
+    m = SH.ShapeShadingNetwork(has_radiance_field=True, env_res=16, env_min_res=4, dtype=dtype)
+    res = m.load_state_dict({k: v.to(dtype) for k, v in g["state"].items()}, strict=False)
+    assert not res.unexpected_keys and res.missing_keys == ["FG_LUT"], res
+    return m
+
+
+def _run(m, i, dt, dev="cpu"):
+    nrm = i["normals"].detach().clone().to(dev, dt).requires_grad_()
+    feat = i["features"].detach().clone().to(dev, dt).requires_grad_()
+    return nrm, feat
+
+
+def test_oracle_shader_golden():
+    g = load("shader.npz")
+    m = _oracle(g)
+    i, o = g["inputs"], g["outputs"]
+    m.envlight.build_mips()
+    assert rel_err(m.envlight.diffuse, o["diffuse"]) < 1e-6
+    for k, s in enumerate(m.envlight.specular):
+        assert rel_err(s, o[f"specular{k}"]) < 1e-6
+    nrm, feat = _run(m, i, torch.float32)
+    color, rad, occ = m(i["points"], nrm, i["view_dirs"], feat, with_radiance=True)
+    assert rel_err(color, o["color"]) < 1e-5 and rel_err(rad, o["radiance"]) < 1e-5
+    assert rel_err(occ["occ_prob"], o["occ_prob"]) < 1e-5 and rel_err(occ["roughness"], o["roughness"]) < 1e-6
+    ((color * i["u"]).sum() + rad.sum() + occ["occ_prob"].sum()).backward()
+    assert rel_err(nrm.grad, g["grads"]["__normals"]) < 1e-4
+    assert rel_err(feat.grad, g["grads"]["__features"]) < 1e-4
+    for n, p in m.named_parameters():
+        if n in g["grads"]:
+            assert rel_err(p.grad, g["grads"][n]) < 1e-4, n
+
+
+@pytest.mark.gpu
+def test_cuda_shader_golden():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from tensoflow_b200.shape_shader import ShapeShadingNetwork
+    dev = torch.device("cuda:0")
+    g = load("shader.npz")
+    i, o = g["inputs"], g["outputs"]
+    m = ShapeShadingNetwork(dict(has_radiance_field=True, radiance_field_step=0, env_res=16, env_min_res=4, device=dev))
+    res = m.load_state_dict(g["state"], strict=False)
+    assert not res.unexpected_keys and res.missing_keys == ["FG_LUT"], res
+    m64 = _oracle(g, torch.float64)
+    m.envlight.build_mips()
+    m64.envlight.build_mips()
+    assert rel_err(m.envlight.diffuse, o["diffuse"]) < 1e-5
+    for k, s in enumerate(m.envlight.specular):
+        assert rel_err(s, o[f"specular{k}"]) < 1e-5
+    nrm, feat = _run(m, i, torch.float32, dev)
+    color, rad, occ = m(i["points"].to(dev), nrm, i["view_dirs"].to(dev), feat, None, step=10)
+    n64, f64 = _run(m64, i, torch.float64)
+    c64, r64, o64 = m64(i["points"].double(), n64, i["view_dirs"].double(), f64, with_radiance=True)
+
+    def close(got, ref32, ref64, tol, what):
+        e, e_ref = rel_err(got, ref64), rel_err(ref32, ref64)
+        assert e <= max(tol, 4 * e_ref), f"{what}: rel err {e:.3e} (reference fp32 vs fp64 oracle {e_ref:.3e})"
+
+    close(color, o["color"], c64, 1e-4, "color")
+    close(rad, o["radiance"], r64, 1e-4, "radiance")
+    close(occ["occ_prob"], o["occ_prob"], o64["occ_prob"], 1e-4, "occ_prob")
+    close(occ["roughness"], o["roughness"], o64["roughness"], 1e-4, "roughness")
+    ((color * i["u"].to(dev)).sum() + rad.sum() + occ["occ_prob"].sum()).backward()
+    ((c64 * i["u"].double()).sum() + r64.sum() + o64["occ_prob"].sum()).backward()
+    close(nrm.grad, g["grads"]["__normals"], n64.grad, 1e-3, "d normals")
+    close(feat.grad, g["grads"]["__features"], f64.grad, 1e-3, "d features")
+    p64 = dict(m64.named_parameters())
+    for n, p in m.named_parameters():
+        if n in g["grads"]:
+            assert p.grad is not None, n
+            close(p.grad, g["grads"][n], p64[n].grad, 1e-3, f"d {n}")
