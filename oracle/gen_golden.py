@@ -182,11 +182,54 @@ def gen_shader():
           grads=_np(grads))
 
 
+RENDERER_CFG = dict(gridSize=[32, 32, 32], sdf_n_comp=8, sdf_dim=32, app_dim=128, max_levels=1, predict_BG=False,
+                    has_radiance_field=True, radiance_field_step=100, occ_loss_step=0, occ_loss_max_pn=100000, n_samples=16,
+                    n_importance=16, up_sample_steps=4, sdf_multires=0)
+
+
+def renderer_total_loss(o):
+    return (o['ray_rgb'].sum() + o['radiance'].sum() * 0.5 + o['gradient_error'].mean() * 0.1 + o['loss_sparse']
+            + o['loss_hessian'] * 1e-3 + o['loss_tv_sdf'] + o['loss_occ'].sum())
+
+
+def gen_renderer():
+    """ShapeRenderer.render (hierarchical sampler + render_core + shader + losses), train mode."""
+    import network.shapeRenderer as RS
+    import network.light as RL
+    from tensoflow_b200 import synthetic
+    torch.manual_seed(4)
+    ref = RS.ShapeRenderer(dict(device='cpu', **RENDERER_CFG), training=False)
+    ref.color_network.envlight = RL.EnvLight(trainable=True, max_res=16, min_res=4)
+    with torch.no_grad():
+        ref.color_network.envlight.base.add_(0.5 * torch.randn_like(ref.color_network.envlight.base))
+        for p in list(ref.sdf_network.sdf_plane) + list(ref.sdf_network.sdf_line):
+            p.add_(0.01 * torch.randn_like(p))
+    R = 48
+    rays = synthetic.make_rays(R, seed=5)
+    batch = dict(rays_o=rays['rays_o'], rays_d=rays['dirs'], dirs=rays['dirs'], radiis=rays['radiis'], rays_cos=rays['rays_cos'])
+    near, far = ref.near_far_from_sphere(batch['rays_o'], batch['dirs'])
+    t_rand = torch.rand(R, 1)
+    orig = torch.rand
+    torch.rand = lambda *a, **k: t_rand
+    try:
+        ref.color_network.envlight.build_mips()
+        out = ref.render(batch, near, far, torch.zeros(R, 3, 4), -1, 0.7, is_train=True, step=30000)
+    finally:
+        torch.rand = orig
+    renderer_total_loss(out).backward()
+    keys = ['ray_rgb', 'acc', 'normal', 'radiance', 'roughness_weights', 'gradient_error', 'loss_sparse', 'loss_hessian', 'std',
+            'loss_tv_sdf', 'loss_occ']
+    sd = {k: v for k, v in ref.state_dict().items() if 'gaussian' not in k and 'outer_light' not in k and 'FG_LUT' not in k}
+    _save("renderer.npz", state=_np(sd), inputs=_np({**batch, "near": near, "far": far, "t_rand": t_rand}),
+          outputs=_np({**{k: torch.as_tensor(out[k]) for k in keys}, "sample_num": torch.tensor(out['sample_num'])}),
+          grads=_np({k: p.grad for k, p in ref.named_parameters() if p.grad is not None and 'outer_light' not in k}))
+
+
 def main():
     sys.path.insert(0, ROOT)
     from oracle import ref_shim
     ref_shim.install()
-    which = sys.argv[1:] or ["tensosdf", "tensoflow", "mcshade", "shader"]
+    which = sys.argv[1:] or ["tensosdf", "tensoflow", "mcshade", "shader", "renderer"]
     for name in which:
         globals()[f"gen_{name}"]()
 

@@ -82,3 +82,401 @@ def render_core(field, variance: torch.Tensor, color_fn: Callable, rays_o, dirs,
         res['hessian'] = hess
         res['std'] = torch.mean(1 / torch.exp(variance * 10.0).clip(1e-6, 1e6))
     return res
+
+
+# ======================================================================================
+# Full shape-stage orchestration (reference network/shapeRenderer.py:79-1326).  Dataset /
+# image IO is out of scope: ray batches are handed in as tensors.
+# ======================================================================================
+def sample_pdf(bins, weights, n_samples, det=False):
+    """reference utils/network_utils.py:117-147"""
+    weights = weights + 1e-5
+    pdf = weights / torch.sum(weights, -1, keepdim=True)
+    cdf = torch.cumsum(pdf, -1)
+    cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], -1)
+    if det:
+        u = torch.linspace(0. + 0.5 / n_samples, 1. - 0.5 / n_samples, steps=n_samples, device=bins.device)
+        u = u.expand(list(cdf.shape[:-1]) + [n_samples])
+    else:
+        u = torch.rand(list(cdf.shape[:-1]) + [n_samples], device=bins.device)
+    u = u.contiguous()
+    inds = torch.searchsorted(cdf, u, right=True)
+    below = torch.max(torch.zeros_like(inds - 1), inds - 1)
+    above = torch.min((cdf.shape[-1] - 1) * torch.ones_like(inds), inds)
+    inds_g = torch.stack([below, above], -1)
+    matched_shape = [inds_g.shape[0], inds_g.shape[1], cdf.shape[-1]]
+    cdf_g = torch.gather(cdf.unsqueeze(1).expand(matched_shape), 2, inds_g)
+    bins_g = torch.gather(bins.unsqueeze(1).expand(matched_shape), 2, inds_g)
+    denom = (cdf_g[..., 1] - cdf_g[..., 0])
+    denom = torch.where(denom < 1e-5, torch.ones_like(denom), denom)
+    t = (u - cdf_g[..., 0]) / denom
+    return bins_g[..., 0] + t * (bins_g[..., 1] - bins_g[..., 0])
+
+
+def get_sphere_intersection(pts, dirs):
+    """reference utils/network_utils.py:108-114"""
+    dtx = torch.sum(pts * dirs, dim=-1, keepdim=True)
+    xtx = torch.sum(pts ** 2, dim=-1, keepdim=True)
+    dist = dtx ** 2 - xtx + 1
+    return -dtx + torch.sqrt(dist + 1e-6)
+
+
+def get_weights(sdf_fun, inv_fun, z_vals, origins, dirs):
+    """reference utils/network_utils.py:149-170"""
+    points = z_vals.unsqueeze(-1) * dirs.unsqueeze(-2) + origins.unsqueeze(-2)
+    inv_s = inv_fun(points[:, :-1, :])[..., 0]
+    pn, sn = points.shape[:2]
+    sdf = sdf_fun(points.reshape(-1, 3)).reshape(pn, sn, -1)[..., 0]
+    prev_sdf, next_sdf = sdf[:, :-1], sdf[:, 1:]
+    prev_z, next_z = z_vals[:, :-1], z_vals[:, 1:]
+    mid_sdf = (prev_sdf + next_sdf) * 0.5
+    cos_val = (next_sdf - prev_sdf) / (next_z - prev_z + 1e-5)
+    surface_mask = (cos_val < 0)
+    cos_val = torch.clamp(cos_val, max=0)
+    dist = next_z - prev_z
+    prev_cdf = torch.sigmoid((mid_sdf - cos_val * dist * 0.5) * inv_s)
+    next_cdf = torch.sigmoid((mid_sdf + cos_val * dist * 0.5) * inv_s)
+    alpha = (prev_cdf - next_cdf + 1e-5) / (prev_cdf + 1e-5) * surface_mask.float()
+    weights = alpha * torch.cumprod(torch.cat([torch.ones([alpha.shape[0], 1], device=alpha.device), 1. - alpha + 1e-7], -1), -1)[:, :-1]
+    mid_sdf = torch.where(surface_mask, mid_sdf, torch.full_like(mid_sdf, -1.0))
+    return weights, mid_sdf
+
+
+def get_intersection(sdf_fun, inv_fun, pts, dirs, sn0=128, sn1=9):
+    """reference utils/network_utils.py:172-202 (secondary-ray occlusion probe, no_grad)"""
+    dev = pts.device
+    inside = torch.norm(pts, dim=-1) < 0.999
+    pn = pts.shape[0]
+    hit_z = torch.zeros([pn, sn1 - 1], device=dev)
+    hit_w = torch.zeros([pn, sn1 - 1], device=dev)
+    hit_sdf = -torch.ones([pn, sn1 - 1], device=dev)
+    if torch.sum(inside) > 0:
+        p, d = pts[inside], dirs[inside]
+        max_dist = get_sphere_intersection(p, d)
+        with torch.no_grad():
+            z = max_dist * torch.linspace(0, 1, sn0, device=dev).unsqueeze(0)
+            w, _ = get_weights(sdf_fun, inv_fun, z, p, d)
+            z_new = sample_pdf(z, w, sn1, True)
+            w, mid_sdf = get_weights(sdf_fun, inv_fun, z_new, p, d)
+            z_mid = (z_new[:, 1:] + z_new[:, :-1]) * 0.5
+        hit_z[inside], hit_w[inside], hit_sdf[inside] = z_mid, w, mid_sdf
+    return hit_z, hit_w, hit_sdf
+
+
+class AlphaGridMask(torch.nn.Module):
+    """reference shapeRenderer.py:79-97"""
+
+    def __init__(self, device, aabb, alpha_volume):
+        super().__init__()
+        self.device = device
+        self.aabb = aabb.to(device)
+        self.aabbSize = self.aabb[1] - self.aabb[0]
+        self.invgridSize = 1.0 / self.aabbSize * 2
+        self.alpha_volume = alpha_volume.view(1, 1, *alpha_volume.shape[-3:])
+
+    def sample_alpha(self, xyz_sampled):
+        xyz = (xyz_sampled - self.aabb[0]) * self.invgridSize - 1
+        return F.grid_sample(self.alpha_volume, xyz.view(1, -1, 1, 1, 3), align_corners=True).view(-1)
+
+
+class ShapeRenderer(torch.nn.Module):
+    default_cfg = {
+        'std_act': 'exp', 'inv_s_init': 0.3, 'freeze_inv_s_step': None, 'n_samples': 64, 'n_importance': 64, 'up_sample_steps': 4,
+        'perturb': 1.0, 'anneal_end': 50000, 'train_ray_num': 1024, 'test_ray_num': 2048, 'clip_sample_variance': True,
+        'rgb_loss': 'charbonier', 'apply_occ_loss': True, 'apply_tv_loss': True, 'apply_sparse_loss': True, 'apply_hessian_loss': True,
+        'apply_gaussian_loss': False, 'occ_loss_step': 20000, 'occ_loss_max_pn': 2048, 'occ_sdf_thresh': 0.01, 'gaussianLoss_step': 20000,
+        'device': 'cuda', 'gridSize': [512, 512, 512], 'aabb': [[-1.0, -1.0, -1.0], [1.0, 1.0, 1.0]], 'step_ratio': 0.5,
+        'alphaMask_thres': 0.0001, 'sdf_n_comp': 16, 'sdf_dim': 128, 'app_dim': 128, 'sdf_multires': 0, 'max_levels': 1,
+        'has_radiance_field': False, 'radiance_field_step': 0, 'predict_BG': False, 'isBGWhite': True, 'apply_mask_loss': False,
+        'mul_length': 10, 'use_occ_grid': False, 'shader_config': {},
+    }
+
+    def __init__(self, cfg, training=True):
+        super().__init__()
+        from .fields import TensoSDF, SingleVarianceNetwork, TVLoss
+        from .shape_shader import ShapeShadingNetwork
+        self.cfg = {**self.default_cfg, **cfg}
+        c = self.cfg
+        if c['predict_BG']:
+            raise NotImplementedError("predict_BG raises in the reference too (shapeRenderer.py:1109-1110)")
+        if c['use_occ_grid']:
+            raise NotImplementedError("occupancy-grid marching is the next row (SURVEY.md 8f-2); hand packed samples to render_core")
+        self.device = c['device']
+        self.aabb = torch.tensor(c['aabb'].cpu().tolist() if isinstance(c['aabb'], torch.Tensor) else c['aabb'], device=self.device)
+        self.radius = (self.aabb[1] - torch.mean(self.aabb, axis=0)).mean().float()
+        self.alphaMask = None
+        self.occ_grid = None
+        self.update_stepSize(torch.tensor(c['gridSize']), c['max_levels'])
+        self.sdf_network = TensoSDF(self.gridSize, self.aabb, device=self.device, init_n_levels=self.max_levels, sdf_n_comp=c['sdf_n_comp'],
+                                    sdf_dim=c['sdf_dim'], app_dim=c['app_dim'], sdf_multires=c['sdf_multires'])
+        self.tv_reg = TVLoss()
+        self.deviation_network = SingleVarianceNetwork(init_val=c['inv_s_init'], activation=c['std_act']).to(self.device)
+        shader_cfg = {'has_radiance_field': c['has_radiance_field'], 'radiance_field_step': c['radiance_field_step'],
+                      'app_feats_dim': c['app_dim'], 'device': self.device, **c['shader_config']}
+        self.color_network = ShapeShadingNetwork(shader_cfg)
+        self.sdf_inter_fun = lambda x: self.sdf_network.sdf(x, None)
+        self.train_batch = None
+
+    # ---- bookkeeping ------------------------------------------------------------------------
+    def update_stepSize(self, gridSize, max_levels):
+        """reference shapeRenderer.py:243-254"""
+        self.aabbSize = self.aabb[1] - self.aabb[0]
+        self.gridSize = torch.tensor(gridSize.cpu().tolist(), dtype=torch.int32).to(self.device)
+        self.max_levels = max_levels
+        self.units = self.aabbSize / (self.gridSize - 1)
+        self.stepSize = torch.mean(self.units) * self.cfg['step_ratio']
+        self.base_radii = self.aabbSize[0] / 2.0 / self.gridSize[0]
+
+    def get_train_opt_params(self, lr_xyz, lr_net, lr_env=0.01):
+        g = self.sdf_network.get_optparam_groups(lr_xyz, lr_net)
+        g += [{'params': self.deviation_network.parameters(), 'lr': lr_net}]
+        g += self.color_network.get_optparam_groups(lr_net, lr_env)
+        return g
+
+    def ckpt_to_save(self):
+        return {'network_state_dict': self.state_dict(), 'gridSize': self.gridSize.tolist(), 'max_levels': self.max_levels}
+
+    def load_ckpt(self, ckpt):
+        self.load_state_dict(ckpt['network_state_dict'], strict=False)
+
+    def upsample_sdf_grid(self, res_target):
+        res, n_levels = self.sdf_network.upsample_volume_grid(torch.as_tensor(res_target))
+        self.update_stepSize(res, n_levels)
+
+    def get_anneal_val(self, step):
+        return 1.0 if self.cfg['anneal_end'] < 0 else float(min(1.0, step / self.cfg['anneal_end']))
+
+    def set_train_batch(self, batch: Dict[str, torch.Tensor]):
+        """rays_o, rays_d, dirs, radiis, rays_cos, rgbs, human_poses (host tensors, like the reference's CPU-resident batch)"""
+        self.train_batch, self.train_batch_i, self.tbn = batch, 0, batch['rays_o'].shape[0]
+
+    # ---- sampling (reference shapeRenderer.py:820-932) -----------------------------------------
+    @staticmethod
+    def upsample(rays_o, rays_d, z_vals, sdf, n_importance, inv_s):
+        batch_size, n_samples = z_vals.shape
+        pts = rays_o[:, None, :] + rays_d[:, None, :] * z_vals[..., :, None]
+        radius = torch.linalg.norm(pts, ord=2, dim=-1, keepdim=False)
+        inside_sphere = (radius[:, :-1] < 1.0) | (radius[:, 1:] < 1.0)
+        sdf = sdf.reshape(batch_size, n_samples)
+        prev_sdf, next_sdf = sdf[:, :-1], sdf[:, 1:]
+        prev_z, next_z = z_vals[:, :-1], z_vals[:, 1:]
+        mid_sdf = (prev_sdf + next_sdf) * 0.5
+        cos_val = (next_sdf - prev_sdf) / (next_z - prev_z + 1e-5)
+        prev_cos = torch.cat([torch.zeros([batch_size, 1], device=z_vals.device), cos_val[:, :-1]], dim=-1)
+        cos_val, _ = torch.min(torch.stack([prev_cos, cos_val], dim=-1), dim=-1, keepdim=False)
+        cos_val = cos_val.clip(-1e3, 0.0) * inside_sphere
+        dist = next_z - prev_z
+        prev_cdf = torch.sigmoid((mid_sdf - cos_val * dist * 0.5) * inv_s)
+        next_cdf = torch.sigmoid((mid_sdf + cos_val * dist * 0.5) * inv_s)
+        alpha = (prev_cdf - next_cdf + 1e-5) / (prev_cdf + 1e-5)
+        weights = alpha * torch.cumprod(torch.cat([torch.ones([batch_size, 1], device=z_vals.device), 1. - alpha + 1e-7], -1), -1)[:, :-1]
+        return sample_pdf(z_vals, weights, n_importance, det=True).detach()
+
+    def cat_z_vals(self, rays_o, rays_d, z_vals, new_z_vals, sdf, last=False, radiis=None, rays_cos=None):
+        batch_size, n_samples = z_vals.shape
+        _, n_importance = new_z_vals.shape
+        pts = rays_o[:, None, :] + rays_d[:, None, :] * new_z_vals[..., :, None]
+        ball = compute_ball_radii(new_z_vals[..., None], radiis[..., None, :], rays_cos[..., None, :])
+        level = torch.log2(ball / self.base_radii)
+        z_vals = torch.cat([z_vals, new_z_vals], dim=-1)
+        z_vals, index = torch.sort(z_vals, dim=-1)
+        if not last:
+            new_sdf = self.sdf_network.sdf(pts.reshape(-1, 3), level).reshape(batch_size, n_importance)
+            sdf = torch.cat([sdf, new_sdf], dim=-1)
+            sdf = torch.gather(sdf, 1, index)
+        return z_vals, sdf
+
+    def sample_ray(self, rays_o, dirs, near, far, perturb, radiis=None, rays_cos=None, t_rand=None):
+        c = self.cfg
+        n_samples, n_importance, up_sample_steps = c['n_samples'], c['n_importance'], c['up_sample_steps']
+        batch_size = len(rays_o)
+        dev = rays_o.device
+        t_vals = torch.linspace(0.0, 1.0, n_samples, device=dev)
+        vec = torch.where(dirs == 0, torch.full_like(dirs, 1e-6), dirs)
+        rate_a = (self.aabb[1] - rays_o) / vec
+        rate_b = (self.aabb[0] - rays_o) / vec
+        t_min = torch.minimum(rate_a, rate_b).amax(-1).clamp(min=near[..., 0], max=far[..., 0]).unsqueeze(-1)
+        t_max = torch.maximum(rate_a, rate_b).amin(-1).clamp(min=near[..., 0], max=far[..., 0]).unsqueeze(-1)
+        t_vals = t_min + (t_max - t_min) * t_vals[None, :]
+        if perturb > 0:
+            if t_rand is None:
+                t_rand = torch.rand([batch_size, 1], device=dev)
+            t_vals = t_vals + (t_rand - 0.5) * 2.0 / n_samples
+        if n_importance > 0:
+            with torch.no_grad():
+                pts = rays_o[:, None, :] + dirs[:, None, :] * t_vals[..., :, None]
+                ball = compute_ball_radii(t_vals[..., :, None], radiis[:, None, :], rays_cos[:, None, :])
+                level = torch.log2(ball / self.base_radii)
+                sdf = self.sdf_network.sdf(pts.reshape(-1, 3), level.reshape(-1, 1)).reshape(batch_size, n_samples)
+                for i in range(up_sample_steps):
+                    rn, sn = t_vals.shape
+                    if c['clip_sample_variance']:
+                        inv_s = self.deviation_network(torch.empty([1, 3], device=dev)).expand(rn, sn - 1)
+                        inv_s = torch.clamp(inv_s, max=64 * 2 ** i)
+                    else:
+                        inv_s = torch.ones(rn, sn - 1, device=dev) * 64 * 2 ** i
+                    new_t = self.upsample(rays_o, dirs, t_vals, sdf, n_importance // up_sample_steps, inv_s)
+                    t_vals, sdf = self.cat_z_vals(rays_o, dirs, t_vals, new_t, sdf, last=(i + 1 == up_sample_steps), radiis=radiis, rays_cos=rays_cos)
+        dists = t_vals[..., 1:] - t_vals[..., :-1]
+        dists = torch.cat([dists, dists[..., -1:]], -1)
+        mid_t = t_vals + dists * 0.5
+        t_starts, t_ends = t_vals, t_vals + dists
+        ray_indices = torch.arange(batch_size, device=dev)[:, None].expand(batch_size, t_vals.shape[1])
+        points = rays_o.unsqueeze(-2) + dirs.unsqueeze(-2) * mid_t.unsqueeze(-1)
+        inner = ~((self.aabb[0] > points) | (points > self.aabb[1])).any(dim=-1)
+        return t_starts[inner], t_ends[inner], ray_indices[inner]
+
+    # ---- occlusion loss (reference shapeRenderer.py:1027-1103) ------------------------------------
+    def compute_occ_loss(self, occ_info, points, sdf, gradients, dirs, step, perm=None):
+        c = self.cfg
+        if step < c['occ_loss_step']:
+            return torch.zeros(1, device=points.device)
+        occ_prob, reflective = occ_info['occ_prob'], occ_info['reflective']
+        inner = ~((self.aabb[0] > points) | (points > self.aabb[1])).any(dim=-1)
+        mask = inner & (torch.sum(gradients * dirs, -1) < 0) & (torch.abs(sdf) < c['occ_sdf_thresh'])
+        if torch.sum(mask) > c['occ_loss_max_pn']:
+            indices = torch.nonzero(mask)[:, 0]
+            idx = torch.randperm(indices.shape[0], device=points.device) if perm is None else perm
+            indices = indices[idx[:c['occ_loss_max_pn']]]
+            mask = torch.zeros_like(mask)
+            mask[indices] = 1
+        if torch.sum(mask) > 0:
+            _, inter_prob, _ = get_intersection(self.sdf_inter_fun, self.deviation_network, points[mask], reflective[mask], sn0=64, sn1=16)
+            return F.l1_loss(occ_prob[mask], torch.sum(inter_prob, -1, keepdim=True))
+        return torch.zeros(1, device=points.device)
+
+    # ---- render (reference shapeRenderer.py:934-963, 1105-1277) --------------------------------------
+    def render(self, ray_batch, near, far, human_poses=None, perturb_overwrite=-1, cos_anneal_ratio=0.0, is_train=True, step=None,
+               t_rand=None):
+        perturb = self.cfg['perturb'] if perturb_overwrite < 0 else perturb_overwrite
+        rays_o, rays_d, dirs, radiis, rays_cos = (ray_batch[k] for k in ('rays_o', 'rays_d', 'dirs', 'radiis', 'rays_cos'))
+        t_starts, t_ends, ray_indices = self.sample_ray(rays_o, dirs, near, far, perturb, radiis=radiis, rays_cos=rays_cos, t_rand=t_rand)
+        return self.render_core(rays_o, rays_d, dirs, radiis, rays_cos, t_starts, t_ends, ray_indices, human_poses,
+                                cos_anneal_ratio=cos_anneal_ratio, step=step, is_train=is_train)
+
+    def render_core(self, rays_o, rays_d, viewdirs, radiis, rays_cos, t_starts, t_ends, ray_indices, human_poses=None,
+                    cos_anneal_ratio=0.0, step=None, is_train=True):
+        c = self.cfg
+        batch_size = rays_o.shape[0]
+        dev = rays_o.device
+        mid_t = (t_starts + t_ends) * 0.5
+        dists = t_ends - t_starts
+        points = rays_o[ray_indices] + viewdirs[ray_indices] * mid_t[:, None]
+        if self.alphaMask is not None:
+            keep = self.alphaMask.sample_alpha(points) > 0
+            ray_indices, mid_t, points, dists = ray_indices[keep], mid_t[keep], points[keep], dists[keep]
+        N = ray_indices.shape[0]
+        viewdir = viewdirs[ray_indices]
+        ball = compute_ball_radii(mid_t[:, None], radiis[ray_indices], rays_cos[ray_indices])
+        levels = torch.log2(ball / self.base_radii)
+        variance = self.deviation_network.variance
+        train_var = not (c['freeze_inv_s_step'] is not None and step < c['freeze_inv_s_step'])
+        sdf, feature_vector, gradients, hessian = self.sdf_network.stencil(points, levels)
+        valid_normals = F.normalize(gradients, dim=-1)
+        with_rad = c['has_radiance_field'] and step > c['radiance_field_step']
+        sampled_color, sampled_radiance, occ_info = self.color_network(points, valid_normals, -viewdir, feature_vector, None, step=step)
+        vals = [sampled_color, gradients]
+        if with_rad:
+            vals += [sampled_radiance, occ_info['roughness']]
+        offsets = ray_offsets_from_indices(ray_indices, batch_size)
+        alpha, weights, acc, out = ops.NeusCompositeFunction.apply(sdf, gradients, dists, viewdirs, offsets, variance,
+                                                                   float(cos_anneal_ratio), torch.cat(vals, -1), train_var)
+        acc_map = acc[:, None]
+        color = out[:, :3] + (1 - acc_map) if c['isBGWhite'] else out[:, :3]
+        outputs = {'ray_rgb': color, 'gradient_error': (torch.linalg.norm(gradients, ord=2, dim=-1) - 1.0) ** 2, 'acc': acc_map,
+                   'sample_num': N / batch_size}
+        up = torch.tensor([0.0, 0.0, 1.0], device=dev)
+        outputs['normal'] = F.normalize(out[:, 3:6] * acc_map + (1. - acc_map) * up, dim=-1)
+        if with_rad:
+            outputs['radiance'] = out[:, 6:9] + (1 - acc_map) if c['isBGWhite'] else out[:, 6:9]
+            outputs['roughness_weights'] = out[:, 9].clone().detach()
+        inv_s = torch.exp(variance * 10.0).clip(1e-6, 1e6)
+        outputs['std'] = torch.mean(1 / inv_s).reshape(()) if N > 0 else torch.zeros(1, device=dev)
+        if step is not None and step < 1000:
+            outputs['sdf_pts'], outputs['sdf_vals'] = (points, sdf) if N > 0 else (torch.zeros(1, device=dev), torch.zeros(1, device=dev))
+        if c['apply_occ_loss']:
+            outputs['loss_occ'] = self.compute_occ_loss(occ_info, points, sdf, valid_normals, viewdir, step) if N > 0 else torch.zeros(1, device=dev)
+        if c['apply_gaussian_loss'] and step > c['gaussianLoss_step']:
+            outputs['loss_gaussian'] = self.sdf_network.grid_gaussian_loss() if N > 0 else torch.zeros(1, device=dev)
+        if c['apply_tv_loss']:
+            outputs['loss_tv_sdf'] = self.sdf_network.TV_loss_sdf(self.tv_reg)
+        if c['apply_sparse_loss']:
+            outputs['loss_sparse'] = torch.exp(-20. * sdf.abs()).mean() if N > 0 else torch.zeros(1, device=dev)
+        if c['apply_hessian_loss']:
+            outputs['loss_hessian'] = hessian.abs().mean() if (is_train and N > 0) else torch.zeros(1, device=dev)
+        outputs.update({'_sdf': sdf, '_alpha': alpha, '_weights': weights})
+        return outputs
+
+    def compute_rgb_loss(self, rgb_pr, rgb_gt):
+        """reference shapeRenderer.py:796-808"""
+        kind = self.cfg['rgb_loss']
+        if kind == 'l2':
+            return torch.sum((rgb_pr - rgb_gt) ** 2, -1)
+        if kind == 'l1':
+            return torch.sum(F.l1_loss(rgb_pr, rgb_gt, reduction='none'), -1)
+        if kind == 'smooth_l1':
+            return torch.sum(F.smooth_l1_loss(rgb_pr, rgb_gt, reduction='none', beta=0.25), -1)
+        if kind == 'charbonier':
+            return charbonnier(rgb_pr, rgb_gt)
+        raise NotImplementedError
+
+    def train_step(self, step):
+        """reference shapeRenderer.py:777-794: slice the host batch, H2D, render, losses."""
+        rn = self.cfg['train_ray_num']
+        b = {k: v[self.train_batch_i:self.train_batch_i + rn].to(self.device, non_blocking=True) for k, v in self.train_batch.items()}
+        self.train_batch_i += rn
+        if self.train_batch_i + rn >= self.tbn:
+            self.train_batch_i = 0
+        near, far = near_far_from_sphere(b['rays_o'], b['dirs'], self.radius)
+        outputs = self.render(b, near, far, b.get('human_poses'), -1, self.get_anneal_val(step), is_train=True, step=step)
+        outputs['loss_rgb'] = self.compute_rgb_loss(outputs['ray_rgb'], b['rgbs'])
+        outputs['psnr'] = 20 * torch.log10(1.0 / torch.sqrt(F.mse_loss(outputs['ray_rgb'], b['rgbs'])))
+        if self.cfg['has_radiance_field'] and step > self.cfg['radiance_field_step']:
+            outputs['loss_radiance'] = self.compute_rgb_loss(outputs['radiance'], b['rgbs']) * outputs['roughness_weights']
+            outputs['loss_rgb'] = outputs['loss_rgb'] * (1.0 - outputs['roughness_weights'])
+        if self.cfg['apply_mask_loss']:
+            outputs['loss_mask'] = F.binary_cross_entropy(outputs['acc'].clip(1e-3, 1.0 - 1e-3), (b['masks'] > 0.5).float())
+        return outputs
+
+    def forward(self, data):
+        """reference shapeRenderer.py:1279-1306 (training branch)"""
+        self.color_network.envlight.build_mips()
+        return self.train_step(data['step'])
+
+    # ---- alpha mask (reference shapeRenderer.py:257-325) --------------------------------------------
+    @torch.no_grad()
+    def compute_grid_alpha(self, xyz_locs, length):
+        if self.alphaMask is not None:
+            alpha_mask = self.alphaMask.sample_alpha(xyz_locs) > 0
+        else:
+            alpha_mask = torch.ones_like(xyz_locs[:, 0], dtype=bool)
+        alpha = torch.zeros(xyz_locs.shape[:-1], device=xyz_locs.device)
+        if alpha_mask.any():
+            x = xyz_locs[alpha_mask]
+            sdfs = self.sdf_inter_fun(x)[..., 0]
+            near_surf = torch.abs(sdfs) < self.cfg['mul_length'] * length
+            inv_s = self.deviation_network(x).clip(1e-6, 1e6)[..., 0]
+            prev_cdf = torch.sigmoid((sdfs + length * 0.5) * inv_s)
+            next_cdf = torch.sigmoid((sdfs - length * 0.5) * inv_s)
+            a = ((prev_cdf - next_cdf + 1e-5) / (prev_cdf + 1e-5)).clip(min=0.0, max=1.0)
+            a[near_surf] = 1
+            alpha[alpha_mask] = a
+        return alpha
+
+    @torch.no_grad()
+    def updateAlphaMask(self, gridSize=(128, 128, 128)):
+        g = torch.LongTensor(list(gridSize)).to(self.device)
+        samples = torch.stack(torch.meshgrid(torch.linspace(0, 1, int(g[0]), device=self.device), torch.linspace(0, 1, int(g[1]), device=self.device),
+                                             torch.linspace(0, 1, int(g[2]), device=self.device), indexing='ij'), -1)
+        grid_xyz = self.aabb[0] * (1 - samples) + self.aabb[1] * samples
+        step_len = torch.mean(self.aabbSize / (g - 1))
+        alpha = torch.zeros_like(grid_xyz[..., 0])
+        for i in range(int(g[0])):
+            alpha[i] = self.compute_grid_alpha(grid_xyz[i].view(-1, 3), step_len).view((int(g[1]), int(g[2])))
+        grid_xyz = grid_xyz.transpose(0, 2).contiguous()
+        alpha = alpha.clamp(0, 1).transpose(0, 2).contiguous()[None, None]
+        alpha = F.max_pool3d(alpha, kernel_size=3, padding=1, stride=1).view(list(gridSize)[::-1])
+        alpha = (alpha >= self.cfg['alphaMask_thres']).float()
+        self.alphaMask = AlphaGridMask(self.device, self.aabb, alpha)
+        valid = grid_xyz[alpha > 0.5]
+        return torch.stack((valid.amin(0), valid.amax(0)))
