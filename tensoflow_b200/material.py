@@ -413,3 +413,75 @@ class MeshTracer:
 
     def __call__(self, o, d):
         return self.trace(o + self.offset * d, d)
+
+
+class MaterialRenderer(nn.Module):
+    """Material-stage orchestration (reference network/materialRenderer.py:98-887), per-step part:
+    gather the precomputed surface points of the batch -> MCShadingNetwork -> rgb / regulariser
+    losses (materialRenderer.py:518-564).  Mesh / image IO and the one-off surface-point
+    precompute are out of scope: the caller supplies the mesh arrays and the
+    surface-point batch (`inters`, `normals`, `rays_d`, `rgb`) as tensors."""
+    default_cfg = {'train_ray_num': 2048, 'rgb_loss': 'charbonier', 'shader_cfg': {}, 'reg_mat': True, 'reg_diffuse_light': True,
+                   'reg_diffuse_light_lambda': 0.1, 'device': 'cuda', 'aabb': [[-1.0, -1.0, -1.0], [1.0, 1.0, 1.0]],
+                   'gridSize': [512, 512, 512]}
+
+    def __init__(self, cfg, vertices, triangles, training=True):
+        super().__init__()
+        self.cfg = {**self.default_cfg, **cfg}
+        dev = self.cfg['device']
+        self.aabb = torch.tensor(self.cfg['aabb'], device=dev)
+        grid = torch.tensor(self.cfg['gridSize'], device=dev)
+        self.unit_size = torch.mean((self.aabb[1] - self.aabb[0]) / (grid - 1))
+        self.tracer = MeshTracer(vertices, triangles, offset=float(2 * self.unit_size))    # materialRenderer.py:223
+        self.shader_network = MCShadingNetwork({**self.cfg['shader_cfg'], 'device': dev}, self.tracer, self.aabb)
+        self.train_batch = None
+
+    def trace(self, rays_o, rays_d):
+        return self.tracer.trace(rays_o, rays_d)
+
+    def get_train_opt_params(self, learning_rate_xyz, learning_rate_net, learning_rate_env):
+        return self.shader_network.get_optparam_groups(learning_rate_xyz, learning_rate_net, learning_rate_env)
+
+    def ckpt_to_save(self):
+        return {'network_state_dict': self.state_dict()}
+
+    def set_train_batch(self, batch: Dict[str, torch.Tensor]):
+        self.train_batch, self.train_batch_i, self.tbn = batch, 0, batch['inters'].shape[0]
+
+    def shade(self, pts, view_dirs, normals, human_poses, is_train, step=None, noise=None):
+        rgb_pr, outputs = self.shader_network(pts, view_dirs, normals, human_poses, step, is_train, noise=noise)
+        outputs['rgb_pr'] = rgb_pr
+        return outputs
+
+    def compute_rgb_loss(self, rgb_pr, rgb_gt):
+        if self.cfg['rgb_loss'] == 'l1':
+            return torch.sum(F.l1_loss(rgb_pr, rgb_gt, reduction='none'), -1)
+        if self.cfg['rgb_loss'] == 'charbonier':
+            return torch.sqrt(torch.sum((rgb_gt - rgb_pr) ** 2, dim=-1) + 0.001)
+        raise NotImplementedError
+
+    def compute_diffuse_light_regularization(self, diffuse_lights):
+        return torch.sum(torch.abs(diffuse_lights - torch.mean(diffuse_lights, dim=-1, keepdim=True)), dim=-1) * self.cfg['reg_diffuse_light_lambda']
+
+    def train_step(self, step, noise=None):
+        rn = self.cfg['train_ray_num']
+        dev = self.cfg['device']
+        b = {k: v[self.train_batch_i:self.train_batch_i + rn].to(dev, non_blocking=True) for k, v in self.train_batch.items()}
+        self.train_batch_i += rn
+        if self.train_batch_i + rn >= self.tbn:
+            self.train_batch_i = 0
+        self.shader_network.update_step(step)
+        out = self.shade(b['inters'], -b['rays_d'], b['normals'], None, True, step, noise=noise)
+        out['rgb_gt'] = b['rgb']
+        out['loss_rgb'] = self.compute_rgb_loss(out['rgb_pr'], b['rgb'])
+        out['psnr'] = 20 * torch.log10(1.0 / torch.sqrt(F.mse_loss(out['rgb_pr'], b['rgb'])))
+        if self.cfg['reg_mat']:
+            out['loss_mat_reg'] = self.shader_network.material_regularization(b['inters'], b['normals'], out['metallic'], out['roughness'],
+                                                                              out['albedo'], step)
+        if self.cfg['reg_diffuse_light']:
+            out['loss_diffuse_light'] = self.compute_diffuse_light_regularization(out['diffuse_light'])
+        return out
+
+    def forward(self, data):
+        self.shader_network.outer_light.build_mips_direct()          # materialRenderer.py:760-761
+        return self.train_step(data['step'], data.get('noise'))

@@ -1,0 +1,90 @@
+"""world_size-2 gloo tests (CPU) of the data-parallel host logic: ray sharding + flat-bucket
+gradient allreduce reproduce the single-process gradients; (sum,count) means; tile gather."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _model():
+    torch.manual_seed(0)
+    m = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.Softplus(beta=100), torch.nn.Linear(16, 3))
+    # a channels-last 4-D parameter like the VM planes
+    plane = torch.empty_strided((1, 4, 5, 5), (100, 1, 20, 4)).copy_(torch.randn(1, 4, 5, 5))
+    m.register_parameter("plane", torch.nn.Parameter(plane))
+    return m
+
+
+def _loss_terms(m, x, y):
+    pred = m(x) + m.plane.mean()
+    per_ray = ((pred - y) ** 2).sum(-1)
+    keep = x[:, 0] > 0                      # rank-dependent sample count, like culled samples
+    return per_ray, (pred[keep] ** 2).sum(), keep.sum()
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tensoflow_b200.dist import FlatGradBucket, shard_slice, global_mean, gather_tiles
+    g = torch.Generator().manual_seed(1)
+    X, Y = torch.randn(37, 6, generator=g), torch.randn(37, 3, generator=g)
+    m = _model()
+    sl = shard_slice(37, rank, world)
+    per_ray, s, c = _loss_terms(m, X[sl], Y[sl])
+    mean_kept = global_mean(s.detach(), c)
+    # loss = mean over ALL rays + mean over ALL kept samples: scale local sums by the global counts
+    c_all = c.clone().float()
+    dist.all_reduce(c_all)
+    loss = per_ray.sum() / 37 + s / c_all
+    loss.backward()
+    bucket = FlatGradBucket(m.parameters())
+    bucket.allreduce()
+    tiles = gather_tiles(per_ray.detach()[:, None])
+    q.put((rank, [p.grad.clone() for p in m.parameters()], float(mean_kept), tiles))
+    dist.destroy_process_group()
+
+
+def test_flat_bucket_allreduce_matches_single_process():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    g = torch.Generator().manual_seed(1)
+    X, Y = torch.randn(37, 6, generator=g), torch.randn(37, 3, generator=g)
+    m = _model()
+    per_ray, s, c = _loss_terms(m, X, Y)
+    (per_ray.mean() + s / c).backward()
+    for r in range(world):
+        for got, p in zip(res[r][1], m.parameters()):
+            assert got.stride() == p.grad.stride() or got.shape == p.grad.shape
+            assert torch.allclose(got, p.grad, rtol=1e-5, atol=1e-6)
+        assert abs(res[r][2] - float(s / c)) < 1e-5
+        assert torch.allclose(res[r][3][:, 0], per_ray.detach(), rtol=1e-5, atol=1e-6)
+
+
+def test_shard_slice_covers_everything():
+    from tensoflow_b200.dist import shard_slice
+    for n in (0, 1, 7, 64, 65537):
+        for w in (1, 2, 3, 8):
+            idx = []
+            for r in range(w):
+                s = shard_slice(n, r, w)
+                idx += list(range(s.start, s.stop))
+            assert idx == list(range(n))
