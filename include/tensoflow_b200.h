@@ -236,6 +236,14 @@ TF_API int tf_csr_spmm3_fwd(const int32_t* rowptr, const int32_t* col, const flo
 TF_API int tf_csr_spmm3_bwd(const int32_t* rowptr, const int32_t* col, const float* val, const float* gy,
                             int32_t n_rows, float* gx, tf_stream_t stream);
 
+/* ---- tcgen05 self-test ---------------------------------------------------------------------
+ * D[128,N] = A[128,K] B[N,K]^T on the 5th-gen tensor cores (TMEM accumulator), N in {128,256},
+ * K % 8 == 0; passes = 1 (plain tf32) or 3 (tf32 operand splitting, fp32-level accuracy);
+ * repeat > 1 re-issues the MMA sequence (throughput probe).  Validates the descriptor / TMEM /
+ * mbarrier plumbing the fused decoder kernels use. */
+TF_API int tf_tc_probe(const float* A, const float* B, int32_t N, int32_t K, int32_t passes, int32_t repeat,
+                       float* D, tf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
