@@ -102,7 +102,8 @@ TF_API int tf_vm_feature_bwd(const tf_vm_field_t* f, const float* xyz, const flo
  *   feat[n,A] : appearance features (decoder outputs 1..A) at the centre
  *   grad[n,3] : central differences          hess[n] : (g.h)/(|g|^2+1e-5)
  * feat / grad / hess may be NULL.  level may be NULL. */
-TF_API size_t tf_sdf_stencil_fwd_workspace(const tf_vm_field_t* f, const tf_sdf_mlp_t* m);
+TF_API size_t tf_sdf_stencil_fwd_workspace(const tf_vm_field_t* f, const tf_sdf_mlp_t* m, int64_t n,
+                                           int32_t with_feat);
 TF_API int tf_sdf_stencil_fwd(const tf_vm_field_t* f, const tf_sdf_mlp_t* m, const float* xyz,
                        const float* level, int64_t n, const float units[3], float* sdf7,
                        float* feat, float* grad, float* hess, void* workspace, size_t ws_bytes,

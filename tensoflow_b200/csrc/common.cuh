@@ -47,6 +47,41 @@ __device__ __forceinline__ float softplus100_grad(float x) {
     return bx > 20.f ? 1.f : 1.f / (1.f + expf(-bx));
 }
 
+// Fast Softplus(beta=100) for the tensor-core epilogues:
+//   softplus(x) = max(x,0) + log1p(exp(-|100 x|)) / 100
+// exp through ex2.approx (rel. error 2^-22), log1p(t) = t*g(t) with a degree-9 interpolant of
+// g on [0,1] (max abs error 1.1e-7 in fp32 Horner) -> absolute error of the result ~1e-9, i.e.
+// fp32-rounding level for the hidden activations; 1 MUFU + ~14 FP ops instead of expf+log1pf (~50).
+__device__ __forceinline__ float ex2_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float log1p_01(float t) {
+    float g = -3.176057010e-03f;
+    g = fmaf(g, t, 1.954252722e-02f);
+    g = fmaf(g, t, -5.637361275e-02f);
+    g = fmaf(g, t, 1.054362379e-01f);
+    g = fmaf(g, t, -1.526966707e-01f);
+    g = fmaf(g, t, 1.966327426e-01f);
+    g = fmaf(g, t, -2.495161626e-01f);
+    g = fmaf(g, t, 3.332971050e-01f);
+    g = fmaf(g, t, -4.999989265e-01f);
+    g = fmaf(g, t, 9.999999947e-01f);
+    return g * t;
+}
+__device__ __forceinline__ float softplus100_fast(float x) {
+    const float t = ex2_approx(-fabsf(x) * 144.26950408889634f);   // exp(-|100x|) = 2^(-|x| * 100*log2(e))
+    return fmaf(log1p_01(t), 0.01f, fmaxf(x, 0.f));
+}
+// softplus and its derivative sigmoid(100x) from one exponential
+__device__ __forceinline__ void softplus100_fast_both(float x, float& sp, float& sg) {
+    const float t = ex2_approx(-fabsf(x) * 144.26950408889634f);
+    sp = fmaf(log1p_01(t), 0.01f, fmaxf(x, 0.f));
+    const float r = __fdividef(1.f, 1.f + t);
+    sg = x >= 0.f ? r : t * r;
+}
+
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 // vector reduction into global memory (sm_90+): 4 floats, 16-byte aligned
@@ -202,6 +237,46 @@ __device__ __forceinline__ void vm_sample(const tf_vm_field_t& f, const float q[
         lt = line_level_ptr(f, i, l1, G);
         float4 L1 = fetch_li(lt, make_litap(lv, G), C, c);
         const float a = 1.f - fl;
+        P = make_float4(a * P.x + fl * P1.x, a * P.y + fl * P1.y, a * P.z + fl * P1.z, a * P.w + fl * P1.w);
+        Lv = make_float4(a * Lv.x + fl * L1.x, a * Lv.y + fl * L1.y, a * Lv.z + fl * L1.z, a * Lv.w + fl * L1.w);
+    }
+}
+
+// Sampling plan of plane i / line i at one point, computed once and reused for every channel group
+struct VmTaps {
+    const float* pt0; const float* pt1; const float* lt0; const float* lt1;
+    BiTap b0, b1;
+    LiTap t0, t1;
+    float fl;
+};
+__device__ __forceinline__ VmTaps vm_taps(const tf_vm_field_t& f, const float q[3], float level, bool has_level, int i) {
+    VmTaps t;
+    float pu, pv, lv;
+    vm_coords(f, q, i, pu, pv, lv);
+    int l0 = 0, l1 = 0;
+    t.fl = 0.f;
+    if (has_level && f.n_levels > 1) mip_levels(level, f.n_levels, l0, l1, t.fl);
+    int H, W, G;
+    t.pt0 = plane_level_ptr(f, i, l0, H, W);
+    t.b0 = make_bitap(pu, pv, W, H);
+    t.lt0 = line_level_ptr(f, i, l0, G);
+    t.t0 = make_litap(lv, G);
+    t.pt1 = t.pt0; t.lt1 = t.lt0; t.b1 = t.b0; t.t1 = t.t0;
+    if (t.fl > 0.f) {
+        t.pt1 = plane_level_ptr(f, i, l1, H, W);
+        t.b1 = make_bitap(pu, pv, W, H);
+        t.lt1 = line_level_ptr(f, i, l1, G);
+        t.t1 = make_litap(lv, G);
+    }
+    return t;
+}
+__device__ __forceinline__ void vm_fetch(const VmTaps& t, int C, int c, float4& P, float4& Lv) {
+    P = fetch_bi(t.pt0, t.b0, C, c);
+    Lv = fetch_li(t.lt0, t.t0, C, c);
+    if (t.fl > 0.f) {
+        const float4 P1 = fetch_bi(t.pt1, t.b1, C, c);
+        const float4 L1 = fetch_li(t.lt1, t.t1, C, c);
+        const float a = 1.f - t.fl, fl = t.fl;
         P = make_float4(a * P.x + fl * P1.x, a * P.y + fl * P1.y, a * P.z + fl * P1.z, a * P.w + fl * P1.w);
         Lv = make_float4(a * Lv.x + fl * L1.x, a * Lv.y + fl * L1.y, a * Lv.z + fl * L1.z, a * Lv.w + fl * L1.w);
     }

@@ -11,6 +11,7 @@
 //   hidden   : processed in chunks of NC=32 units; thread (s = tid/16, tx = tid%16) owns
 //              the 7 stencil rows of sample s x 2 hidden units -> the stencil is thread local
 //   GEMM2    : centre rows only ([16][NC] x [NC][A]); taps need output 0 only (a dot product)
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
@@ -560,10 +561,30 @@ void fill_common(StencilParams& p, const tf_vm_field_t* f, const tf_sdf_mlp_t* m
 
 int tf_check_field(const tf_vm_field_t* f, bool need_mips);
 
-extern "C" TF_API size_t tf_sdf_stencil_fwd_workspace(const tf_vm_field_t* f, const tf_sdf_mlp_t* m) {
+// tensor-core forward (sdf_stencil_tc.cu)
+size_t tf_internal_tc_fwd_smem(int KT, int H);
+size_t tf_internal_tc_w0_floats(int KT, int H);
+int tf_internal_stencil_fwd_tc(const tf_vm_field_t* f, const tf_sdf_mlp_t* m, const float* xyz, const float* level, int64_t n,
+                               const float units[3], int nq, float* sdf7, float* grad, float* hess, float* sdf1, float* spc,
+                               float* w0tc, cudaStream_t stream);
+// TF_STENCIL_SIMT=1 selects the fp32 FFMA kernels below instead of the tcgen05 path (A/B testing only)
+static bool use_simt_path(const Dims& d) {
+    static int forced = -1;
+    if (forced < 0) { const char* e = getenv("TF_STENCIL_SIMT"); forced = (e && e[0] == '1') ? 1 : 0; }
+    const int KT = (d.K + 15) / 16 * 16;
+    return forced == 1 || tf_internal_tc_fwd_smem(KT, d.H) > 227 * 1024 || d.H > 256 || d.H % 32 != 0;
+}
+
+static size_t fwd_ws_floats(const Dims& d, int64_t n, bool with_feat) {
+    if (use_simt_path(d)) return weights_ws_floats(d);
+    const int KT = (d.K + 15) / 16 * 16;
+    return tf_internal_tc_w0_floats(KT, d.H) + (with_feat ? (size_t)(n < 1 ? 1 : n) * d.H : 0);
+}
+
+extern "C" TF_API size_t tf_sdf_stencil_fwd_workspace(const tf_vm_field_t* f, const tf_sdf_mlp_t* m, int64_t n, int32_t with_feat) {
     Dims d;
     if (!f || !m || check_mlp(f, m, d)) return 0;
-    return weights_ws_floats(d) * sizeof(float);
+    return fwd_ws_floats(d, n, with_feat != 0) * sizeof(float);
 }
 
 static int stencil_fwd_impl(int mode, const tf_vm_field_t* f, const tf_sdf_mlp_t* m, const float* xyz, const float* level,
@@ -574,10 +595,23 @@ static int stencil_fwd_impl(int mode, const tf_vm_field_t* f, const tf_sdf_mlp_t
     if (int e = check_mlp(f, m, d)) return e;
     if (n == 0) return 0;
     TF_REQUIRE(xyz, "xyz is NULL");
-    TF_REQUIRE(workspace && ws_bytes >= weights_ws_floats(d) * sizeof(float), "workspace too small (%zu bytes)", ws_bytes);
+    TF_REQUIRE(workspace && ws_bytes >= fwd_ws_floats(d, n, feat != nullptr) * sizeof(float), "workspace too small (%zu bytes)", ws_bytes);
     TF_REQUIRE(((uintptr_t)workspace & 15) == 0, "workspace not 16-byte aligned");
     if (feat) TF_REQUIRE(((uintptr_t)feat & 15) == 0, "feat not 16-byte aligned");
     cudaStream_t stream = (cudaStream_t)stream_;
+    if (!use_simt_path(d)) {
+        // tcgen05 path: first layer on the tensor cores, appearance head as one more linear layer
+        const int KT = (d.K + 15) / 16 * 16;
+        float* w0tc = (float*)workspace;
+        float* spc = feat ? w0tc + tf_internal_tc_w0_floats(KT, d.H) : nullptr;
+        if (mode == 0) TF_REQUIRE(sdf7, "sdf7 is NULL"); else TF_REQUIRE(sdf1, "sdf is NULL");
+        if (int e = tf_internal_stencil_fwd_tc(f, m, xyz, level, n, units, mode == 0 ? 7 : 1, sdf7, grad, hess, sdf1, spc, w0tc, stream)) return e;
+        if (feat) {
+            if (int e = tf_linear_fwd(spc, m->W1 + d.H, m->b1 + 1, n, d.H, d.A, 0, 0.f, feat, stream_)) return e;
+        }
+        TF_CHECK_LAUNCH("tf_sdf_stencil_fwd (tcgen05)");
+        return 0;
+    }
     StencilParams p = {};
     fill_common(p, f, m, d, xyz, level, n, units, (float*)workspace);
     p.sdf7 = sdf7; p.feat = feat; p.grad = grad; p.hess = hess; p.sdf1 = sdf1;

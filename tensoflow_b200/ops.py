@@ -181,7 +181,7 @@ class SdfStencilFunction(torch.autograd.Function):
         feat = torch.empty(n, A, device=dev, dtype=torch.float32)
         grad = torch.empty(n, 3, device=dev, dtype=torch.float32)
         hess = torch.empty(n, device=dev, dtype=torch.float32)
-        wsb = lib.tf_sdf_stencil_fwd_workspace(C.byref(vm.c), C.byref(m))
+        wsb = lib.tf_sdf_stencil_fwd_workspace(C.byref(vm.c), C.byref(m), n, 1)
         if wsb == 0:
             check(1, "tf_sdf_stencil_fwd_workspace")
         ws = torch.empty(wsb // 4, device=dev, dtype=torch.float32)
@@ -230,7 +230,7 @@ def sdf_only(xyz, level, aabb, n_levels, W0, b0, W1, b1, planes, lines) -> torch
     vm = VMDesc(planes, lines, aabb, n_levels, build_mips=lvl_c is not None)
     m, keep = _mlp_desc(W0, b0, W1, b1)
     out = torch.empty(n, device=xyz_c.device, dtype=torch.float32)
-    wsb = lib.tf_sdf_stencil_fwd_workspace(C.byref(vm.c), C.byref(m))
+    wsb = lib.tf_sdf_stencil_fwd_workspace(C.byref(vm.c), C.byref(m), n, 0)
     if wsb == 0:
         check(1, "tf_sdf_stencil_fwd_workspace")
     ws = torch.empty(wsb // 4, device=xyz_c.device, dtype=torch.float32)
