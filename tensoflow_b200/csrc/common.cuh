@@ -282,6 +282,27 @@ __device__ __forceinline__ void vm_fetch(const VmTaps& t, int C, int c, float4& 
     }
 }
 
+// scatter with a precomputed plan (mutable twins of the read pointers are passed by the caller)
+__device__ __forceinline__ void vm_scatter_taps(const VmTaps& t, float* pt0, float* pt1, float* lt0, float* lt1, int C, int c,
+                                                float4 dP, float4 dL) {
+    const float w0 = 1.f - t.fl;
+    red_add_v4(pt0 + (size_t)t.b0.o00 * C + c, f4_scale(w0 * t.b0.w00, dP));
+    red_add_v4(pt0 + (size_t)t.b0.o01 * C + c, f4_scale(w0 * t.b0.w01, dP));
+    red_add_v4(pt0 + (size_t)t.b0.o10 * C + c, f4_scale(w0 * t.b0.w10, dP));
+    red_add_v4(pt0 + (size_t)t.b0.o11 * C + c, f4_scale(w0 * t.b0.w11, dP));
+    red_add_v4(lt0 + (size_t)t.t0.o0 * C + c, f4_scale(w0 * t.t0.w0, dL));
+    red_add_v4(lt0 + (size_t)t.t0.o1 * C + c, f4_scale(w0 * t.t0.w1, dL));
+    if (t.fl > 0.f) {
+        const float w1 = t.fl;
+        red_add_v4(pt1 + (size_t)t.b1.o00 * C + c, f4_scale(w1 * t.b1.w00, dP));
+        red_add_v4(pt1 + (size_t)t.b1.o01 * C + c, f4_scale(w1 * t.b1.w01, dP));
+        red_add_v4(pt1 + (size_t)t.b1.o10 * C + c, f4_scale(w1 * t.b1.w10, dP));
+        red_add_v4(pt1 + (size_t)t.b1.o11 * C + c, f4_scale(w1 * t.b1.w11, dP));
+        red_add_v4(lt1 + (size_t)t.t1.o0 * C + c, f4_scale(w1 * t.t1.w0, dL));
+        red_add_v4(lt1 + (size_t)t.t1.o1 * C + c, f4_scale(w1 * t.t1.w1, dL));
+    }
+}
+
 // scatter dP (grad wrt plane_i(x)) and dL (grad wrt line_i(x)) into the factor grads
 __device__ __forceinline__ void vm_scatter(const tf_vm_field_t& f, const tf_vm_mut_t& g, const float q[3], float level,
                                            bool has_level, int i, int c, float4 dP, float4 dL) {

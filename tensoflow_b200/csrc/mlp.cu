@@ -212,6 +212,16 @@ int tf_internal_xty(const float* X, int ldx, const float* Y, int ldy, int64_t ro
     return 0;
 }
 
+// out[M][Nout] = A[M][Kred] * W[Kred][Nout] (row-major, no bias / activation)
+int tf_internal_matmul(const float* A, int lda, const float* W, int ldw, int64_t M, int Kred, int Nout, float* out, int ldo,
+                       cudaStream_t stream) {
+    if (M == 0 || Nout == 0) return 0;
+    dim3 grid((unsigned)((M + BM - 1) / BM), (Nout + BN - 1) / BN);
+    linear_kernel<true, false><<<grid, 256, 0, stream>>>(A, lda, nullptr, nullptr, W, ldw, nullptr, M, Kred, Nout, 0, 0.f, out, ldo);
+    tf_count_launches(1);
+    return 0;
+}
+
 int tf_internal_colsum(const float* X, int ldx, int64_t rows, int cols, float* out, cudaStream_t stream) {
     if (rows == 0 || cols == 0) return 0;
     int gy = (int)(rows < 256 ? rows : 256);

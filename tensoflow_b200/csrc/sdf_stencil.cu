@@ -653,11 +653,82 @@ static size_t bwd_slice_floats(const Dims& d, int64_t n_slice) {
     return (size_t)tiles * ((size_t)R * d.H + (size_t)R * d.KP + (size_t)TS * d.H);
 }
 
+// tensor-core backward (sdf_stencil_bwd_tc.cu)
+size_t tf_internal_bwd_tc_wtc_floats(int KT, int H);
+size_t tf_internal_bwd_tc_smem(int KT, int H);
+int tf_internal_bwd_tc_prep(const float* W0, int K, int KT, int H, float* wtc, cudaStream_t stream);
+int tf_internal_bwd_tc_fold(const float* tmp, int H, int K, int KT, float* dW0, float* db0, cudaStream_t stream);
+int tf_internal_stencil_bwd_tc(const tf_vm_field_t* f, const tf_vm_mut_t* g, const tf_sdf_mlp_t* m, const float* wtc, const float* xyz,
+                               const float* level, int64_t n, const float units[3], const float* sdf7, const float* g_sdf,
+                               const float* g_grad, const float* g_hess, const float* dHc, float* dpre, float* arow, float* spc,
+                               float* dW1r0, float* db1, cudaStream_t stream);
+int tf_internal_xty(const float* X, int ldx, const float* Y, int ldy, int64_t rows, int M, int N, float* out, int ldo, cudaStream_t stream);
+int tf_internal_colsum(const float* X, int ldx, int64_t rows, int cols, float* out, cudaStream_t stream);
+int tf_internal_matmul(const float* A, int lda, const float* W, int ldw, int64_t M, int Kred, int Nout, float* out, int ldo,
+                       cudaStream_t stream);
+
+static bool use_simt_bwd(const Dims& d) {
+    const int KT = (d.K + 15) / 16 * 16;
+    return use_simt_path(d) || d.C % 4 != 0 || KT > 256 || tf_internal_bwd_tc_smem(KT, d.H) > 227 * 1024;
+}
+// tensor-core backward workspace: [W slices | dW0/db0 staging | per 128-sample block: dPre, A rows, centre hidden, dHidden(centre)]
+static size_t bwd_tc_fixed_floats(const Dims& d) {
+    const int KT = (d.K + 15) / 16 * 16;
+    return tf_internal_bwd_tc_wtc_floats(KT, d.H) + (size_t)d.H * KT;
+}
+static size_t bwd_tc_block_floats(const Dims& d) {
+    const int KT = (d.K + 15) / 16 * 16;
+    return (size_t)128 * ((size_t)NQ * d.H + (size_t)NQ * KT + 2 * (size_t)d.H);
+}
+
 extern "C" TF_API size_t tf_sdf_stencil_bwd_workspace(const tf_vm_field_t* f, const tf_sdf_mlp_t* m, int64_t n_slice) {
     Dims d;
     if (!f || !m || check_mlp(f, m, d)) return 0;
     if (n_slice < 1) n_slice = 1;
+    if (!use_simt_bwd(d)) return (bwd_tc_fixed_floats(d) + (size_t)((n_slice + 127) / 128) * bwd_tc_block_floats(d)) * sizeof(float);
     return (weights_ws_floats(d) + bwd_slice_floats(d, n_slice)) * sizeof(float);
+}
+
+static int stencil_bwd_tc(const tf_vm_field_t* f, const tf_sdf_mlp_t* m, const Dims& d, const float* xyz, const float* level, int64_t n,
+                          const float units[3], const float* sdf7, const float* g_sdf, const float* g_feat, const float* g_grad,
+                          const float* g_hess, const tf_vm_mut_t* g_field, const tf_sdf_mlp_grad_t* g_mlp, float* ws, size_t ws_floats,
+                          cudaStream_t stream) {
+    const int KT = (d.K + 15) / 16 * 16, H = d.H;
+    const size_t fixed = bwd_tc_fixed_floats(d), per_block = bwd_tc_block_floats(d);
+    TF_REQUIRE(ws_floats >= fixed + per_block, "workspace too small (%zu bytes)", ws_floats * sizeof(float));
+    int64_t blocks_fit = (int64_t)((ws_floats - fixed) / per_block);
+    const int64_t nblocks_all = (n + 127) / 128;
+    if (blocks_fit > nblocks_all) blocks_fit = nblocks_all;
+    float* wtc = ws;
+    float* tmp = wtc + tf_internal_bwd_tc_wtc_floats(KT, H);
+    float* dpre = tmp + (size_t)H * KT;
+    float* arow = dpre + (size_t)blocks_fit * 128 * NQ * H;
+    float* spc = arow + (size_t)blocks_fit * 128 * NQ * KT;
+    float* dHc = spc + (size_t)blocks_fit * 128 * H;
+    tf_internal_bwd_tc_prep(m->W0, d.K, KT, H, wtc, stream);
+    cudaMemsetAsync(tmp, 0, (size_t)H * KT * sizeof(float), stream);
+    for (int64_t b0 = 0; b0 < nblocks_all; b0 += blocks_fit) {
+        const int64_t nb = b0 + blocks_fit < nblocks_all ? blocks_fit : nblocks_all - b0;
+        const int64_t s0 = b0 * 128;
+        const int64_t ns = s0 + nb * 128 < n ? nb * 128 : n - s0;
+        const float* gf = g_feat ? g_feat + s0 * d.A : nullptr;
+        // dHidden(centre) = g_feat W1[1:, :]
+        if (gf) tf_internal_matmul(gf, d.A, m->W1 + H, H, ns, d.A, H, dHc, H, stream);
+        if (int e = tf_internal_stencil_bwd_tc(f, g_field, m, wtc, xyz + s0 * 3, level ? level + s0 : nullptr, ns, units, sdf7 + s0 * NQ,
+                                               g_sdf ? g_sdf + s0 : nullptr, g_grad ? g_grad + s0 * 3 : nullptr,
+                                               g_hess ? g_hess + s0 : nullptr, gf ? dHc : nullptr, dpre, arow, gf ? spc : nullptr,
+                                               g_mlp->W1, g_mlp->b1, stream))
+            return e;
+        // [dW0 | db0] staging += dPre^T [A | 1]
+        tf_internal_xty(dpre, H, arow, KT, nb * 128 * NQ, H, KT, tmp, KT, stream);
+        if (gf) {
+            tf_internal_xty(gf, d.A, spc, H, ns, d.A, H, g_mlp->W1 + H, H, stream);
+            tf_internal_colsum(gf, d.A, ns, d.A, g_mlp->b1 + 1, stream);
+        }
+    }
+    tf_internal_bwd_tc_fold(tmp, H, d.K, KT, g_mlp->W0, g_mlp->b0, stream);
+    TF_CHECK_LAUNCH("tf_sdf_stencil_bwd (tcgen05)");
+    return 0;
 }
 
 extern "C" TF_API int tf_sdf_stencil_bwd(const tf_vm_field_t* f, const tf_sdf_mlp_t* m, const float* xyz, const float* level,
@@ -676,10 +747,14 @@ extern "C" TF_API int tf_sdf_stencil_bwd(const tf_vm_field_t* f, const tf_sdf_ml
     }
     TF_REQUIRE(((uintptr_t)workspace & 15) == 0, "workspace not 16-byte aligned");
     if (g_feat) TF_REQUIRE(((uintptr_t)g_feat & 15) == 0, "g_feat not 16-byte aligned");
-    const size_t wfl = weights_ws_floats(d);
-    TF_REQUIRE(workspace && ws_bytes >= (wfl + bwd_slice_floats(d, TS)) * sizeof(float), "workspace too small (%zu bytes)", ws_bytes);
     cudaStream_t stream = (cudaStream_t)stream_;
     float* ws = (float*)workspace;
+    TF_REQUIRE(workspace, "workspace is NULL");
+    if (!use_simt_bwd(d))
+        return stencil_bwd_tc(f, m, d, xyz, level, n, units, sdf7, g_sdf, g_feat, g_grad, g_hess, g_field, g_mlp, ws,
+                              ws_bytes / sizeof(float), stream);
+    const size_t wfl = weights_ws_floats(d);
+    TF_REQUIRE(ws_bytes >= (wfl + bwd_slice_floats(d, TS)) * sizeof(float), "workspace too small (%zu bytes)", ws_bytes);
     // samples per slice that fit the workspace (multiple of TS)
     const size_t per_tile = (size_t)R * d.H + (size_t)R * d.KP + (size_t)TS * d.H;
     int64_t tiles_fit = (int64_t)((ws_bytes / sizeof(float) - wfl) / per_tile);

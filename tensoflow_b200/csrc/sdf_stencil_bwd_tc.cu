@@ -1,0 +1,446 @@
+// Fused TensoSDF stencil backward (activation side) on the 5th-gen tensor cores, sm_100a.
+//
+// Per MMA tile (128 rows = one stencil query of a 128-sample block):
+//   gather     : features -> A operand (tf32 hi/lo, canonical K-major layout) + fp32 copy to the
+//                workspace (`arow`, with a constant-1 column so that dPre^T [A|1] yields dW0 and db0)
+//   GEMM1      : pre = A W0^T on tcgen05 (3xTF32), accumulator D1 [128 x H] in TMEM
+//   epilogue-1 : per 32-column chunk: Softplus / sigmoid, dPost = gq * W1[0,:] (+ g_feat W1[1:,:] for the
+//                centre tile, precomputed), dPre = dPost * sigmoid -> workspace + shared memory (hi/lo)
+//   GEMM-dA    : dA += dPre[:,chunk] W0[chunk,:] on tcgen05, accumulator D2 [128 x KT] in TMEM,
+//                chunk by chunk behind epilogue-1 (double-buffered operand)
+//   scatter    : dA -> shared memory -> d plane / d line with vector reductions
+// Weight slices (W0 by K-slices for GEMM1, W0^T by hidden chunks for GEMM-dA) stream through one
+// 3-stage cp.async.bulk ring.  Weight gradients are finished by X^T Y passes over the workspace.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int TM = 128;
+constexpr int NQ7 = 7;
+constexpr int KSL = 16;     // K slice of GEMM1
+constexpr int HCH = 32;     // hidden chunk of epilogue-1 / GEMM-dA
+constexpr int NST = 3;
+constexpr int NTH = 256;
+
+struct TcBwdParams {
+    tf_vm_field_t f;
+    tf_vm_mut_t g;
+    const float* xyz; const float* level;
+    int64_t n;
+    const float* Wtc;        // [S + NCH] slots of slot_floats
+    const float* b0; const float* w1r0;
+    const float* sdf7; const float* g_sdf; const float* g_grad; const float* g_hess;
+    const float* dHc;        // [n][H] = g_feat . W1[1:,:]  (NULL when there is no feature gradient)
+    int K, KT, H, slot_floats;
+    float units[3];
+    float* dpre;             // [tiles*128][H]
+    float* arow;             // [tiles*128][KT]
+    float* spc;              // [n][H] centre hidden activations (NULL = not needed)
+    float* dW1r0; float* db1;
+};
+
+// slots 0..S-1   : W0 K-slices   [H rows x 16]  hi | lo   (GEMM1 B operand)
+// slots S..S+NCH : W0^T chunks   [KT rows x 32] hi | lo   (GEMM-dA B operand: B[n = feature][k = hidden])
+__global__ void tc_prep_bwd_kernel(const float* __restrict__ W0, int K, int KT, int H, int slot_floats, float* __restrict__ Wtc) {
+    const int S = KT / KSL, NCH = H / HCH;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    for (int i = tid; i < S * H * KSL; i += nth) {
+        const int kl = i % KSL, h = (i / KSL) % H, s = i / (KSL * H);
+        const int k = s * KSL + kl;
+        const float v = k < K ? W0[(size_t)h * K + k] : 0.f;
+        const float hi = tc::tf32_rn(v);
+        float* base = Wtc + (size_t)s * slot_floats;
+        const uint32_t off = tc::tile_off_b32(h, kl, KSL / 4) / 4;
+        base[off] = hi;
+        base[(size_t)H * KSL + off] = tc::tf32_rn(v - hi);
+    }
+    for (int i = tid; i < NCH * KT * HCH; i += nth) {
+        const int kk = i % HCH, kf = (i / HCH) % KT, c = i / (HCH * KT);
+        const float v = kf < K ? W0[(size_t)(c * HCH + kk) * K + kf] : 0.f;
+        const float hi = tc::tf32_rn(v);
+        float* base = Wtc + (size_t)(S + c) * slot_floats;
+        const uint32_t off = tc::tile_off_b32(kf, kk, HCH / 4) / 4;
+        base[off] = hi;
+        base[(size_t)KT * HCH + off] = tc::tf32_rn(v - hi);
+    }
+}
+
+// out[h][k] (k < K) += tmp[h][k];  db0[h] += tmp[h][K]
+__global__ void tc_fold_wgrad_kernel(const float* __restrict__ tmp, int H, int K, int KT, float* __restrict__ dW0, float* __restrict__ db0) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H * KT; i += gridDim.x * blockDim.x) {
+        const int h = i / KT, k = i % KT;
+        const float v = tmp[i];
+        if (k < K) dW0[(size_t)h * K + k] += v;
+        else if (k == K) db0[h] += v;
+    }
+}
+
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tc::smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(tc::smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ float4 split_hi(float4 v) { return make_float4(tc::tf32_rn(v.x), tc::tf32_rn(v.y), tc::tf32_rn(v.z), tc::tf32_rn(v.w)); }
+__device__ __forceinline__ float4 split_lo(float4 v, float4 h) {
+    return make_float4(tc::tf32_rn(v.x - h.x), tc::tf32_rn(v.y - h.y), tc::tf32_rn(v.z - h.z), tc::tf32_rn(v.w - h.w));
+}
+
+__device__ __forceinline__ float* mut_of(const float* p, const float* base0, float* g0, const float* basem, float* gm) {
+    return p == base0 ? g0 : gm + (p - basem);
+}
+
+__device__ __forceinline__ void bwd_gather(const TcBwdParams& p, int64_t sb, int q, int64_t tile_row0, uint8_t* a_hi, uint8_t* a_lo) {
+    const int C = p.f.n_comp, C4 = C / 4, G = p.KT / 4, kch = p.KT / 4;
+    const bool has_level = p.level != nullptr;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int u = warp; u < (TM / 8) * 3; u += NTH / 32) {
+        const int rg = u / 3, i = u % 3;
+        const int row = rg * 8 + (lane & 7);
+        const int64_t n = sb * TM + row;
+        const bool valid = n < p.n;
+        VmTaps taps;
+        if (valid) {
+            const float x[3] = {p.xyz[n * 3 + 0], p.xyz[n * 3 + 1], p.xyz[n * 3 + 2]};
+            float pt[3];
+            stencil_point(x, p.units, q, pt);
+            taps = vm_taps(p.f, pt, has_level ? p.level[n] : 0.f, has_level, i);
+        }
+        for (int c4 = lane >> 3; c4 < C4; c4 += 4) {
+            float4 v = f4_zero();
+            if (valid) {
+                float4 P, L;
+                vm_fetch(taps, C, c4 * 4, P, L);
+                v = f4_mul(P, L);
+            }
+            const int g = i * C4 + c4;
+            const float4 hi = split_hi(v);
+            const uint32_t off = tc::tile_off_b32(row, g * 4, kch);
+            *reinterpret_cast<float4*>(a_hi + off) = hi;
+            *reinterpret_cast<float4*>(a_lo + off) = split_lo(v, hi);
+            *reinterpret_cast<float4*>(p.arow + (size_t)(tile_row0 + row) * p.KT + g * 4) = v;
+        }
+    }
+    const int tail_g = G - 3 * C4;
+    for (int it = threadIdx.x; it < TM * tail_g; it += NTH) {
+        const int row = it % TM, g = 3 * C4 + it / TM;
+        const int64_t n = sb * TM + row;
+        float4 v = f4_zero(), vh = f4_zero();
+        if (g == 3 * C4 && n < p.n) {
+            const float x[3] = {p.xyz[n * 3 + 0], p.xyz[n * 3 + 1], p.xyz[n * 3 + 2]};
+            float pt[3];
+            stencil_point(x, p.units, q, pt);
+            v = make_float4(pt[0], pt[1], pt[2], 0.f);
+            vh = make_float4(pt[0], pt[1], pt[2], 1.f);          // ones column -> db0 through the X^T Y pass
+        }
+        const float4 hi = split_hi(v);
+        const uint32_t off = tc::tile_off_b32(row, g * 4, kch);
+        *reinterpret_cast<float4*>(a_hi + off) = hi;
+        *reinterpret_cast<float4*>(a_lo + off) = split_lo(v, hi);
+        *reinterpret_cast<float4*>(p.arow + (size_t)(tile_row0 + row) * p.KT + g * 4) = vh;
+    }
+}
+
+__global__ void __launch_bounds__(NTH, 1) sdf_stencil_bwd_tc_kernel(TcBwdParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int H = p.H, KT = p.KT, S = KT / KSL, NCH = H / HCH, J = S + NCH, C = p.f.n_comp, C4 = C / 4;
+    const uint32_t a_part = (uint32_t)TM * KT * 4;
+    const uint32_t slot_bytes = (uint32_t)p.slot_floats * 4;
+    const uint32_t c_part = (uint32_t)TM * HCH * 4;                // one dPre chunk part (16 KB)
+    const int DAS = KT + 4;                                        // row stride of the dA tile
+    uint8_t* a_hi = smem;
+    uint8_t* a_lo = a_hi + a_part;
+    uint8_t* wst = a_lo + a_part;
+    float* b0s = reinterpret_cast<float*>(wst + (size_t)NST * slot_bytes);
+    float* w1s = b0s + H;
+    float* accw1 = w1s + H;                                        // per-CTA dW1[0,:]
+    float* gqs = accw1 + H;                                        // [7][TM]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(gqs + NQ7 * TM);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + NST;
+    uint64_t* dfull1 = bars + 2 * NST;
+    uint64_t* dfull2 = dfull1 + 1;
+    uint64_t* cfree = dfull2 + 1;                                  // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cfree + 2);
+    float* accb1 = reinterpret_cast<float*>(tmem_slot + 1);
+    float* dAs = reinterpret_cast<float*>(smem);                   // aliases the A region after the MMAs
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int lq = warp & 3, half = warp >> 2;
+    const int row = lq * 32 + lane;
+    const int64_t nblocks = (p.n + TM - 1) / TM;
+
+    if (warp == 0) tc::tmem_alloc<512>(tmem_slot);
+    if (tid == 0) {
+        for (int i = 0; i < NST; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
+        tc::mbar_init(dfull1, 1); tc::mbar_init(dfull2, 1); tc::mbar_init(&cfree[0], 1); tc::mbar_init(&cfree[1], 1);
+        tc::mbar_fence_init();
+        *accb1 = 0.f;
+    }
+    for (int i = tid; i < H; i += NTH) { b0s[i] = p.b0[i]; w1s[i] = p.w1r0[i]; accw1[i] = 0.f; }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t d1 = tmem_base, d2 = tmem_base + 256;
+    const uint32_t idesc1 = tc::make_idesc(2, 2, TM, H), idesc2 = tc::make_idesc(2, 2, TM, KT);
+    const uint32_t a_sbo = (uint32_t)(KT / 4) * 128, w_sbo = (KSL / 4) * 128, c_sbo = (HCH / 4) * 128;
+
+    int64_t g_issue = 0, g_mma = 0;            // driver state: ring slot counters
+    const int64_t my_blocks = blockIdx.x < nblocks ? (nblocks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t total_slots = my_blocks * NQ7 * J;
+    uint32_t tcount = 0;                       // tiles processed (parity of dfull1 / dfull2)
+    uint32_t cf_commits[2] = {0, 0};           // commits issued on cfree[buf] so far
+
+    // driver helpers -----------------------------------------------------------------------------
+    auto ring_prefetch = [&]() {
+        while (g_issue < total_slots && g_issue < g_mma + NST) {
+            const int st = (int)(g_issue % NST);
+            tc::mbar_wait(&empty[st], (uint32_t)(((g_issue / NST) & 1) ^ 1));
+            mbar_expect_tx(&full[st], slot_bytes);
+            bulk_copy_g2s(wst + (size_t)st * slot_bytes, p.Wtc + (size_t)(g_issue % J) * p.slot_floats, slot_bytes, &full[st]);
+            ++g_issue;
+        }
+    };
+
+    for (int64_t lb = 0; lb < my_blocks; ++lb) {
+        const int64_t sb = blockIdx.x + lb * gridDim.x;
+        // upstream gradients -> per-query SDF gradients of this block (adjoint of fields.py:245-256)
+        if (tid < TM) {
+            const int64_t n = sb * TM + tid;
+            float gq[NQ7];
+#pragma unroll
+            for (int r = 0; r < NQ7; ++r) gq[r] = 0.f;
+            if (n < p.n) {
+                float sd[NQ7];
+#pragma unroll
+                for (int r = 0; r < NQ7; ++r) sd[r] = p.sdf7[n * NQ7 + r];
+                float g[3], h[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const float e = p.units[k];
+                    g[k] = (sd[1 + 2 * k] - sd[2 + 2 * k]) / (2.f * e);
+                    h[k] = (sd[1 + 2 * k] + sd[2 + 2 * k] - 2.f * sd[0]) / (e * e);
+                }
+                const float D = g[0] * g[0] + g[1] * g[1] + g[2] * g[2] + 1e-5f;
+                const float nh = (g[0] * h[0] + g[1] * h[1] + g[2] * h[2]) / D;
+                const float gh = p.g_hess ? p.g_hess[n] : 0.f;
+                gq[0] = p.g_sdf ? p.g_sdf[n] : 0.f;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const float e = p.units[k];
+                    const float Gk = (p.g_grad ? p.g_grad[n * 3 + k] : 0.f) + gh * (h[k] / D - 2.f * g[k] * nh / D);
+                    const float Hk = gh * g[k] / D;
+                    gq[1 + 2 * k] = Gk / (2.f * e) + Hk / (e * e);
+                    gq[2 + 2 * k] = -Gk / (2.f * e) + Hk / (e * e);
+                    gq[0] -= 2.f * Hk / (e * e);
+                }
+            }
+            float tot = 0.f;
+#pragma unroll
+            for (int r = 0; r < NQ7; ++r) { gqs[r * TM + tid] = gq[r]; tot += gq[r]; }
+            if (tot != 0.f) atomicAdd(accb1, tot);
+        }
+        for (int q = 0; q < NQ7; ++q) {
+            const int64_t tile_row0 = ((int64_t)(sb * NQ7 + q)) * TM;
+            // ---- gather -----------------------------------------------------------------------------
+            bwd_gather(p, sb, q, tile_row0, a_hi, a_lo);
+            tc::fence_async_smem();
+            tc::fence_before_sync();
+            __syncthreads();
+            tc::fence_after_sync();
+            // ---- GEMM1 -------------------------------------------------------------------------------
+            if (tid == 0) {
+                for (int s = 0; s < S; ++s) {
+                    ring_prefetch();
+                    const int st = (int)(g_mma % NST);
+                    tc::mbar_wait(&full[st], (uint32_t)((g_mma / NST) & 1));
+                    tc::fence_after_sync();
+                    const uint32_t w_hi = tc::smem_u32(wst + (size_t)st * slot_bytes), w_lo = w_hi + (uint32_t)H * KSL * 4;
+                    const uint32_t ah = tc::smem_u32(a_hi) + s * (KSL / 8) * 256, al = tc::smem_u32(a_lo) + s * (KSL / 8) * 256;
+#pragma unroll
+                    for (int ks = 0; ks < KSL / 8; ++ks) {
+                        const uint64_t adh = tc::make_smem_desc(ah + ks * 256, 128, a_sbo), adl = tc::make_smem_desc(al + ks * 256, 128, a_sbo);
+                        const uint64_t wdh = tc::make_smem_desc(w_hi + ks * 256, 128, w_sbo), wdl = tc::make_smem_desc(w_lo + ks * 256, 128, w_sbo);
+                        tc::mma_tf32_ss(d1, adh, wdh, idesc1, (s | ks) != 0);
+                        tc::mma_tf32_ss(d1, adh, wdl, idesc1, 1);
+                        tc::mma_tf32_ss(d1, adl, wdh, idesc1, 1);
+                    }
+                    tc::mma_commit(&empty[st]);
+                    ++g_mma;
+                }
+                tc::mma_commit(dfull1);
+                ring_prefetch();
+            }
+            tc::mbar_wait(dfull1, tcount & 1);
+            tc::fence_after_sync();
+            // ---- epilogue-1 + GEMM-dA, chunk by chunk over the hidden units -----------------------------------
+            const int64_t n = sb * TM + row;
+            const float gq = gqs[q * TM + row];
+            const bool centre = (q == 0) && n < p.n;
+            for (int c = 0; c < NCH; ++c) {
+                const int buf = c & 1;
+                uint8_t* ch_hi = smem + (size_t)buf * 2 * c_part;
+                uint8_t* ch_lo = ch_hi + c_part;
+                if (c >= 2) tc::mbar_wait(&cfree[buf], (cf_commits[buf] - 1) & 1);
+                const int col0 = c * HCH + half * 16;
+                float v[16];
+                tc::tmem_ld16(d1 + ((uint32_t)(lq * 32) << 16) + col0, v);
+                float sp[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float sg;
+                    softplus100_fast_both(v[j] + b0s[col0 + j], sp[j], sg);
+                    float dpost = gq * w1s[col0 + j];
+                    if (centre && p.dHc) dpost += __ldg(p.dHc + (size_t)n * H + col0 + j);
+                    v[j] = dpost * sg;                                   // dPre
+                }
+                float4* dst = reinterpret_cast<float4*>(p.dpre + (size_t)(tile_row0 + row) * H + col0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 d4 = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    dst[j] = d4;
+                    const float4 hi = split_hi(d4);
+                    const uint32_t off = tc::tile_off_b32(row, half * 16 + 4 * j, HCH / 4);
+                    *reinterpret_cast<float4*>(ch_hi + off) = hi;
+                    *reinterpret_cast<float4*>(ch_lo + off) = split_lo(d4, hi);
+                }
+                if (centre && p.spc) {
+                    float4* sdst = reinterpret_cast<float4*>(p.spc + (size_t)n * H + col0);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) sdst[j] = make_float4(sp[4 * j], sp[4 * j + 1], sp[4 * j + 2], sp[4 * j + 3]);
+                }
+                // dW1[0, col] += sum_rows gq * softplus : butterfly over the warp's 32 rows
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float w = gq * sp[j];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+                    if (lane == j && w != 0.f) atomicAdd(&accw1[col0 + j], w);
+                }
+                tc::fence_async_smem();
+                tc::fence_before_sync();
+                __syncthreads();
+                tc::fence_after_sync();
+                if (tid == 0) {
+                    ring_prefetch();
+                    const int st = (int)(g_mma % NST);
+                    tc::mbar_wait(&full[st], (uint32_t)((g_mma / NST) & 1));
+                    tc::fence_after_sync();
+                    const uint32_t w_hi = tc::smem_u32(wst + (size_t)st * slot_bytes), w_lo = w_hi + (uint32_t)KT * HCH * 4;
+                    const uint32_t ah = tc::smem_u32(ch_hi), al = tc::smem_u32(ch_lo);
+#pragma unroll
+                    for (int ks = 0; ks < HCH / 8; ++ks) {
+                        const uint64_t adh = tc::make_smem_desc(ah + ks * 256, 128, c_sbo), adl = tc::make_smem_desc(al + ks * 256, 128, c_sbo);
+                        const uint64_t wdh = tc::make_smem_desc(w_hi + ks * 256, 128, c_sbo), wdl = tc::make_smem_desc(w_lo + ks * 256, 128, c_sbo);
+                        tc::mma_tf32_ss(d2, adh, wdh, idesc2, (c | ks) != 0);
+                        tc::mma_tf32_ss(d2, adh, wdl, idesc2, 1);
+                        tc::mma_tf32_ss(d2, adl, wdh, idesc2, 1);
+                    }
+                    tc::mma_commit(&empty[st]);
+                    tc::mma_commit(&cfree[buf]);
+                    ++g_mma;
+                    if (c == NCH - 1) tc::mma_commit(dfull2);
+                    ring_prefetch();
+                }
+                ++cf_commits[buf];
+            }
+            tc::mbar_wait(dfull2, tcount & 1);
+            tc::fence_after_sync();
+            ++tcount;
+            // ---- dA: TMEM -> shared memory (fp32, row-major) ----------------------------------------------------
+            for (int c0 = half * 16; c0 < KT; c0 += 32) {
+                float v[16];
+                tc::tmem_ld16(d2 + ((uint32_t)(lq * 32) << 16) + c0, v);
+                float4* dst = reinterpret_cast<float4*>(dAs + (size_t)row * DAS + c0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+            tc::fence_before_sync();
+            __syncthreads();
+            tc::fence_after_sync();
+            // ---- scatter: d plane += w * (dA . line), d line += w * (dA . plane) ----------------------------------
+            {
+                const bool has_level = p.level != nullptr;
+                for (int u = warp; u < (TM / 8) * 3; u += NTH / 32) {
+                    const int rg = u / 3, i = u % 3;
+                    const int r2 = rg * 8 + (lane & 7);
+                    const int64_t n2 = sb * TM + r2;
+                    if (n2 >= p.n) continue;
+                    const float x[3] = {p.xyz[n2 * 3 + 0], p.xyz[n2 * 3 + 1], p.xyz[n2 * 3 + 2]};
+                    float pt[3];
+                    stencil_point(x, p.units, q, pt);
+                    const VmTaps taps = vm_taps(p.f, pt, has_level ? p.level[n2] : 0.f, has_level, i);
+                    float* pm0 = mut_of(taps.pt0, p.f.plane[i], p.g.plane[i], p.f.plane_mip[i], p.g.plane_mip[i]);
+                    float* pm1 = mut_of(taps.pt1, p.f.plane[i], p.g.plane[i], p.f.plane_mip[i], p.g.plane_mip[i]);
+                    float* lm0 = mut_of(taps.lt0, p.f.line[i], p.g.line[i], p.f.line_mip[i], p.g.line_mip[i]);
+                    float* lm1 = mut_of(taps.lt1, p.f.line[i], p.g.line[i], p.f.line_mip[i], p.g.line_mip[i]);
+                    for (int c4 = lane >> 3; c4 < C4; c4 += 4) {
+                        float4 P, L;
+                        vm_fetch(taps, C, c4 * 4, P, L);
+                        const float4 d = *reinterpret_cast<const float4*>(dAs + (size_t)r2 * DAS + (i * C4 + c4) * 4);
+                        vm_scatter_taps(taps, pm0, pm1, lm0, lm1, C, c4 * 4, f4_mul(d, L), f4_mul(d, P));
+                    }
+                }
+            }
+            __syncthreads();       // the next gather overwrites the A region
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < H; i += NTH)
+        if (accw1[i] != 0.f) atomicAdd(p.dW1r0 + i, accw1[i]);
+    if (tid == 0 && *accb1 != 0.f) atomicAdd(p.db1, *accb1);
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<512>(tmem_base);
+}
+
+}  // namespace
+
+int tf_internal_bwd_tc_slot_floats(int KT, int H) {
+    const int a = 2 * H * KSL, b = 2 * KT * HCH;
+    return a > b ? a : b;
+}
+size_t tf_internal_bwd_tc_wtc_floats(int KT, int H) { return (size_t)(KT / KSL + H / HCH) * tf_internal_bwd_tc_slot_floats(KT, H); }
+size_t tf_internal_bwd_tc_smem(int KT, int H) {
+    return (size_t)2 * TM * KT * 4 + (size_t)NST * tf_internal_bwd_tc_slot_floats(KT, H) * 4 + (size_t)3 * H * 4 + (size_t)NQ7 * TM * 4 +
+           (2 * NST + 4) * 8 + 32;
+}
+
+int tf_internal_bwd_tc_prep(const float* W0, int K, int KT, int H, float* wtc, cudaStream_t stream) {
+    tc_prep_bwd_kernel<<<64, 256, 0, stream>>>(W0, K, KT, H, tf_internal_bwd_tc_slot_floats(KT, H), wtc);
+    tf_count_launches(1);
+    return 0;
+}
+
+int tf_internal_bwd_tc_fold(const float* tmp, int H, int K, int KT, float* dW0, float* db0, cudaStream_t stream) {
+    tc_fold_wgrad_kernel<<<32, 256, 0, stream>>>(tmp, H, K, KT, dW0, db0);
+    tf_count_launches(1);
+    return 0;
+}
+
+// one slice of samples (n <= workspace capacity): activation-side backward
+int tf_internal_stencil_bwd_tc(const tf_vm_field_t* f, const tf_vm_mut_t* g, const tf_sdf_mlp_t* m, const float* wtc, const float* xyz,
+                               const float* level, int64_t n, const float units[3], const float* sdf7, const float* g_sdf,
+                               const float* g_grad, const float* g_hess, const float* dHc, float* dpre, float* arow, float* spc,
+                               float* dW1r0, float* db1, cudaStream_t stream) {
+    const int C = f->n_comp, K = 3 * C + 3, KT = (K + KSL - 1) / KSL * KSL, H = m->hidden;
+    TcBwdParams p = {};
+    p.f = *f; p.g = *g; p.xyz = xyz; p.level = level; p.n = n;
+    p.Wtc = wtc; p.b0 = m->b0; p.w1r0 = m->W1;
+    p.sdf7 = sdf7; p.g_sdf = g_sdf; p.g_grad = g_grad; p.g_hess = g_hess; p.dHc = dHc;
+    p.K = K; p.KT = KT; p.H = H; p.slot_floats = tf_internal_bwd_tc_slot_floats(KT, H);
+    for (int k = 0; k < 3; ++k) p.units[k] = units[k];
+    p.dpre = dpre; p.arow = arow; p.spc = spc; p.dW1r0 = dW1r0; p.db1 = db1;
+    const size_t smem = tf_internal_bwd_tc_smem(KT, H);
+    cudaFuncSetAttribute(sdf_stencil_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int64_t nblocks = (n + TM - 1) / TM;
+    const int grid = (int)(nblocks < tf_num_sms() ? nblocks : tf_num_sms());
+    sdf_stencil_bwd_tc_kernel<<<grid, NTH, smem, stream>>>(p);
+    tf_count_launches(1);
+    return 0;
+}
