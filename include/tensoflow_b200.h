@@ -245,6 +245,15 @@ TF_API int tf_csr_spmm3_bwd(const int32_t* rowptr, const int32_t* col, const flo
 TF_API int tf_tc_probe(const float* A, const float* B, int32_t N, int32_t K, int32_t passes, int32_t repeat,
                        float* D, tf_stream_t stream);
 
+/* ---- weight-gradient accumulate --------------------------------------------------------------
+ * out[m][n] += sum_r X[r][m] * Y[r][n]  (X [rows,M], Y [rows,N], out [M,N], all row-major fp32).
+ * This is the dW = dPre^T X product every nn.Linear backward of the path ends with
+ * (torch autograd's addmm in the reference: network/fields.py:192-198 decoder, other/material MLPs).
+ * Shapes with M in {128,256}, N % 16 == 0, N <= 256 run on tcgen05 (3xTF32, fp32-level accuracy);
+ * anything else on the FFMA kernel.  force_simt != 0 selects the FFMA kernel (A/B testing). */
+TF_API int tf_xty_accumulate(const float* X, const float* Y, int64_t rows, int32_t M, int32_t N, float* out,
+                             int32_t force_simt, tf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

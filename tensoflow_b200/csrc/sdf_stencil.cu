@@ -666,6 +666,8 @@ int tf_internal_xty(const float* X, int ldx, const float* Y, int ldy, int64_t ro
 int tf_internal_colsum(const float* X, int ldx, int64_t rows, int cols, float* out, cudaStream_t stream);
 int tf_internal_matmul(const float* A, int lda, const float* W, int ldw, int64_t M, int Kred, int Nout, float* out, int ldo,
                        cudaStream_t stream);
+bool tf_internal_xty_tc_ok(const float* X, const float* Y, int M, int N);
+int tf_internal_xty_tc(const float* X, const float* Y, int64_t rows, int M, int N, float* out, int ldo, int n_valid, cudaStream_t stream);
 
 static bool use_simt_bwd(const Dims& d) {
     const int KT = (d.K + 15) / 16 * 16;
@@ -720,9 +722,11 @@ static int stencil_bwd_tc(const tf_vm_field_t* f, const tf_sdf_mlp_t* m, const D
                                                g_mlp->W1, g_mlp->b1, stream))
             return e;
         // [dW0 | db0] staging += dPre^T [A | 1]
-        tf_internal_xty(dpre, H, arow, KT, nb * 128 * NQ, H, KT, tmp, KT, stream);
+        if (tf_internal_xty_tc_ok(dpre, arow, H, KT)) tf_internal_xty_tc(dpre, arow, nb * 128 * NQ, H, KT, tmp, KT, d.K + 1, stream);
+        else tf_internal_xty(dpre, H, arow, KT, nb * 128 * NQ, H, KT, tmp, KT, stream);
         if (gf) {
-            tf_internal_xty(gf, d.A, spc, H, ns, d.A, H, g_mlp->W1 + H, H, stream);
+            if (tf_internal_xty_tc_ok(gf, spc, d.A, H)) tf_internal_xty_tc(gf, spc, ns, d.A, H, g_mlp->W1 + H, H, H, stream);
+            else tf_internal_xty(gf, d.A, spc, H, ns, d.A, H, g_mlp->W1 + H, H, stream);
             tf_internal_colsum(gf, d.A, ns, d.A, g_mlp->b1 + 1, stream);
         }
     }

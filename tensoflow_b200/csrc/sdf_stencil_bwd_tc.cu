@@ -11,6 +11,7 @@
 //   scatter    : dA -> shared memory -> d plane / d line with vector reductions
 // Weight slices (W0 by K-slices for GEMM1, W0^T by hidden chunks for GEMM-dA) stream through one
 // 3-stage cp.async.bulk ring.  Weight gradients are finished by X^T Y passes over the workspace.
+#include <stdlib.h>
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -38,6 +39,8 @@ struct TcBwdParams {
     float* arow;             // [tiles*128][KT]
     float* spc;              // [n][H] centre hidden activations (NULL = not needed)
     float* dW1r0; float* db1;
+    int debug;               // TF_TC_BWD_DEBUG bitmask (timing experiments only): 1 no gather, 2 no workspace stores,
+                             // 4 no scatter, 8 no dW1 reduction, 16 no chunk loop
 };
 
 // slots 0..S-1   : W0 K-slices   [H rows x 16]  hi | lo   (GEMM1 B operand)
@@ -102,7 +105,7 @@ __device__ __forceinline__ void bwd_gather(const TcBwdParams& p, int64_t sb, int
         const int rg = u / 3, i = u % 3;
         const int row = rg * 8 + (lane & 7);
         const int64_t n = sb * TM + row;
-        const bool valid = n < p.n;
+        const bool valid = n < p.n && !(p.debug & 1);
         VmTaps taps;
         if (valid) {
             const float x[3] = {p.xyz[n * 3 + 0], p.xyz[n * 3 + 1], p.xyz[n * 3 + 2]};
@@ -122,7 +125,7 @@ __device__ __forceinline__ void bwd_gather(const TcBwdParams& p, int64_t sb, int
             const uint32_t off = tc::tile_off_b32(row, g * 4, kch);
             *reinterpret_cast<float4*>(a_hi + off) = hi;
             *reinterpret_cast<float4*>(a_lo + off) = split_lo(v, hi);
-            *reinterpret_cast<float4*>(p.arow + (size_t)(tile_row0 + row) * p.KT + g * 4) = v;
+            if (!(p.debug & 2)) *reinterpret_cast<float4*>(p.arow + (size_t)(tile_row0 + row) * p.KT + g * 4) = v;
         }
     }
     const int tail_g = G - 3 * C4;
@@ -282,7 +285,7 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_bwd_tc_kernel(TcBwdParams 
             const int64_t n = sb * TM + row;
             const float gq = gqs[q * TM + row];
             const bool centre = (q == 0) && n < p.n;
-            for (int c = 0; c < NCH; ++c) {
+            for (int c = 0; c < ((p.debug & 16) ? 0 : NCH); ++c) {
                 const int buf = c & 1;
                 uint8_t* ch_hi = smem + (size_t)buf * 2 * c_part;
                 uint8_t* ch_lo = ch_hi + c_part;
@@ -303,7 +306,7 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_bwd_tc_kernel(TcBwdParams 
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const float4 d4 = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                    dst[j] = d4;
+                    if (!(p.debug & 2)) dst[j] = d4;
                     const float4 hi = split_hi(d4);
                     const uint32_t off = tc::tile_off_b32(row, half * 16 + 4 * j, HCH / 4);
                     *reinterpret_cast<float4*>(ch_hi + off) = hi;
@@ -315,12 +318,23 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_bwd_tc_kernel(TcBwdParams 
                     for (int j = 0; j < 4; ++j) sdst[j] = make_float4(sp[4 * j], sp[4 * j + 1], sp[4 * j + 2], sp[4 * j + 3]);
                 }
                 // dW1[0, col] += sum_rows gq * softplus : butterfly over the warp's 32 rows
+                if (!(p.debug & 8)) {
+                    // 16 column sums over the warp's 32 rows with 16 shuffles: every exchange halves the columns a lane owns
+                    float w8[8], w4[4], w2[2];
+                    const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4, b2 = lane & 2;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    float w = gq * sp[j];
+                    for (int j = 0; j < 8; ++j) {
+                        const float lo_v = gq * sp[j], hi_v = gq * sp[j + 8];
+                        w8[j] = (b16 ? hi_v : lo_v) + __shfl_xor_sync(0xffffffffu, b16 ? lo_v : hi_v, 16);
+                    }
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
-                    if (lane == j && w != 0.f) atomicAdd(&accw1[col0 + j], w);
+                    for (int j = 0; j < 4; ++j) w4[j] = (b8 ? w8[j + 4] : w8[j]) + __shfl_xor_sync(0xffffffffu, b8 ? w8[j] : w8[j + 4], 8);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) w2[j] = (b4 ? w4[j + 2] : w4[j]) + __shfl_xor_sync(0xffffffffu, b4 ? w4[j] : w4[j + 2], 4);
+                    float w1 = (b2 ? w2[1] : w2[0]) + __shfl_xor_sync(0xffffffffu, b2 ? w2[0] : w2[1], 2);
+                    w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
+                    const int col = (b16 ? 8 : 0) + (b8 ? 4 : 0) + (b4 ? 2 : 0) + (b2 ? 1 : 0);
+                    if (!(lane & 1) && w1 != 0.f) atomicAdd(&accw1[col0 + col], w1);
                 }
                 tc::fence_async_smem();
                 tc::fence_before_sync();
@@ -349,7 +363,7 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_bwd_tc_kernel(TcBwdParams 
                 }
                 ++cf_commits[buf];
             }
-            tc::mbar_wait(dfull2, tcount & 1);
+            if (!(p.debug & 16)) tc::mbar_wait(dfull2, tcount & 1);
             tc::fence_after_sync();
             ++tcount;
             // ---- dA: TMEM -> shared memory (fp32, row-major) ----------------------------------------------------
@@ -370,7 +384,7 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_bwd_tc_kernel(TcBwdParams 
                     const int rg = u / 3, i = u % 3;
                     const int r2 = rg * 8 + (lane & 7);
                     const int64_t n2 = sb * TM + r2;
-                    if (n2 >= p.n) continue;
+                    if (n2 >= p.n || (p.debug & 4)) continue;
                     const float x[3] = {p.xyz[n2 * 3 + 0], p.xyz[n2 * 3 + 1], p.xyz[n2 * 3 + 2]};
                     float pt[3];
                     stencil_point(x, p.units, q, pt);
@@ -436,6 +450,7 @@ int tf_internal_stencil_bwd_tc(const tf_vm_field_t* f, const tf_vm_mut_t* g, con
     p.K = K; p.KT = KT; p.H = H; p.slot_floats = tf_internal_bwd_tc_slot_floats(KT, H);
     for (int k = 0; k < 3; ++k) p.units[k] = units[k];
     p.dpre = dpre; p.arow = arow; p.spc = spc; p.dW1r0 = dW1r0; p.db1 = db1;
+    { const char* e = getenv("TF_TC_BWD_DEBUG"); p.debug = e ? atoi(e) : 0; }
     const size_t smem = tf_internal_bwd_tc_smem(KT, H);
     cudaFuncSetAttribute(sdf_stencil_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int64_t nblocks = (n + TM - 1) / TM;

@@ -1,0 +1,169 @@
+// Weight-gradient GEMM on the tensor cores: out[m][n] += sum_r X[r][m] * Y[r][n]   (X^T Y over a long row axis).
+//
+// X [rows][M] and Y [rows][N] are row-major fp32 in HBM (dPre and the gathered feature rows of the stencil
+// backward; g_feat and the centre hidden activations of the appearance head).  The GEMM-K axis (rows) is the
+// slow axis in memory, the tensor core wants it fastest (K-major operands; tf32 MN-major operands read back
+// as zeros on this part), so the staging step transposes in registers: a thread loads the same 4-column group
+// of 4 consecutive rows (coalesced float4 reads), which is a 4x4 block = four 16-byte K-major units, splits
+// them into tf32 hi/lo (3xTF32, fp32-level accuracy) and stores them conflict-free (row-group stride padded
+// by 16 bytes).  One persistent CTA per SM streams its row range through a 2-stage shared-memory pipeline
+// (32 rows per stage) and accumulates [M x N] fp32 in TMEM; the kernel is HBM-bound (one pass over X and Y).
+// Partial sums are added to `out` with atomics at the end.
+#include <stdlib.h>
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int RS = 32;                        // rows (GEMM K) per stage
+constexpr int NTH = 256;
+constexpr uint32_t SBO = (RS / 4) * 128 + 16;   // 8-row-group stride of a staged operand (padded: bank spread)
+
+__device__ __forceinline__ float4 hi4(float4 v) { return make_float4(tc::tf32_rn(v.x), tc::tf32_rn(v.y), tc::tf32_rn(v.z), tc::tf32_rn(v.w)); }
+__device__ __forceinline__ float4 lo4(float4 v, float4 h) {
+    return make_float4(tc::tf32_rn(v.x - h.x), tc::tf32_rn(v.y - h.y), tc::tf32_rn(v.z - h.z), tc::tf32_rn(v.w - h.w));
+}
+
+// stage rows [r0, r0+32) of src [rows][W] as the K-major operand [W][32]: unit (w, c) = rows 4c..4c+3 of column w
+__device__ __forceinline__ void load_split(const float* __restrict__ src, int64_t r0, int64_t r_end, int W, uint8_t* hi, uint8_t* lo) {
+    const int G = W / 4;
+    for (int it = threadIdx.x; it < (RS / 4) * G; it += NTH) {
+        const int g = it % G, c = it / G;
+        float4 v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int64_t r = r0 + c * 4 + i;
+            v[i] = r < r_end ? ldg4(src + (size_t)r * W + g * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const float4 t[4] = {make_float4(v[0].x, v[1].x, v[2].x, v[3].x), make_float4(v[0].y, v[1].y, v[2].y, v[3].y),
+                             make_float4(v[0].z, v[1].z, v[2].z, v[3].z), make_float4(v[0].w, v[1].w, v[2].w, v[3].w)};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int w = g * 4 + j;
+            const uint32_t off = (uint32_t)(w >> 3) * SBO + c * 128 + (w & 7) * 16;
+            const float4 h = hi4(t[j]);
+            *reinterpret_cast<float4*>(hi + off) = h;
+            *reinterpret_cast<float4*>(lo + off) = lo4(t[j], h);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(NTH, 1) xty_tc_kernel(const float* __restrict__ X, const float* __restrict__ Y, int64_t rows, int M, int N,
+                                                        float* __restrict__ out, int ldo, int n_valid, int64_t rows_per_cta) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t x_part = (uint32_t)(M / 8) * SBO, y_part = (uint32_t)(N / 8) * SBO;
+    const uint32_t stage_bytes = 2 * (x_part + y_part);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * stage_bytes);
+    uint64_t* empty = bars;          // [2]
+    uint64_t* done = bars + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int MT = M / 128;
+    const int ncol_tile = N <= 128 ? 128 : 256;      // TMEM column stride between the M tiles
+
+    if (warp == 0) tc::tmem_alloc<512>(tmem_slot);
+    if (tid == 0) {
+        tc::mbar_init(&empty[0], 1); tc::mbar_init(&empty[1], 1); tc::mbar_init(done, 1);
+        tc::mbar_fence_init();
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t idesc = tc::make_idesc(2, 2, 128, N);
+
+    const int64_t r_begin = (int64_t)blockIdx.x * rows_per_cta;
+    const int64_t r_end = r_begin + rows_per_cta < rows ? r_begin + rows_per_cta : rows;
+    const int64_t n_stages = r_begin < r_end ? (r_end - r_begin + RS - 1) / RS : 0;
+
+    for (int64_t it = 0; it < n_stages; ++it) {
+        const int buf = (int)(it & 1);
+        uint8_t* xs_hi = smem + (size_t)buf * stage_bytes;
+        uint8_t* xs_lo = xs_hi + x_part;
+        uint8_t* ys_hi = xs_lo + x_part;
+        uint8_t* ys_lo = ys_hi + y_part;
+        if (it >= 2) tc::mbar_wait(&empty[buf], (uint32_t)(((it >> 1) - 1) & 1));
+        const int64_t r0 = r_begin + it * RS;
+        load_split(X, r0, r_end, M, xs_hi, xs_lo);
+        load_split(Y, r0, r_end, N, ys_hi, ys_lo);
+        tc::fence_async_smem();
+        tc::fence_before_sync();
+        __syncthreads();
+        tc::fence_after_sync();
+        if (tid == 0) {
+            const uint32_t xh = tc::smem_u32(xs_hi), xl = tc::smem_u32(xs_lo), yh = tc::smem_u32(ys_hi), yl = tc::smem_u32(ys_lo);
+#pragma unroll 1
+            for (int ks = 0; ks < RS / 8; ++ks) {
+                const uint64_t bdh = tc::make_smem_desc(yh + ks * 256, 128, SBO), bdl = tc::make_smem_desc(yl + ks * 256, 128, SBO);
+                for (int mt = 0; mt < MT; ++mt) {
+                    const uint32_t d = tmem_base + (uint32_t)mt * ncol_tile;
+                    const uint64_t adh = tc::make_smem_desc(xh + mt * 16 * SBO + ks * 256, 128, SBO);
+                    const uint64_t adl = tc::make_smem_desc(xl + mt * 16 * SBO + ks * 256, 128, SBO);
+                    tc::mma_tf32_ss(d, adh, bdh, idesc, (it | ks) != 0);
+                    tc::mma_tf32_ss(d, adh, bdl, idesc, 1);
+                    tc::mma_tf32_ss(d, adl, bdh, idesc, 1);
+                }
+            }
+            tc::mma_commit(&empty[buf]);
+            if (it == n_stages - 1) tc::mma_commit(done);
+        }
+    }
+    if (n_stages > 0) {
+        tc::mbar_wait(done, 0);
+        tc::fence_after_sync();
+        const int lq = warp & 3, half = warp >> 2;
+        for (int mt = 0; mt < MT; ++mt) {
+            const int m = mt * 128 + lq * 32 + lane;
+            for (int c0 = half * 16; c0 < N; c0 += 32) {
+                float v[16];
+                tc::tmem_ld16(tmem_base + (uint32_t)mt * ncol_tile + ((uint32_t)(lq * 32) << 16) + c0, v);
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (c0 + j < n_valid && v[j] != 0.f) atomicAdd(out + (size_t)m * ldo + c0 + j, v[j]);
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<512>(tmem_base);
+}
+
+size_t xty_tc_smem(int M, int N) { return (size_t)2 * 2 * ((M / 8) + (N / 8)) * SBO + 64; }
+
+}  // namespace
+
+// true when the shapes suit the tensor-core kernel (otherwise callers use the SIMT X^T Y kernel)
+bool tf_internal_xty_tc_ok(const float* X, const float* Y, int M, int N) {
+    if (M % 128 != 0 || M > 256 || N % 16 != 0 || N < 16 || N > 256) return false;
+    if ((M / 128) * (N <= 128 ? 128 : 256) > 512) return false;
+    if (((uintptr_t)X & 15) || ((uintptr_t)Y & 15)) return false;
+    return xty_tc_smem(M, N) <= 227 * 1024;
+}
+
+// X [rows][M] (ld = M), Y [rows][N] (ld = N); out[m][n] (ld = ldo) += X^T Y for n < n_valid
+int tf_internal_xty_tc(const float* X, const float* Y, int64_t rows, int M, int N, float* out, int ldo, int n_valid, cudaStream_t stream) {
+    if (rows == 0) return 0;
+    const size_t smem = xty_tc_smem(M, N);
+    cudaFuncSetAttribute(xty_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int64_t grid = (rows + 4 * RS - 1) / (4 * RS);
+    if (grid > tf_num_sms()) grid = tf_num_sms();
+    int64_t rpc = (rows + grid - 1) / grid;
+    rpc = (rpc + RS - 1) / RS * RS;
+    grid = (rows + rpc - 1) / rpc;
+    xty_tc_kernel<<<(int)grid, NTH, smem, stream>>>(X, Y, rows, M, N, out, ldo, n_valid, rpc);
+    tf_count_launches(1);
+    return 0;
+}
+
+int tf_internal_xty(const float* X, int ldx, const float* Y, int ldy, int64_t rows, int M, int N, float* out, int ldo, cudaStream_t stream);
+
+extern "C" TF_API int tf_xty_accumulate(const float* X, const float* Y, int64_t rows, int32_t M, int32_t N, float* out,
+                                        int32_t force_simt, tf_stream_t stream_) {
+    if (rows == 0) return 0;
+    TF_REQUIRE(X && Y && out && M > 0 && N > 0, "tf_xty_accumulate: NULL pointer or bad shape (%d,%d)", M, N);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!force_simt && tf_internal_xty_tc_ok(X, Y, M, N)) tf_internal_xty_tc(X, Y, rows, M, N, out, N, N, stream);
+    else tf_internal_xty(X, M, Y, N, rows, M, N, out, N, stream);
+    TF_CHECK_LAUNCH("tf_xty_accumulate");
+    return 0;
+}

@@ -35,3 +35,26 @@ def test_tcgen05_gemm_matches_fp64(N, K):
     print(f"N={N} K={K}: tf32 {e1:.2e}  3xtf32 {e3:.2e}  fp32 {e32:.2e}")
     assert e1 < 5e-3, e1          # plain tf32: ~1e-3
     assert e3 < 2e-6, e3          # split: fp32 level
+
+
+@pytest.mark.parametrize("rows,M,N", [(1000, 256, 112), (4099, 128, 256), (31, 128, 16), (20000, 256, 64)])
+def test_xty_tensor_core_matches_fp64(rows, M, N):
+    """dW = X^T Y on tcgen05 with MN-major operands straight from row-major HBM tensors."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from tensoflow_b200 import _lib
+    from tensoflow_b200._lib import check, ptr, stream_ptr
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(rows + M + N)
+    X = torch.randn(rows, M, generator=g).to(dev)
+    Y = torch.randn(rows, N, generator=g).to(dev)
+    ref = X.double().T @ Y.double()
+    outs = []
+    for force_simt in (0, 1):
+        out = torch.ones(M, N, device=dev)
+        check(_lib.load().tf_xty_accumulate(ptr(X), ptr(Y), rows, M, N, ptr(out), force_simt, stream_ptr()), "tf_xty_accumulate")
+        torch.cuda.synchronize()
+        outs.append(out)
+        e = float((out.double() - 1 - ref).abs().max() / ref.abs().max())
+        print(f"rows={rows} M={M} N={N} simt={force_simt}: {e:.2e}")
+        assert e < 5e-6, e
