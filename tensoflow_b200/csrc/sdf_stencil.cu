@@ -657,6 +657,7 @@ static size_t bwd_slice_floats(const Dims& d, int64_t n_slice) {
 size_t tf_internal_bwd_tc_wtc_floats(int KT, int H);
 size_t tf_internal_bwd_tc_smem(int KT, int H);
 int tf_internal_bwd_tc_prep(const float* W0, int K, int KT, int H, float* wtc, cudaStream_t stream);
+int tf_internal_bwd_tc_samples_per_tile();
 int tf_internal_bwd_tc_fold(const float* tmp, int H, int K, int KT, float* dW0, float* db0, cudaStream_t stream);
 int tf_internal_stencil_bwd_tc(const tf_vm_field_t* f, const tf_vm_mut_t* g, const tf_sdf_mlp_t* m, const float* wtc, const float* xyz,
                                const float* level, int64_t n, const float units[3], const float* sdf7, const float* g_sdf,
@@ -673,21 +674,25 @@ static bool use_simt_bwd(const Dims& d) {
     const int KT = (d.K + 15) / 16 * 16;
     return use_simt_path(d) || d.C % 4 != 0 || KT > 256 || tf_internal_bwd_tc_smem(KT, d.H) > 227 * 1024;
 }
-// tensor-core backward workspace: [W slices | dW0/db0 staging | per 128-sample block: dPre, A rows, centre hidden, dHidden(centre)]
+// tensor-core backward workspace: [W slices | dW0/db0 staging | per tile of 18 samples: dPre [128,H], A rows [128,KT],
+// centre hidden [18,H], dHidden(centre) [18,H]]
 static size_t bwd_tc_fixed_floats(const Dims& d) {
     const int KT = (d.K + 15) / 16 * 16;
     return tf_internal_bwd_tc_wtc_floats(KT, d.H) + (size_t)d.H * KT;
 }
-static size_t bwd_tc_block_floats(const Dims& d) {
-    const int KT = (d.K + 15) / 16 * 16;
-    return (size_t)128 * ((size_t)NQ * d.H + (size_t)NQ * KT + 2 * (size_t)d.H);
+static size_t bwd_tc_tile_floats(const Dims& d) {
+    const int KT = (d.K + 15) / 16 * 16, spt = tf_internal_bwd_tc_samples_per_tile();
+    return (size_t)128 * (d.H + KT) + 2 * (size_t)spt * d.H;
 }
 
 extern "C" TF_API size_t tf_sdf_stencil_bwd_workspace(const tf_vm_field_t* f, const tf_sdf_mlp_t* m, int64_t n_slice) {
     Dims d;
     if (!f || !m || check_mlp(f, m, d)) return 0;
     if (n_slice < 1) n_slice = 1;
-    if (!use_simt_bwd(d)) return (bwd_tc_fixed_floats(d) + (size_t)((n_slice + 127) / 128) * bwd_tc_block_floats(d)) * sizeof(float);
+    if (!use_simt_bwd(d)) {
+        const int spt = tf_internal_bwd_tc_samples_per_tile();
+        return (bwd_tc_fixed_floats(d) + (size_t)((n_slice + spt - 1) / spt) * bwd_tc_tile_floats(d)) * sizeof(float);
+    }
     return (weights_ws_floats(d) + bwd_slice_floats(d, n_slice)) * sizeof(float);
 }
 
@@ -696,23 +701,24 @@ static int stencil_bwd_tc(const tf_vm_field_t* f, const tf_sdf_mlp_t* m, const D
                           const float* g_hess, const tf_vm_mut_t* g_field, const tf_sdf_mlp_grad_t* g_mlp, float* ws, size_t ws_floats,
                           cudaStream_t stream) {
     const int KT = (d.K + 15) / 16 * 16, H = d.H;
-    const size_t fixed = bwd_tc_fixed_floats(d), per_block = bwd_tc_block_floats(d);
-    TF_REQUIRE(ws_floats >= fixed + per_block, "workspace too small (%zu bytes)", ws_floats * sizeof(float));
-    int64_t blocks_fit = (int64_t)((ws_floats - fixed) / per_block);
-    const int64_t nblocks_all = (n + 127) / 128;
-    if (blocks_fit > nblocks_all) blocks_fit = nblocks_all;
+    const int spt = tf_internal_bwd_tc_samples_per_tile();
+    const size_t fixed = bwd_tc_fixed_floats(d), per_tile = bwd_tc_tile_floats(d);
+    TF_REQUIRE(ws_floats >= fixed + per_tile, "workspace too small (%zu bytes)", ws_floats * sizeof(float));
+    int64_t tiles_fit = (int64_t)((ws_floats - fixed) / per_tile);
+    const int64_t ntiles_all = (n + spt - 1) / spt;
+    if (tiles_fit > ntiles_all) tiles_fit = ntiles_all;
     float* wtc = ws;
     float* tmp = wtc + tf_internal_bwd_tc_wtc_floats(KT, H);
     float* dpre = tmp + (size_t)H * KT;
-    float* arow = dpre + (size_t)blocks_fit * 128 * NQ * H;
-    float* spc = arow + (size_t)blocks_fit * 128 * NQ * KT;
-    float* dHc = spc + (size_t)blocks_fit * 128 * H;
+    float* arow = dpre + (size_t)tiles_fit * 128 * H;
+    float* spc = arow + (size_t)tiles_fit * 128 * KT;
+    float* dHc = spc + (size_t)tiles_fit * spt * H;
     tf_internal_bwd_tc_prep(m->W0, d.K, KT, H, wtc, stream);
     cudaMemsetAsync(tmp, 0, (size_t)H * KT * sizeof(float), stream);
-    for (int64_t b0 = 0; b0 < nblocks_all; b0 += blocks_fit) {
-        const int64_t nb = b0 + blocks_fit < nblocks_all ? blocks_fit : nblocks_all - b0;
-        const int64_t s0 = b0 * 128;
-        const int64_t ns = s0 + nb * 128 < n ? nb * 128 : n - s0;
+    for (int64_t t0 = 0; t0 < ntiles_all; t0 += tiles_fit) {
+        const int64_t nt = t0 + tiles_fit < ntiles_all ? tiles_fit : ntiles_all - t0;
+        const int64_t s0 = t0 * spt;
+        const int64_t ns = s0 + nt * spt < n ? nt * spt : n - s0;
         const float* gf = g_feat ? g_feat + s0 * d.A : nullptr;
         // dHidden(centre) = g_feat W1[1:, :]
         if (gf) tf_internal_matmul(gf, d.A, m->W1 + H, H, ns, d.A, H, dHc, H, stream);
@@ -722,8 +728,8 @@ static int stencil_bwd_tc(const tf_vm_field_t* f, const tf_sdf_mlp_t* m, const D
                                                g_mlp->W1, g_mlp->b1, stream))
             return e;
         // [dW0 | db0] staging += dPre^T [A | 1]
-        if (tf_internal_xty_tc_ok(dpre, arow, H, KT)) tf_internal_xty_tc(dpre, arow, nb * 128 * NQ, H, KT, tmp, KT, d.K + 1, stream);
-        else tf_internal_xty(dpre, H, arow, KT, nb * 128 * NQ, H, KT, tmp, KT, stream);
+        if (tf_internal_xty_tc_ok(dpre, arow, H, KT)) tf_internal_xty_tc(dpre, arow, nt * 128, H, KT, tmp, KT, d.K + 1, stream);
+        else tf_internal_xty(dpre, H, arow, KT, nt * 128, H, KT, tmp, KT, stream);
         if (gf) {
             if (tf_internal_xty_tc_ok(gf, spc, d.A, H)) tf_internal_xty_tc(gf, spc, ns, d.A, H, g_mlp->W1 + H, H, H, stream);
             else tf_internal_xty(gf, d.A, spc, H, ns, d.A, H, g_mlp->W1 + H, H, stream);

@@ -1,6 +1,7 @@
 // Fused TensoSDF stencil backward (activation side) on the 5th-gen tensor cores, sm_100a.
 //
-// Per MMA tile (128 rows = one stencil query of a 128-sample block):
+// Per MMA tile (128 rows = 18 samples x 7 stencil queries, sample-major so that the queries of a sample share
+// their plane / line fetches and their scatter reductions, stencil_site.cuh):
 //   gather     : features -> A operand (tf32 hi/lo, canonical K-major layout) + fp32 copy to the
 //                workspace (`arow`, with a constant-1 column so that dPre^T [A|1] yields dW0 and db0)
 //   GEMM1      : pre = A W0^T on tcgen05 (3xTF32), accumulator D1 [128 x H] in TMEM
@@ -14,6 +15,7 @@
 #include <stdlib.h>
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "stencil_site.cuh"
 
 namespace {
 
@@ -21,7 +23,7 @@ constexpr int TM = 128;
 constexpr int NQ7 = 7;
 constexpr int KSL = 16;     // K slice of GEMM1
 constexpr int HCH = 32;     // hidden chunk of epilogue-1 / GEMM-dA
-constexpr int NST = 3;
+constexpr int NST = 2;
 constexpr int NTH = 256;
 
 struct TcBwdParams {
@@ -88,70 +90,11 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar)), "r"(bytes) : "memory");
 }
 
-__device__ __forceinline__ float4 split_hi(float4 v) { return make_float4(tc::tf32_rn(v.x), tc::tf32_rn(v.y), tc::tf32_rn(v.z), tc::tf32_rn(v.w)); }
-__device__ __forceinline__ float4 split_lo(float4 v, float4 h) {
-    return make_float4(tc::tf32_rn(v.x - h.x), tc::tf32_rn(v.y - h.y), tc::tf32_rn(v.z - h.z), tc::tf32_rn(v.w - h.w));
-}
-
-__device__ __forceinline__ float* mut_of(const float* p, const float* base0, float* g0, const float* basem, float* gm) {
-    return p == base0 ? g0 : gm + (p - basem);
-}
-
-__device__ __forceinline__ void bwd_gather(const TcBwdParams& p, int64_t sb, int q, int64_t tile_row0, uint8_t* a_hi, uint8_t* a_lo) {
-    const int C = p.f.n_comp, C4 = C / 4, G = p.KT / 4, kch = p.KT / 4;
-    const bool has_level = p.level != nullptr;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int u = warp; u < (TM / 8) * 3; u += NTH / 32) {
-        const int rg = u / 3, i = u % 3;
-        const int row = rg * 8 + (lane & 7);
-        const int64_t n = sb * TM + row;
-        const bool valid = n < p.n && !(p.debug & 1);
-        VmTaps taps;
-        if (valid) {
-            const float x[3] = {p.xyz[n * 3 + 0], p.xyz[n * 3 + 1], p.xyz[n * 3 + 2]};
-            float pt[3];
-            stencil_point(x, p.units, q, pt);
-            taps = vm_taps(p.f, pt, has_level ? p.level[n] : 0.f, has_level, i);
-        }
-        for (int c4 = lane >> 3; c4 < C4; c4 += 4) {
-            float4 v = f4_zero();
-            if (valid) {
-                float4 P, L;
-                vm_fetch(taps, C, c4 * 4, P, L);
-                v = f4_mul(P, L);
-            }
-            const int g = i * C4 + c4;
-            const float4 hi = split_hi(v);
-            const uint32_t off = tc::tile_off_b32(row, g * 4, kch);
-            *reinterpret_cast<float4*>(a_hi + off) = hi;
-            *reinterpret_cast<float4*>(a_lo + off) = split_lo(v, hi);
-            if (!(p.debug & 2)) *reinterpret_cast<float4*>(p.arow + (size_t)(tile_row0 + row) * p.KT + g * 4) = v;
-        }
-    }
-    const int tail_g = G - 3 * C4;
-    for (int it = threadIdx.x; it < TM * tail_g; it += NTH) {
-        const int row = it % TM, g = 3 * C4 + it / TM;
-        const int64_t n = sb * TM + row;
-        float4 v = f4_zero(), vh = f4_zero();
-        if (g == 3 * C4 && n < p.n) {
-            const float x[3] = {p.xyz[n * 3 + 0], p.xyz[n * 3 + 1], p.xyz[n * 3 + 2]};
-            float pt[3];
-            stencil_point(x, p.units, q, pt);
-            v = make_float4(pt[0], pt[1], pt[2], 0.f);
-            vh = make_float4(pt[0], pt[1], pt[2], 1.f);          // ones column -> db0 through the X^T Y pass
-        }
-        const float4 hi = split_hi(v);
-        const uint32_t off = tc::tile_off_b32(row, g * 4, kch);
-        *reinterpret_cast<float4*>(a_hi + off) = hi;
-        *reinterpret_cast<float4*>(a_lo + off) = split_lo(v, hi);
-        *reinterpret_cast<float4*>(p.arow + (size_t)(tile_row0 + row) * p.KT + g * 4) = vh;
-    }
-}
-
 __global__ void __launch_bounds__(NTH, 1) sdf_stencil_bwd_tc_kernel(TcBwdParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const int H = p.H, KT = p.KT, S = KT / KSL, NCH = H / HCH, J = S + NCH, C = p.f.n_comp, C4 = C / 4;
-    const uint32_t a_part = (uint32_t)TM * KT * 4;
+    const int H = p.H, KT = p.KT, S = KT / KSL, NCH = H / HCH, J = S + NCH;
+    constexpr int SPT = site::SPT;
+    const uint32_t a_part = site::a_part_bytes(KT);
     const uint32_t slot_bytes = (uint32_t)p.slot_floats * 4;
     const uint32_t c_part = (uint32_t)TM * HCH * 4;                // one dPre chunk part (16 KB)
     const int DAS = KT + 4;                                        // row stride of the dA tile
@@ -161,8 +104,8 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_bwd_tc_kernel(TcBwdParams 
     float* b0s = reinterpret_cast<float*>(wst + (size_t)NST * slot_bytes);
     float* w1s = b0s + H;
     float* accw1 = w1s + H;                                        // per-CTA dW1[0,:]
-    float* gqs = accw1 + H;                                        // [7][TM]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(gqs + NQ7 * TM);
+    float* gqs = accw1 + H;                                        // [TM] upstream gradient of each row's SDF value
+    uint64_t* bars = reinterpret_cast<uint64_t*>(gqs + TM);
     uint64_t* full = bars;
     uint64_t* empty = bars + NST;
     uint64_t* dfull1 = bars + 2 * NST;
@@ -175,7 +118,8 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_bwd_tc_kernel(TcBwdParams 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int lq = warp & 3, half = warp >> 2;
     const int row = lq * 32 + lane;
-    const int64_t nblocks = (p.n + TM - 1) / TM;
+    const int row_s = row / NQ7, row_q = row - row_s * NQ7;
+    const int64_t ntiles = (p.n + SPT - 1) / SPT;
 
     if (warp == 0) tc::tmem_alloc<512>(tmem_slot);
     if (tid == 0) {
@@ -191,15 +135,13 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_bwd_tc_kernel(TcBwdParams 
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t d1 = tmem_base, d2 = tmem_base + 256;
     const uint32_t idesc1 = tc::make_idesc(2, 2, TM, H), idesc2 = tc::make_idesc(2, 2, TM, KT);
-    const uint32_t a_sbo = (uint32_t)(KT / 4) * 128, w_sbo = (KSL / 4) * 128, c_sbo = (HCH / 4) * 128;
+    const uint32_t a_sbo = site::a_sbo(KT), a_kstep = 2 * site::A_LBO, w_sbo = (KSL / 4) * 128, c_sbo = (HCH / 4) * 128;
 
     int64_t g_issue = 0, g_mma = 0;            // driver state: ring slot counters
-    const int64_t my_blocks = blockIdx.x < nblocks ? (nblocks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const int64_t total_slots = my_blocks * NQ7 * J;
-    uint32_t tcount = 0;                       // tiles processed (parity of dfull1 / dfull2)
+    const int64_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t total_slots = my_tiles * J;
     uint32_t cf_commits[2] = {0, 0};           // commits issued on cfree[buf] so far
 
-    // driver helpers -----------------------------------------------------------------------------
     auto ring_prefetch = [&]() {
         while (g_issue < total_slots && g_issue < g_mma + NST) {
             const int st = (int)(g_issue % NST);
@@ -210,11 +152,14 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_bwd_tc_kernel(TcBwdParams 
         }
     };
 
-    for (int64_t lb = 0; lb < my_blocks; ++lb) {
-        const int64_t sb = blockIdx.x + lb * gridDim.x;
-        // upstream gradients -> per-query SDF gradients of this block (adjoint of fields.py:245-256)
-        if (tid < TM) {
-            const int64_t n = sb * TM + tid;
+    for (int64_t lt = 0; lt < my_tiles; ++lt) {
+        const int64_t tile = blockIdx.x + lt * gridDim.x;
+        const int64_t s_base = tile * SPT;
+        const int64_t tile_row0 = tile * TM;
+        const uint32_t tpar = (uint32_t)(lt & 1);
+        // upstream gradients -> per-query SDF gradients of the tile's samples (adjoint of fields.py:245-256)
+        if (tid < SPT) {
+            const int64_t n = s_base + tid;
             float gq[NQ7];
 #pragma unroll
             for (int r = 0; r < NQ7; ++r) gq[r] = 0.f;
@@ -245,164 +190,140 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_bwd_tc_kernel(TcBwdParams 
             }
             float tot = 0.f;
 #pragma unroll
-            for (int r = 0; r < NQ7; ++r) { gqs[r * TM + tid] = gq[r]; tot += gq[r]; }
+            for (int r = 0; r < NQ7; ++r) { gqs[tid * NQ7 + r] = gq[r]; tot += gq[r]; }
             if (tot != 0.f) atomicAdd(accb1, tot);
+        } else if (tid < SPT + 2) {
+            gqs[SPT * NQ7 + tid - SPT] = 0.f;
         }
-        for (int q = 0; q < NQ7; ++q) {
-            const int64_t tile_row0 = ((int64_t)(sb * NQ7 + q)) * TM;
-            // ---- gather -----------------------------------------------------------------------------
-            bwd_gather(p, sb, q, tile_row0, a_hi, a_lo);
+        // ---- gather -----------------------------------------------------------------------------
+        if (!(p.debug & 1))
+            site::gather_tile(p.f, p.xyz, p.level, p.n, p.units, s_base, KT, a_hi, a_lo, (p.debug & 2) ? nullptr : p.arow + (size_t)tile_row0 * KT, NTH);
+        tc::fence_async_smem();
+        tc::fence_before_sync();
+        __syncthreads();
+        tc::fence_after_sync();
+        // ---- GEMM1 -------------------------------------------------------------------------------
+        if (tid == 0) {
+            for (int s = 0; s < S; ++s) {
+                ring_prefetch();
+                const int st = (int)(g_mma % NST);
+                tc::mbar_wait(&full[st], (uint32_t)((g_mma / NST) & 1));
+                tc::fence_after_sync();
+                const uint32_t w_hi = tc::smem_u32(wst + (size_t)st * slot_bytes), w_lo = w_hi + (uint32_t)H * KSL * 4;
+                const uint32_t ah = tc::smem_u32(a_hi) + s * (KSL / 8) * a_kstep, al = tc::smem_u32(a_lo) + s * (KSL / 8) * a_kstep;
+#pragma unroll
+                for (int ks = 0; ks < KSL / 8; ++ks) {
+                    const uint64_t adh = tc::make_smem_desc(ah + ks * a_kstep, site::A_LBO, a_sbo), adl = tc::make_smem_desc(al + ks * a_kstep, site::A_LBO, a_sbo);
+                    const uint64_t wdh = tc::make_smem_desc(w_hi + ks * 256, 128, w_sbo), wdl = tc::make_smem_desc(w_lo + ks * 256, 128, w_sbo);
+                    tc::mma_tf32_ss(d1, adh, wdh, idesc1, (s | ks) != 0);
+                    tc::mma_tf32_ss(d1, adh, wdl, idesc1, 1);
+                    tc::mma_tf32_ss(d1, adl, wdh, idesc1, 1);
+                }
+                tc::mma_commit(&empty[st]);
+                ++g_mma;
+            }
+            tc::mma_commit(dfull1);
+            ring_prefetch();
+        }
+        tc::mbar_wait(dfull1, tpar);
+        tc::fence_after_sync();
+        // ---- epilogue-1 + GEMM-dA, chunk by chunk over the hidden units -----------------------------------
+        const int64_t n = s_base + row_s;
+        const float gq = gqs[row];
+        const bool centre = row_q == 0 && row_s < SPT && n < p.n;
+        for (int c = 0; c < ((p.debug & 16) ? 0 : NCH); ++c) {
+            const int buf = c & 1;
+            uint8_t* ch_hi = smem + (size_t)buf * 2 * c_part;
+            uint8_t* ch_lo = ch_hi + c_part;
+            if (c >= 2) tc::mbar_wait(&cfree[buf], (cf_commits[buf] - 1) & 1);
+            const int col0 = c * HCH + half * 16;
+            float v[16];
+            tc::tmem_ld16(d1 + ((uint32_t)(lq * 32) << 16) + col0, v);
+            float sp[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float sg;
+                softplus100_fast_both(v[j] + b0s[col0 + j], sp[j], sg);
+                float dpost = gq * w1s[col0 + j];
+                if (centre && p.dHc) dpost += __ldg(p.dHc + (size_t)n * H + col0 + j);
+                v[j] = dpost * sg;                                   // dPre
+            }
+            float4* dst = reinterpret_cast<float4*>(p.dpre + (size_t)(tile_row0 + row) * H + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 d4 = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                if (!(p.debug & 2)) dst[j] = d4;
+                const float4 hi = site::tf32_hi(d4);
+                const uint32_t off = tc::tile_off_b32(row, half * 16 + 4 * j, HCH / 4);
+                *reinterpret_cast<float4*>(ch_hi + off) = hi;
+                *reinterpret_cast<float4*>(ch_lo + off) = site::tf32_lo(d4, hi);
+            }
+            if (centre && p.spc) {
+                float4* sdst = reinterpret_cast<float4*>(p.spc + (size_t)n * H + col0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) sdst[j] = make_float4(sp[4 * j], sp[4 * j + 1], sp[4 * j + 2], sp[4 * j + 3]);
+            }
+            if (!(p.debug & 8)) {
+                // 16 column sums over the warp's 32 rows with 16 shuffles: every exchange halves the columns a lane owns
+                float w8[8], w4[4], w2[2];
+                const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4, b2 = lane & 2;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float lo_v = gq * sp[j], hi_v = gq * sp[j + 8];
+                    w8[j] = (b16 ? hi_v : lo_v) + __shfl_xor_sync(0xffffffffu, b16 ? lo_v : hi_v, 16);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) w4[j] = (b8 ? w8[j + 4] : w8[j]) + __shfl_xor_sync(0xffffffffu, b8 ? w8[j] : w8[j + 4], 8);
+#pragma unroll
+                for (int j = 0; j < 2; ++j) w2[j] = (b4 ? w4[j + 2] : w4[j]) + __shfl_xor_sync(0xffffffffu, b4 ? w4[j] : w4[j + 2], 4);
+                float w1 = (b2 ? w2[1] : w2[0]) + __shfl_xor_sync(0xffffffffu, b2 ? w2[0] : w2[1], 2);
+                w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
+                const int col = (b16 ? 8 : 0) + (b8 ? 4 : 0) + (b4 ? 2 : 0) + (b2 ? 1 : 0);
+                if (!(lane & 1) && w1 != 0.f) atomicAdd(&accw1[col0 + col], w1);
+            }
             tc::fence_async_smem();
             tc::fence_before_sync();
             __syncthreads();
             tc::fence_after_sync();
-            // ---- GEMM1 -------------------------------------------------------------------------------
             if (tid == 0) {
-                for (int s = 0; s < S; ++s) {
-                    ring_prefetch();
-                    const int st = (int)(g_mma % NST);
-                    tc::mbar_wait(&full[st], (uint32_t)((g_mma / NST) & 1));
-                    tc::fence_after_sync();
-                    const uint32_t w_hi = tc::smem_u32(wst + (size_t)st * slot_bytes), w_lo = w_hi + (uint32_t)H * KSL * 4;
-                    const uint32_t ah = tc::smem_u32(a_hi) + s * (KSL / 8) * 256, al = tc::smem_u32(a_lo) + s * (KSL / 8) * 256;
+                ring_prefetch();
+                const int st = (int)(g_mma % NST);
+                tc::mbar_wait(&full[st], (uint32_t)((g_mma / NST) & 1));
+                tc::fence_after_sync();
+                const uint32_t w_hi = tc::smem_u32(wst + (size_t)st * slot_bytes), w_lo = w_hi + (uint32_t)KT * HCH * 4;
+                const uint32_t ah = tc::smem_u32(ch_hi), al = tc::smem_u32(ch_lo);
 #pragma unroll
-                    for (int ks = 0; ks < KSL / 8; ++ks) {
-                        const uint64_t adh = tc::make_smem_desc(ah + ks * 256, 128, a_sbo), adl = tc::make_smem_desc(al + ks * 256, 128, a_sbo);
-                        const uint64_t wdh = tc::make_smem_desc(w_hi + ks * 256, 128, w_sbo), wdl = tc::make_smem_desc(w_lo + ks * 256, 128, w_sbo);
-                        tc::mma_tf32_ss(d1, adh, wdh, idesc1, (s | ks) != 0);
-                        tc::mma_tf32_ss(d1, adh, wdl, idesc1, 1);
-                        tc::mma_tf32_ss(d1, adl, wdh, idesc1, 1);
-                    }
-                    tc::mma_commit(&empty[st]);
-                    ++g_mma;
+                for (int ks = 0; ks < HCH / 8; ++ks) {
+                    const uint64_t adh = tc::make_smem_desc(ah + ks * 256, 128, c_sbo), adl = tc::make_smem_desc(al + ks * 256, 128, c_sbo);
+                    const uint64_t wdh = tc::make_smem_desc(w_hi + ks * 256, 128, c_sbo), wdl = tc::make_smem_desc(w_lo + ks * 256, 128, c_sbo);
+                    tc::mma_tf32_ss(d2, adh, wdh, idesc2, (c | ks) != 0);
+                    tc::mma_tf32_ss(d2, adh, wdl, idesc2, 1);
+                    tc::mma_tf32_ss(d2, adl, wdh, idesc2, 1);
                 }
-                tc::mma_commit(dfull1);
+                tc::mma_commit(&empty[st]);
+                tc::mma_commit(&cfree[buf]);
+                ++g_mma;
+                if (c == NCH - 1) tc::mma_commit(dfull2);
                 ring_prefetch();
             }
-            tc::mbar_wait(dfull1, tcount & 1);
-            tc::fence_after_sync();
-            // ---- epilogue-1 + GEMM-dA, chunk by chunk over the hidden units -----------------------------------
-            const int64_t n = sb * TM + row;
-            const float gq = gqs[q * TM + row];
-            const bool centre = (q == 0) && n < p.n;
-            for (int c = 0; c < ((p.debug & 16) ? 0 : NCH); ++c) {
-                const int buf = c & 1;
-                uint8_t* ch_hi = smem + (size_t)buf * 2 * c_part;
-                uint8_t* ch_lo = ch_hi + c_part;
-                if (c >= 2) tc::mbar_wait(&cfree[buf], (cf_commits[buf] - 1) & 1);
-                const int col0 = c * HCH + half * 16;
-                float v[16];
-                tc::tmem_ld16(d1 + ((uint32_t)(lq * 32) << 16) + col0, v);
-                float sp[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    float sg;
-                    softplus100_fast_both(v[j] + b0s[col0 + j], sp[j], sg);
-                    float dpost = gq * w1s[col0 + j];
-                    if (centre && p.dHc) dpost += __ldg(p.dHc + (size_t)n * H + col0 + j);
-                    v[j] = dpost * sg;                                   // dPre
-                }
-                float4* dst = reinterpret_cast<float4*>(p.dpre + (size_t)(tile_row0 + row) * H + col0);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float4 d4 = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                    if (!(p.debug & 2)) dst[j] = d4;
-                    const float4 hi = split_hi(d4);
-                    const uint32_t off = tc::tile_off_b32(row, half * 16 + 4 * j, HCH / 4);
-                    *reinterpret_cast<float4*>(ch_hi + off) = hi;
-                    *reinterpret_cast<float4*>(ch_lo + off) = split_lo(d4, hi);
-                }
-                if (centre && p.spc) {
-                    float4* sdst = reinterpret_cast<float4*>(p.spc + (size_t)n * H + col0);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) sdst[j] = make_float4(sp[4 * j], sp[4 * j + 1], sp[4 * j + 2], sp[4 * j + 3]);
-                }
-                // dW1[0, col] += sum_rows gq * softplus : butterfly over the warp's 32 rows
-                if (!(p.debug & 8)) {
-                    // 16 column sums over the warp's 32 rows with 16 shuffles: every exchange halves the columns a lane owns
-                    float w8[8], w4[4], w2[2];
-                    const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4, b2 = lane & 2;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float lo_v = gq * sp[j], hi_v = gq * sp[j + 8];
-                        w8[j] = (b16 ? hi_v : lo_v) + __shfl_xor_sync(0xffffffffu, b16 ? lo_v : hi_v, 16);
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) w4[j] = (b8 ? w8[j + 4] : w8[j]) + __shfl_xor_sync(0xffffffffu, b8 ? w8[j] : w8[j + 4], 8);
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) w2[j] = (b4 ? w4[j + 2] : w4[j]) + __shfl_xor_sync(0xffffffffu, b4 ? w4[j] : w4[j + 2], 4);
-                    float w1 = (b2 ? w2[1] : w2[0]) + __shfl_xor_sync(0xffffffffu, b2 ? w2[0] : w2[1], 2);
-                    w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
-                    const int col = (b16 ? 8 : 0) + (b8 ? 4 : 0) + (b4 ? 2 : 0) + (b2 ? 1 : 0);
-                    if (!(lane & 1) && w1 != 0.f) atomicAdd(&accw1[col0 + col], w1);
-                }
-                tc::fence_async_smem();
-                tc::fence_before_sync();
-                __syncthreads();
-                tc::fence_after_sync();
-                if (tid == 0) {
-                    ring_prefetch();
-                    const int st = (int)(g_mma % NST);
-                    tc::mbar_wait(&full[st], (uint32_t)((g_mma / NST) & 1));
-                    tc::fence_after_sync();
-                    const uint32_t w_hi = tc::smem_u32(wst + (size_t)st * slot_bytes), w_lo = w_hi + (uint32_t)KT * HCH * 4;
-                    const uint32_t ah = tc::smem_u32(ch_hi), al = tc::smem_u32(ch_lo);
-#pragma unroll
-                    for (int ks = 0; ks < HCH / 8; ++ks) {
-                        const uint64_t adh = tc::make_smem_desc(ah + ks * 256, 128, c_sbo), adl = tc::make_smem_desc(al + ks * 256, 128, c_sbo);
-                        const uint64_t wdh = tc::make_smem_desc(w_hi + ks * 256, 128, c_sbo), wdl = tc::make_smem_desc(w_lo + ks * 256, 128, c_sbo);
-                        tc::mma_tf32_ss(d2, adh, wdh, idesc2, (c | ks) != 0);
-                        tc::mma_tf32_ss(d2, adh, wdl, idesc2, 1);
-                        tc::mma_tf32_ss(d2, adl, wdh, idesc2, 1);
-                    }
-                    tc::mma_commit(&empty[st]);
-                    tc::mma_commit(&cfree[buf]);
-                    ++g_mma;
-                    if (c == NCH - 1) tc::mma_commit(dfull2);
-                    ring_prefetch();
-                }
-                ++cf_commits[buf];
-            }
-            if (!(p.debug & 16)) tc::mbar_wait(dfull2, tcount & 1);
-            tc::fence_after_sync();
-            ++tcount;
-            // ---- dA: TMEM -> shared memory (fp32, row-major) ----------------------------------------------------
-            for (int c0 = half * 16; c0 < KT; c0 += 32) {
-                float v[16];
-                tc::tmem_ld16(d2 + ((uint32_t)(lq * 32) << 16) + c0, v);
-                float4* dst = reinterpret_cast<float4*>(dAs + (size_t)row * DAS + c0);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            }
-            tc::fence_before_sync();
-            __syncthreads();
-            tc::fence_after_sync();
-            // ---- scatter: d plane += w * (dA . line), d line += w * (dA . plane) ----------------------------------
-            {
-                const bool has_level = p.level != nullptr;
-                for (int u = warp; u < (TM / 8) * 3; u += NTH / 32) {
-                    const int rg = u / 3, i = u % 3;
-                    const int r2 = rg * 8 + (lane & 7);
-                    const int64_t n2 = sb * TM + r2;
-                    if (n2 >= p.n || (p.debug & 4)) continue;
-                    const float x[3] = {p.xyz[n2 * 3 + 0], p.xyz[n2 * 3 + 1], p.xyz[n2 * 3 + 2]};
-                    float pt[3];
-                    stencil_point(x, p.units, q, pt);
-                    const VmTaps taps = vm_taps(p.f, pt, has_level ? p.level[n2] : 0.f, has_level, i);
-                    float* pm0 = mut_of(taps.pt0, p.f.plane[i], p.g.plane[i], p.f.plane_mip[i], p.g.plane_mip[i]);
-                    float* pm1 = mut_of(taps.pt1, p.f.plane[i], p.g.plane[i], p.f.plane_mip[i], p.g.plane_mip[i]);
-                    float* lm0 = mut_of(taps.lt0, p.f.line[i], p.g.line[i], p.f.line_mip[i], p.g.line_mip[i]);
-                    float* lm1 = mut_of(taps.lt1, p.f.line[i], p.g.line[i], p.f.line_mip[i], p.g.line_mip[i]);
-                    for (int c4 = lane >> 3; c4 < C4; c4 += 4) {
-                        float4 P, L;
-                        vm_fetch(taps, C, c4 * 4, P, L);
-                        const float4 d = *reinterpret_cast<const float4*>(dAs + (size_t)r2 * DAS + (i * C4 + c4) * 4);
-                        vm_scatter_taps(taps, pm0, pm1, lm0, lm1, C, c4 * 4, f4_mul(d, L), f4_mul(d, P));
-                    }
-                }
-            }
-            __syncthreads();       // the next gather overwrites the A region
+            ++cf_commits[buf];
         }
+        if (!(p.debug & 16)) tc::mbar_wait(dfull2, tpar);
+        tc::fence_after_sync();
+        // ---- dA: TMEM -> shared memory (fp32, row-major) ----------------------------------------------------
+        for (int c0 = half * 16; c0 < KT; c0 += 32) {
+            float v[16];
+            tc::tmem_ld16(d2 + ((uint32_t)(lq * 32) << 16) + c0, v);
+            float4* dst = reinterpret_cast<float4*>(dAs + (size_t)row * DAS + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        tc::fence_before_sync();
+        __syncthreads();
+        tc::fence_after_sync();
+        // ---- scatter: d plane += w * (dA . line), d line += w * (dA . plane) ----------------------------------
+        if (!(p.debug & 4)) site::scatter_tile(p.f, p.g, p.xyz, p.level, p.n, p.units, s_base, dAs, DAS, NTH);
+        __syncthreads();       // the next gather overwrites the A region
     }
     __syncthreads();
     for (int i = tid; i < H; i += NTH)
@@ -421,8 +342,8 @@ int tf_internal_bwd_tc_slot_floats(int KT, int H) {
 }
 size_t tf_internal_bwd_tc_wtc_floats(int KT, int H) { return (size_t)(KT / KSL + H / HCH) * tf_internal_bwd_tc_slot_floats(KT, H); }
 size_t tf_internal_bwd_tc_smem(int KT, int H) {
-    return (size_t)2 * TM * KT * 4 + (size_t)NST * tf_internal_bwd_tc_slot_floats(KT, H) * 4 + (size_t)3 * H * 4 + (size_t)NQ7 * TM * 4 +
-           (2 * NST + 4) * 8 + 32;
+    return (size_t)2 * 16 * (KT / 4) * site::A_LBO + (size_t)NST * tf_internal_bwd_tc_slot_floats(KT, H) * 4 + (size_t)3 * H * 4 +
+           (size_t)TM * 4 + (2 * NST + 4) * 8 + 32;
 }
 
 int tf_internal_bwd_tc_prep(const float* W0, int K, int KT, int H, float* wtc, cudaStream_t stream) {
@@ -436,6 +357,8 @@ int tf_internal_bwd_tc_fold(const float* tmp, int H, int K, int KT, float* dW0, 
     tf_count_launches(1);
     return 0;
 }
+
+int tf_internal_bwd_tc_samples_per_tile() { return site::SPT; }
 
 // one slice of samples (n <= workspace capacity): activation-side backward
 int tf_internal_stencil_bwd_tc(const tf_vm_field_t* f, const tf_vm_mut_t* g, const tf_sdf_mlp_t* m, const float* wtc, const float* xyz,
@@ -453,8 +376,8 @@ int tf_internal_stencil_bwd_tc(const tf_vm_field_t* f, const tf_vm_mut_t* g, con
     { const char* e = getenv("TF_TC_BWD_DEBUG"); p.debug = e ? atoi(e) : 0; }
     const size_t smem = tf_internal_bwd_tc_smem(KT, H);
     cudaFuncSetAttribute(sdf_stencil_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const int64_t nblocks = (n + TM - 1) / TM;
-    const int grid = (int)(nblocks < tf_num_sms() ? nblocks : tf_num_sms());
+    const int64_t ntiles = (n + site::SPT - 1) / site::SPT;
+    const int grid = (int)(ntiles < tf_num_sms() ? ntiles : tf_num_sms());
     sdf_stencil_bwd_tc_kernel<<<grid, NTH, smem, stream>>>(p);
     tf_count_launches(1);
     return 0;

@@ -5,11 +5,12 @@
 // tcgen05.mma kind::tf32 with fp32-level accuracy from operand splitting
 // (x = hi + lo, D = A_hi W_hi + A_hi W_lo + A_lo W_hi: "3xTF32").
 //
-// One persistent CTA (256 threads) per SM walks "sample blocks" of 128 samples; each block is
-// 7 MMA tiles (one per stencil query: centre, +-x, +-y, +-z) of M = 128 rows:
-//   gather  : all threads; lane -> (row = lane%8, channel group) so that texel reads are 64-byte
-//             runs and shared-memory stores are conflict free; values are split hi/lo and stored
-//             in the canonical K-major no-swizzle UMMA layout (tc_common.cuh)
+// One persistent CTA (256 threads) per SM walks MMA tiles of M = 128 rows.  In stencil mode a tile is
+// sample-major: 18 samples x 7 queries (centre, +-x, +-y, +-z) so that the queries of a sample share
+// their plane / line fetches (stencil_site.cuh); in SDF-only mode it is 128 samples:
+//   gather  : all threads; one (sample, plane, channel group) site per thread and pass, texel reads
+//             are 144-byte runs per site; values are split hi/lo and stored in the K-major no-swizzle
+//             UMMA layout with a padded K-chunk stride (conflict-free stores)
 //   W0      : pre-split / pre-tiled once per call into K-slices of 16 (prep kernel); slices stream
 //             L2 -> shared memory through a 3-stage ring with cp.async.bulk + mbarrier (one driver thread)
 //   MMA     : driver thread issues 6 tcgen05.mma per slice (2 k-steps x 3 passes), accumulator
@@ -17,17 +18,18 @@
 //   epilogue: overlaps the next tile's MMAs; tcgen05.ld -> +b0 -> Softplus(beta=100) -> dot with
 //             W1[0,:] (the SDF output; taps need nothing else) ; the centre tile also streams its
 //             hidden activations to HBM for the appearance head (second layer, [N,H] x [H,A])
-//   finalize: per block, the 7 SDF values -> sdf7, central-difference gradient, hessian term.
+//   finalize: per tile, the 7 SDF values of a sample -> sdf7, central-difference gradient, hessian term.
 #include <stdlib.h>
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "stencil_site.cuh"
 
 namespace {
 
 constexpr int TM = 128;     // rows per MMA tile = samples per block
 constexpr int NQ7 = 7;
 constexpr int KSL = 16;     // K-slice (2 tf32 MMA k-steps)
-constexpr int NST = 3;      // W ring stages
+constexpr int NST = 2;      // W ring stages
 constexpr int NTH = 256;
 
 struct TcParams {
@@ -71,10 +73,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar)), "r"(bytes) : "memory");
 }
 
-// gather the feature rows of MMA tile (block sb, query q) into the A operand (hi / lo parts)
-__device__ __forceinline__ void tc_gather(const TcParams& p, int64_t sb, int q, uint8_t* a_hi, uint8_t* a_lo) {
-    const int C = p.f.n_comp, C4 = C / 4, G = p.KT / 4;      // G float4 groups per row
-    const int kch = p.KT / 4;
+// SDF-only mode: gather the feature rows of 128 samples (one query each) into the A operand
+__device__ __forceinline__ void tc_gather_rows(const TcParams& p, int64_t s_base, uint8_t* a_hi, uint8_t* a_lo) {
+    const int C = p.f.n_comp, C4 = C / 4, G = p.KT / 4;
     const bool has_level = p.level != nullptr;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // unit = (8-row group, plane): lane -> (row = lane%8, channel groups lane/8, lane/8+4, ...); the
@@ -83,14 +84,12 @@ __device__ __forceinline__ void tc_gather(const TcParams& p, int64_t sb, int q, 
     for (int u = warp; u < n_units; u += NTH / 32) {
         const int rg = u / 3, i = u % 3;
         const int row = rg * 8 + (lane & 7);
-        const int64_t n = sb * TM + row;
+        const int64_t n = s_base + row;
         const bool valid = n < p.n;
         VmTaps taps;
         if (valid) {
             const float x[3] = {p.xyz[n * 3 + 0], p.xyz[n * 3 + 1], p.xyz[n * 3 + 2]};
-            float pt[3];
-            stencil_point(x, p.units, q, pt);
-            taps = vm_taps(p.f, pt, has_level ? p.level[n] : 0.f, has_level, i);
+            taps = vm_taps(p.f, x, has_level ? p.level[n] : 0.f, has_level, i);
         }
         for (int c4 = lane >> 3; c4 < C4; c4 += 4) {
             float4 v = f4_zero();
@@ -99,55 +98,47 @@ __device__ __forceinline__ void tc_gather(const TcParams& p, int64_t sb, int q, 
                 vm_fetch(taps, C, c4 * 4, P, L);
                 v = f4_mul(P, L);
             }
-            const float4 hi = make_float4(tc::tf32_rn(v.x), tc::tf32_rn(v.y), tc::tf32_rn(v.z), tc::tf32_rn(v.w));
-            const float4 lo = make_float4(tc::tf32_rn(v.x - hi.x), tc::tf32_rn(v.y - hi.y), tc::tf32_rn(v.z - hi.z), tc::tf32_rn(v.w - hi.w));
-            const uint32_t off = tc::tile_off_b32(row, (i * C4 + c4) * 4, kch);
-            *reinterpret_cast<float4*>(a_hi + off) = hi;
-            *reinterpret_cast<float4*>(a_lo + off) = lo;
+            site::put(a_hi, a_lo, site::a_off(row, i * C4 + c4, p.KT), v);
         }
     }
     // raw xyz (fields.py:265,298) + zero padding groups
     const int tail_g = G - 3 * C4;
     for (int it = threadIdx.x; it < TM * tail_g; it += NTH) {
         const int row = it % TM, g = 3 * C4 + it / TM;
-        const int64_t n = sb * TM + row;
+        const int64_t n = s_base + row;
         float4 v = f4_zero();
-        if (g == 3 * C4 && n < p.n) {
-            const float x[3] = {p.xyz[n * 3 + 0], p.xyz[n * 3 + 1], p.xyz[n * 3 + 2]};
-            float pt[3];
-            stencil_point(x, p.units, q, pt);
-            v = make_float4(pt[0], pt[1], pt[2], 0.f);
-        }
-        const float4 hi = make_float4(tc::tf32_rn(v.x), tc::tf32_rn(v.y), tc::tf32_rn(v.z), tc::tf32_rn(v.w));
-        const float4 lo = make_float4(tc::tf32_rn(v.x - hi.x), tc::tf32_rn(v.y - hi.y), tc::tf32_rn(v.z - hi.z), tc::tf32_rn(v.w - hi.w));
-        const uint32_t off = tc::tile_off_b32(row, g * 4, kch);
-        *reinterpret_cast<float4*>(a_hi + off) = hi;
-        *reinterpret_cast<float4*>(a_lo + off) = lo;
+        if (g == 3 * C4 && n < p.n) v = make_float4(p.xyz[n * 3 + 0], p.xyz[n * 3 + 1], p.xyz[n * 3 + 2], 0.f);
+        site::put(a_hi, a_lo, site::a_off(row, g, p.KT), v);
     }
+}
+
+__device__ __forceinline__ void tc_gather(const TcParams& p, int64_t tile, uint8_t* a_hi, uint8_t* a_lo) {
+    if (p.nq == NQ7) site::gather_tile(p.f, p.xyz, p.level, p.n, p.units, tile * site::SPT, p.KT, a_hi, a_lo, nullptr, NTH);
+    else tc_gather_rows(p, tile * TM, a_hi, a_lo);
 }
 
 __global__ void __launch_bounds__(NTH, 1) sdf_stencil_fwd_tc_kernel(TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int H = p.H, KT = p.KT, S = KT / KSL, nq = p.nq;
-    const uint32_t a_part = (uint32_t)TM * KT * 4;            // bytes of one A part
+    const int spt = nq == NQ7 ? site::SPT : TM;               // samples per tile
+    const uint32_t a_part = site::a_part_bytes(KT);           // bytes of one A part
     const uint32_t w_part = (uint32_t)H * KSL * 4;            // bytes of one W slice part
     uint8_t* a_hi = smem;
     uint8_t* a_lo = a_hi + a_part;
     uint8_t* wst = a_lo + a_part;                             // NST stages x (hi, lo)
     float* b0s = reinterpret_cast<float*>(wst + (size_t)NST * 2 * w_part);
     float* w1s = b0s + H;
-    float* sdfs = w1s + H;                                    // [2][7][TM]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sdfs + 2 * NQ7 * TM);
+    float* sdfs = w1s + H;                                    // [2 tiles][2 column halves][TM]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sdfs + 4 * TM);
     uint64_t* full = bars;                                    // [NST]
     uint64_t* empty = bars + NST;                             // [NST]
     uint64_t* dfull = bars + 2 * NST;                         // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t nblocks = (p.n + TM - 1) / TM;
-    // blocks of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
-    const int64_t my_blocks = blockIdx.x < nblocks ? (nblocks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const int64_t my_tiles = my_blocks * nq;
+    const int64_t ntiles = (p.n + spt - 1) / spt;
+    // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
+    const int64_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
     if (warp == 0) tc::tmem_alloc<512>(tmem_slot);
     if (tid == 0) {
@@ -156,15 +147,14 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_fwd_tc_kernel(TcParams p) 
         tc::mbar_fence_init();
     }
     for (int i = tid; i < H; i += NTH) { b0s[i] = p.b0[i]; w1s[i] = p.w1r0[i]; }
-    for (int i = tid; i < 2 * NQ7 * TM; i += NTH) sdfs[i] = 0.f;
-    if (my_tiles > 0) tc_gather(p, blockIdx.x, 0, a_hi, a_lo);
+    if (my_tiles > 0) tc_gather(p, blockIdx.x, a_hi, a_lo);
     tc::fence_async_smem();
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t idesc = tc::make_idesc(2, 2, TM, H);
-    const uint32_t a_sbo = (uint32_t)(KT / 4) * 128;
+    const uint32_t a_sbo = site::a_sbo(KT), a_kstep = 2 * site::A_LBO;
     const uint32_t w_sbo = (KSL / 4) * 128;
 
     int64_t g_issue = 0, g_mma = 0;                           // driver-thread state (W slice counters)
@@ -186,11 +176,11 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_fwd_tc_kernel(TcParams p) 
                 tc::mbar_wait(&full[st], (uint32_t)((g_mma / NST) & 1));
                 tc::fence_after_sync();
                 const uint32_t w_hi = tc::smem_u32(wst + (size_t)st * 2 * w_part), w_lo = w_hi + w_part;
-                const uint32_t ah = tc::smem_u32(a_hi) + s * (KSL / 8) * 256, al = tc::smem_u32(a_lo) + s * (KSL / 8) * 256;
+                const uint32_t ah = tc::smem_u32(a_hi) + s * (KSL / 8) * a_kstep, al = tc::smem_u32(a_lo) + s * (KSL / 8) * a_kstep;
 #pragma unroll
                 for (int ks = 0; ks < KSL / 8; ++ks) {
                     if (p.debug & 2) break;
-                    const uint64_t adh = tc::make_smem_desc(ah + ks * 256, 128, a_sbo), adl = tc::make_smem_desc(al + ks * 256, 128, a_sbo);
+                    const uint64_t adh = tc::make_smem_desc(ah + ks * a_kstep, site::A_LBO, a_sbo), adl = tc::make_smem_desc(al + ks * a_kstep, site::A_LBO, a_sbo);
                     const uint64_t wdh = tc::make_smem_desc(w_hi + ks * 256, 128, w_sbo), wdl = tc::make_smem_desc(w_lo + ks * 256, 128, w_sbo);
                     tc::mma_tf32_ss(dcol, adh, wdh, idesc, (s | ks) != 0);
                     tc::mma_tf32_ss(dcol, adh, wdl, idesc, 1);
@@ -204,14 +194,14 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_fwd_tc_kernel(TcParams p) 
         // ---- epilogue of tile t-1 (overlaps the MMAs of tile t) --------------------------------------
         if (t > 0) {
             const int64_t tp = t - 1;
-            const int64_t lb = tp / nq;                       // local block index
-            const int q = (int)(tp % nq);
-            const int64_t sb = blockIdx.x + lb * gridDim.x;
+            const int64_t tile = blockIdx.x + tp * gridDim.x;
             tc::mbar_wait(&dfull[tp & 1], (uint32_t)((tp >> 1) & 1));
             tc::fence_after_sync();
             const int lq = warp & 3, chh = warp >> 2;
             const int row = lq * 32 + lane;
-            const int64_t n = sb * TM + row;
+            const int s = row / nq, q = row - s * nq;
+            const int64_t n = tile * spt + s;
+            const bool centre = q == 0 && s < spt && n < p.n;
             const uint32_t dcol = tmem_base + (uint32_t)(tp & 1) * 256 + ((uint32_t)(lq * 32) << 16);
             float psum = 0.f;
             for (int c0 = chh * 32; c0 < H; c0 += 64) {
@@ -227,41 +217,39 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_fwd_tc_kernel(TcParams p) 
                     v[j + 2] = softplus100_fast(v[j + 2] + bb.z); psum = fmaf(v[j + 2], ww.z, psum);
                     v[j + 3] = softplus100_fast(v[j + 3] + bb.w); psum = fmaf(v[j + 3], ww.w, psum);
                 }
-                if (q == 0 && p.spc && n < p.n) {
+                if (centre && p.spc) {
                     float4* dst = reinterpret_cast<float4*>(p.spc + (size_t)n * H + c0);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 }
             }
-            atomicAdd(&sdfs[((lb & 1) * NQ7 + q) * TM + row], psum);
+            sdfs[((tp & 1) * 2 + chh) * TM + row] = psum;
             tc::fence_before_sync();
         }
         // ---- wait for the MMAs of tile t, then gather tile t+1 into the (now free) A buffer ---------------
         if (t < my_tiles) {
             tc::mbar_wait(&dfull[t & 1], (uint32_t)((t >> 1) & 1));
             if (t + 1 < my_tiles) {
-                const int64_t tn = t + 1;
-                if (!(p.debug & 1)) tc_gather(p, blockIdx.x + (tn / nq) * gridDim.x, (int)(tn % nq), a_hi, a_lo);
+                if (!(p.debug & 1)) tc_gather(p, blockIdx.x + (t + 1) * gridDim.x, a_hi, a_lo);
                 tc::fence_async_smem();
             }
         }
         tc::fence_before_sync();
         __syncthreads();
         tc::fence_after_sync();
-        // ---- finalize the block whose last tile's epilogue just completed -------------------------------
-        if (t > 0 && ((t - 1) % nq) == nq - 1 && tid < TM) {
-            const int64_t lb = (t - 1) / nq;
-            const int64_t n = (blockIdx.x + lb * gridDim.x) * TM + tid;
-            float* sp = &sdfs[(lb & 1) * NQ7 * TM + tid];
-            float sd[NQ7];
-#pragma unroll
-            for (int r = 0; r < NQ7; ++r) { sd[r] = r < nq ? sp[r * TM] + __ldg(p.b1) : 0.f; sp[r * TM] = 0.f; }
+        // ---- finalize the samples of tile t-1 ------------------------------------------------------------
+        if (t > 0 && tid < spt) {
+            const int64_t tp = t - 1;
+            const int64_t n = (blockIdx.x + tp * gridDim.x) * spt + tid;
+            const float* sp = &sdfs[(tp & 1) * 2 * TM + tid * nq];
             if (n < p.n) {
+                const float b1 = __ldg(p.b1);
                 if (nq == 1) {
-                    p.sdf1[n] = sd[0];
+                    p.sdf1[n] = sp[0] + sp[TM] + b1;
                 } else {
+                    float sd[NQ7];
 #pragma unroll
-                    for (int r = 0; r < NQ7; ++r) p.sdf7[n * NQ7 + r] = sd[r];
+                    for (int r = 0; r < NQ7; ++r) { sd[r] = sp[r] + sp[TM + r] + b1; p.sdf7[n * NQ7 + r] = sd[r]; }
                     float g[3], h[3];
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
@@ -282,7 +270,7 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_fwd_tc_kernel(TcParams p) 
 }  // namespace
 
 size_t tf_internal_tc_fwd_smem(int KT, int H) {
-    return (size_t)2 * TM * KT * 4 + (size_t)NST * 2 * H * KSL * 4 + (size_t)2 * H * 4 + (size_t)2 * NQ7 * TM * 4 + (2 * NST + 2) * 8 + 16;
+    return (size_t)2 * 16 * (KT / 4) * site::A_LBO + (size_t)NST * 2 * H * KSL * 4 + (size_t)2 * H * 4 + (size_t)4 * TM * 4 + (2 * NST + 2) * 8 + 16;
 }
 
 // workspace floats needed in front of spc: the pre-tiled W0
@@ -303,8 +291,9 @@ int tf_internal_stencil_fwd_tc(const tf_vm_field_t* f, const tf_sdf_mlp_t* m, co
     const size_t smem = tf_internal_tc_fwd_smem(KT, H);
     if (smem > 227 * 1024) { tf_set_error("tensor-core stencil: tile does not fit shared memory (KT=%d, H=%d)", KT, H); return 1; }
     cudaFuncSetAttribute(sdf_stencil_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const int64_t nblocks = (n + TM - 1) / TM;
-    const int grid = (int)(nblocks < tf_num_sms() ? nblocks : tf_num_sms());
+    const int spt = nq == NQ7 ? site::SPT : TM;
+    const int64_t ntiles = (n + spt - 1) / spt;
+    const int grid = (int)(ntiles < tf_num_sms() ? ntiles : tf_num_sms());
     sdf_stencil_fwd_tc_kernel<<<grid, NTH, smem, stream>>>(p);
     tf_count_launches(2);
     return 0;

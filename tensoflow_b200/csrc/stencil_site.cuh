@@ -1,0 +1,247 @@
+// Shared-stencil sampling of the VM field for the tensor-core decoder kernels.
+//
+// The 7 finite-difference queries of a sample (centre, +-x, +-y, +-z; reference network/fields.py:239-244)
+// move one coordinate at a time, and plane i only sees two of the three coordinates while line i sees the
+// third.  So of the 7 (plane, line) fetch pairs per plane index only 5 plane positions and 3 line positions
+// are distinct: 78 texel taps per sample and level instead of 126.  The values are bit-identical to sampling
+// every query on its own because the shared positions have identical coordinates.
+//
+// MMA tiles are therefore sample-major: row r = s * 7 + q for the 18 samples of a tile (126 rows, 2 zero rows),
+// so one thread produces / consumes all 7 rows of a (sample, plane, channel group) site.
+#pragma once
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace site {
+
+constexpr int NQ = 7;
+constexpr int SPT = 18;                 // samples per 128-row MMA tile (stencil mode)
+constexpr uint32_t A_LBO = 144;         // K-chunk stride of the A operand: 128-byte core matrix + 16 bytes (bank spread)
+
+__device__ __forceinline__ uint32_t a_sbo(int KT) { return (uint32_t)(KT / 4) * A_LBO; }
+__device__ __forceinline__ uint32_t a_part_bytes(int KT) { return 16u * a_sbo(KT); }
+// byte offset of the 16-byte unit (row r, column group g) in the A operand
+__device__ __forceinline__ uint32_t a_off(int r, int g, int KT) { return (uint32_t)(r >> 3) * a_sbo(KT) + (uint32_t)g * A_LBO + (uint32_t)(r & 7) * 16; }
+
+struct Levels {
+    const float* pt0; const float* pt1; const float* lt0; const float* lt1;
+    int W0, H0, W1, H1, G0, G1;
+    float fl;                           // weight of the second level (0 = single level)
+};
+
+__device__ __forceinline__ Levels levels(const tf_vm_field_t& f, float level, bool has_level, int i) {
+    Levels L;
+    int l0 = 0, l1 = 0;
+    L.fl = 0.f;
+    if (has_level && f.n_levels > 1) mip_levels(level, f.n_levels, l0, l1, L.fl);
+    L.pt0 = plane_level_ptr(f, i, l0, L.H0, L.W0);
+    L.lt0 = line_level_ptr(f, i, l0, L.G0);
+    L.pt1 = L.pt0; L.lt1 = L.lt0; L.W1 = L.W0; L.H1 = L.H0; L.G1 = L.G0;
+    if (L.fl > 0.f) {
+        L.pt1 = plane_level_ptr(f, i, l1, L.H1, L.W1);
+        L.lt1 = line_level_ptr(f, i, l1, L.G1);
+    }
+    return L;
+}
+
+__device__ __forceinline__ float4 mix(float fl, float4 a, float4 b) {
+    const float w = 1.f - fl;
+    return make_float4(w * a.x + fl * b.x, w * a.y + fl * b.y, w * a.z + fl * b.z, w * a.w + fl * b.w);
+}
+__device__ __forceinline__ float4 plane_at(const Levels& L, float pu, float pv, int C, int c) {
+    float4 P = fetch_bi(L.pt0, make_bitap(pu, pv, L.W0, L.H0), C, c);
+    if (L.fl > 0.f) P = mix(L.fl, P, fetch_bi(L.pt1, make_bitap(pu, pv, L.W1, L.H1), C, c));
+    return P;
+}
+__device__ __forceinline__ float4 line_at(const Levels& L, float lv, int C, int c) {
+    float4 V = fetch_li(L.lt0, make_litap(lv, L.G0), C, c);
+    if (L.fl > 0.f) V = mix(L.fl, V, fetch_li(L.lt1, make_litap(lv, L.G1), C, c));
+    return V;
+}
+
+// normalised coordinate of value v along axis ax (same arithmetic as vm_coords)
+__device__ __forceinline__ float coord(const tf_vm_field_t& f, float v, int ax) { return (v - f.aabb_min[ax]) / (f.aabb_max[ax] - f.aabb_min[ax]); }
+
+struct Axes { int m0, m1, vm; };
+__device__ __forceinline__ Axes axes(int i) { Axes a; a.m0 = (i == 2) ? 1 : 0; a.m1 = (i == 0) ? 1 : 2; a.vm = 2 - i; return a; }
+
+// coordinates of the stencil of sample x for plane i: index 0 centre, 1 = +unit, 2 = -unit along the axis
+struct Coords { float pu[3], pv[3], lv[3]; };
+__device__ __forceinline__ float pick(const float v[3], int ax) { return ax == 0 ? v[0] : (ax == 1 ? v[1] : v[2]); }
+__device__ __forceinline__ Coords coords(const tf_vm_field_t& f, const float x[3], const float units[3], const Axes& a) {
+    Coords k;
+    const float x0 = pick(x, a.m0), x1 = pick(x, a.m1), x2 = pick(x, a.vm);
+    const float e0 = pick(units, a.m0), e1 = pick(units, a.m1), e2 = pick(units, a.vm);
+    k.pu[0] = coord(f, x0, a.m0); k.pu[1] = coord(f, x0 + e0, a.m0); k.pu[2] = coord(f, x0 + (-e0), a.m0);
+    k.pv[0] = coord(f, x1, a.m1); k.pv[1] = coord(f, x1 + e1, a.m1); k.pv[2] = coord(f, x1 + (-e1), a.m1);
+    k.lv[0] = coord(f, x2, a.vm); k.lv[1] = coord(f, x2 + e2, a.vm); k.lv[2] = coord(f, x2 + (-e2), a.vm);
+    return k;
+}
+
+__device__ __forceinline__ float4 tf32_hi(float4 v) { return make_float4(tc::tf32_rn(v.x), tc::tf32_rn(v.y), tc::tf32_rn(v.z), tc::tf32_rn(v.w)); }
+__device__ __forceinline__ float4 tf32_lo(float4 v, float4 h) {
+    return make_float4(tc::tf32_rn(v.x - h.x), tc::tf32_rn(v.y - h.y), tc::tf32_rn(v.z - h.z), tc::tf32_rn(v.w - h.w));
+}
+__device__ __forceinline__ void put(uint8_t* a_hi, uint8_t* a_lo, uint32_t off, float4 v) {
+    const float4 h = tf32_hi(v);
+    *reinterpret_cast<float4*>(a_hi + off) = h;
+    *reinterpret_cast<float4*>(a_lo + off) = tf32_lo(v, h);
+}
+
+// Gather the A operand of one stencil tile (samples [s_base, s_base + 18)).  When `arow` is not NULL the fp32
+// rows are also streamed to HBM ([128][KT] per tile, the constant-1 column at index 3C+3 included).
+__device__ __forceinline__ void gather_tile(const tf_vm_field_t& f, const float* __restrict__ xyz, const float* __restrict__ level, int64_t n_total,
+                                            const float units[3], int64_t s_base, int KT, uint8_t* a_hi, uint8_t* a_lo, float* arow, int nthreads) {
+    const int C = f.n_comp, C4 = C / 4, G = KT / 4;
+    const bool has_level = level != nullptr;
+    const int n_tasks = SPT * 3 * C4;
+    for (int task = threadIdx.x; task < n_tasks; task += nthreads) {
+        const int c4 = task % C4, si = task / C4, i = si % 3, s = si / 3;
+        const int64_t n = s_base + s;
+        const int g = i * C4 + c4, r0 = s * NQ;
+        const Axes a = axes(i);
+        const int r_m0 = r0 + 1 + 2 * a.m0, r_m1 = r0 + 1 + 2 * a.m1, r_vm = r0 + 1 + 2 * a.vm;
+        float4 v[NQ];                                   // products in emission order: centre, m0+-, m1+-, vm+-
+        if (n < n_total) {
+            const float x[3] = {xyz[n * 3 + 0], xyz[n * 3 + 1], xyz[n * 3 + 2]};
+            const Levels L = levels(f, has_level ? level[n] : 0.f, has_level, i);
+            const Coords k = coords(f, x, units, a);
+            const int c = c4 * 4;
+            const float4 L0 = line_at(L, k.lv[0], C, c);
+            const float4 P0 = plane_at(L, k.pu[0], k.pv[0], C, c);
+            v[0] = f4_mul(P0, L0);
+            v[1] = f4_mul(plane_at(L, k.pu[1], k.pv[0], C, c), L0);
+            v[2] = f4_mul(plane_at(L, k.pu[2], k.pv[0], C, c), L0);
+            v[3] = f4_mul(plane_at(L, k.pu[0], k.pv[1], C, c), L0);
+            v[4] = f4_mul(plane_at(L, k.pu[0], k.pv[2], C, c), L0);
+            v[5] = f4_mul(P0, line_at(L, k.lv[1], C, c));
+            v[6] = f4_mul(P0, line_at(L, k.lv[2], C, c));
+        } else {
+#pragma unroll
+            for (int j = 0; j < NQ; ++j) v[j] = f4_zero();
+        }
+        const int rows[NQ] = {r0, r_m0, r_m0 + 1, r_m1, r_m1 + 1, r_vm, r_vm + 1};
+#pragma unroll
+        for (int j = 0; j < NQ; ++j) {
+            put(a_hi, a_lo, a_off(rows[j], g, KT), v[j]);
+            if (arow) *reinterpret_cast<float4*>(arow + (size_t)rows[j] * KT + g * 4) = v[j];
+        }
+    }
+    // raw stencil points (fields.py:265,298), zero padding groups and the two zero rows of the tile
+    const int tail_g = G - 3 * C4;
+    for (int it = threadIdx.x; it < 128 * tail_g; it += nthreads) {
+        const int r = it % 128, g = 3 * C4 + it / 128;
+        const int s = r / NQ, q = r - s * NQ;
+        const int64_t n = s_base + s;
+        float4 v = f4_zero(), vh = f4_zero();
+        if (g == 3 * C4 && s < SPT && n < n_total) {
+            const float x[3] = {xyz[n * 3 + 0], xyz[n * 3 + 1], xyz[n * 3 + 2]};
+            float pt[3];
+            stencil_point(x, units, q, pt);
+            v = make_float4(pt[0], pt[1], pt[2], 0.f);
+            vh = make_float4(pt[0], pt[1], pt[2], 1.f);      // ones column: dPre^T [A | 1] yields db0 next to dW0
+        }
+        put(a_hi, a_lo, a_off(r, g, KT), v);
+        if (arow) *reinterpret_cast<float4*>(arow + (size_t)r * KT + g * 4) = vh;
+    }
+    for (int it = threadIdx.x; it < 2 * 3 * C4; it += nthreads) {
+        const int r = SPT * NQ + it / (3 * C4), g = it % (3 * C4);
+        put(a_hi, a_lo, a_off(r, g, KT), f4_zero());
+        if (arow) *reinterpret_cast<float4*>(arow + (size_t)r * KT + g * 4) = f4_zero();
+    }
+}
+
+__device__ __forceinline__ float* twin(const float* p, const float* base0, float* g0, const float* basem, float* gm) {
+    return p == base0 ? g0 : gm + (p - basem);
+}
+__device__ __forceinline__ void scatter_plane(float* t0, float* t1, const Levels& L, float pu, float pv, int C, int c, float4 d) {
+    const float w0 = 1.f - L.fl;
+    BiTap b = make_bitap(pu, pv, L.W0, L.H0);
+    red_add_v4(t0 + (size_t)b.o00 * C + c, f4_scale(w0 * b.w00, d));
+    red_add_v4(t0 + (size_t)b.o01 * C + c, f4_scale(w0 * b.w01, d));
+    red_add_v4(t0 + (size_t)b.o10 * C + c, f4_scale(w0 * b.w10, d));
+    red_add_v4(t0 + (size_t)b.o11 * C + c, f4_scale(w0 * b.w11, d));
+    if (L.fl > 0.f) {
+        b = make_bitap(pu, pv, L.W1, L.H1);
+        red_add_v4(t1 + (size_t)b.o00 * C + c, f4_scale(L.fl * b.w00, d));
+        red_add_v4(t1 + (size_t)b.o01 * C + c, f4_scale(L.fl * b.w01, d));
+        red_add_v4(t1 + (size_t)b.o10 * C + c, f4_scale(L.fl * b.w10, d));
+        red_add_v4(t1 + (size_t)b.o11 * C + c, f4_scale(L.fl * b.w11, d));
+    }
+}
+__device__ __forceinline__ void scatter_line(float* t0, float* t1, const Levels& L, float lv, int C, int c, float4 d) {
+    const float w0 = 1.f - L.fl;
+    LiTap t = make_litap(lv, L.G0);
+    red_add_v4(t0 + (size_t)t.o0 * C + c, f4_scale(w0 * t.w0, d));
+    red_add_v4(t0 + (size_t)t.o1 * C + c, f4_scale(w0 * t.w1, d));
+    if (L.fl > 0.f) {
+        t = make_litap(lv, L.G1);
+        red_add_v4(t1 + (size_t)t.o0 * C + c, f4_scale(L.fl * t.w0, d));
+        red_add_v4(t1 + (size_t)t.o1 * C + c, f4_scale(L.fl * t.w1, d));
+    }
+}
+
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 f4_fma4(float4 a, float4 b, float4 c) { return make_float4(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y), fmaf(a.z, b.z, c.z), fmaf(a.w, b.w, c.w)); }
+
+// Scatter the feature gradients dA (fp32 tile in shared memory, row stride `ld` floats) of one stencil tile
+// into the plane / line gradients; shared positions are reduced in registers first.
+__device__ __forceinline__ void scatter_tile(const tf_vm_field_t& f, const tf_vm_mut_t& gm, const float* __restrict__ xyz,
+                                             const float* __restrict__ level, int64_t n_total, const float units[3], int64_t s_base,
+                                             const float* dA, int ld, int nthreads) {
+    const int C = f.n_comp, C4 = C / 4;
+    const bool has_level = level != nullptr;
+    const int n_tasks = SPT * 3 * C4;
+    for (int task = threadIdx.x; task < n_tasks; task += nthreads) {
+        const int c4 = task % C4, si = task / C4, i = si % 3, s = si / 3;
+        const int64_t n = s_base + s;
+        if (n >= n_total) continue;
+        const int g = i * C4 + c4, r0 = s * NQ, c = c4 * 4;
+        const Axes a = axes(i);
+        const float x[3] = {xyz[n * 3 + 0], xyz[n * 3 + 1], xyz[n * 3 + 2]};
+        const Levels L = levels(f, has_level ? level[n] : 0.f, has_level, i);
+        const Coords k = coords(f, x, units, a);
+        float* pm0 = twin(L.pt0, f.plane[i], gm.plane[i], f.plane_mip[i], gm.plane_mip[i]);
+        float* pm1 = twin(L.pt1, f.plane[i], gm.plane[i], f.plane_mip[i], gm.plane_mip[i]);
+        float* lm0 = twin(L.lt0, f.line[i], gm.line[i], f.line_mip[i], gm.line_mip[i]);
+        float* lm1 = twin(L.lt1, f.line[i], gm.line[i], f.line_mip[i], gm.line_mip[i]);
+        const float* dcol = dA + g * 4;
+        auto drow = [&](int r) { return *reinterpret_cast<const float4*>(dcol + (size_t)r * ld); };
+        const int r_m0 = r0 + 1 + 2 * a.m0, r_m1 = r0 + 1 + 2 * a.m1, r_vm = r0 + 1 + 2 * a.vm;
+        const float4 L0 = line_at(L, k.lv[0], C, c);
+        const float4 P0 = plane_at(L, k.pu[0], k.pv[0], C, c);
+        const float4 d0 = drow(r0), dvp = drow(r_vm), dvm = drow(r_vm + 1);
+        // plane gradient at the centre position: centre and +-vm queries share it
+        float4 dP = f4_mul(d0, L0);
+        dP = f4_fma4(dvp, line_at(L, k.lv[1], C, c), dP);
+        dP = f4_fma4(dvm, line_at(L, k.lv[2], C, c), dP);
+        scatter_plane(pm0, pm1, L, k.pu[0], k.pv[0], C, c, dP);
+        scatter_line(lm0, lm1, L, k.lv[1], C, c, f4_mul(dvp, P0));
+        scatter_line(lm0, lm1, L, k.lv[2], C, c, f4_mul(dvm, P0));
+        // line gradient at the centre position: centre and the four in-plane queries share it
+        float4 dL = f4_mul(d0, P0);
+        {
+            const float4 d = drow(r_m0);
+            dL = f4_fma4(d, plane_at(L, k.pu[1], k.pv[0], C, c), dL);
+            scatter_plane(pm0, pm1, L, k.pu[1], k.pv[0], C, c, f4_mul(d, L0));
+        }
+        {
+            const float4 d = drow(r_m0 + 1);
+            dL = f4_fma4(d, plane_at(L, k.pu[2], k.pv[0], C, c), dL);
+            scatter_plane(pm0, pm1, L, k.pu[2], k.pv[0], C, c, f4_mul(d, L0));
+        }
+        {
+            const float4 d = drow(r_m1);
+            dL = f4_fma4(d, plane_at(L, k.pu[0], k.pv[1], C, c), dL);
+            scatter_plane(pm0, pm1, L, k.pu[0], k.pv[1], C, c, f4_mul(d, L0));
+        }
+        {
+            const float4 d = drow(r_m1 + 1);
+            dL = f4_fma4(d, plane_at(L, k.pu[0], k.pv[2], C, c), dL);
+            scatter_plane(pm0, pm1, L, k.pu[0], k.pv[2], C, c, f4_mul(d, L0));
+        }
+        scatter_line(lm0, lm1, L, k.lv[0], C, c, dL);
+    }
+}
+
+}  // namespace site
