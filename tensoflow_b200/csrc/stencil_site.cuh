@@ -48,16 +48,48 @@ __device__ __forceinline__ float4 mix(float fl, float4 a, float4 b) {
     const float w = 1.f - fl;
     return make_float4(w * a.x + fl * b.x, w * a.y + fl * b.y, w * a.z + fl * b.z, w * a.w + fl * b.w);
 }
-__device__ __forceinline__ float4 plane_at(const Levels& L, float pu, float pv, int C, int c) {
-    float4 P = fetch_bi(L.pt0, make_bitap(pu, pv, L.W0, L.H0), C, c);
-    if (L.fl > 0.f) P = mix(L.fl, P, fetch_bi(L.pt1, make_bitap(pu, pv, L.W1, L.H1), C, c));
-    return P;
+
+// 1-D sampling plan (same arithmetic as make_bitap / make_litap: texel centres at i + 0.5, clamp addressing)
+struct Tap1 { int i0, i1; float w0, w1; };
+__device__ __forceinline__ Tap1 tap1(float u, int N) {
+    float x = u * (float)N - 0.5f;
+    x = fminf(fmaxf(x, -2.f), (float)N + 1.f);
+    const float x0f = floorf(x);
+    const float fx = x - x0f;
+    const int x0 = (int)x0f;
+    Tap1 t;
+    t.i1 = min(max(x0 + 1, 0), N - 1);
+    t.i0 = min(max(x0, 0), N - 1);
+    t.w0 = 1.f - fx;
+    t.w1 = fx;
+    return t;
 }
-__device__ __forceinline__ float4 line_at(const Levels& L, float lv, int C, int c) {
-    float4 V = fetch_li(L.lt0, make_litap(lv, L.G0), C, c);
-    if (L.fl > 0.f) V = mix(L.fl, V, fetch_li(L.lt1, make_litap(lv, L.G1), C, c));
-    return V;
+// the 4 texels of a bilinear footprint / the 2 texels of a linear one (loads only, no arithmetic: callers batch
+// the loads of several positions before combining them so that many requests are in flight)
+__device__ __forceinline__ void bi_load(const float* T, const Tap1& tx, const Tap1& ty, int W, int C, int c, float4 t[4]) {
+    t[0] = ldg4(T + (size_t)(ty.i0 * W + tx.i0) * C + c);
+    t[1] = ldg4(T + (size_t)(ty.i0 * W + tx.i1) * C + c);
+    t[2] = ldg4(T + (size_t)(ty.i1 * W + tx.i0) * C + c);
+    t[3] = ldg4(T + (size_t)(ty.i1 * W + tx.i1) * C + c);
 }
+__device__ __forceinline__ float4 bi_combine(const Tap1& tx, const Tap1& ty, const float4 t[4]) {
+    float4 r = f4_scale(tx.w0 * ty.w0, t[0]);
+    r = f4_fma(tx.w1 * ty.w0, t[1], r);
+    r = f4_fma(tx.w0 * ty.w1, t[2], r);
+    return f4_fma(tx.w1 * ty.w1, t[3], r);
+}
+__device__ __forceinline__ void li_load(const float* T, const Tap1& tl, int C, int c, float4 t[2]) {
+    t[0] = ldg4(T + (size_t)tl.i0 * C + c);
+    t[1] = ldg4(T + (size_t)tl.i1 * C + c);
+}
+__device__ __forceinline__ float4 li_combine(const Tap1& tl, const float4 t[2]) { return f4_fma(tl.w1, t[1], f4_scale(tl.w0, t[0])); }
+
+// 1-D plans of the 3 coordinate variants (centre, +unit, -unit) of the plane u / plane v / line axes on both levels
+template <bool TWO>
+struct SitePlan {
+    Tap1 x0[3], y0[3], l0[3];
+    Tap1 x1[3], y1[3], l1[3];
+};
 
 // normalised coordinate of value v along axis ax (same arithmetic as vm_coords)
 __device__ __forceinline__ float coord(const tf_vm_field_t& f, float v, int ax) { return (v - f.aabb_min[ax]) / (f.aabb_max[ax] - f.aabb_min[ax]); }
@@ -78,6 +110,45 @@ __device__ __forceinline__ Coords coords(const tf_vm_field_t& f, const float x[3
     return k;
 }
 
+template <bool TWO>
+__device__ __forceinline__ SitePlan<TWO> make_plan(const Levels& L, const Coords& k) {
+    SitePlan<TWO> p;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        p.x0[j] = tap1(k.pu[j], L.W0); p.y0[j] = tap1(k.pv[j], L.H0); p.l0[j] = tap1(k.lv[j], L.G0);
+        if (TWO) { p.x1[j] = tap1(k.pu[j], L.W1); p.y1[j] = tap1(k.pv[j], L.H1); p.l1[j] = tap1(k.lv[j], L.G1); }
+    }
+    return p;
+}
+// plane value at variant (jx, jy) / line value at variant jl; the level-1 part is always fetched when TWO
+// (fl == 0 then multiplies it by zero and its texels coincide with level 0)
+template <bool TWO>
+struct PlaneFetch {
+    float4 t0[4], t1[4];
+    __device__ __forceinline__ void load(const Levels& L, const SitePlan<TWO>& p, int jx, int jy, int C, int c) {
+        bi_load(L.pt0, p.x0[jx], p.y0[jy], L.W0, C, c, t0);
+        if (TWO) bi_load(L.pt1, p.x1[jx], p.y1[jy], L.W1, C, c, t1);
+    }
+    __device__ __forceinline__ float4 value(const Levels& L, const SitePlan<TWO>& p, int jx, int jy) const {
+        float4 P = bi_combine(p.x0[jx], p.y0[jy], t0);
+        if (TWO) P = mix(L.fl, P, bi_combine(p.x1[jx], p.y1[jy], t1));
+        return P;
+    }
+};
+template <bool TWO>
+struct LineFetch {
+    float4 t0[2], t1[2];
+    __device__ __forceinline__ void load(const Levels& L, const SitePlan<TWO>& p, int jl, int C, int c) {
+        li_load(L.lt0, p.l0[jl], C, c, t0);
+        if (TWO) li_load(L.lt1, p.l1[jl], C, c, t1);
+    }
+    __device__ __forceinline__ float4 value(const Levels& L, const SitePlan<TWO>& p, int jl) const {
+        float4 V = li_combine(p.l0[jl], t0);
+        if (TWO) V = mix(L.fl, V, li_combine(p.l1[jl], t1));
+        return V;
+    }
+};
+
 __device__ __forceinline__ float4 tf32_hi(float4 v) { return make_float4(tc::tf32_rn(v.x), tc::tf32_rn(v.y), tc::tf32_rn(v.z), tc::tf32_rn(v.w)); }
 __device__ __forceinline__ float4 tf32_lo(float4 v, float4 h) {
     return make_float4(tc::tf32_rn(v.x - h.x), tc::tf32_rn(v.y - h.y), tc::tf32_rn(v.z - h.z), tc::tf32_rn(v.w - h.w));
@@ -90,7 +161,8 @@ __device__ __forceinline__ void put(uint8_t* a_hi, uint8_t* a_lo, uint32_t off, 
 
 // Gather the A operand of one stencil tile (samples [s_base, s_base + 18)).  When `arow` is not NULL the fp32
 // rows are also streamed to HBM ([128][KT] per tile, the constant-1 column at index 3C+3 included).
-__device__ __forceinline__ void gather_tile(const tf_vm_field_t& f, const float* __restrict__ xyz, const float* __restrict__ level, int64_t n_total,
+template <bool TWO>
+__device__ __forceinline__ void gather_tile_t(const tf_vm_field_t& f, const float* __restrict__ xyz, const float* __restrict__ level, int64_t n_total,
                                             const float units[3], int64_t s_base, int KT, uint8_t* a_hi, uint8_t* a_lo, float* arow, int nthreads) {
     const int C = f.n_comp, C4 = C / 4, G = KT / 4;
     const bool has_level = level != nullptr;
@@ -107,15 +179,21 @@ __device__ __forceinline__ void gather_tile(const tf_vm_field_t& f, const float*
             const Levels L = levels(f, has_level ? level[n] : 0.f, has_level, i);
             const Coords k = coords(f, x, units, a);
             const int c = c4 * 4;
-            const float4 L0 = line_at(L, k.lv[0], C, c);
-            const float4 P0 = plane_at(L, k.pu[0], k.pv[0], C, c);
+            const SitePlan<TWO> sp = make_plan<TWO>(L, k);
+            LineFetch<TWO> fl0, fl1, fl2;
+            PlaneFetch<TWO> fp0, fpa, fpb;
+            fl0.load(L, sp, 0, C, c); fp0.load(L, sp, 0, 0, C, c);
+            fpa.load(L, sp, 1, 0, C, c); fpb.load(L, sp, 2, 0, C, c);
+            const float4 L0 = fl0.value(L, sp, 0), P0 = fp0.value(L, sp, 0, 0);
             v[0] = f4_mul(P0, L0);
-            v[1] = f4_mul(plane_at(L, k.pu[1], k.pv[0], C, c), L0);
-            v[2] = f4_mul(plane_at(L, k.pu[2], k.pv[0], C, c), L0);
-            v[3] = f4_mul(plane_at(L, k.pu[0], k.pv[1], C, c), L0);
-            v[4] = f4_mul(plane_at(L, k.pu[0], k.pv[2], C, c), L0);
-            v[5] = f4_mul(P0, line_at(L, k.lv[1], C, c));
-            v[6] = f4_mul(P0, line_at(L, k.lv[2], C, c));
+            fl1.load(L, sp, 1, C, c); fl2.load(L, sp, 2, C, c);
+            v[1] = f4_mul(fpa.value(L, sp, 1, 0), L0);
+            v[2] = f4_mul(fpb.value(L, sp, 2, 0), L0);
+            fpa.load(L, sp, 0, 1, C, c); fpb.load(L, sp, 0, 2, C, c);
+            v[5] = f4_mul(P0, fl1.value(L, sp, 1));
+            v[6] = f4_mul(P0, fl2.value(L, sp, 2));
+            v[3] = f4_mul(fpa.value(L, sp, 0, 1), L0);
+            v[4] = f4_mul(fpb.value(L, sp, 0, 2), L0);
         } else {
 #pragma unroll
             for (int j = 0; j < NQ; ++j) v[j] = f4_zero();
@@ -151,33 +229,41 @@ __device__ __forceinline__ void gather_tile(const tf_vm_field_t& f, const float*
     }
 }
 
+__device__ __forceinline__ void gather_tile(const tf_vm_field_t& f, const float* __restrict__ xyz, const float* __restrict__ level, int64_t n_total,
+                                            const float units[3], int64_t s_base, int KT, uint8_t* a_hi, uint8_t* a_lo, float* arow, int nthreads) {
+    if (level != nullptr && f.n_levels > 1) gather_tile_t<true>(f, xyz, level, n_total, units, s_base, KT, a_hi, a_lo, arow, nthreads);
+    else gather_tile_t<false>(f, xyz, level, n_total, units, s_base, KT, a_hi, a_lo, arow, nthreads);
+}
+
 __device__ __forceinline__ float* twin(const float* p, const float* base0, float* g0, const float* basem, float* gm) {
     return p == base0 ? g0 : gm + (p - basem);
 }
-__device__ __forceinline__ void scatter_plane(float* t0, float* t1, const Levels& L, float pu, float pv, int C, int c, float4 d) {
-    const float w0 = 1.f - L.fl;
-    BiTap b = make_bitap(pu, pv, L.W0, L.H0);
-    red_add_v4(t0 + (size_t)b.o00 * C + c, f4_scale(w0 * b.w00, d));
-    red_add_v4(t0 + (size_t)b.o01 * C + c, f4_scale(w0 * b.w01, d));
-    red_add_v4(t0 + (size_t)b.o10 * C + c, f4_scale(w0 * b.w10, d));
-    red_add_v4(t0 + (size_t)b.o11 * C + c, f4_scale(w0 * b.w11, d));
-    if (L.fl > 0.f) {
-        b = make_bitap(pu, pv, L.W1, L.H1);
-        red_add_v4(t1 + (size_t)b.o00 * C + c, f4_scale(L.fl * b.w00, d));
-        red_add_v4(t1 + (size_t)b.o01 * C + c, f4_scale(L.fl * b.w01, d));
-        red_add_v4(t1 + (size_t)b.o10 * C + c, f4_scale(L.fl * b.w10, d));
-        red_add_v4(t1 + (size_t)b.o11 * C + c, f4_scale(L.fl * b.w11, d));
+template <bool TWO>
+__device__ __forceinline__ void scatter_plane(float* t0, float* t1, const Levels& L, const SitePlan<TWO>& p, int jx, int jy, int C, int c, float4 d) {
+    {
+        const Tap1 &tx = p.x0[jx], &ty = p.y0[jy];
+        const float w0 = 1.f - L.fl;
+        red_add_v4(t0 + (size_t)(ty.i0 * L.W0 + tx.i0) * C + c, f4_scale(w0 * (tx.w0 * ty.w0), d));
+        red_add_v4(t0 + (size_t)(ty.i0 * L.W0 + tx.i1) * C + c, f4_scale(w0 * (tx.w1 * ty.w0), d));
+        red_add_v4(t0 + (size_t)(ty.i1 * L.W0 + tx.i0) * C + c, f4_scale(w0 * (tx.w0 * ty.w1), d));
+        red_add_v4(t0 + (size_t)(ty.i1 * L.W0 + tx.i1) * C + c, f4_scale(w0 * (tx.w1 * ty.w1), d));
+    }
+    if (TWO && L.fl > 0.f) {
+        const Tap1 &tx = p.x1[jx], &ty = p.y1[jy];
+        red_add_v4(t1 + (size_t)(ty.i0 * L.W1 + tx.i0) * C + c, f4_scale(L.fl * (tx.w0 * ty.w0), d));
+        red_add_v4(t1 + (size_t)(ty.i0 * L.W1 + tx.i1) * C + c, f4_scale(L.fl * (tx.w1 * ty.w0), d));
+        red_add_v4(t1 + (size_t)(ty.i1 * L.W1 + tx.i0) * C + c, f4_scale(L.fl * (tx.w0 * ty.w1), d));
+        red_add_v4(t1 + (size_t)(ty.i1 * L.W1 + tx.i1) * C + c, f4_scale(L.fl * (tx.w1 * ty.w1), d));
     }
 }
-__device__ __forceinline__ void scatter_line(float* t0, float* t1, const Levels& L, float lv, int C, int c, float4 d) {
+template <bool TWO>
+__device__ __forceinline__ void scatter_line(float* t0, float* t1, const Levels& L, const SitePlan<TWO>& p, int jl, int C, int c, float4 d) {
     const float w0 = 1.f - L.fl;
-    LiTap t = make_litap(lv, L.G0);
-    red_add_v4(t0 + (size_t)t.o0 * C + c, f4_scale(w0 * t.w0, d));
-    red_add_v4(t0 + (size_t)t.o1 * C + c, f4_scale(w0 * t.w1, d));
-    if (L.fl > 0.f) {
-        t = make_litap(lv, L.G1);
-        red_add_v4(t1 + (size_t)t.o0 * C + c, f4_scale(L.fl * t.w0, d));
-        red_add_v4(t1 + (size_t)t.o1 * C + c, f4_scale(L.fl * t.w1, d));
+    red_add_v4(t0 + (size_t)p.l0[jl].i0 * C + c, f4_scale(w0 * p.l0[jl].w0, d));
+    red_add_v4(t0 + (size_t)p.l0[jl].i1 * C + c, f4_scale(w0 * p.l0[jl].w1, d));
+    if (TWO && L.fl > 0.f) {
+        red_add_v4(t1 + (size_t)p.l1[jl].i0 * C + c, f4_scale(L.fl * p.l1[jl].w0, d));
+        red_add_v4(t1 + (size_t)p.l1[jl].i1 * C + c, f4_scale(L.fl * p.l1[jl].w1, d));
     }
 }
 
@@ -186,7 +272,8 @@ __device__ __forceinline__ float4 f4_fma4(float4 a, float4 b, float4 c) { return
 
 // Scatter the feature gradients dA (fp32 tile in shared memory, row stride `ld` floats) of one stencil tile
 // into the plane / line gradients; shared positions are reduced in registers first.
-__device__ __forceinline__ void scatter_tile(const tf_vm_field_t& f, const tf_vm_mut_t& gm, const float* __restrict__ xyz,
+template <bool TWO>
+__device__ __forceinline__ void scatter_tile_t(const tf_vm_field_t& f, const tf_vm_mut_t& gm, const float* __restrict__ xyz,
                                              const float* __restrict__ level, int64_t n_total, const float units[3], int64_t s_base,
                                              const float* dA, int ld, int nthreads) {
     const int C = f.n_comp, C4 = C / 4;
@@ -208,40 +295,46 @@ __device__ __forceinline__ void scatter_tile(const tf_vm_field_t& f, const tf_vm
         const float* dcol = dA + g * 4;
         auto drow = [&](int r) { return *reinterpret_cast<const float4*>(dcol + (size_t)r * ld); };
         const int r_m0 = r0 + 1 + 2 * a.m0, r_m1 = r0 + 1 + 2 * a.m1, r_vm = r0 + 1 + 2 * a.vm;
-        const float4 L0 = line_at(L, k.lv[0], C, c);
-        const float4 P0 = plane_at(L, k.pu[0], k.pv[0], C, c);
+        const SitePlan<TWO> sp = make_plan<TWO>(L, k);
+        LineFetch<TWO> fl0, fl1, fl2;
+        PlaneFetch<TWO> fp0, fpa, fpb;
+        fl0.load(L, sp, 0, C, c); fp0.load(L, sp, 0, 0, C, c); fl1.load(L, sp, 1, C, c); fl2.load(L, sp, 2, C, c);
+        fpa.load(L, sp, 1, 0, C, c); fpb.load(L, sp, 2, 0, C, c);
         const float4 d0 = drow(r0), dvp = drow(r_vm), dvm = drow(r_vm + 1);
+        const float4 L0 = fl0.value(L, sp, 0), P0 = fp0.value(L, sp, 0, 0);
         // plane gradient at the centre position: centre and +-vm queries share it
         float4 dP = f4_mul(d0, L0);
-        dP = f4_fma4(dvp, line_at(L, k.lv[1], C, c), dP);
-        dP = f4_fma4(dvm, line_at(L, k.lv[2], C, c), dP);
-        scatter_plane(pm0, pm1, L, k.pu[0], k.pv[0], C, c, dP);
-        scatter_line(lm0, lm1, L, k.lv[1], C, c, f4_mul(dvp, P0));
-        scatter_line(lm0, lm1, L, k.lv[2], C, c, f4_mul(dvm, P0));
+        dP = f4_fma4(dvp, fl1.value(L, sp, 1), dP);
+        dP = f4_fma4(dvm, fl2.value(L, sp, 2), dP);
+        scatter_plane<TWO>(pm0, pm1, L, sp, 0, 0, C, c, dP);
+        scatter_line<TWO>(lm0, lm1, L, sp, 1, C, c, f4_mul(dvp, P0));
+        scatter_line<TWO>(lm0, lm1, L, sp, 2, C, c, f4_mul(dvm, P0));
         // line gradient at the centre position: centre and the four in-plane queries share it
         float4 dL = f4_mul(d0, P0);
         {
-            const float4 d = drow(r_m0);
-            dL = f4_fma4(d, plane_at(L, k.pu[1], k.pv[0], C, c), dL);
-            scatter_plane(pm0, pm1, L, k.pu[1], k.pv[0], C, c, f4_mul(d, L0));
+            const float4 da = drow(r_m0), db = drow(r_m0 + 1);
+            dL = f4_fma4(da, fpa.value(L, sp, 1, 0), dL);
+            dL = f4_fma4(db, fpb.value(L, sp, 2, 0), dL);
+            fpa.load(L, sp, 0, 1, C, c); fpb.load(L, sp, 0, 2, C, c);
+            scatter_plane<TWO>(pm0, pm1, L, sp, 1, 0, C, c, f4_mul(da, L0));
+            scatter_plane<TWO>(pm0, pm1, L, sp, 2, 0, C, c, f4_mul(db, L0));
         }
         {
-            const float4 d = drow(r_m0 + 1);
-            dL = f4_fma4(d, plane_at(L, k.pu[2], k.pv[0], C, c), dL);
-            scatter_plane(pm0, pm1, L, k.pu[2], k.pv[0], C, c, f4_mul(d, L0));
+            const float4 da = drow(r_m1), db = drow(r_m1 + 1);
+            dL = f4_fma4(da, fpa.value(L, sp, 0, 1), dL);
+            dL = f4_fma4(db, fpb.value(L, sp, 0, 2), dL);
+            scatter_plane<TWO>(pm0, pm1, L, sp, 0, 1, C, c, f4_mul(da, L0));
+            scatter_plane<TWO>(pm0, pm1, L, sp, 0, 2, C, c, f4_mul(db, L0));
         }
-        {
-            const float4 d = drow(r_m1);
-            dL = f4_fma4(d, plane_at(L, k.pu[0], k.pv[1], C, c), dL);
-            scatter_plane(pm0, pm1, L, k.pu[0], k.pv[1], C, c, f4_mul(d, L0));
-        }
-        {
-            const float4 d = drow(r_m1 + 1);
-            dL = f4_fma4(d, plane_at(L, k.pu[0], k.pv[2], C, c), dL);
-            scatter_plane(pm0, pm1, L, k.pu[0], k.pv[2], C, c, f4_mul(d, L0));
-        }
-        scatter_line(lm0, lm1, L, k.lv[0], C, c, dL);
+        scatter_line<TWO>(lm0, lm1, L, sp, 0, C, c, dL);
     }
+}
+
+__device__ __forceinline__ void scatter_tile(const tf_vm_field_t& f, const tf_vm_mut_t& gm, const float* __restrict__ xyz,
+                                             const float* __restrict__ level, int64_t n_total, const float units[3], int64_t s_base,
+                                             const float* dA, int ld, int nthreads) {
+    if (level != nullptr && f.n_levels > 1) scatter_tile_t<true>(f, gm, xyz, level, n_total, units, s_base, dA, ld, nthreads);
+    else scatter_tile_t<false>(f, gm, xyz, level, n_total, units, s_base, dA, ld, nthreads);
 }
 
 }  // namespace site
