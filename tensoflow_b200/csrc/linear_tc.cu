@@ -1,0 +1,207 @@
+// Dense layer on the tensor cores: Y[M,N] = act(X[M,K] Wt[N,K]^T + b)   (3xTF32: fp32-level accuracy).
+//
+// Used for the appearance head of the SDF decoder (hidden [n,H] -> feat [n,A], reference network/fields.py:192-198)
+// and its input gradient (g_feat [n,A] -> dHidden [n,H], Wt = W1[1:,:]^T).  X rows stream from HBM once:
+// one persistent CTA per SM walks 128-row tiles; per K-chunk of 32 the threads load the X chunk (coalesced
+// float4 reads), split it into tf32 hi/lo and store it in the K-major no-swizzle UMMA layout (padded K-chunk
+// stride -> conflict-free stores) while the matching pre-split weight chunk arrives by cp.async.bulk; one
+// thread issues the tcgen05.mma's (accumulator [128 x N] fp32 in TMEM, double buffered across tiles) and the
+// epilogue of tile t-1 (bias, activation, 64-byte row stores) overlaps the loads / MMAs of tile t.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int TM = 128;
+constexpr int KC = 32;                 // K chunk per pipeline stage
+constexpr int NSTG = 2;
+constexpr int NTH = 256;
+constexpr uint32_t X_LBO = 144;        // K-chunk (16 B) stride of the X operand, padded for bank spread
+constexpr uint32_t X_SBO = (KC / 4) * X_LBO;
+constexpr uint32_t X_PART = 16 * X_SBO;      // bytes of one X part (hi or lo) of a stage
+
+// pre-split weights: chunk kc -> [N rows x 32] K-major hi | lo
+__global__ void linear_tc_prep_kernel(const float* __restrict__ W, int ldw, int trans, int N, int K, int KP, float* __restrict__ Wtc) {
+    const int nchunks = KP / KC;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nchunks * N * KC; i += gridDim.x * blockDim.x) {
+        const int kl = i % KC, n = (i / KC) % N, kc = i / (KC * N);
+        const int k = kc * KC + kl;
+        // trans == 0: Wt[n][k] = W[n*ldw + k];  trans == 1: Wt[n][k] = W[k*ldw + n]
+        const float v = k < K ? (trans ? W[(size_t)k * ldw + n] : W[(size_t)n * ldw + k]) : 0.f;
+        const float hi = tc::tf32_rn(v);
+        float* base = Wtc + (size_t)kc * 2 * N * KC;
+        const uint32_t off = tc::tile_off_b32(n, kl, KC / 4) / 4;
+        base[off] = hi;
+        base[(size_t)N * KC + off] = tc::tf32_rn(v - hi);
+    }
+}
+
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tc::smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(tc::smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+struct XRegs { float4 v[4]; };     // one stage of X per thread: 128 rows x 8 chunks = 1024 float4 / 256 threads
+
+__device__ __forceinline__ void x_load(const float* __restrict__ X, int64_t M, int K, int64_t row0, int k0, XRegs& r) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int it = threadIdx.x + j * NTH;
+        const int row = it >> 3, ch = it & 7;
+        const int64_t m = row0 + row;
+        const int k = k0 + ch * 4;
+        r.v[j] = (m < M && k < K) ? ldg4(X + (size_t)m * K + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+__device__ __forceinline__ void x_store(const XRegs& r, uint8_t* hi, uint8_t* lo) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int it = threadIdx.x + j * NTH;
+        const int row = it >> 3, ch = it & 7;
+        const uint32_t off = (uint32_t)(row >> 3) * X_SBO + ch * X_LBO + (row & 7) * 16;
+        const float4 v = r.v[j];
+        const float4 h = make_float4(tc::tf32_rn(v.x), tc::tf32_rn(v.y), tc::tf32_rn(v.z), tc::tf32_rn(v.w));
+        *reinterpret_cast<float4*>(hi + off) = h;
+        *reinterpret_cast<float4*>(lo + off) =
+            make_float4(tc::tf32_rn(v.x - h.x), tc::tf32_rn(v.y - h.y), tc::tf32_rn(v.z - h.z), tc::tf32_rn(v.w - h.w));
+    }
+}
+
+__device__ __forceinline__ float act_apply(float v, int act, float a) {
+    switch (act) {
+        case 1: return fmaxf(v, 0.f);
+        case 2: return 1.f / (1.f + __expf(-v));
+        case 3: { const float z = v * a; return z > 20.f ? v : log1pf(__expf(z)) / a; }
+        default: return v;
+    }
+}
+
+__global__ void __launch_bounds__(NTH, 1) linear_tc_kernel(const float* __restrict__ X, const float* __restrict__ Wtc, const float* __restrict__ bias,
+                                                           int64_t M, int K, int KP, int N, int act, float act_p, float* __restrict__ Y) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t w_part = (uint32_t)N * KC * 4;
+    const uint32_t stage_bytes = 2 * X_PART + 2 * w_part;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)NSTG * stage_bytes);
+    uint64_t* wfull = bars;              // [NSTG] weight chunk landed
+    uint64_t* sfree = bars + NSTG;       // [NSTG] stage consumed by its MMAs
+    uint64_t* dfull = bars + 2 * NSTG;   // [2] accumulator complete
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTG + 2);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nchunks = KP / KC;
+    const int64_t ntiles = (M + TM - 1) / TM;
+    const int64_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t total = my_tiles * nchunks;          // pipeline steps of this CTA
+
+    if (warp == 0) tc::tmem_alloc<512>(tmem_slot);
+    if (tid == 0) {
+        for (int i = 0; i < NSTG; ++i) { tc::mbar_init(&wfull[i], 1); tc::mbar_init(&sfree[i], 1); }
+        tc::mbar_init(&dfull[0], 1); tc::mbar_init(&dfull[1], 1);
+        tc::mbar_fence_init();
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t idesc = tc::make_idesc(2, 2, TM, N);
+    const uint32_t w_sbo = (KC / 4) * 128;
+
+    auto epilogue = [&](int64_t tp) {
+        const int64_t tile = blockIdx.x + tp * gridDim.x;
+        tc::mbar_wait(&dfull[tp & 1], (uint32_t)((tp >> 1) & 1));
+        tc::fence_after_sync();
+        const int lq = warp & 3, half = warp >> 2;
+        const int64_t m = tile * TM + lq * 32 + lane;
+        const uint32_t d = tmem_base + (uint32_t)(tp & 1) * 256 + ((uint32_t)(lq * 32) << 16);
+        for (int c0 = half * 16; c0 < N; c0 += 32) {
+            float v[16];
+            tc::tmem_ld16(d + c0, v);
+            if (m < M) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = act_apply(v[j] + (bias ? __ldg(bias + c0 + j) : 0.f), act, act_p);
+                float4* dst = reinterpret_cast<float4*>(Y + (size_t)m * N + c0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+        }
+        tc::fence_before_sync();
+    };
+
+    XRegs xr;
+    if (total > 0) x_load(X, M, K, (int64_t)blockIdx.x * TM, 0, xr);
+    for (int64_t g = 0; g < total; ++g) {
+        const int64_t t = g / nchunks;
+        const int kc = (int)(g % nchunks);
+        const int st = (int)(g % NSTG);
+        uint8_t* x_hi = smem + (size_t)st * stage_bytes;
+        uint8_t* x_lo = x_hi + X_PART;
+        uint8_t* w_hi = x_lo + X_PART;
+        // stage free? (its previous MMAs have completed)
+        if (g >= NSTG) tc::mbar_wait(&sfree[st], (uint32_t)(((g / NSTG) - 1) & 1));
+        if (tid == 0) {
+            mbar_expect_tx(&wfull[st], 2 * w_part);
+            bulk_copy_g2s(w_hi, Wtc + (size_t)kc * 2 * N * KC, 2 * w_part, &wfull[st]);
+        }
+        x_store(xr, x_hi, x_lo);
+        if (g + 1 < total) {
+            const int64_t g1 = g + 1;
+            x_load(X, M, K, (blockIdx.x + (g1 / nchunks) * gridDim.x) * TM, (int)(g1 % nchunks) * KC, xr);
+        }
+        tc::fence_async_smem();
+        tc::fence_before_sync();
+        __syncthreads();
+        tc::fence_after_sync();
+        if (tid == 0) {
+            tc::mbar_wait(&wfull[st], (uint32_t)((g / NSTG) & 1));
+            tc::fence_after_sync();
+            const uint32_t d = tmem_base + (uint32_t)(t & 1) * 256;
+            const uint32_t xh = tc::smem_u32(x_hi), xl = tc::smem_u32(x_lo), wh = tc::smem_u32(w_hi), wl = wh + w_part;
+#pragma unroll
+            for (int ks = 0; ks < KC / 8; ++ks) {
+                const uint64_t adh = tc::make_smem_desc(xh + ks * 2 * X_LBO, X_LBO, X_SBO), adl = tc::make_smem_desc(xl + ks * 2 * X_LBO, X_LBO, X_SBO);
+                const uint64_t wdh = tc::make_smem_desc(wh + ks * 256, 128, w_sbo), wdl = tc::make_smem_desc(wl + ks * 256, 128, w_sbo);
+                tc::mma_tf32_ss(d, adh, wdh, idesc, (kc | ks) != 0);
+                tc::mma_tf32_ss(d, adh, wdl, idesc, 1);
+                tc::mma_tf32_ss(d, adl, wdh, idesc, 1);
+            }
+            tc::mma_commit(&sfree[st]);
+            if (kc == nchunks - 1) tc::mma_commit(&dfull[t & 1]);
+        }
+        // epilogue of the previous tile once this tile's first chunk is in flight
+        if (kc == 0 && t > 0) epilogue(t - 1);
+    }
+    if (my_tiles > 0) epilogue(my_tiles - 1);
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<512>(tmem_base);
+}
+
+size_t linear_tc_smem(int N) { return (size_t)NSTG * (2 * X_PART + 2 * (size_t)N * KC * 4) + (2 * NSTG + 2) * 8 + 16; }
+
+}  // namespace
+
+bool tf_internal_linear_tc_ok(const float* X, const float* Y, int K, int N, int act) {
+    if (N % 16 != 0 || N < 16 || N > 256 || K % 4 != 0 || K < 4) return false;
+    if (act != 0) return false;          // callers on the stencil path need no activation; others use the FFMA kernel
+    if (((uintptr_t)X & 15) || ((uintptr_t)Y & 15)) return false;
+    return linear_tc_smem(N) <= 227 * 1024;
+}
+size_t tf_internal_linear_tc_ws_floats(int K, int N) { return (size_t)2 * N * ((K + KC - 1) / KC * KC); }
+
+// Y = act(X Wt^T + b); Wt[n][k] = trans ? W[k*ldw + n] : W[n*ldw + k]; `wtc` = scratch of tf_internal_linear_tc_ws_floats floats
+int tf_internal_linear_tc(const float* X, const float* W, int ldw, int trans, const float* bias, int64_t M, int K, int N, int act, float act_p,
+                          float* Y, float* wtc, cudaStream_t stream) {
+    if (M == 0) return 0;
+    const int KP = (K + KC - 1) / KC * KC;
+    linear_tc_prep_kernel<<<64, 256, 0, stream>>>(W, ldw, trans, N, K, KP, wtc);
+    const size_t smem = linear_tc_smem(N);
+    cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int64_t ntiles = (M + TM - 1) / TM;
+    const int grid = (int)(ntiles < tf_num_sms() ? ntiles : tf_num_sms());
+    linear_tc_kernel<<<grid, NTH, smem, stream>>>(X, wtc, bias, M, K, KP, N, act, act_p, Y);
+    tf_count_launches(2);
+    return 0;
+}

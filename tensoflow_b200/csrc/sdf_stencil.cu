@@ -561,6 +561,11 @@ void fill_common(StencilParams& p, const tf_vm_field_t* f, const tf_sdf_mlp_t* m
 
 int tf_check_field(const tf_vm_field_t* f, bool need_mips);
 
+// tensor-core dense layer (linear_tc.cu)
+bool tf_internal_linear_tc_ok(const float* X, const float* Y, int K, int N, int act);
+size_t tf_internal_linear_tc_ws_floats(int K, int N);
+int tf_internal_linear_tc(const float* X, const float* W, int ldw, int trans, const float* bias, int64_t M, int K, int N, int act, float act_p,
+                          float* Y, float* wtc, cudaStream_t stream);
 // tensor-core forward (sdf_stencil_tc.cu)
 size_t tf_internal_tc_fwd_smem(int KT, int H);
 size_t tf_internal_tc_w0_floats(int KT, int H);
@@ -578,7 +583,7 @@ static bool use_simt_path(const Dims& d) {
 static size_t fwd_ws_floats(const Dims& d, int64_t n, bool with_feat) {
     if (use_simt_path(d)) return weights_ws_floats(d);
     const int KT = (d.K + 15) / 16 * 16;
-    return tf_internal_tc_w0_floats(KT, d.H) + (with_feat ? (size_t)(n < 1 ? 1 : n) * d.H : 0);
+    return tf_internal_tc_w0_floats(KT, d.H) + (with_feat ? (size_t)(n < 1 ? 1 : n) * d.H + tf_internal_linear_tc_ws_floats(d.H, d.A) : 0);
 }
 
 extern "C" TF_API size_t tf_sdf_stencil_fwd_workspace(const tf_vm_field_t* f, const tf_sdf_mlp_t* m, int64_t n, int32_t with_feat) {
@@ -607,7 +612,11 @@ static int stencil_fwd_impl(int mode, const tf_vm_field_t* f, const tf_sdf_mlp_t
         if (mode == 0) TF_REQUIRE(sdf7, "sdf7 is NULL"); else TF_REQUIRE(sdf1, "sdf is NULL");
         if (int e = tf_internal_stencil_fwd_tc(f, m, xyz, level, n, units, mode == 0 ? 7 : 1, sdf7, grad, hess, sdf1, spc, w0tc, stream)) return e;
         if (feat) {
-            if (int e = tf_linear_fwd(spc, m->W1 + d.H, m->b1 + 1, n, d.H, d.A, 0, 0.f, feat, stream_)) return e;
+            // appearance head: feat = hidden(centre) W1[1:,:]^T + b1[1:]
+            float* wlin = spc + (size_t)n * d.H;
+            if (tf_internal_linear_tc_ok(spc, feat, d.H, d.A, 0))
+                tf_internal_linear_tc(spc, m->W1 + d.H, d.H, 0, m->b1 + 1, n, d.H, d.A, 0, 0.f, feat, wlin, stream);
+            else if (int e = tf_linear_fwd(spc, m->W1 + d.H, m->b1 + 1, n, d.H, d.A, 0, 0.f, feat, stream_)) return e;
         }
         TF_CHECK_LAUNCH("tf_sdf_stencil_fwd (tcgen05)");
         return 0;
@@ -678,7 +687,7 @@ static bool use_simt_bwd(const Dims& d) {
 // centre hidden [18,H], dHidden(centre) [18,H]]
 static size_t bwd_tc_fixed_floats(const Dims& d) {
     const int KT = (d.K + 15) / 16 * 16;
-    return tf_internal_bwd_tc_wtc_floats(KT, d.H) + (size_t)d.H * KT;
+    return tf_internal_bwd_tc_wtc_floats(KT, d.H) + (size_t)d.H * KT + tf_internal_linear_tc_ws_floats(d.A, d.H);
 }
 static size_t bwd_tc_tile_floats(const Dims& d) {
     const int KT = (d.K + 15) / 16 * 16, spt = tf_internal_bwd_tc_samples_per_tile();
@@ -709,7 +718,8 @@ static int stencil_bwd_tc(const tf_vm_field_t* f, const tf_sdf_mlp_t* m, const D
     if (tiles_fit > ntiles_all) tiles_fit = ntiles_all;
     float* wtc = ws;
     float* tmp = wtc + tf_internal_bwd_tc_wtc_floats(KT, H);
-    float* dpre = tmp + (size_t)H * KT;
+    float* wlin = tmp + (size_t)H * KT;
+    float* dpre = wlin + tf_internal_linear_tc_ws_floats(d.A, H);
     float* arow = dpre + (size_t)tiles_fit * 128 * H;
     float* spc = arow + (size_t)tiles_fit * 128 * KT;
     float* dHc = spc + (size_t)tiles_fit * spt * H;
@@ -721,7 +731,10 @@ static int stencil_bwd_tc(const tf_vm_field_t* f, const tf_sdf_mlp_t* m, const D
         const int64_t ns = s0 + nt * spt < n ? nt * spt : n - s0;
         const float* gf = g_feat ? g_feat + s0 * d.A : nullptr;
         // dHidden(centre) = g_feat W1[1:, :]
-        if (gf) tf_internal_matmul(gf, d.A, m->W1 + H, H, ns, d.A, H, dHc, H, stream);
+        if (gf) {
+            if (tf_internal_linear_tc_ok(gf, dHc, d.A, H, 0)) tf_internal_linear_tc(gf, m->W1 + H, H, 1, nullptr, ns, d.A, H, 0, 0.f, dHc, wlin, stream);
+            else tf_internal_matmul(gf, d.A, m->W1 + H, H, ns, d.A, H, dHc, H, stream);
+        }
         if (int e = tf_internal_stencil_bwd_tc(f, g_field, m, wtc, xyz + s0 * 3, level ? level + s0 : nullptr, ns, units, sdf7 + s0 * NQ,
                                                g_sdf ? g_sdf + s0 : nullptr, g_grad ? g_grad + s0 * 3 : nullptr,
                                                g_hess ? g_hess + s0 : nullptr, gf ? dHc : nullptr, dpre, arow, gf ? spc : nullptr,

@@ -60,6 +60,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// named barrier over a subset of the CTA's warps (id 1..15; id 0 is __syncthreads)
+__device__ __forceinline__ void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
 // ---- MMA issue (single thread) -------------------------------------------------------------------------
 // D[tmem] (+)= A[smem] * B[smem]^T ; kind::tf32 (K=8 per instruction) or kind::f16 (K=16)
 __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {

@@ -24,17 +24,33 @@ __device__ __forceinline__ float4 lo4(float4 v, float4 h) {
     return make_float4(tc::tf32_rn(v.x - h.x), tc::tf32_rn(v.y - h.y), tc::tf32_rn(v.z - h.z), tc::tf32_rn(v.w - h.w));
 }
 
-// stage rows [r0, r0+32) of src [rows][W] as the K-major operand [W][32]: unit (w, c) = rows 4c..4c+3 of column w
-__device__ __forceinline__ void load_split(const float* __restrict__ src, int64_t r0, int64_t r_end, int W, uint8_t* hi, uint8_t* lo) {
-    const int G = W / 4;
-    for (int it = threadIdx.x; it < (RS / 4) * G; it += NTH) {
+// One staging task = the 4x4 block (rows 4c..4c+3, columns 4g..4g+3) of src [rows][W]; a thread owns up to
+// 2 tasks per operand and stage.  The global loads of stage it+1 are issued into registers before stage it is
+// converted and stored, so HBM latency overlaps the staging and MMA work.
+struct Prefetch { float4 v[2][4]; };
+
+__device__ __forceinline__ void stage_load(const float* __restrict__ src, int64_t r0, int64_t r_end, int W, Prefetch& pf) {
+    const int G = W / 4, n_tasks = (RS / 4) * G;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int it = threadIdx.x + k * NTH;
         const int g = it % G, c = it / G;
-        float4 v[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int64_t r = r0 + c * 4 + i;
-            v[i] = r < r_end ? ldg4(src + (size_t)r * W + g * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            pf.v[k][i] = (it < n_tasks && r < r_end) ? ldg4(src + (size_t)r * W + g * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+    }
+}
+// transpose the 4x4 blocks in registers (four 16-byte K-major units each), split into tf32 hi / lo, store
+__device__ __forceinline__ void stage_store(const Prefetch& pf, int W, uint8_t* hi, uint8_t* lo) {
+    const int G = W / 4, n_tasks = (RS / 4) * G;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int it = threadIdx.x + k * NTH;
+        if (it >= n_tasks) continue;
+        const int g = it % G, c = it / G;
+        const float4* v = pf.v[k];
         const float4 t[4] = {make_float4(v[0].x, v[1].x, v[2].x, v[3].x), make_float4(v[0].y, v[1].y, v[2].y, v[3].y),
                              make_float4(v[0].z, v[1].z, v[2].z, v[3].z), make_float4(v[0].w, v[1].w, v[2].w, v[3].w)};
 #pragma unroll
@@ -76,16 +92,23 @@ __global__ void __launch_bounds__(NTH, 1) xty_tc_kernel(const float* __restrict_
     const int64_t r_end = r_begin + rows_per_cta < rows ? r_begin + rows_per_cta : rows;
     const int64_t n_stages = r_begin < r_end ? (r_end - r_begin + RS - 1) / RS : 0;
 
-    for (int64_t it = 0; it < n_stages; ++it) {
+    // register prefetch two stages ahead: sets (px0, py0) / (px1, py1) alternate
+    Prefetch px0, py0, px1, py1;
+    if (n_stages > 0) { stage_load(X, r_begin, r_end, M, px0); stage_load(Y, r_begin, r_end, N, py0); }
+    if (n_stages > 1) { stage_load(X, r_begin + RS, r_end, M, px1); stage_load(Y, r_begin + RS, r_end, N, py1); }
+    auto do_stage = [&](int64_t it, Prefetch& px, Prefetch& py) {
         const int buf = (int)(it & 1);
         uint8_t* xs_hi = smem + (size_t)buf * stage_bytes;
         uint8_t* xs_lo = xs_hi + x_part;
         uint8_t* ys_hi = xs_lo + x_part;
         uint8_t* ys_lo = ys_hi + y_part;
         if (it >= 2) tc::mbar_wait(&empty[buf], (uint32_t)(((it >> 1) - 1) & 1));
-        const int64_t r0 = r_begin + it * RS;
-        load_split(X, r0, r_end, M, xs_hi, xs_lo);
-        load_split(Y, r0, r_end, N, ys_hi, ys_lo);
+        stage_store(px, M, xs_hi, xs_lo);
+        stage_store(py, N, ys_hi, ys_lo);
+        if (it + 2 < n_stages) {
+            const int64_t r2 = r_begin + (it + 2) * RS;
+            stage_load(X, r2, r_end, M, px); stage_load(Y, r2, r_end, N, py);
+        }
         tc::fence_async_smem();
         tc::fence_before_sync();
         __syncthreads();
@@ -107,6 +130,10 @@ __global__ void __launch_bounds__(NTH, 1) xty_tc_kernel(const float* __restrict_
             tc::mma_commit(&empty[buf]);
             if (it == n_stages - 1) tc::mma_commit(done);
         }
+    };
+    for (int64_t it = 0; it < n_stages; it += 2) {
+        do_stage(it, px0, py0);
+        if (it + 1 < n_stages) do_stage(it + 1, px1, py1);
     }
     if (n_stages > 0) {
         tc::mbar_wait(done, 0);
