@@ -225,12 +225,20 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_bwd_tc_kernel(TcBwdParams 
             tc::mma_commit(dfull1);
             ring_prefetch();
         }
+        const int64_t n = s_base + row_s;
+        const bool centre = row_q == 0 && row_s < SPT && n < p.n;
+        const bool has_hc = centre && p.dHc;
+        // dHidden(centre) of the next chunk is fetched one chunk ahead (the first one under the GEMM1 wait)
+        float4 hc[4] = {f4_zero(), f4_zero(), f4_zero(), f4_zero()};
+        if (has_hc) {
+            const float4* src = reinterpret_cast<const float4*>(p.dHc + (size_t)n * H + half * 16);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) hc[j] = __ldg(src + j);
+        }
         tc::mbar_wait(dfull1, tpar);
         tc::fence_after_sync();
         // ---- epilogue-1 + GEMM-dA, chunk by chunk over the hidden units -----------------------------------
-        const int64_t n = s_base + row_s;
         const float gq = gqs[row];
-        const bool centre = row_q == 0 && row_s < SPT && n < p.n;
         for (int c = 0; c < ((p.debug & 16) ? 0 : NCH); ++c) {
             const int buf = c & 1;
             uint8_t* ch_hi = smem + (size_t)buf * 2 * c_part;
@@ -240,13 +248,18 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_bwd_tc_kernel(TcBwdParams 
             float v[16];
             tc::tmem_ld16(d1 + ((uint32_t)(lq * 32) << 16) + col0, v);
             float sp[16];
+            const float hcv[16] = {hc[0].x, hc[0].y, hc[0].z, hc[0].w, hc[1].x, hc[1].y, hc[1].z, hc[1].w,
+                                   hc[2].x, hc[2].y, hc[2].z, hc[2].w, hc[3].x, hc[3].y, hc[3].z, hc[3].w};
+            if (has_hc && c + 1 < NCH) {
+                const float4* src = reinterpret_cast<const float4*>(p.dHc + (size_t)n * H + col0 + HCH);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) hc[j] = __ldg(src + j);
+            }
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 float sg;
                 softplus100_fast_both(v[j] + b0s[col0 + j], sp[j], sg);
-                float dpost = gq * w1s[col0 + j];
-                if (centre && p.dHc) dpost += __ldg(p.dHc + (size_t)n * H + col0 + j);
-                v[j] = dpost * sg;                                   // dPre
+                v[j] = fmaf(gq, w1s[col0 + j], hcv[j]) * sg;         // dPre = dPost * sigmoid
             }
             float4* dst = reinterpret_cast<float4*>(p.dpre + (size_t)(tile_row0 + row) * H + col0);
 #pragma unroll
