@@ -245,6 +245,14 @@ TF_API int tf_csr_spmm3_bwd(const int32_t* rowptr, const int32_t* col, const flo
 TF_API int tf_tc_probe(const float* A, const float* B, int32_t N, int32_t K, int32_t passes, int32_t repeat,
                        float* D, tf_stream_t stream);
 
+/* ---- per-kernel timing ------------------------------------------------------------------------
+ * While enabled, the fused decoder kernels (sdf_stencil_fwd_tc, sdf_stencil_bwd_tc, xty_tc, linear_tc) are
+ * bracketed by CUDA events on their launching stream.  tf_kernel_timing_read sums the recorded launches of
+ * one kernel (it synchronises on their events); returns 1 when nothing was recorded under that name. */
+TF_API void tf_kernel_timing_enable(int32_t on);
+TF_API void tf_kernel_timing_reset(void);
+TF_API int tf_kernel_timing_read(const char* name, double* total_ms, int32_t* launches);
+
 /* ---- weight-gradient accumulate --------------------------------------------------------------
  * out[m][n] += sum_r X[r][m] * Y[r][n]  (X [rows,M], Y [rows,N], out [M,N], all row-major fp32).
  * This is the dW = dPre^T X product every nn.Linear backward of the path ends with

@@ -7,6 +7,12 @@
 
 void tf_set_error(const char* fmt, ...);
 void tf_count_launches(int n);   // bumps the counter behind tf_launch_count()
+// scoped CUDA-event timer around a kernel launch; records only while tf_kernel_timing_enable(1) is in effect
+struct TfKernelTimer {
+    TfKernelTimer(const char* name, cudaStream_t stream);
+    ~TfKernelTimer();
+    const char* name_; cudaStream_t stream_; cudaEvent_t start_, stop_;
+};
 
 #define TF_REQUIRE(cond, ...)                 \
     do {                                      \

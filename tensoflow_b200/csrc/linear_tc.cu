@@ -201,7 +201,10 @@ int tf_internal_linear_tc(const float* X, const float* W, int ldw, int trans, co
     cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int64_t ntiles = (M + TM - 1) / TM;
     const int grid = (int)(ntiles < tf_num_sms() ? ntiles : tf_num_sms());
-    linear_tc_kernel<<<grid, NTH, smem, stream>>>(X, wtc, bias, M, K, KP, N, act, act_p, Y);
+    {
+        TfKernelTimer timer("linear_tc", stream);
+        linear_tc_kernel<<<grid, NTH, smem, stream>>>(X, wtc, bias, M, K, KP, N, act, act_p, Y);
+    }
     tf_count_launches(2);
     return 0;
 }

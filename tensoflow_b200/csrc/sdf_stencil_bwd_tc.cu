@@ -391,7 +391,10 @@ int tf_internal_stencil_bwd_tc(const tf_vm_field_t* f, const tf_vm_mut_t* g, con
     cudaFuncSetAttribute(sdf_stencil_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int64_t ntiles = (n + site::SPT - 1) / site::SPT;
     const int grid = (int)(ntiles < tf_num_sms() ? ntiles : tf_num_sms());
-    sdf_stencil_bwd_tc_kernel<<<grid, NTH, smem, stream>>>(p);
+    {
+        TfKernelTimer timer("sdf_stencil_bwd_tc", stream);
+        sdf_stencil_bwd_tc_kernel<<<grid, NTH, smem, stream>>>(p);
+    }
     tf_count_launches(1);
     return 0;
 }

@@ -294,7 +294,10 @@ int tf_internal_stencil_fwd_tc(const tf_vm_field_t* f, const tf_sdf_mlp_t* m, co
     const int spt = nq == NQ7 ? site::SPT : TM;
     const int64_t ntiles = (n + spt - 1) / spt;
     const int grid = (int)(ntiles < tf_num_sms() ? ntiles : tf_num_sms());
-    sdf_stencil_fwd_tc_kernel<<<grid, NTH, smem, stream>>>(p);
+    {
+        TfKernelTimer timer("sdf_stencil_fwd_tc", stream);
+        sdf_stencil_fwd_tc_kernel<<<grid, NTH, smem, stream>>>(p);
+    }
     tf_count_launches(2);
     return 0;
 }

@@ -20,6 +20,52 @@ static std::atomic<long long> g_launches{0};
 void tf_count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 extern "C" TF_API long long tf_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+// ---- optional per-kernel timing (CUDA events on the launching stream; bench.py reads it for the roofline) ----
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+namespace {
+struct KernelEvents { std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev; };
+std::mutex g_timing_mu;
+std::map<std::string, KernelEvents> g_timing;
+std::atomic<int> g_timing_on{0};
+}  // namespace
+TfKernelTimer::TfKernelTimer(const char* name, cudaStream_t stream) : name_(name), stream_(stream), start_(nullptr), stop_(nullptr) {
+    if (!g_timing_on.load(std::memory_order_relaxed)) return;
+    cudaEventCreate(&start_);
+    cudaEventCreate(&stop_);
+    cudaEventRecord(start_, stream_);
+}
+TfKernelTimer::~TfKernelTimer() {
+    if (!start_) return;
+    cudaEventRecord(stop_, stream_);
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    g_timing[name_].ev.emplace_back(start_, stop_);
+}
+extern "C" TF_API void tf_kernel_timing_enable(int32_t on) {
+    g_timing_on.store(on ? 1 : 0);
+    if (on) return;
+}
+extern "C" TF_API void tf_kernel_timing_reset(void) {
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    for (auto& kv : g_timing)
+        for (auto& e : kv.second.ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    g_timing.clear();
+}
+extern "C" TF_API int tf_kernel_timing_read(const char* name, double* total_ms, int32_t* launches) {
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    auto it = g_timing.find(name ? name : "");
+    *total_ms = 0.0; *launches = 0;
+    if (it == g_timing.end()) return 1;
+    for (auto& e : it->second.ev) {
+        cudaEventSynchronize(e.second);
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, e.first, e.second) == cudaSuccess) { *total_ms += ms; *launches += 1; }
+    }
+    return 0;
+}
+
 int tf_check_field(const tf_vm_field_t* f, bool need_mips) {
     TF_REQUIRE(f != nullptr, "field descriptor is NULL");
     TF_REQUIRE(f->n_comp > 0 && f->n_comp % 4 == 0, "n_comp must be a positive multiple of 4 (got %d)", f->n_comp);

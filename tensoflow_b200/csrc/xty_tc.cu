@@ -177,7 +177,10 @@ int tf_internal_xty_tc(const float* X, const float* Y, int64_t rows, int M, int 
     int64_t rpc = (rows + grid - 1) / grid;
     rpc = (rpc + RS - 1) / RS * RS;
     grid = (rows + rpc - 1) / rpc;
-    xty_tc_kernel<<<(int)grid, NTH, smem, stream>>>(X, Y, rows, M, N, out, ldo, n_valid, rpc);
+    {
+        TfKernelTimer timer("xty_tc", stream);
+        xty_tc_kernel<<<(int)grid, NTH, smem, stream>>>(X, Y, rows, M, N, out, ldo, n_valid, rpc);
+    }
     tf_count_launches(1);
     return 0;
 }
