@@ -211,26 +211,20 @@ def run_ours(args):
     n_batches = 4
     host = [{k: v.pin_memory() for k, v in synthetic.make_rays(cfg["rays"], seed=1000 * rank + b).items()} for b in range(n_batches)]
     h2d = sum(v.numel() * v.element_size() for v in host[0].values())
-    flat = None
+    bucket = None
     if world > 1:
-        flat = torch.zeros(sum(p.numel() for p in params), device=dev)
+        from tensoflow_b200.dist import FlatGradBucket
+        bucket = FlatGradBucket(params)
 
     def zero_grads():
         for p in params:
             p.grad = None
 
     def allreduce_grads():
-        if world == 1:
-            return
-        off = 0
-        views = []
-        for p in params:
-            g = p.grad
-            v = g.permute(0, 2, 3, 1).reshape(-1) if g.dim() == 4 else g.reshape(-1)
-            flat[off:off + v.numel()].copy_(v)
-            views.append((p, off, v.numel()))
-            off += v.numel()
-        dist.all_reduce(flat)
+        # one sum-allreduce of the flat fp32 gradient bucket (VM planes / lines, MLP weights, variance); the summed
+        # gradients are written back into p.grad, as an optimizer step would consume them
+        if bucket is not None:
+            bucket.allreduce()
 
     def step_device(b):
         rays = {k: v.to(dev, non_blocking=True) for k, v in host[b % n_batches].items()}
