@@ -154,14 +154,21 @@ TF_API int tf_neus_composite_bwd(const float* sdf, const float* grad, const floa
  * (network/flow.py:577-598) and TensoFlow.nis_mat (network/flow.py:694-697).
  * act: 0 none, 1 ReLU, 2 LeakyReLU(0.01), 3 Softplus(beta=100), 4 Sigmoid,
  *      5 exp(min(x, act_param)) (ExpActivation, network/other_field.py:12-18).
- * Row-major contiguous X, W, Y.  b may be NULL. */
+ * Row-major contiguous X, W, Y.  b may be NULL.
+ * `workspace` (tf_linear_workspace(K, N) bytes, 16-byte aligned, may be NULL) holds the pre-split weights of the
+ * tensor-core path: with it, layers of >= 8192 rows and 96 <= K <= 1024, 96 <= N <= 256 run on tcgen05 (3xTF32,
+ * fp32-level accuracy; K / N need not be aligned, padded inside); without it, for small batches and for narrow
+ * layers the FFMA kernels run. */
+TF_API size_t tf_linear_workspace(int32_t K, int32_t N);
 TF_API int tf_linear_fwd(const float* X, const float* W, const float* b, int64_t M, int32_t K,
-                         int32_t N, int32_t act, float act_param, float* Y, tf_stream_t stream);
+                         int32_t N, int32_t act, float act_param, float* Y, void* workspace,
+                         size_t ws_bytes, tf_stream_t stream);
 /* dpre[M,N] = dY * act'(Y) (written; must not alias dY); dX[M,K] = dpre W (dX may be NULL);
  * dW[N,K] += dpre^T X and db[N] += colsum(dpre) (each may be NULL). */
 TF_API int tf_linear_bwd(const float* X, const float* W, const float* Y, const float* dY,
                          float* dpre, int64_t M, int32_t K, int32_t N, int32_t act,
-                         float act_param, float* dX, float* dW, float* db, tf_stream_t stream);
+                         float act_param, float* dX, float* dW, float* db, void* workspace,
+                         size_t ws_bytes, tf_stream_t stream);
 
 /* ---- TensoFlow sampler: piecewise-quadratic coupling transform -------------------
  * ElementWisePWQuadraticTransform of the reference (network/flow.py:314-525), one

@@ -64,9 +64,10 @@ _SIGNATURES = {
 
 # later sections of the ABI (small MLP layers, flow sampler, MC shading, BVH)
 _OPTIONAL_SIGNATURES = {
-    "tf_linear_fwd": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_float, _P, _P]),
+    "tf_linear_workspace": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "tf_linear_fwd": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_float, _P, _P, C.c_size_t, _P]),
     "tf_linear_bwd": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_float,
-                                _P, _P, _P, _P]),
+                                _P, _P, _P, _P, C.c_size_t, _P]),
     "tf_pwquad_fwd": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, _P, _P]),
     "tf_pwquad_bwd": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P, _P, _P]),
     "tf_bvh_create": (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.POINTER(C.c_void_p)]),

@@ -1,5 +1,9 @@
 // Dense layer on the tensor cores: Y[M,N] = act(X[M,K] Wt[N,K]^T + b)   (3xTF32: fp32-level accuracy).
 //
+// BWD mode computes the data gradient of a layer: the A operand is dPre = dY * act'(Y), formed on load (and written
+// back for the weight-gradient pass), contracted with the transposed weights: dX[M,K] = dPre[M,N] W[N,K].
+// The output width is padded to a multiple of 16 inside the kernel (zero weight rows, masked stores) and X rows of
+// any length are accepted (scalar loads when a row is not float4-aligned).
 // Used for the appearance head of the SDF decoder (hidden [n,H] -> feat [n,A], reference network/fields.py:192-198)
 // and its input gradient (g_feat [n,A] -> dHidden [n,H], Wt = W1[1:,:]^T).  X rows stream from HBM once:
 // one persistent CTA per SM walks 128-row tiles; per K-chunk of 32 the threads load the X chunk (coalesced
@@ -9,6 +13,7 @@
 // epilogue of tile t-1 (bias, activation, 64-byte row stores) overlaps the loads / MMAs of tile t.
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "act.cuh"
 
 namespace {
 
@@ -21,18 +26,18 @@ constexpr uint32_t X_SBO = (KC / 4) * X_LBO;
 constexpr uint32_t X_PART = 16 * X_SBO;      // bytes of one X part (hi or lo) of a stage
 
 // pre-split weights: chunk kc -> [N rows x 32] K-major hi | lo
-__global__ void linear_tc_prep_kernel(const float* __restrict__ W, int ldw, int trans, int N, int K, int KP, float* __restrict__ Wtc) {
+__global__ void linear_tc_prep_kernel(const float* __restrict__ W, int ldw, int trans, int N, int NP, int K, int KP, float* __restrict__ Wtc) {
     const int nchunks = KP / KC;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nchunks * N * KC; i += gridDim.x * blockDim.x) {
-        const int kl = i % KC, n = (i / KC) % N, kc = i / (KC * N);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nchunks * NP * KC; i += gridDim.x * blockDim.x) {
+        const int kl = i % KC, n = (i / KC) % NP, kc = i / (KC * NP);
         const int k = kc * KC + kl;
         // trans == 0: Wt[n][k] = W[n*ldw + k];  trans == 1: Wt[n][k] = W[k*ldw + n]
-        const float v = k < K ? (trans ? W[(size_t)k * ldw + n] : W[(size_t)n * ldw + k]) : 0.f;
+        const float v = (k < K && n < N) ? (trans ? W[(size_t)k * ldw + n] : W[(size_t)n * ldw + k]) : 0.f;
         const float hi = tc::tf32_rn(v);
-        float* base = Wtc + (size_t)kc * 2 * N * KC;
+        float* base = Wtc + (size_t)kc * 2 * NP * KC;
         const uint32_t off = tc::tile_off_b32(n, kl, KC / 4) / 4;
         base[off] = hi;
-        base[(size_t)N * KC + off] = tc::tf32_rn(v - hi);
+        base[(size_t)NP * KC + off] = tc::tf32_rn(v - hi);
     }
 }
 
@@ -47,14 +52,38 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 
 struct XRegs { float4 v[4]; };     // one stage of X per thread: 128 rows x 8 chunks = 1024 float4 / 256 threads
 
-__device__ __forceinline__ void x_load(const float* __restrict__ X, int64_t M, int K, int64_t row0, int k0, XRegs& r) {
+// one stage of the A operand: X[m][k0 .. k0+32) for the tile's 128 rows.  BWD: element = dY * act'(Y), also stored to dpre
+template <bool BWD>
+__device__ __forceinline__ void x_load(const float* __restrict__ X, const float* __restrict__ Yact, float* __restrict__ dpre, int act,
+                                       float act_p, bool vec, int64_t M, int K, int64_t row0, int k0, XRegs& r) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int it = threadIdx.x + j * NTH;
         const int row = it >> 3, ch = it & 7;
         const int64_t m = row0 + row;
         const int k = k0 + ch * 4;
-        r.v[j] = (m < M && k < K) ? ldg4(X + (size_t)m * K + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m < M && k < K) {
+            const size_t o = (size_t)m * K + k;
+            if (vec) {
+                v = ldg4(X + o);
+                if (BWD) {
+                    const float4 y = ldg4(Yact + o);
+                    v.x *= act_bwd(y.x, act, act_p); v.y *= act_bwd(y.y, act, act_p); v.z *= act_bwd(y.z, act, act_p); v.w *= act_bwd(y.w, act, act_p);
+                    *reinterpret_cast<float4*>(dpre + o) = v;
+                }
+            } else {
+                float e[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (k + i < K) {
+                        e[i] = __ldg(X + o + i);
+                        if (BWD) { e[i] *= act_bwd(__ldg(Yact + o + i), act, act_p); dpre[o + i] = e[i]; }
+                    }
+                v = make_float4(e[0], e[1], e[2], e[3]);
+            }
+        }
+        r.v[j] = v;
     }
 }
 __device__ __forceinline__ void x_store(const XRegs& r, uint8_t* hi, uint8_t* lo) {
@@ -71,19 +100,14 @@ __device__ __forceinline__ void x_store(const XRegs& r, uint8_t* hi, uint8_t* lo
     }
 }
 
-__device__ __forceinline__ float act_apply(float v, int act, float a) {
-    switch (act) {
-        case 1: return fmaxf(v, 0.f);
-        case 2: return 1.f / (1.f + __expf(-v));
-        case 3: { const float z = v * a; return z > 20.f ? v : log1pf(__expf(z)) / a; }
-        default: return v;
-    }
-}
-
-__global__ void __launch_bounds__(NTH, 1) linear_tc_kernel(const float* __restrict__ X, const float* __restrict__ Wtc, const float* __restrict__ bias,
-                                                           int64_t M, int K, int KP, int N, int act, float act_p, float* __restrict__ Y) {
+template <bool BWD>
+__global__ void __launch_bounds__(NTH, 1) linear_tc_kernel(const float* __restrict__ X, const float* __restrict__ Yact, float* __restrict__ dpre,
+                                                           const float* __restrict__ Wtc, const float* __restrict__ bias, int64_t M, int K, int KP,
+                                                           int N, int NP, int act, float act_p, float* __restrict__ Y) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const uint32_t w_part = (uint32_t)N * KC * 4;
+    const uint32_t w_part = (uint32_t)NP * KC * 4;
+    const bool vec = (K % 4 == 0) && (((uintptr_t)X & 15) == 0) && (!BWD || ((((uintptr_t)Yact | (uintptr_t)dpre) & 15) == 0));
+    const bool vec_out = (N % 4 == 0) && (((uintptr_t)Y & 15) == 0);
     const uint32_t stage_bytes = 2 * X_PART + 2 * w_part;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)NSTG * stage_bytes);
     uint64_t* wfull = bars;              // [NSTG] weight chunk landed
@@ -106,7 +130,7 @@ __global__ void __launch_bounds__(NTH, 1) linear_tc_kernel(const float* __restri
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t idesc = tc::make_idesc(2, 2, TM, N);
+    const uint32_t idesc = tc::make_idesc(2, 2, TM, NP);
     const uint32_t w_sbo = (KC / 4) * 128;
 
     auto epilogue = [&](int64_t tp) {
@@ -116,22 +140,32 @@ __global__ void __launch_bounds__(NTH, 1) linear_tc_kernel(const float* __restri
         const int lq = warp & 3, half = warp >> 2;
         const int64_t m = tile * TM + lq * 32 + lane;
         const uint32_t d = tmem_base + (uint32_t)(tp & 1) * 256 + ((uint32_t)(lq * 32) << 16);
-        for (int c0 = half * 16; c0 < N; c0 += 32) {
+        for (int c0 = half * 16; c0 < NP; c0 += 32) {
             float v[16];
             tc::tmem_ld16(d + c0, v);
             if (m < M) {
+                if (!BWD) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = act_apply(v[j] + (bias ? __ldg(bias + c0 + j) : 0.f), act, act_p);
-                float4* dst = reinterpret_cast<float4*>(Y + (size_t)m * N + c0);
+                    for (int j = 0; j < 16; ++j)
+                        if (c0 + j < N) v[j] = act_fwd(v[j] + (bias ? __ldg(bias + c0 + j) : 0.f), act, act_p);
+                }
+                if (vec_out) {
+                    float4* dst = reinterpret_cast<float4*>(Y + (size_t)m * N + c0);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    for (int j = 0; j < 4; ++j)
+                        if (c0 + 4 * j < N) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c0 + j < N) Y[(size_t)m * N + c0 + j] = v[j];
+                }
             }
         }
         tc::fence_before_sync();
     };
 
     XRegs xr;
-    if (total > 0) x_load(X, M, K, (int64_t)blockIdx.x * TM, 0, xr);
+    if (total > 0) x_load<BWD>(X, Yact, dpre, act, act_p, vec, M, K, (int64_t)blockIdx.x * TM, 0, xr);
     for (int64_t g = 0; g < total; ++g) {
         const int64_t t = g / nchunks;
         const int kc = (int)(g % nchunks);
@@ -143,12 +177,12 @@ __global__ void __launch_bounds__(NTH, 1) linear_tc_kernel(const float* __restri
         if (g >= NSTG) tc::mbar_wait(&sfree[st], (uint32_t)(((g / NSTG) - 1) & 1));
         if (tid == 0) {
             mbar_expect_tx(&wfull[st], 2 * w_part);
-            bulk_copy_g2s(w_hi, Wtc + (size_t)kc * 2 * N * KC, 2 * w_part, &wfull[st]);
+            bulk_copy_g2s(w_hi, Wtc + (size_t)kc * 2 * NP * KC, 2 * w_part, &wfull[st]);
         }
         x_store(xr, x_hi, x_lo);
         if (g + 1 < total) {
             const int64_t g1 = g + 1;
-            x_load(X, M, K, (blockIdx.x + (g1 / nchunks) * gridDim.x) * TM, (int)(g1 % nchunks) * KC, xr);
+            x_load<BWD>(X, Yact, dpre, act, act_p, vec, M, K, (blockIdx.x + (g1 / nchunks) * gridDim.x) * TM, (int)(g1 % nchunks) * KC, xr);
         }
         tc::fence_async_smem();
         tc::fence_before_sync();
@@ -179,31 +213,52 @@ __global__ void __launch_bounds__(NTH, 1) linear_tc_kernel(const float* __restri
     if (warp == 0) tc::tmem_dealloc<512>(tmem_base);
 }
 
-size_t linear_tc_smem(int N) { return (size_t)NSTG * (2 * X_PART + 2 * (size_t)N * KC * 4) + (2 * NSTG + 2) * 8 + 16; }
+size_t linear_tc_smem(int NP) { return (size_t)NSTG * (2 * X_PART + 2 * (size_t)NP * KC * 4) + (2 * NSTG + 2) * 8 + 16; }
+int pad16(int n) { return (n + 15) / 16 * 16; }
 
 }  // namespace
 
+// shapes the tensor-core dense layer takes: contraction and output widths up to 256
 bool tf_internal_linear_tc_ok(const float* X, const float* Y, int K, int N, int act) {
-    if (N % 16 != 0 || N < 16 || N > 256 || K % 4 != 0 || K < 4) return false;
-    if (act != 0) return false;          // callers on the stencil path need no activation; others use the FFMA kernel
-    if (((uintptr_t)X & 15) || ((uintptr_t)Y & 15)) return false;
-    return linear_tc_smem(N) <= 227 * 1024;
+    (void)X; (void)Y;
+    if (N < 1 || N > 256 || K < 1 || K > 1024) return false;
+    if (act < 0 || act > 5) return false;
+    return linear_tc_smem(pad16(N)) <= 227 * 1024;
 }
-size_t tf_internal_linear_tc_ws_floats(int K, int N) { return (size_t)2 * N * ((K + KC - 1) / KC * KC); }
+size_t tf_internal_linear_tc_ws_floats(int K, int N) { return (size_t)2 * pad16(N) * ((K + KC - 1) / KC * KC); }
 
 // Y = act(X Wt^T + b); Wt[n][k] = trans ? W[k*ldw + n] : W[n*ldw + k]; `wtc` = scratch of tf_internal_linear_tc_ws_floats floats
 int tf_internal_linear_tc(const float* X, const float* W, int ldw, int trans, const float* bias, int64_t M, int K, int N, int act, float act_p,
                           float* Y, float* wtc, cudaStream_t stream) {
     if (M == 0) return 0;
-    const int KP = (K + KC - 1) / KC * KC;
-    linear_tc_prep_kernel<<<64, 256, 0, stream>>>(W, ldw, trans, N, K, KP, wtc);
-    const size_t smem = linear_tc_smem(N);
-    cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int KP = (K + KC - 1) / KC * KC, NP = pad16(N);
+    linear_tc_prep_kernel<<<64, 256, 0, stream>>>(W, ldw, trans, N, NP, K, KP, wtc);
+    const size_t smem = linear_tc_smem(NP);
+    cudaFuncSetAttribute(linear_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int64_t ntiles = (M + TM - 1) / TM;
     const int grid = (int)(ntiles < tf_num_sms() ? ntiles : tf_num_sms());
     {
         TfKernelTimer timer("linear_tc", stream);
-        linear_tc_kernel<<<grid, NTH, smem, stream>>>(X, wtc, bias, M, K, KP, N, act, act_p, Y);
+        linear_tc_kernel<false><<<grid, NTH, smem, stream>>>(X, nullptr, nullptr, wtc, bias, M, K, KP, N, NP, act, act_p, Y);
+    }
+    tf_count_launches(2);
+    return 0;
+}
+
+// data gradient of Y = act(X W^T + b), W [N,K]: dPre = dY * act'(Y) (written to `dpre`), dX[M,K] = dPre W
+int tf_internal_linear_tc_bwd(const float* dY, const float* Yact, float* dpre, const float* W, int64_t M, int K, int N, int act, float act_p,
+                              float* dX, float* wtc, cudaStream_t stream) {
+    if (M == 0) return 0;
+    // contraction over the layer's N outputs, K output columns: Wt[k][n] = W[n*K + k]
+    const int KP = (N + KC - 1) / KC * KC, NP = pad16(K);
+    linear_tc_prep_kernel<<<64, 256, 0, stream>>>(W, K, 1, K, NP, N, KP, wtc);
+    const size_t smem = linear_tc_smem(NP);
+    cudaFuncSetAttribute(linear_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int64_t ntiles = (M + TM - 1) / TM;
+    const int grid = (int)(ntiles < tf_num_sms() ? ntiles : tf_num_sms());
+    {
+        TfKernelTimer timer("linear_tc_bwd", stream);
+        linear_tc_kernel<true><<<grid, NTH, smem, stream>>>(dY, Yact, dpre, wtc, nullptr, M, N, KP, K, NP, act, act_p, dX);
     }
     tf_count_launches(2);
     return 0;

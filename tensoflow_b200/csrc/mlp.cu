@@ -6,34 +6,11 @@
 //   bwd-wgt  : dW += dPre^T X (xty),  db += colsum(dPre)
 // v1 arithmetic is fp32 FFMA (128x64 CTA tile, 8x4 register tile); see DESIGN.md.
 #include "common.cuh"
+#include "act.cuh"
 
 namespace {
 
 constexpr int BM = 128, BN = 64, BK = 16, BMP = BM + 4, BNP = BN + 4;
-
-enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2, ACT_SOFTPLUS100 = 3, ACT_SIGMOID = 4, ACT_EXP = 5 };
-
-__device__ __forceinline__ float act_fwd(float x, int act, float p) {
-    switch (act) {
-        case ACT_RELU: return fmaxf(x, 0.f);
-        case ACT_LEAKY: return x > 0.f ? x : 0.01f * x;
-        case ACT_SOFTPLUS100: return softplus100(x);
-        case ACT_SIGMOID: return 1.f / (1.f + expf(-x));
-        case ACT_EXP: return expf(fminf(x, p));          // ExpActivation (other_field.py:12-18)
-        default: return x;
-    }
-}
-// derivative expressed through the OUTPUT y (so only Y has to be kept for backward)
-__device__ __forceinline__ float act_bwd(float y, int act, float p) {
-    switch (act) {
-        case ACT_RELU: return y > 0.f ? 1.f : 0.f;
-        case ACT_LEAKY: return y > 0.f ? 1.f : 0.01f;
-        case ACT_SOFTPLUS100: return 1.f - expf(-100.f * y);
-        case ACT_SIGMOID: return y * (1.f - y);
-        case ACT_EXP: return y < expf(p) ? y : 0.f;
-        default: return 1.f;
-    }
-}
 
 // out[M][Nout] = epi( A[M][Kred] * B ),  B[kk][j] = TRANS_W ? W[kk*ldw + j] : W[j*ldw + kk]
 // BWD: A element = dY * act'(Y) (and stored to dpre by the blockIdx.y == 0 column of CTAs)
@@ -231,11 +208,40 @@ int tf_internal_colsum(const float* X, int ldx, int64_t rows, int cols, float* o
     return 0;
 }
 
+// tensor-core dense layer (linear_tc.cu) and weight-gradient kernel (xty_tc.cu)
+bool tf_internal_linear_tc_ok(const float* X, const float* Y, int K, int N, int act);
+size_t tf_internal_linear_tc_ws_floats(int K, int N);
+int tf_internal_linear_tc(const float* X, const float* W, int ldw, int trans, const float* bias, int64_t M, int K, int N, int act, float act_p,
+                          float* Y, float* wtc, cudaStream_t stream);
+int tf_internal_linear_tc_bwd(const float* dY, const float* Yact, float* dpre, const float* W, int64_t M, int K, int N, int act, float act_p,
+                              float* dX, float* wtc, cudaStream_t stream);
+bool tf_internal_xty_tc_ok(const float* X, const float* Y, int M, int N);
+int tf_internal_xty_tc(const float* X, const float* Y, int64_t rows, int M, int N, float* out, int ldo, int n_valid, cudaStream_t stream);
+
+// Tensor-core dispatch: at least 8192 rows and both widths >= 96.  Narrow layers (the coupling-layer conditioners,
+// 44 -> 64 -> 64 -> 21, and 1..3-wide heads) stay on the FFMA kernels: the tensor core would run mostly padding
+// there, and the spline parameters they produce are the one place where 3xTF32's ~22-bit products (vs 24) showed
+// up in the gradient tolerances.
+static const int64_t TC_MIN_ROWS = 8192;
+static bool tc_shape(int64_t M, int K, int N) { return M >= TC_MIN_ROWS && K >= 96 && N >= 96; }
+
+extern "C" TF_API size_t tf_linear_workspace(int32_t K, int32_t N) {
+    if (K < 1 || N < 1) return 0;
+    const size_t a = tf_internal_linear_tc_ws_floats(K, N), b = tf_internal_linear_tc_ws_floats(N, K);
+    return (a > b ? a : b) * sizeof(float);
+}
+
 extern "C" TF_API int tf_linear_fwd(const float* X, const float* W, const float* b, int64_t M, int32_t K, int32_t N, int32_t act,
-                                    float act_param, float* Y, tf_stream_t stream) {
+                                    float act_param, float* Y, void* workspace, size_t ws_bytes, tf_stream_t stream) {
     if (M == 0) return 0;
     TF_REQUIRE(X && W && Y, "tf_linear_fwd: NULL pointer");
     TF_REQUIRE(K > 0 && N > 0 && act >= 0 && act <= 5, "tf_linear_fwd: bad K/N/act (%d,%d,%d)", K, N, act);
+    if (workspace && tc_shape(M, K, N) && tf_internal_linear_tc_ok(X, Y, K, N, act) && ((uintptr_t)workspace & 15) == 0 &&
+        ws_bytes >= tf_internal_linear_tc_ws_floats(K, N) * sizeof(float)) {
+        tf_internal_linear_tc(X, W, K, 0, b, M, K, N, act, act_param, Y, (float*)workspace, (cudaStream_t)stream);
+        TF_CHECK_LAUNCH("tf_linear_fwd (tcgen05)");
+        return 0;
+    }
     dim3 grid((unsigned)((M + BM - 1) / BM), (N + BN - 1) / BN);
     linear_kernel<false, false><<<grid, 256, 0, (cudaStream_t)stream>>>(X, K, nullptr, nullptr, W, K, b, M, K, N, act, act_param, Y, N);
     tf_count_launches(1);
@@ -245,25 +251,30 @@ extern "C" TF_API int tf_linear_fwd(const float* X, const float* W, const float*
 
 extern "C" TF_API int tf_linear_bwd(const float* X, const float* W, const float* Y, const float* dY, float* dpre, int64_t M,
                                     int32_t K, int32_t N, int32_t act, float act_param, float* dX, float* dW, float* db,
-                                    tf_stream_t stream_) {
+                                    void* workspace, size_t ws_bytes, tf_stream_t stream_) {
     if (M == 0) return 0;
     TF_REQUIRE(X && W && Y && dY && dpre && dY != dpre, "tf_linear_bwd: NULL pointer (or dY aliases dpre)");
     TF_REQUIRE(K > 0 && N > 0 && act >= 0 && act <= 5, "tf_linear_bwd: bad K/N/act (%d,%d,%d)", K, N, act);
     cudaStream_t stream = (cudaStream_t)stream_;
     // dPre = dY * act'(Y) and dX = dPre W.  dX may be NULL (first layer): then a one-column
     // launch still materialises dPre.
-    float* scratch_dx = dX;
-    int kcols = K;
-    if (!dX) { kcols = 0; }
-    if (dX) {
+    if (dX && workspace && tc_shape(M, K, N) && tf_internal_linear_tc_ok(dY, dX, N, K, act) && ((uintptr_t)workspace & 15) == 0 &&
+        ws_bytes >= tf_internal_linear_tc_ws_floats(N, K) * sizeof(float)) {
+        tf_internal_linear_tc_bwd(dY, Y, dpre, W, M, K, N, act, act_param, dX, (float*)workspace, stream);
+    } else if (dX) {
         dim3 grid((unsigned)((M + BM - 1) / BM), (K + BN - 1) / BN);
-        linear_kernel<true, true><<<grid, 256, 0, stream>>>(dY, N, Y, dpre, W, K, nullptr, M, N, K, act, act_param, scratch_dx, K);
+        linear_kernel<true, true><<<grid, 256, 0, stream>>>(dY, N, Y, dpre, W, K, nullptr, M, N, K, act, act_param, dX, K);
+        tf_count_launches(1);
     } else {
         dim3 grid((unsigned)((M + BM - 1) / BM), 1);
-        linear_kernel<true, true><<<grid, 256, 0, stream>>>(dY, N, Y, dpre, W, K, nullptr, M, N, kcols, act, act_param, nullptr, K);
+        linear_kernel<true, true><<<grid, 256, 0, stream>>>(dY, N, Y, dpre, W, K, nullptr, M, N, 0, act, act_param, nullptr, K);
+        tf_count_launches(1);
     }
-    tf_count_launches(1);
-    if (dW) tf_internal_xty(dpre, N, X, K, M, N, K, dW, K, stream);
+    if (dW) {
+        // dW[n][k] += sum_m dPre[m][n] X[m][k]
+        if (tc_shape(M, K, N) && K % 16 == 0 && tf_internal_xty_tc_ok(dpre, X, N, K)) tf_internal_xty_tc(dpre, X, M, N, K, dW, K, K, stream);
+        else tf_internal_xty(dpre, N, X, K, M, N, K, dW, K, stream);
+    }
     if (db) tf_internal_colsum(dpre, N, M, N, db, stream);
     TF_CHECK_LAUNCH("tf_linear_bwd");
     return 0;

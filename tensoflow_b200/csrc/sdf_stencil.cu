@@ -616,7 +616,7 @@ static int stencil_fwd_impl(int mode, const tf_vm_field_t* f, const tf_sdf_mlp_t
             float* wlin = spc + (size_t)n * d.H;
             if (tf_internal_linear_tc_ok(spc, feat, d.H, d.A, 0))
                 tf_internal_linear_tc(spc, m->W1 + d.H, d.H, 0, m->b1 + 1, n, d.H, d.A, 0, 0.f, feat, wlin, stream);
-            else if (int e = tf_linear_fwd(spc, m->W1 + d.H, m->b1 + 1, n, d.H, d.A, 0, 0.f, feat, stream_)) return e;
+            else if (int e = tf_linear_fwd(spc, m->W1 + d.H, m->b1 + 1, n, d.H, d.A, 0, 0.f, feat, nullptr, 0, stream_)) return e;
         }
         TF_CHECK_LAUNCH("tf_sdf_stencil_fwd (tcgen05)");
         return 0;

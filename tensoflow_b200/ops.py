@@ -336,6 +336,7 @@ class NeusCompositeFunction(torch.autograd.Function):
         return d_sdf, d_grad, None, None, None, dv, None, d_vals, None
 
 
+LINEAR_TC_MIN_ROWS = 8192    # below this the library uses its FFMA kernel and needs no workspace
 ACT = {"none": 0, "relu": 1, "leaky": 2, "softplus100": 3, "sigmoid": 4, "exp": 5}
 
 
@@ -351,9 +352,11 @@ class LinearFunction(torch.autograd.Function):
         M, K = Xc.shape
         N = Wc.shape[0]
         Y = torch.empty(M, N, device=Xc.device, dtype=torch.float32)
-        with _timed("linear_fwd"):
-            check(lib.tf_linear_fwd(ptr(Xc), ptr(Wc), ptr(bc), M, K, N, ACT[act], float(act_param), ptr(Y), stream_ptr()),
-                  "tf_linear_fwd")
+        wsb = int(lib.tf_linear_workspace(K, N)) if M >= LINEAR_TC_MIN_ROWS else 0
+        ws = torch.empty(wsb // 4, device=Xc.device, dtype=torch.float32) if wsb else None
+        with _timed(f"linear_fwd[{K}->{N}]"):
+            check(lib.tf_linear_fwd(ptr(Xc), ptr(Wc), ptr(bc), M, K, N, ACT[act], float(act_param), ptr(Y), ptr(ws), wsb,
+                                    stream_ptr()), "tf_linear_fwd")
         ctx.save_for_backward(Xc, Wc, Y)
         ctx.act, ctx.act_param, ctx.has_bias = act, float(act_param), b is not None
         return Y
@@ -370,9 +373,11 @@ class LinearFunction(torch.autograd.Function):
         dX = torch.empty(M, K, device=Xc.device, dtype=torch.float32) if need_x else None
         dW = torch.zeros_like(Wc) if need_w else None
         db = torch.zeros(N, device=Xc.device, dtype=torch.float32) if need_b else None
-        with _timed("linear_bwd"):
+        wsb = int(lib.tf_linear_workspace(K, N)) if M >= LINEAR_TC_MIN_ROWS else 0
+        ws = torch.empty(wsb // 4, device=Xc.device, dtype=torch.float32) if wsb else None
+        with _timed(f"linear_bwd[{K}->{N}]"):
             check(lib.tf_linear_bwd(ptr(Xc), ptr(Wc), ptr(Y), ptr(gYc), ptr(dpre), M, K, N, ACT[ctx.act], ctx.act_param,
-                                    ptr(dX), ptr(dW), ptr(db), stream_ptr()), "tf_linear_bwd")
+                                    ptr(dX), ptr(dW), ptr(db), ptr(ws), wsb, stream_ptr()), "tf_linear_bwd")
         return dX, dW, db, None, None
 
 

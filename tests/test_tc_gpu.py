@@ -58,3 +58,38 @@ def test_xty_tensor_core_matches_fp64(rows, M, N):
         e = float((out.double() - 1 - ref).abs().max() / ref.abs().max())
         print(f"rows={rows} M={M} N={N} simt={force_simt}: {e:.2e}")
         assert e < 5e-6, e
+
+
+@pytest.mark.parametrize("M,K,N,act", [(20000, 123, 256, "relu"), (9000, 256, 99, "exp"), (10000, 108, 128, "sigmoid"),
+                                       (8200, 256, 256, "relu"), (8192, 97, 101, "none"), (9000, 256, 3, "exp")])
+def test_linear_tensor_core_fwd_bwd(M, K, N, act):
+    """ops.linear on the tcgen05 path (M >= 8192): padded N, unaligned K, activation epilogue, data and weight gradients."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from tensoflow_b200 import ops
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(M + K + N)
+    X = torch.randn(M, K, generator=g)
+    W = torch.randn(N, K, generator=g) / K ** 0.5
+    b = 0.1 * torch.randn(N, generator=g)
+    gY = torch.randn(M, N, generator=g)
+
+    def run(dt, device, fn):
+        x, w, bb = (t.detach().clone().to(device=device, dtype=dt).requires_grad_() for t in (X, W, b))
+        y = fn(x, w, bb)
+        y.backward(gY.to(device=device, dtype=dt))
+        return [t.detach().cpu().double() for t in (y, x.grad, w.grad, bb.grad)]
+
+    def torch_fn(x, w, bb):
+        z = x @ w.T + bb
+        return {"relu": torch.relu, "sigmoid": torch.sigmoid, "none": lambda t: t, "exp": lambda t: torch.exp(t.clamp(max=5.0))}[act](z)
+
+    ref = run(torch.float64, "cpu", torch_fn)
+    f32 = run(torch.float32, "cpu", torch_fn)
+    ours = run(torch.float32, dev, lambda x, w, bb: ops.linear(x, w, bb, act, 5.0))
+    for name, o, r, f in zip(("y", "dX", "dW", "db"), ours, ref, f32):
+        e = float((o - r).abs().max() / r.abs().max())
+        e32 = float((f - r).abs().max() / r.abs().max())
+        print(f"{name}: ours {e:.2e} torch-fp32 {e32:.2e}")
+        # 3xTF32 keeps ~22 mantissa bits per product; exp() turns the absolute error of its argument into a relative one
+        assert e <= max(2e-5 if act == "exp" else 3e-6, 4 * e32), (name, e, e32)
