@@ -50,7 +50,8 @@ def _worker(rank, world, port, q):
     bucket = FlatGradBucket(m.parameters())
     bucket.allreduce()
     tiles = gather_tiles(per_ray.detach()[:, None])
-    q.put((rank, [p.grad.clone() for p in m.parameters()], float(mean_kept), tiles))
+    # numpy payloads are pickled by value (torch tensors travel as file descriptors the exiting worker may close first)
+    q.put((rank, [p.grad.clone().numpy() for p in m.parameters()], float(mean_kept), tiles.numpy()))
     dist.destroy_process_group()
 
 
@@ -63,6 +64,7 @@ def test_flat_bucket_allreduce_matches_single_process():
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    res = [(r, [torch.from_numpy(g) for g in gs], mk, torch.from_numpy(t)) for r, gs, mk, t in res]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
