@@ -30,7 +30,8 @@ constexpr int TM = 128;     // rows per MMA tile = samples per block
 constexpr int NQ7 = 7;
 constexpr int KSL = 16;     // K-slice (2 tf32 MMA k-steps)
 constexpr int NST = 2;      // W ring stages
-constexpr int NTH = 256;
+constexpr int NTH = 512;    // 16 warps at <= 128 registers: the gather is latency-bound, thread-level parallelism hides it
+constexpr int NCG = NTH / 128; // column groups of the epilogue (warps sharing a TMEM lane quarter)
 
 struct TcParams {
     tf_vm_field_t f;
@@ -128,8 +129,8 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_fwd_tc_kernel(TcParams p) 
     uint8_t* wst = a_lo + a_part;                             // NST stages x (hi, lo)
     float* b0s = reinterpret_cast<float*>(wst + (size_t)NST * 2 * w_part);
     float* w1s = b0s + H;
-    float* sdfs = w1s + H;                                    // [2 tiles][2 column halves][TM]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sdfs + 4 * TM);
+    float* sdfs = w1s + H;                                    // [2 tiles][NCG column groups][TM]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sdfs + 2 * NCG * TM);
     uint64_t* full = bars;                                    // [NST]
     uint64_t* empty = bars + NST;                             // [NST]
     uint64_t* dfull = bars + 2 * NST;                         // [2]
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_fwd_tc_kernel(TcParams p) 
             const bool centre = q == 0 && s < spt && n < p.n;
             const uint32_t dcol = tmem_base + (uint32_t)(tp & 1) * 256 + ((uint32_t)(lq * 32) << 16);
             float psum = 0.f;
-            for (int c0 = chh * 32; c0 < H; c0 += 64) {
+            for (int c0 = chh * 32; c0 < H; c0 += 32 * NCG) {
                 if (p.debug & 4) break;
                 float v[32];
                 tc::tmem_ld32(dcol + c0, v);
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_fwd_tc_kernel(TcParams p) 
                     for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 }
             }
-            sdfs[((tp & 1) * 2 + chh) * TM + row] = psum;
+            sdfs[((tp & 1) * NCG + chh) * TM + row] = psum;
             tc::fence_before_sync();
         }
         // ---- wait for the MMAs of tile t, then gather tile t+1 into the (now free) A buffer ---------------
@@ -241,15 +242,23 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_fwd_tc_kernel(TcParams p) 
         if (t > 0 && tid < spt) {
             const int64_t tp = t - 1;
             const int64_t n = (blockIdx.x + tp * gridDim.x) * spt + tid;
-            const float* sp = &sdfs[(tp & 1) * 2 * TM + tid * nq];
+            const float* sp = &sdfs[(tp & 1) * NCG * TM + tid * nq];
             if (n < p.n) {
                 const float b1 = __ldg(p.b1);
                 if (nq == 1) {
-                    p.sdf1[n] = sp[0] + sp[TM] + b1;
+                    float v = b1;
+#pragma unroll
+                    for (int g = 0; g < NCG; ++g) v += sp[g * TM];
+                    p.sdf1[n] = v;
                 } else {
                     float sd[NQ7];
 #pragma unroll
-                    for (int r = 0; r < NQ7; ++r) { sd[r] = sp[r] + sp[TM + r] + b1; p.sdf7[n * NQ7 + r] = sd[r]; }
+                    for (int r = 0; r < NQ7; ++r) {
+                        float v = b1;
+#pragma unroll
+                        for (int g = 0; g < NCG; ++g) v += sp[g * TM + r];
+                        sd[r] = v; p.sdf7[n * NQ7 + r] = v;
+                    }
                     float g[3], h[3];
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
@@ -270,7 +279,7 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_fwd_tc_kernel(TcParams p) 
 }  // namespace
 
 size_t tf_internal_tc_fwd_smem(int KT, int H) {
-    return (size_t)2 * 16 * (KT / 4) * site::A_LBO + (size_t)NST * 2 * H * KSL * 4 + (size_t)2 * H * 4 + (size_t)4 * TM * 4 + (2 * NST + 2) * 8 + 16;
+    return (size_t)2 * 16 * (KT / 4) * site::A_LBO + (size_t)NST * 2 * H * KSL * 4 + (size_t)2 * H * 4 + (size_t)2 * NCG * TM * 4 + (2 * NST + 2) * 8 + 16;
 }
 
 // workspace floats needed in front of spc: the pre-tiled W0
