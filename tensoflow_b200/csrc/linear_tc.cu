@@ -192,11 +192,13 @@ __global__ void __launch_bounds__(NTH, 1) linear_tc_kernel(const float* __restri
             tc::mbar_wait(&wfull[st], (uint32_t)((g / NSTG) & 1));
             tc::fence_after_sync();
             const uint32_t d = tmem_base + (uint32_t)(t & 1) * 256;
-            const uint32_t xh = tc::smem_u32(x_hi), xl = tc::smem_u32(x_lo), wh = tc::smem_u32(w_hi), wl = wh + w_part;
+            const uint32_t wh = tc::smem_u32(w_hi);
+            const uint64_t xdh = tc::make_smem_desc(tc::smem_u32(x_hi), X_LBO, X_SBO), xdl = tc::make_smem_desc(tc::smem_u32(x_lo), X_LBO, X_SBO);
+            const uint64_t wdh0 = tc::make_smem_desc(wh, 128, w_sbo), wdl0 = tc::make_smem_desc(wh + w_part, 128, w_sbo);
 #pragma unroll
             for (int ks = 0; ks < KC / 8; ++ks) {
-                const uint64_t adh = tc::make_smem_desc(xh + ks * 2 * X_LBO, X_LBO, X_SBO), adl = tc::make_smem_desc(xl + ks * 2 * X_LBO, X_LBO, X_SBO);
-                const uint64_t wdh = tc::make_smem_desc(wh + ks * 256, 128, w_sbo), wdl = tc::make_smem_desc(wl + ks * 256, 128, w_sbo);
+                const uint64_t adh = tc::desc_add(xdh, ks * 2 * X_LBO), adl = tc::desc_add(xdl, ks * 2 * X_LBO);
+                const uint64_t wdh = tc::desc_add(wdh0, ks * 256), wdl = tc::desc_add(wdl0, ks * 256);
                 tc::mma_tf32_ss(d, adh, wdh, idesc, (kc | ks) != 0);
                 tc::mma_tf32_ss(d, adh, wdl, idesc, 1);
                 tc::mma_tf32_ss(d, adl, wdh, idesc, 1);

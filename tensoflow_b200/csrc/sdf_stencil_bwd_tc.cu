@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_bwd_tc_kernel(TcBwdParams 
     const uint32_t d1 = tmem_base, d2 = tmem_base + 256;
     const uint32_t idesc1 = tc::make_idesc(2, 2, TM, H), idesc2 = tc::make_idesc(2, 2, TM, KT);
     const uint32_t a_sbo = site::a_sbo(KT), a_kstep = 2 * site::A_LBO, w_sbo = (KSL / 4) * 128, c_sbo = (HCH / 4) * 128;
+    const uint64_t a_desc_hi = tc::make_smem_desc(tc::smem_u32(a_hi), site::A_LBO, a_sbo), a_desc_lo = tc::make_smem_desc(tc::smem_u32(a_lo), site::A_LBO, a_sbo);
 
     int64_t g_issue = 0, g_mma = 0;            // driver state: ring slot counters
     const int64_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -209,12 +210,13 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_bwd_tc_kernel(TcBwdParams 
                 const int st = (int)(g_mma % NST);
                 tc::mbar_wait(&full[st], (uint32_t)((g_mma / NST) & 1));
                 tc::fence_after_sync();
-                const uint32_t w_hi = tc::smem_u32(wst + (size_t)st * slot_bytes), w_lo = w_hi + (uint32_t)H * KSL * 4;
-                const uint32_t ah = tc::smem_u32(a_hi) + s * (KSL / 8) * a_kstep, al = tc::smem_u32(a_lo) + s * (KSL / 8) * a_kstep;
+                const uint32_t w_hi = tc::smem_u32(wst + (size_t)st * slot_bytes);
+                const uint64_t wdh0 = tc::make_smem_desc(w_hi, 128, w_sbo), wdl0 = tc::make_smem_desc(w_hi + (uint32_t)H * KSL * 4, 128, w_sbo);
+                const uint64_t adh0 = tc::desc_add(a_desc_hi, s * (KSL / 8) * a_kstep), adl0 = tc::desc_add(a_desc_lo, s * (KSL / 8) * a_kstep);
 #pragma unroll
                 for (int ks = 0; ks < KSL / 8; ++ks) {
-                    const uint64_t adh = tc::make_smem_desc(ah + ks * a_kstep, site::A_LBO, a_sbo), adl = tc::make_smem_desc(al + ks * a_kstep, site::A_LBO, a_sbo);
-                    const uint64_t wdh = tc::make_smem_desc(w_hi + ks * 256, 128, w_sbo), wdl = tc::make_smem_desc(w_lo + ks * 256, 128, w_sbo);
+                    const uint64_t adh = tc::desc_add(adh0, ks * a_kstep), adl = tc::desc_add(adl0, ks * a_kstep);
+                    const uint64_t wdh = tc::desc_add(wdh0, ks * 256), wdl = tc::desc_add(wdl0, ks * 256);
                     tc::mma_tf32_ss(d1, adh, wdh, idesc1, (s | ks) != 0);
                     tc::mma_tf32_ss(d1, adh, wdl, idesc1, 1);
                     tc::mma_tf32_ss(d1, adl, wdh, idesc1, 1);
@@ -303,12 +305,13 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_bwd_tc_kernel(TcBwdParams 
                 const int st = (int)(g_mma % NST);
                 tc::mbar_wait(&full[st], (uint32_t)((g_mma / NST) & 1));
                 tc::fence_after_sync();
-                const uint32_t w_hi = tc::smem_u32(wst + (size_t)st * slot_bytes), w_lo = w_hi + (uint32_t)KT * HCH * 4;
-                const uint32_t ah = tc::smem_u32(ch_hi), al = tc::smem_u32(ch_lo);
+                const uint32_t w_hi = tc::smem_u32(wst + (size_t)st * slot_bytes);
+                const uint64_t wdh0 = tc::make_smem_desc(w_hi, 128, c_sbo), wdl0 = tc::make_smem_desc(w_hi + (uint32_t)KT * HCH * 4, 128, c_sbo);
+                const uint64_t adh0 = tc::make_smem_desc(tc::smem_u32(ch_hi), 128, c_sbo), adl0 = tc::make_smem_desc(tc::smem_u32(ch_lo), 128, c_sbo);
 #pragma unroll
                 for (int ks = 0; ks < HCH / 8; ++ks) {
-                    const uint64_t adh = tc::make_smem_desc(ah + ks * 256, 128, c_sbo), adl = tc::make_smem_desc(al + ks * 256, 128, c_sbo);
-                    const uint64_t wdh = tc::make_smem_desc(w_hi + ks * 256, 128, c_sbo), wdl = tc::make_smem_desc(w_lo + ks * 256, 128, c_sbo);
+                    const uint64_t adh = tc::desc_add(adh0, ks * 256), adl = tc::desc_add(adl0, ks * 256);
+                    const uint64_t wdh = tc::desc_add(wdh0, ks * 256), wdl = tc::desc_add(wdl0, ks * 256);
                     tc::mma_tf32_ss(d2, adh, wdh, idesc2, (c | ks) != 0);
                     tc::mma_tf32_ss(d2, adh, wdl, idesc2, 1);
                     tc::mma_tf32_ss(d2, adl, wdh, idesc2, 1);

@@ -157,6 +157,7 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_fwd_tc_kernel(TcParams p) 
     const uint32_t idesc = tc::make_idesc(2, 2, TM, H);
     const uint32_t a_sbo = site::a_sbo(KT), a_kstep = 2 * site::A_LBO;
     const uint32_t w_sbo = (KSL / 4) * 128;
+    const uint64_t a_desc_hi = tc::make_smem_desc(tc::smem_u32(a_hi), site::A_LBO, a_sbo), a_desc_lo = tc::make_smem_desc(tc::smem_u32(a_lo), site::A_LBO, a_sbo);
 
     int64_t g_issue = 0, g_mma = 0;                           // driver-thread state (W slice counters)
     const int64_t total_slices = my_tiles * S;
@@ -176,13 +177,14 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_fwd_tc_kernel(TcParams p) 
                 const int st = (int)(g_mma % NST);
                 tc::mbar_wait(&full[st], (uint32_t)((g_mma / NST) & 1));
                 tc::fence_after_sync();
-                const uint32_t w_hi = tc::smem_u32(wst + (size_t)st * 2 * w_part), w_lo = w_hi + w_part;
-                const uint32_t ah = tc::smem_u32(a_hi) + s * (KSL / 8) * a_kstep, al = tc::smem_u32(a_lo) + s * (KSL / 8) * a_kstep;
+                const uint32_t w_hi = tc::smem_u32(wst + (size_t)st * 2 * w_part);
+                const uint64_t wdh0 = tc::make_smem_desc(w_hi, 128, w_sbo), wdl0 = tc::make_smem_desc(w_hi + w_part, 128, w_sbo);
+                const uint64_t adh0 = tc::desc_add(a_desc_hi, s * (KSL / 8) * a_kstep), adl0 = tc::desc_add(a_desc_lo, s * (KSL / 8) * a_kstep);
 #pragma unroll
                 for (int ks = 0; ks < KSL / 8; ++ks) {
                     if (p.debug & 2) break;
-                    const uint64_t adh = tc::make_smem_desc(ah + ks * a_kstep, site::A_LBO, a_sbo), adl = tc::make_smem_desc(al + ks * a_kstep, site::A_LBO, a_sbo);
-                    const uint64_t wdh = tc::make_smem_desc(w_hi + ks * 256, 128, w_sbo), wdl = tc::make_smem_desc(w_lo + ks * 256, 128, w_sbo);
+                    const uint64_t adh = tc::desc_add(adh0, ks * a_kstep), adl = tc::desc_add(adl0, ks * a_kstep);
+                    const uint64_t wdh = tc::desc_add(wdh0, ks * 256), wdl = tc::desc_add(wdl0, ks * 256);
                     tc::mma_tf32_ss(dcol, adh, wdh, idesc, (s | ks) != 0);
                     tc::mma_tf32_ss(dcol, adh, wdl, idesc, 1);
                     tc::mma_tf32_ss(dcol, adl, wdh, idesc, 1);

@@ -21,6 +21,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
     return d;                                              // base_offset 0, lbo_mode 0, layout_type 0 (no swizzle)
 }
 
+// descriptor of the same tile `bytes` further on (start-address field only; addresses stay below 2^18)
+__device__ __forceinline__ uint64_t desc_add(uint64_t d, uint32_t bytes) { return d + (uint64_t)(bytes >> 4); }
+
 // ---- instruction descriptor: D fp32, A/B formats (0 f16, 1 bf16, 2 tf32), both K-major -----------
 __host__ __device__ constexpr uint32_t make_idesc(int a_fmt, int b_fmt, int M, int N) {
     return (1u << 4) | ((uint32_t)a_fmt << 7) | ((uint32_t)b_fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);

@@ -114,14 +114,17 @@ __global__ void __launch_bounds__(NTH, 1) xty_tc_kernel(const float* __restrict_
         __syncthreads();
         tc::fence_after_sync();
         if (tid == 0) {
-            const uint32_t xh = tc::smem_u32(xs_hi), xl = tc::smem_u32(xs_lo), yh = tc::smem_u32(ys_hi), yl = tc::smem_u32(ys_lo);
-#pragma unroll 1
+            // one descriptor per operand part and stage; the MMAs only advance its start address
+            const uint64_t xdh = tc::make_smem_desc(tc::smem_u32(xs_hi), 128, SBO), xdl = tc::make_smem_desc(tc::smem_u32(xs_lo), 128, SBO);
+            const uint64_t ydh = tc::make_smem_desc(tc::smem_u32(ys_hi), 128, SBO), ydl = tc::make_smem_desc(tc::smem_u32(ys_lo), 128, SBO);
+#pragma unroll
             for (int ks = 0; ks < RS / 8; ++ks) {
-                const uint64_t bdh = tc::make_smem_desc(yh + ks * 256, 128, SBO), bdl = tc::make_smem_desc(yl + ks * 256, 128, SBO);
-                for (int mt = 0; mt < MT; ++mt) {
+                const uint64_t bdh = tc::desc_add(ydh, ks * 256), bdl = tc::desc_add(ydl, ks * 256);
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    if (mt >= MT) break;
                     const uint32_t d = tmem_base + (uint32_t)mt * ncol_tile;
-                    const uint64_t adh = tc::make_smem_desc(xh + mt * 16 * SBO + ks * 256, 128, SBO);
-                    const uint64_t adl = tc::make_smem_desc(xl + mt * 16 * SBO + ks * 256, 128, SBO);
+                    const uint64_t adh = tc::desc_add(xdh, mt * 16 * SBO + ks * 256), adl = tc::desc_add(xdl, mt * 16 * SBO + ks * 256);
                     tc::mma_tf32_ss(d, adh, bdh, idesc, (it | ks) != 0);
                     tc::mma_tf32_ss(d, adh, bdl, idesc, 1);
                     tc::mma_tf32_ss(d, adl, bdh, idesc, 1);
