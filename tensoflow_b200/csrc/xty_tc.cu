@@ -28,35 +28,44 @@ __device__ __forceinline__ float4 lo4(float4 v, float4 h) {
 // 2 tasks per operand and stage.  The global loads of stage it+1 are issued into registers before stage it is
 // converted and stored, so HBM latency overlaps the staging and MMA work.
 struct Prefetch { float4 v[2][4]; };
+// per-thread staging plan of one operand (fixed for the whole kernel: only the row base advances)
+struct StagePlan { int src_off[2]; int row[2]; uint32_t smem_off[2]; bool on[2]; };
 
-__device__ __forceinline__ void stage_load(const float* __restrict__ src, int64_t r0, int64_t r_end, int W, Prefetch& pf) {
+__device__ __forceinline__ StagePlan make_stage_plan(int W) {
+    StagePlan p;
     const int G = W / 4, n_tasks = (RS / 4) * G;
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
         const int it = threadIdx.x + k * NTH;
         const int g = it % G, c = it / G;
+        p.on[k] = it < n_tasks;
+        p.row[k] = c * 4;
+        p.src_off[k] = c * 4 * W + g * 4;
+        const int w = g * 4;                              // first of the task's 4 columns (w & 7 is 0 or 4)
+        p.smem_off[k] = (uint32_t)(w >> 3) * SBO + c * 128 + (w & 7) * 16;
+    }
+    return p;
+}
+__device__ __forceinline__ void stage_load(const float* __restrict__ src, int64_t r0, int64_t r_end, int W, const StagePlan& sp, Prefetch& pf) {
+    const float* base = src + (size_t)r0 * W;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int64_t r = r0 + c * 4 + i;
-            pf.v[k][i] = (it < n_tasks && r < r_end) ? ldg4(src + (size_t)r * W + g * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+    for (int k = 0; k < 2; ++k) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            pf.v[k][i] = (sp.on[k] && r0 + sp.row[k] + i < r_end) ? ldg4(base + sp.src_off[k] + i * W) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
 // transpose the 4x4 blocks in registers (four 16-byte K-major units each), split into tf32 hi / lo, store
-__device__ __forceinline__ void stage_store(const Prefetch& pf, int W, uint8_t* hi, uint8_t* lo) {
-    const int G = W / 4, n_tasks = (RS / 4) * G;
+__device__ __forceinline__ void stage_store(const Prefetch& pf, const StagePlan& sp, uint8_t* hi, uint8_t* lo) {
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
-        const int it = threadIdx.x + k * NTH;
-        if (it >= n_tasks) continue;
-        const int g = it % G, c = it / G;
+        if (!sp.on[k]) continue;
         const float4* v = pf.v[k];
         const float4 t[4] = {make_float4(v[0].x, v[1].x, v[2].x, v[3].x), make_float4(v[0].y, v[1].y, v[2].y, v[3].y),
                              make_float4(v[0].z, v[1].z, v[2].z, v[3].z), make_float4(v[0].w, v[1].w, v[2].w, v[3].w)};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int w = g * 4 + j;
-            const uint32_t off = (uint32_t)(w >> 3) * SBO + c * 128 + (w & 7) * 16;
+            const uint32_t off = sp.smem_off[k] + j * 16;     // columns 4g..4g+3 stay inside one 8-row group
             const float4 h = hi4(t[j]);
             *reinterpret_cast<float4*>(hi + off) = h;
             *reinterpret_cast<float4*>(lo + off) = lo4(t[j], h);
@@ -94,8 +103,9 @@ __global__ void __launch_bounds__(NTH, 1) xty_tc_kernel(const float* __restrict_
 
     // register prefetch two stages ahead: sets (px0, py0) / (px1, py1) alternate
     Prefetch px0, py0, px1, py1;
-    if (n_stages > 0) { stage_load(X, r_begin, r_end, M, px0); stage_load(Y, r_begin, r_end, N, py0); }
-    if (n_stages > 1) { stage_load(X, r_begin + RS, r_end, M, px1); stage_load(Y, r_begin + RS, r_end, N, py1); }
+    const StagePlan spx = make_stage_plan(M), spy = make_stage_plan(N);
+    if (n_stages > 0) { stage_load(X, r_begin, r_end, M, spx, px0); stage_load(Y, r_begin, r_end, N, spy, py0); }
+    if (n_stages > 1) { stage_load(X, r_begin + RS, r_end, M, spx, px1); stage_load(Y, r_begin + RS, r_end, N, spy, py1); }
     auto do_stage = [&](int64_t it, Prefetch& px, Prefetch& py) {
         const int buf = (int)(it & 1);
         uint8_t* xs_hi = smem + (size_t)buf * stage_bytes;
@@ -103,11 +113,11 @@ __global__ void __launch_bounds__(NTH, 1) xty_tc_kernel(const float* __restrict_
         uint8_t* ys_hi = xs_lo + x_part;
         uint8_t* ys_lo = ys_hi + y_part;
         if (it >= 2) tc::mbar_wait(&empty[buf], (uint32_t)(((it >> 1) - 1) & 1));
-        stage_store(px, M, xs_hi, xs_lo);
-        stage_store(py, N, ys_hi, ys_lo);
+        stage_store(px, spx, xs_hi, xs_lo);
+        stage_store(py, spy, ys_hi, ys_lo);
         if (it + 2 < n_stages) {
             const int64_t r2 = r_begin + (it + 2) * RS;
-            stage_load(X, r2, r_end, M, px); stage_load(Y, r2, r_end, N, py);
+            stage_load(X, r2, r_end, M, spx, px); stage_load(Y, r2, r_end, N, spy, py);
         }
         tc::fence_async_smem();
         tc::fence_before_sync();
