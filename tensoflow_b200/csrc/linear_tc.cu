@@ -108,22 +108,28 @@ __global__ void __launch_bounds__(NTH, 1) linear_tc_kernel(const float* __restri
     const uint32_t w_part = (uint32_t)NP * KC * 4;
     const bool vec = (K % 4 == 0) && (((uintptr_t)X & 15) == 0) && (!BWD || ((((uintptr_t)Yact | (uintptr_t)dpre) & 15) == 0));
     const bool vec_out = (N % 4 == 0) && (((uintptr_t)Y & 15) == 0);
-    const uint32_t stage_bytes = 2 * X_PART + 2 * w_part;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)NSTG * stage_bytes);
-    uint64_t* wfull = bars;              // [NSTG] weight chunk landed
-    uint64_t* sfree = bars + NSTG;       // [NSTG] stage consumed by its MMAs
-    uint64_t* dfull = bars + 2 * NSTG;   // [2] accumulator complete
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTG + 2);
+    // shared memory: NSTG X stages (hi | lo) + 2 weight-chunk buffers (hi | lo); TMEM: one accumulator per tile of a group
+    uint8_t* wbuf0 = smem + (size_t)NSTG * 2 * X_PART;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wbuf0 + (size_t)2 * 2 * w_part);
+    uint64_t* wfull = bars;              // [2] weight chunk landed
+    uint64_t* wfree = bars + 2;          // [2] weight chunk consumed by the last MMA that reads it
+    uint64_t* sfree = bars + 4;          // [NSTG] X stage consumed by its MMAs
+    uint64_t* dfull = bars + 4 + NSTG;   // accumulators of the group complete
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 + NSTG);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nchunks = KP / KC;
+    const int cstride = NP <= 128 ? 128 : 256;         // TMEM columns per accumulator
+    const int G = 512 / cstride;                       // row tiles per group: they share every weight chunk
     const int64_t ntiles = (M + TM - 1) / TM;
     const int64_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const int64_t total = my_tiles * nchunks;          // pipeline steps of this CTA
+    const int64_t ngroups = (my_tiles + G - 1) / G;
+    const int64_t total_w = ngroups * nchunks;         // weight chunks this CTA streams
 
     if (warp == 0) tc::tmem_alloc<512>(tmem_slot);
     if (tid == 0) {
-        for (int i = 0; i < NSTG; ++i) { tc::mbar_init(&wfull[i], 1); tc::mbar_init(&sfree[i], 1); }
-        tc::mbar_init(&dfull[0], 1); tc::mbar_init(&dfull[1], 1);
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&wfull[i], 1); tc::mbar_init(&wfree[i], 1); }
+        for (int i = 0; i < NSTG; ++i) tc::mbar_init(&sfree[i], 1);
+        tc::mbar_init(dfull, 1);
         tc::mbar_fence_init();
     }
     tc::fence_before_sync();
@@ -133,66 +139,81 @@ __global__ void __launch_bounds__(NTH, 1) linear_tc_kernel(const float* __restri
     const uint32_t idesc = tc::make_idesc(2, 2, TM, NP);
     const uint32_t w_sbo = (KC / 4) * 128;
 
-    auto epilogue = [&](int64_t tp) {
-        const int64_t tile = blockIdx.x + tp * gridDim.x;
-        tc::mbar_wait(&dfull[tp & 1], (uint32_t)((tp >> 1) & 1));
-        tc::fence_after_sync();
+    auto epilogue = [&](int64_t local_tile, int j) {
+        const int64_t tile = blockIdx.x + local_tile * gridDim.x;
         const int lq = warp & 3, half = warp >> 2;
         const int64_t m = tile * TM + lq * 32 + lane;
-        const uint32_t d = tmem_base + (uint32_t)(tp & 1) * 256 + ((uint32_t)(lq * 32) << 16);
+        const uint32_t d = tmem_base + (uint32_t)j * cstride + ((uint32_t)(lq * 32) << 16);
         for (int c0 = half * 16; c0 < NP; c0 += 32) {
             float v[16];
             tc::tmem_ld16(d + c0, v);
             if (m < M) {
                 if (!BWD) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (c0 + j < N) v[j] = act_fwd(v[j] + (bias ? __ldg(bias + c0 + j) : 0.f), act, act_p);
+                    for (int jj = 0; jj < 16; ++jj)
+                        if (c0 + jj < N) v[jj] = act_fwd(v[jj] + (bias ? __ldg(bias + c0 + jj) : 0.f), act, act_p);
                 }
                 if (vec_out) {
                     float4* dst = reinterpret_cast<float4*>(Y + (size_t)m * N + c0);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (c0 + 4 * j < N) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    for (int jj = 0; jj < 4; ++jj)
+                        if (c0 + 4 * jj < N) dst[jj] = make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (c0 + j < N) Y[(size_t)m * N + c0 + j] = v[j];
+                    for (int jj = 0; jj < 16; ++jj)
+                        if (c0 + jj < N) Y[(size_t)m * N + c0 + jj] = v[jj];
                 }
             }
         }
-        tc::fence_before_sync();
     };
+    // weight chunk w of the CTA's stream -> buffer w & 1 (thread 0)
+    auto issue_w = [&](int64_t w) {
+        const int buf = (int)(w & 1);
+        if (w >= 2) tc::mbar_wait(&wfree[buf], (uint32_t)(((w >> 1) - 1) & 1));
+        mbar_expect_tx(&wfull[buf], 2 * w_part);
+        bulk_copy_g2s(wbuf0 + (size_t)buf * 2 * w_part, Wtc + (size_t)(w % nchunks) * 2 * NP * KC, 2 * w_part, &wfull[buf]);
+    };
+    if (tid == 0 && total_w > 0) issue_w(0);
 
-    XRegs xr;
-    if (total > 0) x_load<BWD>(X, Yact, dpre, act, act_p, vec, M, K, (int64_t)blockIdx.x * TM, 0, xr);
-    for (int64_t g = 0; g < total; ++g) {
-        const int64_t t = g / nchunks;
-        const int kc = (int)(g % nchunks);
-        const int st = (int)(g % NSTG);
-        uint8_t* x_hi = smem + (size_t)st * stage_bytes;
+    // step = (group, weight chunk, tile of the group); the X rows of a step are loaded into registers PF steps ahead
+    struct Step { int64_t grp; int kc, j; };
+    auto group_size = [&](int64_t grp) { return (int)(my_tiles - grp * G < G ? my_tiles - grp * G : G); };
+    auto advance = [&](Step& s) {
+        if (++s.j == group_size(s.grp)) { s.j = 0; if (++s.kc == nchunks) { s.kc = 0; ++s.grp; } }
+    };
+    auto load_step = [&](const Step& s, XRegs& r) {
+        if (s.grp < ngroups) x_load<BWD>(X, Yact, dpre, act, act_p, vec, M, K, (blockIdx.x + (s.grp * G + s.j) * gridDim.x) * TM, s.kc * KC, r);
+    };
+    constexpr int PF = 4;
+    XRegs xr[PF];
+    Step ahead = {0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < PF; ++i) { load_step(ahead, xr[i]); if (ahead.grp < ngroups) advance(ahead); }
+    Step cur = {0, 0, 0};
+    int64_t q = 0;                                     // X stage counter
+    auto do_step = [&](XRegs& r) {
+        const int64_t grp = cur.grp;
+        const int kc = cur.kc, j = cur.j, Gc = group_size(grp);
+        const int64_t w = grp * nchunks + kc;
+        const int st = (int)(q % NSTG);
+        uint8_t* x_hi = smem + (size_t)st * 2 * X_PART;
         uint8_t* x_lo = x_hi + X_PART;
-        uint8_t* w_hi = x_lo + X_PART;
-        // stage free? (its previous MMAs have completed)
-        if (g >= NSTG) tc::mbar_wait(&sfree[st], (uint32_t)(((g / NSTG) - 1) & 1));
-        if (tid == 0) {
-            mbar_expect_tx(&wfull[st], 2 * w_part);
-            bulk_copy_g2s(w_hi, Wtc + (size_t)kc * 2 * NP * KC, 2 * w_part, &wfull[st]);
-        }
-        x_store(xr, x_hi, x_lo);
-        if (g + 1 < total) {
-            const int64_t g1 = g + 1;
-            x_load<BWD>(X, Yact, dpre, act, act_p, vec, M, K, (blockIdx.x + (g1 / nchunks) * gridDim.x) * TM, (int)(g1 % nchunks) * KC, xr);
-        }
+        if (q >= NSTG) tc::mbar_wait(&sfree[st], (uint32_t)(((q / NSTG) - 1) & 1));
+        x_store(r, x_hi, x_lo);
+        load_step(ahead, r);
+        if (ahead.grp < ngroups) advance(ahead);
         tc::fence_async_smem();
         tc::fence_before_sync();
         __syncthreads();
         tc::fence_after_sync();
         if (tid == 0) {
-            tc::mbar_wait(&wfull[st], (uint32_t)((g / NSTG) & 1));
-            tc::fence_after_sync();
-            const uint32_t d = tmem_base + (uint32_t)(t & 1) * 256;
-            const uint32_t wh = tc::smem_u32(w_hi);
+            if (j == 0) {
+                if (w + 1 < total_w) issue_w(w + 1);
+                tc::mbar_wait(&wfull[w & 1], (uint32_t)((w >> 1) & 1));
+                tc::fence_after_sync();
+            }
+            const uint32_t d = tmem_base + (uint32_t)j * cstride;
+            const uint32_t wh = tc::smem_u32(wbuf0 + (size_t)(w & 1) * 2 * w_part);
             const uint64_t xdh = tc::make_smem_desc(tc::smem_u32(x_hi), X_LBO, X_SBO), xdl = tc::make_smem_desc(tc::smem_u32(x_lo), X_LBO, X_SBO);
             const uint64_t wdh0 = tc::make_smem_desc(wh, 128, w_sbo), wdl0 = tc::make_smem_desc(wh + w_part, 128, w_sbo);
 #pragma unroll
@@ -204,18 +225,32 @@ __global__ void __launch_bounds__(NTH, 1) linear_tc_kernel(const float* __restri
                 tc::mma_tf32_ss(d, adl, wdh, idesc, 1);
             }
             tc::mma_commit(&sfree[st]);
-            if (kc == nchunks - 1) tc::mma_commit(&dfull[t & 1]);
+            if (j == Gc - 1) {
+                tc::mma_commit(&wfree[w & 1]);
+                if (kc == nchunks - 1) tc::mma_commit(dfull);
+            }
         }
-        // epilogue of the previous tile once this tile's first chunk is in flight
-        if (kc == 0 && t > 0) epilogue(t - 1);
+        ++q;
+        if (j == Gc - 1 && kc == nchunks - 1) {
+            // the group's accumulators: bias + activation + store, then TMEM is free for the next group
+            tc::mbar_wait(dfull, (uint32_t)(grp & 1));
+            tc::fence_after_sync();
+            for (int jj = 0; jj < Gc; ++jj) epilogue(grp * G + jj, jj);
+            tc::fence_before_sync();
+        }
+        advance(cur);
+    };
+    while (cur.grp < ngroups) {
+#pragma unroll
+        for (int i = 0; i < PF; ++i)
+            if (cur.grp < ngroups) do_step(xr[i]);
     }
-    if (my_tiles > 0) epilogue(my_tiles - 1);
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc<512>(tmem_base);
 }
 
-size_t linear_tc_smem(int NP) { return (size_t)NSTG * (2 * X_PART + 2 * (size_t)NP * KC * 4) + (2 * NSTG + 2) * 8 + 16; }
+size_t linear_tc_smem(int NP) { return (size_t)NSTG * 2 * X_PART + (size_t)2 * 2 * NP * KC * 4 + (5 + NSTG) * 8 + 16; }
 int pad16(int n) { return (n + 15) / 16 * 16; }
 
 }  // namespace

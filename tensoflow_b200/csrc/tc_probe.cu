@@ -52,15 +52,16 @@ __global__ void __launch_bounds__(128, 1) tc_probe_kernel(const float* __restric
     if (tid == 0) {
         const uint32_t idesc = tc::make_idesc(2, 2, PM, N);
         const uint32_t sbo = (uint32_t)kch * 128, lbo = 128;
+        const uint64_t adh = tc::make_smem_desc(tc::smem_u32(a_hi), lbo, sbo), adl = tc::make_smem_desc(tc::smem_u32(a_lo), lbo, sbo);
+        const uint64_t bdh = tc::make_smem_desc(tc::smem_u32(b_hi), lbo, sbo), bdl = tc::make_smem_desc(tc::smem_u32(b_lo), lbo, sbo);
         for (int rep = 0; rep < repeat; ++rep) {
             uint32_t acc = 0;
             for (int p = 0; p < passes; ++p) {
-                const uint8_t* ap = (p == 2) ? a_lo : a_hi;       // pass 0: hi*hi, 1: hi*lo, 2: lo*hi
-                const uint8_t* bp = (p == 1) ? b_lo : b_hi;
+                const uint64_t ad0 = (p == 2) ? adl : adh;        // pass 0: hi*hi, 1: hi*lo, 2: lo*hi
+                const uint64_t bd0 = (p == 1) ? bdl : bdh;
+#pragma unroll 4
                 for (int ks = 0; ks < K / 8; ++ks) {
-                    const uint64_t ad = tc::make_smem_desc(tc::smem_u32(ap) + ks * 256, lbo, sbo);
-                    const uint64_t bd = tc::make_smem_desc(tc::smem_u32(bp) + ks * 256, lbo, sbo);
-                    tc::mma_tf32_ss(tmem_d, ad, bd, idesc, acc);
+                    tc::mma_tf32_ss(tmem_d, tc::desc_add(ad0, ks * 256), tc::desc_add(bd0, ks * 256), idesc, acc);
                     acc = 1;
                 }
             }

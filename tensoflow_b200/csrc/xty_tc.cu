@@ -73,17 +73,20 @@ __device__ __forceinline__ void stage_store(const Prefetch& pf, const StagePlan&
     }
 }
 
-__global__ void __launch_bounds__(NTH, 1) xty_tc_kernel(const float* __restrict__ X, const float* __restrict__ Y, int64_t rows, int M, int N,
-                                                        float* __restrict__ out, int ldo, int n_valid, int64_t rows_per_cta) {
+// D[i][j] = sum_r X[r][i] Y[r][j]: X (width M, a multiple of 4; padded to MP = 128 or 256 MMA rows) is the MMA M side,
+// Y (width N, a multiple of 16) the MMA N side.  An SS-mode tf32 MMA costs ~130 cycles whatever its N (the 4 KB A-operand
+// read), so the host puts the wider operand on the N side; `tr` then writes the result transposed.
+__global__ void __launch_bounds__(NTH, 1) xty_tc_kernel(const float* __restrict__ X, const float* __restrict__ Y, int64_t rows, int M, int MP, int N,
+                                                        float* __restrict__ out, int ldo, int x_valid, int y_valid, int tr, int64_t rows_per_cta) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const uint32_t x_part = (uint32_t)(M / 8) * SBO, y_part = (uint32_t)(N / 8) * SBO;
+    const uint32_t x_part = (uint32_t)(MP / 8) * SBO, y_part = (uint32_t)(N / 8) * SBO;
     const uint32_t stage_bytes = 2 * (x_part + y_part);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * stage_bytes);
     uint64_t* empty = bars;          // [2]
     uint64_t* done = bars + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int MT = M / 128;
+    const int MT = MP / 128;
     const int ncol_tile = N <= 128 ? 128 : 256;      // TMEM column stride between the M tiles
 
     if (warp == 0) tc::tmem_alloc<512>(tmem_slot);
@@ -159,7 +162,8 @@ __global__ void __launch_bounds__(NTH, 1) xty_tc_kernel(const float* __restrict_
                 tc::tmem_ld16(tmem_base + (uint32_t)mt * ncol_tile + ((uint32_t)(lq * 32) << 16) + c0, v);
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
-                    if (c0 + j < n_valid && v[j] != 0.f) atomicAdd(out + (size_t)m * ldo + c0 + j, v[j]);
+                    if (m < x_valid && c0 + j < y_valid && v[j] != 0.f)
+                        atomicAdd(tr ? out + (size_t)(c0 + j) * ldo + m : out + (size_t)m * ldo + c0 + j, v[j]);
             }
         }
     }
@@ -168,22 +172,29 @@ __global__ void __launch_bounds__(NTH, 1) xty_tc_kernel(const float* __restrict_
     if (warp == 0) tc::tmem_dealloc<512>(tmem_base);
 }
 
-size_t xty_tc_smem(int M, int N) { return (size_t)2 * 2 * ((M / 8) + (N / 8)) * SBO + 64; }
+size_t xty_tc_smem(int MP, int N) { return (size_t)2 * 2 * ((MP / 8) + (N / 8)) * SBO + 64; }
 
 }  // namespace
 
 // true when the shapes suit the tensor-core kernel (otherwise callers use the SIMT X^T Y kernel)
 bool tf_internal_xty_tc_ok(const float* X, const float* Y, int M, int N) {
-    if (M % 128 != 0 || M > 256 || N % 16 != 0 || N < 16 || N > 256) return false;
-    if ((M / 128) * (N <= 128 ? 128 : 256) > 512) return false;
+    if (M % 16 != 0 || N % 16 != 0 || M < 16 || N < 16 || M > 256 || N > 256) return false;
     if (((uintptr_t)X & 15) || ((uintptr_t)Y & 15)) return false;
-    return xty_tc_smem(M, N) <= 227 * 1024;
+    const int mw = M > N ? N : M, nw = M > N ? M : N;
+    return xty_tc_smem((mw + 127) / 128 * 128, nw) <= 227 * 1024;
 }
 
 // X [rows][M] (ld = M), Y [rows][N] (ld = N); out[m][n] (ld = ldo) += X^T Y for n < n_valid
 int tf_internal_xty_tc(const float* X, const float* Y, int64_t rows, int M, int N, float* out, int ldo, int n_valid, cudaStream_t stream) {
     if (rows == 0) return 0;
-    const size_t smem = xty_tc_smem(M, N);
+    // MMA N side = the wider operand; the M side is padded to whole 128-row MMAs (its extra rows are never read back)
+    const bool tr = M > N;
+    const float* xs = tr ? Y : X;
+    const float* ys = tr ? X : Y;
+    const int mw = tr ? N : M, nw = tr ? M : N;
+    const int mp = (mw + 127) / 128 * 128;
+    const int x_valid = tr ? n_valid : M, y_valid = tr ? M : n_valid;
+    const size_t smem = xty_tc_smem(mp, nw);
     cudaFuncSetAttribute(xty_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int64_t grid = (rows + 4 * RS - 1) / (4 * RS);
     if (grid > tf_num_sms()) grid = tf_num_sms();
@@ -192,7 +203,7 @@ int tf_internal_xty_tc(const float* X, const float* Y, int64_t rows, int M, int 
     grid = (rows + rpc - 1) / rpc;
     {
         TfKernelTimer timer("xty_tc", stream);
-        xty_tc_kernel<<<(int)grid, NTH, smem, stream>>>(X, Y, rows, M, N, out, ldo, n_valid, rpc);
+        xty_tc_kernel<<<(int)grid, NTH, smem, stream>>>(xs, ys, rows, mw, mp, nw, out, ldo, x_valid, y_valid, tr ? 1 : 0, rpc);
     }
     tf_count_launches(1);
     return 0;
