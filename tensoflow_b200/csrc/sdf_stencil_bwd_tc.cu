@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_bwd_tc_kernel(TcBwdParams 
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t d1 = tmem_base, d2 = tmem_base + 256;
+    const uint32_t d1 = tmem_base, d2 = tmem_base + 256, chunk_a = tmem_base + 384;   // chunk_a: 2 x (hi 32 | lo 32) columns
     const uint32_t idesc1 = tc::make_idesc(2, 2, TM, H), idesc2 = tc::make_idesc(2, 2, TM, KT);
     const uint32_t a_sbo = site::a_sbo(KT), a_kstep = 2 * site::A_LBO, w_sbo = (KSL / 4) * 128, c_sbo = (HCH / 4) * 128;
     const uint64_t a_desc_hi = tc::make_smem_desc(tc::smem_u32(a_hi), site::A_LBO, a_sbo), a_desc_lo = tc::make_smem_desc(tc::smem_u32(a_lo), site::A_LBO, a_sbo);
@@ -243,9 +243,7 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_bwd_tc_kernel(TcBwdParams 
         const float gq = gqs[row];
         for (int c = 0; c < ((p.debug & 16) ? 0 : NCH); ++c) {
             const int buf = c & 1;
-            uint8_t* ch_hi = smem + (size_t)buf * 2 * c_part;
-            uint8_t* ch_lo = ch_hi + c_part;
-            if (c >= 2) tc::mbar_wait(&cfree[buf], (cf_commits[buf] - 1) & 1);
+            if (c >= 2) { tc::mbar_wait(&cfree[buf], (cf_commits[buf] - 1) & 1); tc::fence_after_sync(); }
             const int col0 = c * HCH + half * 16;
             float v[16];
             tc::tmem_ld16(d1 + ((uint32_t)(lq * 32) << 16) + col0, v);
@@ -265,13 +263,16 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_bwd_tc_kernel(TcBwdParams 
             }
             float4* dst = reinterpret_cast<float4*>(p.dpre + (size_t)(tile_row0 + row) * H + col0);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float4 d4 = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                if (!(p.debug & 2)) dst[j] = d4;
-                const float4 hi = site::tf32_hi(d4);
-                const uint32_t off = tc::tile_off_b32(row, half * 16 + 4 * j, HCH / 4);
-                *reinterpret_cast<float4*>(ch_hi + off) = hi;
-                *reinterpret_cast<float4*>(ch_lo + off) = site::tf32_lo(d4, hi);
+            for (int j = 0; j < 4; ++j)
+                if (!(p.debug & 2)) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            {   // the chunk becomes the A operand of the dA MMAs straight in tensor memory (tf32 hi | lo, lane = row)
+                float lo[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { const float h = tc::tf32_rn(v[j]); lo[j] = tc::tf32_rn(v[j] - h); v[j] = h; }
+                const uint32_t ca = chunk_a + (uint32_t)buf * 64 + ((uint32_t)(lq * 32) << 16) + half * 16;
+                tc::tmem_st16(ca, v);
+                tc::tmem_st16(ca + 32, lo);
+                tc::tmem_st_wait();
             }
             if (centre && p.spc) {
                 float4* sdst = reinterpret_cast<float4*>(p.spc + (size_t)n * H + col0);
@@ -307,14 +308,13 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_bwd_tc_kernel(TcBwdParams 
                 tc::fence_after_sync();
                 const uint32_t w_hi = tc::smem_u32(wst + (size_t)st * slot_bytes);
                 const uint64_t wdh0 = tc::make_smem_desc(w_hi, 128, c_sbo), wdl0 = tc::make_smem_desc(w_hi + (uint32_t)KT * HCH * 4, 128, c_sbo);
-                const uint64_t adh0 = tc::make_smem_desc(tc::smem_u32(ch_hi), 128, c_sbo), adl0 = tc::make_smem_desc(tc::smem_u32(ch_lo), 128, c_sbo);
+                const uint32_t ah = chunk_a + (uint32_t)buf * 64, al = ah + 32;
 #pragma unroll
                 for (int ks = 0; ks < HCH / 8; ++ks) {
-                    const uint64_t adh = tc::desc_add(adh0, ks * 256), adl = tc::desc_add(adl0, ks * 256);
                     const uint64_t wdh = tc::desc_add(wdh0, ks * 256), wdl = tc::desc_add(wdl0, ks * 256);
-                    tc::mma_tf32_ss(d2, adh, wdh, idesc2, (c | ks) != 0);
-                    tc::mma_tf32_ss(d2, adh, wdl, idesc2, 1);
-                    tc::mma_tf32_ss(d2, adl, wdh, idesc2, 1);
+                    tc::mma_tf32_ts(d2, ah + ks * 8, wdh, idesc2, (c | ks) != 0);
+                    tc::mma_tf32_ts(d2, ah + ks * 8, wdl, idesc2, 1);
+                    tc::mma_tf32_ts(d2, al + ks * 8, wdh, idesc2, 1);
                 }
                 tc::mma_commit(&empty[st]);
                 tc::mma_commit(&cfree[buf]);
