@@ -1,17 +1,17 @@
 // Fused TensoSDF stencil backward (activation side) on the 5th-gen tensor cores, sm_100a.
 //
-// Per MMA tile (128 rows = 18 samples x 7 stencil queries, sample-major so that the queries of a sample share
-// their plane / line fetches and their scatter reductions, stencil_site.cuh):
-//   gather     : features -> A operand (tf32 hi/lo, canonical K-major layout) + fp32 copy to the
-//                workspace (`arow`, with a constant-1 column so that dPre^T [A|1] yields dW0 and db0)
-//   GEMM1      : pre = A W0^T on tcgen05 (3xTF32), accumulator D1 [128 x H] in TMEM
-//   epilogue-1 : per 32-column chunk: Softplus / sigmoid, dPost = gq * W1[0,:] (+ g_feat W1[1:,:] for the
-//                centre tile, precomputed), dPre = dPost * sigmoid -> workspace + shared memory (hi/lo)
-//   GEMM-dA    : dA += dPre[:,chunk] W0[chunk,:] on tcgen05, accumulator D2 [128 x KT] in TMEM,
-//                chunk by chunk behind epilogue-1 (double-buffered operand)
-//   scatter    : dA -> shared memory -> d plane / d line with vector reductions
-// Weight slices (W0 by K-slices for GEMM1, W0^T by hidden chunks for GEMM-dA) stream through one
-// 3-stage cp.async.bulk ring.  Weight gradients are finished by X^T Y passes over the workspace.
+// One persistent CTA per SM, 16 warps in two groups that work on different tiles at the same time
+// (MMA tile = 128 rows = 18 samples x 7 stencil queries, sample-major: stencil_site.cuh):
+//   memory group (8 warps, LSU-bound): gather of tile t+1 (features -> A operand hi/lo in shared memory + fp32 rows
+//       to the workspace) and shared-stencil scatter of tile t-1 (dA in shared memory -> RED.v4 into plane / line grads)
+//   math group (8 warps, ALU-bound) on tile t: GEMM1 pre = A W0^T (3xTF32, accumulator D1 in TMEM), then per
+//       32-column hidden chunk: tcgen05.ld -> Softplus / sigmoid -> dPre = (gq W1[0,:] + [centre] g_feat W1[1:]) * sigmoid
+//       -> workspace + TENSOR MEMORY (tcgen05.st, tf32 hi | lo), which the driver thread turns into
+//       dA += dPre[:,chunk] W0[chunk,:] MMAs with the A operand read from TMEM (no shared-memory round trip and no
+//       4 KB A read per instruction), accumulator D2; finally D2 -> shared memory for the memory group
+// Hand-offs are mbarriers (A ready / GEMM1 done / dA ready / dA consumed); weight slices (W0 by 8 features for GEMM1,
+// W0^T by 16 hidden units for GEMM-dA) stream through one cp.async.bulk ring.  Weight gradients are finished by
+// X^T Y passes over the workspace (xty_tc.cu).
 #include <stdlib.h>
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -21,10 +21,13 @@ namespace {
 
 constexpr int TM = 128;
 constexpr int NQ7 = 7;
-constexpr int KSL = 16;     // K slice of GEMM1
+constexpr int KSL = 16;     // KT granularity (shared with the forward kernel)
+constexpr int KS1 = 8;      // K slice of GEMM1 streamed per ring slot
+constexpr int HHC = 16;     // hidden units of a W0^T ring slot (half a chunk)
 constexpr int HCH = 32;     // hidden chunk of epilogue-1 / GEMM-dA
 constexpr int NST = 2;
-constexpr int NTH = 256;
+constexpr int NGRP = 256;             // threads per group
+constexpr int NTH = 2 * NGRP;         // math group (warps 0-7) + memory group (warps 8-15)
 
 struct TcBwdParams {
     tf_vm_field_t f;
@@ -45,29 +48,29 @@ struct TcBwdParams {
                              // 4 no scatter, 8 no dW1 reduction, 16 no chunk loop
 };
 
-// slots 0..S-1   : W0 K-slices   [H rows x 16]  hi | lo   (GEMM1 B operand)
-// slots S..S+NCH : W0^T chunks   [KT rows x 32] hi | lo   (GEMM-dA B operand: B[n = feature][k = hidden])
+// slots 0..S-1        : W0 K-slices      [H rows x 8]   hi | lo   (GEMM1 B operand)
+// slots S..S+2*NCH-1   : W0^T half-chunks [KT rows x 16] hi | lo   (GEMM-dA B operand: B[n = feature][k = hidden])
 __global__ void tc_prep_bwd_kernel(const float* __restrict__ W0, int K, int KT, int H, int slot_floats, float* __restrict__ Wtc) {
-    const int S = KT / KSL, NCH = H / HCH;
+    const int S = KT / KS1, NHC = H / HHC;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-    for (int i = tid; i < S * H * KSL; i += nth) {
-        const int kl = i % KSL, h = (i / KSL) % H, s = i / (KSL * H);
-        const int k = s * KSL + kl;
+    for (int i = tid; i < S * H * KS1; i += nth) {
+        const int kl = i % KS1, h = (i / KS1) % H, s = i / (KS1 * H);
+        const int k = s * KS1 + kl;
         const float v = k < K ? W0[(size_t)h * K + k] : 0.f;
         const float hi = tc::tf32_rn(v);
         float* base = Wtc + (size_t)s * slot_floats;
-        const uint32_t off = tc::tile_off_b32(h, kl, KSL / 4) / 4;
+        const uint32_t off = tc::tile_off_b32(h, kl, KS1 / 4) / 4;
         base[off] = hi;
-        base[(size_t)H * KSL + off] = tc::tf32_rn(v - hi);
+        base[(size_t)H * KS1 + off] = tc::tf32_rn(v - hi);
     }
-    for (int i = tid; i < NCH * KT * HCH; i += nth) {
-        const int kk = i % HCH, kf = (i / HCH) % KT, c = i / (HCH * KT);
-        const float v = kf < K ? W0[(size_t)(c * HCH + kk) * K + kf] : 0.f;
+    for (int i = tid; i < NHC * KT * HHC; i += nth) {
+        const int kk = i % HHC, kf = (i / HHC) % KT, c = i / (HHC * KT);
+        const float v = kf < K ? W0[(size_t)(c * HHC + kk) * K + kf] : 0.f;
         const float hi = tc::tf32_rn(v);
         float* base = Wtc + (size_t)(S + c) * slot_floats;
-        const uint32_t off = tc::tile_off_b32(kf, kk, HCH / 4) / 4;
+        const uint32_t off = tc::tile_off_b32(kf, kk, HHC / 4) / 4;
         base[off] = hi;
-        base[(size_t)KT * HCH + off] = tc::tf32_rn(v - hi);
+        base[(size_t)KT * HHC + off] = tc::tf32_rn(v - hi);
     }
 }
 
@@ -92,15 +95,15 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 
 __global__ void __launch_bounds__(NTH, 1) sdf_stencil_bwd_tc_kernel(TcBwdParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const int H = p.H, KT = p.KT, S = KT / KSL, NCH = H / HCH, J = S + NCH;
+    const int H = p.H, KT = p.KT, S = KT / KS1, NCH = H / HCH, J = S + 2 * NCH;
     constexpr int SPT = site::SPT;
     const uint32_t a_part = site::a_part_bytes(KT);
     const uint32_t slot_bytes = (uint32_t)p.slot_floats * 4;
-    const uint32_t c_part = (uint32_t)TM * HCH * 4;                // one dPre chunk part (16 KB)
     const int DAS = KT + 4;                                        // row stride of the dA tile
     uint8_t* a_hi = smem;
     uint8_t* a_lo = a_hi + a_part;
-    uint8_t* wst = a_lo + a_part;
+    float* dAs = reinterpret_cast<float*>(a_lo + a_part);          // [TM][DAS] fp32, math group -> memory group
+    uint8_t* wst = reinterpret_cast<uint8_t*>(dAs + (size_t)TM * DAS);
     float* b0s = reinterpret_cast<float*>(wst + (size_t)NST * slot_bytes);
     float* w1s = b0s + H;
     float* accw1 = w1s + H;                                        // per-CTA dW1[0,:]
@@ -108,23 +111,24 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_bwd_tc_kernel(TcBwdParams 
     uint64_t* bars = reinterpret_cast<uint64_t*>(gqs + TM);
     uint64_t* full = bars;
     uint64_t* empty = bars + NST;
-    uint64_t* dfull1 = bars + 2 * NST;
-    uint64_t* dfull2 = dfull1 + 1;
-    uint64_t* cfree = dfull2 + 1;                                  // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cfree + 2);
+    uint64_t* dfull1 = bars + 2 * NST;                             // GEMM1 accumulator complete (= A operand consumed)
+    uint64_t* dfull2 = dfull1 + 1;                                 // dA accumulator complete
+    uint64_t* cfree = dfull2 + 1;                                  // [2] dPre chunk (TMEM) consumed by its MMAs
+    uint64_t* aready = cfree + 2;                                  // A operand of the next tile gathered
+    uint64_t* daready = aready + 1;                                // dA tile in shared memory
+    uint64_t* dafree = daready + 1;                                // dA tile scattered
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dafree + 1);
     float* accb1 = reinterpret_cast<float*>(tmem_slot + 1);
-    float* dAs = reinterpret_cast<float*>(smem);                   // aliases the A region after the MMAs
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int lq = warp & 3, half = warp >> 2;
-    const int row = lq * 32 + lane;
-    const int row_s = row / NQ7, row_q = row - row_s * NQ7;
     const int64_t ntiles = (p.n + SPT - 1) / SPT;
+    const int64_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
     if (warp == 0) tc::tmem_alloc<512>(tmem_slot);
     if (tid == 0) {
         for (int i = 0; i < NST; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
         tc::mbar_init(dfull1, 1); tc::mbar_init(dfull2, 1); tc::mbar_init(&cfree[0], 1); tc::mbar_init(&cfree[1], 1);
+        tc::mbar_init(aready, NGRP); tc::mbar_init(daready, NGRP); tc::mbar_init(dafree, NGRP);
         tc::mbar_fence_init();
         *accb1 = 0.f;
     }
@@ -133,213 +137,249 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_bwd_tc_kernel(TcBwdParams 
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t d1 = tmem_base, d2 = tmem_base + 256, chunk_a = tmem_base + 384;   // chunk_a: 2 x (hi 32 | lo 32) columns
-    const uint32_t idesc1 = tc::make_idesc(2, 2, TM, H), idesc2 = tc::make_idesc(2, 2, TM, KT);
-    const uint32_t a_sbo = site::a_sbo(KT), a_kstep = 2 * site::A_LBO, w_sbo = (KSL / 4) * 128, c_sbo = (HCH / 4) * 128;
-    const uint64_t a_desc_hi = tc::make_smem_desc(tc::smem_u32(a_hi), site::A_LBO, a_sbo), a_desc_lo = tc::make_smem_desc(tc::smem_u32(a_lo), site::A_LBO, a_sbo);
 
-    int64_t g_issue = 0, g_mma = 0;            // driver state: ring slot counters
-    const int64_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const int64_t total_slots = my_tiles * J;
-    uint32_t cf_commits[2] = {0, 0};           // commits issued on cfree[buf] so far
-
-    auto ring_prefetch = [&]() {
-        while (g_issue < total_slots && g_issue < g_mma + NST) {
-            const int st = (int)(g_issue % NST);
-            tc::mbar_wait(&empty[st], (uint32_t)(((g_issue / NST) & 1) ^ 1));
-            mbar_expect_tx(&full[st], slot_bytes);
-            bulk_copy_g2s(wst + (size_t)st * slot_bytes, p.Wtc + (size_t)(g_issue % J) * p.slot_floats, slot_bytes, &full[st]);
-            ++g_issue;
-        }
-    };
-
-    for (int64_t lt = 0; lt < my_tiles; ++lt) {
-        const int64_t tile = blockIdx.x + lt * gridDim.x;
-        const int64_t s_base = tile * SPT;
-        const int64_t tile_row0 = tile * TM;
-        const uint32_t tpar = (uint32_t)(lt & 1);
-        // upstream gradients -> per-query SDF gradients of the tile's samples (adjoint of fields.py:245-256)
-        if (tid < SPT) {
-            const int64_t n = s_base + tid;
-            float gq[NQ7];
-#pragma unroll
-            for (int r = 0; r < NQ7; ++r) gq[r] = 0.f;
-            if (n < p.n) {
-                float sd[NQ7];
-#pragma unroll
-                for (int r = 0; r < NQ7; ++r) sd[r] = p.sdf7[n * NQ7 + r];
-                float g[3], h[3];
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const float e = p.units[k];
-                    g[k] = (sd[1 + 2 * k] - sd[2 + 2 * k]) / (2.f * e);
-                    h[k] = (sd[1 + 2 * k] + sd[2 + 2 * k] - 2.f * sd[0]) / (e * e);
-                }
-                const float D = g[0] * g[0] + g[1] * g[1] + g[2] * g[2] + 1e-5f;
-                const float nh = (g[0] * h[0] + g[1] * h[1] + g[2] * h[2]) / D;
-                const float gh = p.g_hess ? p.g_hess[n] : 0.f;
-                gq[0] = p.g_sdf ? p.g_sdf[n] : 0.f;
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const float e = p.units[k];
-                    const float Gk = (p.g_grad ? p.g_grad[n * 3 + k] : 0.f) + gh * (h[k] / D - 2.f * g[k] * nh / D);
-                    const float Hk = gh * g[k] / D;
-                    gq[1 + 2 * k] = Gk / (2.f * e) + Hk / (e * e);
-                    gq[2 + 2 * k] = -Gk / (2.f * e) + Hk / (e * e);
-                    gq[0] -= 2.f * Hk / (e * e);
-                }
+    if (tid >= NGRP) {
+        // ======================= memory group: gather tile t+1, scatter tile t-1 ========================================
+        // the batched texel fetches want registers, the math group needs few: rebalance the 64K register file
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 160;");
+        const int mtid = tid - NGRP;
+        for (int64_t lt = 0; lt < my_tiles; ++lt) {
+            const int64_t tile = blockIdx.x + lt * gridDim.x;
+            if (lt > 0) tc::mbar_wait(dfull1, (uint32_t)((lt - 1) & 1));       // GEMM1 of the previous tile has consumed A
+            if (!(p.debug & 1))
+                site::gather_tile_lean(p.f, p.xyz, p.level, p.n, p.units, tile * SPT, KT, a_hi, a_lo,
+                                  (p.debug & 2) ? nullptr : p.arow + (size_t)tile * TM * KT, NGRP, mtid);
+            tc::fence_async_smem();
+            tc::mbar_arrive(aready);
+            if (lt > 0) {
+                tc::mbar_wait(daready, (uint32_t)((lt - 1) & 1));
+                if (!(p.debug & 4))
+                    site::scatter_tile_lean(p.f, p.g, p.xyz, p.level, p.n, p.units, (blockIdx.x + (lt - 1) * gridDim.x) * SPT, dAs, DAS, NGRP, mtid);
+                tc::mbar_arrive(dafree);
             }
-            float tot = 0.f;
-#pragma unroll
-            for (int r = 0; r < NQ7; ++r) { gqs[tid * NQ7 + r] = gq[r]; tot += gq[r]; }
-            if (tot != 0.f) atomicAdd(accb1, tot);
-        } else if (tid < SPT + 2) {
-            gqs[SPT * NQ7 + tid - SPT] = 0.f;
         }
-        // ---- gather -----------------------------------------------------------------------------
-        if (!(p.debug & 1))
-            site::gather_tile(p.f, p.xyz, p.level, p.n, p.units, s_base, KT, a_hi, a_lo, (p.debug & 2) ? nullptr : p.arow + (size_t)tile_row0 * KT, NTH);
-        tc::fence_async_smem();
-        tc::fence_before_sync();
-        __syncthreads();
-        tc::fence_after_sync();
-        // ---- GEMM1 -------------------------------------------------------------------------------
-        if (tid == 0) {
-            for (int s = 0; s < S; ++s) {
-                ring_prefetch();
-                const int st = (int)(g_mma % NST);
-                tc::mbar_wait(&full[st], (uint32_t)((g_mma / NST) & 1));
-                tc::fence_after_sync();
-                const uint32_t w_hi = tc::smem_u32(wst + (size_t)st * slot_bytes);
-                const uint64_t wdh0 = tc::make_smem_desc(w_hi, 128, w_sbo), wdl0 = tc::make_smem_desc(w_hi + (uint32_t)H * KSL * 4, 128, w_sbo);
-                const uint64_t adh0 = tc::desc_add(a_desc_hi, s * (KSL / 8) * a_kstep), adl0 = tc::desc_add(a_desc_lo, s * (KSL / 8) * a_kstep);
+        if (my_tiles > 0) {
+            tc::mbar_wait(daready, (uint32_t)((my_tiles - 1) & 1));
+            if (!(p.debug & 4))
+                site::scatter_tile_lean(p.f, p.g, p.xyz, p.level, p.n, p.units, (blockIdx.x + (my_tiles - 1) * gridDim.x) * SPT, dAs, DAS, NGRP, mtid);
+        }
+    } else {
+        // ======================= math group: GEMM1, chunked dPre epilogue, GEMM-dA ======================================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+        const int lq = warp & 3, half = warp >> 2;
+        const int row = lq * 32 + lane;
+        const int row_s = row / NQ7, row_q = row - row_s * NQ7;
+        const uint32_t d1 = tmem_base, d2 = tmem_base + 256, chunk_a = tmem_base + 384;   // chunk_a: 2 x (hi 32 | lo 32) columns
+        const uint32_t idesc1 = tc::make_idesc(2, 2, TM, H), idesc2 = tc::make_idesc(2, 2, TM, KT);
+        const uint32_t a_sbo = site::a_sbo(KT), w1_sbo = (KS1 / 4) * 128, w2_sbo = (HHC / 4) * 128;
+        const uint64_t a_desc_hi = tc::make_smem_desc(tc::smem_u32(a_hi), site::A_LBO, a_sbo), a_desc_lo = tc::make_smem_desc(tc::smem_u32(a_lo), site::A_LBO, a_sbo);
+
+        int64_t g_issue = 0, g_mma = 0;            // driver (thread 0): ring slot counters
+        const int64_t total_slots = my_tiles * J;
+        uint32_t cf_commits[2] = {0, 0};           // commits issued on cfree[buf] so far
+        auto ring_prefetch = [&]() {
+            while (g_issue < total_slots && g_issue < g_mma + NST) {
+                const int st = (int)(g_issue % NST);
+                tc::mbar_wait(&empty[st], (uint32_t)(((g_issue / NST) & 1) ^ 1));
+                mbar_expect_tx(&full[st], slot_bytes);
+                bulk_copy_g2s(wst + (size_t)st * slot_bytes, p.Wtc + (size_t)(g_issue % J) * p.slot_floats, slot_bytes, &full[st]);
+                ++g_issue;
+            }
+        };
+        if (tid == 0) ring_prefetch();
+
+        for (int64_t lt = 0; lt < my_tiles; ++lt) {
+            const int64_t tile = blockIdx.x + lt * gridDim.x;
+            const int64_t s_base = tile * SPT;
+            const int64_t tile_row0 = tile * TM;
+            const uint32_t tpar = (uint32_t)(lt & 1);
+            // upstream gradients -> per-query SDF gradients of the tile's samples (adjoint of fields.py:245-256)
+            if (tid < SPT) {
+                const int64_t n = s_base + tid;
+                float gq[NQ7];
 #pragma unroll
-                for (int ks = 0; ks < KSL / 8; ++ks) {
-                    const uint64_t adh = tc::desc_add(adh0, ks * a_kstep), adl = tc::desc_add(adl0, ks * a_kstep);
-                    const uint64_t wdh = tc::desc_add(wdh0, ks * 256), wdl = tc::desc_add(wdl0, ks * 256);
-                    tc::mma_tf32_ss(d1, adh, wdh, idesc1, (s | ks) != 0);
+                for (int r = 0; r < NQ7; ++r) gq[r] = 0.f;
+                if (n < p.n) {
+                    float sd[NQ7];
+#pragma unroll
+                    for (int r = 0; r < NQ7; ++r) sd[r] = p.sdf7[n * NQ7 + r];
+                    float g[3], h[3];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const float e = p.units[k];
+                        g[k] = (sd[1 + 2 * k] - sd[2 + 2 * k]) / (2.f * e);
+                        h[k] = (sd[1 + 2 * k] + sd[2 + 2 * k] - 2.f * sd[0]) / (e * e);
+                    }
+                    const float D = g[0] * g[0] + g[1] * g[1] + g[2] * g[2] + 1e-5f;
+                    const float nh = (g[0] * h[0] + g[1] * h[1] + g[2] * h[2]) / D;
+                    const float gh = p.g_hess ? p.g_hess[n] : 0.f;
+                    gq[0] = p.g_sdf ? p.g_sdf[n] : 0.f;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const float e = p.units[k];
+                        const float Gk = (p.g_grad ? p.g_grad[n * 3 + k] : 0.f) + gh * (h[k] / D - 2.f * g[k] * nh / D);
+                        const float Hk = gh * g[k] / D;
+                        gq[1 + 2 * k] = Gk / (2.f * e) + Hk / (e * e);
+                        gq[2 + 2 * k] = -Gk / (2.f * e) + Hk / (e * e);
+                        gq[0] -= 2.f * Hk / (e * e);
+                    }
+                }
+                float tot = 0.f;
+#pragma unroll
+                for (int r = 0; r < NQ7; ++r) { gqs[tid * NQ7 + r] = gq[r]; tot += gq[r]; }
+                if (tot != 0.f) atomicAdd(accb1, tot);
+            } else if (tid < SPT + 2) {
+                gqs[SPT * NQ7 + tid - SPT] = 0.f;
+            }
+            // ---- GEMM1 (thread 0): pre = A W0^T ----------------------------------------------------------------------
+            if (tid == 0) {
+                tc::mbar_wait(aready, tpar);
+                tc::fence_after_sync();
+                for (int s = 0; s < S; ++s) {
+                    ring_prefetch();
+                    const int st = (int)(g_mma % NST);
+                    tc::mbar_wait(&full[st], (uint32_t)((g_mma / NST) & 1));
+                    tc::fence_after_sync();
+                    const uint32_t w_hi = tc::smem_u32(wst + (size_t)st * slot_bytes);
+                    const uint64_t wdh = tc::make_smem_desc(w_hi, 128, w1_sbo), wdl = tc::make_smem_desc(w_hi + (uint32_t)H * KS1 * 4, 128, w1_sbo);
+                    const uint64_t adh = tc::desc_add(a_desc_hi, s * 2 * site::A_LBO), adl = tc::desc_add(a_desc_lo, s * 2 * site::A_LBO);
+                    tc::mma_tf32_ss(d1, adh, wdh, idesc1, s != 0);
                     tc::mma_tf32_ss(d1, adh, wdl, idesc1, 1);
                     tc::mma_tf32_ss(d1, adl, wdh, idesc1, 1);
+                    tc::mma_commit(&empty[st]);
+                    ++g_mma;
                 }
-                tc::mma_commit(&empty[st]);
-                ++g_mma;
+                tc::mma_commit(dfull1);
+                ring_prefetch();
             }
-            tc::mma_commit(dfull1);
-            ring_prefetch();
-        }
-        const int64_t n = s_base + row_s;
-        const bool centre = row_q == 0 && row_s < SPT && n < p.n;
-        const bool has_hc = centre && p.dHc;
-        // dHidden(centre) of the next chunk is fetched one chunk ahead (the first one under the GEMM1 wait)
-        float4 hc[4] = {f4_zero(), f4_zero(), f4_zero(), f4_zero()};
-        if (has_hc) {
-            const float4* src = reinterpret_cast<const float4*>(p.dHc + (size_t)n * H + half * 16);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) hc[j] = __ldg(src + j);
-        }
-        tc::mbar_wait(dfull1, tpar);
-        tc::fence_after_sync();
-        // ---- epilogue-1 + GEMM-dA, chunk by chunk over the hidden units -----------------------------------
-        const float gq = gqs[row];
-        for (int c = 0; c < ((p.debug & 16) ? 0 : NCH); ++c) {
-            const int buf = c & 1;
-            if (c >= 2) { tc::mbar_wait(&cfree[buf], (cf_commits[buf] - 1) & 1); tc::fence_after_sync(); }
-            const int col0 = c * HCH + half * 16;
-            float v[16];
-            tc::tmem_ld16(d1 + ((uint32_t)(lq * 32) << 16) + col0, v);
-            float sp[16];
-            const float hcv[16] = {hc[0].x, hc[0].y, hc[0].z, hc[0].w, hc[1].x, hc[1].y, hc[1].z, hc[1].w,
-                                   hc[2].x, hc[2].y, hc[2].z, hc[2].w, hc[3].x, hc[3].y, hc[3].z, hc[3].w};
-            if (has_hc && c + 1 < NCH) {
-                const float4* src = reinterpret_cast<const float4*>(p.dHc + (size_t)n * H + col0 + HCH);
+            const int64_t n = s_base + row_s;
+            const bool centre = row_q == 0 && row_s < SPT && n < p.n;
+            const bool has_hc = centre && p.dHc;
+            // dHidden(centre) of the next chunk is fetched one chunk ahead (the first one under the GEMM1 wait)
+            float4 hc[4] = {f4_zero(), f4_zero(), f4_zero(), f4_zero()};
+            if (has_hc) {
+                const float4* src = reinterpret_cast<const float4*>(p.dHc + (size_t)n * H + half * 16);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) hc[j] = __ldg(src + j);
             }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                float sg;
-                softplus100_fast_both(v[j] + b0s[col0 + j], sp[j], sg);
-                v[j] = fmaf(gq, w1s[col0 + j], hcv[j]) * sg;         // dPre = dPost * sigmoid
-            }
-            float4* dst = reinterpret_cast<float4*>(p.dpre + (size_t)(tile_row0 + row) * H + col0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (!(p.debug & 2)) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            {   // the chunk becomes the A operand of the dA MMAs straight in tensor memory (tf32 hi | lo, lane = row)
-                float lo[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) { const float h = tc::tf32_rn(v[j]); lo[j] = tc::tf32_rn(v[j] - h); v[j] = h; }
-                const uint32_t ca = chunk_a + (uint32_t)buf * 64 + ((uint32_t)(lq * 32) << 16) + half * 16;
-                tc::tmem_st16(ca, v);
-                tc::tmem_st16(ca + 32, lo);
-                tc::tmem_st_wait();
-            }
-            if (centre && p.spc) {
-                float4* sdst = reinterpret_cast<float4*>(p.spc + (size_t)n * H + col0);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) sdst[j] = make_float4(sp[4 * j], sp[4 * j + 1], sp[4 * j + 2], sp[4 * j + 3]);
-            }
-            if (!(p.debug & 8)) {
-                // 16 column sums over the warp's 32 rows with 16 shuffles: every exchange halves the columns a lane owns
-                float w8[8], w4[4], w2[2];
-                const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4, b2 = lane & 2;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float lo_v = gq * sp[j], hi_v = gq * sp[j + 8];
-                    w8[j] = (b16 ? hi_v : lo_v) + __shfl_xor_sync(0xffffffffu, b16 ? lo_v : hi_v, 16);
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) w4[j] = (b8 ? w8[j + 4] : w8[j]) + __shfl_xor_sync(0xffffffffu, b8 ? w8[j] : w8[j + 4], 8);
-#pragma unroll
-                for (int j = 0; j < 2; ++j) w2[j] = (b4 ? w4[j + 2] : w4[j]) + __shfl_xor_sync(0xffffffffu, b4 ? w4[j] : w4[j + 2], 4);
-                float w1 = (b2 ? w2[1] : w2[0]) + __shfl_xor_sync(0xffffffffu, b2 ? w2[0] : w2[1], 2);
-                w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
-                const int col = (b16 ? 8 : 0) + (b8 ? 4 : 0) + (b4 ? 2 : 0) + (b2 ? 1 : 0);
-                if (!(lane & 1) && w1 != 0.f) atomicAdd(&accw1[col0 + col], w1);
-            }
-            tc::fence_async_smem();
-            tc::fence_before_sync();
-            __syncthreads();
+            tc::bar_sync(1, NGRP);                     // gqs visible to the group
+            tc::mbar_wait(dfull1, tpar);
             tc::fence_after_sync();
-            if (tid == 0) {
-                ring_prefetch();
-                const int st = (int)(g_mma % NST);
-                tc::mbar_wait(&full[st], (uint32_t)((g_mma / NST) & 1));
-                tc::fence_after_sync();
-                const uint32_t w_hi = tc::smem_u32(wst + (size_t)st * slot_bytes);
-                const uint64_t wdh0 = tc::make_smem_desc(w_hi, 128, c_sbo), wdl0 = tc::make_smem_desc(w_hi + (uint32_t)KT * HCH * 4, 128, c_sbo);
-                const uint32_t ah = chunk_a + (uint32_t)buf * 64, al = ah + 32;
+            // ---- epilogue-1 + GEMM-dA, chunk by chunk over the hidden units -----------------------------------
+            const float gq = gqs[row];
+            for (int c = 0; c < ((p.debug & 16) ? 0 : NCH); ++c) {
+                const int buf = c & 1;
+                if (c >= 2) { tc::mbar_wait(&cfree[buf], (cf_commits[buf] - 1) & 1); tc::fence_after_sync(); }
+                const int col0 = c * HCH + half * 16;
+                float v[16];
+                tc::tmem_ld16(d1 + ((uint32_t)(lq * 32) << 16) + col0, v);
+                float sp[16];
+                const float hcv[16] = {hc[0].x, hc[0].y, hc[0].z, hc[0].w, hc[1].x, hc[1].y, hc[1].z, hc[1].w,
+                                       hc[2].x, hc[2].y, hc[2].z, hc[2].w, hc[3].x, hc[3].y, hc[3].z, hc[3].w};
+                if (has_hc && c + 1 < NCH) {
+                    const float4* src = reinterpret_cast<const float4*>(p.dHc + (size_t)n * H + col0 + HCH);
 #pragma unroll
-                for (int ks = 0; ks < HCH / 8; ++ks) {
-                    const uint64_t wdh = tc::desc_add(wdh0, ks * 256), wdl = tc::desc_add(wdl0, ks * 256);
-                    tc::mma_tf32_ts(d2, ah + ks * 8, wdh, idesc2, (c | ks) != 0);
-                    tc::mma_tf32_ts(d2, ah + ks * 8, wdl, idesc2, 1);
-                    tc::mma_tf32_ts(d2, al + ks * 8, wdh, idesc2, 1);
+                    for (int j = 0; j < 4; ++j) hc[j] = __ldg(src + j);
                 }
-                tc::mma_commit(&empty[st]);
-                tc::mma_commit(&cfree[buf]);
-                ++g_mma;
-                if (c == NCH - 1) tc::mma_commit(dfull2);
-                ring_prefetch();
-            }
-            ++cf_commits[buf];
-        }
-        if (!(p.debug & 16)) tc::mbar_wait(dfull2, tpar);
-        tc::fence_after_sync();
-        // ---- dA: TMEM -> shared memory (fp32, row-major) ----------------------------------------------------
-        for (int c0 = half * 16; c0 < KT; c0 += 32) {
-            float v[16];
-            tc::tmem_ld16(d2 + ((uint32_t)(lq * 32) << 16) + c0, v);
-            float4* dst = reinterpret_cast<float4*>(dAs + (size_t)row * DAS + c0);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                for (int j = 0; j < 16; ++j) {
+                    float sg;
+                    softplus100_fast_both(v[j] + b0s[col0 + j], sp[j], sg);
+                    v[j] = fmaf(gq, w1s[col0 + j], hcv[j]) * sg;         // dPre = dPost * sigmoid
+                }
+                float4* dst = reinterpret_cast<float4*>(p.dpre + (size_t)(tile_row0 + row) * H + col0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (!(p.debug & 2)) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                {   // the chunk becomes the A operand of the dA MMAs straight in tensor memory (tf32 hi | lo, lane = row)
+                    float lo[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { const float h = tc::tf32_rn(v[j]); lo[j] = tc::tf32_rn(v[j] - h); v[j] = h; }
+                    const uint32_t ca = chunk_a + (uint32_t)buf * 64 + ((uint32_t)(lq * 32) << 16) + half * 16;
+                    tc::tmem_st16(ca, v);
+                    tc::tmem_st16(ca + 32, lo);
+                    tc::tmem_st_wait();
+                }
+                if (centre && p.spc) {
+                    float4* sdst = reinterpret_cast<float4*>(p.spc + (size_t)n * H + col0);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) sdst[j] = make_float4(sp[4 * j], sp[4 * j + 1], sp[4 * j + 2], sp[4 * j + 3]);
+                }
+                if (!(p.debug & 8)) {
+                    // 16 column sums over the warp's 32 rows with 16 shuffles: every exchange halves the columns a lane owns
+                    float w8[8], w4[4], w2[2];
+                    const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4, b2 = lane & 2;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float lo_v = gq * sp[j], hi_v = gq * sp[j + 8];
+                        w8[j] = (b16 ? hi_v : lo_v) + __shfl_xor_sync(0xffffffffu, b16 ? lo_v : hi_v, 16);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) w4[j] = (b8 ? w8[j + 4] : w8[j]) + __shfl_xor_sync(0xffffffffu, b8 ? w8[j] : w8[j + 4], 8);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) w2[j] = (b4 ? w4[j + 2] : w4[j]) + __shfl_xor_sync(0xffffffffu, b4 ? w4[j] : w4[j + 2], 4);
+                    float w1 = (b2 ? w2[1] : w2[0]) + __shfl_xor_sync(0xffffffffu, b2 ? w2[0] : w2[1], 2);
+                    w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
+                    const int col = (b16 ? 8 : 0) + (b8 ? 4 : 0) + (b4 ? 2 : 0) + (b2 ? 1 : 0);
+                    if (!(lane & 1) && w1 != 0.f) atomicAdd(&accw1[col0 + col], w1);
+                }
+                tc::fence_before_sync();
+                tc::bar_sync(1, NGRP);
+                tc::fence_after_sync();
+                if (tid == 0) {
+                    const uint32_t ah = chunk_a + (uint32_t)buf * 64, al = ah + 32;
+#pragma unroll
+                    for (int hh = 0; hh < HCH / HHC; ++hh) {
+                        ring_prefetch();
+                        const int st = (int)(g_mma % NST);
+                        tc::mbar_wait(&full[st], (uint32_t)((g_mma / NST) & 1));
+                        tc::fence_after_sync();
+                        const uint32_t w_hi = tc::smem_u32(wst + (size_t)st * slot_bytes);
+                        const uint64_t wdh0 = tc::make_smem_desc(w_hi, 128, w2_sbo), wdl0 = tc::make_smem_desc(w_hi + (uint32_t)KT * HHC * 4, 128, w2_sbo);
+#pragma unroll
+                        for (int ks = 0; ks < HHC / 8; ++ks) {
+                            const uint64_t wdh = tc::desc_add(wdh0, ks * 256), wdl = tc::desc_add(wdl0, ks * 256);
+                            const uint32_t kc = hh * HHC + ks * 8;
+                            tc::mma_tf32_ts(d2, ah + kc, wdh, idesc2, (c | hh | ks) != 0);
+                            tc::mma_tf32_ts(d2, ah + kc, wdl, idesc2, 1);
+                            tc::mma_tf32_ts(d2, al + kc, wdh, idesc2, 1);
+                        }
+                        tc::mma_commit(&empty[st]);
+                        ++g_mma;
+                    }
+                    tc::mma_commit(&cfree[buf]);
+                    if (c == NCH - 1) tc::mma_commit(dfull2);
+                    ring_prefetch();
+                }
+                ++cf_commits[buf];
+            }
+            if (p.debug & 16) {
+                if (tid == 0) {                         // timing experiments: the skipped slots still rotate through the ring
+                    for (int c = 0; c < 2 * NCH; ++c) {
+                        ring_prefetch();
+                        const int st = (int)(g_mma % NST);
+                        tc::mbar_wait(&full[st], (uint32_t)((g_mma / NST) & 1));
+                        tc::mma_commit(&empty[st]);
+                        ++g_mma;
+                    }
+                    ring_prefetch();
+                }
+            } else {
+                tc::mbar_wait(dfull2, tpar);
+            }
+            tc::fence_after_sync();
+            // ---- dA: TMEM -> shared memory (fp32, row-major) once the memory group has scattered the previous tile ----
+            if (lt > 0) tc::mbar_wait(dafree, (uint32_t)((lt - 1) & 1));
+            for (int c0 = half * 16; c0 < KT; c0 += 32) {
+                float v[16];
+                tc::tmem_ld16(d2 + ((uint32_t)(lq * 32) << 16) + c0, v);
+                float4* dst = reinterpret_cast<float4*>(dAs + (size_t)row * DAS + c0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+            tc::fence_before_sync();
+            tc::mbar_arrive(daready);
         }
-        tc::fence_before_sync();
-        __syncthreads();
-        tc::fence_after_sync();
-        // ---- scatter: d plane += w * (dA . line), d line += w * (dA . plane) ----------------------------------
-        if (!(p.debug & 4)) site::scatter_tile(p.f, p.g, p.xyz, p.level, p.n, p.units, s_base, dAs, DAS, NTH);
-        __syncthreads();       // the next gather overwrites the A region
     }
     __syncthreads();
     for (int i = tid; i < H; i += NTH)
@@ -353,13 +393,13 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_bwd_tc_kernel(TcBwdParams 
 }  // namespace
 
 int tf_internal_bwd_tc_slot_floats(int KT, int H) {
-    const int a = 2 * H * KSL, b = 2 * KT * HCH;
+    const int a = 2 * H * KS1, b = 2 * KT * HHC;
     return a > b ? a : b;
 }
-size_t tf_internal_bwd_tc_wtc_floats(int KT, int H) { return (size_t)(KT / KSL + H / HCH) * tf_internal_bwd_tc_slot_floats(KT, H); }
+size_t tf_internal_bwd_tc_wtc_floats(int KT, int H) { return (size_t)(KT / KS1 + H / HHC) * tf_internal_bwd_tc_slot_floats(KT, H); }
 size_t tf_internal_bwd_tc_smem(int KT, int H) {
-    return (size_t)2 * 16 * (KT / 4) * site::A_LBO + (size_t)NST * tf_internal_bwd_tc_slot_floats(KT, H) * 4 + (size_t)3 * H * 4 +
-           (size_t)TM * 4 + (2 * NST + 4) * 8 + 32;
+    return (size_t)2 * 16 * (KT / 4) * site::A_LBO + (size_t)TM * (KT + 4) * 4 + (size_t)NST * tf_internal_bwd_tc_slot_floats(KT, H) * 4 +
+           (size_t)3 * H * 4 + (size_t)TM * 4 + (2 * NST + 9) * 8 + 32;
 }
 
 int tf_internal_bwd_tc_prep(const float* W0, int K, int KT, int H, float* wtc, cudaStream_t stream) {

@@ -163,11 +163,11 @@ __device__ __forceinline__ void put(uint8_t* a_hi, uint8_t* a_lo, uint32_t off, 
 // rows are also streamed to HBM ([128][KT] per tile, the constant-1 column at index 3C+3 included).
 template <bool TWO>
 __device__ __forceinline__ void gather_tile_t(const tf_vm_field_t& f, const float* __restrict__ xyz, const float* __restrict__ level, int64_t n_total,
-                                            const float units[3], int64_t s_base, int KT, uint8_t* a_hi, uint8_t* a_lo, float* arow, int nthreads) {
+                                            const float units[3], int64_t s_base, int KT, uint8_t* a_hi, uint8_t* a_lo, float* arow, int nthreads, int tid0) {
     const int C = f.n_comp, C4 = C / 4, G = KT / 4;
     const bool has_level = level != nullptr;
     const int n_tasks = SPT * 3 * C4;
-    for (int task = threadIdx.x; task < n_tasks; task += nthreads) {
+    for (int task = tid0; task < n_tasks; task += nthreads) {
         const int c4 = task % C4, si = task / C4, i = si % 3, s = si / 3;
         const int64_t n = s_base + s;
         const int g = i * C4 + c4, r0 = s * NQ;
@@ -207,7 +207,7 @@ __device__ __forceinline__ void gather_tile_t(const tf_vm_field_t& f, const floa
     }
     // raw stencil points (fields.py:265,298), zero padding groups and the two zero rows of the tile
     const int tail_g = G - 3 * C4;
-    for (int it = threadIdx.x; it < 128 * tail_g; it += nthreads) {
+    for (int it = tid0; it < 128 * tail_g; it += nthreads) {
         const int r = it % 128, g = 3 * C4 + it / 128;
         const int s = r / NQ, q = r - s * NQ;
         const int64_t n = s_base + s;
@@ -222,7 +222,7 @@ __device__ __forceinline__ void gather_tile_t(const tf_vm_field_t& f, const floa
         put(a_hi, a_lo, a_off(r, g, KT), v);
         if (arow) *reinterpret_cast<float4*>(arow + (size_t)r * KT + g * 4) = vh;
     }
-    for (int it = threadIdx.x; it < 2 * 3 * C4; it += nthreads) {
+    for (int it = tid0; it < 2 * 3 * C4; it += nthreads) {
         const int r = SPT * NQ + it / (3 * C4), g = it % (3 * C4);
         put(a_hi, a_lo, a_off(r, g, KT), f4_zero());
         if (arow) *reinterpret_cast<float4*>(arow + (size_t)r * KT + g * 4) = f4_zero();
@@ -230,9 +230,10 @@ __device__ __forceinline__ void gather_tile_t(const tf_vm_field_t& f, const floa
 }
 
 __device__ __forceinline__ void gather_tile(const tf_vm_field_t& f, const float* __restrict__ xyz, const float* __restrict__ level, int64_t n_total,
-                                            const float units[3], int64_t s_base, int KT, uint8_t* a_hi, uint8_t* a_lo, float* arow, int nthreads) {
-    if (level != nullptr && f.n_levels > 1) gather_tile_t<true>(f, xyz, level, n_total, units, s_base, KT, a_hi, a_lo, arow, nthreads);
-    else gather_tile_t<false>(f, xyz, level, n_total, units, s_base, KT, a_hi, a_lo, arow, nthreads);
+                                            const float units[3], int64_t s_base, int KT, uint8_t* a_hi, uint8_t* a_lo, float* arow, int nthreads, int tid0 = -1) {
+    if (tid0 < 0) tid0 = threadIdx.x;      // threads tid0 = 0..nthreads-1 of the calling group share the tile
+    if (level != nullptr && f.n_levels > 1) gather_tile_t<true>(f, xyz, level, n_total, units, s_base, KT, a_hi, a_lo, arow, nthreads, tid0);
+    else gather_tile_t<false>(f, xyz, level, n_total, units, s_base, KT, a_hi, a_lo, arow, nthreads, tid0);
 }
 
 __device__ __forceinline__ float* twin(const float* p, const float* base0, float* g0, const float* basem, float* gm) {
@@ -275,11 +276,11 @@ __device__ __forceinline__ float4 f4_fma4(float4 a, float4 b, float4 c) { return
 template <bool TWO>
 __device__ __forceinline__ void scatter_tile_t(const tf_vm_field_t& f, const tf_vm_mut_t& gm, const float* __restrict__ xyz,
                                              const float* __restrict__ level, int64_t n_total, const float units[3], int64_t s_base,
-                                             const float* dA, int ld, int nthreads) {
+                                             const float* dA, int ld, int nthreads, int tid0) {
     const int C = f.n_comp, C4 = C / 4;
     const bool has_level = level != nullptr;
     const int n_tasks = SPT * 3 * C4;
-    for (int task = threadIdx.x; task < n_tasks; task += nthreads) {
+    for (int task = tid0; task < n_tasks; task += nthreads) {
         const int c4 = task % C4, si = task / C4, i = si % 3, s = si / 3;
         const int64_t n = s_base + s;
         if (n >= n_total) continue;
@@ -332,9 +333,201 @@ __device__ __forceinline__ void scatter_tile_t(const tf_vm_field_t& f, const tf_
 
 __device__ __forceinline__ void scatter_tile(const tf_vm_field_t& f, const tf_vm_mut_t& gm, const float* __restrict__ xyz,
                                              const float* __restrict__ level, int64_t n_total, const float units[3], int64_t s_base,
-                                             const float* dA, int ld, int nthreads) {
-    if (level != nullptr && f.n_levels > 1) scatter_tile_t<true>(f, gm, xyz, level, n_total, units, s_base, dA, ld, nthreads);
-    else scatter_tile_t<false>(f, gm, xyz, level, n_total, units, s_base, dA, ld, nthreads);
+                                             const float* dA, int ld, int nthreads, int tid0 = -1) {
+    if (tid0 < 0) tid0 = threadIdx.x;
+    if (level != nullptr && f.n_levels > 1) scatter_tile_t<true>(f, gm, xyz, level, n_total, units, s_base, dA, ld, nthreads, tid0);
+    else scatter_tile_t<false>(f, gm, xyz, level, n_total, units, s_base, dA, ld, nthreads, tid0);
+}
+
+// ---- register-lean variants (the warp-specialised backward runs its memory group next to a math group and cannot
+// ---- afford the ~200 registers of the batched fetch): sampling plans are built position by position (16 registers
+// ---- each), 8 texel loads in flight per thread, latency hidden by the group's 8 warps
+template <bool TWO> struct PlanePos { Tap1 x0, y0, x1, y1; };
+template <bool TWO> struct LinePos { Tap1 l0, l1; };
+template <bool TWO>
+__device__ __forceinline__ PlanePos<TWO> plane_pos(const Levels& L, float pu, float pv) {
+    PlanePos<TWO> p;
+    p.x0 = tap1(pu, L.W0); p.y0 = tap1(pv, L.H0);
+    if (TWO) { p.x1 = tap1(pu, L.W1); p.y1 = tap1(pv, L.H1); }
+    return p;
+}
+template <bool TWO>
+__device__ __forceinline__ LinePos<TWO> line_pos(const Levels& L, float lv) {
+    LinePos<TWO> p;
+    p.l0 = tap1(lv, L.G0);
+    if (TWO) p.l1 = tap1(lv, L.G1);
+    return p;
+}
+template <bool TWO>
+__device__ __forceinline__ float4 fetch_plane(const Levels& L, const PlanePos<TWO>& p, int C, int c) {
+    float4 t0[4], t1[4];
+    bi_load(L.pt0, p.x0, p.y0, L.W0, C, c, t0);
+    if (TWO) bi_load(L.pt1, p.x1, p.y1, L.W1, C, c, t1);
+    float4 P = bi_combine(p.x0, p.y0, t0);
+    if (TWO) P = mix(L.fl, P, bi_combine(p.x1, p.y1, t1));
+    return P;
+}
+template <bool TWO>
+__device__ __forceinline__ float4 fetch_line(const Levels& L, const LinePos<TWO>& p, int C, int c) {
+    float4 t0[2], t1[2];
+    li_load(L.lt0, p.l0, C, c, t0);
+    if (TWO) li_load(L.lt1, p.l1, C, c, t1);
+    float4 V = li_combine(p.l0, t0);
+    if (TWO) V = mix(L.fl, V, li_combine(p.l1, t1));
+    return V;
+}
+template <bool TWO>
+__device__ __forceinline__ void scatter_plane_pos(float* t0, float* t1, const Levels& L, const PlanePos<TWO>& p, int C, int c, float4 d) {
+    {
+        const float w0 = 1.f - L.fl;
+        red_add_v4(t0 + (size_t)(p.y0.i0 * L.W0 + p.x0.i0) * C + c, f4_scale(w0 * (p.x0.w0 * p.y0.w0), d));
+        red_add_v4(t0 + (size_t)(p.y0.i0 * L.W0 + p.x0.i1) * C + c, f4_scale(w0 * (p.x0.w1 * p.y0.w0), d));
+        red_add_v4(t0 + (size_t)(p.y0.i1 * L.W0 + p.x0.i0) * C + c, f4_scale(w0 * (p.x0.w0 * p.y0.w1), d));
+        red_add_v4(t0 + (size_t)(p.y0.i1 * L.W0 + p.x0.i1) * C + c, f4_scale(w0 * (p.x0.w1 * p.y0.w1), d));
+    }
+    if (TWO && L.fl > 0.f) {
+        red_add_v4(t1 + (size_t)(p.y1.i0 * L.W1 + p.x1.i0) * C + c, f4_scale(L.fl * (p.x1.w0 * p.y1.w0), d));
+        red_add_v4(t1 + (size_t)(p.y1.i0 * L.W1 + p.x1.i1) * C + c, f4_scale(L.fl * (p.x1.w1 * p.y1.w0), d));
+        red_add_v4(t1 + (size_t)(p.y1.i1 * L.W1 + p.x1.i0) * C + c, f4_scale(L.fl * (p.x1.w0 * p.y1.w1), d));
+        red_add_v4(t1 + (size_t)(p.y1.i1 * L.W1 + p.x1.i1) * C + c, f4_scale(L.fl * (p.x1.w1 * p.y1.w1), d));
+    }
+}
+template <bool TWO>
+__device__ __forceinline__ void scatter_line_pos(float* t0, float* t1, const Levels& L, const LinePos<TWO>& p, int C, int c, float4 d) {
+    const float w0 = 1.f - L.fl;
+    red_add_v4(t0 + (size_t)p.l0.i0 * C + c, f4_scale(w0 * p.l0.w0, d));
+    red_add_v4(t0 + (size_t)p.l0.i1 * C + c, f4_scale(w0 * p.l0.w1, d));
+    if (TWO && L.fl > 0.f) {
+        red_add_v4(t1 + (size_t)p.l1.i0 * C + c, f4_scale(L.fl * p.l1.w0, d));
+        red_add_v4(t1 + (size_t)p.l1.i1 * C + c, f4_scale(L.fl * p.l1.w1, d));
+    }
+}
+
+template <bool TWO>
+__device__ __forceinline__ void gather_tile_lean_t(const tf_vm_field_t& f, const float* __restrict__ xyz, const float* __restrict__ level,
+                                                   int64_t n_total, const float units[3], int64_t s_base, int KT, uint8_t* a_hi, uint8_t* a_lo,
+                                                   float* arow, int nthreads, int tid0) {
+    const int C = f.n_comp, C4 = C / 4, G = KT / 4;
+    const bool has_level = level != nullptr;
+    const int n_tasks = SPT * 3 * C4;
+    auto emit = [&](int r, int g, float4 v) {
+        put(a_hi, a_lo, a_off(r, g, KT), v);
+        if (arow) *reinterpret_cast<float4*>(arow + (size_t)r * KT + g * 4) = v;
+    };
+    for (int task = tid0; task < n_tasks; task += nthreads) {
+        const int c4 = task % C4, si = task / C4, i = si % 3, s = si / 3;
+        const int64_t n = s_base + s;
+        const int g = i * C4 + c4, r0 = s * NQ, c = c4 * 4;
+        const Axes a = axes(i);
+        const int r_m0 = r0 + 1 + 2 * a.m0, r_m1 = r0 + 1 + 2 * a.m1, r_vm = r0 + 1 + 2 * a.vm;
+        if (n >= n_total) {
+#pragma unroll
+            for (int j = 0; j < NQ; ++j) emit(r0 + j, g, f4_zero());
+            continue;
+        }
+        const float x[3] = {xyz[n * 3 + 0], xyz[n * 3 + 1], xyz[n * 3 + 2]};
+        const Levels L = levels(f, has_level ? level[n] : 0.f, has_level, i);
+        const Coords k = coords(f, x, units, a);
+        const float4 L0 = fetch_line<TWO>(L, line_pos<TWO>(L, k.lv[0]), C, c);
+        const float4 P0 = fetch_plane<TWO>(L, plane_pos<TWO>(L, k.pu[0], k.pv[0]), C, c);
+        emit(r0, g, f4_mul(P0, L0));
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const float pu = v == 0 ? k.pu[1] : (v == 1 ? k.pu[2] : k.pu[0]);
+            const float pv = v == 2 ? k.pv[1] : (v == 3 ? k.pv[2] : k.pv[0]);
+            const int r = v < 2 ? r_m0 + v : r_m1 + (v - 2);
+            emit(r, g, f4_mul(fetch_plane<TWO>(L, plane_pos<TWO>(L, pu, pv), C, c), L0));
+        }
+        emit(r_vm, g, f4_mul(P0, fetch_line<TWO>(L, line_pos<TWO>(L, k.lv[1]), C, c)));
+        emit(r_vm + 1, g, f4_mul(P0, fetch_line<TWO>(L, line_pos<TWO>(L, k.lv[2]), C, c)));
+    }
+    // raw stencil points, zero padding groups and the two zero rows of the tile (as in gather_tile_t)
+    const int tail_g = G - 3 * C4;
+    for (int it = tid0; it < 128 * tail_g; it += nthreads) {
+        const int r = it % 128, g = 3 * C4 + it / 128;
+        const int s = r / NQ, q = r - s * NQ;
+        const int64_t n = s_base + s;
+        float4 v = f4_zero(), vh = f4_zero();
+        if (g == 3 * C4 && s < SPT && n < n_total) {
+            const float x[3] = {xyz[n * 3 + 0], xyz[n * 3 + 1], xyz[n * 3 + 2]};
+            float pt[3];
+            stencil_point(x, units, q, pt);
+            v = make_float4(pt[0], pt[1], pt[2], 0.f);
+            vh = make_float4(pt[0], pt[1], pt[2], 1.f);
+        }
+        put(a_hi, a_lo, a_off(r, g, KT), v);
+        if (arow) *reinterpret_cast<float4*>(arow + (size_t)r * KT + g * 4) = vh;
+    }
+    for (int it = tid0; it < 2 * 3 * C4; it += nthreads) {
+        const int r = SPT * NQ + it / (3 * C4), g = it % (3 * C4);
+        put(a_hi, a_lo, a_off(r, g, KT), f4_zero());
+        if (arow) *reinterpret_cast<float4*>(arow + (size_t)r * KT + g * 4) = f4_zero();
+    }
+}
+__device__ __forceinline__ void gather_tile_lean(const tf_vm_field_t& f, const float* __restrict__ xyz, const float* __restrict__ level, int64_t n_total,
+                                                 const float units[3], int64_t s_base, int KT, uint8_t* a_hi, uint8_t* a_lo, float* arow, int nthreads,
+                                                 int tid0) {
+    if (level != nullptr && f.n_levels > 1) gather_tile_lean_t<true>(f, xyz, level, n_total, units, s_base, KT, a_hi, a_lo, arow, nthreads, tid0);
+    else gather_tile_lean_t<false>(f, xyz, level, n_total, units, s_base, KT, a_hi, a_lo, arow, nthreads, tid0);
+}
+
+template <bool TWO>
+__device__ __forceinline__ void scatter_tile_lean_t(const tf_vm_field_t& f, const tf_vm_mut_t& gm, const float* __restrict__ xyz,
+                                                    const float* __restrict__ level, int64_t n_total, const float units[3], int64_t s_base,
+                                                    const float* dA, int ld, int nthreads, int tid0) {
+    const int C = f.n_comp, C4 = C / 4;
+    const bool has_level = level != nullptr;
+    const int n_tasks = SPT * 3 * C4;
+    for (int task = tid0; task < n_tasks; task += nthreads) {
+        const int c4 = task % C4, si = task / C4, i = si % 3, s = si / 3;
+        const int64_t n = s_base + s;
+        if (n >= n_total) continue;
+        const int g = i * C4 + c4, r0 = s * NQ, c = c4 * 4;
+        const Axes a = axes(i);
+        const float x[3] = {xyz[n * 3 + 0], xyz[n * 3 + 1], xyz[n * 3 + 2]};
+        const Levels L = levels(f, has_level ? level[n] : 0.f, has_level, i);
+        const Coords k = coords(f, x, units, a);
+        float* pm0 = twin(L.pt0, f.plane[i], gm.plane[i], f.plane_mip[i], gm.plane_mip[i]);
+        float* pm1 = twin(L.pt1, f.plane[i], gm.plane[i], f.plane_mip[i], gm.plane_mip[i]);
+        float* lm0 = twin(L.lt0, f.line[i], gm.line[i], f.line_mip[i], gm.line_mip[i]);
+        float* lm1 = twin(L.lt1, f.line[i], gm.line[i], f.line_mip[i], gm.line_mip[i]);
+        const float* dcol = dA + g * 4;
+        auto drow = [&](int r) { return *reinterpret_cast<const float4*>(dcol + (size_t)r * ld); };
+        const int r_m0 = r0 + 1 + 2 * a.m0, r_m1 = r0 + 1 + 2 * a.m1, r_vm = r0 + 1 + 2 * a.vm;
+        const LinePos<TWO> l0 = line_pos<TWO>(L, k.lv[0]);
+        const PlanePos<TWO> p0 = plane_pos<TWO>(L, k.pu[0], k.pv[0]);
+        const float4 L0 = fetch_line<TWO>(L, l0, C, c), P0 = fetch_plane<TWO>(L, p0, C, c);
+        const float4 d0 = drow(r0);
+        // plane gradient at the centre position: centre and +-vm queries share it
+        float4 dP = f4_mul(d0, L0);
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+            const LinePos<TWO> lp = line_pos<TWO>(L, k.lv[1 + v]);
+            const float4 dv = drow(r_vm + v);
+            dP = f4_fma4(dv, fetch_line<TWO>(L, lp, C, c), dP);
+            scatter_line_pos<TWO>(lm0, lm1, L, lp, C, c, f4_mul(dv, P0));
+        }
+        scatter_plane_pos<TWO>(pm0, pm1, L, p0, C, c, dP);
+        // line gradient at the centre position: centre and the four in-plane queries share it
+        float4 dL = f4_mul(d0, P0);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const float pu = v == 0 ? k.pu[1] : (v == 1 ? k.pu[2] : k.pu[0]);
+            const float pv = v == 2 ? k.pv[1] : (v == 3 ? k.pv[2] : k.pv[0]);
+            const int r = v < 2 ? r_m0 + v : r_m1 + (v - 2);
+            const PlanePos<TWO> pp = plane_pos<TWO>(L, pu, pv);
+            const float4 d = drow(r);
+            dL = f4_fma4(d, fetch_plane<TWO>(L, pp, C, c), dL);
+            scatter_plane_pos<TWO>(pm0, pm1, L, pp, C, c, f4_mul(d, L0));
+        }
+        scatter_line_pos<TWO>(lm0, lm1, L, l0, C, c, dL);
+    }
+}
+__device__ __forceinline__ void scatter_tile_lean(const tf_vm_field_t& f, const tf_vm_mut_t& gm, const float* __restrict__ xyz,
+                                                  const float* __restrict__ level, int64_t n_total, const float units[3], int64_t s_base,
+                                                  const float* dA, int ld, int nthreads, int tid0) {
+    if (level != nullptr && f.n_levels > 1) scatter_tile_lean_t<true>(f, gm, xyz, level, n_total, units, s_base, dA, ld, nthreads, tid0);
+    else scatter_tile_lean_t<false>(f, gm, xyz, level, n_total, units, s_base, dA, ld, nthreads, tid0);
 }
 
 }  // namespace site
