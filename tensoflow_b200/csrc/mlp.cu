@@ -163,12 +163,20 @@ __global__ void __launch_bounds__(256) xty_kernel(const float* __restrict__ X, i
 }
 
 // column sums: out[c] += sum_r X[r][c]
+// (threads along the columns: coalesced rows; 8 independent loads in flight per thread, the kernel is HBM-bound)
 __global__ void colsum_kernel(const float* __restrict__ X, int ldx, int64_t rows, int cols, float* __restrict__ out) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= cols) return;
-    float acc = 0.f;
-    for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) acc += X[r * ldx + c];
-    if (acc != 0.f) atomicAdd(out + c, acc);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const int64_t stride = gridDim.y;
+    int64_t r = blockIdx.y;
+    for (; r + 7 * stride < rows; r += 8 * stride) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[u] += __ldg(X + (r + u * stride) * ldx + c);
+    }
+    for (; r < rows; r += stride) acc[0] += __ldg(X + r * ldx + c);
+    const float t = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+    if (t != 0.f) atomicAdd(out + c, t);
 }
 
 }  // namespace
@@ -201,7 +209,7 @@ int tf_internal_matmul(const float* A, int lda, const float* W, int ldw, int64_t
 
 int tf_internal_colsum(const float* X, int ldx, int64_t rows, int cols, float* out, cudaStream_t stream) {
     if (rows == 0 || cols == 0) return 0;
-    int gy = (int)(rows < 256 ? rows : 256);
+    int gy = (int)(rows < 1184 ? rows : 1184);          // 8 x 148 row slices
     dim3 cg((cols + 127) / 128, gy);
     colsum_kernel<<<cg, 128, 0, stream>>>(X, ldx, rows, cols, out);
     tf_count_launches(1);

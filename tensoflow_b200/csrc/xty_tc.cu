@@ -15,9 +15,9 @@
 
 namespace {
 
-constexpr int RS = 32;                        // rows (GEMM K) per stage
+// RS = rows (GEMM K) per stage: 32, or 16 when both operands are 256 wide (shared-memory budget)
 constexpr int NTH = 256;
-constexpr uint32_t SBO = (RS / 4) * 128 + 16;   // 8-row-group stride of a staged operand (padded: bank spread)
+template <int RS> struct Stage { static constexpr uint32_t SBO = (RS / 4) * 128 + 16; };   // 8-row-group stride of a staged operand (padded: bank spread)
 
 __device__ __forceinline__ float4 hi4(float4 v) { return make_float4(tc::tf32_rn(v.x), tc::tf32_rn(v.y), tc::tf32_rn(v.z), tc::tf32_rn(v.w)); }
 __device__ __forceinline__ float4 lo4(float4 v, float4 h) {
@@ -31,7 +31,9 @@ struct Prefetch { float4 v[2][4]; };
 // per-thread staging plan of one operand (fixed for the whole kernel: only the row base advances)
 struct StagePlan { int src_off[2]; int row[2]; uint32_t smem_off[2]; bool on[2]; };
 
+template <int RS>
 __device__ __forceinline__ StagePlan make_stage_plan(int W) {
+    constexpr uint32_t SBO = Stage<RS>::SBO;
     StagePlan p;
     const int G = W / 4, n_tasks = (RS / 4) * G;
 #pragma unroll
@@ -76,9 +78,11 @@ __device__ __forceinline__ void stage_store(const Prefetch& pf, const StagePlan&
 // D[i][j] = sum_r X[r][i] Y[r][j]: X (width M, a multiple of 4; padded to MP = 128 or 256 MMA rows) is the MMA M side,
 // Y (width N, a multiple of 16) the MMA N side.  An SS-mode tf32 MMA costs ~130 cycles whatever its N (the 4 KB A-operand
 // read), so the host puts the wider operand on the N side; `tr` then writes the result transposed.
+template <int RS>
 __global__ void __launch_bounds__(NTH, 1) xty_tc_kernel(const float* __restrict__ X, const float* __restrict__ Y, int64_t rows, int M, int MP, int N,
                                                         float* __restrict__ out, int ldo, int x_valid, int y_valid, int tr, int64_t rows_per_cta) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    constexpr uint32_t SBO = Stage<RS>::SBO;
     const uint32_t x_part = (uint32_t)(MP / 8) * SBO, y_part = (uint32_t)(N / 8) * SBO;
     const uint32_t stage_bytes = 2 * (x_part + y_part);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * stage_bytes);
@@ -106,7 +110,7 @@ __global__ void __launch_bounds__(NTH, 1) xty_tc_kernel(const float* __restrict_
 
     // register prefetch two stages ahead: sets (px0, py0) / (px1, py1) alternate
     Prefetch px0, py0, px1, py1;
-    const StagePlan spx = make_stage_plan(M), spy = make_stage_plan(N);
+    const StagePlan spx = make_stage_plan<RS>(M), spy = make_stage_plan<RS>(N);
     if (n_stages > 0) { stage_load(X, r_begin, r_end, M, spx, px0); stage_load(Y, r_begin, r_end, N, spy, py0); }
     if (n_stages > 1) { stage_load(X, r_begin + RS, r_end, M, spx, px1); stage_load(Y, r_begin + RS, r_end, N, spy, py1); }
     auto do_stage = [&](int64_t it, Prefetch& px, Prefetch& py) {
@@ -172,7 +176,8 @@ __global__ void __launch_bounds__(NTH, 1) xty_tc_kernel(const float* __restrict_
     if (warp == 0) tc::tmem_dealloc<512>(tmem_base);
 }
 
-size_t xty_tc_smem(int MP, int N) { return (size_t)2 * 2 * ((MP / 8) + (N / 8)) * SBO + 64; }
+size_t xty_tc_smem(int MP, int N, int rs) { return (size_t)2 * 2 * ((MP / 8) + (N / 8)) * ((rs / 4) * 128 + 16) + 64; }
+int xty_tc_stage_rows(int MP, int N) { return xty_tc_smem(MP, N, 32) <= 227 * 1024 ? 32 : 16; }
 
 }  // namespace
 
@@ -181,7 +186,7 @@ bool tf_internal_xty_tc_ok(const float* X, const float* Y, int M, int N) {
     if (M % 16 != 0 || N % 16 != 0 || M < 16 || N < 16 || M > 256 || N > 256) return false;
     if (((uintptr_t)X & 15) || ((uintptr_t)Y & 15)) return false;
     const int mw = M > N ? N : M, nw = M > N ? M : N;
-    return xty_tc_smem((mw + 127) / 128 * 128, nw) <= 227 * 1024;
+    return xty_tc_smem((mw + 127) / 128 * 128, nw, 16) <= 227 * 1024;
 }
 
 // X [rows][M] (ld = M), Y [rows][N] (ld = N); out[m][n] (ld = ldo) += X^T Y for n < n_valid
@@ -194,8 +199,8 @@ int tf_internal_xty_tc(const float* X, const float* Y, int64_t rows, int M, int 
     const int mw = tr ? N : M, nw = tr ? M : N;
     const int mp = (mw + 127) / 128 * 128;
     const int x_valid = tr ? n_valid : M, y_valid = tr ? M : n_valid;
-    const size_t smem = xty_tc_smem(mp, nw);
-    cudaFuncSetAttribute(xty_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int RS = xty_tc_stage_rows(mp, nw);
+    const size_t smem = xty_tc_smem(mp, nw, RS);
     int64_t grid = (rows + 4 * RS - 1) / (4 * RS);
     if (grid > tf_num_sms()) grid = tf_num_sms();
     int64_t rpc = (rows + grid - 1) / grid;
@@ -203,7 +208,13 @@ int tf_internal_xty_tc(const float* X, const float* Y, int64_t rows, int M, int 
     grid = (rows + rpc - 1) / rpc;
     {
         TfKernelTimer timer("xty_tc", stream);
-        xty_tc_kernel<<<(int)grid, NTH, smem, stream>>>(xs, ys, rows, mw, mp, nw, out, ldo, x_valid, y_valid, tr ? 1 : 0, rpc);
+        if (RS == 32) {
+            cudaFuncSetAttribute(xty_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            xty_tc_kernel<32><<<(int)grid, NTH, smem, stream>>>(xs, ys, rows, mw, mp, nw, out, ldo, x_valid, y_valid, tr ? 1 : 0, rpc);
+        } else {
+            cudaFuncSetAttribute(xty_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            xty_tc_kernel<16><<<(int)grid, NTH, smem, stream>>>(xs, ys, rows, mw, mp, nw, out, ldo, x_valid, y_valid, tr ? 1 : 0, rpc);
+        }
     }
     tf_count_launches(1);
     return 0;

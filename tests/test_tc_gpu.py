@@ -37,7 +37,7 @@ def test_tcgen05_gemm_matches_fp64(N, K):
     assert e3 < 2e-6, e3          # split: fp32 level
 
 
-@pytest.mark.parametrize("rows,M,N", [(1000, 256, 112), (4099, 128, 256), (31, 128, 16), (20000, 256, 64)])
+@pytest.mark.parametrize("rows,M,N", [(1000, 256, 112), (4099, 128, 256), (31, 128, 16), (20000, 256, 64), (9000, 256, 256), (5000, 48, 240)])
 def test_xty_tensor_core_matches_fp64(rows, M, N):
     """dW = X^T Y on tcgen05 with MN-major operands straight from row-major HBM tensors."""
     if not torch.cuda.is_available():
