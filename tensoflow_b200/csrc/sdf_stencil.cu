@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(NT, 2) sdf_stencil_fwd_kernel(StencilParams p)
 // Per tile: regather A, recompute hidden chunk by chunk, form dPre, accumulate
 // dA = dPre . W0 in registers, then scatter dA into the plane/line gradients.
 // dPre, A and the centre hidden activations are streamed to the workspace for the
-// weight-gradient GEMMs (xty_kernel below).
+// weight-gradient GEMMs (tf_internal_xty, mlp.cu).
 constexpr int DSS = NC + 4;   // row stride of the dPre chunk tile (float4 aligned)
 
 __global__ void __launch_bounds__(NT, 1) sdf_stencil_bwd_kernel(StencilParams p) {
@@ -442,89 +442,6 @@ __global__ void __launch_bounds__(NT, 1) sdf_stencil_bwd_kernel(StencilParams p)
         if (accw1[i] != 0.f) atomicAdd(p.dW1r0 + i, accw1[i]);
     }
     if (threadIdx.x == 0 && accb1[0] != 0.f) atomicAdd(p.db1, accb1[0]);
-}
-
-// ---- weight-gradient GEMM: out[m][n] (ld = ldo) += sum_r X[r][m] * Y[r][n] ---------------
-// X [rows][ldx], Y [rows][ldy]; CTA computes a [128][<=128] output tile over a slice of rows
-// with 8x8 register tiles and adds it to `out` with atomics (few CTAs per tile).
-constexpr int XT_M = 128, XT_N = 128, XT_R = 16;
-__global__ void __launch_bounds__(256) xty_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ Y, int ldy,
-                                                  int64_t rows, int M, int N, float* __restrict__ out, int ldo,
-                                                  int64_t rows_per_cta) {
-    __shared__ __align__(16) float Xs[XT_R][XT_M];
-    __shared__ __align__(16) float Ys[XT_R][XT_N];
-    const int m0 = blockIdx.x * XT_M, n0 = blockIdx.y * XT_N;
-    const int64_t r_begin = (int64_t)blockIdx.z * rows_per_cta;
-    const int64_t r_end = r_begin + rows_per_cta < rows ? r_begin + rows_per_cta : rows;
-    const int ty = threadIdx.x / 16, tx = threadIdx.x % 16;
-    float acc[8][8];
-#pragma unroll
-    for (int a = 0; a < 8; ++a)
-#pragma unroll
-        for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
-    for (int64_t r0 = r_begin; r0 < r_end; r0 += XT_R) {
-        for (int i = threadIdx.x; i < XT_R * (XT_M / 4); i += 256) {
-            const int rr = i / (XT_M / 4), m = (i % (XT_M / 4)) * 4;
-            float4 v = f4_zero();
-            if (r0 + rr < r_end && m0 + m < M) v = ldg4(X + (size_t)(r0 + rr) * ldx + m0 + m);
-            *reinterpret_cast<float4*>(&Xs[rr][m]) = v;
-        }
-        for (int i = threadIdx.x; i < XT_R * (XT_N / 4); i += 256) {
-            const int rr = i / (XT_N / 4), nn = (i % (XT_N / 4)) * 4;
-            float4 v = f4_zero();
-            if (r0 + rr < r_end && n0 + nn < N) v = ldg4(Y + (size_t)(r0 + rr) * ldy + n0 + nn);
-            *reinterpret_cast<float4*>(&Ys[rr][nn]) = v;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int rr = 0; rr < XT_R; ++rr) {
-            const float4 xa = *reinterpret_cast<const float4*>(&Xs[rr][ty * 4]);
-            const float4 xb = *reinterpret_cast<const float4*>(&Xs[rr][64 + ty * 4]);
-            const float4 ya = *reinterpret_cast<const float4*>(&Ys[rr][tx * 4]);
-            const float4 yb = *reinterpret_cast<const float4*>(&Ys[rr][64 + tx * 4]);
-            const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
-            const float yv[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
-#pragma unroll
-            for (int a = 0; a < 8; ++a)
-#pragma unroll
-                for (int b = 0; b < 8; ++b) acc[a][b] = fmaf(xv[a], yv[b], acc[a][b]);
-        }
-        __syncthreads();
-    }
-#pragma unroll
-    for (int a = 0; a < 8; ++a) {
-        const int m = m0 + (a < 4 ? ty * 4 + a : 64 + ty * 4 + a - 4);
-        if (m >= M) continue;
-#pragma unroll
-        for (int b = 0; b < 8; ++b) {
-            const int nn = n0 + (b < 4 ? tx * 4 + b : 64 + tx * 4 + b - 4);
-            if (nn < N && acc[a][b] != 0.f) atomicAdd(out + (size_t)m * ldo + nn, acc[a][b]);
-        }
-    }
-}
-
-// column sums: out[c] += sum_r X[r][c]
-__global__ void colsum_kernel(const float* __restrict__ X, int64_t rows, int cols, float* __restrict__ out) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= cols) return;
-    float acc = 0.f;
-    for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) acc += X[r * cols + c];
-    if (acc != 0.f) atomicAdd(out + c, acc);
-}
-
-int launch_xty(const float* X, int ldx, const float* Y, int ldy, int64_t rows, int M, int N, float* out, int ldo,
-               cudaStream_t stream) {
-    if (rows == 0) return 0;
-    dim3 grid((M + XT_M - 1) / XT_M, (N + XT_N - 1) / XT_N, 1);
-    const int tiles = grid.x * grid.y;
-    int64_t slices = (2 * (int64_t)tf_num_sms() + tiles - 1) / tiles;
-    int64_t rpc = (rows + slices - 1) / slices;
-    rpc = ((rpc + XT_R - 1) / XT_R) * XT_R;
-    if (rpc < 256) rpc = 256;
-    grid.z = (unsigned)((rows + rpc - 1) / rpc);
-    xty_kernel<<<grid, 256, 0, stream>>>(X, ldx, Y, ldy, rows, M, N, out, ldo, rpc);
-    tf_count_launches(1);
-    return 0;
 }
 
 struct Dims { int C, K, KP, KS, H, A; };
@@ -809,13 +726,11 @@ extern "C" TF_API int tf_sdf_stencil_bwd(const tf_vm_field_t* f, const tf_sdf_ml
         sdf_stencil_bwd_kernel<<<grid, NT, smem, stream>>>(q);
         tf_count_launches(1);
         // dW0[h][k] += sum_rows dPre[row][h] * A[row][k]
-        launch_xty(dpre, d.H, arow, d.KP, nt * R, d.H, d.K, g_mlp->W0, d.K, stream);
+        tf_internal_xty(dpre, d.H, arow, d.KP, nt * R, d.H, d.K, g_mlp->W0, d.K, stream);
         if (g_feat) {
             // dW1[1+o][h] += sum_n g_feat[n][o] * softplus(hidden_centre)[n][h];  db1[1+o] += sum_n g_feat[n][o]
-            launch_xty(q.g_feat, d.A, spc, d.H, ns, d.A, d.H, g_mlp->W1 + d.H, d.H, stream);
-            dim3 cg((d.A + 127) / 128, 64);
-            colsum_kernel<<<cg, 128, 0, stream>>>(q.g_feat, ns, d.A, g_mlp->b1 + 1);
-            tf_count_launches(1);
+            tf_internal_xty(q.g_feat, d.A, spc, d.H, ns, d.A, d.H, g_mlp->W1 + d.H, d.H, stream);
+            tf_internal_colsum(q.g_feat, d.A, ns, d.A, g_mlp->b1 + 1, stream);
         }
     }
     TF_CHECK_LAUNCH("tf_sdf_stencil_bwd");
