@@ -84,6 +84,20 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def profiled_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the committed `ncu --set full` summary
+    (profiles/r1_<kernel>_ncu_full_summary.txt; the capture's launch is one 4 GiB-workspace slice, the same size as the bench's)."""
+    path = os.path.join(ROOT, "profiles", f"r1_{kernel.replace('sdf_', '')}_ncu_full_summary.txt")
+    if not os.path.exists(path):
+        return None
+    tot, scale = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    for line in open(path):
+        f = line.split()
+        if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and f[2] in scale:
+            tot += float(f[1]) * scale[f[2]]
+    return tot or None
+
+
 def shape_algorithmic(cfg, n_samples, n_rays):
     """algorithmic bytes and decoder FLOPs of one shape-stage step."""
     C, H, A, G, L = cfg["C"], cfg["H"], cfg["A"], cfg["G"], cfg["L"]
@@ -317,7 +331,8 @@ def run_ours(args):
         flops = fwd_flops * (2 if "bwd" in dom else 1) if "stencil" in dom else 0
         ach = flops / (per_step_ms / 1e3) / 1e12
         roof = {"bound": "tensor", "kernel": dom + "_kernel", "achieved": ach, "peak": pk["tf"], "unit": "TFLOP/s", "frac": ach / pk["tf"],
-                "traffic": None, "peak_source": f"{pk['src']} dense bf16 sustained (cuBLAS)",
+                "traffic": profiled_traffic(dom), "traffic_unit": "bytes per launch (dram read + write, ncu --set full, profiles/)",
+                "peak_source": f"{pk['src']} dense bf16 sustained (cuBLAS)",
                 "ms_per_launch": dom_ms / max(dom_n, 1), "launches_per_step": dom_n / args.steps, "ms_per_step": per_step_ms,
                 "share_of_step": dom_ms / ms,
                 "note": ("achieved = algorithmic fp32 decoder FLOPs of the step's samples / the kernel's summed launch time; the MMAs run "

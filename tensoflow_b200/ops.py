@@ -13,7 +13,7 @@ import torch
 from . import _lib
 from ._lib import VMField, VMMut, SdfMlp, SdfMlpGrad, check, ptr, stream_ptr
 
-BWD_WORKSPACE_BYTES = 4 << 30   # upper bound for the stencil-backward scratch
+BWD_WORKSPACE_BYTES = int(__import__('os').environ.get('TF_BWD_WORKSPACE_GIB', '4')) << 30   # upper bound for the stencil-backward scratch
 
 
 class KernelTimers:
