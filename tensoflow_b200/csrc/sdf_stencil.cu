@@ -588,7 +588,8 @@ int tf_internal_bwd_tc_fold(const float* tmp, int H, int K, int KT, float* dW0, 
 int tf_internal_stencil_bwd_tc(const tf_vm_field_t* f, const tf_vm_mut_t* g, const tf_sdf_mlp_t* m, const float* wtc, const float* xyz,
                                const float* level, int64_t n, const float units[3], const float* sdf7, const float* g_sdf,
                                const float* g_grad, const float* g_hess, const float* dHc, float* dpre, float* arow, float* spc,
-                               float* dW1r0, float* db1, cudaStream_t stream);
+                               float* da_scratch, float* dW1r0, float* db1, cudaStream_t stream);
+size_t tf_internal_bwd_tc_scratch_floats(int KT);
 int tf_internal_xty(const float* X, int ldx, const float* Y, int ldy, int64_t rows, int M, int N, float* out, int ldo, cudaStream_t stream);
 int tf_internal_colsum(const float* X, int ldx, int64_t rows, int cols, float* out, cudaStream_t stream);
 int tf_internal_matmul(const float* A, int lda, const float* W, int ldw, int64_t M, int Kred, int Nout, float* out, int ldo,
@@ -604,7 +605,8 @@ static bool use_simt_bwd(const Dims& d) {
 // centre hidden [18,H], dHidden(centre) [18,H]]
 static size_t bwd_tc_fixed_floats(const Dims& d) {
     const int KT = (d.K + 15) / 16 * 16;
-    return tf_internal_bwd_tc_wtc_floats(KT, d.H) + (size_t)d.H * KT + tf_internal_linear_tc_ws_floats(d.A, d.H);
+    return tf_internal_bwd_tc_wtc_floats(KT, d.H) + (size_t)d.H * KT + tf_internal_linear_tc_ws_floats(d.A, d.H) +
+           tf_internal_bwd_tc_scratch_floats(KT);
 }
 static size_t bwd_tc_tile_floats(const Dims& d) {
     const int KT = (d.K + 15) / 16 * 16, spt = tf_internal_bwd_tc_samples_per_tile();
@@ -636,7 +638,8 @@ static int stencil_bwd_tc(const tf_vm_field_t* f, const tf_sdf_mlp_t* m, const D
     float* wtc = ws;
     float* tmp = wtc + tf_internal_bwd_tc_wtc_floats(KT, H);
     float* wlin = tmp + (size_t)H * KT;
-    float* dpre = wlin + tf_internal_linear_tc_ws_floats(d.A, H);
+    float* da_scratch = wlin + tf_internal_linear_tc_ws_floats(d.A, H);
+    float* dpre = da_scratch + tf_internal_bwd_tc_scratch_floats(KT);
     float* arow = dpre + (size_t)tiles_fit * 128 * H;
     float* spc = arow + (size_t)tiles_fit * 128 * KT;
     float* dHc = spc + (size_t)tiles_fit * spt * H;
@@ -655,7 +658,7 @@ static int stencil_bwd_tc(const tf_vm_field_t* f, const tf_sdf_mlp_t* m, const D
         if (int e = tf_internal_stencil_bwd_tc(f, g_field, m, wtc, xyz + s0 * 3, level ? level + s0 : nullptr, ns, units, sdf7 + s0 * NQ,
                                                g_sdf ? g_sdf + s0 : nullptr, g_grad ? g_grad + s0 * 3 : nullptr,
                                                g_hess ? g_hess + s0 : nullptr, gf ? dHc : nullptr, dpre, arow, gf ? spc : nullptr,
-                                               g_mlp->W1, g_mlp->b1, stream))
+                                               da_scratch, g_mlp->W1, g_mlp->b1, stream))
             return e;
         // [dW0 | db0] staging += dPre^T [A | 1]
         if (tf_internal_xty_tc_ok(dpre, arow, H, KT)) tf_internal_xty_tc(dpre, arow, nt * 128, H, KT, tmp, KT, d.K + 1, stream);

@@ -22,8 +22,8 @@ namespace {
 constexpr int TM = 128;
 constexpr int NQ7 = 7;
 constexpr int KSL = 16;     // KT granularity (shared with the forward kernel)
-constexpr int KS1 = 8;      // K slice of GEMM1 streamed per ring slot
-constexpr int HHC = 16;     // hidden units of a W0^T ring slot (half a chunk)
+constexpr int KS1 = 16;     // K slice of GEMM1 streamed per ring slot
+constexpr int HHC = 32;     // hidden units of a W0^T ring slot (a whole chunk)
 constexpr int HCH = 32;     // hidden chunk of epilogue-1 / GEMM-dA
 constexpr int NST = 2;
 constexpr int NGRP = 256;             // threads per group
@@ -40,6 +40,7 @@ struct TcBwdParams {
     const float* dHc;        // [n][H] = g_feat . W1[1:,:]  (NULL when there is no feature gradient)
     int K, KT, H, slot_floats;
     float units[3];
+    float* da_scratch;       // [gridDim][128][KT+4]: dA tiles handed from the math to the memory group through L2
     float* dpre;             // [tiles*128][H]
     float* arow;             // [tiles*128][KT]
     float* spc;              // [n][H] centre hidden activations (NULL = not needed)
@@ -95,15 +96,16 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 
 __global__ void __launch_bounds__(NTH, 1) sdf_stencil_bwd_tc_kernel(TcBwdParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const int H = p.H, KT = p.KT, S = KT / KS1, NCH = H / HCH, J = S + 2 * NCH;
+    const int H = p.H, KT = p.KT, S = KT / KS1, NCH = H / HCH, J = S + H / HHC;
     constexpr int SPT = site::SPT;
     const uint32_t a_part = site::a_part_bytes(KT);
     const uint32_t slot_bytes = (uint32_t)p.slot_floats * 4;
     const int DAS = KT + 4;                                        // row stride of the dA tile
     uint8_t* a_hi = smem;
     uint8_t* a_lo = a_hi + a_part;
-    float* dAs = reinterpret_cast<float*>(a_lo + a_part);          // [TM][DAS] fp32, math group -> memory group
-    uint8_t* wst = reinterpret_cast<uint8_t*>(dAs + (size_t)TM * DAS);
+    float* dAs = p.da_scratch + (size_t)blockIdx.x * TM * DAS;     // [TM][DAS] fp32, math group -> memory group (global / L2:
+                                                                   // shared memory goes to the A operand and a deep weight ring)
+    uint8_t* wst = a_lo + a_part;
     float* b0s = reinterpret_cast<float*>(wst + (size_t)NST * slot_bytes);
     float* w1s = b0s + H;
     float* accw1 = w1s + H;                                        // per-CTA dW1[0,:]
@@ -154,14 +156,14 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_bwd_tc_kernel(TcBwdParams 
             if (lt > 0) {
                 tc::mbar_wait(daready, (uint32_t)((lt - 1) & 1));
                 if (!(p.debug & 4))
-                    site::scatter_tile_lean(p.f, p.g, p.xyz, p.level, p.n, p.units, (blockIdx.x + (lt - 1) * gridDim.x) * SPT, dAs, DAS, NGRP, mtid);
+                    site::scatter_tile_lean(p.f, p.g, p.xyz, p.level, p.n, p.units, (blockIdx.x + (lt - 1) * gridDim.x) * SPT, dAs, DAS, NGRP, mtid, true);
                 tc::mbar_arrive(dafree);
             }
         }
         if (my_tiles > 0) {
             tc::mbar_wait(daready, (uint32_t)((my_tiles - 1) & 1));
             if (!(p.debug & 4))
-                site::scatter_tile_lean(p.f, p.g, p.xyz, p.level, p.n, p.units, (blockIdx.x + (my_tiles - 1) * gridDim.x) * SPT, dAs, DAS, NGRP, mtid);
+                site::scatter_tile_lean(p.f, p.g, p.xyz, p.level, p.n, p.units, (blockIdx.x + (my_tiles - 1) * gridDim.x) * SPT, dAs, DAS, NGRP, mtid, true);
         }
     } else {
         // ======================= math group: GEMM1, chunked dPre epilogue, GEMM-dA ======================================
@@ -241,11 +243,16 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_bwd_tc_kernel(TcBwdParams 
                     tc::mbar_wait(&full[st], (uint32_t)((g_mma / NST) & 1));
                     tc::fence_after_sync();
                     const uint32_t w_hi = tc::smem_u32(wst + (size_t)st * slot_bytes);
-                    const uint64_t wdh = tc::make_smem_desc(w_hi, 128, w1_sbo), wdl = tc::make_smem_desc(w_hi + (uint32_t)H * KS1 * 4, 128, w1_sbo);
-                    const uint64_t adh = tc::desc_add(a_desc_hi, s * 2 * site::A_LBO), adl = tc::desc_add(a_desc_lo, s * 2 * site::A_LBO);
-                    tc::mma_tf32_ss(d1, adh, wdh, idesc1, s != 0);
-                    tc::mma_tf32_ss(d1, adh, wdl, idesc1, 1);
-                    tc::mma_tf32_ss(d1, adl, wdh, idesc1, 1);
+                    const uint64_t wdh0 = tc::make_smem_desc(w_hi, 128, w1_sbo), wdl0 = tc::make_smem_desc(w_hi + (uint32_t)H * KS1 * 4, 128, w1_sbo);
+#pragma unroll
+                    for (int ks = 0; ks < KS1 / 8; ++ks) {
+                        const uint32_t koff = (uint32_t)(s * (KS1 / 8) + ks) * 2 * site::A_LBO;
+                        const uint64_t adh = tc::desc_add(a_desc_hi, koff), adl = tc::desc_add(a_desc_lo, koff);
+                        const uint64_t wdh = tc::desc_add(wdh0, ks * 256), wdl = tc::desc_add(wdl0, ks * 256);
+                        tc::mma_tf32_ss(d1, adh, wdh, idesc1, (s | ks) != 0);
+                        tc::mma_tf32_ss(d1, adh, wdl, idesc1, 1);
+                        tc::mma_tf32_ss(d1, adl, wdh, idesc1, 1);
+                    }
                     tc::mma_commit(&empty[st]);
                     ++g_mma;
                 }
@@ -355,7 +362,7 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_bwd_tc_kernel(TcBwdParams 
             }
             if (p.debug & 16) {
                 if (tid == 0) {                         // timing experiments: the skipped slots still rotate through the ring
-                    for (int c = 0; c < 2 * NCH; ++c) {
+                    for (int c = 0; c < H / HHC; ++c) {
                         ring_prefetch();
                         const int st = (int)(g_mma % NST);
                         tc::mbar_wait(&full[st], (uint32_t)((g_mma / NST) & 1));
@@ -398,7 +405,7 @@ int tf_internal_bwd_tc_slot_floats(int KT, int H) {
 }
 size_t tf_internal_bwd_tc_wtc_floats(int KT, int H) { return (size_t)(KT / KS1 + H / HHC) * tf_internal_bwd_tc_slot_floats(KT, H); }
 size_t tf_internal_bwd_tc_smem(int KT, int H) {
-    return (size_t)2 * 16 * (KT / 4) * site::A_LBO + (size_t)TM * (KT + 4) * 4 + (size_t)NST * tf_internal_bwd_tc_slot_floats(KT, H) * 4 +
+    return (size_t)2 * 16 * (KT / 4) * site::A_LBO + (size_t)NST * tf_internal_bwd_tc_slot_floats(KT, H) * 4 +
            (size_t)3 * H * 4 + (size_t)TM * 4 + (2 * NST + 9) * 8 + 32;
 }
 
@@ -415,12 +422,13 @@ int tf_internal_bwd_tc_fold(const float* tmp, int H, int K, int KT, float* dW0, 
 }
 
 int tf_internal_bwd_tc_samples_per_tile() { return site::SPT; }
+size_t tf_internal_bwd_tc_scratch_floats(int KT) { return (size_t)tf_num_sms() * TM * (KT + 4); }
 
 // one slice of samples (n <= workspace capacity): activation-side backward
 int tf_internal_stencil_bwd_tc(const tf_vm_field_t* f, const tf_vm_mut_t* g, const tf_sdf_mlp_t* m, const float* wtc, const float* xyz,
                                const float* level, int64_t n, const float units[3], const float* sdf7, const float* g_sdf,
                                const float* g_grad, const float* g_hess, const float* dHc, float* dpre, float* arow, float* spc,
-                               float* dW1r0, float* db1, cudaStream_t stream) {
+                               float* da_scratch, float* dW1r0, float* db1, cudaStream_t stream) {
     const int C = f->n_comp, K = 3 * C + 3, KT = (K + KSL - 1) / KSL * KSL, H = m->hidden;
     TcBwdParams p = {};
     p.f = *f; p.g = *g; p.xyz = xyz; p.level = level; p.n = n;
@@ -428,7 +436,7 @@ int tf_internal_stencil_bwd_tc(const tf_vm_field_t* f, const tf_vm_mut_t* g, con
     p.sdf7 = sdf7; p.g_sdf = g_sdf; p.g_grad = g_grad; p.g_hess = g_hess; p.dHc = dHc;
     p.K = K; p.KT = KT; p.H = H; p.slot_floats = tf_internal_bwd_tc_slot_floats(KT, H);
     for (int k = 0; k < 3; ++k) p.units[k] = units[k];
-    p.dpre = dpre; p.arow = arow; p.spc = spc; p.dW1r0 = dW1r0; p.db1 = db1;
+    p.dpre = dpre; p.arow = arow; p.spc = spc; p.da_scratch = da_scratch; p.dW1r0 = dW1r0; p.db1 = db1;
     { const char* e = getenv("TF_TC_BWD_DEBUG"); p.debug = e ? atoi(e) : 0; }
     const size_t smem = tf_internal_bwd_tc_smem(KT, H);
     cudaFuncSetAttribute(sdf_stencil_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -471,10 +471,11 @@ __device__ __forceinline__ void gather_tile_lean(const tf_vm_field_t& f, const f
     else gather_tile_lean_t<false>(f, xyz, level, n_total, units, s_base, KT, a_hi, a_lo, arow, nthreads, tid0);
 }
 
+// dA may live in shared memory or in a global scratch tile written by other warps of the same CTA (read with ld.global.cg)
 template <bool TWO>
 __device__ __forceinline__ void scatter_tile_lean_t(const tf_vm_field_t& f, const tf_vm_mut_t& gm, const float* __restrict__ xyz,
                                                     const float* __restrict__ level, int64_t n_total, const float units[3], int64_t s_base,
-                                                    const float* dA, int ld, int nthreads, int tid0) {
+                                                    const float* dA, int ld, int nthreads, int tid0, bool da_global) {
     const int C = f.n_comp, C4 = C / 4;
     const bool has_level = level != nullptr;
     const int n_tasks = SPT * 3 * C4;
@@ -492,7 +493,10 @@ __device__ __forceinline__ void scatter_tile_lean_t(const tf_vm_field_t& f, cons
         float* lm0 = twin(L.lt0, f.line[i], gm.line[i], f.line_mip[i], gm.line_mip[i]);
         float* lm1 = twin(L.lt1, f.line[i], gm.line[i], f.line_mip[i], gm.line_mip[i]);
         const float* dcol = dA + g * 4;
-        auto drow = [&](int r) { return *reinterpret_cast<const float4*>(dcol + (size_t)r * ld); };
+        auto drow = [&](int r) {
+            const float4* q = reinterpret_cast<const float4*>(dcol + (size_t)r * ld);
+            return da_global ? __ldcg(q) : *q;
+        };
         const int r_m0 = r0 + 1 + 2 * a.m0, r_m1 = r0 + 1 + 2 * a.m1, r_vm = r0 + 1 + 2 * a.vm;
         const LinePos<TWO> l0 = line_pos<TWO>(L, k.lv[0]);
         const PlanePos<TWO> p0 = plane_pos<TWO>(L, k.pu[0], k.pv[0]);
@@ -525,9 +529,9 @@ __device__ __forceinline__ void scatter_tile_lean_t(const tf_vm_field_t& f, cons
 }
 __device__ __forceinline__ void scatter_tile_lean(const tf_vm_field_t& f, const tf_vm_mut_t& gm, const float* __restrict__ xyz,
                                                   const float* __restrict__ level, int64_t n_total, const float units[3], int64_t s_base,
-                                                  const float* dA, int ld, int nthreads, int tid0) {
-    if (level != nullptr && f.n_levels > 1) scatter_tile_lean_t<true>(f, gm, xyz, level, n_total, units, s_base, dA, ld, nthreads, tid0);
-    else scatter_tile_lean_t<false>(f, gm, xyz, level, n_total, units, s_base, dA, ld, nthreads, tid0);
+                                                  const float* dA, int ld, int nthreads, int tid0, bool da_global = false) {
+    if (level != nullptr && f.n_levels > 1) scatter_tile_lean_t<true>(f, gm, xyz, level, n_total, units, s_base, dA, ld, nthreads, tid0, da_global);
+    else scatter_tile_lean_t<false>(f, gm, xyz, level, n_total, units, s_base, dA, ld, nthreads, tid0, da_global);
 }
 
 }  // namespace site
