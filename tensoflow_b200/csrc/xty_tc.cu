@@ -16,7 +16,8 @@
 namespace {
 
 // RS = rows (GEMM K) per stage: 32, or 16 when both operands are 256 wide (shared-memory budget)
-constexpr int NTH = 256;
+constexpr int NTH = 512;
+constexpr int TPT = (8 * 64 + NTH - 1) / NTH;   // staging tasks per thread and operand (32 rows x 256 columns at most)
 template <int RS> struct Stage { static constexpr uint32_t SBO = (RS / 4) * 128 + 16; };   // 8-row-group stride of a staged operand (padded: bank spread)
 
 __device__ __forceinline__ float4 hi4(float4 v) { return make_float4(tc::tf32_rn(v.x), tc::tf32_rn(v.y), tc::tf32_rn(v.z), tc::tf32_rn(v.w)); }
@@ -27,9 +28,9 @@ __device__ __forceinline__ float4 lo4(float4 v, float4 h) {
 // One staging task = the 4x4 block (rows 4c..4c+3, columns 4g..4g+3) of src [rows][W]; a thread owns up to
 // 2 tasks per operand and stage.  The global loads of stage it+1 are issued into registers before stage it is
 // converted and stored, so HBM latency overlaps the staging and MMA work.
-struct Prefetch { float4 v[2][4]; };
+struct Prefetch { float4 v[TPT][4]; };
 // per-thread staging plan of one operand (fixed for the whole kernel: only the row base advances)
-struct StagePlan { int src_off[2]; int row[2]; uint32_t smem_off[2]; bool on[2]; };
+struct StagePlan { int src_off[TPT]; int row[TPT]; uint32_t smem_off[TPT]; bool on[TPT]; };
 
 template <int RS>
 __device__ __forceinline__ StagePlan make_stage_plan(int W) {
@@ -37,7 +38,7 @@ __device__ __forceinline__ StagePlan make_stage_plan(int W) {
     StagePlan p;
     const int G = W / 4, n_tasks = (RS / 4) * G;
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < TPT; ++k) {
         const int it = threadIdx.x + k * NTH;
         const int g = it % G, c = it / G;
         p.on[k] = it < n_tasks;
@@ -51,7 +52,7 @@ __device__ __forceinline__ StagePlan make_stage_plan(int W) {
 __device__ __forceinline__ void stage_load(const float* __restrict__ src, int64_t r0, int64_t r_end, int W, const StagePlan& sp, Prefetch& pf) {
     const float* base = src + (size_t)r0 * W;
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < TPT; ++k) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
             pf.v[k][i] = (sp.on[k] && r0 + sp.row[k] + i < r_end) ? ldg4(base + sp.src_off[k] + i * W) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -60,7 +61,7 @@ __device__ __forceinline__ void stage_load(const float* __restrict__ src, int64_
 // transpose the 4x4 blocks in registers (four 16-byte K-major units each), split into tf32 hi / lo, store
 __device__ __forceinline__ void stage_store(const Prefetch& pf, const StagePlan& sp, uint8_t* hi, uint8_t* lo) {
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < TPT; ++k) {
         if (!sp.on[k]) continue;
         const float4* v = pf.v[k];
         const float4 t[4] = {make_float4(v[0].x, v[1].x, v[2].x, v[3].x), make_float4(v[0].y, v[1].y, v[2].y, v[3].y),
@@ -161,7 +162,7 @@ __global__ void __launch_bounds__(NTH, 1) xty_tc_kernel(const float* __restrict_
         const int lq = warp & 3, half = warp >> 2;
         for (int mt = 0; mt < MT; ++mt) {
             const int m = mt * 128 + lq * 32 + lane;
-            for (int c0 = half * 16; c0 < N; c0 += 32) {
+            for (int c0 = half * 16; c0 < N; c0 += 16 * (NTH / 128)) {
                 float v[16];
                 tc::tmem_ld16(tmem_base + (uint32_t)mt * ncol_tile + ((uint32_t)(lq * 32) << 16) + c0, v);
 #pragma unroll
