@@ -20,7 +20,8 @@ namespace {
 constexpr int TM = 128;
 constexpr int KC = 32;                 // K chunk per pipeline stage
 constexpr int NSTG = 2;
-constexpr int NTH = 256;
+constexpr int NTH = 512;
+constexpr int XPT = 1024 / NTH;         // float4 loads per thread and stage (128 rows x 8 chunks)
 constexpr uint32_t X_LBO = 144;        // K-chunk (16 B) stride of the X operand, padded for bank spread
 constexpr uint32_t X_SBO = (KC / 4) * X_LBO;
 constexpr uint32_t X_PART = 16 * X_SBO;      // bytes of one X part (hi or lo) of a stage
@@ -50,14 +51,14 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar)), "r"(bytes) : "memory");
 }
 
-struct XRegs { float4 v[4]; };     // one stage of X per thread: 128 rows x 8 chunks = 1024 float4 / 256 threads
+struct XRegs { float4 v[XPT]; };     // one stage of X per thread: 128 rows x 8 chunks = 1024 float4 / 256 threads
 
 // one stage of the A operand: X[m][k0 .. k0+32) for the tile's 128 rows.  BWD: element = dY * act'(Y), also stored to dpre
 template <bool BWD>
 __device__ __forceinline__ void x_load(const float* __restrict__ X, const float* __restrict__ Yact, float* __restrict__ dpre, int act,
                                        float act_p, bool vec, int64_t M, int K, int64_t row0, int k0, XRegs& r) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < XPT; ++j) {
         const int it = threadIdx.x + j * NTH;
         const int row = it >> 3, ch = it & 7;
         const int64_t m = row0 + row;
@@ -88,7 +89,7 @@ __device__ __forceinline__ void x_load(const float* __restrict__ X, const float*
 }
 __device__ __forceinline__ void x_store(const XRegs& r, uint8_t* hi, uint8_t* lo) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < XPT; ++j) {
         const int it = threadIdx.x + j * NTH;
         const int row = it >> 3, ch = it & 7;
         const uint32_t off = (uint32_t)(row >> 3) * X_SBO + ch * X_LBO + (row & 7) * 16;
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(NTH, 1) linear_tc_kernel(const float* __restri
         const int lq = warp & 3, half = warp >> 2;
         const int64_t m = tile * TM + lq * 32 + lane;
         const uint32_t d = tmem_base + (uint32_t)j * cstride + ((uint32_t)(lq * 32) << 16);
-        for (int c0 = half * 16; c0 < NP; c0 += 32) {
+        for (int c0 = half * 16; c0 < NP; c0 += 16 * (NTH / 128)) {
             float v[16];
             tc::tmem_ld16(d + c0, v);
             if (m < M) {
