@@ -163,8 +163,8 @@ TF_API size_t tf_linear_workspace(int32_t K, int32_t N);
 TF_API int tf_linear_fwd(const float* X, const float* W, const float* b, int64_t M, int32_t K,
                          int32_t N, int32_t act, float act_param, float* Y, void* workspace,
                          size_t ws_bytes, tf_stream_t stream);
-/* dpre[M,N] = dY * act'(Y) (written; must not alias dY); dX[M,K] = dpre W (dX may be NULL);
- * dW[N,K] += dpre^T X and db[N] += colsum(dpre) (each may be NULL). */
+/* dpre[M,N] = dY * act'(Y) (scratch: written except by the fused narrow-layer path, K,N <= 64; must not alias dY);
+ * dX[M,K] = dpre W (dX may be NULL); dW[N,K] += dpre^T X and db[N] += colsum(dpre) (each may be NULL). */
 TF_API int tf_linear_bwd(const float* X, const float* W, const float* Y, const float* dY,
                          float* dpre, int64_t M, int32_t K, int32_t N, int32_t act,
                          float act_param, float* dX, float* dW, float* db, void* workspace,

@@ -179,6 +179,90 @@ __global__ void colsum_kernel(const float* __restrict__ X, int ldx, int64_t rows
     if (t != 0.f) atomicAdd(out + c, t);
 }
 
+// ---- narrow layers (K, N <= 64): the whole backward of one layer in one pass -----------------------------------
+// The coupling-layer conditioners (44 -> 64 -> 64 -> 64 -> 21 on 10^5..10^6 rows) are far below any GEMM roofline; what
+// they cost is HBM passes and launches.  One persistent kernel reads dY, Y, X once, forms dPre = dY * act'(Y) in shared
+// memory, writes dX = dPre W, and keeps the CTA's share of dW = dPre^T X and db in registers until the end.
+constexpr int SL_ROWS = 128, SL_MAX = 64, SL_DS = SL_MAX + 1, SL_XS = SL_MAX + 4;
+__global__ void __launch_bounds__(256, 2) small_linear_bwd_kernel(const float* __restrict__ X, const float* __restrict__ W, const float* __restrict__ Y,
+                                                                  const float* __restrict__ dY, int64_t M, int K, int N, int act, float act_p,
+                                                                  float* __restrict__ dX, float* __restrict__ dW, float* __restrict__ db) {
+    extern __shared__ __align__(16) float sl_smem[];
+    float* Ds = sl_smem;                         // [128][65]  dPre tile
+    float* Xs = Ds + SL_ROWS * SL_DS;            // [128][68]  X tile
+    float* Ws = Xs + SL_ROWS * SL_XS;            // [64][68]   W
+    const int tid = threadIdx.x;
+    for (int i = tid; i < SL_MAX * SL_XS; i += 256) {
+        const int n = i / SL_XS, k = i % SL_XS;
+        Ws[i] = (n < N && k < K) ? W[(size_t)n * K + k] : 0.f;
+    }
+    // dW / db ownership: thread -> (n = tid / 4, 16 consecutive k)
+    const int wn = tid >> 2, wk0 = (tid & 3) * 16;
+    float accw[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) accw[j] = 0.f;
+    float accb = 0.f;
+    // dX ownership: thread -> (row = tid / 2, 32 consecutive k)
+    const int xr = tid >> 1, xk0 = (tid & 1) * 32;
+    const int64_t ntiles = (M + SL_ROWS - 1) / SL_ROWS;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t r0 = t * SL_ROWS;
+        const int rows = (int)(M - r0 < SL_ROWS ? M - r0 : SL_ROWS);
+        __syncthreads();                         // previous tile fully consumed (also covers the W load)
+        for (int i = tid; i < SL_ROWS * N; i += 256) {
+            const int r = i / N, n = i % N;
+            float v = 0.f;
+            if (r < rows) { const size_t o = (size_t)(r0 + r) * N + n; v = __ldg(dY + o) * act_bwd(__ldg(Y + o), act, act_p); }
+            Ds[r * SL_DS + n] = v;
+        }
+        for (int i = tid; i < SL_ROWS * K; i += 256) {
+            const int r = i / K, k = i % K;
+            Xs[r * SL_XS + k] = r < rows ? __ldg(X + (size_t)(r0 + r) * K + k) : 0.f;
+        }
+        __syncthreads();
+        if (dX && xr < rows && xk0 < K) {
+            float acc[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+            for (int n = 0; n < N; ++n) {
+                const float d = Ds[xr * SL_DS + n];
+                const float4* w4 = reinterpret_cast<const float4*>(Ws + n * SL_XS + xk0);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 w = w4[j];
+                    acc[4 * j] = fmaf(d, w.x, acc[4 * j]); acc[4 * j + 1] = fmaf(d, w.y, acc[4 * j + 1]);
+                    acc[4 * j + 2] = fmaf(d, w.z, acc[4 * j + 2]); acc[4 * j + 3] = fmaf(d, w.w, acc[4 * j + 3]);
+                }
+            }
+            float* dst = dX + (size_t)(r0 + xr) * K + xk0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (xk0 + j < K) dst[j] = acc[j];
+        }
+        if (wn < N) {
+            for (int r = 0; r < rows; ++r) {
+                const float d = Ds[r * SL_DS + wn];
+                const float4* x4 = reinterpret_cast<const float4*>(Xs + r * SL_XS + wk0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 x = x4[j];
+                    accw[4 * j] = fmaf(d, x.x, accw[4 * j]); accw[4 * j + 1] = fmaf(d, x.y, accw[4 * j + 1]);
+                    accw[4 * j + 2] = fmaf(d, x.z, accw[4 * j + 2]); accw[4 * j + 3] = fmaf(d, x.w, accw[4 * j + 3]);
+                }
+                accb += d;
+            }
+        }
+    }
+    if (wn < N) {
+        if (dW) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (wk0 + j < K && accw[j] != 0.f) atomicAdd(dW + (size_t)wn * K + wk0 + j, accw[j]);
+        }
+        if (db && (tid & 3) == 0 && accb != 0.f) atomicAdd(db + wn, accb);
+    }
+}
+
 }  // namespace
 
 // internal entry points shared with the other translation units
@@ -264,6 +348,17 @@ extern "C" TF_API int tf_linear_bwd(const float* X, const float* W, const float*
     TF_REQUIRE(X && W && Y && dY && dpre && dY != dpre, "tf_linear_bwd: NULL pointer (or dY aliases dpre)");
     TF_REQUIRE(K > 0 && N > 0 && act >= 0 && act <= 5, "tf_linear_bwd: bad K/N/act (%d,%d,%d)", K, N, act);
     cudaStream_t stream = (cudaStream_t)stream_;
+    if (K <= SL_MAX && N <= SL_MAX && M >= 4096) {
+        // narrow layer: fused one-pass backward (dPre stays in shared memory; the `dpre` buffer is left untouched)
+        const size_t smem = sizeof(float) * ((size_t)SL_ROWS * SL_DS + (size_t)SL_ROWS * SL_XS + (size_t)SL_MAX * SL_XS);
+        cudaFuncSetAttribute(small_linear_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        const int64_t ntiles = (M + SL_ROWS - 1) / SL_ROWS;
+        const int grid = (int)(ntiles < 2 * tf_num_sms() ? ntiles : 2 * tf_num_sms());
+        small_linear_bwd_kernel<<<grid, 256, smem, stream>>>(X, W, Y, dY, M, K, N, act, act_param, dX, dW, db);
+        tf_count_launches(1);
+        TF_CHECK_LAUNCH("tf_linear_bwd (narrow)");
+        return 0;
+    }
     // dPre = dY * act'(Y) and dX = dPre W.  dX may be NULL (first layer): then a one-column
     // launch still materialises dPre.
     if (dX && workspace && tc_shape(M, K, N) && tf_internal_linear_tc_ok(dY, dX, N, K, act) && ((uintptr_t)workspace & 15) == 0 &&

@@ -61,9 +61,11 @@ def test_xty_tensor_core_matches_fp64(rows, M, N):
 
 
 @pytest.mark.parametrize("M,K,N,act", [(20000, 123, 256, "relu"), (9000, 256, 99, "exp"), (10000, 108, 128, "sigmoid"),
-                                       (8200, 256, 256, "relu"), (8192, 97, 101, "none"), (9000, 256, 3, "exp")])
+                                       (8200, 256, 256, "relu"), (8192, 97, 101, "none"), (9000, 256, 3, "exp"),
+                                       (10000, 44, 64, "leaky"), (5000, 64, 21, "none"), (4099, 57, 64, "leaky"), (9000, 16, 3, "sigmoid")])
 def test_linear_tensor_core_fwd_bwd(M, K, N, act):
-    """ops.linear on the tcgen05 path (M >= 8192): padded N, unaligned K, activation epilogue, data and weight gradients."""
+    """ops.linear on the tcgen05 path (M >= 8192, wide layers) and on the fused narrow-layer backward (K, N <= 64):
+    padded N, unaligned K, activation epilogue, data and weight gradients."""
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     from tensoflow_b200 import ops
@@ -82,7 +84,8 @@ def test_linear_tensor_core_fwd_bwd(M, K, N, act):
 
     def torch_fn(x, w, bb):
         z = x @ w.T + bb
-        return {"relu": torch.relu, "sigmoid": torch.sigmoid, "none": lambda t: t, "exp": lambda t: torch.exp(t.clamp(max=5.0))}[act](z)
+        return {"relu": torch.relu, "sigmoid": torch.sigmoid, "none": lambda t: t, "exp": lambda t: torch.exp(t.clamp(max=5.0)),
+                "leaky": lambda t: torch.nn.functional.leaky_relu(t, 0.01)}[act](z)
 
     ref = run(torch.float64, "cpu", torch_fn)
     f32 = run(torch.float32, "cpu", torch_fn)
