@@ -252,6 +252,16 @@ TF_API int tf_csr_spmm3_bwd(const int32_t* rowptr, const int32_t* col, const flo
 TF_API int tf_tc_probe(const float* A, const float* B, int32_t N, int32_t K, int32_t passes, int32_t repeat,
                        float* D, tf_stream_t stream);
 
+/* ---- total-variation regulariser ---------------------------------------------------------------
+ * TVLoss of the reference (network/other_field.py:170-191; TensoSDF.TV_loss_sdf network/fields.py:133-138,
+ * MCShadingNetwork.TV_loss :1525-1530) on one channels-last texture x[H,W,C] (C % 4 == 0; lines are W = 1):
+ *   sums[0] += sum_{h<H-1} (x[h+1,w,c] - x[h,w,c])^2,  sums[1] += sum_{w<W-1} (x[h,w+1,c] - x[h,w,c])^2
+ *   g[h,w,c] += u * (scale_h * d sums[0] / dx + scale_w * d sums[1] / dx),  u = *upstream (device scalar) or 1 if NULL
+ * (the host applies weight * 2 / (batch * count_h|w) as in the reference). */
+TF_API int tf_tv_fwd(const float* x, int32_t H, int32_t W, int32_t C, float* sums, tf_stream_t stream);
+TF_API int tf_tv_bwd(const float* x, int32_t H, int32_t W, int32_t C, float scale_h, float scale_w,
+                     const float* upstream, float* g, tf_stream_t stream);
+
 /* ---- per-kernel timing ------------------------------------------------------------------------
  * While enabled, the fused decoder kernels (sdf_stencil_fwd_tc, sdf_stencil_bwd_tc, xty_tc, linear_tc) are
  * bracketed by CUDA events on their launching stream.  tf_kernel_timing_read sums the recorded launches of

@@ -36,6 +36,8 @@ class TVLoss(nn.Module):
 
     def forward(self, x):
         b, c, h, w = x.shape
+        if x.is_cuda and b == 1 and c % 4 == 0 and x.dtype == torch.float32 and x.permute(0, 2, 3, 1).is_contiguous():
+            return ops.TVFunction.apply(x, self.TVLoss_weight)       # fused kernels on the channels-last factors
         count_h = c * (h - 1) * w
         count_w = c * h * (w - 1)
         total = 0.

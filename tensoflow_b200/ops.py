@@ -387,6 +387,36 @@ def linear(X, W, b=None, act="none", act_param=0.0):
     return LinearFunction.apply(X, W, b, act, act_param)
 
 
+class TVFunction(torch.autograd.Function):
+    """TVLoss (reference network/other_field.py:170-191) of one [1,C,H,W] texture stored channels-last: two sums of
+    squared neighbour differences in one pass, gradient in one pass.  Returns weight * 2 * (sum_h/count_h + sum_w/count_w)."""
+
+    @staticmethod
+    def forward(ctx, x, weight):
+        lib = _lib.load()
+        v = _nhwc(x)                                     # [H,W,C] contiguous view of the channels-last parameter
+        H, W, C = v.shape
+        sums = torch.zeros(2, device=x.device, dtype=torch.float32)
+        with _timed("tv_fwd"):
+            check(lib.tf_tv_fwd(ptr(v), H, W, C, ptr(sums), stream_ptr()), "tf_tv_fwd")
+        count_h, count_w = C * (H - 1) * W, C * H * (W - 1)
+        ctx.save_for_backward(x)
+        ctx.scales = (float(weight) * 2.0 / count_h if count_h else 0.0, float(weight) * 2.0 / count_w if count_w else 0.0)
+        return sums[0] * ctx.scales[0] + sums[1] * ctx.scales[1]
+
+    @staticmethod
+    def backward(ctx, g_out):
+        lib = _lib.load()
+        (x,) = ctx.saved_tensors
+        v = _nhwc(x)
+        H, W, C = v.shape
+        g = torch.zeros_like(v)
+        go = _f32c(g_out.reshape(1))                     # stays on the device: no host sync in backward
+        with _timed("tv_bwd"):
+            check(lib.tf_tv_bwd(ptr(v), H, W, C, ctx.scales[0], ctx.scales[1], ptr(go), ptr(g), stream_ptr()), "tf_tv_bwd")
+        return g.permute(2, 0, 1)[None], None            # logical [1,C,H,W], channels-last memory like the parameter
+
+
 class PwquadFunction(torch.autograd.Function):
     """Piecewise-quadratic coupling transform (reference network/flow.py:314-525).
     y [M], st [M,21] -> x [M], logj [M].  inverse=True is the sampling direction (no grad)."""

@@ -236,3 +236,23 @@ def test_render_core_end_to_end(C, H, A, G0, ups, R, S):
     close_as_fp32(var.grad, v64.grad, v32.grad, 1e-3, "d variance")
     for (name, p64), (_, p32), (_, pc) in zip(o64.named_parameters(), o32.named_parameters(), cu.named_parameters()):
         close_as_fp32(pc.grad, p64.grad, p32.grad, 1e-3, f"d {name}")
+
+
+@pytest.mark.parametrize("shape", [(1, 8, 33, 47), (1, 36, 64, 1), (1, 16, 5, 5)])
+def test_tv_loss_fused_matches_reference_formula(shape):
+    """TVLoss (reference other_field.py:170-191) through the fused channels-last kernels: value and gradient."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from tensoflow_b200.fields import TVLoss, _cl
+    dev = torch.device("cuda:0")
+    torch.manual_seed(sum(shape))
+    x0 = torch.randn(*shape)
+    tv = TVLoss(1.7)
+    xc = torch.nn.Parameter(_cl(x0.to(dev)))
+    loss = tv(xc) * 0.3
+    loss.backward()
+    xr = x0.double().requires_grad_()
+    ref = tv(xr) * 0.3              # CPU tensor: the plain PyTorch formulation
+    ref.backward()
+    assert abs(float(loss) - float(ref)) <= 1e-5 * abs(float(ref))
+    assert rel_err(xc.grad.cpu(), xr.grad) < 1e-5
