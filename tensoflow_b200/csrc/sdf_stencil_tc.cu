@@ -114,7 +114,7 @@ __device__ __forceinline__ void tc_gather_rows(const TcParams& p, int64_t s_base
 }
 
 __device__ __forceinline__ void tc_gather(const TcParams& p, int64_t tile, uint8_t* a_hi, uint8_t* a_lo) {
-    if (p.nq == NQ7) site::gather_tile(p.f, p.xyz, p.level, p.n, p.units, tile * site::SPT, p.KT, a_hi, a_lo, nullptr, NTH);
+    if (p.nq == NQ7) site::gather_tile_lean(p.f, p.xyz, p.level, p.n, p.units, tile * site::SPT, p.KT, a_hi, a_lo, nullptr, NTH, threadIdx.x);
     else tc_gather_rows(p, tile * TM, a_hi, a_lo);
 }
 
