@@ -209,21 +209,25 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_fwd_tc_kernel(TcParams p) 
             float psum = 0.f;
             for (int c0 = chh * 32; c0 < H; c0 += 32 * NCG) {
                 if (p.debug & 4) break;
-                float v[32];
-                tc::tmem_ld32(dcol + c0, v);
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 bb = *reinterpret_cast<const float4*>(b0s + c0 + j);
-                    const float4 ww = *reinterpret_cast<const float4*>(w1s + c0 + j);
-                    v[j + 0] = softplus100_fast(v[j + 0] + bb.x); psum = fmaf(v[j + 0], ww.x, psum);
-                    v[j + 1] = softplus100_fast(v[j + 1] + bb.y); psum = fmaf(v[j + 1], ww.y, psum);
-                    v[j + 2] = softplus100_fast(v[j + 2] + bb.z); psum = fmaf(v[j + 2], ww.z, psum);
-                    v[j + 3] = softplus100_fast(v[j + 3] + bb.w); psum = fmaf(v[j + 3], ww.w, psum);
-                }
-                if (centre && p.spc) {
-                    float4* dst = reinterpret_cast<float4*>(p.spc + (size_t)n * H + c0);
+                for (int hh = 0; hh < 2; ++hh) {            // two 16-column reads keep the register footprint small
+                    const int cc = c0 + hh * 16;
+                    float v[16];
+                    tc::tmem_ld16(dcol + cc, v);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 bb = *reinterpret_cast<const float4*>(b0s + cc + j);
+                        const float4 ww = *reinterpret_cast<const float4*>(w1s + cc + j);
+                        v[j + 0] = softplus100_fast(v[j + 0] + bb.x); psum = fmaf(v[j + 0], ww.x, psum);
+                        v[j + 1] = softplus100_fast(v[j + 1] + bb.y); psum = fmaf(v[j + 1], ww.y, psum);
+                        v[j + 2] = softplus100_fast(v[j + 2] + bb.z); psum = fmaf(v[j + 2], ww.z, psum);
+                        v[j + 3] = softplus100_fast(v[j + 3] + bb.w); psum = fmaf(v[j + 3], ww.w, psum);
+                    }
+                    if (centre && p.spc) {
+                        float4* dst = reinterpret_cast<float4*>(p.spc + (size_t)n * H + cc);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    }
                 }
             }
             sdfs[((tp & 1) * NCG + chh) * TM + row] = psum;
