@@ -66,6 +66,38 @@ def mip_sizes(h: int, w: int, n_levels: int):
     return out
 
 
+_AABB_CACHE: dict = {}
+_VMDESC_CACHE: dict = {}
+
+
+def _aabb_floats(aabb: torch.Tensor):
+    """The 6 aabb bounds as Python floats; cached per (storage, version) so that a CUDA aabb costs one D2H sync, not one per call."""
+    key = (aabb.data_ptr(), aabb._version, str(aabb.device))
+    v = _AABB_CACHE.get(key)
+    if v is None:
+        if len(_AABB_CACHE) > 64:
+            _AABB_CACHE.clear()
+        ab = aabb.detach().float().cpu()
+        v = ([float(ab[0, i]) for i in range(3)], [float(ab[1, i]) for i in range(3)])
+        _AABB_CACHE[key] = v
+    return v
+
+
+def vm_desc(planes, lines, aabb, n_levels, build_mips):
+    """VMDesc for these factors, reused while none of them has been modified (same storage and autograd version): the
+    forward / backward / SDF-only calls of one training step share one descriptor and ONE mip-chain build."""
+    key = tuple((t.data_ptr(), t._version) for t in (*planes, *lines)) + (aabb.data_ptr(), aabb._version, int(n_levels), bool(build_mips),
+                                                                         torch.cuda.current_stream().cuda_stream)
+    if not (build_mips and int(n_levels) > 1):
+        return VMDesc(planes, lines, aabb, n_levels, build_mips)      # nothing expensive to share
+    d = _VMDESC_CACHE.get(key)
+    if d is None:
+        _VMDESC_CACHE.clear()                             # one live entry per call site pattern is enough; mips are large
+        d = VMDesc(planes, lines, aabb, n_levels, build_mips)
+        _VMDESC_CACHE[key] = d
+    return d
+
+
 class VMDesc:
     """Owns the C descriptor of a VM field plus the tensors it points to."""
 
@@ -81,15 +113,15 @@ class VMDesc:
         f = VMField()
         self.plane_mips: List[Optional[torch.Tensor]] = [None] * 3
         self.line_mips: List[Optional[torch.Tensor]] = [None] * 3
-        ab = aabb.detach().float().cpu()
+        ab_min, ab_max = _aabb_floats(aabb)
         for i in range(3):
             H, W, _ = self.planes[i].shape
             G = self.lines[i].shape[0]
             f.plane[i] = self.planes[i].data_ptr()
             f.line[i] = self.lines[i].data_ptr()
             f.plane_h[i], f.plane_w[i], f.line_g[i] = H, W, G
-            f.aabb_min[i] = float(ab[0, i])
-            f.aabb_max[i] = float(ab[1, i])
+            f.aabb_min[i] = ab_min[i]
+            f.aabb_max[i] = ab_max[i]
             if self.n_levels > 1 and build_mips:
                 npl = sum(h * w for h, w in mip_sizes(H, W, self.n_levels))
                 nln = sum(h for h, _ in mip_sizes(G, 1, self.n_levels))
@@ -173,7 +205,7 @@ class SdfStencilFunction(torch.autograd.Function):
         xyz_c = _f32c(xyz.reshape(-1, 3))
         lvl_c = None if level is None else _f32c(level.reshape(-1))
         n = xyz_c.shape[0]
-        vm = VMDesc(planes, lines, aabb, n_levels, build_mips=lvl_c is not None)
+        vm = vm_desc(planes, lines, aabb, n_levels, lvl_c is not None)
         m, mlp_keep = _mlp_desc(W0, b0, W1, b1)
         A = m.app_dim
         dev = xyz_c.device
@@ -202,7 +234,7 @@ class SdfStencilFunction(torch.autograd.Function):
         planes, lines = factors[:3], factors[3:6]
         n = xyz_c.shape[0]
         with_mips = lvl_c is not None
-        vm = VMDesc(planes, lines, aabb, ctx.n_levels, build_mips=with_mips)
+        vm = vm_desc(planes, lines, aabb, ctx.n_levels, with_mips)
         m, mlp_keep = _mlp_desc(W0, b0, W1, b1)
         g, gp, gl, gpm, glm = vm.new_grads(with_mips)
         dW0 = torch.zeros_like(mlp_keep[0]); db0 = torch.zeros_like(mlp_keep[1])
@@ -227,7 +259,7 @@ def sdf_only(xyz, level, aabb, n_levels, W0, b0, W1, b1, planes, lines) -> torch
     xyz_c = _f32c(xyz.reshape(-1, 3))
     lvl_c = None if level is None else _f32c(level.reshape(-1))
     n = xyz_c.shape[0]
-    vm = VMDesc(planes, lines, aabb, n_levels, build_mips=lvl_c is not None)
+    vm = vm_desc(planes, lines, aabb, n_levels, lvl_c is not None)
     m, keep = _mlp_desc(W0, b0, W1, b1)
     out = torch.empty(n, device=xyz_c.device, dtype=torch.float32)
     wsb = lib.tf_sdf_stencil_fwd_workspace(C.byref(vm.c), C.byref(m), n, 0)
@@ -250,7 +282,7 @@ class VMFeatureFunction(torch.autograd.Function):
         xyz_c = _f32c(xyz.reshape(-1, 3))
         lvl_c = None if level is None else _f32c(level.reshape(-1))
         n = xyz_c.shape[0]
-        vm = VMDesc(planes, lines, aabb, n_levels, build_mips=lvl_c is not None)
+        vm = vm_desc(planes, lines, aabb, n_levels, lvl_c is not None)
         feat = torch.empty(n, 3 * vm.C, device=xyz_c.device, dtype=torch.float32)
         check(lib.tf_vm_feature_fwd(C.byref(vm.c), ptr(xyz_c), ptr(lvl_c), n, ptr(feat), stream_ptr()), "tf_vm_feature_fwd")
         ctx.save_for_backward(xyz_c, lvl_c, aabb, *factors)
@@ -263,7 +295,7 @@ class VMFeatureFunction(torch.autograd.Function):
         xyz_c, lvl_c, aabb, *factors = ctx.saved_tensors
         planes, lines = factors[:3], factors[3:6]
         with_mips = lvl_c is not None
-        vm = VMDesc(planes, lines, aabb, ctx.n_levels, build_mips=with_mips)
+        vm = vm_desc(planes, lines, aabb, ctx.n_levels, with_mips)
         g, gp, gl, gpm, glm = vm.new_grads(with_mips)
         gf = _f32c(g_feat)
         check(lib.tf_vm_feature_bwd(C.byref(vm.c), ptr(xyz_c), ptr(lvl_c), xyz_c.shape[0], ptr(gf), C.byref(g), stream_ptr()),
