@@ -599,7 +599,7 @@ int tf_internal_xty_tc(const float* X, const float* Y, int64_t rows, int M, int 
 
 static bool use_simt_bwd(const Dims& d) {
     const int KT = (d.K + 15) / 16 * 16;
-    return use_simt_path(d) || d.C % 4 != 0 || KT > 256 || tf_internal_bwd_tc_smem(KT, d.H) > 227 * 1024;
+    return use_simt_path(d) || d.C % 4 != 0 || KT > 128 /* dA accumulator + TMEM chunk operands share 256 columns */ || tf_internal_bwd_tc_smem(KT, d.H) > 227 * 1024;
 }
 // tensor-core backward workspace: [W slices | dW0/db0 staging | per tile of 18 samples: dPre [128,H], A rows [128,KT],
 // centre hidden [18,H], dHidden(centre) [18,H]]
