@@ -1,3 +1,4 @@
+"""torch.profiler breakdown of one ShapeRenderer.forward + backward step (module-level path; see DESIGN.md round-1 numbers)."""
 import os, sys, torch
 sys.path.insert(0, os.getcwd())
 from tensoflow_b200 import synthetic
