@@ -254,5 +254,5 @@ def test_tv_loss_fused_matches_reference_formula(shape):
     xr = x0.double().requires_grad_()
     ref = tv(xr) * 0.3              # CPU tensor: the plain PyTorch formulation
     ref.backward()
-    assert abs(float(loss) - float(ref)) <= 1e-5 * abs(float(ref))
+    assert abs(float(loss.detach()) - float(ref.detach())) <= 1e-5 * abs(float(ref.detach()))
     assert rel_err(xc.grad.cpu(), xr.grad) < 1e-5
