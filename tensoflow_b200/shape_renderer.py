@@ -443,6 +443,56 @@ class ShapeRenderer(torch.nn.Module):
         self.color_network.envlight.build_mips()
         return self.train_step(data['step'])
 
+    # ---- full-image inference (reference shapeRenderer.py:569-668) ------------------------------------------------
+    @staticmethod
+    def image_rays(pose, K, h, w, device):
+        """nerfDataType ray construction of the reference (`construct_ray_dirs_nerf` shapeRenderer.py:592-621 and
+        `_process_ray_batch_nerf` :708-719): pixel directions in the OpenGL camera frame, tri-mip pixel radii, rays_cos,
+        rotated by the camera-to-world pose [3,4]."""
+        K = torch.as_tensor(K, dtype=torch.float32, device=device)
+        pose = torch.as_tensor(pose, dtype=torch.float32, device=device)
+        i, j = torch.meshgrid(torch.linspace(0, w - 1, w, device=device), torch.linspace(0, h - 1, h, device=device), indexing='ij')
+        i, j = i.t(), j.t()
+        rays_d = torch.stack([(i - K[0][2]) / K[0][0], -(j - K[1][2]) / K[1][1], -torch.ones_like(i)], -1)      # h,w,3
+        dx = (rays_d[:, :-1, :] - rays_d[:, 1:, :]).norm(dim=-1, keepdim=True)
+        dx = torch.cat([dx, dx[:, -2:-1, :]], 1)
+        dy = (rays_d[:-1, :, :] - rays_d[1:, :, :]).norm(dim=-1, keepdim=True)
+        dy = torch.cat([dy, dy[-2:-1, :, :]], 0)
+        radiis = torch.sqrt(dx * dy / torch.pi).reshape(-1, 1)
+        rays_d = rays_d.reshape(-1, 3)
+        rays_cos = 1 / rays_d.norm(dim=-1, keepdim=True)
+        rays_o = pose[:3, -1].expand(rays_d.shape[0], 3).contiguous()
+        rays_d = torch.sum(rays_d[..., None, :] * pose[:3, :3], -1)
+        return {'rays_o': rays_o, 'rays_d': rays_d, 'dirs': F.normalize(rays_d, dim=-1), 'radiis': radiis, 'rays_cos': rays_cos}
+
+    @torch.no_grad()
+    def nvs(self, pose, K, h, w, step=300000, rank=0, world=1, perturb_overwrite=-1):
+        """Forward-only rendering of a full h x w image in `test_ray_num` chunks (reference shapeRenderer.py:569-668).
+        With world > 1 (BASELINE config 5) each rank renders a contiguous slice of the rays and the slices are
+        all-gathered in rank order (dist.gather_tiles); every rank returns the full image.  Returns [h,w,C] numpy arrays
+        'color', 'normal', 'acc' (+ 'radiance' when the radiance field is on): the channels the fused compositor produces."""
+        from .dist import shard_slice, gather_tiles
+        rays = self.image_rays(pose, K, h, w, self.device)
+        rn = h * w
+        sl = shard_slice(rn, rank, world)
+        trn = self.cfg['test_ray_num']
+        keys = {'color': 'ray_rgb', 'normal': 'normal', 'acc': 'acc'}
+        if self.cfg['has_radiance_field'] and step > self.cfg['radiance_field_step']:
+            keys['radiance'] = 'radiance'
+        chunks = {k: [] for k in keys}
+        for r0 in range(sl.start, sl.stop, trn):
+            cur = {k: v[r0:min(r0 + trn, sl.stop)] for k, v in rays.items()}
+            near, far = near_far_from_sphere(cur['rays_o'], cur['rays_d'], float(self.radius))
+            out = self.render(cur, near, far, None, perturb_overwrite=perturb_overwrite, is_train=False, step=step)   # as :646
+            for k, src in keys.items():
+                chunks[k].append(out[src])
+        res = {}
+        for k in keys:
+            local = torch.cat(chunks[k], 0) if chunks[k] else torch.zeros(0, 1, device=self.device)
+            full = gather_tiles(local) if world > 1 else local
+            res[k] = full.reshape(h, w, -1).cpu().numpy()
+        return res
+
     # ---- alpha mask (reference shapeRenderer.py:257-325) --------------------------------------------
     @torch.no_grad()
     def compute_grid_alpha(self, xyz_locs, length):

@@ -107,3 +107,28 @@ def test_alpha_mask_and_train_step():
     out2 = m({'step': 30001})
     assert out2['sample_num'] <= n_before + 1e-6       # the mask only removes samples
     assert torch.isfinite(out2['ray_rgb']).all()
+
+
+@pytest.mark.gpu
+def test_nvs_full_image_chunked():
+    """ShapeRenderer.nvs (reference shapeRenderer.py:569-668): chunking must not change the image."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import numpy as np
+    from tensoflow_b200.shape_renderer import ShapeRenderer
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    h, w = 10, 12
+    K = np.array([[20.0, 0, w / 2], [0, 20.0, h / 2], [0, 0, 1]], np.float32)
+    pose = np.array([[1, 0, 0, 0.1], [0, 1, 0, -0.05], [0, 0, 1, 2.0]], np.float32)      # camera at z = 2 looking down -z
+    imgs = []
+    for trn in (4096, 37):
+        torch.manual_seed(0)
+        m = ShapeRenderer(dict(device=dev, shader_config=dict(env_res=16, env_min_res=4), test_ray_num=trn, **CFG))
+        m.color_network.envlight.build_mips()
+        imgs.append(m.nvs(pose, K, h, w, perturb_overwrite=0))
+    for k in ('color', 'normal', 'acc', 'radiance'):
+        assert imgs[0][k].shape[:2] == (h, w)
+        assert np.isfinite(imgs[0][k]).all()
+        assert np.abs(imgs[0][k] - imgs[1][k]).max() < 1e-4, k
+    assert imgs[0]['acc'].max() > 0.5            # the initial sphere is visible
