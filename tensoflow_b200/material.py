@@ -421,9 +421,10 @@ class MaterialRenderer(nn.Module):
     losses (materialRenderer.py:518-564).  Mesh / image IO and the one-off surface-point
     precompute are out of scope: the caller supplies the mesh arrays and the
     surface-point batch (`inters`, `normals`, `rays_d`, `rgb`) as tensors."""
-    default_cfg = {'train_ray_num': 2048, 'rgb_loss': 'charbonier', 'shader_cfg': {}, 'reg_mat': True, 'reg_diffuse_light': True,
-                   'reg_diffuse_light_lambda': 0.1, 'device': 'cuda', 'aabb': [[-1.0, -1.0, -1.0], [1.0, 1.0, 1.0]],
-                   'gridSize': [512, 512, 512]}
+    default_cfg = {'train_ray_num': 2048, 'test_ray_num': 8192, 'rgb_loss': 'charbonier', 'shader_cfg': {}, 'reg_mat': True,
+                   'reg_diffuse_light': True, 'reg_diffuse_light_lambda': 0.1, 'device': 'cuda',
+                   'aabb': [[-1.0, -1.0, -1.0], [1.0, 1.0, 1.0]], 'gridSize': [512, 512, 512], 'nvs_ray_num': 512,
+                   'std_act': 'exp', 'inv_s_init': 0.3, 'direct_sn0': 128, 'direct_sn1': 9}
 
     def __init__(self, cfg, vertices, triangles, training=True):
         super().__init__()
@@ -435,6 +436,145 @@ class MaterialRenderer(nn.Module):
         self.tracer = MeshTracer(vertices, triangles, offset=float(2 * self.unit_size))    # materialRenderer.py:223
         self.shader_network = MCShadingNetwork({**self.cfg['shader_cfg'], 'device': dev}, self.tracer, self.aabb)
         self.train_batch = None
+        self.sdf_network = None                 # set by init_sdf (frozen shape-stage geometry)
+        self.radius = (self.aabb[1] - torch.mean(self.aabb, 0)).mean().float()
+
+    # ---- frozen geometry from the shape stage (reference materialRenderer.py:148-179) -----------------------------
+    def init_sdf(self, ckpt):
+        """Builds the frozen TensoSDF + deviation network from a shape-stage checkpoint (`ShapeRenderer.ckpt_to_save()` here or
+        the reference's: keys 'kwargs', 'network_state_dict')."""
+        from .fields import TensoSDF, SingleVarianceNetwork
+        dev = self.cfg['device']
+        kw = ckpt['kwargs']
+        self.aabb = torch.as_tensor(kw['aabb'], dtype=torch.float32, device=dev)
+        grid = torch.tensor(kw['gridSize'], device=dev)
+        self.radius = (self.aabb[1] - torch.mean(self.aabb, 0)).mean().float()
+        self.unit_size = torch.mean((self.aabb[1] - self.aabb[0]) / (grid - 1))
+        self.tracer.offset = float(2 * self.unit_size)
+        self.sdf_network = TensoSDF(grid, self.aabb, device=dev, init_n_levels=kw['max_levels'], sdf_n_comp=kw['sdf_n_comp'],
+                                    sdf_dim=kw['sdf_dim'], app_dim=kw['app_dim'], sdf_multires=kw.get('sdf_multires', 0))
+        self.deviation_net = SingleVarianceNetwork(init_val=self.cfg['inv_s_init'], activation=self.cfg['std_act']).to(dev)
+        sd = ckpt['network_state_dict']
+        self.sdf_network.load_state_dict({k.split('.', 1)[1]: v for k, v in sd.items() if k.startswith('sdf_network.')}, strict=False)
+        self.deviation_net.load_state_dict({k.split('.', 1)[1]: v for k, v in sd.items() if k.startswith('deviation')})
+        for p in list(self.sdf_network.parameters()) + list(self.deviation_net.parameters()):
+            p.requires_grad = False
+        self.sdf_inter_fun = lambda x: self.sdf_network.sdf(x, None)
+
+    # ---- surface points: mesh hit refined on the SDF (reference materialRenderer.py:265-357) ----------------------
+    def near_far_from_sphere(self, rays_o, rays_d):
+        a = torch.sum(rays_d ** 2, dim=-1, keepdim=True)
+        b = 2.0 * torch.sum(rays_o * rays_d, dim=-1, keepdim=True)
+        mid = 0.5 * (-b) / a
+        return torch.clamp(mid - self.radius, min=1e-3), mid + self.radius
+
+    @torch.no_grad()
+    def get_intersection_around_mesh(self, sdf_fun, inv_fun, rays_o, rays_d, m_depth, sn0=128, sn1=9):
+        """reference materialRenderer.py:281-313: NeuS weights on sn0 samples within +-4 voxels of the mesh depth, sn1 importance
+        samples from them (deterministic), weights again -> (z_mid, weights, mid_sdf) [pn, sn1-1]."""
+        from .shape_renderer import get_weights, sample_pdf
+        near, far = self.near_far_from_sphere(rays_o, rays_d)
+        t_min = torch.minimum(torch.maximum(m_depth - self.unit_size * 4, near), far)
+        t_max = torch.minimum(torch.maximum(m_depth + self.unit_size * 4, near), far)
+        z = t_min + (t_max - t_min) * torch.linspace(0.0, 1.0, sn0, device=rays_o.device)[None, :]
+        w, _ = get_weights(sdf_fun, inv_fun, z, rays_o, rays_d)
+        z_new = sample_pdf(z, w, sn1, True)
+        w, mid_sdf = get_weights(sdf_fun, inv_fun, z_new, rays_o, rays_d)
+        return (z_new[:, 1:] + z_new[:, :-1]) * 0.5, w, mid_sdf
+
+    @torch.no_grad()
+    def trace_sdf_with_mesh(self, rays_o, rays_d, sn0, sn1):
+        """reference materialRenderer.py:315-343: BVH closest hit, depth refined as the NeuS-weighted mean of sn1-1 mid-points,
+        normal = normalised finite-difference SDF gradient (fused stencil kernel) flipped towards the camera."""
+        inters, normals, depth, hit_mask = self.trace(rays_o, rays_d)
+        hit = hit_mask.squeeze(-1)
+        if self.sdf_network is not None and bool(hit.any()):
+            o, d = rays_o[hit], rays_d[hit]
+            z, w, _ = self.get_intersection_around_mesh(self.sdf_inter_fun, self.deviation_net, o, d, depth[hit], sn0, sn1)
+            w = w / torch.sum(w, dim=-1, keepdim=True)
+            w = torch.where(torch.isnan(w), torch.full_like(w, 1. / (sn1 - 1)), w)
+            dep = torch.sum(w * z, -1, keepdim=True)
+            pts = o + dep * d
+            g, _ = self.sdf_network.gradient(pts, None)
+            n = F.normalize(g, dim=-1)
+            n = torch.where((n * d).sum(-1, keepdim=True) >= 0, -n, n)
+            depth, inters, normals = depth.clone(), inters.clone(), normals.clone()
+            depth[hit], inters[hit], normals[hit] = dep, pts, n
+        return inters, normals, depth, hit.unsqueeze(-1)
+
+    def trace_sdf_in_batch(self, rays_o, rays_d, batch_size=10240 * 5):
+        """reference materialRenderer.py:265-279 (sn0 = 32, sn1 = 9 as there)"""
+        outs = [self.trace_sdf_with_mesh(rays_o[i:i + batch_size], rays_d[i:i + batch_size], 32, 9)
+                for i in range(0, rays_o.shape[0], batch_size)]
+        return tuple(torch.cat(x, 0) for x in zip(*outs))
+
+    def _get_trace_ray_batch_info(self, ray_batch_infos, is_train=True):
+        """reference materialRenderer.py:481-504"""
+        rays_o, rays_d = ray_batch_infos['rays_o'], ray_batch_infos['rays_d']
+        pn = rays_o.shape[0]
+        inters, normals, depth, hit_mask = self.trace_sdf_in_batch(rays_o, rays_d)
+        inters, normals, depth, hit_mask = inters.reshape(pn, 3), normals.reshape(pn, 3), depth.reshape(pn, 1), hit_mask.reshape(pn)
+        if is_train:
+            out = {k: v[hit_mask] for k, v in ray_batch_infos.items()}
+            out.update({'inters': inters[hit_mask], 'normals': normals[hit_mask], 'depth': depth[hit_mask]})
+        else:
+            out = dict(ray_batch_infos)
+            out.update({'inters': inters, 'normals': normals, 'depth': depth, 'hit_mask': hit_mask})
+        return out
+
+    # ---- full-image relighting / novel-view inference (reference materialRenderer.py:641-752) --------------------
+    NVS_KEYS = {'color': 3, 'normal': 3, 'spec_light': 3, 'diff_light': 3, 'indirect_light': 3, 'spec_color': 3, 'diff_color': 3,
+                'albedo': 3, 'roughness': 1, 'metallic': 1, 'occ_trace': 1}
+
+    @staticmethod
+    def image_rays(pose, K, h, w, device):
+        """`construct_ray_dirs_nerf` of reference materialRenderer.py:647-672: OpenGL pixel directions rotated by the
+        camera-to-world pose [3,4] and normalised; origin = pose translation."""
+        K = torch.as_tensor(np.asarray(K, np.float32), device=device)
+        pose = torch.as_tensor(np.asarray(pose, np.float32), device=device)
+        i, j = torch.meshgrid(torch.linspace(0, w - 1, w, device=device), torch.linspace(0, h - 1, h, device=device), indexing='ij')
+        i, j = i.t(), j.t()
+        d = torch.stack([(i - K[0][2]) / K[0][0], -(j - K[1][2]) / K[1][1], -torch.ones_like(i)], -1).reshape(-1, 3)
+        rays_d = F.normalize(d @ pose[:3, :3].t(), dim=-1)
+        rays_o = pose[:3, 3].expand(h * w, 3).contiguous()
+        return {'rays_o': rays_o, 'rays_d': rays_d}
+
+    @torch.no_grad()
+    def nvs(self, pose, K, h, w, rank=0, world=1, noise_fn=None):
+        """Forward-only shading of a full h x w view in `nvs_ray_num`-ray chunks (512 in the reference, :705): trace + SDF
+        refinement -> MCShadingNetwork with is_train=False, step=None (both the plain and the NIS estimators run, the plain one is
+        the image).  With world > 1 (BASELINE config 5) each rank shades a contiguous slice of the pixels and the slices are
+        all-gathered in rank order.  `noise_fn(r0, n)` may supply the per-chunk random draws (tests)."""
+        from .dist import shard_slice, gather_tiles
+        dev = self.cfg['device']
+        rays = self.image_rays(pose, K, h, w, dev)
+        sl = shard_slice(h * w, rank, world)
+        trn = self.cfg['nvs_ray_num']
+        chunks = {k: [] for k in self.NVS_KEYS}
+        for r0 in range(sl.start, sl.stop, trn):
+            cur = self._get_trace_ray_batch_info({k: v[r0:min(r0 + trn, sl.stop)] for k, v in rays.items()}, is_train=False)
+            hit = cur['hit_mask']
+            out = {k: torch.zeros(hit.shape[0], d, device=dev) for k, d in self.NVS_KEYS.items()}
+            out['color'][:] = 1.0
+            out['normal'][:, 2] = 1.0
+            if bool(hit.any()):
+                nrm = cur['normals'][hit]
+                so = self.shade(cur['inters'][hit], -cur['rays_d'][hit], nrm, None, False,
+                                noise=None if noise_fn is None else noise_fn(r0, int(hit.sum())))
+                for k, src in (('color', 'rgb_pr'), ('spec_light', 'specular_light'), ('diff_light', 'diffuse_light'),
+                               ('indirect_light', 'indirect_light'), ('occ_trace', 'visibility'), ('spec_color', 'specular_color'),
+                               ('diff_color', 'diffuse_color'), ('albedo', 'albedo'), ('metallic', 'metallic')):
+                    out[k][hit] = so[src]
+                out['normal'][hit] = nrm
+                out['roughness'][hit] = torch.sqrt(so['roughness'])          # predictions are roughness squared (:738)
+            for k in self.NVS_KEYS:
+                chunks[k].append(out[k])
+        res = {}
+        for k, d in self.NVS_KEYS.items():
+            local = torch.cat(chunks[k], 0) if chunks[k] else torch.zeros(0, d, device=dev)
+            full = gather_tiles(local) if world > 1 else local
+            res[k] = full.reshape(h, w, -1).cpu().numpy()
+        return res
 
     def trace(self, rays_o, rays_d):
         return self.tracer.trace(rays_o, rays_d)

@@ -233,11 +233,38 @@ class ShapeRenderer(torch.nn.Module):
         g += self.color_network.get_optparam_groups(lr_net, lr_env)
         return g
 
+    def get_kwargs(self):
+        """reference shapeRenderer.py:326-341 (the keys MaterialRenderer.init_sdf reads back)"""
+        c = self.cfg
+        return {'aabb': self.aabb, 'gridSize': self.gridSize.tolist(), 'sdf_n_comp': c['sdf_n_comp'], 'sdf_dim': c['sdf_dim'],
+                'app_dim': c['app_dim'], 'sdf_multires': c['sdf_multires'], 'alphaMask_thres': c['alphaMask_thres'],
+                'step_ratio': c['step_ratio'], 'max_levels': self.max_levels}
+
     def ckpt_to_save(self):
-        return {'network_state_dict': self.state_dict(), 'gridSize': self.gridSize.tolist(), 'max_levels': self.max_levels}
+        """reference shapeRenderer.py:343-354: same dictionary layout (kwargs, state dict, bit-packed alpha mask)"""
+        import numpy as np
+        ckpt = {'kwargs': self.get_kwargs(), 'network_state_dict': self.state_dict()}
+        if self.alphaMask is not None:
+            vol = self.alphaMask.alpha_volume.bool().cpu().numpy()
+            ckpt.update({'alphaMask.shape': vol.shape, 'alphaMask.mask': np.packbits(vol.reshape(-1)),
+                         'alphaMask.aabb': self.alphaMask.aabb.cpu()})
+        return ckpt
 
     def load_ckpt(self, ckpt):
-        self.load_state_dict(ckpt['network_state_dict'], strict=False)
+        """reference shapeRenderer.py:356-363; a checkpoint saved at a finer grid than this module was built with is followed:
+        the factors take the stored shapes and `gridSize` / `max_levels` / step sizes are updated (the reference trainer replays its
+        upsampling schedule before loading instead)."""
+        import numpy as np
+        if 'alphaMask.aabb' in ckpt:
+            length = int(np.prod(ckpt['alphaMask.shape']))
+            vol = torch.from_numpy(np.unpackbits(ckpt['alphaMask.mask'])[:length].reshape(ckpt['alphaMask.shape']))
+            self.alphaMask = AlphaGridMask(self.device, ckpt['alphaMask.aabb'].to(self.device), vol.float().to(self.device))
+        self.load_state_dict(ckpt['network_state_dict'], strict=False)       # TensoSDF adopts the stored factor shapes
+        kw = ckpt.get('kwargs')
+        if kw is not None and (list(kw['gridSize']) != self.gridSize.tolist() or kw['max_levels'] != self.max_levels):
+            res = torch.tensor(kw['gridSize'])
+            self.sdf_network.update_gridSize_aabb(res.long().cpu(), self.sdf_network.aabb, kw['max_levels'])
+            self.update_stepSize(res, kw['max_levels'])
 
     def upsample_sdf_grid(self, res_target):
         res, n_levels = self.sdf_network.upsample_volume_grid(torch.as_tensor(res_target))

@@ -65,3 +65,19 @@ def copy_field_params(src, dst):
             b.copy_(a.to(b.device, b.dtype))
         for a, b in zip(src.sdf_mat.parameters(), dst.sdf_mat.parameters()):
             b.copy_(a.to(b.device, b.dtype))
+
+
+def bumpy_sphere(nu: int, nv: int, r: float = 0.5, bump: float = 0.1):
+    """Lat-long sphere of radius r with radial bumps: the synthetic mesh family of BASELINE config 3 (1000 x 500 quads there).
+    Returns (vertices [nu*nv,3] fp32, triangles [2*nu*(nv-1),3] int32), both on the host."""
+    u = torch.linspace(0, 2 * math.pi, nu + 1)[:-1]
+    v = torch.linspace(0.05, math.pi - 0.05, nv)
+    vv, uu = torch.meshgrid(v, u, indexing="ij")
+    rad = r * (1 + bump * torch.sin(5 * uu) * torch.sin(4 * vv))
+    verts = torch.stack([rad * torch.sin(vv) * torch.cos(uu), rad * torch.sin(vv) * torch.sin(uu), rad * torch.cos(vv)], -1).reshape(-1, 3)
+    i = torch.arange(nv - 1)[:, None]
+    j = torch.arange(nu)[None, :]
+    a, b = i * nu + j, i * nu + (j + 1) % nu
+    c, d = (i + 1) * nu + j, (i + 1) * nu + (j + 1) % nu
+    tris = torch.cat([torch.stack([a, c, b], -1).reshape(-1, 3), torch.stack([b, c, d], -1).reshape(-1, 3)], 0)
+    return verts.float(), tris.to(torch.int32)
