@@ -138,6 +138,8 @@ def main():
             total += loss.detach()
         if allreduce:
             bucket.allreduce()
+            if world > 1:
+                dist.all_reduce(total)              # reported loss = the full batch's
         return total
 
     if args.check:

@@ -95,3 +95,21 @@ def gather_tiles(local: torch.Tensor) -> torch.Tensor:
     outs = [torch.zeros_like(pad) for _ in range(world)]
     dist.all_gather(outs, pad)
     return torch.cat([o[:int(s.item())] for o, s in zip(outs, sizes)], 0)
+
+
+def interleaved_ids(n: int, rank: int, world: int, device=None) -> torch.Tensor:
+    """Pixel ids rank, rank+world, rank+2*world, ... : the inference split (config 5).  Object pixels cluster in the image, so
+    contiguous tiles leave the ranks that own background rows idle; a strided split gives every rank the same mix."""
+    return torch.arange(rank, max(n, rank), world, device=device)
+
+
+def gather_interleaved(local: torch.Tensor, n: int) -> torch.Tensor:
+    """All-gather per-rank results of `interleaved_ids` and put them back in pixel order -> [n, C] on every rank."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return local
+    world = dist.get_world_size()
+    full = gather_tiles(local)
+    order = torch.cat([interleaved_ids(n, r, world, local.device) for r in range(world)])
+    out = torch.empty_like(full)
+    out[order] = full
+    return out

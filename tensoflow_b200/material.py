@@ -543,16 +543,19 @@ class MaterialRenderer(nn.Module):
     def nvs(self, pose, K, h, w, rank=0, world=1, noise_fn=None):
         """Forward-only shading of a full h x w view in `nvs_ray_num`-ray chunks (512 in the reference, :705): trace + SDF
         refinement -> MCShadingNetwork with is_train=False, step=None (both the plain and the NIS estimators run, the plain one is
-        the image).  With world > 1 (BASELINE config 5) each rank shades a contiguous slice of the pixels and the slices are
-        all-gathered in rank order.  `noise_fn(r0, n)` may supply the per-chunk random draws (tests)."""
-        from .dist import shard_slice, gather_tiles
+        the image).  With world > 1 (BASELINE config 5) rank r shades pixels r, r+world, ... and the results are
+        all-gathered back into pixel order.  `noise_fn(r0, n)` may supply the per-chunk random draws (tests)."""
+        from .dist import interleaved_ids, gather_interleaved
         dev = self.cfg['device']
         rays = self.image_rays(pose, K, h, w, dev)
-        sl = shard_slice(h * w, rank, world)
+        if world > 1:
+            ids = interleaved_ids(h * w, rank, world, dev)
+            rays = {k: v[ids] for k, v in rays.items()}
+        n_loc = rays['rays_o'].shape[0]
         trn = self.cfg['nvs_ray_num']
         chunks = {k: [] for k in self.NVS_KEYS}
-        for r0 in range(sl.start, sl.stop, trn):
-            cur = self._get_trace_ray_batch_info({k: v[r0:min(r0 + trn, sl.stop)] for k, v in rays.items()}, is_train=False)
+        for r0 in range(0, n_loc, trn):
+            cur = self._get_trace_ray_batch_info({k: v[r0:r0 + trn] for k, v in rays.items()}, is_train=False)
             hit = cur['hit_mask']
             out = {k: torch.zeros(hit.shape[0], d, device=dev) for k, d in self.NVS_KEYS.items()}
             out['color'][:] = 1.0
@@ -572,7 +575,7 @@ class MaterialRenderer(nn.Module):
         res = {}
         for k, d in self.NVS_KEYS.items():
             local = torch.cat(chunks[k], 0) if chunks[k] else torch.zeros(0, d, device=dev)
-            full = gather_tiles(local) if world > 1 else local
+            full = gather_interleaved(local, h * w) if world > 1 else local
             res[k] = full.reshape(h, w, -1).cpu().numpy()
         return res
 

@@ -495,20 +495,23 @@ class ShapeRenderer(torch.nn.Module):
     @torch.no_grad()
     def nvs(self, pose, K, h, w, step=300000, rank=0, world=1, perturb_overwrite=-1):
         """Forward-only rendering of a full h x w image in `test_ray_num` chunks (reference shapeRenderer.py:569-668).
-        With world > 1 (BASELINE config 5) each rank renders a contiguous slice of the rays and the slices are
-        all-gathered in rank order (dist.gather_tiles); every rank returns the full image.  Returns [h,w,C] numpy arrays
+        With world > 1 (BASELINE config 5) rank r renders pixels r, r+world, ... (a strided split balances object and
+        background pixels over the ranks) and the results are all-gathered back into pixel order; every rank returns the full image.  Returns [h,w,C] numpy arrays
         'color', 'normal', 'acc' (+ 'radiance' when the radiance field is on): the channels the fused compositor produces."""
-        from .dist import shard_slice, gather_tiles
+        from .dist import interleaved_ids, gather_interleaved
         rays = self.image_rays(pose, K, h, w, self.device)
         rn = h * w
-        sl = shard_slice(rn, rank, world)
+        if world > 1:
+            ids = interleaved_ids(rn, rank, world, self.device)
+            rays = {k: v[ids] for k, v in rays.items()}
+        n_loc = rays['rays_o'].shape[0]
         trn = self.cfg['test_ray_num']
         keys = {'color': 'ray_rgb', 'normal': 'normal', 'acc': 'acc'}
         if self.cfg['has_radiance_field'] and step > self.cfg['radiance_field_step']:
             keys['radiance'] = 'radiance'
         chunks = {k: [] for k in keys}
-        for r0 in range(sl.start, sl.stop, trn):
-            cur = {k: v[r0:min(r0 + trn, sl.stop)] for k, v in rays.items()}
+        for r0 in range(0, n_loc, trn):
+            cur = {k: v[r0:r0 + trn] for k, v in rays.items()}
             near, far = near_far_from_sphere(cur['rays_o'], cur['rays_d'], float(self.radius))
             out = self.render(cur, near, far, None, perturb_overwrite=perturb_overwrite, is_train=False, step=step)   # as :646
             for k, src in keys.items():
@@ -516,7 +519,7 @@ class ShapeRenderer(torch.nn.Module):
         res = {}
         for k in keys:
             local = torch.cat(chunks[k], 0) if chunks[k] else torch.zeros(0, 1, device=self.device)
-            full = gather_tiles(local) if world > 1 else local
+            full = gather_interleaved(local, rn) if world > 1 else local
             res[k] = full.reshape(h, w, -1).cpu().numpy()
         return res
 

@@ -35,7 +35,7 @@ def _loss_terms(m, x, y):
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from tensoflow_b200.dist import FlatGradBucket, shard_slice, global_mean, gather_tiles
+    from tensoflow_b200.dist import FlatGradBucket, shard_slice, global_mean, gather_tiles, interleaved_ids, gather_interleaved
     g = torch.Generator().manual_seed(1)
     X, Y = torch.randn(37, 6, generator=g), torch.randn(37, 3, generator=g)
     m = _model()
@@ -50,6 +50,10 @@ def _worker(rank, world, port, q):
     bucket = FlatGradBucket(m.parameters())
     bucket.allreduce()
     tiles = gather_tiles(per_ray.detach()[:, None])
+    # inference split (config 5): strided pixel ids, results gathered back into pixel order
+    ids = interleaved_ids(37, rank, world)
+    inter = gather_interleaved(X[ids] * 2.0, 37)
+    assert torch.equal(inter, X * 2.0)
     # numpy payloads are pickled by value (torch tensors travel as file descriptors the exiting worker may close first)
     q.put((rank, [p.grad.clone().numpy() for p in m.parameters()], float(mean_kept), tiles.numpy()))
     dist.destroy_process_group()
@@ -90,3 +94,12 @@ def test_shard_slice_covers_everything():
                 s = shard_slice(n, r, w)
                 idx += list(range(s.start, s.stop))
             assert idx == list(range(n))
+
+
+def test_interleaved_ids_cover_everything():
+    from tensoflow_b200.dist import interleaved_ids
+    for n in (0, 1, 7, 64, 640000):
+        for w in (1, 2, 3, 8):
+            ids = torch.cat([interleaved_ids(n, r, w) for r in range(w)])
+            assert ids.numel() == n and torch.equal(torch.sort(ids).values, torch.arange(n))
+            assert max(interleaved_ids(n, r, w).numel() for r in range(w)) - min(interleaved_ids(n, r, w).numel() for r in range(w)) <= 1

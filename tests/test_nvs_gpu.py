@@ -119,13 +119,12 @@ def test_material_nvs_image():
     assert 10 < hit.sum() < h * w
     assert np.allclose(a['color'][~hit], 1.0) and np.allclose(a['albedo'][~hit], 0.0)
     assert np.allclose(np.linalg.norm(a['normal'], axis=-1), 1.0, atol=1e-5)
-    # rank slices: render rows of pixels as two "ranks" and stitch
-    from tensoflow_b200.dist import shard_slice
+    # rank split: surface points of the strided pixel sets of two "ranks", put back in pixel order, equal the full image's
+    from tensoflow_b200.dist import interleaved_ids
     rays = mat.image_rays(pose, K, h, w, dev)
-    parts = []
-    for r in range(2):
-        sl = shard_slice(h * w, r, 2)
-        cur = mat._get_trace_ray_batch_info({k: v[sl] for k, v in rays.items()}, is_train=False)
-        parts.append(cur['inters'])
     full = mat._get_trace_ray_batch_info(rays, is_train=False)['inters']
-    assert torch.equal(torch.cat(parts, 0), full)
+    stitched = torch.empty_like(full)
+    for r in range(2):
+        ids = interleaved_ids(h * w, r, 2, dev)
+        stitched[ids] = mat._get_trace_ray_batch_info({k: v[ids] for k, v in rays.items()}, is_train=False)['inters']
+    assert torch.equal(stitched, full)
