@@ -262,6 +262,18 @@ TF_API int tf_tv_fwd(const float* x, int32_t H, int32_t W, int32_t C, float* sum
 TF_API int tf_tv_bwd(const float* x, int32_t H, int32_t W, int32_t C, float scale_h, float scale_w,
                      const float* upstream, float* g, tf_stream_t stream);
 
+/* ---- optimizer step ------------------------------------------------------------------------------
+ * torch.optim.Adam(grad_vars, betas=(0.9, 0.99)).step() of the reference trainer (train/trainer_inv.py:112,212; one
+ * learning rate per parameter group, :247-248) as ONE streaming pass: for tensor t (numel[t] fp32 elements in any
+ * memory order, the four buffers laid out alike) and step k >= 1
+ *   m = m + (1-beta1)(g - m);  v = beta2 v + (1-beta2) g^2;
+ *   p = p - lr[t] / (1-beta1^k) * m / (sqrt(v) / sqrt(1-beta2^k) + eps)
+ * The pointer / numel / lr tables are HOST arrays of n_tensors entries (device pointers inside); launches cover 32
+ * tensors each.  28 B of HBM traffic per element. */
+TF_API int tf_adam_step(int32_t n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                        float* const* exp_avg_sq, const int64_t* numel, const float* lr, float beta1, float beta2,
+                        float eps, int32_t step, tf_stream_t stream);
+
 /* ---- per-kernel timing ------------------------------------------------------------------------
  * While enabled, the fused decoder kernels (sdf_stencil_fwd_tc, sdf_stencil_bwd_tc, xty_tc, linear_tc) are
  * bracketed by CUDA events on their launching stream.  tf_kernel_timing_read sums the recorded launches of
