@@ -9,6 +9,8 @@ namespace {
 
 constexpr int MAXD = 16;
 
+__device__ __forceinline__ float ldg_stream(const float* p) { return __ldg(p); }   // read-only path, each byte used once per pass
+
 struct AlphaTerms {
     float alpha, raw, P, Nx, est_prev, est_next, tc, inv_s;
 };
@@ -56,6 +58,11 @@ __device__ __forceinline__ float warp_scan_add(float v, int lane) {
     return v;
 }
 
+// One warp per ray.  The prefix product makes the 32-sample chunks of a ray a serial chain, and a chunk's loads used to be
+// issued only after the previous chunk's scan: with every warp resident at once the kernel lasted (chunks per ray) x (one
+// DRAM round trip).  Now U chunks are loaded up front (U x (5 + D) independent loads per lane in flight) and scanned from
+// registers, which shortens the chain U-fold; DMAX bounds the register arrays (D <= 8 covers colour + SDF gradient).
+template <int DMAX, int U>
 __global__ void __launch_bounds__(256) neus_composite_fwd_kernel(
     const float* __restrict__ sdf, const float* __restrict__ grad, const float* __restrict__ dists,
     const float* __restrict__ dirs, const int32_t* __restrict__ offs, int n_rays, const float* __restrict__ variance,
@@ -68,39 +75,50 @@ __global__ void __launch_bounds__(256) neus_composite_fwd_kernel(
         const int b = offs[ray], e = offs[ray + 1];
         const float d[3] = {dirs[ray * 3 + 0], dirs[ray * 3 + 1], dirs[ray * 3 + 2]};
         float carry = 1.f, acc = 0.f;
-        float o[MAXD];
+        float o[DMAX];
 #pragma unroll
-        for (int k = 0; k < MAXD; ++k) o[k] = 0.f;
-        for (int base = b; base < e; base += 32) {
-            const int i = base + lane;
-            float a = 0.f;
-            if (i < e) {
-                const float g[3] = {grad[(size_t)i * 3 + 0], grad[(size_t)i * 3 + 1], grad[(size_t)i * 3 + 2]};
-                a = neus_alpha(sdf[i], g, d, dists[i], inv_s, cos_anneal).alpha;
+        for (int k = 0; k < DMAX; ++k) o[k] = 0.f;
+        for (int base = b; base < e; base += 32 * U) {
+            float s_[U], g_[U][3], dist_[U], v_[U][DMAX];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = base + u * 32 + lane;
+                const bool ok = i < e;
+                s_[u] = ok ? ldg_stream(sdf + i) : 0.f;
+                dist_[u] = ok ? ldg_stream(dists + i) : 0.f;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) g_[u][k] = ok ? ldg_stream(grad + (size_t)i * 3 + k) : 0.f;
+#pragma unroll
+                for (int k = 0; k < DMAX; ++k) v_[u][k] = (ok && k < D) ? ldg_stream(vals + (size_t)i * D + k) : 0.f;
             }
-            const float incl = warp_scan_mul(1.f - a, lane);
-            float excl = __shfl_up_sync(0xffffffffu, incl, 1);
-            if (lane == 0) excl = 1.f;
-            const float T = carry * excl;
-            const float w = a * T;
-            carry *= __shfl_sync(0xffffffffu, incl, 31);
-            if (i < e) {
-                alpha_out[i] = a;
-                weights[i] = w;
-                acc += w;
 #pragma unroll
-                for (int k = 0; k < MAXD; ++k)
-                    if (k < D) o[k] = fmaf(w, vals[(size_t)i * D + k], o[k]);
+            for (int u = 0; u < U; ++u) {
+                const int i = base + u * 32 + lane;
+                const bool ok = i < e;
+                const float a = ok ? neus_alpha(s_[u], g_[u], d, dist_[u], inv_s, cos_anneal).alpha : 0.f;
+                const float incl = warp_scan_mul(1.f - a, lane);
+                float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+                if (lane == 0) excl = 1.f;
+                const float T = carry * excl;
+                const float w = a * T;
+                carry *= __shfl_sync(0xffffffffu, incl, 31);
+                if (ok) {
+                    alpha_out[i] = a;
+                    weights[i] = w;
+                    acc += w;
+#pragma unroll
+                    for (int k = 0; k < DMAX; ++k) o[k] = fmaf(w, v_[u][k], o[k]);
+                }
             }
         }
         acc = warp_sum(acc);
 #pragma unroll
-        for (int k = 0; k < MAXD; ++k)
+        for (int k = 0; k < DMAX; ++k)
             if (k < D) o[k] = warp_sum(o[k]);
         if (lane == 0) {
             acc_out[ray] = acc;
 #pragma unroll
-            for (int k = 0; k < MAXD; ++k)
+            for (int k = 0; k < DMAX; ++k)
                 if (k < D) out[(size_t)ray * D + k] = o[k];
         }
     }
@@ -110,6 +128,7 @@ __global__ void __launch_bounds__(256) neus_composite_fwd_kernel(
 //   dL/dalpha_i = u_i T_i - (sum_{j>i} u_j w_j) / max(1-alpha_i, 1e-10)
 // (the running "total - prefix" form nerfacc's own backward uses), then through the
 // alpha formula into sdf, the SDF gradient (via true_cos) and inv_s.
+template <int DMAX, int U>
 __global__ void __launch_bounds__(256) neus_composite_bwd_kernel(
     const float* __restrict__ sdf, const float* __restrict__ grad, const float* __restrict__ dists,
     const float* __restrict__ dirs, const int32_t* __restrict__ offs, int n_rays, const float* __restrict__ variance,
@@ -125,69 +144,95 @@ __global__ void __launch_bounds__(256) neus_composite_bwd_kernel(
         const int b = offs[ray], e = offs[ray + 1];
         const float d[3] = {dirs[ray * 3 + 0], dirs[ray * 3 + 1], dirs[ray * 3 + 2]};
         const float ga = g_acc ? g_acc[ray] : 0.f;
-        float go[MAXD];
+        float go[DMAX];
 #pragma unroll
-        for (int k = 0; k < MAXD; ++k) go[k] = (k < D && g_out) ? g_out[(size_t)ray * D + k] : 0.f;
-        // pass 1: total = sum_i u_i w_i
+        for (int k = 0; k < DMAX; ++k) go[k] = (k < D && g_out) ? g_out[(size_t)ray * D + k] : 0.f;
+        // pass 1: total = sum_i u_i w_i (independent iterations: U of them in flight per lane; these reads leave the
+        // ray's samples in L1/L2 for pass 2)
         float total = 0.f;
-        for (int i = b + lane; i < e; i += 32) {
-            float u = ga + (g_w ? g_w[i] : 0.f);
+        for (int base = b; base < e; base += 32 * U) {
+            float w_[U], gw_[U], v_[U][DMAX];
 #pragma unroll
-            for (int k = 0; k < MAXD; ++k)
-                if (k < D) u = fmaf(go[k], vals[(size_t)i * D + k], u);
-            total = fmaf(u, weights[i], total);
+            for (int u = 0; u < U; ++u) {
+                const int i = base + u * 32 + lane;
+                const bool ok = i < e;
+                w_[u] = ok ? weights[i] : 0.f;
+                gw_[u] = (ok && g_w) ? g_w[i] : 0.f;
+#pragma unroll
+                for (int k = 0; k < DMAX; ++k) v_[u][k] = (ok && k < D) ? vals[(size_t)i * D + k] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                float uu = ga + gw_[u];
+#pragma unroll
+                for (int k = 0; k < DMAX; ++k) uu = fmaf(go[k], v_[u][k], uu);
+                total = fmaf(uu, w_[u], total);
+            }
         }
         total = warp_sum(total);
         // pass 2
         float carryT = 1.f, carryS = 0.f;
-        for (int base = b; base < e; base += 32) {
-            const int i = base + lane;
-            const bool ok = i < e;
-            float a = 0.f, u = 0.f, w = 0.f;
-            if (ok) {
-                a = alpha_in[i];
-                w = weights[i];
-                u = ga + (g_w ? g_w[i] : 0.f);
+        for (int base = b; base < e; base += 32 * U) {
+            float a_[U], w_[U], u_[U], s_[U], dist_[U], g_[U][3];
 #pragma unroll
-                for (int k = 0; k < MAXD; ++k)
-                    if (k < D) u = fmaf(go[k], vals[(size_t)i * D + k], u);
+            for (int u = 0; u < U; ++u) {
+                const int i = base + u * 32 + lane;
+                const bool ok = i < e;
+                a_[u] = ok ? ldg_stream(alpha_in + i) : 0.f;
+                w_[u] = ok ? ldg_stream(weights + i) : 0.f;
+                s_[u] = ok ? ldg_stream(sdf + i) : 0.f;
+                dist_[u] = ok ? ldg_stream(dists + i) : 0.f;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) g_[u][k] = ok ? ldg_stream(grad + (size_t)i * 3 + k) : 0.f;
+                float uu = ok ? ga + (g_w ? ldg_stream(g_w + i) : 0.f) : 0.f;
+                float v[DMAX];
+#pragma unroll
+                for (int k = 0; k < DMAX; ++k) v[k] = (ok && k < D) ? ldg_stream(vals + (size_t)i * D + k) : 0.f;
+#pragma unroll
+                for (int k = 0; k < DMAX; ++k) uu = fmaf(go[k], v[k], uu);
+                u_[u] = uu;
             }
-            const float incl = warp_scan_mul(1.f - a, lane);
-            float excl = __shfl_up_sync(0xffffffffu, incl, 1);
-            if (lane == 0) excl = 1.f;
-            const float T = carryT * excl;
-            carryT *= __shfl_sync(0xffffffffu, incl, 31);
-            const float pre = warp_scan_add(u * w, lane);
-            const float S = total - (carryS + pre);
-            carryS += __shfl_sync(0xffffffffu, pre, 31);
-            if (ok) {
-                const float dalpha = u * T - S / fmaxf(1.f - a, 1e-10f);
-                if (d_vals) {
 #pragma unroll
-                    for (int k = 0; k < MAXD; ++k)
-                        if (k < D) d_vals[(size_t)i * D + k] = w * go[k];
+            for (int u = 0; u < U; ++u) {
+                const int i = base + u * 32 + lane;
+                const bool ok = i < e;
+                const float a = a_[u], w = w_[u], uu = u_[u];
+                const float incl = warp_scan_mul(1.f - a, lane);
+                float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+                if (lane == 0) excl = 1.f;
+                const float T = carryT * excl;
+                carryT *= __shfl_sync(0xffffffffu, incl, 31);
+                const float pre = warp_scan_add(uu * w, lane);
+                const float S = total - (carryS + pre);
+                carryS += __shfl_sync(0xffffffffu, pre, 31);
+                if (ok) {
+                    const float dalpha = uu * T - S / fmaxf(1.f - a, 1e-10f);
+                    if (d_vals) {
+#pragma unroll
+                        for (int k = 0; k < DMAX; ++k)
+                            if (k < D) d_vals[(size_t)i * D + k] = w * go[k];
+                    }
+                    const float dist = dist_[u];
+                    const AlphaTerms t = neus_alpha(s_[u], g_[u], d, dist, inv_s, cos_anneal);
+                    float dsdf = 0.f, dtc = 0.f;
+                    if (t.raw >= 0.f && t.raw <= 1.f) {   // torch.clip passes the gradient inside [0,1]
+                        const float den = t.P + 1e-5f;
+                        const float dP = dalpha * t.Nx / (den * den);     // d alpha / d prev_cdf
+                        const float dN = -dalpha / den;                   // d alpha / d next_cdf
+                        const float dzp = dP * t.P * (1.f - t.P);         // wrt est_prev*inv_s
+                        const float dzn = dN * t.Nx * (1.f - t.Nx);       // wrt est_next*inv_s
+                        dsdf = (dzp + dzn) * inv_s;
+                        const float dic = (dzn - dzp) * inv_s * dist * 0.5f;
+                        const float dic_dtc = ((-t.tc * 0.5f + 0.5f) > 0.f ? 0.5f * (1.f - cos_anneal) : 0.f) +
+                                              ((-t.tc) > 0.f ? cos_anneal : 0.f);
+                        dtc = dic * dic_dtc;
+                        ds_total += dzp * t.est_prev + dzn * t.est_next;
+                    }
+                    d_sdf[i] = dsdf;
+                    d_grad[(size_t)i * 3 + 0] = dtc * d[0];
+                    d_grad[(size_t)i * 3 + 1] = dtc * d[1];
+                    d_grad[(size_t)i * 3 + 2] = dtc * d[2];
                 }
-                const float g[3] = {grad[(size_t)i * 3 + 0], grad[(size_t)i * 3 + 1], grad[(size_t)i * 3 + 2]};
-                const float dist = dists[i];
-                const AlphaTerms t = neus_alpha(sdf[i], g, d, dist, inv_s, cos_anneal);
-                float dsdf = 0.f, dtc = 0.f;
-                if (t.raw >= 0.f && t.raw <= 1.f) {   // torch.clip passes the gradient inside [0,1]
-                    const float den = t.P + 1e-5f;
-                    const float dP = dalpha * t.Nx / (den * den);     // d alpha / d prev_cdf
-                    const float dN = -dalpha / den;                   // d alpha / d next_cdf
-                    const float dzp = dP * t.P * (1.f - t.P);         // wrt est_prev*inv_s
-                    const float dzn = dN * t.Nx * (1.f - t.Nx);       // wrt est_next*inv_s
-                    dsdf = (dzp + dzn) * inv_s;
-                    const float dic = (dzn - dzp) * inv_s * dist * 0.5f;
-                    const float dic_dtc = ((-t.tc * 0.5f + 0.5f) > 0.f ? 0.5f * (1.f - cos_anneal) : 0.f) +
-                                          ((-t.tc) > 0.f ? cos_anneal : 0.f);
-                    dtc = dic * dic_dtc;
-                    ds_total += dzp * t.est_prev + dzn * t.est_next;
-                }
-                d_sdf[i] = dsdf;
-                d_grad[(size_t)i * 3 + 0] = dtc * d[0];
-                d_grad[(size_t)i * 3 + 1] = dtc * d[1];
-                d_grad[(size_t)i * 3 + 2] = dtc * d[2];
             }
         }
     }
@@ -220,8 +265,12 @@ extern "C" TF_API int tf_neus_composite_fwd(const float* sdf, const float* grad,
     int grid = (n_rays + wpb - 1) / wpb;
     const int cap = tf_num_sms() * 16;
     if (grid > cap) grid = cap;
-    neus_composite_fwd_kernel<<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(sdf, grad, dists, dirs, ray_offsets, n_rays, variance,
-                                                                          cos_anneal, vals, D, alpha, weights, acc, out);
+    if (D <= 8)
+        neus_composite_fwd_kernel<8, 4><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(sdf, grad, dists, dirs, ray_offsets, n_rays, variance,
+                                                                                    cos_anneal, vals, D, alpha, weights, acc, out);
+    else
+        neus_composite_fwd_kernel<MAXD, 2><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(sdf, grad, dists, dirs, ray_offsets, n_rays, variance,
+                                                                                       cos_anneal, vals, D, alpha, weights, acc, out);
     tf_count_launches(1);
     TF_CHECK_LAUNCH("tf_neus_composite_fwd");
     return 0;
@@ -241,9 +290,14 @@ extern "C" TF_API int tf_neus_composite_bwd(const float* sdf, const float* grad,
     int grid = (n_rays + wpb - 1) / wpb;
     const int cap = tf_num_sms() * 16;
     if (grid > cap) grid = cap;
-    neus_composite_bwd_kernel<<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(sdf, grad, dists, dirs, ray_offsets, n_rays, variance,
-                                                                          cos_anneal, vals, D, alpha, weights, g_acc, g_out,
-                                                                          g_weights, d_sdf, d_grad, d_vals, d_variance);
+    if (D <= 8)
+        neus_composite_bwd_kernel<8, 4><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(sdf, grad, dists, dirs, ray_offsets, n_rays, variance,
+                                                                                    cos_anneal, vals, D, alpha, weights, g_acc, g_out,
+                                                                                    g_weights, d_sdf, d_grad, d_vals, d_variance);
+    else
+        neus_composite_bwd_kernel<MAXD, 2><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(sdf, grad, dists, dirs, ray_offsets, n_rays, variance,
+                                                                                       cos_anneal, vals, D, alpha, weights, g_acc, g_out,
+                                                                                       g_weights, d_sdf, d_grad, d_vals, d_variance);
     tf_count_launches(1);
     TF_CHECK_LAUNCH("tf_neus_composite_bwd");
     return 0;

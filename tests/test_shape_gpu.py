@@ -143,7 +143,7 @@ def test_stencil_backward(C, H, A, G0, ups, N, with_level, monkeypatch):
         close_as_fp32(pc.grad, p64.grad, p32.grad, 1e-3, f"d {name}")
 
 
-def _composite_inputs(n_rays, max_s, seed):
+def _composite_inputs(n_rays, max_s, seed, D=7):
     g = torch.Generator().manual_seed(seed)
     counts = torch.randint(0, max_s + 1, (n_rays,), generator=g)
     counts[0] = 0
@@ -154,19 +154,23 @@ def _composite_inputs(n_rays, max_s, seed):
     grad = F.normalize(torch.randn(n, 3, generator=g), dim=-1) * (1 + 0.1 * torch.randn(n, 1, generator=g))
     dists = torch.rand(n, generator=g) * 0.02 + 0.002
     dirs = F.normalize(torch.randn(n_rays, 3, generator=g), dim=-1)
-    vals = torch.rand(n, 7, generator=g)
+    vals = torch.rand(n, D, generator=g)
     return idx, sdf, grad, dists, dirs, vals
 
 
-@pytest.mark.parametrize("cos_anneal", [0.0, 0.4, 1.0])
-def test_neus_composite(cos_anneal):
+@pytest.mark.parametrize("cos_anneal,max_s,D", [(0.0, 100, 7), (0.4, 100, 7), (1.0, 100, 7), (0.7, 700, 6), (0.7, 300, 13), (1.0, 40, 1)])
+def test_neus_composite(cos_anneal, max_s, D):
+    """ragged rays (0 .. max_s samples: one to several 128- / 64-sample iterations of the kernels' chunk loop), D <= 8 and
+    D > 8 accumulated channels (the two template instances)"""
     from tensoflow_b200 import ops
     from tensoflow_b200.shape_renderer import ray_offsets_from_indices
     dev = _cuda()
     n_rays = 333
-    idx, sdf, grad, dists, dirs, vals = _composite_inputs(n_rays, 100, 21)
+    idx, sdf, grad, dists, dirs, vals = _composite_inputs(n_rays, max_s, 21, D)
+    if max_s > 200:
+        sdf = sdf + 0.15                     # long rays: keep the transmittance alive beyond the first chunks
     g = torch.Generator().manual_seed(22)
-    u_acc, u_out = torch.randn(n_rays, generator=g), torch.randn(n_rays, 7, generator=g)
+    u_acc, u_out = torch.randn(n_rays, generator=g), torch.randn(n_rays, D, generator=g)
     u_w = torch.randn(sdf.shape[0], generator=g) * 0.1
 
     def run_oracle(dt):
