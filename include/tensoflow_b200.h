@@ -262,6 +262,22 @@ TF_API int tf_tv_fwd(const float* x, int32_t H, int32_t W, int32_t C, float* sum
 TF_API int tf_tv_bwd(const float* x, int32_t H, int32_t W, int32_t C, float scale_h, float scale_w,
                      const float* upstream, float* g, tf_stream_t stream);
 
+/* ---- occupancy-grid marcher ---------------------------------------------------------------------
+ * nerfacc.OccGridEstimator.sampling as the reference calls it (network/shapeRenderer.py:950-959, 1065-1072): fixed
+ * render_step_size, no cone angle, no visibility filter.  nerfacc is not vendored; the rule restated here:
+ *   t_k = near[r] + k * step;  interval [t_k, t_k + step] is kept iff its mid-point m satisfies m < far, o + d m lies
+ *   inside aabb = {lo xyz, hi xyz} and binaries[(cx * res[1] + cy) * res[2] + cz] != 0, c = floor((p - lo) / (hi - lo) * res).
+ * Two passes around a host-side exclusive prefix sum: counts[r] = kept intervals of ray r; then, with offsets[R+1],
+ * ray_indices / t_starts / t_ends [offsets[R]] are written ray after ray in marching order (nerfacc's packed format).
+ * `aabb` (6 floats) and `res` (3 ints) are HOST arrays; binaries is the device bool / uint8 grid. */
+TF_API int tf_occ_march_count(const float* rays_o, const float* rays_d, const float* near, int32_t n_rays, float far,
+                              float step, const float* aabb, const int32_t* res, const uint8_t* binaries, int32_t* counts,
+                              tf_stream_t stream);
+TF_API int tf_occ_march_write(const float* rays_o, const float* rays_d, const float* near, int32_t n_rays, float far,
+                              float step, const float* aabb, const int32_t* res, const uint8_t* binaries,
+                              const int32_t* offsets, int64_t* ray_indices, float* t_starts, float* t_ends,
+                              tf_stream_t stream);
+
 /* ---- optimizer step ------------------------------------------------------------------------------
  * torch.optim.Adam(grad_vars, betas=(0.9, 0.99)).step() of the reference trainer (train/trainer_inv.py:112,212; one
  * learning rate per parameter group, :247-248) as ONE streaming pass: for tensor t (numel[t] fp32 elements in any

@@ -188,7 +188,7 @@ class ShapeRenderer(torch.nn.Module):
         'device': 'cuda', 'gridSize': [512, 512, 512], 'aabb': [[-1.0, -1.0, -1.0], [1.0, 1.0, 1.0]], 'step_ratio': 0.5,
         'alphaMask_thres': 0.0001, 'sdf_n_comp': 16, 'sdf_dim': 128, 'app_dim': 128, 'sdf_multires': 0, 'max_levels': 1,
         'has_radiance_field': False, 'radiance_field_step': 0, 'predict_BG': False, 'isBGWhite': True, 'apply_mask_loss': False,
-        'mul_length': 10, 'use_occ_grid': False, 'shader_config': {},
+        'mul_length': 10, 'use_occ_grid': False, 'occ_grid_reso': 128, 'shader_config': {},
     }
 
     def __init__(self, cfg, training=True):
@@ -199,13 +199,14 @@ class ShapeRenderer(torch.nn.Module):
         c = self.cfg
         if c['predict_BG']:
             raise NotImplementedError("predict_BG raises in the reference too (shapeRenderer.py:1109-1110)")
-        if c['use_occ_grid']:
-            raise NotImplementedError("occupancy-grid marching is the next row (SURVEY.md 8f-2); hand packed samples to render_core")
         self.device = c['device']
         self.aabb = torch.tensor(c['aabb'].cpu().tolist() if isinstance(c['aabb'], torch.Tensor) else c['aabb'], device=self.device)
         self.radius = (self.aabb[1] - torch.mean(self.aabb, axis=0)).mean().float()
         self.alphaMask = None
         self.occ_grid = None
+        if c['use_occ_grid']:                                   # reference shapeRenderer.py:211-215
+            from .occ_grid import OccGridEstimator
+            self.occ_grid = OccGridEstimator(self.aabb.reshape(-1), resolution=c['occ_grid_reso']).to(self.device)
         self.update_stepSize(torch.tensor(c['gridSize']), c['max_levels'])
         self.sdf_network = TensoSDF(self.gridSize, self.aabb, device=self.device, init_n_levels=self.max_levels, sdf_n_comp=c['sdf_n_comp'],
                                     sdf_dim=c['sdf_dim'], app_dim=c['app_dim'], sdf_multires=c['sdf_multires'])
@@ -248,6 +249,8 @@ class ShapeRenderer(torch.nn.Module):
             vol = self.alphaMask.alpha_volume.bool().cpu().numpy()
             ckpt.update({'alphaMask.shape': vol.shape, 'alphaMask.mask': np.packbits(vol.reshape(-1)),
                          'alphaMask.aabb': self.alphaMask.aabb.cpu()})
+        if self.occ_grid is not None:
+            ckpt['occ_grid_state_dict'] = self.occ_grid.state_dict()
         return ckpt
 
     def load_ckpt(self, ckpt):
@@ -259,6 +262,8 @@ class ShapeRenderer(torch.nn.Module):
             length = int(np.prod(ckpt['alphaMask.shape']))
             vol = torch.from_numpy(np.unpackbits(ckpt['alphaMask.mask'])[:length].reshape(ckpt['alphaMask.shape']))
             self.alphaMask = AlphaGridMask(self.device, ckpt['alphaMask.aabb'].to(self.device), vol.float().to(self.device))
+        if 'occ_grid_state_dict' in ckpt and self.occ_grid is not None:
+            self.occ_grid.load_state_dict(ckpt['occ_grid_state_dict'], strict=False)
         self.load_state_dict(ckpt['network_state_dict'], strict=False)       # TensoSDF adopts the stored factor shapes
         kw = ckpt.get('kwargs')
         if kw is not None and (list(kw['gridSize']) != self.gridSize.tolist() or kw['max_levels'] != self.max_levels):
@@ -368,16 +373,67 @@ class ShapeRenderer(torch.nn.Module):
             mask = torch.zeros_like(mask)
             mask[indices] = 1
         if torch.sum(mask) > 0:
-            _, inter_prob, _ = get_intersection(self.sdf_inter_fun, self.deviation_network, points[mask], reflective[mask], sn0=64, sn1=16)
-            return F.l1_loss(occ_prob[mask], torch.sum(inter_prob, -1, keepdim=True))
+            if self.occ_grid is None:
+                _, inter_prob, _ = get_intersection(self.sdf_inter_fun, self.deviation_network, points[mask], reflective[mask], sn0=64, sn1=16)
+                return F.l1_loss(occ_prob[mask], torch.sum(inter_prob, -1, keepdim=True))
+            return F.l1_loss(occ_prob[mask], self.occ_grid_hit_probability(points[mask], reflective[mask]))
         return torch.zeros(1, device=points.device)
+
+    @torch.no_grad()
+    def occ_grid_hit_probability(self, pts, dirs):
+        """Occlusion probability of the secondary rays (pts, dirs) marched through the occupancy grid with the fixed step
+        (reference shapeRenderer.py:1055-1100) -> [pn,1]."""
+        occ_prob_gt = torch.zeros(pts.shape[0], 1, device=pts.device)
+        inside = torch.norm(pts, dim=-1) < 0.999
+        if torch.sum(inside) == 0:
+            return occ_prob_gt
+        pts, dirs = pts[inside].contiguous(), dirs[inside].contiguous()
+        pn = pts.shape[0]
+        step = float(self.stepSize)
+        max_dist = get_sphere_intersection(pts, dirs)
+        ray_indices, t0, t1 = self.occ_grid.sampling(pts, dirs, near_plane=step, far_plane=max_dist.max().item(), render_step_size=step,
+                                                     stratified=False)
+        if ray_indices.shape[0] == 0:
+            return occ_prob_gt
+        prev_points = pts[ray_indices] + dirs[ray_indices] * t0.unsqueeze(-1)
+        next_points = pts[ray_indices] + dirs[ray_indices] * t1.unsqueeze(-1)
+        prev_sdf = self.sdf_network.sdf(prev_points)[..., 0]
+        next_sdf = self.sdf_network.sdf(next_points)[..., 0]
+        mid_sdf = (prev_sdf + next_sdf) * 0.5
+        cos_val = (next_sdf - prev_sdf) / (t1 - t0 + 1e-5)
+        surface_mask = (cos_val < 0)
+        cos_val = torch.clamp(cos_val, max=0)
+        inv_s = self.deviation_network(prev_points).clip(1e-6, 1e6)[..., 0]
+        prev_cdf = torch.sigmoid((mid_sdf - cos_val * step * 0.5) * inv_s)
+        next_cdf = torch.sigmoid((mid_sdf + cos_val * step * 0.5) * inv_s)
+        alpha = (prev_cdf - next_cdf + 1e-5) / (prev_cdf + 1e-5) * surface_mask.float()
+        # nerfacc.render_weight_from_alpha + accumulate_along_rays(values=None): 1 - prod(1 - alpha) per ray, here through a
+        # segmented sum of log(1 - alpha) over the packed samples (no_grad target of an L1 loss)
+        log_t = torch.zeros(pn, device=pts.device).index_add_(0, ray_indices, torch.log1p(-alpha.clamp(max=1.0 - 1e-7)))
+        occ_prob_gt[inside] = (1.0 - torch.exp(log_t))[:, None]
+        return occ_prob_gt
+
+    @torch.no_grad()
+    def compute_alpha(self, points):
+        """reference shapeRenderer.py:972-993: opacity of one fixed-size step at `points` (the occupancy-grid refresh criterion)"""
+        if points.shape[0] == 0:
+            return torch.zeros(0, device=self.device)
+        sdf = self.sdf_network.sdf(points).squeeze(-1)
+        inv_s = self.deviation_network(points).clip(1e-6, 1e6)[..., 0]
+        prev_cdf = torch.sigmoid((sdf + self.stepSize * 0.5) * inv_s)
+        next_cdf = torch.sigmoid((sdf - self.stepSize * 0.5) * inv_s)
+        return ((prev_cdf - next_cdf + 1e-5) / (prev_cdf + 1e-5)).clip(0.0, 1.0)
 
     # ---- render (reference shapeRenderer.py:934-963, 1105-1277) --------------------------------------
     def render(self, ray_batch, near, far, human_poses=None, perturb_overwrite=-1, cos_anneal_ratio=0.0, is_train=True, step=None,
                t_rand=None):
         perturb = self.cfg['perturb'] if perturb_overwrite < 0 else perturb_overwrite
         rays_o, rays_d, dirs, radiis, rays_cos = (ray_batch[k] for k in ('rays_o', 'rays_d', 'dirs', 'radiis', 'rays_cos'))
-        t_starts, t_ends, ray_indices = self.sample_ray(rays_o, dirs, near, far, perturb, radiis=radiis, rays_cos=rays_cos, t_rand=t_rand)
+        if self.occ_grid is not None:                           # reference shapeRenderer.py:950-959
+            ray_indices, t_starts, t_ends = self.occ_grid.sampling(rays_o, dirs, near_plane=near.min().item(), far_plane=far.max().item(),
+                                                                   render_step_size=float(self.stepSize), stratified=is_train, noise=t_rand)
+        else:
+            t_starts, t_ends, ray_indices = self.sample_ray(rays_o, dirs, near, far, perturb, radiis=radiis, rays_cos=rays_cos, t_rand=t_rand)
         return self.render_core(rays_o, rays_d, dirs, radiis, rays_cos, t_starts, t_ends, ray_indices, human_poses,
                                 cos_anneal_ratio=cos_anneal_ratio, step=step, is_train=is_train)
 
@@ -389,7 +445,7 @@ class ShapeRenderer(torch.nn.Module):
         mid_t = (t_starts + t_ends) * 0.5
         dists = t_ends - t_starts
         points = rays_o[ray_indices] + viewdirs[ray_indices] * mid_t[:, None]
-        if self.alphaMask is not None:
+        if self.occ_grid is None and self.alphaMask is not None:                  # reference shapeRenderer.py:1119
             keep = self.alphaMask.sample_alpha(points) > 0
             ray_indices, mid_t, points, dists = ray_indices[keep], mid_t[keep], points[keep], dists[keep]
         N = ray_indices.shape[0]
@@ -467,6 +523,8 @@ class ShapeRenderer(torch.nn.Module):
 
     def forward(self, data):
         """reference shapeRenderer.py:1279-1306 (training branch)"""
+        if self.occ_grid is not None:                           # reference shapeRenderer.py:1285-1290
+            self.occ_grid.update_every_n_steps(step=data['step'], occ_eval_fn=self.compute_alpha, n=100, warmup_steps=10000)
         self.color_network.envlight.build_mips()
         return self.train_step(data['step'])
 
