@@ -104,9 +104,15 @@ def test_shape_renderer_with_occ_grid():
     loss.backward()
     assert m.sdf_network.sdf_plane[0].grad is not None and float(m.sdf_network.sdf_plane[0].grad.abs().sum()) > 0
     assert float(out['acc'].max()) > 0.5
-    # skipping empty cells must not change the picture much: compare with the full grid
+    # skipping empty cells must not change the picture much: compare with the full grid.  With the initial inv_s = 20 the NeuS
+    # opacity has long tails (alpha ~ 0.01 a fifth of the box away from the surface), so sharpen the surface first and refresh
+    # the grid a few times (one random probe per cell and refresh; the EMA keeps the maximum)
     near, far = near_far_from_sphere(rays['rays_o'], rays['dirs'], float(m.radius))
     with torch.no_grad():
+        m.deviation_network.variance.fill_(0.5)
+        for _ in range(6):
+            m.occ_grid._update(0, m.compute_alpha, warmup_steps=10)
+        assert 0.0 < float(m.occ_grid.binaries.float().mean()) < 0.9
         a = m.render(rays, near, far, None, perturb_overwrite=0, is_train=False, step=30001)['ray_rgb']
         m.occ_grid.mark_all_occupied()
         b = m.render(rays, near, far, None, perturb_overwrite=0, is_train=False, step=30001)['ray_rgb']
