@@ -77,6 +77,31 @@ def occlusion_probability(sdf_fun, inv_s, pts, dirs, sn0=64, sn1=16):        # n
     return out
 
 
+def surface_refine(field, inv_s, rays_o, rays_d, m_depth, unit_size, radius, sn0=32, sn1=9):
+    """MaterialRenderer.get_intersection_around_mesh + the tail of trace_sdf_with_mesh (materialRenderer.py:281-343) for rays
+    that hit the mesh at depth m_depth [pn,1]: NeuS weights on sn0 samples within +-4 voxels, sn1 deterministic importance samples,
+    depth = weighted mean of their mid-points, normal = normalised FD gradient flipped against the ray.
+    -> (depth [pn,1], points [pn,3], normals [pn,3])"""
+    with torch.no_grad():
+        sdf_fun = lambda x: field.sdf(x, None).reshape(-1)
+        near, far = near_far_from_sphere(rays_o, rays_d, radius)
+        t_min = torch.minimum(torch.maximum(m_depth - unit_size * 4, near), far)
+        t_max = torch.minimum(torch.maximum(m_depth + unit_size * 4, near), far)
+        z = t_min + (t_max - t_min) * torch.linspace(0.0, 1.0, sn0, dtype=rays_o.dtype)[None, :]
+        w = probe_weights(sdf_fun, inv_s, z, rays_o, rays_d)
+        z_new = sample_pdf_det(z, w, sn1)
+        w = probe_weights(sdf_fun, inv_s, z_new, rays_o, rays_d)
+        z_mid = (z_new[:, 1:] + z_new[:, :-1]) * 0.5
+        w = w / torch.sum(w, dim=-1, keepdim=True)
+        w = torch.where(torch.isnan(w), torch.full_like(w, 1.0 / (sn1 - 1)), w)
+        depth = torch.sum(w * z_mid, -1, keepdim=True)
+        pts = rays_o + depth * rays_d
+    g, _ = field.gradient(pts, None)
+    n = F.normalize(g.detach(), dim=-1)
+    n = torch.where((n * rays_d).sum(-1, keepdim=True) >= 0, -n, n)
+    return depth, pts, n
+
+
 class ShapeRenderer(nn.Module):
     def __init__(self, gridSize, sdf_n_comp=16, sdf_dim=128, app_dim=128, max_levels=1, has_radiance_field=False,
                  radiance_field_step=0, n_samples=64, n_importance=64, up_sample_steps=4, clip_sample_variance=True,

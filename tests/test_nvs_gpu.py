@@ -74,22 +74,8 @@ def test_surface_points_match_oracle():
     oh, dh, m_depth = o[hit].cpu().double(), d[hit].cpu().double(), depth0[hit].cpu().double()
     inv_s = float(mat.deviation_net(torch.zeros(1, 3, device=dev))[0, 0])
     unit = float(mat.unit_size)
-    with torch.no_grad():
-        sdf_fun = lambda x: f64.sdf(x, None).reshape(-1)
-        near, far = RR.near_far_from_sphere(oh, dh, float(mat.radius))
-        t_min = torch.minimum(torch.maximum(m_depth - unit * 4, near), far)
-        t_max = torch.minimum(torch.maximum(m_depth + unit * 4, near), far)
-        z = t_min + (t_max - t_min) * torch.linspace(0, 1, 32, dtype=torch.float64)[None]
-        w = RR.probe_weights(sdf_fun, inv_s, z, oh, dh)
-        z_new = RR.sample_pdf_det(z, w, 9)
-        w = RR.probe_weights(sdf_fun, inv_s, z_new, oh, dh)
-        w = w / w.sum(-1, keepdim=True)
-        w = torch.where(torch.isnan(w), torch.full_like(w, 1 / 8), w)
-        dep = (w * (z_new[:, 1:] + z_new[:, :-1]) * 0.5).sum(-1, keepdim=True)
-        pts = oh + dep * dh
-        g, _ = f64.gradient(pts, None)
-        n = F.normalize(g, dim=-1)
-        n = torch.where((n * dh).sum(-1, keepdim=True) >= 0, -n, n)
+    # oracle/torch_oracle_renderer.surface_refine is pinned to the reference's own trace_sdf_with_mesh (tests/test_oracle_cpu.py)
+    dep, pts, n = RR.surface_refine(f64, inv_s, oh, dh, m_depth, unit, float(mat.radius), 32, 9)
     assert rel_err(depth[hit], dep) < 1e-4
     assert rel_err(inters[hit], pts) < 1e-4
     # FD normals divide by the voxel size: same bar as the stencil tests (a few 1e-4 absolute on unit vectors)

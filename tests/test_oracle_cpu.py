@@ -84,3 +84,45 @@ def test_oracle_matches_reference_tensosdf():
     (a.sum() + ga.sum()).backward(); (b.sum() + gb.sum()).backward()
     for (n, p), (_, q) in zip(ref.named_parameters(), mine.named_parameters()):
         assert rel_err(q.grad, p.grad) < 1e-5, n
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present")
+def test_surface_refine_matches_reference_material_renderer():
+    """oracle surface_refine == the reference's own MaterialRenderer.trace_sdf_with_mesh (materialRenderer.py:315-343) driven by
+    a stand-in tracer (the mesh depth is an input of both)."""
+    import types
+    ref_shim.install()
+    import network.fields as RF
+    import network.materialRenderer as MR
+    from oracle import torch_oracle_renderer as RR
+    torch.manual_seed(0)
+    G = torch.tensor([32, 32, 32]); aabb = torch.tensor([[-1., -1, -1], [1, 1, 1]])
+    ref_field = RF.TensoSDF(G, aabb, device='cpu', sdf_n_comp=8, sdf_dim=32, app_dim=16, init_n_levels=1, sdf_multires=0)
+    with torch.no_grad():
+        for p in list(ref_field.sdf_plane) + list(ref_field.sdf_line):
+            p.add_(5e-3 * torch.randn_like(p))
+    mine = O.TensoSDF(G, aabb, sdf_n_comp=8, sdf_dim=32, app_dim=16, init_n_levels=1)
+    mine.load_state_dict({k: v for k, v in ref_field.state_dict().items() if 'gaussian' not in k}, strict=False)
+    pn = 200
+    o = torch.nn.functional.normalize(torch.randn(pn, 3), dim=-1) * 2.0
+    d = torch.nn.functional.normalize((torch.rand(pn, 3) - 0.5) * 0.2 - o, dim=-1)
+    m_depth = 2.0 - 0.22 + 0.05 * torch.randn(pn, 1)                 # a bumpy sphere of radius ~0.22 seen from distance 2
+    hit = torch.rand(pn) < 0.8
+    inv_s = 20.0
+    unit = torch.mean((aabb[1] - aabb[0]) / (G - 1))
+    radius = (aabb[1] - aabb.mean(0)).mean()
+
+    fake = types.SimpleNamespace()
+    fake.radius, fake.unit_size, fake.sdf_network = radius, unit, ref_field
+    fake.sdf_inter_fun = lambda x: ref_field.sdf(x, None)
+    fake.deviation_net = lambda x: torch.full_like(x[..., :1], inv_s)
+    fake.near_far_from_sphere = types.MethodType(MR.MaterialRenderer.near_far_from_sphere, fake)
+    fake.get_intersection_around_mesh = types.MethodType(MR.MaterialRenderer.get_intersection_around_mesh, fake)
+    fake.trace = lambda ro, rd: (ro + m_depth * rd, -rd.clone(), torch.where(hit[:, None], m_depth, torch.full_like(m_depth, 10.0)).clone(),
+                                 hit[:, None].clone())
+    inters, normals, depth, hit_out = MR.MaterialRenderer.trace_sdf_with_mesh(fake, o, d, 32, 9)
+    dep, pts, n = RR.surface_refine(mine, inv_s, o[hit], d[hit], m_depth[hit], float(unit), float(radius), 32, 9)
+    assert torch.equal(hit_out.squeeze(-1), hit)
+    assert rel_err(dep, depth[hit]) < 1e-6
+    assert rel_err(pts, inters[hit]) < 1e-6
+    assert float((n - normals[hit]).abs().max()) < 1e-4
