@@ -139,13 +139,14 @@ TF_API int tf_neus_composite_fwd(const float* sdf, const float* grad, const floa
                           const float* variance, float cos_anneal, const float* vals, int32_t D,
                           float* alpha, float* weights, float* acc, float* out,
                           tf_stream_t stream);
-/* g_weights may be NULL.  d_variance is a device scalar accumulated atomically
- * (pass NULL when inv_s is frozen: network/shapeRenderer.py:1007-1008). */
+/* alpha, weights, acc, out are the forward's outputs (acc / out give sum_i u_i w_i without a pass over the samples).
+ * g_acc, g_out, g_weights may each be NULL (no upstream gradient on that output).  d_variance is a device scalar
+ * accumulated atomically (pass NULL when inv_s is frozen: network/shapeRenderer.py:1007-1008). */
 TF_API int tf_neus_composite_bwd(const float* sdf, const float* grad, const float* dists,
                           const float* dirs, const int32_t* ray_offsets, int32_t n_rays,
                           const float* variance, float cos_anneal, const float* vals, int32_t D,
-                          const float* alpha, const float* weights, const float* g_acc,
-                          const float* g_out, const float* g_weights, float* d_sdf,
+                          const float* alpha, const float* weights, const float* acc, const float* out,
+                          const float* g_acc, const float* g_out, const float* g_weights, float* d_sdf,
                           float* d_grad, float* d_vals, float* d_variance, tf_stream_t stream);
 
 /* ---- small MLP layers (tall-skinny fused linear) -------------------------------

@@ -59,7 +59,7 @@ _SIGNATURES = {
     "tf_neus_composite_fwd": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, _P, C.c_float, _P, C.c_int32,
                                         _P, _P, _P, _P, _P]),
     "tf_neus_composite_bwd": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, _P, C.c_float, _P, C.c_int32,
-                                        _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+                                        _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
 }
 
 # later sections of the ABI (small MLP layers, flow sampler, MC shading, BVH)

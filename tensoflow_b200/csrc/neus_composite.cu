@@ -133,7 +133,8 @@ __global__ void __launch_bounds__(256) neus_composite_bwd_kernel(
     const float* __restrict__ sdf, const float* __restrict__ grad, const float* __restrict__ dists,
     const float* __restrict__ dirs, const int32_t* __restrict__ offs, int n_rays, const float* __restrict__ variance,
     float cos_anneal, const float* __restrict__ vals, int D, const float* __restrict__ alpha_in,
-    const float* __restrict__ weights, const float* __restrict__ g_acc, const float* __restrict__ g_out,
+    const float* __restrict__ weights, const float* __restrict__ acc_in, const float* __restrict__ out_in,
+    const float* __restrict__ g_acc, const float* __restrict__ g_out,
     const float* __restrict__ g_w, float* __restrict__ d_sdf, float* __restrict__ d_grad, float* __restrict__ d_vals,
     float* __restrict__ d_variance) {
     const int lane = threadIdx.x & 31;
@@ -147,29 +148,29 @@ __global__ void __launch_bounds__(256) neus_composite_bwd_kernel(
         float go[DMAX];
 #pragma unroll
         for (int k = 0; k < DMAX; ++k) go[k] = (k < D && g_out) ? g_out[(size_t)ray * D + k] : 0.f;
-        // pass 1: total = sum_i u_i w_i (independent iterations: U of them in flight per lane; these reads leave the
-        // ray's samples in L1/L2 for pass 2)
-        float total = 0.f;
-        for (int base = b; base < e; base += 32 * U) {
-            float w_[U], gw_[U], v_[U][DMAX];
+        // total = sum_i u_i w_i with u_i = g_acc + g_out . vals_i + g_w_i.  The first two terms are the forward's own per-ray
+        // results, sum_i w_i = acc and sum_i w_i vals_i = out, so no pass over the samples is needed for them; only an upstream
+        // gradient on the weights themselves (g_w) needs one (8 B/sample, U chunks in flight).
+        float total = ga * acc_in[ray];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int i = base + u * 32 + lane;
-                const bool ok = i < e;
-                w_[u] = ok ? weights[i] : 0.f;
-                gw_[u] = (ok && g_w) ? g_w[i] : 0.f;
+        for (int k = 0; k < DMAX; ++k)
+            if (k < D) total = fmaf(go[k], out_in[(size_t)ray * D + k], total);
+        if (g_w) {
+            float part = 0.f;
+            for (int base = b; base < e; base += 32 * U) {
+                float w_[U], gw_[U];
 #pragma unroll
-                for (int k = 0; k < DMAX; ++k) v_[u][k] = (ok && k < D) ? vals[(size_t)i * D + k] : 0.f;
+                for (int u = 0; u < U; ++u) {
+                    const int i = base + u * 32 + lane;
+                    const bool ok = i < e;
+                    w_[u] = ok ? weights[i] : 0.f;
+                    gw_[u] = ok ? g_w[i] : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) part = fmaf(gw_[u], w_[u], part);
             }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                float uu = ga + gw_[u];
-#pragma unroll
-                for (int k = 0; k < DMAX; ++k) uu = fmaf(go[k], v_[u][k], uu);
-                total = fmaf(uu, w_[u], total);
-            }
+            total += warp_sum(part);
         }
-        total = warp_sum(total);
         // pass 2
         float carryT = 1.f, carryS = 0.f;
         for (int base = b; base < e; base += 32 * U) {
@@ -279,6 +280,7 @@ extern "C" TF_API int tf_neus_composite_fwd(const float* sdf, const float* grad,
 extern "C" TF_API int tf_neus_composite_bwd(const float* sdf, const float* grad, const float* dists, const float* dirs,
                                      const int32_t* ray_offsets, int32_t n_rays, const float* variance, float cos_anneal,
                                      const float* vals, int32_t D, const float* alpha, const float* weights,
+                                     const float* acc, const float* out,
                                      const float* g_acc, const float* g_out, const float* g_weights, float* d_sdf,
                                      float* d_grad, float* d_vals, float* d_variance, tf_stream_t stream) {
     if (n_rays == 0) return 0;
@@ -286,17 +288,18 @@ extern "C" TF_API int tf_neus_composite_bwd(const float* sdf, const float* grad,
     TF_REQUIRE(d_sdf && d_grad, "an output pointer is NULL");
     TF_REQUIRE(D >= 0 && D <= MAXD, "D must be in [0,%d] (got %d)", MAXD, D);
     TF_REQUIRE(D == 0 || vals, "vals is NULL with D > 0");
+    TF_REQUIRE(acc && (D == 0 || out), "the forward's acc / out are needed by the backward");
     const int wpb = 8;
     int grid = (n_rays + wpb - 1) / wpb;
     const int cap = tf_num_sms() * 16;
     if (grid > cap) grid = cap;
     if (D <= 8)
         neus_composite_bwd_kernel<8, 4><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(sdf, grad, dists, dirs, ray_offsets, n_rays, variance,
-                                                                                    cos_anneal, vals, D, alpha, weights, g_acc, g_out,
+                                                                                    cos_anneal, vals, D, alpha, weights, acc, out, g_acc, g_out,
                                                                                     g_weights, d_sdf, d_grad, d_vals, d_variance);
     else
         neus_composite_bwd_kernel<MAXD, 2><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(sdf, grad, dists, dirs, ray_offsets, n_rays, variance,
-                                                                                       cos_anneal, vals, D, alpha, weights, g_acc, g_out,
+                                                                                       cos_anneal, vals, D, alpha, weights, acc, out, g_acc, g_out,
                                                                                        g_weights, d_sdf, d_grad, d_vals, d_variance);
     tf_count_launches(1);
     TF_CHECK_LAUNCH("tf_neus_composite_bwd");

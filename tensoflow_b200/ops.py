@@ -330,25 +330,27 @@ class NeusCompositeFunction(torch.autograd.Function):
         out = torch.empty(R, D, device=dev, dtype=torch.float32)
         if n == 0:   # no samples at all: every ray composites to zero
             acc.zero_(); out.zero_()
-            ctx.save_for_backward(sdf_c, grad_c, dists_c, dirs_c, offs, var_c, vals_c, alpha, weights)
+            ctx.save_for_backward(sdf_c, grad_c, dists_c, dirs_c, offs, var_c, vals_c, alpha, weights, acc, out)
             ctx.cos_anneal, ctx.train_variance, ctx.var_shape = float(cos_anneal), bool(train_variance), variance.shape
             ctx.mark_non_differentiable(alpha)
+            ctx.set_materialize_grads(False)
             return alpha, weights, acc, out
         with _timed("neus_composite_fwd"):
           check(lib.tf_neus_composite_fwd(ptr(sdf_c), ptr(grad_c), ptr(dists_c), ptr(dirs_c), ptr(offs), R, ptr(var_c),
                                         float(cos_anneal), ptr(vals_c), D, ptr(alpha), ptr(weights), ptr(acc), ptr(out),
                                         stream_ptr()), "tf_neus_composite_fwd")
-        ctx.save_for_backward(sdf_c, grad_c, dists_c, dirs_c, offs, var_c, vals_c, alpha, weights)
+        ctx.save_for_backward(sdf_c, grad_c, dists_c, dirs_c, offs, var_c, vals_c, alpha, weights, acc, out)
         ctx.cos_anneal = float(cos_anneal)
         ctx.train_variance = bool(train_variance)
         ctx.var_shape = variance.shape
         ctx.mark_non_differentiable(alpha)
+        ctx.set_materialize_grads(False)       # an unused output (usually `weights`) reaches backward as None, not as zeros [N]
         return alpha, weights, acc, out
 
     @staticmethod
     def backward(ctx, _g_alpha, g_weights, g_acc, g_out):
         lib = _lib.load()
-        sdf_c, grad_c, dists_c, dirs_c, offs, var_c, vals_c, alpha, weights = ctx.saved_tensors
+        sdf_c, grad_c, dists_c, dirs_c, offs, var_c, vals_c, alpha, weights, acc, out = ctx.saved_tensors
         n, R = sdf_c.shape[0], dirs_c.shape[0]
         D = 0 if vals_c is None else int(vals_c.shape[1])
         dev = sdf_c.device
@@ -361,8 +363,8 @@ class NeusCompositeFunction(torch.autograd.Function):
             return d_sdf, d_grad, None, None, None, dv, None, d_vals, None
         with _timed("neus_composite_bwd"):
           check(lib.tf_neus_composite_bwd(ptr(sdf_c), ptr(grad_c), ptr(dists_c), ptr(dirs_c), ptr(offs), R, ptr(var_c),
-                                        ctx.cos_anneal, ptr(vals_c), D, ptr(alpha), ptr(weights), ptr(_f32c(g_acc)),
-                                        ptr(_f32c(g_out)), ptr(_f32c(g_weights)), ptr(d_sdf), ptr(d_grad), ptr(d_vals),
+                                        ctx.cos_anneal, ptr(vals_c), D, ptr(alpha), ptr(weights), ptr(acc), ptr(out),
+                                        ptr(_f32c(g_acc)), ptr(_f32c(g_out)), ptr(_f32c(g_weights)), ptr(d_sdf), ptr(d_grad), ptr(d_vals),
                                         ptr(d_var), stream_ptr()), "tf_neus_composite_bwd")
         dv = None if d_var is None else d_var.reshape(ctx.var_shape)
         return d_sdf, d_grad, None, None, None, dv, None, d_vals, None
