@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the TensoFlow hot path on B200 (see the contract in DESIGN.md).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload shape|material]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 Default workload = BASELINE.json configs[1]: shape stage, VM field 512^3 (C=36, H=256,
 A=128, 3 mip levels), 8192-ray batch x 512 samples, forward + backward
@@ -11,6 +11,10 @@ its own 8192-ray batch (weak scaling) and the VM-factor / MLP gradients are summ
 flat-bucket NCCL allreduce inside the timed region.
 
 Prints ONE JSON line on rank 0.
+
+The other BASELINE.json configurations have their own scripts (same timing rules, one JSON line each):
+scripts/bench_material.py (config 3), scripts/bench_joint.py (config 4, torchrun), scripts/bench_relight.py (config 5,
+torchrun), scripts/bench_shape_renderer.py (the full ShapeRenderer.forward module path), scripts/bench_adam.py (optimizer step).
 """
 from __future__ import annotations
 
