@@ -167,7 +167,7 @@ class MCShadingNetwork(nn.Module):
 
     def __init__(self, ray_trace_fun: Callable, aabb, gridSize=(512, 512, 512), mat_n_comp=36, flow_grid=(512, 512, 512),
                  light_reso=128, diffuse_sample_num=512, specular_sample_num=256, nis_diffuse_sample_num=64,
-                 nis_specular_sample_num=32, exp_max=5.0, dtype=torch.float32):
+                 nis_specular_sample_num=32, exp_max=5.0, dtype=torch.float32, outer_light_version='envlight'):
         super().__init__()
         self.register_buffer("aabb", torch.as_tensor(aabb, dtype=dtype).clone())
         self.n_levels = 3
@@ -181,7 +181,12 @@ class MCShadingNetwork(nn.Module):
         self.metallic_predictor = make_predictor(2, fd, 1).to(dtype)
         self.roughness_predictor = make_predictor(2, fd, 1).to(dtype)
         self.albedo_predictor = make_predictor(2, fd, 3).to(dtype)
-        self.outer_light = EnvLight(light_reso, dtype)
+        self.outer_light_version = outer_light_version
+        if outer_light_version == 'envlight':                                 # fields.py:716-723
+            self.outer_light = EnvLight(light_reso, dtype)
+        else:
+            self.outer_light = make_predictor(4, 72 if outer_light_version == 'direction' else 144, 3, 'exp', exp_max).to(dtype)
+            nn.init.constant_(self.outer_light[-2].bias, math.log(0.5))
         self.inner_light = make_predictor(4, 51 + 72, 3, 'exp', exp_max).to(dtype)
         nn.init.constant_(self.inner_light[-2].bias, math.log(0.5))
         self.register_buffer("diffuse_direction_samples", direction_samples(diffuse_sample_num, dtype))
@@ -210,6 +215,17 @@ class MCShadingNetwork(nn.Module):
         return metallic, roughness, albedo
 
     # ---- lights (fields.py:905-975) -----------------------------------------------------------
+    def predict_outer_lights(self, points, directions):                       # fields.py:913-933
+        if self.outer_light_version == 'envlight':
+            return self.outer_light.direct_light(directions)
+        enc = ide_encode(directions, 0)
+        if self.outer_light_version == 'direction':
+            return self.outer_light(enc)
+        pts = torch.where((torch.norm(points, dim=-1) > 0.999)[:, None], points * 0.999, points)
+        dtx = torch.sum(pts * directions, dim=-1, keepdim=True)                # utils/network_utils.py:108-114
+        dist = -dtx + torch.sqrt(dtx ** 2 - torch.sum(pts ** 2, dim=-1, keepdim=True) + 1 + 1e-6)
+        return self.outer_light(torch.cat([enc, ide_encode(pts + directions * dist, 0)], -1))
+
     def get_lights(self, points, directions):
         shape = points.shape[:-1]
         eps = 1e-5
@@ -219,7 +235,7 @@ class MCShadingNetwork(nn.Module):
         lights = torch.zeros(*shape, 3, dtype=points.dtype, device=points.device)
         miss = ~hit
         if miss.any():
-            lights[miss] = self.outer_light.direct_light(directions[miss])
+            lights[miss] = self.predict_outer_lights(points[miss], directions[miss])
         if hit.any():
             p, v, n = inters[hit], -directions[hit], normals[hit]
             n, v = F.normalize(n, dim=-1), F.normalize(v, dim=-1)

@@ -2,8 +2,8 @@
 EnvLight, network/materialRenderer.py) on the sm_100a kernels.
 
 In-scope branches: shade_mixed, use_nis_diffuse + use_nis_specular with the
-half-vector parametrisation, outer_light_version='envlight', geometry_type='schlick', no
-human lights.  Parameter names follow the reference so its checkpoints load
+half-vector parametrisation, outer_light_version='envlight' | 'direction' | 'sphere_direction',
+geometry_type='schlick', no human lights.  Parameter names follow the reference so its checkpoints load
 (`mat_plane.*`, `mat_line.*`, `*_predictor.*`, `outer_light.base`, `inner_light.*`,
 `flow_{diffuse,specular}[_copy].*`); the reference's dead weights (`feats_network`,
 `mat_n_comp_mat`) are not instantiated.
@@ -182,10 +182,12 @@ class MCShadingNetwork(nn.Module):
         super().__init__()
         self.cfg = {**self.default_cfg, **cfg}
         c = self.cfg
-        if c['outer_light_version'] != 'envlight' or c['human_lights'] or c['shade_fn'] != 'shade_mixed' \
-                or c['geometry_type'] != 'schlick' or not (c['use_half_diffuse'] and c['use_half_specular']):
-            raise NotImplementedError("tensoflow_b200 implements the shipped material configuration "
-                                      "(envlight, shade_mixed, half-vector flows, schlick geometry)")
+        if c['outer_light_version'] not in ('envlight', 'direction', 'sphere_direction') or c['human_lights'] \
+                or c['shade_fn'] != 'shade_mixed' or c['geometry_type'] != 'schlick' \
+                or not (c['use_half_diffuse'] and c['use_half_specular']):
+            raise NotImplementedError("tensoflow_b200 implements the shipped material configurations "
+                                      "(envlight / direction / sphere_direction outer light, shade_mixed, half-vector flows, "
+                                      "schlick geometry, no human lights)")
         dev = c['device']
         self.aabb = torch.as_tensor(aabb, dtype=torch.float32).to(dev)
         self.use_nis = True
@@ -202,7 +204,11 @@ class MCShadingNetwork(nn.Module):
         self.metallic_predictor = make_predictor(2, self.mat_feature_dim, 1).to(dev)
         self.roughness_predictor = make_predictor(2, self.mat_feature_dim, 1).to(dev)
         self.albedo_predictor = make_predictor(2, self.mat_feature_dim, 3).to(dev)
-        self.outer_light = EnvLight(trainable=True, max_res=c['light_reso'], device=dev)
+        if c['outer_light_version'] == 'envlight':              # reference fields.py:716-723
+            self.outer_light = EnvLight(trainable=True, max_res=c['light_reso'], device=dev)
+        else:                                                    # 4-layer MLP on the IDE of the direction (+ of the sphere exit point)
+            self.outer_light = make_predictor(4, 72 if c['outer_light_version'] == 'direction' else 144, 3).to(dev)
+            nn.init.constant_(self.outer_light[-2].bias, np.log(0.5))
         self.inner_light = make_predictor(4, 51 + 72, 3).to(dev)
         nn.init.constant_(self.inner_light[-2].bias, np.log(0.5))
         for name, n in (('diffuse_direction_samples', c['diffuse_sample_num']), ('specular_direction_samples', c['specular_sample_num'])):
@@ -219,7 +225,7 @@ class MCShadingNetwork(nn.Module):
     # ---- bookkeeping --------------------------------------------------------------------
     def get_optparam_groups(self, lr_init_spatialxyz=0.02, lr_init_network=0.001, lr_init_env=0.1):
         g = [{'params': self.mat_line, 'lr': lr_init_spatialxyz}, {'params': self.mat_plane, 'lr': lr_init_spatialxyz},
-             {'params': self.outer_light.parameters(), 'lr': lr_init_env},
+             {'params': self.outer_light.parameters(), 'lr': lr_init_env if self.cfg['outer_light_version'] == 'envlight' else lr_init_network},
              {'params': list(self.albedo_predictor.parameters()) + list(self.metallic_predictor.parameters())
               + list(self.roughness_predictor.parameters()) + list(self.inner_light.parameters()), 'lr': lr_init_network}]
         g += self.flow_diffuse.get_optparam_groups(lr_init_spatialxyz, lr_init_network)
@@ -236,7 +242,8 @@ class MCShadingNetwork(nn.Module):
                 copy.load_state_dict(getattr(self, f'flow_{kind}').state_dict())
                 for p in copy.parameters():
                     p.requires_grad = False
-        if (step + 1) % c['light_upsample_interval'] == 0:
+        if (step + 1) % c['light_upsample_interval'] == 0 and c['outer_light_version'] == 'envlight':
+            # (the reference calls .upsample() on the MLP lights too and raises there: fields.py:1067-1068)
             self.outer_light.upsample()
 
     # ---- materials (reference fields.py:776-810, 1010-1017) ------------------------------------
@@ -274,7 +281,22 @@ class MCShadingNetwork(nn.Module):
             inters, hit_normals, depth, hit = self.ray_trace_fun(o, dirs.reshape(-1, 3))
             hit = hit.reshape(-1)
             near = (depth.reshape(-1, 1) > eps).to(torch.float32)
-        lights = self.outer_light.direct_light(dirs.reshape(-1, 3), None, ~hit)
+        flat_dirs = dirs.reshape(-1, 3)
+        if self.cfg['outer_light_version'] == 'envlight':
+            lights = self.outer_light.direct_light(flat_dirs, None, ~hit)
+        else:                                                    # reference fields.py:913-928, on the directions that miss
+            lights = torch.zeros(pn * D, 3, device=pts.device)
+            midx = torch.nonzero(~hit)[:, 0]
+            if midx.numel() > 0:
+                d = flat_dirs[midx]
+                enc = ide_encode(d)
+                if self.cfg['outer_light_version'] == 'sphere_direction':
+                    p = pts[torch.div(midx, D, rounding_mode='floor')]
+                    p = torch.where((torch.norm(p, dim=-1) > 0.999)[:, None], p * 0.999, p)
+                    dtx = torch.sum(p * d, dim=-1, keepdim=True)             # get_sphere_intersection, utils/network_utils.py:108-114
+                    dist = -dtx + torch.sqrt(dtx ** 2 - torch.sum(p ** 2, dim=-1, keepdim=True) + 1 + 1e-6)
+                    enc = torch.cat([enc, ide_encode(p + d * dist)], -1)
+                lights = lights.index_add(0, midx, run_predictor(self.outer_light, enc, "exp", self.cfg['light_exp_max']))
         idx = torch.nonzero(hit)[:, 0]
         if idx.numel() > 0:                                           # occluded directions: indirect-light MLP
             p, v, n = inters[idx], -dirs.reshape(-1, 3)[idx], F.normalize(hit_normals[idx], dim=-1)
@@ -626,5 +648,6 @@ class MaterialRenderer(nn.Module):
         return out
 
     def forward(self, data):
-        self.shader_network.outer_light.build_mips_direct()          # materialRenderer.py:760-761
+        if self.shader_network.cfg['outer_light_version'] == 'envlight':
+            self.shader_network.outer_light.build_mips_direct()      # materialRenderer.py:760-761
         return self.train_step(data['step'], data.get('noise'))

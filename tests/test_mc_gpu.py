@@ -195,3 +195,62 @@ def test_mcshade_fixed_sets_and_bvh():
     ok = (rgb.detach().cpu().double() - rgb64).abs().max(-1).values <= 1e-3
     assert rel_err(rgb.detach().cpu()[ok], rgb64[ok]) < 1e-3
     assert float(out["visibility"].mean()) < 0.999        # some occlusion present
+
+
+@pytest.mark.parametrize("version", ["direction", "sphere_direction"])
+def test_mcshade_mlp_outer_lights(version):
+    """`outer_light_version: direction / sphere_direction` (reference fields.py:716-721, 913-928; the oracle's restatement is pinned
+    to the reference class in tests/test_oracle_flow_cpu.py): whole shading step against the fp64 oracle, outputs and gradients."""
+    from tensoflow_b200.material import MCShadingNetwork
+    dev = _cuda()
+    g = load("mcshade.npz")                                   # materials / flows / inner light of the reference fixture ...
+    torch.manual_seed(11)
+    cfg = dict(gridSize=[16, 16, 16], light_reso=16, mat_grid=24, device=dev, outer_light_version=version)
+    m = MCShadingNetwork(cfg, occluder_tracer(), torch.tensor([[-1., -1, -1], [1, 1, 1]]))
+    state = {k: v for k, v in g["state"].items() if not k.startswith("outer_light")}
+    m.load_state_dict(state, strict=False)                    # ... with a freshly initialised MLP light
+    with torch.no_grad():
+        for p in m.outer_light.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+    m.use_flow_diffuse_copy = m.use_flow_specular_copy = True
+    for f in (m.flow_diffuse_copy, m.flow_specular_copy):
+        for p in f.parameters():
+            p.requires_grad = False
+    def oracle(dt):
+        o = MC.MCShadingNetwork(occluder_tracer(), torch.tensor([[-1., -1, -1], [1, 1, 1]]), gridSize=(24, 24, 24), flow_grid=(16, 16, 16),
+                                light_reso=16, dtype=dt, outer_light_version=version)
+        res = o.load_state_dict({k: v.detach().cpu().to(dt) for k, v in m.state_dict().items()}, strict=False)
+        assert not [k for k in res.missing_keys if 'outer_light' in k], res.missing_keys
+        return o
+
+    i = g["inputs"]
+    keys = ("az_diffuse", "phi_diffuse", "phi_specular")
+    runs = {}
+    for dt in (torch.float64, torch.float32):                  # the fp32 oracle run calibrates what fp32 can reach (hit / miss flips)
+        o = oracle(dt)
+        rgb_o, out_o = o(i["pts"].to(dt), i["view_dirs"].to(dt), i["normals"].to(dt), {k: i[k].to(dt) for k in keys}, 2000)
+        ((rgb_o * i["u_rgb"].to(dt)).sum() + 100.0 * out_o["loss_nis"]).backward()
+        runs[dt] = (rgb_o, out_o, {n: p.grad for n, p in o.named_parameters() if p.grad is not None})
+    rgb64, out64, g64 = runs[torch.float64]
+    rgb32, out32, g32 = runs[torch.float32]
+
+    def close(got, b32, b64, tol, what):
+        e, e_ref = rel_err(got, b64), rel_err(b32, b64)
+        assert e <= max(tol, 4 * e_ref), f"{what}: rel err {e:.3e} (fp32 oracle vs fp64 oracle {e_ref:.3e})"
+
+    m.train()
+    rgb, out = m(i["pts"].to(dev), i["view_dirs"].to(dev), i["normals"].to(dev), None, 2000, True, noise={k: i[k].to(dev) for k in keys})
+    close(rgb, rgb32, rgb64, 1e-4, "rgb")
+    for k in MC_KEYS:
+        close(out[k], out32[k], out64[k], 1e-4, k)
+    ((rgb * i["u_rgb"].to(dev)).sum() + 100.0 * out["loss_nis"]).backward()
+    n_light = 0
+    for n, p in m.named_parameters():
+        if not p.requires_grad or p.grad is None or n not in g64:
+            continue
+        close(p.grad, g32[n], g64[n], 1e-3, f"d {n}")
+        n_light += n.startswith("outer_light")
+    assert n_light >= 8                                       # weight-norm g / v + bias of the four light layers
+    groups = m.get_optparam_groups(0.02, 0.001, 0.1)
+    assert groups[2]['lr'] == 0.001                           # MLP lights train at the network rate (reference fields.py:1584)
+    m.update_step(999)                                        # no cubemap to upsample (the reference raises here)

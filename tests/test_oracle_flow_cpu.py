@@ -79,3 +79,32 @@ def test_oracle_matches_reference_tensoflow():
     for n, p in ref.named_parameters():
         if p.grad is not None:
             assert torch.allclose(p.grad, gm[n].grad, rtol=0, atol=0), n
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present")
+@pytest.mark.parametrize("version", ["direction", "sphere_direction"])
+def test_oracle_outer_mlp_lights_match_reference(version):
+    """MLP outer lights (reference fields.py:716-721, 913-928; `outer_light_version: direction` is the reference default and the
+    setting of 8 shipped material configs): oracle predict_outer_lights == the reference class's, same weights."""
+    import torch.nn.functional as F
+    from conftest import rel_err
+    ref_shim.install()
+    import network.fields as RF
+    from oracle import torch_oracle_mc as MC
+    torch.manual_seed(3)
+    aabb = torch.tensor([[-1., -1, -1], [1, 1, 1]])
+    tracer = MC.analytic_sphere_tracer(0.45)
+    ref = RF.MCShadingNetwork(dict(outer_light_version=version, light_exp_max=5.0, inner_light_exp_max=5.0, human_lights=False,
+                                   gridSize=[16, 16, 16]), tracer, aabb)
+    mine = MC.MCShadingNetwork(tracer, aabb, gridSize=(8, 8, 8), flow_grid=(16, 16, 16), outer_light_version=version)
+    with torch.no_grad():
+        for p in ref.outer_light.parameters():
+            p.add_(0.1 * torch.randn_like(p))
+    mine.outer_light.load_state_dict(ref.outer_light.state_dict())
+    n = 500
+    pts = F.normalize(torch.randn(n, 3), dim=-1) * torch.rand(n, 1)
+    pts[:20] = F.normalize(pts[:20], dim=-1) * (0.999 + 0.0019 * torch.rand(20, 1))    # the `> 0.999 -> shrink` branch (the reference asserts beyond ~1.001)
+    dirs = F.normalize(torch.randn(n, 3), dim=-1)
+    a = ref.predict_outer_lights(pts, dirs)
+    b = mine.predict_outer_lights(pts, dirs)
+    assert a.shape == (n, 3) and rel_err(b, a) < 1e-6
