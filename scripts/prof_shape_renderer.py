@@ -30,3 +30,9 @@ torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof:
     one_step(); torch.cuda.synchronize()
 print(prof.key_averages(group_by_input_shape=True).table(sort_by="cuda_time_total", row_limit=30, max_name_column_width=45, max_shapes_column_width=60))
+print(prof.key_averages().table(sort_by="self_cpu_time_total", row_limit=45, max_name_column_width=60))
+import time
+torch.cuda.synchronize(); t = time.perf_counter()
+for _ in range(5): one_step()
+t_host = (time.perf_counter() - t) / 5; torch.cuda.synchronize(); t_all = (time.perf_counter() - t) / 5
+print(f"host time per step {t_host * 1e3:.1f} ms, wall per step {t_all * 1e3:.1f} ms")

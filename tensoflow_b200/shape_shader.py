@@ -51,20 +51,20 @@ def dir_to_face_xy(d: torch.Tensor):
     return face, x / m, y / m
 
 
-def cube_sample(tex: torch.Tensor, d: torch.Tensor) -> torch.Tensor:
-    """Seamless bilinear lookup (dr.texture(..., boundary_mode='cube'), reference light.py:107,135):
-    tex [6,R,R,C], d [N,3] -> [N,C]; differentiable in tex and d.  Taps that leave the face fold onto
+def cube_taps(R: int, d: torch.Tensor):
+    """The four texel taps of a seamless bilinear cube lookup at directions d [N,3] on a [6,R,R,C] texture:
+    -> (idx [N,4] flat texel indices, w [N,4] normalised weights, differentiable in d).  Taps that leave the face fold onto
     the neighbouring face, the tap leaving in both axes is dropped and the weights renormalised."""
-    R = tex.shape[1]
     face, x, y = dir_to_face_xy(d)
     u = (x + 1.0) * 0.5 * R - 0.5
     v = (y + 1.0) * 0.5 * R - 0.5
     u0, v0 = torch.floor(u), torch.floor(v)
-    fu, fv = (u - u0).unsqueeze(-1), (v - v0).unsqueeze(-1)
+    fu, fv = u - u0, v - v0
     u0, v0 = u0.long(), v0.long()
-    flat = tex.reshape(-1, tex.shape[-1])
     major = face // 2
-    out, wsum = 0, 0
+    ar = torch.arange(3, device=d.device)
+    is_major = ar[None, :] == major[:, None]
+    idx, ws = [], []
     for du, dv in ((0, 0), (1, 0), (0, 1), (1, 1)):
         iu, iv = u0 + du, v0 + dv
         w = (fu if du else 1 - fu) * (fv if dv else 1 - fv)
@@ -73,8 +73,6 @@ def cube_sample(tex: torch.Tensor, d: torch.Tensor) -> torch.Tensor:
         fy = 2.0 * (iv.to(d.dtype) + 0.5) / R - 1.0
         p = cube_to_dir_t(face, fx, fy)
         ex = (p.abs() - 1.0).clamp_min(0.0)
-        ar = torch.arange(3, device=d.device)
-        is_major = ar[None, :] == major[:, None]
         ex = torch.where(is_major, torch.zeros_like(ex), ex)
         e = ex.sum(-1, keepdim=True)
         q = torch.where(ex > 0, torch.sign(p), p)
@@ -86,10 +84,17 @@ def cube_sample(tex: torch.Tensor, d: torch.Tensor) -> torch.Tensor:
         f_use = torch.where(fold, f2, face)
         iu_use = torch.where(fold, iu2, iu.clamp(0, R - 1))
         iv_use = torch.where(fold, iv2, iv.clamp(0, R - 1))
-        w = torch.where((ou & ov).unsqueeze(-1), torch.zeros_like(w), w)
-        out = out + flat[(f_use * R + iv_use) * R + iu_use] * w
-        wsum = wsum + w
-    return out / wsum
+        idx.append((f_use * R + iv_use) * R + iu_use)
+        ws.append(torch.where(ou & ov, torch.zeros_like(w), w))
+    w = torch.stack(ws, -1)
+    return torch.stack(idx, -1), w / w.sum(-1, keepdim=True)
+
+
+def cube_sample(tex: torch.Tensor, d: torch.Tensor) -> torch.Tensor:
+    """Seamless bilinear lookup (dr.texture(..., boundary_mode='cube'), reference light.py:107,135):
+    tex [6,R,R,C], d [N,3] -> [N,C]; differentiable in tex and d."""
+    idx, w = cube_taps(tex.shape[1], d)
+    return (tex.reshape(-1, tex.shape[-1])[idx] * w.unsqueeze(-1)).sum(1)
 
 
 def cube_sample_mip(stack: List[torch.Tensor], d: torch.Tensor, level: torch.Tensor) -> torch.Tensor:
@@ -248,14 +253,22 @@ class CubemapMip(torch.autograd.Function):
     def forward(ctx, cubemap):
         return F.avg_pool2d(cubemap.permute(0, 3, 1, 2), (2, 2)).permute(0, 2, 3, 1).contiguous()
 
+    _taps = {}      # (res, device) -> taps of the fine texel centres: constant geometry, built once
+
     @staticmethod
     def backward(ctx, dout):
         res = dout.shape[1] * 2
-        c = torch.linspace(-1.0 + 1.0 / res, 1.0 - 1.0 / res, res, device=dout.device)
-        gy, gx = torch.meshgrid(c, c, indexing="ij")
-        face = torch.arange(6, device=dout.device)[:, None, None].expand(6, res, res)
-        v = F.normalize(cube_to_dir_t(face, gx.expand(6, res, res), gy.expand(6, res, res)), dim=-1, eps=1e-20)
-        return cube_sample(dout * 0.25, v.reshape(-1, 3)).reshape(6, res, res, -1)
+        key = (res, str(dout.device))
+        if key not in CubemapMip._taps:
+            with torch.no_grad():
+                c = torch.linspace(-1.0 + 1.0 / res, 1.0 - 1.0 / res, res, device=dout.device)
+                gy, gx = torch.meshgrid(c, c, indexing="ij")
+                face = torch.arange(6, device=dout.device)[:, None, None].expand(6, res, res)
+                v = F.normalize(cube_to_dir_t(face, gx.expand(6, res, res), gy.expand(6, res, res)), dim=-1, eps=1e-20)
+                CubemapMip._taps[key] = cube_taps(dout.shape[1], v.reshape(-1, 3))
+        idx, w = CubemapMip._taps[key]
+        src = (dout * 0.25).reshape(-1, dout.shape[-1])
+        return (src[idx] * w.unsqueeze(-1)).sum(1).reshape(6, res, res, -1)
 
 
 class ShadingEnvLight(nn.Module):
