@@ -263,6 +263,19 @@ TF_API int tf_tv_fwd(const float* x, int32_t H, int32_t W, int32_t C, float* sum
 TF_API int tf_tv_bwd(const float* x, int32_t H, int32_t W, int32_t C, float scale_h, float scale_w,
                      const float* upstream, float* g, tf_stream_t stream);
 
+/* ---- differentiable cubemap lookup ---------------------------------------------------------------
+ * dr.texture(tex, dirs, [mip=stack, mip_level_bias=level,] filter_mode='linear[-mipmap-linear]', boundary_mode='cube') of the
+ * shape-stage light (reference network/light.py:95-122, 135; network/light_utils.py:46-63): seamless bilinear footprint per
+ * level (edge taps fold onto the neighbouring face, the corner tap is dropped, weights renormalised), linear blend of the two
+ * levels around clamp(level, 0, n_levels-1).  tex[l] is [6,res[l],res[l],3] fp32; `tex`, `d_tex`, `res` are HOST arrays of
+ * n_levels (<= 8) entries; level == NULL reads level 0 only.  Backward accumulates into d_tex[l] (atomics, zero-initialised
+ * by the caller; entries / the array may be NULL) and writes d_dirs[n,3], d_level[n] (each may be NULL). */
+TF_API int tf_cube_sample_fwd(const float* const* tex, const int32_t* res, int32_t n_levels, const float* dirs,
+                              const float* level, int64_t n, float* out, tf_stream_t stream);
+TF_API int tf_cube_sample_bwd(const float* const* tex, const int32_t* res, int32_t n_levels, const float* dirs,
+                              const float* level, int64_t n, const float* g_out, float* const* d_tex, float* d_dirs,
+                              float* d_level, tf_stream_t stream);
+
 /* ---- occupancy-grid marcher ---------------------------------------------------------------------
  * nerfacc.OccGridEstimator.sampling as the reference calls it (network/shapeRenderer.py:950-959, 1065-1072): fixed
  * render_step_size, no cone angle, no visibility filter.  nerfacc is not vendored; the rule restated here:

@@ -84,6 +84,8 @@ _OPTIONAL_SIGNATURES = {
     "tf_tc_probe": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "tf_tv_fwd": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "tf_tv_bwd": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, _P, _P, _P]),
+    "tf_cube_sample_fwd": (C.c_int, [_P, _P, C.c_int32, _P, _P, C.c_int64, _P, _P]),
+    "tf_cube_sample_bwd": (C.c_int, [_P, _P, C.c_int32, _P, _P, C.c_int64, _P, _P, _P, _P, _P]),
     "tf_occ_march_count": (C.c_int, [_P, _P, _P, C.c_int32, C.c_float, C.c_float, _P, _P, _P, _P, _P]),
     "tf_occ_march_write": (C.c_int, [_P, _P, _P, C.c_int32, C.c_float, C.c_float, _P, _P, _P, _P, _P, _P, _P, _P]),
     "tf_adam_step": (C.c_int, [C.c_int32, _P, _P, _P, _P, _P, _P, C.c_float, C.c_float, C.c_float, C.c_int32, _P]),

@@ -97,6 +97,53 @@ def cube_sample(tex: torch.Tensor, d: torch.Tensor) -> torch.Tensor:
     return (tex.reshape(-1, tex.shape[-1])[idx] * w.unsqueeze(-1)).sum(1)
 
 
+class CubeSampleFunction(torch.autograd.Function):
+    """Seamless (tri)linear cube lookup on `tf_cube_sample_fwd/bwd`, differentiable in the textures, the direction and the level:
+    (d [N,3], level [N] or None, *texs [6,R_l,R_l,3]) -> [N,3].  Same arithmetic as `cube_sample` / `cube_sample_mip` below (which
+    stay as the tensor formulation the kernel is tested against)."""
+
+    @staticmethod
+    def forward(ctx, d, level, *texs):
+        import ctypes as C
+        lib = _lib.load()
+        d_c = d.detach().float().contiguous()
+        lv = None if level is None else level.detach().float().contiguous().reshape(-1)
+        tex_c = [t.detach().float().contiguous() for t in texs]
+        n, L = d_c.shape[0], len(tex_c)
+        out = torch.empty(n, 3, device=d_c.device, dtype=torch.float32)
+        ptrs = (C.c_void_p * L)(*[t.data_ptr() for t in tex_c])
+        res = (C.c_int32 * L)(*[int(t.shape[1]) for t in tex_c])
+        check(lib.tf_cube_sample_fwd(ptrs, res, L, ptr(d_c), ptr(lv), n, ptr(out), stream_ptr()), "tf_cube_sample_fwd")
+        ctx.save_for_backward(d_c, lv, *tex_c)
+        ctx.has_level = level is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        import ctypes as C
+        lib = _lib.load()
+        d_c, lv, *tex_c = ctx.saved_tensors
+        n, L = d_c.shape[0], len(tex_c)
+        g_c = g.detach().float().contiguous()
+        need_tex = [ctx.needs_input_grad[2 + l] for l in range(L)]
+        d_tex = [torch.zeros_like(t) if need else None for t, need in zip(tex_c, need_tex)]
+        d_d = torch.empty_like(d_c) if ctx.needs_input_grad[0] else None
+        d_lv = torch.empty(n, device=d_c.device, dtype=torch.float32) if (ctx.has_level and ctx.needs_input_grad[1]) else None
+        ptrs = (C.c_void_p * L)(*[t.data_ptr() for t in tex_c])
+        dptrs = (C.c_void_p * L)(*[(t.data_ptr() if t is not None else None) for t in d_tex])
+        res = (C.c_int32 * L)(*[int(t.shape[1]) for t in tex_c])
+        check(lib.tf_cube_sample_bwd(ptrs, res, L, ptr(d_c), ptr(lv), n, ptr(g_c), dptrs, ptr(d_d), ptr(d_lv), stream_ptr()),
+              "tf_cube_sample_bwd")
+        return (d_d, d_lv, *d_tex)
+
+
+def cube_lookup(texs: List[torch.Tensor], d: torch.Tensor, level: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The product path of the cube lookups (CUDA kernel; no CPU fallback)."""
+    if d.shape[0] == 0:
+        return torch.zeros(0, 3, device=d.device)
+    return CubeSampleFunction.apply(d, level, *texs)
+
+
 def cube_sample_mip(stack: List[torch.Tensor], d: torch.Tensor, level: torch.Tensor) -> torch.Tensor:
     """linear-mipmap-linear over a user-supplied stack (reference light.py:111-118); differentiable in
     the textures, the direction and the level."""
@@ -301,8 +348,8 @@ class ShadingEnvLight(nn.Module):
 
     def forward(self, l, roughness=None):
         if roughness is None:
-            return torch.exp(cube_sample(self.diffuse, l))
-        return torch.exp(cube_sample_mip(self.specular, l, self.get_mip(roughness)[..., 0]))
+            return torch.exp(cube_lookup([self.diffuse], l))
+        return torch.exp(cube_lookup(self.specular, l, self.get_mip(roughness)[..., 0]))
 
 
 def load_fg_lut(device):

@@ -81,3 +81,58 @@ def test_cuda_shader_golden():
         if n in g["grads"]:
             assert p.grad is not None, n
             close(p.grad, g["grads"][n], p64[n].grad, 1e-3, f"d {n}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("with_level", [False, True])
+def test_cube_lookup_kernel_matches_tensor_formulation(with_level):
+    """tf_cube_sample_fwd/bwd against cube_sample / cube_sample_mip (the tensor formulation pinned to the reference shader by the
+    golden test above) in fp64: values and the gradients wrt every texture level, the direction and the mip level."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import torch.nn.functional as F
+    from conftest import rel_err
+    from tensoflow_b200 import shape_shader as S
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(5)
+    res = [32, 16, 8, 4] if with_level else [16]
+    texs = [torch.randn(6, r, r, 3, generator=g) * 0.5 for r in res]
+    d = F.normalize(torch.randn(6000, 3, generator=g), dim=-1)
+    # directions within a texel of cube edges / corners exercise the fold and the dropped corner tap
+    e = F.normalize(torch.tensor([[1.0, 1.0, 0.3], [1.0, -1.0, 0.99], [0.98, 1.0, 1.0], [-1.0, 0.2, 1.0], [0.1, -1.0, -1.0]]), dim=-1)
+    e = F.normalize(e[None] + 0.03 * torch.randn(300, 5, 3, generator=g), dim=-1).reshape(-1, 3)
+    d = torch.cat([d, e], 0) * (0.5 + torch.rand(7500, 1, generator=g))          # un-normalised directions are legal inputs
+    n = d.shape[0]
+    level = torch.rand(n, generator=g) * 4.0 - 0.5 if with_level else None        # below 0 and above L-1: clamped
+    if with_level:
+        level[:50] = torch.randint(0, 4, (50,), generator=g).float()              # integer levels (f = 0)
+    u = torch.randn(n, 3, generator=g)
+
+    def tensor_version(dt):
+        tx = [t.detach().clone().to(dt).requires_grad_() for t in texs]
+        dd = d.detach().clone().to(dt).requires_grad_()
+        lv = None if level is None else level.detach().clone().to(dt).requires_grad_()
+        out = S.cube_sample(tx[0], dd) if lv is None else S.cube_sample_mip(tx, dd, lv)
+        (out * u.to(dt)).sum().backward()
+        return out, [t.grad for t in tx], dd.grad, None if lv is None else lv.grad
+
+    o64, gt64, gd64, gl64 = tensor_version(torch.float64)
+    o32, gt32, gd32, gl32 = tensor_version(torch.float32)
+    tx = [t.detach().clone().to(dev).requires_grad_() for t in texs]
+    dd = d.detach().clone().to(dev).requires_grad_()
+    lv = None if level is None else level.detach().clone().to(dev).requires_grad_()
+    out = S.cube_lookup(tx, dd, lv)
+    (out * u.to(dev)).sum().backward()
+
+    def close(a, b32, b64, tol, what):
+        e_, e_ref = rel_err(a, b64), rel_err(b32, b64)
+        assert e_ <= max(tol, 4 * e_ref), f"{what}: {e_:.3e} (fp32 tensor version {e_ref:.3e})"
+
+    close(out, o32, o64, 1e-5, "out")
+    for l in range(len(res)):
+        close(tx[l].grad, gt32[l], gt64[l], 1e-4, f"d tex[{l}]")
+    close(dd.grad, gd32, gd64, 1e-4, "d dirs")
+    if with_level:
+        close(lv.grad, gl32, gl64, 1e-4, "d level")
+        outside = (level < 0) | (level > 3)
+        assert float(lv.grad.cpu()[outside].abs().max()) == 0.0
