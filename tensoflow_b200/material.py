@@ -93,7 +93,7 @@ def ide_encode(xyz: torch.Tensor) -> torch.Tensor:
         re.append(re_n)
         im.append(im_n)
     vmz = torch.cat(zs, -1)
-    re, im = torch.cat(re, -1)[:, m_idx], torch.cat(im, -1)[:, m_idx]
+    re, im = torch.cat(re, -1).index_select(1, m_idx), torch.cat(im, -1).index_select(1, m_idx)   # backward = index_add, not a sorted index_put
     poly = vmz @ mat
     return torch.cat([re * poly, im * poly], -1)
 

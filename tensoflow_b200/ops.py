@@ -418,6 +418,14 @@ class LinearFunction(torch.autograd.Function):
 def linear(X, W, b=None, act="none", act_param=0.0):
     if X.shape[0] == 0:
         return X.new_zeros(0, W.shape[0])
+    K = X.shape[1]
+    if X.shape[0] >= LINEAR_TC_MIN_ROWS and W.shape[0] >= 96 and K >= 80 and K % 16 != 0:
+        # wide layer with a ragged input width (the shader heads read 90 / 123 / 161 concatenated features): zero columns up to
+        # the next multiple of 16 put the layer, its data gradient and its weight gradient on the tensor-core kernels (16-byte
+        # aligned rows, K >= 96); the result is unchanged and autograd slices the padding off both gradients
+        pad = 16 - K % 16
+        X = torch.nn.functional.pad(X, (0, pad))
+        W = torch.nn.functional.pad(W, (0, pad))
     return LinearFunction.apply(X, W, b, act, act_param)
 
 

@@ -191,7 +191,7 @@ def ide_encode_rough(xyz: torch.Tensor, kappa_inv: torch.Tensor) -> torch.Tensor
         re.append(re_n)
         im.append(im_n)
     vmz = torch.cat(zs, -1)
-    re, im = torch.cat(re, -1)[:, m_idx], torch.cat(im, -1)[:, m_idx]
+    re, im = torch.cat(re, -1).index_select(1, m_idx), torch.cat(im, -1).index_select(1, m_idx)   # backward = index_add, not a sorted index_put
     att = (vmz @ mat) * torch.exp(-sigma * kappa_inv)
     return torch.cat([re * att, im * att], -1)
 
