@@ -300,6 +300,128 @@ int tf_internal_colsum(const float* X, int ldx, int64_t rows, int cols, float* o
     return 0;
 }
 
+// ---- output heads: wide input, N <= 8 outputs (albedo / roughness / metallic / light / weight heads: K = 128 or 256, N = 1..5) --------
+// The generic tiles waste their N side here and the X^T dPre product becomes a tall-skinny reduction at a fraction of the
+// memory bandwidth.  One warp per row instead: a lane owns 4 consecutive k per 128-column chunk (one coalesced 512-byte row
+// segment per load), the N weight rows live in registers.
+//   forward   y[m][n] = act(sum_k x[m][k] W[n][k] + b[n])                       (N butterfly reductions per row)
+//   backward  dpre = dY act'(Y);  dX[m][:] = sum_n dpre[n] W[n][:];  dW[n][:] += dpre[n] x[m][:];  db[n] += dpre[n]
+//             in ONE pass over X (read once) and dX (written once); per-warp partial dW / db are reduced through shared
+//             memory and added to the zero-initialised outputs with one atomic per element and CTA.
+constexpr int HEAD_NMAX = 8, HEAD_KMAX = 256;
+bool head_shape(int64_t M, int K, int N, const void* a, const void* b) {
+    return M >= 4096 && N <= HEAD_NMAX && K % 4 == 0 && K > SL_MAX && K <= HEAD_KMAX && (((uintptr_t)a | (uintptr_t)b) & 15) == 0;
+}
+
+template <int CH>   // 128-column chunks per row
+__global__ void __launch_bounds__(256) head_fwd_kernel(const float* __restrict__ X, const float* __restrict__ W, const float* __restrict__ b,
+                                                       int64_t M, int K, int N, int act, float act_p, float* __restrict__ Y) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    float4 w[HEAD_NMAX][CH];
+#pragma unroll
+    for (int n = 0; n < HEAD_NMAX; ++n)
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const int k = c * 128 + lane * 4;
+            w[n][c] = (n < N && k < K) ? *reinterpret_cast<const float4*>(W + (size_t)n * K + k) : f4_zero();
+        }
+    const float bias = (b && lane < N) ? b[lane] : 0.f;
+    for (int64_t m = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); m < M; m += (int64_t)gridDim.x * wpb) {
+        float4 x[CH];
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const int k = c * 128 + lane * 4;
+            x[c] = k < K ? ldg4(X + (size_t)m * K + k) : f4_zero();
+        }
+        float mine = 0.f;
+#pragma unroll
+        for (int n = 0; n < HEAD_NMAX; ++n) {
+            if (n >= N) break;
+            float a = 0.f;
+#pragma unroll
+            for (int c = 0; c < CH; ++c) a += (x[c].x * w[n][c].x + x[c].y * w[n][c].y) + (x[c].z * w[n][c].z + x[c].w * w[n][c].w);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (lane == n) mine = a;
+        }
+        if (lane < N) Y[(size_t)m * N + lane] = act_fwd(mine + bias, act, act_p);
+    }
+}
+
+template <int CH>
+__global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ X, const float* __restrict__ W, const float* __restrict__ Y,
+                                                       const float* __restrict__ dY, int64_t M, int K, int N, int act, float act_p,
+                                                       float* __restrict__ dX, float* __restrict__ dW, float* __restrict__ db) {
+    __shared__ float red[8][HEAD_NMAX][HEAD_KMAX / 2 + 4];     // two passes of 128 columns keep it at 33 KB
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    float4 w[HEAD_NMAX][CH], acc[HEAD_NMAX][CH];
+#pragma unroll
+    for (int n = 0; n < HEAD_NMAX; ++n)
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const int k = c * 128 + lane * 4;
+            w[n][c] = (n < N && k < K) ? *reinterpret_cast<const float4*>(W + (size_t)n * K + k) : f4_zero();
+            acc[n][c] = f4_zero();
+        }
+    float accb = 0.f;                                           // lane n < N owns db[n]
+    for (int64_t m = (int64_t)blockIdx.x * wpb + warp; m < M; m += (int64_t)gridDim.x * wpb) {
+        float dp = 0.f;
+        if (lane < N) { const size_t o = (size_t)m * N + lane; dp = __ldg(dY + o) * act_bwd(__ldg(Y + o), act, act_p); }
+        accb += dp;
+        float4 x[CH], dx[CH];
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const int k = c * 128 + lane * 4;
+            x[c] = k < K ? ldg4(X + (size_t)m * K + k) : f4_zero();
+            dx[c] = f4_zero();
+        }
+#pragma unroll
+        for (int n = 0; n < HEAD_NMAX; ++n) {
+            if (n >= N) break;
+            const float d = __shfl_sync(0xffffffffu, dp, n);
+#pragma unroll
+            for (int c = 0; c < CH; ++c) { dx[c] = f4_fma(d, w[n][c], dx[c]); acc[n][c] = f4_fma(d, x[c], acc[n][c]); }
+        }
+        if (dX) {
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+                const int k = c * 128 + lane * 4;
+                if (k < K) *reinterpret_cast<float4*>(dX + (size_t)m * K + k) = dx[c];
+            }
+        }
+    }
+    // CTA reduction of dW (one 128-column chunk at a time) and db
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+        __syncthreads();
+#pragma unroll
+        for (int n = 0; n < HEAD_NMAX; ++n) *reinterpret_cast<float4*>(&red[warp][n][lane * 4]) = acc[n][c];
+        __syncthreads();
+        for (int i = threadIdx.x; i < N * 128; i += blockDim.x) {
+            const int n = i >> 7, kk = i & 127, k = c * 128 + kk;
+            if (k >= K) continue;
+            float sum = 0.f;
+            for (int wv = 0; wv < wpb; ++wv) sum += red[wv][n][kk];
+            if (dW && sum != 0.f) atomicAdd(dW + (size_t)n * K + k, sum);
+        }
+    }
+    if (db) {
+        __syncthreads();
+        if (lane < N) red[warp][lane][0] = accb;
+        __syncthreads();
+        if (threadIdx.x < N) {
+            float sum = 0.f;
+            for (int wv = 0; wv < wpb; ++wv) sum += red[wv][threadIdx.x][0];
+            if (sum != 0.f) atomicAdd(db + threadIdx.x, sum);
+        }
+    }
+}
+
+int head_grid(int64_t M) {
+    const int64_t want = (M + 127) / 128, cap = (int64_t)tf_num_sms() * 4;     // >= 16 rows per warp: few, well-filled partial sums
+    return (int)(want < cap ? want : cap);
+}
+
 // tensor-core dense layer (linear_tc.cu) and weight-gradient kernel (xty_tc.cu)
 bool tf_internal_linear_tc_ok(const float* X, const float* Y, int K, int N, int act);
 size_t tf_internal_linear_tc_ws_floats(int K, int N);
@@ -328,6 +450,13 @@ extern "C" TF_API int tf_linear_fwd(const float* X, const float* W, const float*
     if (M == 0) return 0;
     TF_REQUIRE(X && W && Y, "tf_linear_fwd: NULL pointer");
     TF_REQUIRE(K > 0 && N > 0 && act >= 0 && act <= 5, "tf_linear_fwd: bad K/N/act (%d,%d,%d)", K, N, act);
+    if (head_shape(M, K, N, X, W)) {
+        if (K <= 128) head_fwd_kernel<1><<<head_grid(M), 256, 0, (cudaStream_t)stream>>>(X, W, b, M, K, N, act, act_param, Y);
+        else head_fwd_kernel<2><<<head_grid(M), 256, 0, (cudaStream_t)stream>>>(X, W, b, M, K, N, act, act_param, Y);
+        tf_count_launches(1);
+        TF_CHECK_LAUNCH("tf_linear_fwd (head)");
+        return 0;
+    }
     if (workspace && tc_shape(M, K, N) && tf_internal_linear_tc_ok(X, Y, K, N, act) && ((uintptr_t)workspace & 15) == 0 &&
         ws_bytes >= tf_internal_linear_tc_ws_floats(K, N) * sizeof(float)) {
         tf_internal_linear_tc(X, W, K, 0, b, M, K, N, act, act_param, Y, (float*)workspace, (cudaStream_t)stream);
@@ -357,6 +486,14 @@ extern "C" TF_API int tf_linear_bwd(const float* X, const float* W, const float*
         small_linear_bwd_kernel<<<grid, 256, smem, stream>>>(X, W, Y, dY, M, K, N, act, act_param, dX, dW, db);
         tf_count_launches(1);
         TF_CHECK_LAUNCH("tf_linear_bwd (narrow)");
+        return 0;
+    }
+    if (head_shape(M, K, N, X, W) && (!dX || ((uintptr_t)dX & 15) == 0)) {
+        // output head: one pass for dX, dW and db (the `dpre` buffer is left untouched)
+        if (K <= 128) head_bwd_kernel<1><<<head_grid(M), 256, 0, stream>>>(X, W, Y, dY, M, K, N, act, act_param, dX, dW, db);
+        else head_bwd_kernel<2><<<head_grid(M), 256, 0, stream>>>(X, W, Y, dY, M, K, N, act, act_param, dX, dW, db);
+        tf_count_launches(1);
+        TF_CHECK_LAUNCH("tf_linear_bwd (head)");
         return 0;
     }
     // dPre = dY * act'(Y) and dX = dPre W.  dX may be NULL (first layer): then a one-column
