@@ -44,3 +44,49 @@ def test_product_does_not_import_oracle():
     for p in (ROOT / "tensoflow_b200").glob("*.py"):
         src = p.read_text()
         assert "import oracle" not in src and "from oracle" not in src, p
+
+
+def test_new_entry_points_refuse_cpu_tensors():
+    """FusedAdam, the occupancy marcher and the cube lookup have no CPU path either: CPU tensors raise before any launch."""
+    import torch
+    from tensoflow_b200.optim import FusedAdam
+    from tensoflow_b200.occ_grid import OccGridEstimator
+    from tensoflow_b200.shape_shader import cube_lookup
+    p = torch.nn.Parameter(torch.zeros(4))
+    p.grad = torch.ones(4)
+    with pytest.raises(RuntimeError):
+        FusedAdam([p]).step()
+    est = OccGridEstimator([-1, -1, -1, 1, 1, 1], resolution=4)
+    est.mark_all_occupied()
+    with pytest.raises(RuntimeError):
+        est.sampling(torch.zeros(2, 3), torch.ones(2, 3), near_plane=0.1, far_plane=2.0, render_step_size=0.1)
+    with pytest.raises(RuntimeError):
+        cube_lookup([torch.zeros(6, 4, 4, 3)], torch.ones(5, 3))
+
+
+def test_occ_grid_refresh_host_logic():
+    """OccGridEstimator._update / update_every_n_steps / state_dict are tensor logic: check them on CPU (nerfacc semantics:
+    occs = max(occs * decay, occ), binaries = occs > min(mean, thre); refresh only when step % n == 0 in training mode)."""
+    import torch
+    from tensoflow_b200.occ_grid import OccGridEstimator
+    est = OccGridEstimator([-1, -1, -1, 1, 1, 1], resolution=8)
+    ball = lambda x: (x.norm(dim=-1) < 0.6).float()
+    est._update(0, ball, warmup_steps=10, jitter=torch.full((512, 3), 0.5))
+    centres = (est.grid_coords.float() + 0.5) / 8 * 2 - 1
+    assert torch.equal(est.binaries.reshape(-1), centres.norm(dim=-1) < 0.6)
+    before = est.occs.clone()
+    est._update(0, lambda x: torch.zeros(x.shape[0]), ema_decay=0.5, warmup_steps=10)
+    assert torch.allclose(est.occs, before * 0.5)                    # decay only
+    est.eval()
+    est.update_every_n_steps(100, ball, n=100, warmup_steps=0)        # not training: untouched
+    assert torch.allclose(est.occs, before * 0.5)
+    est.train()
+    est.update_every_n_steps(101, ball, n=100, warmup_steps=0)        # not a multiple of n: untouched
+    assert torch.allclose(est.occs, before * 0.5)
+    est.update_every_n_steps(200, ball, n=100, warmup_steps=0)        # partial refresh (a quarter + the occupied cells)
+    assert float(est.occs.max()) == 1.0
+    sd = est.state_dict()
+    assert set(sd) == {"resolution", "aabbs", "occs", "binaries"}
+    est2 = OccGridEstimator([-1, -1, -1, 1, 1, 1], resolution=8)
+    est2.load_state_dict(sd)
+    assert torch.equal(est2.binaries, est.binaries) and torch.equal(est2.occs, est.occs)
