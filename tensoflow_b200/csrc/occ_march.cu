@@ -49,7 +49,7 @@ __device__ __forceinline__ void occ_range(const OccGrid& g, const float o[3], co
         }
     }
     tb = fminf(tb, far);
-    if (!(tb >= ta)) { k0 = 0; k1 = 0; return; }
+    if (!(tb >= ta) || ta <= -1e29f) { k0 = 0; k1 = 0; return; }      // miss, or a zero direction (no slab bounds the march)
     const float lo = (ta - near) / step - 2.f, hi = (tb - near) / step + 2.f;
     k0 = lo > 0.f ? (int)fminf(lo, 2.0e9f) : 0;
     k1 = hi > 0.f ? (int)fminf(hi, 2.0e9f) : 0;
