@@ -1,0 +1,81 @@
+"""The pure-tensor host logic of the product (sampler helpers of tensoflow_b200/shape_renderer.py) against the reference's
+own functions, imported on CPU through the shim (skipped where /root/reference is absent, i.e. on the GPU box)."""
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import ref_shim
+
+pytestmark = pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present")
+
+
+def _sdf_sphere(x):
+    return (x.norm(dim=-1, keepdim=True) - 0.45) + 0.02 * torch.sin(7 * x[..., :1])
+
+
+def test_sample_pdf_and_weights_match_reference():
+    ref_shim.install()
+    import utils.network_utils as RU
+    from tensoflow_b200 import shape_renderer as P
+    torch.manual_seed(0)
+    pn, sn = 64, 33
+    z = torch.sort(torch.rand(pn, sn) * 2.0, dim=-1).values
+    w = torch.rand(pn, sn - 1) ** 3
+    w[:5] = 0.0                                                       # rays without any surface: uniform fallback
+    assert torch.equal(P.sample_pdf(z, w, 9, det=True), RU.sample_pdf(z, w, 9, True))
+    o = torch.nn.functional.normalize(torch.randn(pn, 3), dim=-1) * 0.9
+    d = torch.nn.functional.normalize(-o + 0.3 * torch.randn(pn, 3), dim=-1)
+    inv = lambda p: torch.full_like(p[..., :1], 37.0)
+    zz = P.get_sphere_intersection(o, d) * torch.linspace(0, 1, 24)[None]
+    assert torch.equal(P.get_sphere_intersection(o, d), RU.get_sphere_intersection(o, d))
+    wa, ma = P.get_weights(_sdf_sphere, inv, zz, o, d)
+    wb, mb = RU.get_weights(_sdf_sphere, inv, zz, o, d)
+    assert torch.equal(wa, wb) and torch.equal(ma, mb)
+    ha = P.get_intersection(_sdf_sphere, inv, o, d, sn0=32, sn1=9)
+    hb = RU.get_intersection(_sdf_sphere, inv, o, d, sn0=32, sn1=9)
+    for a, b in zip(ha, hb):
+        assert torch.equal(a, b)
+
+
+def test_upsample_and_ball_radii_match_reference():
+    ref_shim.install()
+    import network.shapeRenderer as RS
+    from tensoflow_b200 import shape_renderer as P
+    torch.manual_seed(1)
+    pn, sn = 48, 40
+    o = torch.nn.functional.normalize(torch.randn(pn, 3), dim=-1) * 2.0
+    d = torch.nn.functional.normalize(-o + 0.2 * torch.randn(pn, 3), dim=-1)
+    near, far = P.near_far_from_sphere(o, d, 1.0)
+    z = near + (far - near) * torch.linspace(0, 1, sn)[None]
+    sdf = _sdf_sphere(o[:, None, :] + d[:, None, :] * z[..., None])[..., 0]
+    inv_s = torch.full((pn, sn - 1), 64.0)
+    a = P.ShapeRenderer.upsample(o, d, z, sdf, 16, inv_s)
+    b = RS.ShapeRenderer.upsample(o, d, z, sdf, 16, inv_s)
+    assert torch.equal(a, b)
+    dist, radiis, cos = torch.rand(pn, 1) * 3 + 0.5, torch.rand(pn, 1) * 2e-3 + 1e-4, torch.rand(pn, 1) * 0.5 + 0.5
+    assert torch.equal(P.compute_ball_radii(dist, radiis, cos), RS.ShapeRenderer.compute_ball_radii(dist, radiis, cos))
+
+
+def test_surface_refinement_helpers_match_reference():
+    """MaterialRenderer.near_far_from_sphere / get_intersection_around_mesh (pure tensor logic around the SDF callback) ==
+    the reference's (materialRenderer.py:281-357), called unbound on stand-in objects."""
+    import types
+    ref_shim.install()
+    import network.materialRenderer as RM
+    from tensoflow_b200.material import MaterialRenderer as PM
+    torch.manual_seed(2)
+    pn = 80
+    o = torch.nn.functional.normalize(torch.randn(pn, 3), dim=-1) * 2.0
+    d = torch.nn.functional.normalize(-o + 0.15 * torch.randn(pn, 3), dim=-1)
+    m_depth = 2.0 - 0.45 + 0.03 * torch.randn(pn, 1)
+    inv = lambda p: torch.full_like(p[..., :1], 25.0)
+    unit, radius = torch.tensor(2.0 / 63), torch.tensor(1.0)
+    ref, mine = types.SimpleNamespace(radius=radius, unit_size=unit), types.SimpleNamespace(radius=radius, unit_size=unit)
+    ref.near_far_from_sphere = types.MethodType(RM.MaterialRenderer.near_far_from_sphere, ref)
+    mine.near_far_from_sphere = types.MethodType(PM.near_far_from_sphere, mine)
+    for a, b in zip(mine.near_far_from_sphere(o, d), ref.near_far_from_sphere(o, d)):
+        assert torch.equal(a, b)
+    got = PM.get_intersection_around_mesh(mine, _sdf_sphere, inv, o, d, m_depth, 32, 9)
+    want = RM.MaterialRenderer.get_intersection_around_mesh(ref, _sdf_sphere, inv, o, d, m_depth, 32, 9)
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
