@@ -79,3 +79,34 @@ def test_surface_refinement_helpers_match_reference():
     want = RM.MaterialRenderer.get_intersection_around_mesh(ref, _sdf_sphere, inv, o, d, m_depth, 32, 9)
     for a, b in zip(got, want):
         assert torch.equal(a, b)
+
+
+def test_alpha_mask_encodings_and_losses_match_reference():
+    ref_shim.install()
+    import network.shapeRenderer as RS
+    import utils.network_utils as RU
+    import utils.ref_utils as RR
+    from tensoflow_b200 import shape_renderer as P
+    from tensoflow_b200.flow import posenc
+    from tensoflow_b200.material import ide_encode
+    from tensoflow_b200.shape_shader import ide_encode_rough
+    torch.manual_seed(3)
+    aabb = torch.tensor([[-1.0, -0.8, -1.2], [1.0, 0.9, 1.1]])
+    vol = (torch.rand(12, 10, 14) > 0.6).float()
+    x = (torch.rand(500, 3) * 2.4 - 1.2)
+    a = P.AlphaGridMask('cpu', aabb, vol).sample_alpha(x)
+    b = RS.AlphaGridMask('cpu', aabb, vol).sample_alpha(x)
+    assert torch.equal(a, b)
+    for multires in (3, 4, 6, 8):                                      # get_embedder (utils/network_utils.py:6-50)
+        emb, dim = RU.get_embedder(multires, 3)
+        assert torch.equal(posenc(x, multires), emb(x)) and dim == 3 + 6 * multires
+    d = torch.nn.functional.normalize(torch.randn(400, 3), dim=-1)
+    ide = RR.generate_ide_fn(5)                                        # complex arithmetic in the reference, real recurrences here
+    rough = torch.rand(400, 1)
+    from oracle import torch_oracle_mc as MC                            # the reference function is fp32-only: fp64 arbiter = oracle
+    want0, want1 = MC.ide_encode(d.double(), 0), MC.ide_encode(d.double(), rough.double())
+    # fp32 evaluation of the degree-16 harmonics carries ~4e-3 of rounding in the reference as well
+    assert rel_err(ide_encode(d), want0) < 4 * max(rel_err(ide(d, torch.zeros(400, 1)), want0), 1e-4)
+    assert rel_err(ide_encode_rough(d, rough), want1) < 4 * max(rel_err(ide(d, rough), want1), 1e-4)
+    pr, gt = torch.rand(64, 3), torch.rand(64, 3)
+    assert torch.equal(P.charbonnier(pr, gt), torch.sqrt(torch.sum((gt - pr) ** 2, dim=-1) + 0.001))   # shapeRenderer.py:803-805
