@@ -110,3 +110,27 @@ def test_alpha_mask_encodings_and_losses_match_reference():
     assert rel_err(ide_encode_rough(d, rough), want1) < 4 * max(rel_err(ide(d, rough), want1), 1e-4)
     pr, gt = torch.rand(64, 3), torch.rand(64, 3)
     assert torch.equal(P.charbonnier(pr, gt), torch.sqrt(torch.sum((gt - pr) ** 2, dim=-1) + 0.001))   # shapeRenderer.py:803-805
+
+
+def test_loss_variants_and_schedules_match_reference():
+    import types
+    ref_shim.install()
+    import network.shapeRenderer as RS
+    import network.materialRenderer as RM
+    from tensoflow_b200.shape_renderer import ShapeRenderer as PS
+    from tensoflow_b200.material import MaterialRenderer as PM
+    torch.manual_seed(4)
+    pr, gt = torch.rand(100, 3), torch.rand(100, 3)
+    for kind in ('l2', 'l1', 'smooth_l1', 'charbonier'):
+        s = types.SimpleNamespace(cfg={'rgb_loss': kind})
+        assert torch.equal(PS.compute_rgb_loss(s, pr, gt), RS.ShapeRenderer.compute_rgb_loss(s, pr, gt)), kind
+    for kind in ('l1', 'charbonier'):
+        s = types.SimpleNamespace(cfg={'rgb_loss': kind, 'reg_diffuse_light_lambda': 0.1})
+        assert torch.equal(PM.compute_rgb_loss(s, pr, gt), RM.MaterialRenderer.compute_rgb_loss(s, pr, gt)), kind
+        assert torch.equal(PM.compute_diffuse_light_regularization(s, pr), RM.MaterialRenderer.compute_diffuse_light_regularization(s, pr))
+    with pytest.raises(NotImplementedError):
+        PS.compute_rgb_loss(types.SimpleNamespace(cfg={'rgb_loss': 'huber'}), pr, gt)
+    for anneal_end in (-1, 50000):                                     # cos-anneal schedule (shapeRenderer.py get_anneal_val)
+        s = types.SimpleNamespace(cfg={'anneal_end': anneal_end})
+        for step in (0, 1, 24999, 50000, 300000):
+            assert PS.get_anneal_val(s, step) == RS.ShapeRenderer.get_anneal_val(s, step)
