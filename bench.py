@@ -168,6 +168,64 @@ def cpu_baseline_shape(cfg, n_rays, iters, threads):
     return n_rays / statistics.median(times), times
 
 
+def parity_check(field, variance, cfg, dev, n_rays):
+    """The benchmarked field and step on a ray subset against the oracle (fp64, PyTorch on the same device; checker only):
+    max|a-b| / max|b| of the rendered colour / SDF / alpha and of the parameter gradients."""
+    from oracle import torch_oracle as O
+    from tensoflow_b200 import synthetic
+    from tensoflow_b200.shape_renderer import render_core, charbonnier
+    rays = synthetic.make_rays(n_rays, seed=4242, device=dev)
+    t0, t1, idx = synthetic.uniform_samples(rays["rays_o"], rays["dirs"], field.aabb, cfg["samples"])
+    dt = torch.float64
+    G0 = cfg["G"] >> (cfg["L"] - 1)
+    o = O.TensoSDF([G0] * 3, [[-1.0] * 3, [1.0] * 3], sdf_n_comp=cfg["C"], sdf_dim=cfg["H"], app_dim=cfg["A"], init_n_levels=1, dtype=dt)
+    for l in range(1, cfg["L"]):
+        o.upsample_volume_grid(torch.tensor([G0 << l] * 3))
+    synthetic.copy_field_params(field, o)
+    o = o.to(dev)
+    o.update_gridSize(o.gridSize, o.n_levels)
+    var_o = variance.detach().to(dt).clone().requires_grad_()
+    ro = O.shape_render_core(o, var_o, rays["rays_o"].to(dt), rays["dirs"].to(dt), rays["radiis"].to(dt), rays["rays_cos"].to(dt),
+                             t0.to(dt), t1.to(dt), idx, synthetic.simple_color_fn, cos_anneal_ratio=1.0)
+    (O.charbonnier(ro["ray_rgb"], rays["rgbs"].to(dt)).mean() + 0.1 * ro["gradient_error"].mean()).backward()
+    for p in list(field.parameters()) + [variance]:
+        p.grad = None
+    rc = render_core(field, variance, synthetic.simple_color_fn, rays["rays_o"], rays["dirs"], rays["radiis"], rays["rays_cos"],
+                     t0, t1, idx, cos_anneal_ratio=1.0)
+    (charbonnier(rc["ray_rgb"], rays["rgbs"]).mean() + 0.1 * rc["gradient_error"].mean()).backward()
+
+    def rel(a, b):
+        return float((a.detach().double() - b.detach().double()).abs().max() / b.detach().double().abs().max().clamp_min(1e-30))
+
+    errs = {"rays": n_rays, "samples": int(idx.shape[0]), "rgb": rel(rc["ray_rgb"], ro["ray_rgb"]), "sdf": rel(rc["sdf"], ro["sdf"]),
+            "alpha": rel(rc["alpha"], ro["alpha"]), "d_variance": rel(variance.grad, var_o.grad)}
+    og = dict(o.named_parameters())
+    for name, p in field.named_parameters():
+        errs["d_" + name] = rel(p.grad, og[name].grad)
+    errs["max_output"] = max(errs["rgb"], errs["sdf"], errs["alpha"])
+    errs["max_grad"] = max(v for k, v in errs.items() if k.startswith("d_"))
+    errs["within_tolerance"] = bool(errs["max_output"] < 1e-4 and errs["max_grad"] < 1e-3)
+    for p in list(field.parameters()) + [variance]:
+        p.grad = None
+    return errs
+
+
+def secondary_lines():
+    """Config 3 (material stage) and the module-level shape step (ShapeRenderer.forward), measured in this same run by their
+    own scripts in child processes (same box, same clocks): so that they are driver-visible, not builder-only, numbers."""
+    out = {}
+    for key, script, extra in (("material_stage_config3", "bench_material.py", ["--steps", "5"]),
+                               ("shape_renderer_forward_4096x128", "bench_shape_renderer.py", ["--steps", "5"])):
+        try:
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", script), *extra], capture_output=True, text=True, timeout=600)
+            line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+            d = json.loads(line[-1]) if line else {"error": (r.stderr or "no output")[-300:]}
+            out[key] = {k: d[k] for k in ("metric", "value", "unit", "ms_per_step", "gpu_launches_per_step", "config", "rays", "error") if k in d}
+        except Exception as e:  # noqa: BLE001
+            out[key] = {"error": repr(e)[:300]}
+    return out
+
+
 def workload_name(cfg):
     return (f"shape stage: TensoSDF VM field {cfg['G']}^3 (C={cfg['C']}, H={cfg['H']}, A={cfg['A']}, {cfg['L']} mip levels), "
             f"{cfg['rays']}-ray batch x {cfg['samples']} samples, fwd+bwd")
@@ -182,18 +240,23 @@ def run_reference(args):
     n_rays = args.ref_rays
     from oracle import torch_oracle as O  # noqa: F401
     t_all = time.perf_counter()
-    rps, times = cpu_baseline_shape(cfg, n_rays, max(1, args.steps + args.warmup - 1), threads)
-    times = times[max(0, args.warmup - 1):] or times
+    # a 512-ray step of the port costs 10-25 s on the host cores: the arm times a BOUNDED number of steps (<= 3 after one
+    # warm-up step) whatever K / W say, so that the run ends within a few minutes; the line says how many
+    timed = max(1, min(args.steps, args.ref_steps))
+    rps, times = cpu_baseline_shape(cfg, n_rays, timed, threads)
     ms = 1e3 * statistics.median(times)
     val = n_rays / (ms / 1e3)
     line = {
         "impl": "reference", "metric": "train rays/sec (fwd+bwd)", "value": val, "unit": "rays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(cfg), "sample": f"{n_rays} rays x {cfg['samples']} samples per step"},
+        "config": {"workload": workload_name(cfg),
+                   "sample": f"{n_rays} of {cfg['rays']} rays (BASELINE.md 3: 1/16 subset) x {cfg['samples']} samples per step; "
+                             f"{len(times)} timed steps after 1 warm-up step (bounded sample, not K / W)"},
         "cpu_baseline": {"value": val, "unit": "rays/s", "cores": threads, "kind": "port",
-                         "sample": f"oracle/torch_oracle.py (PyTorch CPU restatement of the reference path), {n_rays} rays x "
-                                   f"{cfg['samples']} samples per step, median of {len(times)} steps"},
+                         "sample": f"oracle/torch_oracle.py (PyTorch CPU restatement of the reference path, pinned bit for bit to the "
+                                   f"reference classes), {n_rays} rays x {cfg['samples']} samples per step, median of {len(times)} steps",
+                         "step_seconds": [round(t, 2) for t in times]},
         "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t_all,
     }
@@ -235,14 +298,18 @@ def run_ours(args):
         bucket = FlatGradBucket(params)
 
     def zero_grads():
-        for p in params:
-            p.grad = None
+        if bucket is not None:
+            bucket.begin_step()        # one memset of the flat buffer; the backward kernels scatter straight into its views
+        else:
+            for p in params:
+                p.grad = None
 
     def allreduce_grads():
-        # one sum-allreduce of the flat fp32 gradient bucket (VM planes / lines, MLP weights, variance); the summed
-        # gradients are written back into p.grad, as an optimizer step would consume them
+        # one in-place sum-allreduce of the flat fp32 gradient buffer (VM planes / lines, MLP weights, variance) on NCCL's
+        # stream; p.grad of every parameter is a view into it afterwards, as an optimizer step would consume them
         if bucket is not None:
-            bucket.allreduce()
+            bucket.allreduce(async_op=True)
+            bucket.finish()
 
     def step_device(b):
         rays = {k: v.to(dev, non_blocking=True) for k, v in host[b % n_batches].items()}
@@ -350,9 +417,12 @@ def run_ours(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         threads = len(os.sched_getaffinity(0))
-        rps, times = cpu_baseline_shape(cfg, args.ref_rays, 2, threads)
+        rps, times = cpu_baseline_shape(cfg, args.ref_rays, 1, threads)
         cpu = {"value": rps, "unit": "rays/s", "cores": threads, "kind": "port",
-               "sample": f"oracle port, {args.ref_rays} of {cfg['rays']} rays x {cfg['samples']} samples, fwd+bwd, median of {len(times)}"}
+               "sample": f"oracle port, {args.ref_rays} of {cfg['rays']} rays x {cfg['samples']} samples, fwd+bwd, "
+                         f"{len(times)} timed step after 1 warm-up step ({times[0]:.1f} s)"}
+    check = parity_check(field, variance, cfg, dev, args.check_rays) if (world == 1 and args.check_rays > 0) else None
+    secondary = secondary_lines() if (world == 1 and not args.no_secondary) else None
     line = {
         "metric": "train rays/sec (fwd+bwd)", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -364,6 +434,7 @@ def run_ours(args):
         "roofline": roof, "cpu_baseline": cpu,
         "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches, "clocks": clocks, "loss": losses[-1] if losses else None,
+        "check": check, "secondary": secondary,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -378,7 +449,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rays", type=int, default=0, help="override rays per GPU per step (parity/debug only)")
     ap.add_argument("--samples", type=int, default=0, help="override samples per ray (parity/debug only)")
-    ap.add_argument("--ref-rays", type=int, default=32, help="rays per CPU-baseline step (bounded sample)")
+    ap.add_argument("--ref-rays", type=int, default=512, help="rays per CPU-baseline step (BASELINE.md 3: 1/16 of the batch)")
+    ap.add_argument("--ref-steps", type=int, default=3, help="upper bound on the timed steps of the CPU arm")
+    ap.add_argument("--check-rays", type=int, default=64, help="rays of the parity check against the oracle (0 = off)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the config-3 / module-path lines of `secondary`")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

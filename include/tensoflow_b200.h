@@ -245,14 +245,6 @@ TF_API int tf_csr_spmm3_fwd(const int32_t* rowptr, const int32_t* col, const flo
 TF_API int tf_csr_spmm3_bwd(const int32_t* rowptr, const int32_t* col, const float* val, const float* gy,
                             int32_t n_rows, float* gx, tf_stream_t stream);
 
-/* ---- tcgen05 self-test ---------------------------------------------------------------------
- * D[128,N] = A[128,K] B[N,K]^T on the 5th-gen tensor cores (TMEM accumulator), N in {128,256},
- * K % 8 == 0; passes = 1 (plain tf32) or 3 (tf32 operand splitting, fp32-level accuracy);
- * repeat > 1 re-issues the MMA sequence (throughput probe).  Validates the descriptor / TMEM /
- * mbarrier plumbing the fused decoder kernels use. */
-TF_API int tf_tc_probe(const float* A, const float* B, int32_t N, int32_t K, int32_t passes, int32_t repeat,
-                       float* D, tf_stream_t stream);
-
 /* ---- total-variation regulariser ---------------------------------------------------------------
  * TVLoss of the reference (network/other_field.py:170-191; TensoSDF.TV_loss_sdf network/fields.py:133-138,
  * MCShadingNetwork.TV_loss :1525-1530) on one channels-last texture x[H,W,C] (C % 4 == 0; lines are W = 1):
@@ -262,6 +254,18 @@ TF_API int tf_tc_probe(const float* A, const float* B, int32_t N, int32_t K, int
 TF_API int tf_tv_fwd(const float* x, int32_t H, int32_t W, int32_t C, float* sums, tf_stream_t stream);
 TF_API int tf_tv_bwd(const float* x, int32_t H, int32_t W, int32_t C, float scale_h, float scale_w,
                      const float* upstream, float* g, tf_stream_t stream);
+
+/* ---- Gaussian-smoothness regulariser ------------------------------------------------------------
+ * grid_gaussian_loss of the reference (TensoSDF network/fields.py:301-309, MCShadingNetwork :1537-1545; GaussianBlur2D /
+ * GaussianBlur1D network/other_field.py:121-168: F.conv2d / F.conv1d, stride 1, zero padding) on one channels-last
+ * texture x[H,W,C] (C % 4 == 0; lines are W = 1, KW = 1).  taps is a HOST array [KH*KW] (odd KH, KW; KH*KW <= 81):
+ *   r[h,w,c] = x[h,w,c] - sum_{a,b} taps[a,b] x[h+a-KH/2, w+b-KW/2, c]   on the interior KH/2 <= h < H-KH/2, KW/2 <= w < W-KW/2,
+ *   r = 0 elsewhere;  *sum += sum r^2
+ *   g[h,w,c] += 2 u (r[h,w,c] - sum_{a,b} taps[a,b] r[h-(a-KH/2), w-(b-KW/2), c]),  u = *upstream (device scalar) or 1 if NULL */
+TF_API int tf_gauss_residual_fwd(const float* x, int32_t H, int32_t W, int32_t C, const float* taps, int32_t KH,
+                                 int32_t KW, float* r, float* sum, tf_stream_t stream);
+TF_API int tf_gauss_residual_bwd(const float* r, int32_t H, int32_t W, int32_t C, const float* taps, int32_t KH,
+                                 int32_t KW, const float* upstream, float* g, tf_stream_t stream);
 
 /* ---- differentiable cubemap lookup ---------------------------------------------------------------
  * dr.texture(tex, dirs, [mip=stack, mip_level_bias=level,] filter_mode='linear[-mipmap-linear]', boundary_mode='cube') of the

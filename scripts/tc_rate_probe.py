@@ -1,23 +1,48 @@
-"""tcgen05.mma kind::tf32 issue-rate probe (one CTA): time per MMA for N in {128, 256}."""
-import os, sys, torch
-sys.path.insert(0, os.getcwd())
-from tensoflow_b200 import _lib
-from tensoflow_b200._lib import check, ptr, stream_ptr
-dev = torch.device('cuda:0')
-lib = _lib.load()
-for N, K in ((128, 32), (256, 32), (256, 56)):
-    A = torch.randn(128, K, device=dev); B = torch.randn(N, K, device=dev); D = torch.empty(128, N, device=dev)
-    for passes in (1, 3):
-        res = {}
-        for rep in (200, 2200):
-            check(lib.tf_tc_probe(ptr(A), ptr(B), N, K, passes, rep, ptr(D), stream_ptr()), "probe")
-            torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            check(lib.tf_tc_probe(ptr(A), ptr(B), N, K, passes, rep, ptr(D), stream_ptr()), "probe")
-            b.record(); torch.cuda.synchronize()
-            res[rep] = a.elapsed_time(b)
-        n_mma = (2200 - 200) * (K // 8) * passes
-        us = (res[2200] - res[200]) * 1e3 / n_mma
-        print(f"N={N} K={K} passes={passes}: {us * 1e3:.1f} ns per MMA = {us * 1.965e3:.0f} cycles @1.965 GHz; "
-              f"{128 * N * 8 * 2 / (us * 1e-6) / 1e12:.2f} TFLOP/s per SM -> x148 = {128 * N * 8 * 2 / (us * 1e-6) / 1e12 * 148:.0f} TFLOP/s")
+"""tcgen05.mma kind::tf32 layout / issue-rate table from the standalone probe (tests/probes/tc_probe.cu).
+
+    python scripts/tc_rate_probe.py [out.json]
+
+Every configuration runs in its own process (a faulting descriptor only kills that run).  Modes: 0 K-major no-swizzle,
+1 MN-major no-swizzle, 2 K-major SWIZZLE_128B, 3 (A) tensor memory."""
+import json, os, subprocess, sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "tests", "probes", "_bin", "tc_probe")
+
+
+def run(N, K, passes, reps, a_mode, b_mode, a_lbo=128, mn_sbo=128, swap_mn=0):
+    try:
+        out = subprocess.run([BIN] + [str(x) for x in (N, K, passes, reps, a_mode, b_mode, a_lbo, mn_sbo, swap_mn)], capture_output=True,
+                             text=True, timeout=60)
+        line = out.stdout.strip().splitlines()[-1] if out.stdout.strip() else ""
+        r = json.loads(line) if line.startswith("{") else {"error": (out.stderr or "no output").strip()[-200:]}
+    except subprocess.TimeoutExpired:
+        r = {"error": "timeout"}
+    r.update(dict(N=N, K=K, passes=passes, reps=reps, a_mode=a_mode, b_mode=b_mode, a_lbo=a_lbo, mn_sbo=mn_sbo, swap_mn=swap_mn))
+    return r
+
+
+def main():
+    rows = []
+    # layout correctness (reps = 1) -------------------------------------------------------------------
+    for a_mode, b_mode, a_lbo, mn_sbo, swap in [(0, 0, 128, 128, 0), (0, 0, 144, 128, 0), (3, 0, 128, 128, 0), (2, 2, 128, 128, 0), (2, 0, 128, 128, 0),
+                                                (0, 2, 128, 128, 0),
+                                                (0, 1, 128, 128, 0), (0, 1, 128, 128, 1), (0, 1, 128, 144, 0), (0, 1, 128, 144, 1),
+                                                (1, 0, 128, 128, 0), (1, 0, 128, 128, 1), (1, 1, 128, 144, 0), (1, 1, 128, 144, 1), (3, 1, 128, 144, 0),
+                                                (3, 1, 128, 144, 1)]:
+        for N, K in ((112, 32), (256, 64), (128, 128)):
+            rows.append(dict(kind="layout", **run(N, K, 3, 1, a_mode, b_mode, a_lbo, mn_sbo, swap)))
+            print(json.dumps(rows[-1]), flush=True)
+    # issue rate (reps = 400, passes = 1) -----------------------------------------------------------------
+    for a_mode, b_mode, a_lbo, mn_sbo, swap in [(0, 0, 128, 128, 0), (0, 0, 144, 128, 0), (2, 2, 128, 128, 0), (2, 0, 128, 128, 0), (3, 0, 128, 128, 0),
+                                                (3, 2, 128, 128, 0), (0, 1, 128, 144, 0), (0, 1, 128, 144, 1), (1, 1, 128, 144, 0), (1, 1, 128, 144, 1),
+                                                (3, 1, 128, 144, 0), (3, 1, 128, 144, 1), (1, 0, 128, 128, 0), (1, 0, 128, 128, 1)]:
+        for N in (32, 64, 112, 128, 256):
+            rows.append(dict(kind="rate", **run(N, 64, 1, 400, a_mode, b_mode, a_lbo, mn_sbo, swap)))
+            print(json.dumps(rows[-1]), flush=True)
+    if len(sys.argv) > 1:
+        json.dump(rows, open(sys.argv[1], "w"), indent=0)
+
+
+if __name__ == "__main__":
+    main()

@@ -81,7 +81,8 @@ _OPTIONAL_SIGNATURES = {
                                      _P, _P, _P, _P, _P]),
     "tf_csr_spmm3_fwd": (C.c_int, [_P, _P, _P, _P, C.c_int32, _P, _P]),
     "tf_csr_spmm3_bwd": (C.c_int, [_P, _P, _P, _P, C.c_int32, _P, _P]),
-    "tf_tc_probe": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+    "tf_gauss_residual_fwd": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.c_int32, C.c_int32, _P, _P, _P]),
+    "tf_gauss_residual_bwd": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.c_int32, C.c_int32, _P, _P, _P]),
     "tf_tv_fwd": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "tf_tv_bwd": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, _P, _P, _P]),
     "tf_cube_sample_fwd": (C.c_int, [_P, _P, C.c_int32, _P, _P, C.c_int64, _P, _P]),

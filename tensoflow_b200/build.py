@@ -77,6 +77,27 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
+PROBE_SRC = PKG.parent / "tests" / "probes" / "tc_probe.cu"
+PROBE_BIN = PKG.parent / "tests" / "probes" / "_bin" / "tc_probe"
+
+
+def build_probes(force: bool = False) -> Path | None:
+    """tests/probes/tc_probe.cu -> tests/probes/_bin/tc_probe: the tcgen05 self-test / issue-rate probe (test infrastructure,
+    a standalone executable; nothing of it is linked into libtensoflow_b200.so)."""
+    if not PROBE_SRC.exists():
+        return None
+    h = hashlib.sha256(PROBE_SRC.read_bytes() + (CSRC / "tc_common.cuh").read_bytes()).hexdigest()
+    stamp = PROBE_BIN.parent / ".stamp"
+    if not force and PROBE_BIN.exists() and stamp.exists() and stamp.read_text().strip() == h:
+        return PROBE_BIN
+    PROBE_BIN.parent.mkdir(parents=True, exist_ok=True)
+    subprocess.run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-o", str(PROBE_BIN),
+                    str(PROBE_SRC)], check=True)
+    stamp.write_text(h)
+    return PROBE_BIN
+
+
 if __name__ == "__main__":
     path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
     print(path)
+    print(build_probes(force="--force" in sys.argv))

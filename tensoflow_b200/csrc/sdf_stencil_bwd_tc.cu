@@ -45,9 +45,17 @@ struct TcBwdParams {
     float* arow;             // [tiles*128][KT]
     float* spc;              // [n][H] centre hidden activations (NULL = not needed)
     float* dW1r0; float* db1;
-    int debug;               // TF_TC_BWD_DEBUG bitmask (timing experiments only): 1 no gather, 2 no workspace stores,
+#ifdef TF_TC_DEBUG_SWITCHES
+    int debug;               // timing experiments only (never compiled into the product library): 1 no gather, 2 no workspace stores,
                              // 4 no scatter, 8 no dW1 reduction, 16 no chunk loop
+#endif
 };
+
+#ifdef TF_TC_DEBUG_SWITCHES
+#define TF_DBG(p, bit) ((p).debug & (bit))
+#else
+#define TF_DBG(p, bit) 0
+#endif
 
 // slots 0..S-1        : W0 K-slices      [H rows x 8]   hi | lo   (GEMM1 B operand)
 // slots S..S+2*NCH-1   : W0^T half-chunks [KT rows x 16] hi | lo   (GEMM-dA B operand: B[n = feature][k = hidden])
@@ -148,21 +156,21 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_bwd_tc_kernel(TcBwdParams 
         for (int64_t lt = 0; lt < my_tiles; ++lt) {
             const int64_t tile = blockIdx.x + lt * gridDim.x;
             if (lt > 0) tc::mbar_wait(dfull1, (uint32_t)((lt - 1) & 1));       // GEMM1 of the previous tile has consumed A
-            if (!(p.debug & 1))
+            if (!TF_DBG(p, 1))
                 site::gather_tile_lean(p.f, p.xyz, p.level, p.n, p.units, tile * SPT, KT, a_hi, a_lo,
-                                  (p.debug & 2) ? nullptr : p.arow + (size_t)tile * TM * KT, NGRP, mtid);
+                                  TF_DBG(p, 2) ? nullptr : p.arow + (size_t)tile * TM * KT, NGRP, mtid);
             tc::fence_async_smem();
             tc::mbar_arrive(aready);
             if (lt > 0) {
                 tc::mbar_wait(daready, (uint32_t)((lt - 1) & 1));
-                if (!(p.debug & 4))
+                if (!TF_DBG(p, 4))
                     site::scatter_tile_lean(p.f, p.g, p.xyz, p.level, p.n, p.units, (blockIdx.x + (lt - 1) * gridDim.x) * SPT, dAs, DAS, NGRP, mtid, true);
                 tc::mbar_arrive(dafree);
             }
         }
         if (my_tiles > 0) {
             tc::mbar_wait(daready, (uint32_t)((my_tiles - 1) & 1));
-            if (!(p.debug & 4))
+            if (!TF_DBG(p, 4))
                 site::scatter_tile_lean(p.f, p.g, p.xyz, p.level, p.n, p.units, (blockIdx.x + (my_tiles - 1) * gridDim.x) * SPT, dAs, DAS, NGRP, mtid, true);
         }
     } else {
@@ -274,7 +282,7 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_bwd_tc_kernel(TcBwdParams 
             tc::fence_after_sync();
             // ---- epilogue-1 + GEMM-dA, chunk by chunk over the hidden units -----------------------------------
             const float gq = gqs[row];
-            for (int c = 0; c < ((p.debug & 16) ? 0 : NCH); ++c) {
+            for (int c = 0; c < (TF_DBG(p, 16) ? 0 : NCH); ++c) {
                 const int buf = c & 1;
                 if (c >= 2) { tc::mbar_wait(&cfree[buf], (cf_commits[buf] - 1) & 1); tc::fence_after_sync(); }
                 const int col0 = c * HCH + half * 16;
@@ -297,7 +305,7 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_bwd_tc_kernel(TcBwdParams 
                 float4* dst = reinterpret_cast<float4*>(p.dpre + (size_t)(tile_row0 + row) * H + col0);
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    if (!(p.debug & 2)) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    if (!TF_DBG(p, 2)) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 {   // the chunk becomes the A operand of the dA MMAs straight in tensor memory (tf32 hi | lo, lane = row)
                     float lo[16];
 #pragma unroll
@@ -312,7 +320,7 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_bwd_tc_kernel(TcBwdParams 
 #pragma unroll
                     for (int j = 0; j < 4; ++j) sdst[j] = make_float4(sp[4 * j], sp[4 * j + 1], sp[4 * j + 2], sp[4 * j + 3]);
                 }
-                if (!(p.debug & 8)) {
+                if (!TF_DBG(p, 8)) {
                     // 16 column sums over the warp's 32 rows with 16 shuffles: every exchange halves the columns a lane owns
                     float w8[8], w4[4], w2[2];
                     const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4, b2 = lane & 2;
@@ -360,7 +368,7 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_bwd_tc_kernel(TcBwdParams 
                 }
                 ++cf_commits[buf];
             }
-            if (p.debug & 16) {
+            if (TF_DBG(p, 16)) {
                 if (tid == 0) {                         // timing experiments: the skipped slots still rotate through the ring
                     for (int c = 0; c < H / HHC; ++c) {
                         ring_prefetch();
@@ -437,7 +445,9 @@ int tf_internal_stencil_bwd_tc(const tf_vm_field_t* f, const tf_vm_mut_t* g, con
     p.K = K; p.KT = KT; p.H = H; p.slot_floats = tf_internal_bwd_tc_slot_floats(KT, H);
     for (int k = 0; k < 3; ++k) p.units[k] = units[k];
     p.dpre = dpre; p.arow = arow; p.spc = spc; p.da_scratch = da_scratch; p.dW1r0 = dW1r0; p.db1 = db1;
+#ifdef TF_TC_DEBUG_SWITCHES
     { const char* e = getenv("TF_TC_BWD_DEBUG"); p.debug = e ? atoi(e) : 0; }
+#endif
     const size_t smem = tf_internal_bwd_tc_smem(KT, H);
     cudaFuncSetAttribute(sdf_stencil_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int64_t ntiles = (n + site::SPT - 1) / site::SPT;

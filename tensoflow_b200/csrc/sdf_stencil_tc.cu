@@ -46,8 +46,17 @@ struct TcParams {
     float units[3];
     float* sdf7; float* grad; float* hess; float* sdf1;
     float* spc;          // [n][H] centre hidden activations (NULL = not needed)
-    int debug;           // TF_TC_DEBUG bitmask: 1 skip gathers, 2 skip MMAs, 4 skip epilogue math (timing experiments only)
+#ifdef TF_TC_DEBUG_SWITCHES
+    int debug;           // timing experiments only (never compiled into the product library): 1 skip gathers, 2 skip MMAs, 4 skip epilogue math
+#endif
 };
+
+// timing-experiment switches exist only in builds made with -DTF_TC_DEBUG_SWITCHES; the product library has none
+#ifdef TF_TC_DEBUG_SWITCHES
+#define TF_DBG(p, bit) ((p).debug & (bit))
+#else
+#define TF_DBG(p, bit) 0
+#endif
 
 __global__ void tc_prep_w0_kernel(const float* __restrict__ W0, int K, int KT, int H, float* __restrict__ W0tc) {
     const int S = KT / KSL;
@@ -182,7 +191,7 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_fwd_tc_kernel(TcParams p) 
                 const uint64_t adh0 = tc::desc_add(a_desc_hi, s * (KSL / 8) * a_kstep), adl0 = tc::desc_add(a_desc_lo, s * (KSL / 8) * a_kstep);
 #pragma unroll
                 for (int ks = 0; ks < KSL / 8; ++ks) {
-                    if (p.debug & 2) break;
+                    if (TF_DBG(p, 2)) break;
                     const uint64_t adh = tc::desc_add(adh0, ks * a_kstep), adl = tc::desc_add(adl0, ks * a_kstep);
                     const uint64_t wdh = tc::desc_add(wdh0, ks * 256), wdl = tc::desc_add(wdl0, ks * 256);
                     tc::mma_tf32_ss(dcol, adh, wdh, idesc, (s | ks) != 0);
@@ -208,7 +217,7 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_fwd_tc_kernel(TcParams p) 
             const uint32_t dcol = tmem_base + (uint32_t)(tp & 1) * 256 + ((uint32_t)(lq * 32) << 16);
             float psum = 0.f;
             for (int c0 = chh * 32; c0 < H; c0 += 32 * NCG) {
-                if (p.debug & 4) break;
+                if (TF_DBG(p, 4)) break;
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {            // two 16-column reads keep the register footprint small
                     const int cc = c0 + hh * 16;
@@ -237,7 +246,7 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_fwd_tc_kernel(TcParams p) 
         if (t < my_tiles) {
             tc::mbar_wait(&dfull[t & 1], (uint32_t)((t >> 1) & 1));
             if (t + 1 < my_tiles) {
-                if (!(p.debug & 1)) tc_gather(p, blockIdx.x + (t + 1) * gridDim.x, a_hi, a_lo);
+                if (!TF_DBG(p, 1)) tc_gather(p, blockIdx.x + (t + 1) * gridDim.x, a_hi, a_lo);
                 tc::fence_async_smem();
             }
         }
@@ -301,7 +310,9 @@ int tf_internal_stencil_fwd_tc(const tf_vm_field_t* f, const tf_sdf_mlp_t* m, co
     p.K = K; p.KT = KT; p.H = H; p.nq = nq;
     for (int k = 0; k < 3; ++k) p.units[k] = units ? units[k] : 0.f;
     p.sdf7 = sdf7; p.grad = grad; p.hess = hess; p.sdf1 = sdf1; p.spc = spc;
+#ifdef TF_TC_DEBUG_SWITCHES
     { const char* e = getenv("TF_TC_DEBUG"); p.debug = e ? atoi(e) : 0; }
+#endif
     tc_prep_w0_kernel<<<64, 256, 0, stream>>>(m->W0, K, KT, H, w0tc);
     const size_t smem = tf_internal_tc_fwd_smem(KT, H);
     if (smem > 227 * 1024) { tf_set_error("tensor-core stencil: tile does not fit shared memory (KT=%d, H=%d)", KT, H); return 1; }

@@ -18,58 +18,100 @@ def shard_slice(n: int, rank: int, world: int) -> slice:
     return slice(min(rank * per, n), min((rank + 1) * per, n))
 
 
-def _flat_view(g: torch.Tensor) -> torch.Tensor:
-    """1-D view of a gradient in its MEMORY order (channels-last factor grads stay views)."""
-    if g.is_contiguous():
-        return g.reshape(-1)
-    if g.dim() == 4 and g.permute(0, 2, 3, 1).is_contiguous():
-        return g.permute(0, 2, 3, 1).reshape(-1)
-    return None
+def _dense(t: torch.Tensor) -> bool:
+    """True when the tensor covers numel() consecutive elements in SOME dimension order (contiguous, channels-last, ...)."""
+    expect = 1
+    for size, stride in sorted(((s, st) for s, st in zip(t.shape, t.stride()) if s > 1), key=lambda x: x[1]):
+        if stride != expect:
+            return False
+        expect *= size
+    return True
+
+
+def _aliases(a: torch.Tensor, b: torch.Tensor) -> bool:
+    """Same elements at the same addresses (strides of size-1 dimensions are irrelevant)."""
+    return a.data_ptr() == b.data_ptr() and a.shape == b.shape and \
+        all(sa == sb for n, sa, sb in zip(a.shape, a.stride(), b.stride()) if n > 1)
 
 
 class FlatGradBucket:
-    """One flat fp32 buffer holding every parameter gradient: a single collective per step."""
+    """One flat fp32 buffer that IS the gradient storage of every parameter: `views[i]` has parameter i's shape and strides
+    (channels-last factors included) and lives inside `flat`, so the collective runs in place and there is no pack / unpack
+    copy on the common path:
+
+        bucket.begin_step()      # flat.zero_(), p.grad = None, the kernels' gradient buffers are handed out from `flat`
+        loss.backward()          # tensoflow_b200.ops backward functions scatter straight into the views; autograd adopts them
+        bucket.allreduce(async_op=True)   # in-place sum over ranks on the backend's own stream (NCCL: NVLS / ring)
+        ...                      # anything independent of the gradients overlaps the collective
+        bucket.finish()          # wait, p.grad = view for EVERY parameter (also those this rank did not touch)
+
+    A gradient that did not land in its view (a parameter fed by ordinary PyTorch ops, or by two backward calls in one
+    step) is copied into it before the collective, so the result is the same either way."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter]):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         self.numel = sum(p.numel() for p in self.params)
         dev = self.params[0].device
         self.flat = torch.zeros(self.numel, device=dev, dtype=torch.float32)
-
-    def pack(self):
+        self.views: List[torch.Tensor] = []
+        self._by_ptr = {}
         off = 0
-        for p in self.params:
+        for i, p in enumerate(self.params):
             n = p.numel()
-            if p.grad is None:
-                self.flat[off:off + n].zero_()
-            else:
-                v = _flat_view(p.grad)
-                self.flat[off:off + n].copy_(v if v is not None else p.grad.contiguous().reshape(-1))
+            seg = self.flat[off:off + n]
+            self.views.append(seg.as_strided(p.shape, p.stride()) if _dense(p) else seg.view(p.shape))
+            self._by_ptr[p.data_ptr()] = i
             off += n
+        self._handed = set()
+        self._work = None
+        self._average = False
 
-    def unpack(self):
-        off = 0
+    # ---- gradient buffers for the kernels ------------------------------------------------------------
+    def _alloc(self, like: torch.Tensor):
+        """Zeroed gradient buffer for the parameter whose storage `like` aliases: its view, once per step."""
+        i = self._by_ptr.get(like.data_ptr())
+        if i is None or i in self._handed or like.numel() != self.params[i].numel():
+            return None
+        self._handed.add(i)
+        return self.views[i]
+
+    def begin_step(self):
+        from . import ops
+        self.flat.zero_()
+        self._handed.clear()
         for p in self.params:
-            n = p.numel()
-            if p.grad is not None:
-                v = _flat_view(p.grad)
-                if v is not None:
-                    v.copy_(self.flat[off:off + n])
-                else:
-                    p.grad.copy_(self.flat[off:off + n].reshape(p.grad.shape))
-            off += n
+            p.grad = None
+        ops.set_grad_allocator(self._alloc)
 
+    # ---- the collective ----------------------------------------------------------------------------------
     def allreduce(self, average: bool = False, async_op: bool = False):
-        """Sum the bucket over all ranks (NCCL picks NVLS / ring on the NVSwitch domain)."""
-        self.pack()
-        work = None
+        """Sum (or average) every gradient over all ranks, in place in the flat buffer."""
+        from . import ops
+        ops.set_grad_allocator(None)
+        for i, (p, v) in enumerate(zip(self.params, self.views)):
+            g = p.grad
+            if g is None:
+                if i not in self._handed:
+                    v.zero_()                      # this rank did not touch the parameter: it contributes zeros
+            elif not _aliases(g, v):
+                v.copy_(g)
+        self._average = average
+        self._work = None
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=async_op)
-            if average and not async_op:
-                self.flat.div_(dist.get_world_size())
+            self._work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=True)
         if not async_op:
-            self.unpack()
-        return work
+            self.finish()
+        return self._work
+
+    def finish(self):
+        """Wait for the collective and make the summed gradients the parameters' .grad (views, no copy)."""
+        if self._work is not None:
+            self._work.wait()
+            self._work = None
+            if self._average:
+                self.flat.div_(dist.get_world_size())
+        for p, v in zip(self.params, self.views):
+            p.grad = v
 
 
 def global_mean(local_sum: torch.Tensor, local_count: torch.Tensor) -> torch.Tensor:

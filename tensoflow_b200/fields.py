@@ -36,16 +36,10 @@ class TVLoss(nn.Module):
 
     def forward(self, x):
         b, c, h, w = x.shape
-        if x.is_cuda and b == 1 and c % 4 == 0 and x.dtype == torch.float32 and x.permute(0, 2, 3, 1).is_contiguous():
-            return ops.TVFunction.apply(x, self.TVLoss_weight)       # fused kernels on the channels-last factors
-        count_h = c * (h - 1) * w
-        count_w = c * h * (w - 1)
-        total = 0.
-        if count_h != 0:
-            total = total + torch.pow(x[:, :, 1:, :] - x[:, :, :h - 1, :], 2).sum() / count_h
-        if count_w != 0:
-            total = total + torch.pow(x[:, :, :, 1:] - x[:, :, :, :w - 1], 2).sum() / count_w
-        return self.TVLoss_weight * 2 * total / b
+        if not (x.is_cuda and b == 1 and c % 4 == 0 and x.dtype == torch.float32 and x.permute(0, 2, 3, 1).is_contiguous()):
+            raise RuntimeError("tensoflow_b200.TVLoss needs one fp32 CUDA texture [1,C,H,W] stored channels-last with C % 4 == 0 "
+                               "(the VM factors of this package); there is no PyTorch fallback")
+        return ops.TVFunction.apply(x, self.TVLoss_weight)           # fused kernels on the channels-last factors
 
 
 class TensoSDF(nn.Module):
@@ -159,22 +153,18 @@ class TensoSDF(nn.Module):
         return total
 
     def grid_gaussian_loss(self):
-        k = self.kernel_size // 2
-        xs = torch.arange(-self.kernel_size // 2 + 1.0, self.kernel_size // 2 + 1.0, device=self.sdf_plane[0].device)
-        k1 = torch.exp(-xs ** 2 / (2 * self.sigma ** 2))
-        k1 = (k1 / k1.sum())[None, None]
-        xx, yy = torch.meshgrid(xs, xs, indexing='ij')
-        k2 = torch.exp(-(xx ** 2 + yy ** 2) / (2 * self.sigma ** 2))
-        k2 = (k2 / k2.sum())[None, None]
-        total = 0.
-        for i in range(3):
-            p = self.sdf_plane[i]
-            pg = F.conv2d(p.permute(1, 0, 2, 3), k2, stride=1, padding=k).permute(1, 0, 2, 3)
-            l = self.sdf_line[i]
-            lg = F.conv1d(l.permute(1, 0, 2, 3).squeeze(-1), k1, stride=1, padding=k).unsqueeze(-1).permute(1, 0, 2, 3)
-            total = total + torch.sum((p[..., k:-k, k:-k] - pg[..., k:-k, k:-k]).square())
-            total = total + torch.sum((l[..., k:-k, :] - lg[..., k:-k, :]).square())
-        return total
+        """reference fields.py:301-309 (GaussianBlur2D / 1D of other_field.py:142-168 with kernel_size 5, sigma 0.5)"""
+        return gaussian_loss(self.sdf_plane, self.sdf_line, self.kernel_size, self.sigma)
+
+
+def gaussian_loss(planes, lines, kernel_size, sigma):
+    """sum_i sum_interior (plane_i - blur2d(plane_i))^2 + (line_i - blur1d(line_i))^2 on the fused residual kernels."""
+    k1, k2 = ops.gaussian_taps(kernel_size, sigma)
+    total = 0.
+    for i in range(len(planes)):
+        total = total + ops.GaussResidualFunction.apply(planes[i], k2, kernel_size, kernel_size)
+        total = total + ops.GaussResidualFunction.apply(lines[i], k1, kernel_size, 1)
+    return total
 
 
 class SingleVarianceNetwork(nn.Module):

@@ -628,13 +628,22 @@ class MaterialRenderer(nn.Module):
     def compute_diffuse_light_regularization(self, diffuse_lights):
         return torch.sum(torch.abs(diffuse_lights - torch.mean(diffuse_lights, dim=-1, keepdim=True)), dim=-1) * self.cfg['reg_diffuse_light_lambda']
 
+    def _shuffle_train_batch(self):
+        """reference materialRenderer.py:472-476: a new host-side permutation of the surface-point pool at every wrap"""
+        self.train_batch_i = 0
+        idx = torch.randperm(self.tbn, device='cpu')
+        for k, v in self.train_batch.items():
+            pinned = v.is_pinned()
+            v = v[idx]
+            self.train_batch[k] = v.pin_memory() if pinned else v
+
     def train_step(self, step, noise=None):
         rn = self.cfg['train_ray_num']
         dev = self.cfg['device']
         b = {k: v[self.train_batch_i:self.train_batch_i + rn].to(dev, non_blocking=True) for k, v in self.train_batch.items()}
         self.train_batch_i += rn
         if self.train_batch_i + rn >= self.tbn:
-            self.train_batch_i = 0
+            self._shuffle_train_batch()
         self.shader_network.update_step(step)
         out = self.shade(b['inters'], -b['rays_d'], b['normals'], None, True, step, noise=noise)
         out['rgb_gt'] = b['rgb']

@@ -66,28 +66,60 @@ def mip_sizes(h: int, w: int, n_levels: int):
     return out
 
 
+_GRAD_ALLOCATOR = None
+
+
+def set_grad_allocator(fn):
+    """fn(tensor aliasing a parameter's storage) -> zeroed gradient buffer with the parameter's shape and strides, or None.
+    dist.FlatGradBucket installs it for the duration of a backward pass so that the kernels scatter parameter gradients
+    straight into the flat allreduce buffer."""
+    global _GRAD_ALLOCATOR
+    _GRAD_ALLOCATOR = fn
+
+
+def _grad_zeros(param_like: torch.Tensor) -> torch.Tensor:
+    """Zero-initialised gradient buffer shaped / strided like this parameter."""
+    if _GRAD_ALLOCATOR is not None:
+        v = _GRAD_ALLOCATOR(param_like)
+        if v is not None:
+            return v
+    return torch.zeros_like(param_like, memory_format=torch.preserve_format)
+
+
 _AABB_CACHE: dict = {}
 _VMDESC_CACHE: dict = {}
+_PARAM_EPOCH = 0
+
+
+def bump_param_epoch():
+    """Invalidate every cached descriptor / mip chain.  Called by code that rewrites parameters through raw device pointers
+    (optim.FusedAdam, which cannot bump the autograd version counters the cache keys rely on)."""
+    global _PARAM_EPOCH
+    _PARAM_EPOCH += 1
+    _VMDESC_CACHE.clear()
 
 
 def _aabb_floats(aabb: torch.Tensor):
-    """The 6 aabb bounds as Python floats; cached per (storage, version) so that a CUDA aabb costs one D2H sync, not one per call."""
+    """The 6 aabb bounds as Python floats; cached per (storage, version) so that a CUDA aabb costs one D2H sync, not one per
+    call.  The entry keeps the tensor alive: its storage cannot be freed and handed to another tensor (with another box)
+    while the key is live."""
     key = (aabb.data_ptr(), aabb._version, str(aabb.device))
-    v = _AABB_CACHE.get(key)
-    if v is None:
+    hit = _AABB_CACHE.get(key)
+    if hit is None:
         if len(_AABB_CACHE) > 64:
             _AABB_CACHE.clear()
         ab = aabb.detach().float().cpu()
-        v = ([float(ab[0, i]) for i in range(3)], [float(ab[1, i]) for i in range(3)])
-        _AABB_CACHE[key] = v
-    return v
+        hit = (aabb, ([float(ab[0, i]) for i in range(3)], [float(ab[1, i]) for i in range(3)]))
+        _AABB_CACHE[key] = hit
+    return hit[1]
 
 
 def vm_desc(planes, lines, aabb, n_levels, build_mips):
-    """VMDesc for these factors, reused while none of them has been modified (same storage and autograd version): the
-    forward / backward / SDF-only calls of one training step share one descriptor and ONE mip-chain build."""
+    """VMDesc for these factors, reused while none of them has been modified (same storage, same autograd version, same
+    parameter epoch): the forward / backward / SDF-only calls of one training step share one descriptor and ONE mip-chain
+    build.  The descriptor holds references to the factor tensors and the aabb, so a key cannot outlive its storage."""
     key = tuple((t.data_ptr(), t._version) for t in (*planes, *lines)) + (aabb.data_ptr(), aabb._version, int(n_levels), bool(build_mips),
-                                                                         torch.cuda.current_stream().cuda_stream)
+                                                                         torch.cuda.current_stream().cuda_stream, _PARAM_EPOCH)
     if not (build_mips and int(n_levels) > 1):
         return VMDesc(planes, lines, aabb, n_levels, build_mips)      # nothing expensive to share
     d = _VMDESC_CACHE.get(key)
@@ -103,10 +135,12 @@ class VMDesc:
 
     def __init__(self, planes: Sequence[torch.Tensor], lines: Sequence[torch.Tensor], aabb: torch.Tensor,
                  n_levels: int, build_mips: bool):
+        self.param_planes, self.param_lines = list(planes), list(lines)
         self.planes = [_nhwc(p) for p in planes]          # [H,W,C]
         self.lines = [_nhwc(l)[:, 0, :] for l in lines]   # [G,C]
         self.lines = [l if l.is_contiguous() else l.contiguous() for l in self.lines]
         self.n_levels = int(n_levels)
+        self.aabb = aabb                                  # keeps the storage behind the cache key alive
         self.C = int(self.planes[0].shape[-1])
         dev = self.planes[0].device
         self.device = dev
@@ -142,8 +176,14 @@ class VMDesc:
     def new_grads(self, with_mips: bool):
         """Zeroed gradient accumulators with the same layouts; returns (VMMut, tensors)."""
         g = VMMut()
-        gp = [torch.zeros_like(p) for p in self.planes]
-        gl = [torch.zeros_like(l) for l in self.lines]
+        gp, gl = [], []
+        for p, l, pv, lv in zip(self.param_planes, self.param_lines, self.planes, self.lines):
+            if pv.data_ptr() == p.data_ptr() and lv.data_ptr() == l.data_ptr():     # channels-last parameters (no staging copy)
+                gp.append(_nhwc(_grad_zeros(p.detach())))
+                gl.append(_nhwc(_grad_zeros(l.detach()))[:, 0, :])
+            else:
+                gp.append(torch.zeros_like(pv))
+                gl.append(torch.zeros_like(lv))
         gpm: List[Optional[torch.Tensor]] = [None] * 3
         glm: List[Optional[torch.Tensor]] = [None] * 3
         for i in range(3):
@@ -237,8 +277,7 @@ class SdfStencilFunction(torch.autograd.Function):
         vm = vm_desc(planes, lines, aabb, ctx.n_levels, with_mips)
         m, mlp_keep = _mlp_desc(W0, b0, W1, b1)
         g, gp, gl, gpm, glm = vm.new_grads(with_mips)
-        dW0 = torch.zeros_like(mlp_keep[0]); db0 = torch.zeros_like(mlp_keep[1])
-        dW1 = torch.zeros_like(mlp_keep[2]); db1 = torch.zeros_like(mlp_keep[3])
+        dW0, db0, dW1, db1 = (_grad_zeros(w) for w in mlp_keep)
         mg = SdfMlpGrad()
         mg.W0, mg.b0, mg.W1, mg.b1 = dW0.data_ptr(), db0.data_ptr(), dW1.data_ptr(), db1.data_ptr()
         need_all = lib.tf_sdf_stencil_bwd_workspace(C.byref(vm.c), C.byref(m), max(n, 1))
@@ -361,10 +400,11 @@ class NeusCompositeFunction(torch.autograd.Function):
         if n == 0:
             dv = None if d_var is None else d_var.reshape(ctx.var_shape)
             return d_sdf, d_grad, None, None, None, dv, None, d_vals, None
+        ga, go, gw = _f32c(g_acc), _f32c(g_out), _f32c(g_weights)      # converted copies must outlive the launch
         with _timed("neus_composite_bwd"):
           check(lib.tf_neus_composite_bwd(ptr(sdf_c), ptr(grad_c), ptr(dists_c), ptr(dirs_c), ptr(offs), R, ptr(var_c),
                                         ctx.cos_anneal, ptr(vals_c), D, ptr(alpha), ptr(weights), ptr(acc), ptr(out),
-                                        ptr(_f32c(g_acc)), ptr(_f32c(g_out)), ptr(_f32c(g_weights)), ptr(d_sdf), ptr(d_grad), ptr(d_vals),
+                                        ptr(ga), ptr(go), ptr(gw), ptr(d_sdf), ptr(d_grad), ptr(d_vals),
                                         ptr(d_var), stream_ptr()), "tf_neus_composite_bwd")
         dv = None if d_var is None else d_var.reshape(ctx.var_shape)
         return d_sdf, d_grad, None, None, None, dv, None, d_vals, None
@@ -459,6 +499,50 @@ class TVFunction(torch.autograd.Function):
         return g.permute(2, 0, 1)[None], None            # logical [1,C,H,W], channels-last memory like the parameter
 
 
+def gaussian_taps(kernel_size: int, sigma: float):
+    """Normalised 1-D and 2-D taps of the reference's GaussianBlur1D / GaussianBlur2D (network/other_field.py:121-135),
+    evaluated in fp32 like the reference buffers.  Returns (taps1d [KS], taps2d [KS*KS]) as Python float lists."""
+    xs = torch.arange(-kernel_size // 2 + 1.0, kernel_size // 2 + 1.0)
+    k1 = torch.exp(-xs ** 2 / (2 * sigma ** 2))
+    k1 = k1 / k1.sum()
+    xx, yy = torch.meshgrid(xs, xs, indexing='ij')
+    k2 = torch.exp(-(xx ** 2 + yy ** 2) / (2 * sigma ** 2))
+    k2 = k2 / k2.sum()
+    return [float(v) for v in k1], [float(v) for v in k2.reshape(-1)]
+
+
+class GaussResidualFunction(torch.autograd.Function):
+    """sum over the interior of (x - GaussianBlur(x))^2 for one [1,C,H,W] texture stored channels-last (one term of
+    grid_gaussian_loss, reference network/fields.py:301-309): one kernel for the residual + its squared sum, one for the
+    gradient.  `taps` is the row-major [KH*KW] kernel (KW = 1 for the [1,C,G,1] lines)."""
+
+    @staticmethod
+    def forward(ctx, x, taps, KH, KW):
+        lib = _lib.load()
+        v = _nhwc(x)
+        H, W, Cc = v.shape
+        r = torch.empty_like(v)
+        total = torch.zeros(1, device=x.device, dtype=torch.float32)
+        tp = (C.c_float * len(taps))(*taps)
+        with _timed("gauss_fwd"):
+            check(lib.tf_gauss_residual_fwd(ptr(v), H, W, Cc, tp, KH, KW, ptr(r), ptr(total), stream_ptr()), "tf_gauss_residual_fwd")
+        ctx.save_for_backward(r)
+        ctx.taps, ctx.k = tp, (KH, KW)
+        return total[0]
+
+    @staticmethod
+    def backward(ctx, g_out):
+        lib = _lib.load()
+        (r,) = ctx.saved_tensors
+        H, W, Cc = r.shape
+        g = torch.zeros_like(r)
+        go = _f32c(g_out.reshape(1))
+        with _timed("gauss_bwd"):
+            check(lib.tf_gauss_residual_bwd(ptr(r), H, W, Cc, ctx.taps, ctx.k[0], ctx.k[1], ptr(go), ptr(g), stream_ptr()),
+                  "tf_gauss_residual_bwd")
+        return g.permute(2, 0, 1)[None], None, None, None
+
+
 class PwquadFunction(torch.autograd.Function):
     """Piecewise-quadratic coupling transform (reference network/flow.py:314-525).
     y [M], st [M,21] -> x [M], logj [M].  inverse=True is the sampling direction (no grad)."""
@@ -485,7 +569,8 @@ class PwquadFunction(torch.autograd.Function):
         M = yc.shape[0]
         d_y = torch.empty_like(yc)
         d_st = torch.empty_like(stc)
+        gx, gl = _f32c(g_x), _f32c(g_logj)                           # converted copies must outlive the launch
         with _timed("pwquad_bwd"):
-            check(lib.tf_pwquad_bwd(ptr(yc), ptr(stc), M, ptr(_f32c(g_x)), ptr(_f32c(g_logj)), ptr(d_y), ptr(d_st), stream_ptr()),
+            check(lib.tf_pwquad_bwd(ptr(yc), ptr(stc), M, ptr(gx), ptr(gl), ptr(d_y), ptr(d_st), stream_ptr()),
                   "tf_pwquad_bwd")
         return d_y, d_st, None

@@ -76,4 +76,9 @@ class FusedAdam(torch.optim.Optimizer):
             check(lib.tf_adam_step(n, vp(*ps), vp(*gs), vp(*ms), vp(*vs), (C.c_int64 * n)(*numel), (C.c_float * n)(*lr), b1, b2, eps,
                                    int(k), stream), "tf_adam_step")
         del keep
+        if calls:
+            # the kernel rewrote the parameters through raw pointers: autograd version counters did not move, so everything
+            # derived from parameter values and cached on them (VM descriptors with their mip chains) must be dropped
+            from . import ops
+            ops.bump_param_epoch()
         return None

@@ -239,7 +239,10 @@ class ShapeRenderer(torch.nn.Module):
         c = self.cfg
         return {'aabb': self.aabb, 'gridSize': self.gridSize.tolist(), 'sdf_n_comp': c['sdf_n_comp'], 'sdf_dim': c['sdf_dim'],
                 'app_dim': c['app_dim'], 'sdf_multires': c['sdf_multires'], 'alphaMask_thres': c['alphaMask_thres'],
-                'step_ratio': c['step_ratio'], 'max_levels': self.max_levels}
+                'step_ratio': c['step_ratio'], 'max_levels': self.max_levels,
+                # carried by the reference dictionary as well (shapeRenderer.py:332,338); unused by this package
+                'appearance_n_comp': c.get('app_n_comp', c.get('appearance_n_comp', 0)),
+                'marched_weights_thres': c.get('marched_weights_thres', 0.0001)}
 
     def ckpt_to_save(self):
         """reference shapeRenderer.py:343-354: same dictionary layout (kwargs, state dict, bit-packed alpha mask)"""
@@ -281,6 +284,15 @@ class ShapeRenderer(torch.nn.Module):
     def set_train_batch(self, batch: Dict[str, torch.Tensor]):
         """rays_o, rays_d, dirs, radiis, rays_cos, rgbs, human_poses (host tensors, like the reference's CPU-resident batch)"""
         self.train_batch, self.train_batch_i, self.tbn = batch, 0, batch['rays_o'].shape[0]
+
+    def _shuffle_train_batch(self):
+        """reference shapeRenderer.py:411-415: a new host-side permutation of the ray pool at every wrap"""
+        self.train_batch_i = 0
+        idx = torch.randperm(self.tbn, device='cpu')
+        for k, v in self.train_batch.items():
+            pinned = v.is_pinned()
+            v = v[idx]
+            self.train_batch[k] = v.pin_memory() if pinned else v
 
     # ---- sampling (reference shapeRenderer.py:820-932) -----------------------------------------
     @staticmethod
@@ -509,7 +521,7 @@ class ShapeRenderer(torch.nn.Module):
         b = {k: v[self.train_batch_i:self.train_batch_i + rn].to(self.device, non_blocking=True) for k, v in self.train_batch.items()}
         self.train_batch_i += rn
         if self.train_batch_i + rn >= self.tbn:
-            self.train_batch_i = 0
+            self._shuffle_train_batch()
         near, far = near_far_from_sphere(b['rays_o'], b['dirs'], self.radius)
         outputs = self.render(b, near, far, b.get('human_poses'), -1, self.get_anneal_val(step), is_train=True, step=step)
         outputs['loss_rgb'] = self.compute_rgb_loss(outputs['ray_rgb'], b['rgbs'])

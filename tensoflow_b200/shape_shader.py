@@ -374,6 +374,12 @@ class ShapeShadingNetwork(nn.Module):
         self.mat_mlp = make_predictor(3, fd, 5, run_dim=128).to(dev)
         self.register_buffer('FG_LUT', load_fg_lut(dev)[None])
         self.envlight = ShadingEnvLight(device=dev, max_res=c['env_res'], min_res=c['env_min_res'])
+        # the reference registers `outer_light` (fields.py:352-358) but its forward never calls it (:422, :444 are commented
+        # out): kept as an idle module so that state dicts round-trip with the reference's strict load_state_dict
+        self.outer_light = make_predictor(3, 72 * 2 if c['sphere_direction'] else 72, 3, run_dim=128).to(dev)
+        nn.init.constant_(self.outer_light[-2].bias, np.log(0.5))
+        for p_ in self.outer_light.parameters():
+            p_.requires_grad_(False)
         self.inner_light = make_predictor(3, 51 + 72, 3, run_dim=128).to(dev)
         nn.init.constant_(self.inner_light[-2].bias, np.log(0.5))
         self.inner_weight = make_predictor(3, 51 + 39, 1, run_dim=128).to(dev)

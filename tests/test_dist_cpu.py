@@ -103,3 +103,47 @@ def test_interleaved_ids_cover_everything():
             ids = torch.cat([interleaved_ids(n, r, w) for r in range(w)])
             assert ids.numel() == n and torch.equal(torch.sort(ids).values, torch.arange(n))
             assert max(interleaved_ids(n, r, w).numel() for r in range(w)) - min(interleaved_ids(n, r, w).numel() for r in range(w)) <= 1
+
+
+def _worker_untouched(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tensoflow_b200.dist import FlatGradBucket
+    torch.manual_seed(0)
+    a = torch.nn.Parameter(torch.randn(5))
+    b = torch.nn.Parameter(torch.randn(3))           # only rank 0's shard reaches it (e.g. inner_light without occluded directions)
+    bucket = FlatGradBucket([a, b])
+    outs = []
+    for step in range(2):                            # twice: the views of step 1 must not leak into step 2
+        bucket.begin_step()
+        loss = (a * (rank + 1.0)).sum() * (step + 1)
+        if rank == 0:
+            loss = loss + (b * 2.0).sum()
+        loss.backward()
+        assert (b.grad is None) == (rank != 0)
+        work = bucket.allreduce(average=True, async_op=True)
+        bucket.finish()
+        assert work is not None and a.grad.data_ptr() == bucket.views[0].data_ptr()
+        outs.append((a.grad.clone().numpy(), b.grad.clone().numpy()))
+    q.put((rank, outs))
+    dist.destroy_process_group()
+
+
+def test_bucket_delivers_gradients_to_untouched_parameters_and_averages():
+    """a rank whose shard never touched a parameter must still receive the gradient summed from the other ranks
+    (replicas would diverge otherwise), and average=True must divide also on the asynchronous path."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_untouched, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank in range(world):
+        for step, (ga, gb) in enumerate(res[rank]):
+            assert torch.allclose(torch.from_numpy(ga), torch.full((5,), (1.0 + 2.0) / 2 * (step + 1)))
+            assert torch.allclose(torch.from_numpy(gb), torch.full((3,), 2.0 / 2))

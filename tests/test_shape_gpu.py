@@ -10,7 +10,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from conftest import rel_err
+from conftest import rel_err, record_err
 
 pytestmark = pytest.mark.gpu
 
@@ -23,10 +23,20 @@ def _cuda():
     return torch.device("cuda:0")
 
 
-def close_as_fp32(got, o64, o32, tol, what, slack=4.0):
-    e_got = rel_err(got, o64)
+def close_as_fp32(got, o64, o32, tol, what, slack=4.0, fd=False):
+    """|got - fp64 oracle| <= tol (relative, conftest.rel_err).  Only finite-difference outputs (`fd=True`: normals,
+    hessian, and what is differentiated through them) may instead sit within `slack` x the fp32 oracle's own error:
+    they divide fp32 SDF differences by units ~ 2/G, so the fp32 reference itself misses the bar there.
+    The achieved errors are recorded (conftest.record_err -> gpurun_out/gpu_test_errors.json)."""
     e_ref = rel_err(o32, o64)
-    assert e_got <= max(tol, slack * e_ref), f"{what}: rel err {e_got:.3e} (fp32 oracle {e_ref:.3e}, tol {tol:.1e})"
+    e_got = record_err(what, got, o64, tol, fp32_oracle_rel_err=e_ref, fd=bool(fd))
+    if fd:
+        bar = max(tol, slack * e_ref)
+    elif tol < 1e-4:          # bars tighter than the north star's 1e-4: may float with the fp32 oracle, never above 1e-4
+        bar = min(1e-4, max(tol, slack * e_ref))
+    else:
+        bar = tol
+    assert e_got <= bar, f"{what}: rel err {e_got:.3e} (fp32 oracle {e_ref:.3e}, tol {tol:.1e}, fd={fd})"
     return e_got
 
 
@@ -112,8 +122,8 @@ def test_stencil_forward(C, H, A, G0, ups, N, with_level):
     close_as_fp32(only[:, 0], r64[:, 0], r32[:, 0], 1e-5, "sdf (sdf-only kernel)")
     close_as_fp32(feat, r64[:, 1:], r32[:, 1:], 1e-5, "appearance features")
     close_as_fp32(full, r64, r32, 1e-5, "TensoSDF.forward")
-    close_as_fp32(grad, g64, g32, 1e-4, "FD gradient")
-    close_as_fp32(hess, h64, h32, 1e-4, "normal hessian")
+    close_as_fp32(grad, g64, g32, 1e-4, "FD gradient", fd=True)
+    close_as_fp32(hess, h64, h32, 1e-4, "normal hessian", fd=True)
 
 
 @pytest.mark.parametrize("C,H,A,G0,ups,N", CONFIGS)
@@ -140,7 +150,7 @@ def test_stencil_backward(C, H, A, G0, ups, N, with_level, monkeypatch):
     ((sdf * u_sdf.to(dev)).sum() + (feat * u_feat.to(dev)).sum() + (grad * u_grad.to(dev)).sum() + (hess * u_hess.to(dev)).sum()).backward()
     for (name, p64), (_, p32), (_, pc) in zip(o64.named_parameters(), o32.named_parameters(), cu.named_parameters()):
         assert pc.grad is not None, name
-        close_as_fp32(pc.grad, p64.grad, p32.grad, 1e-3, f"d {name}")
+        close_as_fp32(pc.grad, p64.grad, p32.grad, 1e-3, f"d {name}", fd=True)    # upstream gradients enter through the FD taps
 
 
 def _composite_inputs(n_rays, max_s, seed, D=7):
@@ -233,13 +243,68 @@ def test_render_core_end_to_end(C, H, A, G0, ups, R, S):
     loss = charbonnier(rc["ray_rgb"], rays["rgbs"].to(dev)).mean() + 0.1 * rc["gradient_error"].mean() \
         + 0.01 * rc["loss_sparse"] + 1e-4 * rc["loss_hessian"]
     loss.backward()
-    for k in ("ray_rgb", "acc", "sdf", "alpha", "weights"):
-        close_as_fp32(rc[k], r64[k], r32[k], 1e-4, k)
-    close_as_fp32(rc["normal"], r64["normal"], r32["normal"], 1e-4, "normal")
-    close_as_fp32(loss, l64, l32, 1e-4, "loss")
-    close_as_fp32(var.grad, v64.grad, v32.grad, 1e-3, "d variance")
+    close_as_fp32(rc["sdf"], r64["sdf"], r32["sdf"], 1e-4, "sdf")
+    for k in ("ray_rgb", "acc", "alpha", "weights"):          # alpha takes the FD normal (cos of the NeuS section)
+        close_as_fp32(rc[k], r64[k], r32[k], 1e-4, k, fd=True)
+    close_as_fp32(rc["normal"], r64["normal"], r32["normal"], 1e-4, "normal", fd=True)
+    close_as_fp32(loss, l64, l32, 1e-4, "loss", fd=True)
+    close_as_fp32(var.grad, v64.grad, v32.grad, 1e-3, "d variance", fd=True)
     for (name, p64), (_, p32), (_, pc) in zip(o64.named_parameters(), o32.named_parameters(), cu.named_parameters()):
-        close_as_fp32(pc.grad, p64.grad, p32.grad, 1e-3, f"d {name}")
+        close_as_fp32(pc.grad, p64.grad, p32.grad, 1e-3, f"d {name}", fd=True)
+
+
+def test_bench_configuration_parity(monkeypatch):
+    """The configuration bench.py measures (BASELINE.json configs[1]: G = 512, C = 36, H = 256, A = 128, 3 mip levels,
+    512 samples per ray, bench.build_shape / bench.shape_step themselves) at a ray count the oracle finishes in seconds:
+    288 rays x 512 samples = 147 k samples = 8192 stencil tiles = 55 tiles per persistent CTA (the mbarrier phase
+    arithmetic, the W ring and the TMEM double buffers wrap many times), with the stencil-backward workspace forced
+    into 2 slices.  Oracle (fp64 arbiter, fp32 for the finite-difference slack) runs on the GPU device in PyTorch."""
+    import bench
+    from tensoflow_b200 import ops, synthetic
+    from tensoflow_b200.shape_renderer import render_core, charbonnier
+    dev = _cuda()
+    cfg = dict(bench.SHAPE_CFG)
+    R = 288
+    field, variance = bench.build_shape(cfg, dev)
+    assert int(field.gridSize[0]) == 512 and field.n_levels == 3 and field.sdf_n_comp == 36
+    rays = synthetic.make_rays(R, seed=0, device=dev)
+    t0, t1, idx = synthetic.uniform_samples(rays["rays_o"], rays["dirs"], field.aabb, cfg["samples"])
+    n = int(idx.shape[0])
+    assert n >= 50 * 148 * 18, n
+    monkeypatch.setattr(ops, "BWD_WORKSPACE_BYTES", 1 << 30)       # 8192 tiles x 225 KB = 1.85 GB -> 2 slices
+
+    def oracle(dt):
+        o = O.TensoSDF([128] * 3, [[-1.0] * 3, [1.0] * 3], sdf_n_comp=cfg["C"], sdf_dim=cfg["H"], app_dim=cfg["A"], init_n_levels=1, dtype=dt)
+        for r in (256, 512):
+            o.upsample_volume_grid(torch.tensor([r] * 3))
+        synthetic.copy_field_params(field, o)
+        o = o.to(dev)
+        o.update_gridSize(o.gridSize, o.n_levels)                    # units follow the aabb buffer onto the device
+        var = torch.tensor(0.3, dtype=dt, device=dev, requires_grad=True)
+        r = O.shape_render_core(o, var, rays["rays_o"].to(dt), rays["dirs"].to(dt), rays["radiis"].to(dt), rays["rays_cos"].to(dt),
+                                t0.to(dt), t1.to(dt), idx, synthetic.simple_color_fn, cos_anneal_ratio=1.0)
+        loss = O.charbonnier(r["ray_rgb"], rays["rgbs"].to(dt)).mean() + 0.1 * r["gradient_error"].mean()
+        loss.backward()
+        keep = {k: r[k].detach() for k in ("ray_rgb", "acc", "sdf", "alpha", "weights", "normal", "levels")}
+        return keep, loss.detach(), var.grad, {n_: p.grad for n_, p in o.named_parameters()}
+
+    r64, l64, v64, g64 = oracle(torch.float64)
+    r32, l32, v32, g32 = oracle(torch.float32)
+    lv = r64["levels"]
+    assert float((lv > 0).float().mean()) > 0.3 and float(lv.max()) > 1.0      # the mip chain is really exercised
+    for p in field.parameters():
+        p.grad = None
+    rc = render_core(field, variance, synthetic.simple_color_fn, rays["rays_o"], rays["dirs"], rays["radiis"], rays["rays_cos"],
+                     t0, t1, idx, cos_anneal_ratio=1.0)
+    loss = charbonnier(rc["ray_rgb"], rays["rgbs"]).mean() + 0.1 * rc["gradient_error"].mean()
+    loss.backward()
+    close_as_fp32(rc["sdf"], r64["sdf"], r32["sdf"], 1e-4, "sdf")
+    for k in ("ray_rgb", "acc", "alpha", "weights", "normal"):
+        close_as_fp32(rc[k], r64[k], r32[k], 1e-4, k, fd=True)
+    close_as_fp32(loss, l64, l32, 1e-4, "loss", fd=True)
+    close_as_fp32(variance.grad, v64, v32, 1e-3, "d variance", fd=True)
+    for name, pc in field.named_parameters():
+        close_as_fp32(pc.grad, g64[name], g32[name], 1e-3, f"d {name}", fd=True)
 
 
 @pytest.mark.parametrize("shape", [(1, 8, 33, 47), (1, 36, 64, 1), (1, 16, 5, 5)])
@@ -256,7 +321,44 @@ def test_tv_loss_fused_matches_reference_formula(shape):
     loss = tv(xc) * 0.3
     loss.backward()
     xr = x0.double().requires_grad_()
-    ref = tv(xr) * 0.3              # CPU tensor: the plain PyTorch formulation
+    ref = O.tv_loss(xr, 1.7) * 0.3   # the reference formulation (oracle/torch_oracle.py)
     ref.backward()
     assert abs(float(loss.detach()) - float(ref.detach())) <= 1e-5 * abs(float(ref.detach()))
     assert rel_err(xc.grad.cpu(), xr.grad) < 1e-5
+
+
+@pytest.mark.parametrize("shape,ks,sigma", [((1, 8, 33, 47), 5, 0.5), ((1, 36, 64, 1), 5, 0.5), ((1, 16, 12, 9), 3, 0.8), ((1, 4, 4, 4), 5, 0.5)])
+def test_gaussian_residual_loss(shape, ks, sigma):
+    """one term of grid_gaussian_loss (reference network/fields.py:301-309; GaussianBlur2D / 1D network/other_field.py:121-168,
+    F.conv2d / F.conv1d with zero padding, interior only) through tf_gauss_residual_*: value and gradient against the
+    reference formulation in fp64.  (1,4,4,4) with a 5x5 kernel has an empty interior: loss 0, gradient 0."""
+    from tensoflow_b200 import ops
+    from tensoflow_b200.fields import _cl
+    dev = _cuda()
+    torch.manual_seed(sum(shape) + ks)
+    x0 = torch.randn(*shape)
+    line = shape[3] == 1
+    k1, k2 = ops.gaussian_taps(ks, sigma)
+    xc = torch.nn.Parameter(_cl(x0.to(dev)))
+    loss = ops.GaussResidualFunction.apply(xc, k1 if line else k2, ks, 1 if line else ks) * 0.7
+    loss.backward()
+    xr = x0.double().requires_grad_()
+    k = ks // 2
+    xs = torch.arange(-ks // 2 + 1.0, ks // 2 + 1.0, dtype=torch.float64)
+    if line:
+        kern = torch.exp(-xs ** 2 / (2 * sigma ** 2))
+        kern = (kern / kern.sum())[None, None]
+        blur = F.conv1d(xr.permute(1, 0, 2, 3).squeeze(-1), kern, stride=1, padding=k).unsqueeze(-1).permute(1, 0, 2, 3)
+        ref = torch.sum((xr[..., k:-k, :] - blur[..., k:-k, :]).square()) * 0.7
+    else:
+        xx, yy = torch.meshgrid(xs, xs, indexing="ij")
+        kern = torch.exp(-(xx ** 2 + yy ** 2) / (2 * sigma ** 2))
+        kern = (kern / kern.sum())[None, None]
+        blur = F.conv2d(xr.permute(1, 0, 2, 3), kern, stride=1, padding=k).permute(1, 0, 2, 3)
+        ref = torch.sum((xr[..., k:-k, k:-k] - blur[..., k:-k, k:-k]).square()) * 0.7
+    ref.backward()
+    assert abs(float(loss.detach()) - float(ref.detach())) <= 1e-5 * max(abs(float(ref.detach())), 1e-6)
+    if float(ref.detach()) > 0:
+        assert rel_err(xc.grad.cpu(), xr.grad) < 1e-5
+    else:
+        assert float(xc.grad.abs().max()) == 0.0
