@@ -61,7 +61,15 @@ def pytest_sessionfinish(session, exitstatus):
     out = os.path.join(ROOT, "gpurun_out")
     try:
         os.makedirs(out, exist_ok=True)
-        with open(os.path.join(out, "gpu_test_errors.json"), "w") as f:
-            json.dump(_ERRORS, f, indent=1, sort_keys=True)
+        path = os.path.join(out, "gpu_test_errors.json")
+        merged = {}
+        if os.path.exists(path):                     # several pytest sessions of one GPU job (suite, sanitizer passes) add up
+            try:
+                merged = json.load(open(path))
+            except ValueError:
+                merged = {}
+        merged.update(_ERRORS)
+        with open(path, "w") as f:
+            json.dump(merged, f, indent=1, sort_keys=True)
     except OSError:
         pass

@@ -118,33 +118,34 @@ __global__ void __launch_bounds__(128, 1) tc_probe_kernel(ProbeParams p) {
         const uint64_t adl = operand_desc(a_smem_mode, tc::smem_u32(a_lo), PM, K, p.a_lbo, p.mn_sbo, p.swap_mn);
         const uint64_t bdh = operand_desc(p.b_mode, tc::smem_u32(b_hi), N, K, 128, p.mn_sbo, p.swap_mn);
         const uint64_t bdl = operand_desc(p.b_mode, tc::smem_u32(b_lo), N, K, 128, p.mn_sbo, p.swap_mn);
-        // descriptors of every k-step up front: the timed loop is MMA issue only
-        uint64_t ad_hi[16], ad_lo[16], bd_hi[16], bd_lo[16];
+        // the timed loop is MMA issue only: fully unrolled groups of 8 k-steps with the descriptor offsets in registers
+        const uint32_t a_step = operand_kstep(a_smem_mode, 1, PM, p.a_lbo, p.mn_sbo), b_step = operand_kstep(p.b_mode, 1, N, 128, p.mn_sbo);
+        const bool linear_steps = a_smem_mode != 2 && p.b_mode != 2;     // SWIZZLE_128B advances 32 B inside a 128-byte span
         const int nks = K / 8;
-        for (int ks = 0; ks < nks && ks < 16; ++ks) {
-            ad_hi[ks] = tc::desc_add(adh, operand_kstep(a_smem_mode, ks, PM, p.a_lbo, p.mn_sbo));
-            ad_lo[ks] = tc::desc_add(adl, operand_kstep(a_smem_mode, ks, PM, p.a_lbo, p.mn_sbo));
-            bd_hi[ks] = tc::desc_add(bdh, operand_kstep(p.b_mode, ks, N, 128, p.mn_sbo));
-            bd_lo[ks] = tc::desc_add(bdl, operand_kstep(p.b_mode, ks, N, 128, p.mn_sbo));
-        }
         const long long t0 = clock64();
-        if (p.a_mode == 3) {
-            for (int rep = 0; rep < p.reps; ++rep) {
-                uint32_t acc = 0;
-                for (int ps = 0; ps < p.passes; ++ps)
+        for (int rep = 0; rep < p.reps; ++rep) {
+            uint32_t acc = 0;
+            for (int ps = 0; ps < p.passes; ++ps) {                       // pass 0: hi*hi, 1: hi*lo, 2: lo*hi
+                const uint64_t a0 = ps == 2 ? adl : adh, b0 = ps == 1 ? bdl : bdh;
+                const uint32_t ta = tmem_a + (ps == 2 ? K : 0);
+                if (linear_steps) {
+                    uint64_t ad = a0, bd = b0;
+                    uint32_t tk = ta;
+#pragma unroll 8
                     for (int ks = 0; ks < nks; ++ks) {
-                        tc::mma_tf32_ts(tmem_d, tmem_a + (ps == 2 ? K : 0) + ks * 8, ps == 1 ? bd_lo[ks] : bd_hi[ks], idesc, acc);
+                        if (p.a_mode == 3) tc::mma_tf32_ts(tmem_d, tk, bd, idesc, acc);
+                        else tc::mma_tf32_ss(tmem_d, ad, bd, idesc, acc);
+                        acc = 1;
+                        ad = tc::desc_add(ad, a_step); bd = tc::desc_add(bd, b_step); tk += 8;
+                    }
+                } else {
+                    for (int ks = 0; ks < nks; ++ks) {
+                        const uint64_t bd = tc::desc_add(b0, operand_kstep(p.b_mode, ks, N, 128, p.mn_sbo));
+                        if (p.a_mode == 3) tc::mma_tf32_ts(tmem_d, ta + ks * 8, bd, idesc, acc);
+                        else tc::mma_tf32_ss(tmem_d, tc::desc_add(a0, operand_kstep(a_smem_mode, ks, PM, p.a_lbo, p.mn_sbo)), bd, idesc, acc);
                         acc = 1;
                     }
-            }
-        } else {
-            for (int rep = 0; rep < p.reps; ++rep) {
-                uint32_t acc = 0;
-                for (int ps = 0; ps < p.passes; ++ps)                     // pass 0: hi*hi, 1: hi*lo, 2: lo*hi
-                    for (int ks = 0; ks < nks; ++ks) {
-                        tc::mma_tf32_ss(tmem_d, ps == 2 ? ad_lo[ks] : ad_hi[ks], ps == 1 ? bd_lo[ks] : bd_hi[ks], idesc, acc);
-                        acc = 1;
-                    }
+                }
             }
         }
         tc::mma_commit(&bar);
@@ -194,7 +195,7 @@ int main(int argc, char** argv) {
     cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice);
     cudaMemset(dD, 0xFF, D.size() * 4);
     ProbeParams p = {dA, dB, dD, dC, N, K, passes, reps < 1 ? 1 : reps, a_mode, b_mode, a_lbo, mn_sbo, swap_mn};
-    const size_t smem = 2 * (size_t)(PM + N) * K * 4 * 2 + 8192;     // generous: padded / swizzled layouts included
+    const size_t smem = (size_t)(PM + N) * K * 4 * 2 * 9 / 8 + 8192;    // hi + lo of both operands, 144-byte padded chunks included
     if (smem > 220 * 1024) { fprintf(stderr, "tile does not fit shared memory\n"); return 2; }
     cudaFuncSetAttribute(tc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     long long cyc = 0;

@@ -52,7 +52,8 @@ def test_cuda_shader_golden():
     i, o = g["inputs"], g["outputs"]
     m = ShapeShadingNetwork(dict(has_radiance_field=True, radiance_field_step=0, env_res=16, env_min_res=4, device=dev))
     res = m.load_state_dict(g["state"], strict=False)
-    assert not res.unexpected_keys and res.missing_keys == ["FG_LUT"], res
+    # the fixture was written without the reference's idle `outer_light` head (registered for checkpoint round trips only)
+    assert not res.unexpected_keys and [k for k in res.missing_keys if not k.startswith("outer_light")] == ["FG_LUT"], res
     m64 = _oracle(g, torch.float64)
     m.envlight.build_mips()
     m64.envlight.build_mips()
