@@ -267,6 +267,56 @@ TF_API int tf_gauss_residual_fwd(const float* x, int32_t H, int32_t W, int32_t C
 TF_API int tf_gauss_residual_bwd(const float* r, int32_t H, int32_t W, int32_t C, const float* taps, int32_t KH,
                                  int32_t KW, const float* upstream, float* g, tf_stream_t stream);
 
+/* ---- hierarchical ray sampler ----------------------------------------------------------------------
+ * ShapeRenderer.sample_ray / upsample / cat_z_vals (reference network/shapeRenderer.py:820-932) and sample_pdf(det=True)
+ * (utils/network_utils.py:117-147) around the SDF-only field queries (tf_sdf_only_fwd).  Depth lists are rows of
+ * z[R, stride] / sdf[R, stride] (sorted, the first n entries valid; stride <= 256).
+ *   tf_sampler_init     : z[r, j] = clip(box entry / exit, near, far) stratified by lin[j] (= torch.linspace(0, 1, n)) and
+ *                         shifted by (t_rand[r] - 0.5) * 2 / n when t_rand != NULL; pts[R*n, 3], level[R*n] = the query points
+ *                         and their mip levels log2(ball radius / base_radii) (shapeRenderer.py:966-970).  aabb = HOST
+ *                         {min xyz, max xyz}.
+ *   tf_sampler_upsample : per ray: merge the m_in samples of the previous round (new_z_in[R, m_in] with their SDF
+ *                         new_sdf_in[R*m_in]; NULL / 0 = nothing to merge) into the lists (n -> n + m_in, in place), then
+ *                         m new depths from the NeuS section weights of the merged list at the quantiles u[m]
+ *                         (= linspace(0.5/m, 1 - 0.5/m, m)) with inv_s = min(exp(10 * *variance), inv_s_cap) (variance == NULL:
+ *                         inv_s_cap): new_z[R, m], new_pts[R*m, 3], new_level[R*m].  m == 0 only merges (new_sdf_in may
+ *                         then be NULL: the last round's samples carry no SDF).
+ *   tf_sampler_finalize : intervals [z_k, z_k + dist_k) (the last one repeats the previous length) whose mid point lies
+ *                         inside the box.  Count pass (counts != NULL): counts[r]; write pass (offsets[R+1] = exclusive
+ *                         prefix sums of the counts): packed t_starts, t_ends, ray_indices (int64) in ray order. */
+TF_API int tf_sampler_init(const float* rays_o, const float* dirs, const float* near, const float* far, const float* radiis,
+                           const float* rays_cos, const float* lin, const float* t_rand, const float aabb[6],
+                           float base_radii, int32_t R, int32_t n, int32_t stride, float* z, float* pts, float* level,
+                           tf_stream_t stream);
+TF_API int tf_sampler_upsample(const float* rays_o, const float* dirs, const float* radiis, const float* rays_cos, float* z,
+                               float* sdf, const float* new_z_in, const float* new_sdf_in, int32_t m_in, const float* u,
+                               int32_t m, const float* variance, float inv_s_cap, float base_radii, int32_t R, int32_t n,
+                               int32_t stride, float* new_z, float* new_pts, float* new_level, tf_stream_t stream);
+TF_API int tf_sampler_finalize(const float* rays_o, const float* dirs, const float* z, const float aabb[6], int32_t R,
+                               int32_t n, int32_t stride, int32_t* counts, const int64_t* offsets, float* t_starts,
+                               float* t_ends, int64_t* ray_indices, tf_stream_t stream);
+
+/* ---- secondary-ray SDF probes ----------------------------------------------------------------------
+ * get_weights / get_intersection (reference utils/network_utils.py:149-202) and get_intersection_around_mesh
+ * (network/materialRenderer.py:281-313) around the SDF-only field queries: NeuS weights of sn depths per ray with
+ * inv_s = exp(10 * *variance).
+ *   tf_probe_init    : z[r, j] = t0[r] + (t1[r] - t0[r]) * lin[j]  (t0 == NULL: t1[r] * lin[j]), pts = z * dirs + origins
+ *   tf_probe_weights : m > 0: m depths resampled at the quantiles u[m] (sample_pdf, det=True) -> new_z[pn, m], new_pts;
+ *                      m == 0: weights[pn, sn-1], mid_sdf[pn, sn-1] (-1 where the SDF rises), z_mid[pn, sn-1]. */
+TF_API int tf_probe_init(const float* origins, const float* dirs, const float* t0, const float* t1, const float* lin,
+                         int32_t pn, int32_t sn, float* z, float* pts, tf_stream_t stream);
+TF_API int tf_probe_weights(const float* origins, const float* dirs, const float* z, const float* sdf, const float* variance,
+                            int32_t pn, int32_t sn, const float* u, int32_t m, float* new_z, float* new_pts,
+                            float* weights, float* mid_sdf, float* z_mid, tf_stream_t stream);
+
+/* ---- alpha-mask lookup ---------------------------------------------------------------------------
+ * AlphaGridMask.sample_alpha (reference network/shapeRenderer.py:79-97): out[i] = trilinear sample of volume[D,H,W] at
+ * g = (xyz[i] - aabb_min) * inv_half_size - 1 with F.grid_sample's align_corners=True mapping and zero padding
+ * (x -> W, y -> H, z -> D).  aabb_min / inv_half_size (= 2 / aabb size) are HOST arrays of 3 floats.  No gradient: the
+ * reference only thresholds the result. */
+TF_API int tf_alpha_mask_sample(const float* volume, int32_t D, int32_t H, int32_t W, const float aabb_min[3],
+                                const float inv_half_size[3], const float* xyz, int64_t n, float* out, tf_stream_t stream);
+
 /* ---- differentiable cubemap lookup ---------------------------------------------------------------
  * dr.texture(tex, dirs, [mip=stack, mip_level_bias=level,] filter_mode='linear[-mipmap-linear]', boundary_mode='cube') of the
  * shape-stage light (reference network/light.py:95-122, 135; network/light_utils.py:46-63): seamless bilinear footprint per

@@ -227,3 +227,12 @@ class ShapeRenderer(nn.Module):
             res['loss_occ'] = torch.zeros(1, dtype=pts.dtype)
         res.update({'_sdf': sdf, '_alpha': alpha, '_weights': w})
         return res
+
+
+def alpha_mask_sample(alpha_volume, aabb, xyz_sampled):
+    """AlphaGridMask.sample_alpha (network/shapeRenderer.py:79-97): alpha_volume [D,H,W], aabb [2,3], xyz [N,3] -> [N]."""
+    aabb_size = aabb[1] - aabb[0]
+    inv = 1.0 / aabb_size * 2
+    xyz = (xyz_sampled - aabb[0]) * inv - 1
+    vol = alpha_volume.view(1, 1, *alpha_volume.shape[-3:])
+    return F.grid_sample(vol, xyz.view(1, -1, 1, 1, 3), align_corners=True).view(-1)

@@ -81,6 +81,13 @@ _OPTIONAL_SIGNATURES = {
                                      _P, _P, _P, _P, _P]),
     "tf_csr_spmm3_fwd": (C.c_int, [_P, _P, _P, _P, C.c_int32, _P, _P]),
     "tf_csr_spmm3_bwd": (C.c_int, [_P, _P, _P, _P, C.c_int32, _P, _P]),
+    "tf_sampler_init": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(C.c_float), C.c_float, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P]),
+    "tf_sampler_upsample": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, _P, C.c_int32, _P, C.c_float, C.c_float, C.c_int32,
+                                      C.c_int32, C.c_int32, _P, _P, _P, _P]),
+    "tf_sampler_finalize": (C.c_int, [_P, _P, _P, C.POINTER(C.c_float), C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P]),
+    "tf_probe_init": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P]),
+    "tf_probe_weights": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, C.c_int32, _P, _P, _P, _P, _P, _P]),
+    "tf_alpha_mask_sample": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float), _P, C.c_int64, _P, _P]),
     "tf_gauss_residual_fwd": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.c_int32, C.c_int32, _P, _P, _P]),
     "tf_gauss_residual_bwd": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.c_int32, C.c_int32, _P, _P, _P]),
     "tf_tv_fwd": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),

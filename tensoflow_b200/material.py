@@ -494,15 +494,11 @@ class MaterialRenderer(nn.Module):
     def get_intersection_around_mesh(self, sdf_fun, inv_fun, rays_o, rays_d, m_depth, sn0=128, sn1=9):
         """reference materialRenderer.py:281-313: NeuS weights on sn0 samples within +-4 voxels of the mesh depth, sn1 importance
         samples from them (deterministic), weights again -> (z_mid, weights, mid_sdf) [pn, sn1-1]."""
-        from .shape_renderer import get_weights, sample_pdf
+        from . import sampler
         near, far = self.near_far_from_sphere(rays_o, rays_d)
         t_min = torch.minimum(torch.maximum(m_depth - self.unit_size * 4, near), far)
         t_max = torch.minimum(torch.maximum(m_depth + self.unit_size * 4, near), far)
-        z = t_min + (t_max - t_min) * torch.linspace(0.0, 1.0, sn0, device=rays_o.device)[None, :]
-        w, _ = get_weights(sdf_fun, inv_fun, z, rays_o, rays_d)
-        z_new = sample_pdf(z, w, sn1, True)
-        w, mid_sdf = get_weights(sdf_fun, inv_fun, z_new, rays_o, rays_d)
-        return (z_new[:, 1:] + z_new[:, :-1]) * 0.5, w, mid_sdf
+        return sampler.probe_sections(lambda x: sdf_fun(x).reshape(-1), inv_fun.variance, rays_o, rays_d, t_min, t_max, sn0, sn1)
 
     @torch.no_grad()
     def trace_sdf_with_mesh(self, rays_o, rays_d, sn0, sn1):

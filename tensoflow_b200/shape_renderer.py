@@ -88,31 +88,6 @@ def render_core(field, variance: torch.Tensor, color_fn: Callable, rays_o, dirs,
 # Full shape-stage orchestration (reference network/shapeRenderer.py:79-1326).  Dataset /
 # image IO is out of scope: ray batches are handed in as tensors.
 # ======================================================================================
-def sample_pdf(bins, weights, n_samples, det=False):
-    """reference utils/network_utils.py:117-147"""
-    weights = weights + 1e-5
-    pdf = weights / torch.sum(weights, -1, keepdim=True)
-    cdf = torch.cumsum(pdf, -1)
-    cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], -1)
-    if det:
-        u = torch.linspace(0. + 0.5 / n_samples, 1. - 0.5 / n_samples, steps=n_samples, device=bins.device)
-        u = u.expand(list(cdf.shape[:-1]) + [n_samples])
-    else:
-        u = torch.rand(list(cdf.shape[:-1]) + [n_samples], device=bins.device)
-    u = u.contiguous()
-    inds = torch.searchsorted(cdf, u, right=True)
-    below = torch.max(torch.zeros_like(inds - 1), inds - 1)
-    above = torch.min((cdf.shape[-1] - 1) * torch.ones_like(inds), inds)
-    inds_g = torch.stack([below, above], -1)
-    matched_shape = [inds_g.shape[0], inds_g.shape[1], cdf.shape[-1]]
-    cdf_g = torch.gather(cdf.unsqueeze(1).expand(matched_shape), 2, inds_g)
-    bins_g = torch.gather(bins.unsqueeze(1).expand(matched_shape), 2, inds_g)
-    denom = (cdf_g[..., 1] - cdf_g[..., 0])
-    denom = torch.where(denom < 1e-5, torch.ones_like(denom), denom)
-    t = (u - cdf_g[..., 0]) / denom
-    return bins_g[..., 0] + t * (bins_g[..., 1] - bins_g[..., 0])
-
-
 def get_sphere_intersection(pts, dirs):
     """reference utils/network_utils.py:108-114"""
     dtx = torch.sum(pts * dirs, dim=-1, keepdim=True)
@@ -121,29 +96,11 @@ def get_sphere_intersection(pts, dirs):
     return -dtx + torch.sqrt(dist + 1e-6)
 
 
-def get_weights(sdf_fun, inv_fun, z_vals, origins, dirs):
-    """reference utils/network_utils.py:149-170"""
-    points = z_vals.unsqueeze(-1) * dirs.unsqueeze(-2) + origins.unsqueeze(-2)
-    inv_s = inv_fun(points[:, :-1, :])[..., 0]
-    pn, sn = points.shape[:2]
-    sdf = sdf_fun(points.reshape(-1, 3)).reshape(pn, sn, -1)[..., 0]
-    prev_sdf, next_sdf = sdf[:, :-1], sdf[:, 1:]
-    prev_z, next_z = z_vals[:, :-1], z_vals[:, 1:]
-    mid_sdf = (prev_sdf + next_sdf) * 0.5
-    cos_val = (next_sdf - prev_sdf) / (next_z - prev_z + 1e-5)
-    surface_mask = (cos_val < 0)
-    cos_val = torch.clamp(cos_val, max=0)
-    dist = next_z - prev_z
-    prev_cdf = torch.sigmoid((mid_sdf - cos_val * dist * 0.5) * inv_s)
-    next_cdf = torch.sigmoid((mid_sdf + cos_val * dist * 0.5) * inv_s)
-    alpha = (prev_cdf - next_cdf + 1e-5) / (prev_cdf + 1e-5) * surface_mask.float()
-    weights = alpha * torch.cumprod(torch.cat([torch.ones([alpha.shape[0], 1], device=alpha.device), 1. - alpha + 1e-7], -1), -1)[:, :-1]
-    mid_sdf = torch.where(surface_mask, mid_sdf, torch.full_like(mid_sdf, -1.0))
-    return weights, mid_sdf
-
-
-def get_intersection(sdf_fun, inv_fun, pts, dirs, sn0=128, sn1=9):
-    """reference utils/network_utils.py:172-202 (secondary-ray occlusion probe, no_grad)"""
+def get_intersection(sdf_fun, variance, pts, dirs, sn0=128, sn1=9):
+    """reference utils/network_utils.py:172-202 (secondary-ray occlusion probe, no_grad) on the `tf_probe_*` kernels
+    (tensoflow_b200/sampler.py): `variance` is the SingleVarianceNetwork parameter (inv_s = exp(10 variance)),
+    sdf_fun(points [N,3]) -> [N,1]."""
+    from . import sampler
     dev = pts.device
     inside = torch.norm(pts, dim=-1) < 0.999
     pn = pts.shape[0]
@@ -153,12 +110,7 @@ def get_intersection(sdf_fun, inv_fun, pts, dirs, sn0=128, sn1=9):
     if torch.sum(inside) > 0:
         p, d = pts[inside], dirs[inside]
         max_dist = get_sphere_intersection(p, d)
-        with torch.no_grad():
-            z = max_dist * torch.linspace(0, 1, sn0, device=dev).unsqueeze(0)
-            w, _ = get_weights(sdf_fun, inv_fun, z, p, d)
-            z_new = sample_pdf(z, w, sn1, True)
-            w, mid_sdf = get_weights(sdf_fun, inv_fun, z_new, p, d)
-            z_mid = (z_new[:, 1:] + z_new[:, :-1]) * 0.5
+        z_mid, w, mid_sdf = sampler.probe_sections(lambda x: sdf_fun(x).reshape(-1), variance, p, d, None, max_dist, sn0, sn1)
         hit_z[inside], hit_w[inside], hit_sdf[inside] = z_mid, w, mid_sdf
     return hit_z, hit_w, hit_sdf
 
@@ -173,10 +125,21 @@ class AlphaGridMask(torch.nn.Module):
         self.aabbSize = self.aabb[1] - self.aabb[0]
         self.invgridSize = 1.0 / self.aabbSize * 2
         self.alpha_volume = alpha_volume.view(1, 1, *alpha_volume.shape[-3:])
+        self._a0 = [float(v) for v in self.aabb[0].cpu()]
+        self._inv = [float(v) for v in self.invgridSize.cpu()]
 
     def sample_alpha(self, xyz_sampled):
-        xyz = (xyz_sampled - self.aabb[0]) * self.invgridSize - 1
-        return F.grid_sample(self.alpha_volume, xyz.view(1, -1, 1, 1, 3), align_corners=True).view(-1)
+        """trilinear lookup on `tf_alpha_mask_sample` (the reference's F.grid_sample(..., align_corners=True))"""
+        import ctypes as C
+        from . import _lib
+        from ._lib import check, ptr, stream_ptr
+        xyz = xyz_sampled.detach().reshape(-1, 3).float().contiguous()
+        vol = self.alpha_volume.float().contiguous()
+        out = torch.empty(xyz.shape[0], device=xyz.device, dtype=torch.float32)
+        _, _, D, H, W = vol.shape
+        check(_lib.load().tf_alpha_mask_sample(ptr(vol), D, H, W, (C.c_float * 3)(*self._a0), (C.c_float * 3)(*self._inv), ptr(xyz),
+                                               xyz.shape[0], ptr(out), stream_ptr()), "tf_alpha_mask_sample")
+        return out
 
 
 class ShapeRenderer(torch.nn.Module):
@@ -227,6 +190,7 @@ class ShapeRenderer(torch.nn.Module):
         self.units = self.aabbSize / (self.gridSize - 1)
         self.stepSize = torch.mean(self.units) * self.cfg['step_ratio']
         self.base_radii = self.aabbSize[0] / 2.0 / self.gridSize[0]
+        self._base_radii_f = float(self.base_radii)              # host copy: the sampler kernels take it by value
 
     def get_train_opt_params(self, lr_xyz, lr_net, lr_env=0.01):
         g = self.sdf_network.get_optparam_groups(lr_xyz, lr_net)
@@ -295,80 +259,18 @@ class ShapeRenderer(torch.nn.Module):
             self.train_batch[k] = v.pin_memory() if pinned else v
 
     # ---- sampling (reference shapeRenderer.py:820-932) -----------------------------------------
-    @staticmethod
-    def upsample(rays_o, rays_d, z_vals, sdf, n_importance, inv_s):
-        batch_size, n_samples = z_vals.shape
-        pts = rays_o[:, None, :] + rays_d[:, None, :] * z_vals[..., :, None]
-        radius = torch.linalg.norm(pts, ord=2, dim=-1, keepdim=False)
-        inside_sphere = (radius[:, :-1] < 1.0) | (radius[:, 1:] < 1.0)
-        sdf = sdf.reshape(batch_size, n_samples)
-        prev_sdf, next_sdf = sdf[:, :-1], sdf[:, 1:]
-        prev_z, next_z = z_vals[:, :-1], z_vals[:, 1:]
-        mid_sdf = (prev_sdf + next_sdf) * 0.5
-        cos_val = (next_sdf - prev_sdf) / (next_z - prev_z + 1e-5)
-        prev_cos = torch.cat([torch.zeros([batch_size, 1], device=z_vals.device), cos_val[:, :-1]], dim=-1)
-        cos_val, _ = torch.min(torch.stack([prev_cos, cos_val], dim=-1), dim=-1, keepdim=False)
-        cos_val = cos_val.clip(-1e3, 0.0) * inside_sphere
-        dist = next_z - prev_z
-        prev_cdf = torch.sigmoid((mid_sdf - cos_val * dist * 0.5) * inv_s)
-        next_cdf = torch.sigmoid((mid_sdf + cos_val * dist * 0.5) * inv_s)
-        alpha = (prev_cdf - next_cdf + 1e-5) / (prev_cdf + 1e-5)
-        weights = alpha * torch.cumprod(torch.cat([torch.ones([batch_size, 1], device=z_vals.device), 1. - alpha + 1e-7], -1), -1)[:, :-1]
-        return sample_pdf(z_vals, weights, n_importance, det=True).detach()
-
-    def cat_z_vals(self, rays_o, rays_d, z_vals, new_z_vals, sdf, last=False, radiis=None, rays_cos=None):
-        batch_size, n_samples = z_vals.shape
-        _, n_importance = new_z_vals.shape
-        pts = rays_o[:, None, :] + rays_d[:, None, :] * new_z_vals[..., :, None]
-        ball = compute_ball_radii(new_z_vals[..., None], radiis[..., None, :], rays_cos[..., None, :])
-        level = torch.log2(ball / self.base_radii)
-        z_vals = torch.cat([z_vals, new_z_vals], dim=-1)
-        z_vals, index = torch.sort(z_vals, dim=-1)
-        if not last:
-            new_sdf = self.sdf_network.sdf(pts.reshape(-1, 3), level).reshape(batch_size, n_importance)
-            sdf = torch.cat([sdf, new_sdf], dim=-1)
-            sdf = torch.gather(sdf, 1, index)
-        return z_vals, sdf
-
     def sample_ray(self, rays_o, dirs, near, far, perturb, radiis=None, rays_cos=None, t_rand=None):
+        """Coarse + hierarchical importance depths on the `tf_sampler_*` kernels (tensoflow_b200/sampler.py); the SDF of the
+        query points comes from the SDF-only field kernel.  Returns the packed (t_starts, t_ends, ray_indices)."""
+        from . import sampler
         c = self.cfg
-        n_samples, n_importance, up_sample_steps = c['n_samples'], c['n_importance'], c['up_sample_steps']
-        batch_size = len(rays_o)
-        dev = rays_o.device
-        t_vals = torch.linspace(0.0, 1.0, n_samples, device=dev)
-        vec = torch.where(dirs == 0, torch.full_like(dirs, 1e-6), dirs)
-        rate_a = (self.aabb[1] - rays_o) / vec
-        rate_b = (self.aabb[0] - rays_o) / vec
-        t_min = torch.minimum(rate_a, rate_b).amax(-1).clamp(min=near[..., 0], max=far[..., 0]).unsqueeze(-1)
-        t_max = torch.maximum(rate_a, rate_b).amin(-1).clamp(min=near[..., 0], max=far[..., 0]).unsqueeze(-1)
-        t_vals = t_min + (t_max - t_min) * t_vals[None, :]
-        if perturb > 0:
-            if t_rand is None:
-                t_rand = torch.rand([batch_size, 1], device=dev)
-            t_vals = t_vals + (t_rand - 0.5) * 2.0 / n_samples
-        if n_importance > 0:
-            with torch.no_grad():
-                pts = rays_o[:, None, :] + dirs[:, None, :] * t_vals[..., :, None]
-                ball = compute_ball_radii(t_vals[..., :, None], radiis[:, None, :], rays_cos[:, None, :])
-                level = torch.log2(ball / self.base_radii)
-                sdf = self.sdf_network.sdf(pts.reshape(-1, 3), level.reshape(-1, 1)).reshape(batch_size, n_samples)
-                for i in range(up_sample_steps):
-                    rn, sn = t_vals.shape
-                    if c['clip_sample_variance']:
-                        inv_s = self.deviation_network(torch.empty([1, 3], device=dev)).expand(rn, sn - 1)
-                        inv_s = torch.clamp(inv_s, max=64 * 2 ** i)
-                    else:
-                        inv_s = torch.ones(rn, sn - 1, device=dev) * 64 * 2 ** i
-                    new_t = self.upsample(rays_o, dirs, t_vals, sdf, n_importance // up_sample_steps, inv_s)
-                    t_vals, sdf = self.cat_z_vals(rays_o, dirs, t_vals, new_t, sdf, last=(i + 1 == up_sample_steps), radiis=radiis, rays_cos=rays_cos)
-        dists = t_vals[..., 1:] - t_vals[..., :-1]
-        dists = torch.cat([dists, dists[..., -1:]], -1)
-        mid_t = t_vals + dists * 0.5
-        t_starts, t_ends = t_vals, t_vals + dists
-        ray_indices = torch.arange(batch_size, device=dev)[:, None].expand(batch_size, t_vals.shape[1])
-        points = rays_o.unsqueeze(-2) + dirs.unsqueeze(-2) * mid_t.unsqueeze(-1)
-        inner = ~((self.aabb[0] > points) | (points > self.aabb[1])).any(dim=-1)
-        return t_starts[inner], t_ends[inner], ray_indices[inner]
+        net = self.sdf_network
+        sdf_fn = lambda pts, level: net.sdf(pts, level.reshape(-1, 1)).reshape(-1)
+        t_starts, t_ends, ray_indices, offsets = sampler.hierarchical_sample(
+            sdf_fn, self.aabb, self._base_radii_f, rays_o, dirs, near, far, radiis, rays_cos, c['n_samples'], c['n_importance'],
+            c['up_sample_steps'], perturb, t_rand, self.deviation_network.variance, c['clip_sample_variance'])
+        self._last_ray_offsets = (ray_indices, offsets)          # the compositor's CSR offsets come for free
+        return t_starts, t_ends, ray_indices
 
     # ---- occlusion loss (reference shapeRenderer.py:1027-1103) ------------------------------------
     def compute_occ_loss(self, occ_info, points, sdf, gradients, dirs, step, perm=None):
@@ -386,7 +288,7 @@ class ShapeRenderer(torch.nn.Module):
             mask[indices] = 1
         if torch.sum(mask) > 0:
             if self.occ_grid is None:
-                _, inter_prob, _ = get_intersection(self.sdf_inter_fun, self.deviation_network, points[mask], reflective[mask], sn0=64, sn1=16)
+                _, inter_prob, _ = get_intersection(self.sdf_inter_fun, self.deviation_network.variance, points[mask], reflective[mask], sn0=64, sn1=16)
                 return F.l1_loss(occ_prob[mask], torch.sum(inter_prob, -1, keepdim=True))
             return F.l1_loss(occ_prob[mask], self.occ_grid_hit_probability(points[mask], reflective[mask]))
         return torch.zeros(1, device=points.device)
@@ -473,7 +375,11 @@ class ShapeRenderer(torch.nn.Module):
         vals = [sampled_color, gradients]
         if with_rad:
             vals += [sampled_radiance, occ_info['roughness']]
-        offsets = ray_offsets_from_indices(ray_indices, batch_size)
+        last = getattr(self, '_last_ray_offsets', None)
+        if last is not None and last[0] is ray_indices and N == ray_indices.shape[0]:
+            offsets = last[1]                                     # CSR offsets of the sampler (no sample was culled since)
+        else:
+            offsets = ray_offsets_from_indices(ray_indices, batch_size)
         alpha, weights, acc, out = ops.NeusCompositeFunction.apply(sdf, gradients, dists, viewdirs, offsets, variance,
                                                                    float(cos_anneal_ratio), torch.cat(vals, -1), train_var)
         acc_map = acc[:, None]

@@ -14,27 +14,31 @@ def _sdf_sphere(x):
 
 
 def test_sample_pdf_and_weights_match_reference():
+    """The product runs these on the tf_sampler_* / tf_probe_* kernels (GPU tests: tests/test_renderer.py); here their checker --
+    the oracle's restatements of sample_pdf(det=True), get_sphere_intersection, get_weights and get_intersection -- is pinned to
+    the reference's own functions (utils/network_utils.py:108-202), bit for bit."""
     ref_shim.install()
     import utils.network_utils as RU
     from tensoflow_b200 import shape_renderer as P
+    from oracle import torch_oracle_renderer as OR
     torch.manual_seed(0)
     pn, sn = 64, 33
     z = torch.sort(torch.rand(pn, sn) * 2.0, dim=-1).values
     w = torch.rand(pn, sn - 1) ** 3
     w[:5] = 0.0                                                       # rays without any surface: uniform fallback
-    assert torch.equal(P.sample_pdf(z, w, 9, det=True), RU.sample_pdf(z, w, 9, True))
+    assert torch.equal(OR.sample_pdf_det(z, w, 9), RU.sample_pdf(z, w, 9, True))
     o = torch.nn.functional.normalize(torch.randn(pn, 3), dim=-1) * 0.9
     d = torch.nn.functional.normalize(-o + 0.3 * torch.randn(pn, 3), dim=-1)
     inv = lambda p: torch.full_like(p[..., :1], 37.0)
     zz = P.get_sphere_intersection(o, d) * torch.linspace(0, 1, 24)[None]
     assert torch.equal(P.get_sphere_intersection(o, d), RU.get_sphere_intersection(o, d))
-    wa, ma = P.get_weights(_sdf_sphere, inv, zz, o, d)
-    wb, mb = RU.get_weights(_sdf_sphere, inv, zz, o, d)
-    assert torch.equal(wa, wb) and torch.equal(ma, mb)
-    ha = P.get_intersection(_sdf_sphere, inv, o, d, sn0=32, sn1=9)
-    hb = RU.get_intersection(_sdf_sphere, inv, o, d, sn0=32, sn1=9)
-    for a, b in zip(ha, hb):
-        assert torch.equal(a, b)
+    assert torch.equal(OR.sphere_exit(o, d), RU.get_sphere_intersection(o, d))
+    wa = OR.probe_weights(lambda x: _sdf_sphere(x).reshape(-1), 37.0, zz, o, d)
+    wb, _ = RU.get_weights(_sdf_sphere, inv, zz, o, d)
+    assert torch.equal(wa, wb)
+    pa = OR.occlusion_probability(lambda x: _sdf_sphere(x).reshape(-1), 37.0, o, d, sn0=32, sn1=9)
+    _, hw, _ = RU.get_intersection(_sdf_sphere, inv, o, d, sn0=32, sn1=9)
+    assert torch.equal(pa, hw.sum(-1, keepdim=True))
 
 
 def test_upsample_and_ball_radii_match_reference():
@@ -49,7 +53,10 @@ def test_upsample_and_ball_radii_match_reference():
     z = near + (far - near) * torch.linspace(0, 1, sn)[None]
     sdf = _sdf_sphere(o[:, None, :] + d[:, None, :] * z[..., None])[..., 0]
     inv_s = torch.full((pn, sn - 1), 64.0)
-    a = P.ShapeRenderer.upsample(o, d, z, sdf, 16, inv_s)
+    # the product's sampler is the tf_sampler_* kernels (GPU test: tests/test_renderer.py); their checker, the oracle's
+    # restatement of upsample + sample_pdf, is pinned here to the reference's own function
+    from oracle import torch_oracle_renderer as OR
+    a = OR.ShapeRenderer._upsample(None, o, d, z, sdf, 16, inv_s)
     b = RS.ShapeRenderer.upsample(o, d, z, sdf, 16, inv_s)
     assert torch.equal(a, b)
     dist, radiis, cos = torch.rand(pn, 1) * 3 + 0.5, torch.rand(pn, 1) * 2e-3 + 1e-4, torch.rand(pn, 1) * 0.5 + 0.5
@@ -57,12 +64,14 @@ def test_upsample_and_ball_radii_match_reference():
 
 
 def test_surface_refinement_helpers_match_reference():
-    """MaterialRenderer.near_far_from_sphere / get_intersection_around_mesh (pure tensor logic around the SDF callback) ==
-    the reference's (materialRenderer.py:281-357), called unbound on stand-in objects."""
+    """MaterialRenderer.near_far_from_sphere == the reference's, and the checker of the kernel-backed
+    get_intersection_around_mesh (oracle surface_refine's depth; GPU test tests/test_nvs_gpu.py) == the reference's
+    get_intersection_around_mesh + the depth reduction of trace_sdf_with_mesh (materialRenderer.py:281-343)."""
     import types
     ref_shim.install()
     import network.materialRenderer as RM
     from tensoflow_b200.material import MaterialRenderer as PM
+    from oracle import torch_oracle_renderer as OR
     torch.manual_seed(2)
     pn = 80
     o = torch.nn.functional.normalize(torch.randn(pn, 3), dim=-1) * 2.0
@@ -75,10 +84,13 @@ def test_surface_refinement_helpers_match_reference():
     mine.near_far_from_sphere = types.MethodType(PM.near_far_from_sphere, mine)
     for a, b in zip(mine.near_far_from_sphere(o, d), ref.near_far_from_sphere(o, d)):
         assert torch.equal(a, b)
-    got = PM.get_intersection_around_mesh(mine, _sdf_sphere, inv, o, d, m_depth, 32, 9)
-    want = RM.MaterialRenderer.get_intersection_around_mesh(ref, _sdf_sphere, inv, o, d, m_depth, 32, 9)
-    for a, b in zip(got, want):
-        assert torch.equal(a, b)
+    z, w, _ = RM.MaterialRenderer.get_intersection_around_mesh(ref, _sdf_sphere, inv, o, d, m_depth, 32, 9)
+    w = w / torch.sum(w, dim=-1, keepdim=True)
+    w = torch.where(torch.isnan(w), torch.full_like(w, 1. / 8), w)
+    want = torch.sum(w * z, -1, keepdim=True)
+    field = types.SimpleNamespace(sdf=lambda x, lvl: _sdf_sphere(x), gradient=lambda x, lvl: (torch.nn.functional.normalize(x, dim=-1), None))
+    got, _, _ = OR.surface_refine(field, 25.0, o, d, m_depth, unit, radius, 32, 9)
+    assert torch.equal(got, want)
 
 
 def test_alpha_mask_encodings_and_losses_match_reference():
@@ -94,7 +106,8 @@ def test_alpha_mask_encodings_and_losses_match_reference():
     aabb = torch.tensor([[-1.0, -0.8, -1.2], [1.0, 0.9, 1.1]])
     vol = (torch.rand(12, 10, 14) > 0.6).float()
     x = (torch.rand(500, 3) * 2.4 - 1.2)
-    a = P.AlphaGridMask('cpu', aabb, vol).sample_alpha(x)
+    from oracle import torch_oracle_renderer as OR         # the product's lookup is a CUDA kernel (tests/test_renderer.py); here
+    a = OR.alpha_mask_sample(vol, aabb, x)                  # the oracle restatement is pinned to the reference class
     b = RS.AlphaGridMask('cpu', aabb, vol).sample_alpha(x)
     assert torch.equal(a, b)
     for multires in (3, 4, 6, 8):                                      # get_embedder (utils/network_utils.py:6-50)
