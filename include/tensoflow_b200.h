@@ -219,21 +219,39 @@ TF_API int tf_cube_light_fwd(const float* base, int32_t res, const float* dirs, 
                              int64_t n, float* out, tf_stream_t stream);
 TF_API int tf_cube_light_bwd(int32_t res, const float* dirs, const uint8_t* mask, int64_t n,
                              const float* out, const float* g_out, float* d_base, tf_stream_t stream);
+/* Input rows of the inner-light MLP for the occluded (point, direction) pairs (fields.py:951-975): for the pair idx[i]
+ * (flat index into the [pn*D] arrays) X[i, 0:51] = positional encoding (8 octaves) of the hit point inters[idx[i]],
+ * X[i, 51:123] = integrated directional encoding (utils/ref_utils.py:53-117, degree 5, kappa_inv = 0) of the view direction
+ * -dirs[idx[i]] mirrored at normalize(hit_normals[idx[i]]), X[i, 123:ldx] = 0.  ide_mat [17, 36] fp32 and ide_m [36] int32 are
+ * the device copies of the IDE polynomial table and the order m of each of its 36 (m, l) entries.  No gradient: the hit
+ * records are geometry. */
+TF_API int tf_hit_encode(const float* inters, const float* dirs, const float* hit_normals, const int64_t* idx,
+                         int64_t n_hits, const float* ide_mat, const int32_t* ide_m, int32_t ldx, float* X,
+                         tf_stream_t stream);
 /* BRDF weights + estimators per surface point over D = n_diffuse + n_specular directions
- * (fields.py:1146-1157, 1208-1234).  out[pn,16] = diffuse estimate (3), specular estimate (3),
- * mean diffuse light (3), mean specular light (3), visibility (1), indirect light (3).
- * bwd: g_out[pn,16] -> d_albedo[pn,3], d_metallic[pn], d_roughness[pn], d_lights[pn,D,3]. */
+ * (fields.py:1146-1157, 1208-1234) and the neural-importance-sampling loss terms (fields.py:1254-1333).
+ * out[pn,19] = diffuse estimate (3), specular estimate (3), mean diffuse light (3), mean specular light (3), visibility (1),
+ * indirect light (3), then the NIS sums: [16] sum_{j < n_nis_diffuse} sum_rgb f(x_j) log q(x_j) / p(x_j) over the flow-sampled
+ * diffuse directions (the first n_nis_diffuse of the diffuse set), [17] the same over the specular directions with N.L > 0,
+ * [18] their number, with log q(x) = logq[p,j] - log(max(4 pi^2 H.V sin(theta), 1e-6)), theta = angles[p,j,1] * pi/2 (the
+ * half-vector parametrisation).  logq_* / angles_* may be NULL (no NIS term; [16:19] = 0): logq_diffuse [pn, n_nis_diffuse],
+ * angles_diffuse [pn, n_nis_diffuse, 2], logq_specular [pn, n_specular], angles_specular [pn, n_specular, 2].
+ * The host forms loss_nis_diffuse = -sum_p out[p,16] / (pn n_nis_diffuse 3), loss_nis_specular = -sum_p out[p,17] /
+ * max(3 sum_p out[p,18], 1).
+ * bwd: g_out[pn,19] -> d_albedo[pn,3], d_metallic[pn], d_roughness[pn], d_lights[pn,D,3], d_logq_diffuse, d_logq_specular. */
 TF_API int tf_mc_estimate_fwd(const float* normals, const float* view_dirs, const float* albedo,
-                              const float* metallic, const float* roughness, const float* dirs,
-                              const float* prob, const float* lights, const uint8_t* hit,
-                              int64_t n_points, int32_t n_diffuse, int32_t n_specular, float* out,
-                              tf_stream_t stream);
+                              const float* metallic, const float* roughness, const float* dirs, const float* prob,
+                              const float* lights, const uint8_t* hit, int64_t n_points, int32_t n_diffuse,
+                              int32_t n_specular, const float* logq_diffuse, const float* angles_diffuse,
+                              int32_t n_nis_diffuse, const float* logq_specular, const float* angles_specular,
+                              float* out, tf_stream_t stream);
 TF_API int tf_mc_estimate_bwd(const float* normals, const float* view_dirs, const float* albedo,
-                              const float* metallic, const float* roughness, const float* dirs,
-                              const float* prob, const float* lights, const uint8_t* hit,
-                              int64_t n_points, int32_t n_diffuse, int32_t n_specular,
-                              const float* g_out, float* d_albedo, float* d_metallic,
-                              float* d_roughness, float* d_lights, tf_stream_t stream);
+                              const float* metallic, const float* roughness, const float* dirs, const float* prob,
+                              const float* lights, const uint8_t* hit, int64_t n_points, int32_t n_diffuse,
+                              int32_t n_specular, const float* logq_diffuse, const float* angles_diffuse,
+                              int32_t n_nis_diffuse, const float* logq_specular, const float* angles_specular,
+                              const float* g_out, float* d_albedo, float* d_metallic, float* d_roughness,
+                              float* d_lights, float* d_logq_diffuse, float* d_logq_specular, tf_stream_t stream);
 
 /* ---- cubemap prefilter (EnvLight.build_mips, network/light.py:52-64) -----------------------
  * The reference's diffuse / specular prefilter kernels (network/renderutils/c_src/cubemap.cu:

@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(256) cube_light_bwd_kernel(int R, const float*
 
 // ---- BRDF + estimators, one warp per point ------------------------------------------------------
 struct Brdf {   // specular weight terms of one direction (fields.py:1216-1224)
-    float q, F0[3], Fr[3], G, gv, gl, Dg, den2, noh, nov, nol, den4;
+    float q, F0[3], Fr[3], G, gv, gl, Dg, den2, noh, nov, nol, den4, hov;
     bool dclamped;
 };
 __device__ __forceinline__ float g1(float c, float k) { return c / (c * (1.f - k) + k + 1e-5f); }
@@ -210,6 +210,7 @@ __device__ __forceinline__ Brdf brdf_terms(V3 n, V3 v, V3 d, const float alb[3],
     Brdf b;
     const V3 H = normalize12(v + d);
     const float hov = clamp01(dot(H, v));
+    b.hov = hov;
     const float t = clamp01(1.f - hov);
     b.q = t * t * t * t * t;
 #pragma unroll
@@ -236,15 +237,26 @@ __device__ __forceinline__ float wsum(float v) {
 }
 
 // per point outputs: [0:3] diffuse estimate, [3:6] specular estimate, [6:9] mean diffuse light,
-// [9:12] mean specular light (valid dirs), [12] visibility, [13:16] indirect light   (16 floats)
-constexpr int EST_OUT = 16;
+// [9:12] mean specular light (valid dirs), [12] visibility, [13:16] indirect light,
+// neural-importance-sampling loss terms (fields.py:1254-1333): [16] sum over the nd flow-sampled diffuse directions and rgb of
+// f(x) log q(x) / p(x), [17] the same over the N.L > 0 flow-sampled specular directions, [18] their count   (19 floats)
+constexpr int EST_OUT = 19;
+
+// log of the direction pdf of a flow sample in the half-vector parametrisation: log q(x) - log(max(4 pi^2 H.V sin(theta), EPS))
+__device__ __forceinline__ float nis_logq(float logq_x, float hov, float theta_unit) {
+    return logq_x - logf(fmaxf(4.f * PI_F * PI_F * hov * sinf(theta_unit * (0.5f * PI_F)), EPSF));
+}
+struct NisArgs {
+    const float* logq_d; const float* ang_d; int nd;     // [pn, nd], [pn, nd, 2]: the first nd diffuse directions (NULL: no term)
+    const float* logq_s; const float* ang_s;             // [pn, Ds], [pn, Ds, 2]: every specular direction (NULL: no term)
+};
 
 __global__ void __launch_bounds__(256) mc_estimate_fwd_kernel(const float* __restrict__ normals, const float* __restrict__ view,
                                                               const float* __restrict__ albedo, const float* __restrict__ metallic,
                                                               const float* __restrict__ rough, const float* __restrict__ dirs,
                                                               const float* __restrict__ prob, const float* __restrict__ lights,
                                                               const uint8_t* __restrict__ hit, int64_t pn, int Dd, int Ds,
-                                                              float* __restrict__ out) {
+                                                              NisArgs nis, float* __restrict__ out) {
     const int lane = threadIdx.x & 31;
     const int64_t p = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     if (p >= pn) return;
@@ -264,12 +276,27 @@ __global__ void __launch_bounds__(256) mc_estimate_fwd_kernel(const float* __res
             const float c = clamp01(dot(d, n)) / PI_F * (1.f - m);
 #pragma unroll
             for (int k = 0; k < 3; ++k) { acc[k] += alb[k] * c * L[k] * ip; acc[6 + k] += L[k]; }
+            if (nis.logq_d && j < nis.nd) {
+                const int64_t q = p * nis.nd + j;
+                const float hov = clamp01(dot(normalize12(v + d), v));
+                const float A = nis_logq(nis.logq_d[q], hov, nis.ang_d[q * 2 + 1]) * ip;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) acc[16] += alb[k] * c * L[k] * A;
+            }
         } else if (dot(d, n) > 0.f) {
             const Brdf b = brdf_terms(n, v, d, alb, m, a);
             const float h = hit[o] ? 1.f : 0.f;
+            float A = 0.f;
+            if (nis.logq_s) {
+                const int64_t q = p * Ds + (j - Dd);
+                A = nis_logq(nis.logq_s[q], b.hov, nis.ang_s[q * 2 + 1]) * ip;
+                acc[18] += 1.f;
+            }
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                acc[3 + k] += b.Dg * b.Fr[k] * b.G / b.den4 * L[k] * ip;
+                const float sw = b.Dg * b.Fr[k] * b.G / b.den4 * L[k];
+                acc[3 + k] += sw * ip;
+                acc[17] += sw * A;
                 acc[9 + k] += L[k];
                 acc[13 + k] += L[k] * h;
             }
@@ -289,6 +316,7 @@ __global__ void __launch_bounds__(256) mc_estimate_fwd_kernel(const float* __res
             out[p * EST_OUT + 13 + k] = acc[13 + k] * is;
         }
         out[p * EST_OUT + 12] = 1.f - acc[12] * is;
+        out[p * EST_OUT + 16] = acc[16]; out[p * EST_OUT + 17] = acc[17]; out[p * EST_OUT + 18] = acc[18];
     }
 }
 
@@ -298,9 +326,10 @@ __global__ void __launch_bounds__(256) mc_estimate_bwd_kernel(const float* __res
                                                               const float* __restrict__ rough, const float* __restrict__ dirs,
                                                               const float* __restrict__ prob, const float* __restrict__ lights,
                                                               const uint8_t* __restrict__ hit, int64_t pn, int Dd, int Ds,
-                                                              const float* __restrict__ g_out, float* __restrict__ d_albedo,
+                                                              NisArgs nis, const float* __restrict__ g_out, float* __restrict__ d_albedo,
                                                               float* __restrict__ d_metallic, float* __restrict__ d_rough,
-                                                              float* __restrict__ d_lights) {
+                                                              float* __restrict__ d_lights, float* __restrict__ d_logq_d,
+                                                              float* __restrict__ d_logq_s) {
     const int lane = threadIdx.x & 31;
     const int64_t p = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     if (p >= pn) return;
@@ -322,27 +351,41 @@ __global__ void __launch_bounds__(256) mc_estimate_bwd_kernel(const float* __res
         if (j < Dd) {
             const float c0 = clamp01(dot(d, n)) / PI_F;
             const float c = c0 * (1.f - m);
+            // the NIS term of the pair: g16 * sum_k albedo_k c L_k * A with A = log q / p  (same shape as the estimator's 1 / p)
+            float A = 0.f;
+            if (nis.logq_d && j < nis.nd) {
+                const int64_t q = p * nis.nd + j;
+                const float hov = clamp01(dot(normalize12(v + d), v));
+                A = nis_logq(nis.logq_d[q], hov, nis.ang_d[q * 2 + 1]) * ip;
+                d_logq_d[q] = g[16] * (alb[0] * L[0] + alb[1] * L[1] + alb[2] * L[2]) * c * ip;
+            }
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                const float gk = g[k] * id;
-                da[k] += gk * c * L[k] * ip;
-                dm -= gk * alb[k] * c0 * L[k] * ip;
-                dL[k] = gk * alb[k] * c * ip + g[6 + k] * id;
+                const float gk = g[k] * id * ip + g[16] * A;
+                da[k] += gk * c * L[k];
+                dm -= gk * alb[k] * c0 * L[k];
+                dL[k] = gk * alb[k] * c + g[6 + k] * id;
             }
         } else if (dot(d, n) > 0.f) {
             const Brdf b = brdf_terms(n, v, d, alb, m, a);
             const float h = hit[o] ? 1.f : 0.f;
             float dDg = 0.f, dG = 0.f;
+            float A = 0.f;
+            if (nis.logq_s) {
+                const int64_t q = p * Ds + (j - Dd);
+                A = nis_logq(nis.logq_s[q], b.hov, nis.ang_s[q * 2 + 1]) * ip;
+                d_logq_s[q] = g[17] * b.Dg * b.G / b.den4 * (b.Fr[0] * L[0] + b.Fr[1] * L[1] + b.Fr[2] * L[2]) * ip;
+            }
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                const float gsw = g[3 + k] * is * L[k] * ip;            // d / d specular weight
+                const float gsw = (g[3 + k] * is * ip + g[17] * A) * L[k];   // d / d specular weight (estimator + NIS term)
                 const float dF = gsw * b.Dg * b.G / b.den4;
                 dDg += gsw * b.Fr[k] * b.G / b.den4;
                 dG += gsw * b.Fr[k] * b.Dg / b.den4;
                 const float dF0 = dF * (1.f - b.q);
                 dm += dF0 * (alb[k] - 0.04f);
                 da[k] += dF0 * m;
-                dL[k] = g[3 + k] * is * b.Dg * b.Fr[k] * b.G / b.den4 * ip + g[9 + k] * is + g[13 + k] * is * h;
+                dL[k] = (g[3 + k] * is * ip + g[17] * A) * b.Dg * b.Fr[k] * b.G / b.den4 + g[9 + k] * is + g[13 + k] * is * h;
             }
             // D_ggx wrt a (fields.py:1019-1024)
             const float a2 = a * a;
@@ -353,6 +396,8 @@ __global__ void __launch_bounds__(256) mc_estimate_bwd_kernel(const float* __res
             const float dv = b.nov * (1.f - k) + k + 1e-5f, dl = b.nol * (1.f - k) + k + 1e-5f;
             const float dgv = -b.nov * (1.f - b.nov) / (dv * dv), dgl = -b.nol * (1.f - b.nol) / (dl * dl);
             dr += dG * (dgv * b.gl + b.gv * dgl) * 0.5f;
+        } else if (nis.logq_s && j >= Dd) {
+            d_logq_s[p * Ds + (j - Dd)] = 0.f;                       // N.L <= 0: the pair is not part of the loss
         }
         d_lights[o * 3] = dL[0]; d_lights[o * 3 + 1] = dL[1]; d_lights[o * 3 + 2] = dL[2];
     }
@@ -364,6 +409,57 @@ __global__ void __launch_bounds__(256) mc_estimate_bwd_kernel(const float* __res
         d_metallic[p] = dm;
         d_rough[p] = dr;
     }
+}
+
+// ---- hit records -> inner-light MLP input (fields.py:951-975) ---------------------------------------------------------
+// X[i, 0:51] = posenc(p, 8), X[i, 51:123] = IDE(reflect(v, n)) with kappa_inv = 0 (utils/ref_utils.py:53-117, degree 5: 36 (m, l)
+// pairs), X[i, 123:ldx] = 0, for the i-th occluded (point, direction) pair: p = inters[idx[i]], v = -dirs[idx[i]],
+// n = normalize(hit_normals[idx[i]]).  One thread per hit; the IDE polynomial table mat[17, 36] sits in shared memory.
+constexpr int IDE_NP = 17, IDE_N = 36, PE_L = 8;
+__global__ void __launch_bounds__(128) hit_encode_kernel(const float* __restrict__ inters, const float* __restrict__ dirs,
+                                                         const float* __restrict__ hit_normals, const int64_t* __restrict__ idx, int64_t M,
+                                                         const float* __restrict__ ide_mat, const int32_t* __restrict__ ide_m, int ldx,
+                                                         float* __restrict__ X) {
+    __shared__ float s_mat[IDE_NP * IDE_N];
+    __shared__ int s_m[IDE_N];
+    for (int i = threadIdx.x; i < IDE_NP * IDE_N; i += blockDim.x) s_mat[i] = ide_mat[i];
+    for (int i = threadIdx.x; i < IDE_N; i += blockDim.x) s_m[i] = ide_m[i];
+    __syncthreads();
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    const int64_t o = idx[i];
+    const V3 p = ld3(inters, o), v = -1.f * ld3(dirs, o), n = normalize12(ld3(hit_normals, o));
+    const V3 r = (dot(v, n) * 2.f) * n - v;
+    float* x = X + i * ldx;
+    const float pc[3] = {p.x, p.y, p.z};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) x[c] = pc[c];
+#pragma unroll
+    for (int k = 0; k < PE_L; ++k) {
+        const float f = (float)(1 << k);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { x[3 + k * 6 + c] = sinf(pc[c] * f); x[3 + k * 6 + 3 + c] = cosf(pc[c] * f); }
+    }
+    float zk[IDE_NP], re[IDE_NP], im[IDE_NP];
+    zk[0] = 1.f; re[0] = 1.f; im[0] = 0.f;
+#pragma unroll
+    for (int k = 1; k < IDE_NP; ++k) {
+        zk[k] = zk[k - 1] * r.z;
+        re[k] = re[k - 1] * r.x - im[k - 1] * r.y;
+        im[k] = re[k - 1] * r.y + im[k - 1] * r.x;
+    }
+    for (int j = 0; j < IDE_N; ++j) {
+        float poly = 0.f;
+#pragma unroll
+        for (int k = 0; k < IDE_NP; ++k) poly = fmaf(zk[k], s_mat[k * IDE_N + j], poly);
+        const int m = s_m[j];
+        float rm = 0.f, imm = 0.f;
+#pragma unroll
+        for (int k = 0; k < IDE_NP; ++k) if (k == m) { rm = re[k]; imm = im[k]; }
+        x[51 + j] = rm * poly;
+        x[51 + IDE_N + j] = imm * poly;
+    }
+    for (int c = 51 + 2 * IDE_N; c < ldx; ++c) x[c] = 0.f;
 }
 
 }  // namespace
@@ -408,15 +504,19 @@ extern "C" TF_API int tf_cube_light_bwd(int32_t res, const float* dirs, const ui
 
 extern "C" TF_API int tf_mc_estimate_fwd(const float* normals, const float* view_dirs, const float* albedo, const float* metallic,
                                          const float* roughness, const float* dirs, const float* prob, const float* lights,
-                                         const uint8_t* hit, int64_t n_points, int32_t n_diffuse, int32_t n_specular, float* out,
-                                         tf_stream_t stream) {
+                                         const uint8_t* hit, int64_t n_points, int32_t n_diffuse, int32_t n_specular,
+                                         const float* logq_diffuse, const float* angles_diffuse, int32_t n_nis_diffuse,
+                                         const float* logq_specular, const float* angles_specular, float* out, tf_stream_t stream) {
     if (n_points == 0) return 0;
     TF_REQUIRE(normals && view_dirs && albedo && metallic && roughness && dirs && prob && lights && hit && out, "tf_mc_estimate_fwd: NULL pointer");
     TF_REQUIRE(n_diffuse > 0 && n_specular > 0, "tf_mc_estimate_fwd: need diffuse and specular directions");
+    TF_REQUIRE(!logq_diffuse || (angles_diffuse && n_nis_diffuse > 0 && n_nis_diffuse <= n_diffuse), "tf_mc_estimate_fwd: bad diffuse NIS arguments");
+    TF_REQUIRE(!logq_specular || angles_specular, "tf_mc_estimate_fwd: bad specular NIS arguments");
+    const NisArgs nis = {logq_diffuse, angles_diffuse, logq_diffuse ? n_nis_diffuse : 0, logq_specular, angles_specular};
     const int64_t threads = n_points * 32;
     mc_estimate_fwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(normals, view_dirs, albedo, metallic, roughness,
                                                                                                 dirs, prob, lights, hit, n_points, n_diffuse,
-                                                                                                n_specular, out);
+                                                                                                n_specular, nis, out);
     tf_count_launches(1);
     TF_CHECK_LAUNCH("tf_mc_estimate_fwd");
     return 0;
@@ -424,17 +524,36 @@ extern "C" TF_API int tf_mc_estimate_fwd(const float* normals, const float* view
 
 extern "C" TF_API int tf_mc_estimate_bwd(const float* normals, const float* view_dirs, const float* albedo, const float* metallic,
                                          const float* roughness, const float* dirs, const float* prob, const float* lights,
-                                         const uint8_t* hit, int64_t n_points, int32_t n_diffuse, int32_t n_specular, const float* g_out,
-                                         float* d_albedo, float* d_metallic, float* d_roughness, float* d_lights, tf_stream_t stream) {
+                                         const uint8_t* hit, int64_t n_points, int32_t n_diffuse, int32_t n_specular,
+                                         const float* logq_diffuse, const float* angles_diffuse, int32_t n_nis_diffuse,
+                                         const float* logq_specular, const float* angles_specular, const float* g_out,
+                                         float* d_albedo, float* d_metallic, float* d_roughness, float* d_lights, float* d_logq_diffuse,
+                                         float* d_logq_specular, tf_stream_t stream) {
     if (n_points == 0) return 0;
     TF_REQUIRE(normals && view_dirs && albedo && metallic && roughness && dirs && prob && lights && hit && g_out, "tf_mc_estimate_bwd: NULL input");
     TF_REQUIRE(d_albedo && d_metallic && d_roughness && d_lights, "tf_mc_estimate_bwd: NULL output");
+    TF_REQUIRE(!logq_diffuse || (angles_diffuse && d_logq_diffuse && n_nis_diffuse > 0 && n_nis_diffuse <= n_diffuse), "tf_mc_estimate_bwd: bad diffuse NIS arguments");
+    TF_REQUIRE(!logq_specular || (angles_specular && d_logq_specular), "tf_mc_estimate_bwd: bad specular NIS arguments");
+    const NisArgs nis = {logq_diffuse, angles_diffuse, logq_diffuse ? n_nis_diffuse : 0, logq_specular, angles_specular};
     const int64_t threads = n_points * 32;
     mc_estimate_bwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(normals, view_dirs, albedo, metallic, roughness,
                                                                                                 dirs, prob, lights, hit, n_points, n_diffuse,
-                                                                                                n_specular, g_out, d_albedo, d_metallic,
-                                                                                                d_roughness, d_lights);
+                                                                                                n_specular, nis, g_out, d_albedo, d_metallic,
+                                                                                                d_roughness, d_lights, d_logq_diffuse,
+                                                                                                d_logq_specular);
     tf_count_launches(1);
     TF_CHECK_LAUNCH("tf_mc_estimate_bwd");
+    return 0;
+}
+
+extern "C" TF_API int tf_hit_encode(const float* inters, const float* dirs, const float* hit_normals, const int64_t* idx, int64_t n_hits,
+                                    const float* ide_mat, const int32_t* ide_m, int32_t ldx, float* X, tf_stream_t stream) {
+    if (n_hits == 0) return 0;
+    TF_REQUIRE(inters && dirs && hit_normals && idx && ide_mat && ide_m && X, "tf_hit_encode: NULL pointer");
+    TF_REQUIRE(ldx >= 123, "tf_hit_encode: rows need at least 123 columns");
+    hit_encode_kernel<<<(unsigned)((n_hits + 127) / 128), 128, 0, (cudaStream_t)stream>>>(inters, dirs, hit_normals, idx, n_hits, ide_mat, ide_m,
+                                                                                          ldx, X);
+    tf_count_launches(1);
+    TF_CHECK_LAUNCH("tf_hit_encode");
     return 0;
 }

@@ -242,22 +242,11 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_fwd_tc_kernel(TcParams p) 
             sdfs[((tp & 1) * NCG + chh) * TM + row] = psum;
             tc::fence_before_sync();
         }
-        // ---- gather tile t+1: the texel fetches and products run into registers while the tensor core still reads the A
-        // ---- operand of tile t; only the stores wait for its MMAs (stencil mode, one site per thread) ------------------
+        // ---- wait for the MMAs of tile t, then gather tile t+1 into the (now free) A buffer ---------------
         if (t < my_tiles) {
-            const bool more = t + 1 < my_tiles;
-            const int64_t s_next = (blockIdx.x + (t + 1) * gridDim.x) * site::SPT;
-            const bool split = nq == NQ7 && site::SPT * 3 * (p.f.n_comp / 4) <= NTH;
-            site::SiteRegs sr;
-            sr.g = -1;
-            if (more && split && !TF_DBG(p, 1)) site::gather_site_regs(p.f, p.xyz, p.level, p.n, p.units, s_next, tid, sr);
             tc::mbar_wait(&dfull[t & 1], (uint32_t)((t >> 1) & 1));
-            if (more) {
-                if (split) {
-                    if (!TF_DBG(p, 1)) site::emit_site_regs(sr, p.f, p.xyz, p.n, p.units, s_next, KT, a_hi, a_lo, NTH, tid);
-                } else if (!TF_DBG(p, 1)) {
-                    tc_gather(p, blockIdx.x + (t + 1) * gridDim.x, a_hi, a_lo);
-                }
+            if (t + 1 < my_tiles) {
+                if (!TF_DBG(p, 1)) tc_gather(p, blockIdx.x + (t + 1) * gridDim.x, a_hi, a_lo);
                 tc::fence_async_smem();
             }
         }

@@ -403,85 +403,6 @@ __device__ __forceinline__ void scatter_line_pos(float* t0, float* t1, const Lev
     }
 }
 
-// ---- split gather: the 7 products of ONE (sample, plane, channel group) site are computed into registers first (texel
-// ---- fetches + arithmetic, no shared-memory access) and stored later, so that a kernel can run the fetches of tile t+1
-// ---- while the tensor core still reads the A operand of tile t and only the 14 stores wait for it
-struct SiteRegs {
-    float4 v[NQ];          // products in emission order: centre, m0 +-, m1 +-, vm +-
-    int r0, g, i;          // first row of the sample, column group (g < 0: no site for this thread), plane index
-};
-template <bool TWO>
-__device__ __forceinline__ void gather_site_regs_t(const tf_vm_field_t& f, const float* __restrict__ xyz, const float* __restrict__ level,
-                                                   int64_t n_total, const float units[3], int64_t s_base, int task, SiteRegs& out) {
-    const int C = f.n_comp, C4 = C / 4;
-    const bool has_level = level != nullptr;
-    out.g = -1;
-    if (task >= SPT * 3 * C4) return;
-    const int c4 = task % C4, si = task / C4, i = si % 3, s = si / 3;
-    const int64_t n = s_base + s;
-    out.g = i * C4 + c4;
-    out.r0 = s * NQ;
-    out.i = i;
-    const int c = c4 * 4;
-#pragma unroll
-    for (int j = 0; j < NQ; ++j) out.v[j] = f4_zero();
-    if (n >= n_total) return;
-    const Axes a = axes(i);
-    const float x[3] = {xyz[n * 3 + 0], xyz[n * 3 + 1], xyz[n * 3 + 2]};
-    const Levels L = levels(f, has_level ? level[n] : 0.f, has_level, i);
-    const Coords k = coords(f, x, units, a);
-    const float4 L0 = fetch_line<TWO>(L, line_pos<TWO>(L, k.lv[0]), C, c);
-    const float4 P0 = fetch_plane<TWO>(L, plane_pos<TWO>(L, k.pu[0], k.pv[0]), C, c);
-    out.v[0] = f4_mul(P0, L0);
-#pragma unroll
-    for (int v = 0; v < 4; ++v) {
-        const float pu = v == 0 ? k.pu[1] : (v == 1 ? k.pu[2] : k.pu[0]);
-        const float pv = v == 2 ? k.pv[1] : (v == 3 ? k.pv[2] : k.pv[0]);
-        out.v[1 + v] = f4_mul(fetch_plane<TWO>(L, plane_pos<TWO>(L, pu, pv), C, c), L0);
-    }
-    out.v[5] = f4_mul(P0, fetch_line<TWO>(L, line_pos<TWO>(L, k.lv[1]), C, c));
-    out.v[6] = f4_mul(P0, fetch_line<TWO>(L, line_pos<TWO>(L, k.lv[2]), C, c));
-}
-__device__ __forceinline__ void gather_site_regs(const tf_vm_field_t& f, const float* __restrict__ xyz, const float* __restrict__ level,
-                                                 int64_t n_total, const float units[3], int64_t s_base, int task, SiteRegs& out) {
-    if (level != nullptr && f.n_levels > 1) gather_site_regs_t<true>(f, xyz, level, n_total, units, s_base, task, out);
-    else gather_site_regs_t<false>(f, xyz, level, n_total, units, s_base, task, out);
-}
-// second half: the stores of the site, plus (all threads of the group) the raw stencil points / zero padding of the tile
-__device__ __forceinline__ void emit_site_regs(const SiteRegs& sr, const tf_vm_field_t& f, const float* __restrict__ xyz, int64_t n_total,
-                                               const float units[3], int64_t s_base, int KT, uint8_t* a_hi, uint8_t* a_lo, int nthreads, int tid0) {
-    const int C4 = f.n_comp / 4, G = KT / 4;
-    if (sr.g >= 0) {
-        const Axes a = axes(sr.i);
-        const int r_m0 = sr.r0 + 1 + 2 * a.m0, r_m1 = sr.r0 + 1 + 2 * a.m1, r_vm = sr.r0 + 1 + 2 * a.vm;
-        put(a_hi, a_lo, a_off(sr.r0, sr.g, KT), sr.v[0]);
-        put(a_hi, a_lo, a_off(r_m0, sr.g, KT), sr.v[1]);
-        put(a_hi, a_lo, a_off(r_m0 + 1, sr.g, KT), sr.v[2]);
-        put(a_hi, a_lo, a_off(r_m1, sr.g, KT), sr.v[3]);
-        put(a_hi, a_lo, a_off(r_m1 + 1, sr.g, KT), sr.v[4]);
-        put(a_hi, a_lo, a_off(r_vm, sr.g, KT), sr.v[5]);
-        put(a_hi, a_lo, a_off(r_vm + 1, sr.g, KT), sr.v[6]);
-    }
-    const int tail_g = G - 3 * C4;
-    for (int it = tid0; it < 128 * tail_g; it += nthreads) {
-        const int r = it % 128, g = 3 * C4 + it / 128;
-        const int s = r / NQ, q = r - s * NQ;
-        const int64_t n = s_base + s;
-        float4 v = f4_zero();
-        if (g == 3 * C4 && s < SPT && n < n_total) {
-            const float x[3] = {xyz[n * 3 + 0], xyz[n * 3 + 1], xyz[n * 3 + 2]};
-            float pt[3];
-            stencil_point(x, units, q, pt);
-            v = make_float4(pt[0], pt[1], pt[2], 0.f);
-        }
-        put(a_hi, a_lo, a_off(r, g, KT), v);
-    }
-    for (int it = tid0; it < 2 * 3 * C4; it += nthreads) {
-        const int r = SPT * NQ + it / (3 * C4), g = it % (3 * C4);
-        put(a_hi, a_lo, a_off(r, g, KT), f4_zero());
-    }
-}
-
 template <bool TWO>
 __device__ __forceinline__ void gather_tile_lean_t(const tf_vm_field_t& f, const float* __restrict__ xyz, const float* __restrict__ level,
                                                    int64_t n_total, const float units[3], int64_t s_base, int KT, uint8_t* a_hi, uint8_t* a_lo,

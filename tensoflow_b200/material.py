@@ -111,6 +111,33 @@ def make_predictor(n_layers, feats_dim, output_dim, run_dim=None):
     return nn.Sequential(*layers)
 
 
+_IDE_DEV = {}
+
+
+def _ide_device_tables(device):
+    """IDE polynomial table [17,36] fp32 and the order m of its 36 entries (int32) on the device, for tf_hit_encode."""
+    key = str(device)
+    if key not in _IDE_DEV:
+        ml, mat = _ide_tables(5)
+        _IDE_DEV[key] = (torch.from_numpy(np.ascontiguousarray(mat, dtype=np.float32)).to(device).contiguous(),
+                         torch.from_numpy(ml[0].astype(np.int32)).to(device).contiguous())
+    return _IDE_DEV[key]
+
+
+def run_predictor_padded(seq: nn.Sequential, x_padded, k_valid: int, final_act: str, act_param: float = 0.0):
+    """run_predictor for an input whose rows are already zero-padded from k_valid to x_padded.shape[1] columns: the first
+    layer's weight is padded alike (zero columns), so no copy of the activations is made."""
+    n = len(seq) // 2
+    x = x_padded
+    for i in range(n):
+        lin = seq[2 * i]
+        w = lin.weight
+        if i == 0 and x.shape[1] != k_valid:
+            w = F.pad(w, (0, x.shape[1] - k_valid))
+        x = ops.linear(x, w, lin.bias, "relu" if i < n - 1 else final_act, act_param)
+    return x
+
+
 def run_predictor(seq: nn.Sequential, x, final_act: str, act_param: float = 0.0):
     n = len(seq) // 2
     for i in range(n):
@@ -299,10 +326,11 @@ class MCShadingNetwork(nn.Module):
                 lights = lights.index_add(0, midx, run_predictor(self.outer_light, enc, "exp", self.cfg['light_exp_max']))
         idx = torch.nonzero(hit)[:, 0]
         if idx.numel() > 0:                                           # occluded directions: indirect-light MLP
-            p, v, n = inters[idx], -dirs.reshape(-1, 3)[idx], F.normalize(hit_normals[idx], dim=-1)
-            refl = torch.sum(v * n, -1, keepdim=True) * n * 2 - v
-            enc = torch.cat([posenc(p, 8), ide_encode(refl)], -1)
-            inner = run_predictor(self.inner_light, enc, "exp", self.cfg['inner_light_exp_max'])
+            # [posenc(hit point, 8) | IDE(view mirrored at the hit normal)] of the hit records in one kernel, already padded to
+            # the 128 columns the tensor-core first layer wants
+            ide_mat, ide_m = _ide_device_tables(pts.device)
+            enc = mc_ops.hit_encode(inters, dirs, hit_normals, idx, ide_mat, ide_m, 128)
+            inner = run_predictor_padded(self.inner_light, enc, 123, "exp", self.cfg['inner_light_exp_max'])
             lights = lights.index_add(0, idx, inner)
         lights = lights * near
         return lights.reshape(pn, D, 3), hit.reshape(pn, D), inters.reshape(pn, D, 3)
@@ -348,7 +376,20 @@ class MCShadingNetwork(nn.Module):
                 mc_ops.mc_directions(2, normals, view_dirs, self.specular_direction_samples, None if az is None else az.reshape(pn),
                                      rough_d.reshape(pn), Ds, dirs, prob, Dd)
         lights, hit, inters = self.get_lights(pts, dirs)
-        est = mc_ops.McEstimateFunction.apply(normals, view_dirs, albedo, metallic, roughness, dirs, prob, lights, hit, Dd)
+        # ---- flow densities of the flow-sampled directions (reference fields.py:1254-1333): log q(x) enters the estimator
+        # ---- kernel, which also accumulates the two neural-importance-sampling loss sums per point --------------------
+        nis_d = use_fd and step is not None and step >= c['nis_loss_iter_diffuse']
+        nis_s = use_fs and step is not None and step >= c['nis_loss_iter_specular']
+        logq_d = logq_s = None
+        def flow_input(ang):            # fields.py:1272-1273: the angles go through radians and back before the clamp
+            phi, theta = ang[..., :1] * (2 * np.pi), ang[..., 1:2] * (0.5 * np.pi)
+            return torch.cat([phi / (2 * np.pi), theta / (0.5 * np.pi)], -1).clamp(EPS, 1 - EPS)
+        if nis_d:
+            _, logq_d = self.flow_diffuse(pts, view_angles, roughness, flow_input(ang_d), return_jacobian=True)
+        if nis_s:
+            _, logq_s = self.flow_specular(pts, view_angles, roughness, flow_input(ang_s), return_jacobian=True)
+        est = mc_ops.McEstimateFunction.apply(normals, view_dirs, albedo, metallic, roughness, dirs, prob, lights, hit, Dd,
+                                              logq_d, ang_d if nis_d else None, logq_s, ang_s if nis_s else None)
         diffuse_colors, specular_colors = est[:, 0:3], est[:, 3:6]
         colors = linear_to_srgb(diffuse_colors + specular_colors)
         outputs = {
@@ -361,42 +402,9 @@ class MCShadingNetwork(nn.Module):
             'human_lights': torch.zeros(1, 3, device=dev),
         }
         zero = torch.zeros((), device=dev)
-        # ---- neural-importance-sampling losses (reference fields.py:1254-1333) ----
-        if use_fd and step is not None and step >= c['nis_loss_iter_diffuse']:
-            d1, L1, p1 = dirs[:, :nd], lights[:, :nd], prob[:, :nd, None].clamp_min(EPS)
-            fx = albedo.unsqueeze(1) * (1 - metallic.unsqueeze(1)) * (saturate_dot(d1, normals.unsqueeze(1)) / np.pi) * L1
-            H = F.normalize(view_dirs.unsqueeze(1) + d1, dim=-1)
-            HoV = torch.clamp(torch.sum(H * view_dirs.unsqueeze(1), dim=-1, keepdim=True), min=0.0, max=1.0)
-            phi, theta = ang_d[..., :1] * (2 * np.pi), ang_d[..., 1:2] * (0.5 * np.pi)
-            x = torch.cat([phi / (2 * np.pi), theta / (0.5 * np.pi)], -1).clamp(EPS, 1 - EPS)
-            _, logq_ = self.flow_diffuse(pts, view_angles, roughness, x, return_jacobian=True)
-            logq = logq_ - (4 * np.pi ** 2 * HoV * torch.sin(theta)).clamp_min(EPS).log()
-            outputs['loss_nis_diffuse'] = -(fx * logq / p1).mean()
-        else:
-            outputs['loss_nis_diffuse'] = zero
-        if use_fs and step is not None and step >= c['nis_loss_iter_specular']:
-            d2, L2, p2 = dirs[:, Dd:], lights[:, Dd:], prob[:, Dd:, None].clamp_min(EPS)
-            valid = (torch.sum(d2 * normals.unsqueeze(1), dim=-1, keepdim=True) > 0).to(torch.float32)
-            H = F.normalize(view_dirs.unsqueeze(1) + d2, dim=-1)
-            HoV = torch.clamp(torch.sum(H * view_dirs.unsqueeze(1), dim=-1, keepdim=True), min=0.0, max=1.0)
-            F0 = (0.04 * (1 - metallic) + metallic * albedo).unsqueeze(1)
-            fres = F0 + (1.0 - F0) * torch.clamp(1.0 - HoV, min=0.0, max=1.0) ** 5.0
-            NoV = saturate_dot(normals, view_dirs).unsqueeze(1)
-            NoL = saturate_dot(normals.unsqueeze(1), d2)
-            k = roughness.unsqueeze(1) / 2
-            geo = (NoV / (NoV * (1 - k) + k + 1e-5)) * (NoL / (NoL * (1 - k) + k + 1e-5))
-            NoH = saturate_dot(normals.unsqueeze(1), H)
-            a2 = roughness.unsqueeze(1) ** 2
-            dist = a2 / (np.pi * (NoH ** 2 * (a2 - 1.0) + 1.0) ** 2).clamp_min(EPS)
-            fxs = dist * fres * geo / (4 * NoV).clamp_min(EPS) * L2
-            phi, theta = ang_s[..., :1] * (2 * np.pi), ang_s[..., 1:2] * (0.5 * np.pi)
-            x = torch.cat([phi / (2 * np.pi), theta / (0.5 * np.pi)], -1).clamp(EPS, 1 - EPS)
-            _, logq_ = self.flow_specular(pts, view_angles, roughness, x, return_jacobian=True)
-            logq = logq_ - (4 * np.pi ** 2 * HoV * torch.sin(theta)).clamp_min(EPS).log()
-            # the reference compacts the N.L > 0 pairs and takes the mean over them (fields.py:1209-1214,1321)
-            outputs['loss_nis_specular'] = -((fxs * logq / p2) * valid).sum() / (valid.sum() * 3).clamp_min(1.0)
-        else:
-            outputs['loss_nis_specular'] = zero
+        outputs['loss_nis_diffuse'] = -est[:, 16].sum() / float(pn * nd * 3) if nis_d else zero
+        # the reference compacts the N.L > 0 pairs and takes the mean over them (fields.py:1209-1214,1321)
+        outputs['loss_nis_specular'] = -est[:, 17].sum() / (est[:, 18].sum().detach() * 3).clamp_min(1.0) if nis_s else zero
         outputs['loss_nis'] = outputs['loss_nis_diffuse'] + outputs['loss_nis_specular']
         return colors, outputs
 

@@ -64,6 +64,17 @@ def mc_directions(mode: int, normals, view_dirs, src, aux, roughness, n_dirs: in
               "tf_mc_directions")
 
 
+def hit_encode(inters, dirs, hit_normals, idx, ide_mat, ide_m, ldx: int = 128):
+    """[posenc(hit point, 8) | IDE(mirrored view direction)] rows of the occluded pairs `idx`, zero-padded to ldx columns
+    (the inner-light MLP input of reference fields.py:951-975) in one kernel; no autograd (hit records are geometry)."""
+    M = int(idx.shape[0])
+    X = torch.empty(M, ldx, device=inters.device, dtype=torch.float32)
+    with _timed("hit_encode"):
+        check(_lib.load().tf_hit_encode(ptr(_f32c(inters.reshape(-1, 3))), ptr(_f32c(dirs.reshape(-1, 3))), ptr(_f32c(hit_normals.reshape(-1, 3))),
+                                        ptr(idx.contiguous()), M, ptr(ide_mat), ptr(ide_m), ldx, ptr(X), stream_ptr()), "tf_hit_encode")
+    return X
+
+
 class CubeLightFunction(torch.autograd.Function):
     """EnvLight.direct_light: exp(cube bilinear(base, dirs)) on the masked pairs, 0 elsewhere."""
 
@@ -92,35 +103,47 @@ class CubeLightFunction(torch.autograd.Function):
 
 
 class McEstimateFunction(torch.autograd.Function):
-    """BRDF weights + diffuse / specular Monte-Carlo estimators per surface point.
-    returns out [pn,16]: diffuse(3) specular(3) mean diffuse light(3) mean specular light(3)
-    visibility(1) indirect(3)."""
+    """BRDF weights + diffuse / specular Monte-Carlo estimators per surface point, plus the per-point sums of the two
+    neural-importance-sampling losses (reference fields.py:1254-1333) when the flows' log q are given.
+    returns out [pn,19]: diffuse(3) specular(3) mean diffuse light(3) mean specular light(3) visibility(1) indirect(3)
+    nis_diffuse_sum(1) nis_specular_sum(1) nis_specular_count(1)."""
 
     @staticmethod
-    def forward(ctx, normals, view_dirs, albedo, metallic, roughness, dirs, prob, lights, hit, n_diffuse):
+    def forward(ctx, normals, view_dirs, albedo, metallic, roughness, dirs, prob, lights, hit, n_diffuse,
+                logq_d=None, ang_d=None, logq_s=None, ang_s=None):
         t = [_f32c(x) for x in (normals, view_dirs, albedo, metallic.reshape(-1), roughness.reshape(-1), dirs, prob, lights)]
         hitc = hit.to(torch.uint8).contiguous()
         pn, D = t[6].shape
-        out = torch.empty(pn, 16, device=t[0].device, dtype=torch.float32)
+        nis = [None if x is None else _f32c(x) for x in (logq_d, ang_d, logq_s, ang_s)]
+        nd = 0 if nis[0] is None else int(nis[0].numel() // max(pn, 1))
+        out = torch.empty(pn, 19, device=t[0].device, dtype=torch.float32)
         with _timed("mc_estimate_fwd"):
-            check(_lib.load().tf_mc_estimate_fwd(*(ptr(x) for x in t), ptr(hitc), pn, int(n_diffuse), int(D - n_diffuse), ptr(out),
-                                                 stream_ptr()), "tf_mc_estimate_fwd")
-        ctx.save_for_backward(*t, hitc)
-        ctx.n_diffuse = int(n_diffuse)
+            check(_lib.load().tf_mc_estimate_fwd(*(ptr(x) for x in t), ptr(hitc), pn, int(n_diffuse), int(D - n_diffuse), ptr(nis[0]),
+                                                 ptr(nis[1]), nd, ptr(nis[2]), ptr(nis[3]), ptr(out), stream_ptr()), "tf_mc_estimate_fwd")
+        ctx.save_for_backward(*t, hitc, *[x for x in nis if x is not None])
+        ctx.has_nis = [x is not None for x in nis]
+        ctx.n_diffuse, ctx.nd = int(n_diffuse), nd
         ctx.m_shape, ctx.r_shape = metallic.shape, roughness.shape
+        ctx.q_shapes = (None if logq_d is None else logq_d.shape, None if logq_s is None else logq_s.shape)
         return out
 
     @staticmethod
     def backward(ctx, g_out):
-        *t, hitc = ctx.saved_tensors
+        saved = list(ctx.saved_tensors)
+        t, hitc, rest = saved[:8], saved[8], saved[9:]
+        nis = [rest.pop(0) if h else None for h in ctx.has_nis]
         pn, D = t[6].shape
         dev = t[0].device
         d_alb = torch.empty(pn, 3, device=dev, dtype=torch.float32)
         d_met = torch.empty(pn, device=dev, dtype=torch.float32)
         d_rgh = torch.empty(pn, device=dev, dtype=torch.float32)
         d_lights = torch.empty(pn, D, 3, device=dev, dtype=torch.float32)
+        d_qd = None if nis[0] is None else torch.empty_like(nis[0])
+        d_qs = None if nis[2] is None else torch.empty_like(nis[2])
+        go = _f32c(g_out)
         with _timed("mc_estimate_bwd"):
-            check(_lib.load().tf_mc_estimate_bwd(*(ptr(x) for x in t), ptr(hitc), pn, ctx.n_diffuse, D - ctx.n_diffuse,
-                                                 ptr(_f32c(g_out)), ptr(d_alb), ptr(d_met), ptr(d_rgh), ptr(d_lights), stream_ptr()),
-                  "tf_mc_estimate_bwd")
-        return None, None, d_alb, d_met.reshape(ctx.m_shape), d_rgh.reshape(ctx.r_shape), None, None, d_lights, None, None
+            check(_lib.load().tf_mc_estimate_bwd(*(ptr(x) for x in t), ptr(hitc), pn, ctx.n_diffuse, D - ctx.n_diffuse, ptr(nis[0]),
+                                                 ptr(nis[1]), ctx.nd, ptr(nis[2]), ptr(nis[3]), ptr(go), ptr(d_alb), ptr(d_met), ptr(d_rgh),
+                                                 ptr(d_lights), ptr(d_qd), ptr(d_qs), stream_ptr()), "tf_mc_estimate_bwd")
+        return (None, None, d_alb, d_met.reshape(ctx.m_shape), d_rgh.reshape(ctx.r_shape), None, None, d_lights, None, None,
+                None if d_qd is None else d_qd.reshape(ctx.q_shapes[0]), None, None if d_qs is None else d_qs.reshape(ctx.q_shapes[1]), None)

@@ -200,8 +200,8 @@ def test_hierarchical_sampler_kernels_match_oracle(box, clip_var, perturb):
     assert torch.equal(offs.cpu().long(), torch.cat([torch.zeros(1, dtype=torch.long), torch.cumsum(cnt_k, 0)]))
     same = cnt_o == cnt_k                                     # a mid point within fp32 rounding of the box face may flip
     assert float(same.float().mean()) > 0.99, float(same.float().mean())
-    if box == 1.0:
-        assert int(cnt_k.min()) == 128                        # unit sphere inside the box: nothing culled
+    if box == 1.0:                                            # unit sphere inside the box: only the mid point of a ray's LAST interval
+        assert int(cnt_k.min()) >= 127                        # (which reaches past the sphere exit) can leave it
     ko = same[idx]
     kk = same[sidx.cpu()]
     assert float((s0.cpu().double()[kk] - t0[ko]).abs().max()) < 2e-5
