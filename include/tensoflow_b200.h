@@ -219,6 +219,26 @@ TF_API int tf_cube_light_fwd(const float* base, int32_t res, const float* dirs, 
                              int64_t n, float* out, tf_stream_t stream);
 TF_API int tf_cube_light_bwd(int32_t res, const float* dirs, const uint8_t* mask, int64_t n,
                              const float* out, const float* g_out, float* d_base, tf_stream_t stream);
+/* Fused coupling block of the TensoFlow sampler (reference network/flow.py:549-641): for each of the M = pn * sn (point,
+ * direction) pairs, conditioner MLP [Reshift(PE(y_c, 3 octaves)) (7) | Reshift(feat[p]) (feat_dim)] -> 64 -> 64 -> 64 -> 21
+ * with LeakyReLU(0.01) between the layers, then the piecewise-quadratic spline (10 bins) of the other coordinate y_t:
+ *   y_out[c] = y_in[c], y_out[t] = spline(y_in[t]) (inverse != 0: the inverse spline = sampling direction),
+ *   logj_out = logj_in + log|d y_out[t] / d y_in[t]|   (logj_in == NULL: 0)
+ * c = cond (0 / 1), t = 1 - c; feat[pn, feat_dim] holds one conditioning vector per point (sn >= 16 consecutive pairs share
+ * it; feat_dim <= 40); W1[64, 7 + feat_dim], W2/W3[64, 64], W4[21, 64] are the nn.Linear weights (row-major [out, in]);
+ * scale / offset are the Reshift constants (2, -1).  The [M, 64] activations stay on chip.
+ * bwd (forward spline only): g_y_out[M,2] / g_logj[M] (each may be NULL) -> g_y_in[M,2]; d_feat[pn, feat_dim] and the weight
+ * / bias gradients are ACCUMULATED (atomics; the caller zero-initialises).  The gradient of logj_in equals g_logj. */
+TF_API int tf_flow_block_fwd(const float* y_in, const float* logj_in, const float* feat, int32_t feat_dim, int32_t sn,
+                             const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,
+                             const float* b3, const float* W4, const float* b4, float scale, float offset, int32_t cond,
+                             int32_t inverse, int64_t M, float* y_out, float* logj_out, tf_stream_t stream);
+TF_API int tf_flow_block_bwd(const float* y_in, const float* feat, int32_t feat_dim, int32_t sn, const float* W1,
+                             const float* b1, const float* W2, const float* b2, const float* W3, const float* b3,
+                             const float* W4, const float* b4, float scale, float offset, int32_t cond, int64_t M,
+                             const float* g_y_out, const float* g_logj, float* g_y_in, float* d_feat, float* dW1,
+                             float* db1, float* dW2, float* db2, float* dW3, float* db3, float* dW4, float* db4,
+                             tf_stream_t stream);
 /* Input rows of the inner-light MLP for the occluded (point, direction) pairs (fields.py:951-975): for the pair idx[i]
  * (flat index into the [pn*D] arrays) X[i, 0:51] = positional encoding (8 octaves) of the hit point inters[idx[i]],
  * X[i, 51:123] = integrated directional encoding (utils/ref_utils.py:53-117, degree 5, kappa_inv = 0) of the view direction

@@ -116,6 +116,22 @@ class Block(nn.Module):
     def flow_inv(self, y, logj, feature, return_jacobian=True):      # density direction
         return self._couple(y, logj, feature, False)
 
+    # ---- fused path: one kernel per block (tf_flow_block_*), one conditioning vector per point ---------------------
+    def _reshift_consts(self):
+        r = self.nn[0]
+        key = (r.scale._version, r.offset._version, r.scale.data_ptr())
+        if getattr(self, '_reshift_key', None) != key:
+            self._reshift_key, self._reshift_val = key, (float(r.scale), float(r.offset))     # one host read per (re)load
+        return self._reshift_val
+
+    def couple_points(self, y, logj, feature_pp, sn, inverse):
+        """y [pn*sn,2], logj [pn*sn,1], feature_pp [pn,F] (shared by the sn directions of a point)"""
+        scale, offset = self._reshift_consts()
+        yo, lj = ops.FlowBlockFunction.apply(y, logj, feature_pp, sn, self.cond, inverse, scale, offset, self.nn[1].weight, self.nn[1].bias,
+                                             self.nn[3].weight, self.nn[3].bias, self.nn[5].weight, self.nn[5].bias, self.nn[7].weight,
+                                             self.nn[7].bias)
+        return yo, lj[:, None]
+
 
 class TensoFlow(nn.Module):
     def __init__(self, d, aabb, device='cuda', gridSize=[512, 512, 512], nis_n_comp=12, nis_dim=64, nis_feature_dim=16,
@@ -170,15 +186,24 @@ class TensoFlow(nn.Module):
         rough = torch.zeros(pts.shape[0], self.roughness_input_ch, device=pts.device)   # zeroed in the reference (flow.py:814,847)
         return torch.cat([feature, refl, rough], -1)
 
+    @staticmethod
+    def _fused_ok(feature, sn):
+        """the fused block kernels take one conditioning vector per point shared by >= 16 consecutive directions"""
+        return feature.is_cuda and sn >= 16 and feature.shape[1] <= 40
+
     def sample(self, pts, reflections, roughness, n_samples, return_jacobian=False, phi_shift=None):
         """reference flow.py:833-855 -> angles [pn,sn,2] (, logj [pn,sn,1] = -log q)"""
         pn = pts.shape[0]
         x, logj = self.latent_prior((pn, n_samples), pts.device, phi_shift)
         feature = self._condition(pts, reflections, roughness)
-        feature = feature[:, None, :].expand(-1, n_samples, -1).reshape(pn * n_samples, -1)
         x, logj = x.reshape(-1, 2), logj.reshape(-1, 1)
-        for f in self.flows:
-            x, logj = f.flow(x, logj, feature)
+        if self._fused_ok(feature, n_samples):
+            for f in self.flows:
+                x, logj = f.couple_points(x, logj, feature, n_samples, True)
+        else:
+            feature = feature[:, None, :].expand(-1, n_samples, -1).reshape(pn * n_samples, -1)
+            for f in self.flows:
+                x, logj = f.flow(x, logj, feature)
         x, logj = x.reshape(pn, n_samples, 2), logj.reshape(pn, n_samples, 1)
         return (x, logj) if return_jacobian else x
 
@@ -189,13 +214,20 @@ class TensoFlow(nn.Module):
         if rays_id is not None:
             feature = feature[rays_id]
         pre = x.shape[:-1]
-        if x.dim() == 3:
-            feature = feature[:, None, :].expand(-1, x.shape[1], -1)
-        x = x.reshape(-1, 2)
-        feature = feature.reshape(-1, feature.shape[-1])
-        logj = torch.zeros(x.shape[0], 1, device=x.device)
-        for f in list(self.flows)[::-1]:
-            x, logj = f.flow_inv(x, logj, feature)
+        if x.dim() == 3 and rays_id is None and self._fused_ok(feature, x.shape[1]) and feature.shape[0] == x.shape[0]:
+            sn = x.shape[1]
+            x = x.reshape(-1, 2)
+            logj = None
+            for f in list(self.flows)[::-1]:
+                x, logj = f.couple_points(x, logj, feature, sn, False)
+        else:
+            if x.dim() == 3:
+                feature = feature[:, None, :].expand(-1, x.shape[1], -1)
+            x = x.reshape(-1, 2)
+            feature = feature.reshape(-1, feature.shape[-1])
+            logj = torch.zeros(x.shape[0], 1, device=x.device)
+            for f in list(self.flows)[::-1]:
+                x, logj = f.flow_inv(x, logj, feature)
         z = x.reshape(*pre, 2)
         if not return_jacobian:
             return z

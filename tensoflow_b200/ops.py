@@ -574,3 +574,45 @@ class PwquadFunction(torch.autograd.Function):
             check(lib.tf_pwquad_bwd(ptr(yc), ptr(stc), M, ptr(gx), ptr(gl), ptr(d_y), ptr(d_st), stream_ptr()),
                   "tf_pwquad_bwd")
         return d_y, d_st, None
+
+
+class FlowBlockFunction(torch.autograd.Function):
+    """One coupling block of the TensoFlow sampler (reference network/flow.py:549-641) as ONE kernel per direction of
+    differentiation: conditioner MLP + spline for every (point, direction) pair, the per-point feature part of the first
+    layer evaluated once per point.  y [M,2], logj [M] or None, feat [pn,F] (M = pn * sn), the eight nn.Linear tensors of the
+    conditioner, Reshift constants.  inverse=True is the sampling direction (no backward)."""
+
+    @staticmethod
+    def forward(ctx, y, logj, feat, sn, cond, inverse, scale, offset, W1, b1, W2, b2, W3, b3, W4, b4):
+        lib = _lib.load()
+        yc, fc = _f32c(y.reshape(-1, 2)), _f32c(feat)
+        lc = None if logj is None else _f32c(logj.reshape(-1))
+        ws = [_f32c(w) for w in (W1, b1, W2, b2, W3, b3, W4, b4)]
+        M = yc.shape[0]
+        y_out = torch.empty_like(yc)
+        lj_out = torch.empty(M, device=yc.device, dtype=torch.float32)
+        with _timed("flow_block_fwd"):
+            check(lib.tf_flow_block_fwd(ptr(yc), ptr(lc), ptr(fc), int(fc.shape[1]), int(sn), *(ptr(w) for w in ws), float(scale), float(offset),
+                                        int(cond), 1 if inverse else 0, M, ptr(y_out), ptr(lj_out), stream_ptr()), "tf_flow_block_fwd")
+        ctx.save_for_backward(yc, fc, *ws)
+        ctx.cfg = (int(sn), int(cond), bool(inverse), float(scale), float(offset), None if logj is None else logj.shape)
+        return y_out, lj_out
+
+    @staticmethod
+    def backward(ctx, g_y, g_lj):
+        sn, cond, inverse, scale, offset, logj_shape = ctx.cfg
+        if inverse:
+            raise RuntimeError("the inverse (sampling) coupling block has no backward: the reference samples from frozen flow copies")
+        lib = _lib.load()
+        yc, fc, *ws = ctx.saved_tensors
+        M = yc.shape[0]
+        gy = None if g_y is None else _f32c(g_y.reshape(-1, 2))
+        gl = None if g_lj is None else _f32c(g_lj.reshape(-1))
+        g_in = torch.empty_like(yc)
+        d_feat = torch.zeros_like(fc)
+        dws = [_grad_zeros(w) for w in ws]
+        with _timed("flow_block_bwd"):
+            check(lib.tf_flow_block_bwd(ptr(yc), ptr(fc), int(fc.shape[1]), sn, *(ptr(w) for w in ws), scale, offset, cond, M, ptr(gy), ptr(gl),
+                                        ptr(g_in), ptr(d_feat), *(ptr(d) for d in dws), stream_ptr()), "tf_flow_block_bwd")
+        g_logj_in = None if (logj_shape is None or gl is None) else gl.reshape(logj_shape)
+        return (g_in, g_logj_in, d_feat, None, None, None, None, None, *dws)

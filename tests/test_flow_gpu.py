@@ -145,6 +145,13 @@ def test_tensoflow_sample():
         a, l = cu.sample(pts.to(dev), va.to(dev), rough.to(dev), sn, return_jacobian=True, phi_shift=shift.to(dev))
         close_as_fp32(a, a64, a32, 1e-4, "sampled angles")
         close_as_fp32(l, l64, l32, 1e-4, "sample logj")
+        for sn2 in (80, 8):               # 200 x 80: points straddle the 128-pair tiles of the fused kernel; 8 < 16: per-layer path
+            sh2 = torch.rand(pn, sn2, 1, generator=g)
+            b64, m64 = o64.sample(pts.double(), va.double(), rough.double(), sn2, sh2.double())
+            b32, m32 = o32.sample(pts, va, rough, sn2, sh2)
+            b, m = cu.sample(pts.to(dev), va.to(dev), rough.to(dev), sn2, return_jacobian=True, phi_shift=sh2.to(dev))
+            close_as_fp32(b, b64, b32, 1e-4, f"sampled angles ({sn2})")
+            close_as_fp32(m, m64, m32, 1e-4, f"sample logj ({sn2})")
         cu.eval()
         a_eval = cu.sample(pts.to(dev), va.to(dev), rough.to(dev), 32)
         e64, _ = o64.sample(pts.double(), va.double(), rough.double(), 32, None)
@@ -152,11 +159,13 @@ def test_tensoflow_sample():
         close_as_fp32(a_eval, e64, e32, 1e-4, "sampled angles (eval, 32)")
 
 
-@pytest.mark.parametrize("ragged", [False, True])
-def test_tensoflow_logq_forward_backward(ragged):
+@pytest.mark.parametrize("ragged,pn,sn", [(False, 150, 64), (True, 150, 64), (False, 37, 48), (False, 5, 16), (False, 9, 8)])
+def test_tensoflow_logq_forward_backward(ragged, pn, sn):
+    """dense [pn, sn] direction sets run on the fused coupling-block kernels (tf_flow_block_*: sn >= 16; 37 x 48 = 13.9 tiles of 128
+    pairs with points straddling tile boundaries, 5 x 16 = less than one tile), ragged sets (rays_id) and sn < 16 on the
+    per-layer kernels"""
     dev = _cuda()
     o32, o64, cu = _make_flows(seed=1)
-    pn, sn = 150, 64
     g = torch.Generator().manual_seed(9)
     pts, va, rough = torch.rand(pn, 3, generator=g) * 1.9 - 0.95, torch.rand(pn, 2, generator=g), torch.rand(pn, 1, generator=g)
     if ragged:
