@@ -355,6 +355,40 @@ TF_API int tf_probe_weights(const float* origins, const float* dirs, const float
 TF_API int tf_alpha_mask_sample(const float* volume, int32_t D, int32_t H, int32_t W, const float aabb_min[3],
                                 const float inv_half_size[3], const float* xyz, int64_t n, float* out, tf_stream_t stream);
 
+/* ---- per-sample shape shader ------------------------------------------------------------------------
+ * The per-sample arithmetic of ShapeShadingNetwork.forward (reference network/fields.py:448-567) around its MLP heads and
+ * environment-light lookups.  ide_mat [17,36] fp32, ide_m [36] int32, ide_sigma [36] fp32 (= l (l + 1) / 2) are device copies of
+ * the degree-5 integrated-directional-encoding tables (utils/ref_utils.py:53-117).
+ *   tf_shader_encode_fwd: n = normalize(normals) (degenerate n.x + n.y == 0 -> (0, 1e-6, 1)), v = normalize(view_dirs),
+ *       nov = n.v, refl = 2 (n.v) n - v, rough = 0.9 mat[:,3] + 0.09 (mat [n,5] = sigmoid outputs of the material head), and the
+ *       zero-padded MLP inputs  X_rad[n, ld_rad] = [feat (feat_dim) | points | PE(v, 4 octaves) | n]  (X_rad == NULL: skipped),
+ *       X_il[n, 128] = [PE(points, 8) | IDE(refl, rough)],  X_iw[n, 96] = [PE(points, 8) | PE(refl, 6)].
+ *   tf_shader_encode_bwd: upstream gradients of nrm, refl, nov, rough, X_rad, X_il (each may be NULL; X_iw carries none, the
+ *       reference detaches it) -> d_normals[n,3], d_mat3[n] (gradient of mat[:,3]), d_feat[n, feat_dim] (NULL: skipped).
+ *   tf_shader_combine_fwd: albedo = 0.77 mat[:,0:3] + 0.03, metallic = mat[:,4], occ_prob = 0.5 w_raw + 0.5,
+ *       specular light = indirect * occ + direct * (1 - occ) (occ = clamp(occ_prob, 0, 1)), split-sum terms from the bilinear
+ *       clamp lookup of lut[lut_h, lut_w, 2] at (clamp(nov), clamp(rough)), color = clamp(linear_to_srgb(diffuse + specular), 0, 1).
+ *   tf_shader_combine_bwd: g_color[n,3], g_occ[n] (may be NULL) -> d_mat[n,5], d_diffuse, d_direct, d_indirect [n,3],
+ *       d_w_raw[n], d_nov[n]. */
+TF_API int tf_shader_encode_fwd(const float* points, const float* normals, const float* view_dirs, const float* mat,
+                                const float* feat, int32_t feat_dim, int32_t ld_rad, int64_t n, const float* ide_mat,
+                                const int32_t* ide_m, const float* ide_sigma, float* nrm, float* vdir, float* refl,
+                                float* nov, float* rough, float* X_rad, float* X_il, float* X_iw, tf_stream_t stream);
+TF_API int tf_shader_encode_bwd(const float* normals, const float* view_dirs, const float* mat, int32_t feat_dim,
+                                int32_t ld_rad, int64_t n, const float* ide_mat, const int32_t* ide_m,
+                                const float* ide_sigma, const float* g_nrm, const float* g_refl, const float* g_nov,
+                                const float* g_rough, const float* g_X_rad, const float* g_X_il, float* d_normals,
+                                float* d_mat3, float* d_feat, tf_stream_t stream);
+TF_API int tf_shader_combine_fwd(const float* mat, const float* diffuse_light, const float* direct_light,
+                                 const float* indirect_light, const float* w_raw, const float* nov, const float* lut,
+                                 int32_t lut_h, int32_t lut_w, int64_t n, float* color, float* occ_prob,
+                                 tf_stream_t stream);
+TF_API int tf_shader_combine_bwd(const float* mat, const float* diffuse_light, const float* direct_light,
+                                 const float* indirect_light, const float* w_raw, const float* nov, const float* lut,
+                                 int32_t lut_h, int32_t lut_w, int64_t n, const float* g_color, const float* g_occ,
+                                 float* d_mat, float* d_diffuse, float* d_direct, float* d_indirect, float* d_w_raw,
+                                 float* d_nov, tf_stream_t stream);
+
 /* ---- differentiable cubemap lookup ---------------------------------------------------------------
  * dr.texture(tex, dirs, [mip=stack, mip_level_bias=level,] filter_mode='linear[-mipmap-linear]', boundary_mode='cube') of the
  * shape-stage light (reference network/light.py:95-122, 135; network/light_utils.py:46-63): seamless bilinear footprint per

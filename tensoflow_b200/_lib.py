@@ -84,6 +84,10 @@ _OPTIONAL_SIGNATURES = {
                                     C.c_int64, _P, _P, _P]),
     "tf_flow_block_bwd": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, C.c_float, C.c_float, C.c_int32, C.c_int64,
                                     _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "tf_shader_encode_fwd": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "tf_shader_encode_bwd": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "tf_shader_combine_fwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int64, _P, _P, _P]),
+    "tf_shader_combine_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "tf_hit_encode": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P, _P, C.c_int32, _P, _P]),
     "tf_csr_spmm3_fwd": (C.c_int, [_P, _P, _P, _P, C.c_int32, _P, _P]),
     "tf_csr_spmm3_bwd": (C.c_int, [_P, _P, _P, _P, C.c_int32, _P, _P]),

@@ -22,7 +22,7 @@ import torch.nn.functional as F
 from . import _lib, ops
 from ._lib import check, ptr, stream_ptr
 from .flow import posenc
-from .material import make_predictor, run_predictor, linear_to_srgb, _ide_tables
+from .material import make_predictor, run_predictor, run_predictor_padded, linear_to_srgb, _ide_tables
 
 
 # ---- cube geometry (reference network/light_utils.py:24-31, renderutils/c_src/cubemap.cu:32-60) ----
@@ -352,6 +352,115 @@ class ShadingEnvLight(nn.Module):
         return torch.exp(cube_lookup(self.specular, l, self.get_mip(roughness)[..., 0]))
 
 
+_IDE_ROUGH_DEV = {}
+
+
+def _ide_rough_tables(device):
+    """device copies of the degree-5 IDE tables for tf_shader_encode_*: mat [17,36] fp32, m [36] int32, sigma = l (l + 1) / 2 [36]"""
+    key = str(device)
+    if key not in _IDE_ROUGH_DEV:
+        ml, mat = _ide_tables(5)
+        _IDE_ROUGH_DEV[key] = (torch.from_numpy(np.ascontiguousarray(mat, dtype=np.float32)).to(device).contiguous(),
+                               torch.from_numpy(ml[0].astype(np.int32)).to(device).contiguous(),
+                               torch.from_numpy((0.5 * ml[1] * (ml[1] + 1)).astype(np.float32)).to(device).contiguous())
+    return _IDE_ROUGH_DEV[key]
+
+
+def _c32(t):
+    t = t.detach()
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+class ShaderEncodeFunction(torch.autograd.Function):
+    """Normalised normal / view, mirror direction, N.V, roughness and the zero-padded inputs of the radiance, indirect-light
+    and occlusion heads (reference fields.py:453-501) in one kernel; backward in one kernel (IDE / mirror / normalisation
+    adjoints).  (points, normals, view_dirs, mat [N,5], feat [N,fd] or None) ->
+    (nrm [N,3], vdir [N,3], refl [N,3], nov [N], rough [N], X_rad [N,ld] or None, X_il [N,128], X_iw [N,96])"""
+
+    @staticmethod
+    def forward(ctx, points, normals, view_dirs, mat, feat):
+        lib = _lib.load()
+        pc, nc, vc, mc = _c32(points), _c32(normals), _c32(view_dirs), _c32(mat)
+        fc = None if feat is None else _c32(feat)
+        n, dev = pc.shape[0], pc.device
+        fd = 0 if fc is None else int(fc.shape[1])
+        ld_rad = 0 if fc is None else (fd + 33 + 15) // 16 * 16
+        ide = _ide_rough_tables(dev)
+        f32 = dict(device=dev, dtype=torch.float32)
+        nrm, vdir, refl = torch.empty(n, 3, **f32), torch.empty(n, 3, **f32), torch.empty(n, 3, **f32)
+        nov, rough = torch.empty(n, **f32), torch.empty(n, **f32)
+        X_rad = None if fc is None else torch.empty(n, ld_rad, **f32)
+        X_il, X_iw = torch.empty(n, 128, **f32), torch.empty(n, 96, **f32)
+        with ops._timed("shader_encode_fwd"):
+            check(lib.tf_shader_encode_fwd(ptr(pc), ptr(nc), ptr(vc), ptr(mc), ptr(fc), fd, ld_rad, n, ptr(ide[0]), ptr(ide[1]), ptr(ide[2]),
+                                           ptr(nrm), ptr(vdir), ptr(refl), ptr(nov), ptr(rough), ptr(X_rad), ptr(X_il), ptr(X_iw), stream_ptr()),
+                  "tf_shader_encode_fwd")
+        ctx.save_for_backward(nc, vc, mc)
+        ctx.dims = (fd, ld_rad, feat is not None)
+        ctx.mark_non_differentiable(vdir, X_iw)
+        ctx.set_materialize_grads(False)
+        return nrm, vdir, refl, nov, rough, X_rad, X_il, X_iw
+
+    @staticmethod
+    def backward(ctx, g_nrm, _g_vdir, g_refl, g_nov, g_rough, g_Xrad, g_Xil, _g_Xiw):
+        lib = _lib.load()
+        nc, vc, mc = ctx.saved_tensors
+        fd, ld_rad, has_feat = ctx.dims
+        n, dev = nc.shape[0], nc.device
+        ide = _ide_rough_tables(dev)
+        gs = [None if g is None else _c32(g) for g in (g_nrm, g_refl, g_nov, g_rough, g_Xrad, g_Xil)]
+        d_normals = torch.empty(n, 3, device=dev, dtype=torch.float32)
+        d_mat = torch.zeros(n, 5, device=dev, dtype=torch.float32)
+        d_mat3 = torch.empty(n, device=dev, dtype=torch.float32)
+        d_feat = None
+        if has_feat:
+            d_feat = torch.empty(n, fd, device=dev, dtype=torch.float32) if gs[4] is not None else torch.zeros(n, fd, device=dev, dtype=torch.float32)
+        with ops._timed("shader_encode_bwd"):
+            check(lib.tf_shader_encode_bwd(ptr(nc), ptr(vc), ptr(mc), fd, ld_rad, n, ptr(ide[0]), ptr(ide[1]), ptr(ide[2]), *(ptr(g) for g in gs),
+                                           ptr(d_normals), ptr(d_mat3), ptr(d_feat) if gs[4] is not None else None, stream_ptr()),
+                  "tf_shader_encode_bwd")
+        d_mat[:, 3] = d_mat3
+        return None, d_normals, None, d_mat, d_feat
+
+
+class ShaderCombineFunction(torch.autograd.Function):
+    """Material affine maps + split-sum FG LUT + diffuse / specular combination with the occlusion blend + linear->sRGB + clamp
+    (reference fields.py:463-531) in one kernel each way.
+    (mat [N,5], diffuse_light, direct_light, indirect_light [N,3], w_raw [N], nov [N], lut [H,W,2]) -> color [N,3], occ_prob [N]"""
+
+    @staticmethod
+    def forward(ctx, mat, diffuse_light, direct_light, indirect_light, w_raw, nov, lut):
+        lib = _lib.load()
+        t = [_c32(x) for x in (mat, diffuse_light, direct_light, indirect_light, w_raw.reshape(-1), nov.reshape(-1), lut)]
+        n, dev = t[0].shape[0], t[0].device
+        color = torch.empty(n, 3, device=dev, dtype=torch.float32)
+        occ = torch.empty(n, device=dev, dtype=torch.float32)
+        with ops._timed("shader_combine_fwd"):
+            check(lib.tf_shader_combine_fwd(*(ptr(x) for x in t), int(t[6].shape[0]), int(t[6].shape[1]), n, ptr(color), ptr(occ), stream_ptr()),
+                  "tf_shader_combine_fwd")
+        ctx.save_for_backward(*t)
+        ctx.shapes = (w_raw.shape, nov.shape)
+        ctx.set_materialize_grads(False)
+        return color, occ
+
+    @staticmethod
+    def backward(ctx, g_color, g_occ):
+        lib = _lib.load()
+        t = list(ctx.saved_tensors)
+        n, dev = t[0].shape[0], t[0].device
+        gc = _c32(g_color) if g_color is not None else torch.zeros(n, 3, device=dev, dtype=torch.float32)
+        go = None if g_occ is None else _c32(g_occ.reshape(-1))
+        f32 = dict(device=dev, dtype=torch.float32)
+        d_mat, d_dif, d_dir, d_ind = torch.empty(n, 5, **f32), torch.empty(n, 3, **f32), torch.empty(n, 3, **f32), torch.empty(n, 3, **f32)
+        d_w, d_nov = torch.empty(n, **f32), torch.empty(n, **f32)
+        with ops._timed("shader_combine_bwd"):
+            check(lib.tf_shader_combine_bwd(*(ptr(x) for x in t), int(t[6].shape[0]), int(t[6].shape[1]), n, ptr(gc), ptr(go), ptr(d_mat), ptr(d_dif),
+                                            ptr(d_dir), ptr(d_ind), ptr(d_w), ptr(d_nov), stream_ptr()), "tf_shader_combine_bwd")
+        return d_mat, d_dif, d_dir, d_ind, d_w.reshape(ctx.shapes[0]), d_nov.reshape(ctx.shapes[1]), None
+
+
 def load_fg_lut(device):
     p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets", "fg_lut_256.npz")
     return torch.from_numpy(np.load(p)["fg"]).to(device)
@@ -400,34 +509,33 @@ class ShapeShadingNetwork(nn.Module):
         if points.shape[0] == 0:
             occ_info = {'reflective': torch.zeros(0, 1, device=dev), 'occ_prob': torch.zeros(0, 1, device=dev), 'roughness': torch.zeros(0, 1, device=dev)}
             return torch.zeros(0, 3, device=dev), (torch.zeros(0, 3, device=dev) if with_rad else None), occ_info
-        normals = F.normalize(normals, dim=-1)
-        bad = normals[:, :2].sum(dim=-1) == 0.
-        normals = torch.where(bad[:, None], torch.tensor([0.0, 1e-6, 1.0], device=dev), normals)
-        view_dirs = F.normalize(view_dirs, dim=-1)
-        reflective = torch.sum(view_dirs * normals, -1, keepdim=True) * normals * 2 - view_dirs
-        NoV = torch.sum(normals * view_dirs, -1, keepdim=True)
+        # material head, then the per-sample kernels: encode (normalisation, mirror direction, N.V, roughness, the padded inputs of
+        # the three remaining heads) -> heads + environment lookups -> combine (FG LUT, occlusion blend, sRGB)
+        fd = feature_vectors.shape[1]
         mat = run_predictor(self.mat_mlp, feature_vectors, "sigmoid")
-        albedo, roughness, metallic = mat[..., :3] * 0.77 + 0.03, mat[..., 3:4] * 0.9 + 0.09, mat[..., 4:]
-        radiance = None
-        if with_rad:
-            radiance = run_predictor(self.rad_mlp, torch.cat([feature_vectors, points, posenc(view_dirs, 4), normals], -1), "sigmoid")
-        diffuse_albedo = (1 - metallic) * albedo
+        normals, view_dirs, reflective, nov, rough, X_rad, X_il, X_iw = ShaderEncodeFunction.apply(
+            points, normals, view_dirs, mat, feature_vectors if with_rad else None)
+        roughness = rough[:, None]
+        radiance = run_predictor_padded(self.rad_mlp, X_rad, fd + 33, "sigmoid") if with_rad else None
         diffuse_light = self.envlight(normals)
-        diffuse_color = diffuse_albedo * diffuse_light
-        specular_albedo = 0.04 * (1 - metallic) + metallic * albedo
-        ref_roughness = ide_encode_rough(reflective, roughness)
         direct_light = self.envlight(reflective, roughness)
-        pts = posenc(points, 8)
-        indirect_light = run_predictor(self.inner_light, torch.cat([pts, ref_roughness], -1), "exp", c['light_exp_max'])
-        occ_prob = run_predictor(self.inner_weight, torch.cat([pts.detach(), posenc(reflective, 6).detach()], -1), "none") * 0.5 + 0.5
-        occ_ = torch.clamp(occ_prob, min=0, max=1)
-        specular_light = indirect_light * occ_ + direct_light * (1 - occ_)
-        indirect = indirect_light * occ_
-        fg_uv = torch.cat([torch.clamp(NoV, min=0.0, max=1.0), torch.clamp(roughness, min=0.0, max=1.0)], -1)
-        fg = texture2d_linear_clamp(self.FG_LUT[0], fg_uv)
-        specular_ref = specular_albedo * fg[:, 0:1] + fg[:, 1:2]
-        specular_color = specular_ref * specular_light
-        color = torch.clamp(linear_to_srgb(diffuse_color + specular_color), min=0.0, max=1.0)
+        indirect_light = run_predictor_padded(self.inner_light, X_il, 123, "exp", c['light_exp_max'])
+        w_raw = run_predictor_padded(self.inner_weight, X_iw, 90, "none")
+        color, occ = ShaderCombineFunction.apply(mat, diffuse_light, direct_light, indirect_light, w_raw, nov, self.FG_LUT[0])
+        occ_prob = occ[:, None]
+        if inter_results:                                        # visualisation outputs of the inference path: plain tensor arithmetic
+            albedo, metallic = mat[..., :3] * 0.77 + 0.03, mat[..., 4:]
+            NoV = nov[:, None]
+            diffuse_albedo = (1 - metallic) * albedo
+            diffuse_color = diffuse_albedo * diffuse_light
+            specular_albedo = 0.04 * (1 - metallic) + metallic * albedo
+            occ_ = torch.clamp(occ_prob, min=0, max=1)
+            specular_light = indirect_light * occ_ + direct_light * (1 - occ_)
+            indirect = indirect_light * occ_
+            fg_uv = torch.cat([torch.clamp(NoV, min=0.0, max=1.0), torch.clamp(roughness, min=0.0, max=1.0)], -1)
+            fg = texture2d_linear_clamp(self.FG_LUT[0], fg_uv)
+            specular_ref = specular_albedo * fg[:, 0:1] + fg[:, 1:2]
+            specular_color = specular_ref * specular_light
         occ_info = {'reflective': reflective, 'occ_prob': occ_prob, 'roughness': roughness}
         if inter_results:
             inter = {
