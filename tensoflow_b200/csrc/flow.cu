@@ -1,188 +1,13 @@
 // Piecewise-quadratic coupling transform of the TensoFlow sampler, one thread per
 // (surface point, direction) pair.  Restates ElementWisePWQuadraticTransform
 // (reference network/flow.py:314-525) for K = 10 bins: st = 11 vertex heights + 10 widths.
-#include <float.h>
+#include <stdlib.h>
 #include "common.cuh"
+#include "flow_spline.cuh"
 
 namespace {
 
-constexpr int NB = 10;       // bins
-constexpr int NV = NB + 1;   // vertices
-constexpr int NST = NB + NV; // conditioner outputs per coordinate (21)
-
-// torch.lerp(a, b, w)
-__device__ __forceinline__ float lerp_t(float a, float b, float w) { return w < 0.5f ? a + w * (b - a) : b - (b - a) * (1.f - w); }
-
-struct Spline {
-    float e[NB], w[NB], ws[NB], u[NV], v[NV], wr[NB], vr[NV];
-    float S, Z;
-};
-
-// clamp_w = true for the forward spline (flow.py:343-346), false for the inverse (flow.py:427-431)
-template <bool CLAMP_W>
-__device__ __forceinline__ void spline_params(const float* __restrict__ st, Spline& s) {
-    float cum = 0.f;
-    float c[NB];
-#pragma unroll
-    for (int i = 0; i < NB; ++i) {
-        float ei = expf(st[NV + i]);
-        if (CLAMP_W) ei = fmaxf(ei, 1e-6f);
-        s.e[i] = ei;
-        cum += ei;
-        c[i] = cum;
-    }
-    s.S = cum;
-#pragma unroll
-    for (int i = 0; i < NB; ++i) {
-        s.wr[i] = s.e[i] / s.S;
-        s.w[i] = CLAMP_W ? fmaxf(s.wr[i], 1e-6f) : s.wr[i];
-        s.ws[i] = c[i] / s.S;
-    }
-#pragma unroll
-    for (int j = 0; j < NV; ++j) s.u[j] = expf(st[j]);
-    float Z = 0.f;
-#pragma unroll
-    for (int i = 0; i < NB; ++i) Z += (s.u[i] + s.u[i + 1]) * 0.5f * s.w[i];
-    s.Z = Z;
-#pragma unroll
-    for (int j = 0; j < NV; ++j) {
-        s.vr[j] = s.u[j] / Z;
-        s.v[j] = fmaxf(s.vr[j], 1e-6f);
-    }
-}
-
-// forward spline of one element (flow.py:343-412): x, log|dx/dy|
-__device__ __forceinline__ void pwquad_eval_forward(const float* sr, float yy, float& x, float& lj) {
-    const float eps = FLT_EPSILON;
-    Spline s;
-    spline_params<true>(sr, s);
-    int m = 0;
-#pragma unroll
-    for (int i = 0; i < NB; ++i) m += (s.ws[i] <= yy) ? 1 : 0;   // number of cumulated widths <= x (flow.py:355-370)
-    m = min(m, NB - 1);
-    float wm = 0.f, vm = 0.f, vm1 = 0.f, wsh = 0.f, vw = 0.f;
-#pragma unroll
-    for (int i = 0; i < NB; ++i) {
-        if (i == m) { wm = s.w[i]; vm = s.v[i]; vm1 = s.v[i + 1]; wsh = i == 0 ? 0.f : s.ws[i > 0 ? i - 1 : 0]; }
-        if (i < m) vw += (s.v[i] + s.v[i + 1]) * 0.5f * s.w[i];
-    }
-    const float a = fminf(fmaxf((yy - wsh) / wm, 0.f), 1.f);
-    float out = a * a * 0.5f * ((vm1 - vm) * wm) + a * vm * wm + vw;
-    x = fminf(fmaxf(out, eps), 1.f - eps);
-    lj = logf(lerp_t(vm, vm1, a));
-}
-
-// inverse spline (the sampling direction, flow.py:415-525)
-__device__ __forceinline__ void pwquad_eval_inverse(const float* sr, float yy, float& x, float& lj) {
-    const float eps = FLT_EPSILON;
-    Spline s;
-    spline_params<false>(sr, s);
-    float vwc[NV];
-    vwc[0] = 0.f;
-#pragma unroll
-    for (int i = 0; i < NB; ++i) vwc[i + 1] = vwc[i] + (s.v[i] + s.v[i + 1]) * 0.5f * s.w[i];
-    int cnt = 0;
-#pragma unroll
-    for (int j = 0; j < NV; ++j) cnt += (vwc[j] <= yy) ? 1 : 0;  // last vertex whose cumulated area <= y (flow.py:443-457)
-    int e = min(max(cnt - 1, 0), NB - 1);
-    float we = 0.f, ve = 0.f, ve1 = 0.f, wsh = 0.f, vwe = 0.f;
-#pragma unroll
-    for (int i = 0; i < NB; ++i)
-        if (i == e) { we = s.w[i]; ve = s.v[i]; ve1 = s.v[i + 1]; wsh = i == 0 ? 0.f : s.ws[i > 0 ? i - 1 : 0]; vwe = vwc[i]; }
-    float a = (ve1 - ve) * we;
-    const float b = ve * we;
-    const float c = vwe - yy;
-    if (fabsf(a) < eps) a = eps;
-    const float d = fmaxf(b * b - 2.f * a * c, 0.f);
-    const float sq = sqrtf(d);
-    const float sol1 = (-b - sq) / a, sol2 = (-b + sq) / a;
-    float sol = (sol1 >= 0.f && sol1 < 1.f) ? sol1 : sol2;
-    sol = fminf(fmaxf(sol, eps), 1.f - eps);
-    x = fminf(fmaxf(we * sol + wsh, eps), 1.f - eps);
-    lj = -logf(lerp_t(ve, ve1, sol));
-}
-
-// adjoint of the forward spline: upstream (g_x, g_logj) -> d_y and d_st[21]  (derivation: DESIGN.md, "pwquad adjoint")
-__device__ __forceinline__ void pwquad_adjoint(const float* sr, float yy, float gx, float gl, float& d_y, float* d_st) {
-    const float eps = FLT_EPSILON;
-    Spline s;
-    spline_params<true>(sr, s);
-    int m = 0;
-#pragma unroll
-    for (int i = 0; i < NB; ++i) m += (s.ws[i] <= yy) ? 1 : 0;
-    m = min(m, NB - 1);
-    float wm = 0.f, vm = 0.f, vm1 = 0.f, wsh = 0.f, vw = 0.f, cum_m1 = 0.f;
-    {
-        float cum = 0.f;
-#pragma unroll
-        for (int i = 0; i < NB; ++i) {
-            if (i == m) { wm = s.w[i]; vm = s.v[i]; vm1 = s.v[i + 1]; wsh = i == 0 ? 0.f : s.ws[i > 0 ? i - 1 : 0]; cum_m1 = cum; }
-            if (i < m) vw += (s.v[i] + s.v[i + 1]) * 0.5f * s.w[i];
-            cum += s.e[i];
-        }
-    }
-    const float a_raw = (yy - wsh) / wm;
-    const float a = fminf(fmaxf(a_raw, 0.f), 1.f);
-    const float dv = vm1 - vm;
-    const float L = lerp_t(vm, vm1, a);
-    const float out_raw = a * a * 0.5f * (dv * wm) + a * vm * wm + vw;
-    const float go = (out_raw >= eps && out_raw <= 1.f - eps) ? gx : 0.f;
-    // d/d alpha
-    float ga = go * wm * (vm + a * dv) + gl * dv / L;
-    if (!(a_raw >= 0.f && a_raw <= 1.f)) ga = 0.f;
-    float gv[NV], gw[NB];
-#pragma unroll
-    for (int j = 0; j < NV; ++j) gv[j] = 0.f;
-#pragma unroll
-    for (int i = 0; i < NB; ++i) gw[i] = 0.f;
-    const float gvm = go * (a * wm - a * a * 0.5f * wm) + gl * (1.f - a) / L;
-    const float gvm1 = go * (a * a * 0.5f * wm) + gl * a / L;
-    const float gwm = go * (a * a * 0.5f * dv + a * vm) - ga * a_raw / wm;
-    const float gwsh = -ga / wm;
-#pragma unroll
-    for (int i = 0; i < NB; ++i) {
-        if (i == m) { gv[i] += gvm; gv[i + 1] += gvm1; gw[i] += gwm; }
-        if (i < m) { gv[i] += go * 0.5f * s.w[i]; gv[i + 1] += go * 0.5f * s.w[i]; gw[i] += go * (s.v[i] + s.v[i + 1]) * 0.5f; }
-    }
-    d_y = ga / wm;
-    // v = max(u / Z, 1e-6)
-    float gu[NV];
-    float gZ = 0.f;
-#pragma unroll
-    for (int j = 0; j < NV; ++j) {
-        const float g = s.vr[j] >= 1e-6f ? gv[j] : 0.f;
-        gu[j] = g / s.Z;
-        gZ -= g * s.vr[j] / s.Z;
-    }
-#pragma unroll
-    for (int i = 0; i < NB; ++i) {
-        gu[i] += gZ * 0.5f * s.w[i];
-        gu[i + 1] += gZ * 0.5f * s.w[i];
-        gw[i] += gZ * (s.u[i] + s.u[i + 1]) * 0.5f;
-    }
-#pragma unroll
-    for (int j = 0; j < NV; ++j) d_st[j] = gu[j] * s.u[j];
-    // w = max(e / S, 1e-6), wshift_m = cum_{m-1} / S
-    float ge[NB];
-    float gS = 0.f;
-#pragma unroll
-    for (int i = 0; i < NB; ++i) {
-        const float g = s.wr[i] >= 1e-6f ? gw[i] : 0.f;
-        ge[i] = g / s.S;
-        gS -= g * s.wr[i] / s.S;
-    }
-    if (m > 0) {
-        gS -= gwsh * cum_m1 / (s.S * s.S);
-#pragma unroll
-        for (int i = 0; i < NB; ++i)
-            if (i < m) ge[i] += gwsh / s.S;
-    }
-#pragma unroll
-    for (int i = 0; i < NB; ++i) {
-        const float ex = expf(sr[NV + i]);
-        d_st[NV + i] = ex >= 1e-6f ? (ge[i] + gS) * ex : 0.f;
-    }
-}
+using namespace flowsp;
 
 __global__ void __launch_bounds__(128) pwquad_fwd_kernel(const float* __restrict__ y, const float* __restrict__ st, int64_t M,
                                                          int inverse, float* __restrict__ x, float* __restrict__ logj) {
@@ -609,6 +434,18 @@ extern "C" TF_API int tf_pwquad_bwd(const float* y, const float* st, int64_t M, 
     return 0;
 }
 
+// tensor-core forward (flow_tc.cu)
+int tf_internal_flow_block_fwd_tc(const float* y_in, const float* logj_in, const float* feat, int feat_dim, int sn, const float* W1,
+                                  const float* b1, const float* W2, const float* b2, const float* W3, const float* b3, const float* W4,
+                                  const float* b4, float scale, float offset, int cond, int inverse, int64_t M, float* y_out, float* logj_out,
+                                  float* save_h, float* save_st, cudaStream_t stream);
+// TF_FLOW_SIMT=1 selects the FP32-pipe kernel below instead of the tcgen05 one (A/B runs; read once per process)
+static bool flow_use_simt() {
+    static int forced = -1;
+    if (forced < 0) { const char* e = getenv("TF_FLOW_SIMT"); forced = (e && e[0] == '1') ? 1 : 0; }
+    return forced == 1;
+}
+
 extern "C" TF_API int tf_flow_block_fwd(const float* y_in, const float* logj_in, const float* feat, int32_t feat_dim, int32_t sn,
                                         const float* W1, const float* b1, const float* W2, const float* b2, const float* W3, const float* b3,
                                         const float* W4, const float* b4, float scale, float offset, int32_t cond, int32_t inverse, int64_t M,
@@ -617,6 +454,12 @@ extern "C" TF_API int tf_flow_block_fwd(const float* y_in, const float* logj_in,
     FlowW w = {W1, b1, W2, b2, W3, b3, W4, b4, feat_dim, scale, offset};
     if (int e = flow_check(w, sn, cond, M)) return e;
     TF_REQUIRE(y_in && feat && y_out && logj_out, "tf_flow_block_fwd: NULL pointer");
+    if (!flow_use_simt()) {
+        tf_internal_flow_block_fwd_tc(y_in, logj_in, feat, feat_dim, sn, W1, b1, W2, b2, W3, b3, W4, b4, scale, offset, cond, inverse, M, y_out,
+                                      logj_out, nullptr, nullptr, (cudaStream_t)stream);
+        TF_CHECK_LAUNCH("tf_flow_block_fwd (tcgen05)");
+        return 0;
+    }
     FlowFwdParams p = {w, y_in, logj_in, feat, sn, cond, M, y_out, logj_out};
     const size_t smem = flow_fwd_smem();
     const int64_t ntiles = (M + FTILE - 1) / FTILE;
