@@ -227,16 +227,23 @@ TF_API int tf_cube_light_bwd(int32_t res, const float* dirs, const uint8_t* mask
  * c = cond (0 / 1), t = 1 - c; feat[pn, feat_dim] holds one conditioning vector per point (sn >= 16 consecutive pairs share
  * it; feat_dim <= 40); W1[64, 7 + feat_dim], W2/W3[64, 64], W4[21, 64] are the nn.Linear weights (row-major [out, in]);
  * scale / offset are the Reshift constants (2, -1).  The [M, 64] activations stay on chip.
+ * save_h[M, 3, 64] / save_st[M, 24] (both or none; NULL = not kept): the tensor-core forward stores the three hidden activations
+ * and the spline parameters there, and tf_flow_block_bwd given them (saved_h / saved_st) runs its adjoint chain on the tensor
+ * cores without recomputing the forward; with NULL it recomputes on the FP32 pipe.  tf_flow_block_uses_tensor_cores() tells
+ * which forward kernel is active (TF_FLOW_SIMT=1 in the environment selects the FP32-pipe kernels for A/B runs).
  * bwd (forward spline only): g_y_out[M,2] / g_logj[M] (each may be NULL) -> g_y_in[M,2]; d_feat[pn, feat_dim] and the weight
  * / bias gradients are ACCUMULATED (atomics; the caller zero-initialises).  The gradient of logj_in equals g_logj. */
 TF_API int tf_flow_block_fwd(const float* y_in, const float* logj_in, const float* feat, int32_t feat_dim, int32_t sn,
                              const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,
                              const float* b3, const float* W4, const float* b4, float scale, float offset, int32_t cond,
-                             int32_t inverse, int64_t M, float* y_out, float* logj_out, tf_stream_t stream);
+                             int32_t inverse, int64_t M, float* y_out, float* logj_out, float* save_h, float* save_st,
+                             tf_stream_t stream);
+TF_API int tf_flow_block_uses_tensor_cores(void);
 TF_API int tf_flow_block_bwd(const float* y_in, const float* feat, int32_t feat_dim, int32_t sn, const float* W1,
                              const float* b1, const float* W2, const float* b2, const float* W3, const float* b3,
                              const float* W4, const float* b4, float scale, float offset, int32_t cond, int64_t M,
-                             const float* g_y_out, const float* g_logj, float* g_y_in, float* d_feat, float* dW1,
+                             const float* saved_h, const float* saved_st, const float* g_y_out, const float* g_logj,
+                             float* g_y_in, float* d_feat, float* dW1,
                              float* db1, float* dW2, float* db2, float* dW3, float* db3, float* dW4, float* db4,
                              tf_stream_t stream);
 /* Input rows of the inner-light MLP for the occluded (point, direction) pairs (fields.py:951-975): for the pair idx[i]

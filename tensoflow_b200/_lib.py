@@ -81,9 +81,10 @@ _OPTIONAL_SIGNATURES = {
     "tf_mc_estimate_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P, _P, C.c_int32, _P, _P,
                                      _P, _P, _P, _P, _P, _P, _P, _P]),
     "tf_flow_block_fwd": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, C.c_float, C.c_float, C.c_int32, C.c_int32,
-                                    C.c_int64, _P, _P, _P]),
+                                    C.c_int64, _P, _P, _P, _P, _P]),
+    "tf_flow_block_uses_tensor_cores": (C.c_int, []),
     "tf_flow_block_bwd": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, C.c_float, C.c_float, C.c_int32, C.c_int64,
-                                    _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+                                    _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "tf_shader_encode_fwd": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "tf_shader_encode_bwd": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "tf_shader_combine_fwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int64, _P, _P, _P]),

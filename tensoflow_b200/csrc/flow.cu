@@ -439,6 +439,10 @@ int tf_internal_flow_block_fwd_tc(const float* y_in, const float* logj_in, const
                                   const float* b1, const float* W2, const float* b2, const float* W3, const float* b3, const float* W4,
                                   const float* b4, float scale, float offset, int cond, int inverse, int64_t M, float* y_out, float* logj_out,
                                   float* save_h, float* save_st, cudaStream_t stream);
+int tf_internal_flow_block_bwd_tc(const float* y_in, const float* feat, int feat_dim, int sn, const float* W1, const float* W2, const float* W3,
+                                  const float* W4, float scale, float offset, int cond, int64_t M, const float* saved_h, const float* saved_st,
+                                  const float* g_y_out, const float* g_logj, float* g_y_in, float* d_feat, float* dW1, float* db1, float* dW2,
+                                  float* db2, float* dW3, float* db3, float* dW4, float* db4, cudaStream_t stream);
 // TF_FLOW_SIMT=1 selects the FP32-pipe kernel below instead of the tcgen05 one (A/B runs; read once per process)
 static bool flow_use_simt() {
     static int forced = -1;
@@ -449,14 +453,15 @@ static bool flow_use_simt() {
 extern "C" TF_API int tf_flow_block_fwd(const float* y_in, const float* logj_in, const float* feat, int32_t feat_dim, int32_t sn,
                                         const float* W1, const float* b1, const float* W2, const float* b2, const float* W3, const float* b3,
                                         const float* W4, const float* b4, float scale, float offset, int32_t cond, int32_t inverse, int64_t M,
-                                        float* y_out, float* logj_out, tf_stream_t stream) {
+                                        float* y_out, float* logj_out, float* save_h, float* save_st, tf_stream_t stream) {
     if (M == 0) return 0;
     FlowW w = {W1, b1, W2, b2, W3, b3, W4, b4, feat_dim, scale, offset};
     if (int e = flow_check(w, sn, cond, M)) return e;
     TF_REQUIRE(y_in && feat && y_out && logj_out, "tf_flow_block_fwd: NULL pointer");
     if (!flow_use_simt()) {
+        TF_REQUIRE((save_h == nullptr) == (save_st == nullptr), "tf_flow_block_fwd: pass both activation buffers or none");
         tf_internal_flow_block_fwd_tc(y_in, logj_in, feat, feat_dim, sn, W1, b1, W2, b2, W3, b3, W4, b4, scale, offset, cond, inverse, M, y_out,
-                                      logj_out, nullptr, nullptr, (cudaStream_t)stream);
+                                      logj_out, save_h, save_st, (cudaStream_t)stream);
         TF_CHECK_LAUNCH("tf_flow_block_fwd (tcgen05)");
         return 0;
     }
@@ -479,13 +484,19 @@ extern "C" TF_API int tf_flow_block_fwd(const float* y_in, const float* logj_in,
 
 extern "C" TF_API int tf_flow_block_bwd(const float* y_in, const float* feat, int32_t feat_dim, int32_t sn, const float* W1, const float* b1,
                                         const float* W2, const float* b2, const float* W3, const float* b3, const float* W4, const float* b4,
-                                        float scale, float offset, int32_t cond, int64_t M, const float* g_y_out, const float* g_logj,
-                                        float* g_y_in, float* d_feat, float* dW1, float* db1, float* dW2, float* db2, float* dW3, float* db3,
-                                        float* dW4, float* db4, tf_stream_t stream) {
+                                        float scale, float offset, int32_t cond, int64_t M, const float* saved_h, const float* saved_st,
+                                        const float* g_y_out, const float* g_logj, float* g_y_in, float* d_feat, float* dW1, float* db1,
+                                        float* dW2, float* db2, float* dW3, float* db3, float* dW4, float* db4, tf_stream_t stream) {
     if (M == 0) return 0;
     FlowW w = {W1, b1, W2, b2, W3, b3, W4, b4, feat_dim, scale, offset};
     if (int e = flow_check(w, sn, cond, M)) return e;
     TF_REQUIRE(y_in && feat && g_y_in && d_feat && dW1 && db1 && dW2 && db2 && dW3 && db3 && dW4 && db4, "tf_flow_block_bwd: NULL pointer");
+    if (saved_h && saved_st) {          // activations kept by the tcgen05 forward: tensor-core adjoint chain, no recompute
+        if (int e = tf_internal_flow_block_bwd_tc(y_in, feat, feat_dim, sn, W1, W2, W3, W4, scale, offset, cond, M, saved_h, saved_st, g_y_out, g_logj,
+                                                  g_y_in, d_feat, dW1, db1, dW2, db2, dW3, db3, dW4, db4, (cudaStream_t)stream)) return e;
+        TF_CHECK_LAUNCH("tf_flow_block_bwd (tcgen05)");
+        return 0;
+    }
     FlowBwdParams p = {w, y_in, feat, sn, cond, M, g_y_out, g_logj, g_y_in, d_feat, dW1, db1, dW2, db2, dW3, db3, dW4, db4};
     const size_t smem = flow_bwd_smem();
     TF_REQUIRE(smem <= 227 * 1024, "tf_flow_block_bwd: shared-memory budget exceeded (%zu bytes)", smem);
@@ -497,3 +508,6 @@ extern "C" TF_API int tf_flow_block_bwd(const float* y_in, const float* feat, in
     TF_CHECK_LAUNCH("tf_flow_block_bwd");
     return 0;
 }
+
+/* 1 when tf_flow_block_fwd runs on the tcgen05 kernel (which can keep the activations for tf_flow_block_bwd), 0 for the FP32-pipe kernel */
+extern "C" TF_API int tf_flow_block_uses_tensor_cores(void) { return flow_use_simt() ? 0 : 1; }

@@ -193,6 +193,275 @@ __global__ void __launch_bounds__(FTILE, 2) flow_block_fwd_tc_kernel(FlowTcParam
     if (warp == 0) tc::tmem_dealloc<256>(tmem);
 }
 
+// =====================================================================================================================
+// Backward of the coupling block (density direction) with the activations kept by the forward (h1, h2, h3, spline parameters):
+//   adjoint chain   d_st -> dh3 -> dpre3 -> dh2 -> dpre2 -> dh1 -> dpre1 -> d x_in : four TS-mode GEMMs against W^T tiles in shared
+//                   memory, the running adjoint written to tensor memory by the epilogues (x LeakyReLU' of the kept activation)
+//   weight gradients dW_l += dpre_l^T h_(l-1) over the 128 rows of the tile: register-tiled FP32 products from two row-major
+//                   shared-memory tiles while the tensor core runs the next chain GEMM; every thread owns a patch of the
+//                   per-CTA accumulators (no atomics until the final flush)
+//   feature part     per-point sums of dpre1 -> dW1[:, 7:], d feature
+// =====================================================================================================================
+constexpr int FLD = FH + 4;          // row stride of the fp32 tiles (bank spread for per-thread rows)
+constexpr int FLDS = FSTP + 4;
+constexpr int FMAXF = 40;
+
+struct FlowTcBwdParams {
+    const float *W1, *W2, *W3, *W4;
+    int F; float scale, offset;
+    const float* y_in; const float* feat; const float* saved_h; const float* saved_st;
+    int sn, cond; int64_t M;
+    const float* g_y_out; const float* g_logj;
+    float* g_y_in; float* d_feat;
+    float *dW1, *db1, *dW2, *db2, *dW3, *db3, *dW4, *db4;
+};
+
+// acc[j][k] += sum_p D[p][j] H[p][k] over the 128 rows of a tile; every thread owns a JP x KP patch
+template <int JP, int KP>
+__device__ __forceinline__ void tile_xty(const float* __restrict__ D, int ldd, const float* __restrict__ H, int ldh, float* __restrict__ acc, int ldacc,
+                                         int j0, int k0) {
+    float a[JP][KP];
+#pragma unroll
+    for (int x = 0; x < JP; ++x)
+#pragma unroll
+        for (int y = 0; y < KP; ++y) a[x][y] = 0.f;
+#pragma unroll 2
+    for (int r = 0; r < FTILE; ++r) {
+        float d[JP], h[KP];
+#pragma unroll
+        for (int x = 0; x < JP; ++x) d[x] = D[r * ldd + j0 + x];
+#pragma unroll
+        for (int y = 0; y < KP; ++y) h[y] = H[r * ldh + k0 + y];
+#pragma unroll
+        for (int x = 0; x < JP; ++x)
+#pragma unroll
+            for (int y = 0; y < KP; ++y) a[x][y] = fmaf(d[x], h[y], a[x][y]);
+    }
+#pragma unroll
+    for (int x = 0; x < JP; ++x)
+#pragma unroll
+        for (int y = 0; y < KP; ++y) acc[(j0 + x) * ldacc + k0 + y] += a[x][y];
+}
+__device__ __forceinline__ void tile_colsum(const float* __restrict__ D, int ldd, int ncols, float* __restrict__ acc, int tid) {
+    if (tid < ncols) {
+        float s = 0.f;
+        for (int r = 0; r < FTILE; ++r) s += D[r * ldd + tid];
+        acc[tid] += s;
+    }
+}
+// rows [i0, i0 + 128) of the kept activation `layer` -> shared-memory tile (coalesced: 16 threads per 256-byte row)
+__device__ __forceinline__ void load_h_tile(float* T, const float* __restrict__ saved_h, int layer, int64_t i0, int64_t M, int tid) {
+    for (int e = tid; e < FTILE * (FH / 4); e += FTILE) {
+        const int r = e / (FH / 4), c4 = e % (FH / 4);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i0 + r < M) v = __ldg(reinterpret_cast<const float4*>(saved_h + ((size_t)(i0 + r) * 3 + layer) * FH) + c4);
+        *reinterpret_cast<float4*>(T + r * FLD + 4 * c4) = v;
+    }
+}
+
+__global__ void __launch_bounds__(FTILE, 1) flow_block_bwd_tc_kernel(FlowTcBwdParams p) {
+    extern __shared__ __align__(1024) uint8_t fsm_raw[];
+    float* sp = reinterpret_cast<float*>(fsm_raw);
+    auto carve = [&](int n) { float* r = sp; sp += n; return r; };
+    // B tiles of the adjoint chain: B[n = input unit][k = output unit] = W[k][n]
+    float* t4_hi = carve(FH * N4); float* t4_lo = carve(FH * N4);      // [64][32]: W4^T
+    float* t3_hi = carve(FH * FH); float* t3_lo = carve(FH * FH);
+    float* t2_hi = carve(FH * FH); float* t2_lo = carve(FH * FH);
+    float* t1_hi = carve(K1 * FH); float* t1_lo = carve(K1 * FH);      // [8][64]: W1[:, :7]^T
+    float* aW1a = carve(FH * 8); float* aW1b = carve(FH * FMAXF); float* aW2 = carve(FH * FH); float* aW3 = carve(FH * FH); float* aW4 = carve(FSTP * FH);
+    float* ab1 = carve(FH); float* ab2 = carve(FH); float* ab3 = carve(FH); float* ab4 = carve(FSTP);
+    float* Th = carve(FTILE * FLD);          // kept activation of the previous layer (row-major fp32)
+    float* Td = carve(FTILE * FLD);          // adjoint of the current layer's pre-activation (row-major fp32)
+    float* Sp = carve(FMAXP * FH);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(carve(2));
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(carve(2));
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int F = p.F, KW1 = FPE + F;
+    // transposed weight tiles: element (n, k) = W[k][n]
+    for (int i = tid; i < FH * N4; i += FTILE) {
+        const int n = i / N4, k = i % N4;
+        const float v = k < NST ? p.W4[(size_t)k * FH + n] : 0.f;
+        const float h = tc::tf32_rn(v); const uint32_t off = tc::tile_off_b32(n, k, N4 / 4) / 4;
+        t4_hi[off] = h; t4_lo[off] = tc::tf32_rn(v - h);
+    }
+    for (int i = tid; i < FH * FH; i += FTILE) {
+        const int n = i / FH, k = i % FH;
+        const uint32_t off = tc::tile_off_b32(n, k, FH / 4) / 4;
+        float v = p.W3[(size_t)k * FH + n]; float h = tc::tf32_rn(v);
+        t3_hi[off] = h; t3_lo[off] = tc::tf32_rn(v - h);
+        v = p.W2[(size_t)k * FH + n]; h = tc::tf32_rn(v);
+        t2_hi[off] = h; t2_lo[off] = tc::tf32_rn(v - h);
+    }
+    for (int i = tid; i < K1 * FH; i += FTILE) {
+        const int n = i / FH, k = i % FH;
+        const float v = n < FPE ? p.W1[(size_t)k * KW1 + n] : 0.f;
+        const float h = tc::tf32_rn(v); const uint32_t off = tc::tile_off_b32(n, k, FH / 4) / 4;
+        t1_hi[off] = h; t1_lo[off] = tc::tf32_rn(v - h);
+    }
+    for (int i = tid; i < FH * 8 + FH * FMAXF + 2 * FH * FH + FSTP * FH + 3 * FH + FSTP; i += FTILE) aW1a[i] = 0.f;      // contiguous accumulators
+    if (warp == 0) tc::tmem_alloc<256>(tmem_slot);
+    if (tid == 0) { tc::mbar_init(bar, 1); tc::mbar_fence_init(); }
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t d_col = tmem, a_hi = tmem + 64, a_lo = tmem + 128;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    uint32_t parity = 0;
+
+    const int64_t ntiles = (p.M + FTILE - 1) / FTILE;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t i0 = tile * FTILE;
+        const int64_t i_last = (i0 + FTILE - 1 < p.M ? i0 + FTILE - 1 : p.M - 1);
+        const int64_t p_first = i0 / p.sn;
+        const int np = (int)(i_last / p.sn - p_first) + 1;
+        const int64_t i = i0 + tid;
+        const bool live = i < p.M;
+        float yc = 0.f, d_yt = 0.f;
+        {   // ---- spline adjoint -> d_st: A operand (tensor memory) + row-major tile --------------------------------------
+            float dst[N4], lo[N4];
+#pragma unroll
+            for (int k = 0; k < N4; ++k) dst[k] = 0.f;
+            if (live) {
+                float st[FSTP];
+                const float4* s4 = reinterpret_cast<const float4*>(p.saved_st + (size_t)i * FSTP);
+#pragma unroll
+                for (int j = 0; j < FSTP / 4; ++j) { const float4 v = __ldg(s4 + j); st[4 * j] = v.x; st[4 * j + 1] = v.y; st[4 * j + 2] = v.z; st[4 * j + 3] = v.w; }
+                const float y0 = p.y_in[i * 2], y1 = p.y_in[i * 2 + 1];
+                yc = p.cond ? y1 : y0;
+                const float yt = p.cond ? y0 : y1;
+                const float gx = p.g_y_out ? p.g_y_out[i * 2 + 1 - p.cond] : 0.f;
+                const float gl = p.g_logj ? p.g_logj[i] : 0.f;
+                pwquad_adjoint(st, yt, gx, gl, d_yt, dst);
+            }
+#pragma unroll
+            for (int k = 0; k < FLDS; ++k) Td[tid * FLD + k] = k < FSTP ? dst[k] : 0.f;
+#pragma unroll
+            for (int k = 0; k < N4; ++k) { const float h = tc::tf32_rn(dst[k]); lo[k] = tc::tf32_rn(dst[k] - h); dst[k] = h; }
+            tc::tmem_st16(a_hi + lane_base, dst); tc::tmem_st16(a_hi + lane_base + 16, dst + 16);
+            tc::tmem_st16(a_lo + lane_base, lo); tc::tmem_st16(a_lo + lane_base + 16, lo + 16);
+            tc::tmem_st_wait();
+        }
+        load_h_tile(Th, p.saved_h, 2, i0, p.M, tid);                      // h3
+        tc::fence_before_sync();
+        __syncthreads();
+        if (tid == 0) { tc::fence_after_sync(); issue_layer(d_col, a_hi, a_lo, t4_hi, t4_lo, N4, FH); tc::mma_commit(bar); }    // dh3 = d_st W4
+        tile_xty<3, 4>(Td, FLD, Th, FLD, aW4, FH, 3 * (tid >> 4), 4 * (tid & 15));                                             // dW4 += d_st^T h3
+        tile_colsum(Td, FLD, FSTP, ab4, tid);
+        // ---- layers 3, 2, 1: epilogue (x LeakyReLU') -> next chain GEMM on the tensor core || weight-gradient products ------
+#pragma unroll 1
+        for (int layer = 2; layer >= 0; --layer) {
+            tc::mbar_wait(bar, parity); parity ^= 1;
+            tc::fence_after_sync();
+            __syncthreads();                                            // every thread is done reading Td / Th of the previous products
+#pragma unroll
+            for (int c0 = 0; c0 < FH; c0 += 16) {
+                float v[16], lo[16];
+                tc::tmem_ld16(d_col + lane_base + c0, v);
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    const float4 h = *reinterpret_cast<const float4*>(Th + tid * FLD + c0 + 4 * j4);       // own row of the kept activation
+                    v[4 * j4] *= h.x > 0.f ? 1.f : 0.01f; v[4 * j4 + 1] *= h.y > 0.f ? 1.f : 0.01f;
+                    v[4 * j4 + 2] *= h.z > 0.f ? 1.f : 0.01f; v[4 * j4 + 3] *= h.w > 0.f ? 1.f : 0.01f;
+                    *reinterpret_cast<float4*>(Td + tid * FLD + c0 + 4 * j4) = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { const float h = tc::tf32_rn(v[j]); lo[j] = tc::tf32_rn(v[j] - h); v[j] = h; }
+                tc::tmem_st16(a_hi + lane_base + c0, v);
+                tc::tmem_st16(a_lo + lane_base + c0, lo);
+            }
+            tc::tmem_st_wait();
+            tc::fence_before_sync();
+            __syncthreads();                                            // dpre tile + A operand complete, Th free
+            if (tid == 0) {
+                tc::fence_after_sync();
+                if (layer == 2) issue_layer(d_col, a_hi, a_lo, t3_hi, t3_lo, FH, FH);          // dh2 = dpre3 W3
+                else if (layer == 1) issue_layer(d_col, a_hi, a_lo, t2_hi, t2_lo, FH, FH);     // dh1 = dpre2 W2
+                else issue_layer(d_col, a_hi, a_lo, t1_hi, t1_lo, FH, K1);                     // d x_in = dpre1 W1[:, :7]
+                tc::mma_commit(bar);
+            }
+            if (layer > 0) {
+                load_h_tile(Th, p.saved_h, layer - 1, i0, p.M, tid);    // h2 / h1: input of this layer, also the next epilogue's LeakyReLU'
+            } else {                                                    // layer 1: the input is Reshift(PE(y_c)), recomputed
+                float x[8];
+                x[0] = yc; x[1] = sinf(yc); x[2] = cosf(yc); x[3] = sinf(yc * 2.f); x[4] = cosf(yc * 2.f); x[5] = sinf(yc * 4.f); x[6] = cosf(yc * 4.f);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) Th[tid * FLD + k] = (live && k < FPE) ? x[k] * p.scale + p.offset : 0.f;
+            }
+            __syncthreads();
+            if (layer == 2) { tile_xty<4, 8>(Td, FLD, Th, FLD, aW3, FH, 4 * (tid >> 3), 8 * (tid & 7)); tile_colsum(Td, FLD, FH, ab3, tid); }
+            else if (layer == 1) { tile_xty<4, 8>(Td, FLD, Th, FLD, aW2, FH, 4 * (tid >> 3), 8 * (tid & 7)); tile_colsum(Td, FLD, FH, ab2, tid); }
+            else {
+                tile_xty<1, 4>(Td, FLD, Th, FLD, aW1a, 8, tid >> 1, 4 * (tid & 1));
+                tile_colsum(Td, FLD, FH, ab1, tid);
+                if (tid >= FH) {                                        // S[lp][j]: dpre1 summed over the tile's rows of point lp
+                    const int j = tid - FH;
+                    float sacc = 0.f;
+                    int cur = 0;
+                    for (int r = 0; r < FTILE; ++r) {
+                        const int64_t ir = i0 + r;
+                        const int lr = ir < p.M ? (int)(ir / p.sn - p_first) : cur;
+                        if (lr != cur) { Sp[cur * FH + j] = sacc; sacc = 0.f; cur = lr; }
+                        sacc += Td[r * FLD + j];
+                    }
+                    Sp[cur * FH + j] = sacc;
+                }
+            }
+        }
+        // ---- d y_c from d x_in, feature part of the first layer -----------------------------------------------------------
+        tc::mbar_wait(bar, parity); parity ^= 1;
+        tc::fence_after_sync();
+        {
+            float dx[8];
+            tc::tmem_ld8(d_col + lane_base, dx);
+            if (live) {
+                const float dyc = p.scale * (dx[0] + dx[1] * cosf(yc) - dx[2] * sinf(yc) + 2.f * (dx[3] * cosf(2.f * yc) - dx[4] * sinf(2.f * yc)) +
+                                             4.f * (dx[5] * cosf(4.f * yc) - dx[6] * sinf(4.f * yc)));
+                p.g_y_in[i * 2 + p.cond] = (p.g_y_out ? p.g_y_out[i * 2 + p.cond] : 0.f) + dyc;
+                p.g_y_in[i * 2 + 1 - p.cond] = d_yt;
+            }
+        }
+        __syncthreads();                                                // Sp complete
+        for (int e = tid; e < np * F; e += FTILE) {
+            const int l = e / F, k = e % F;
+            const float xf = __ldg(p.feat + (p_first + l) * F + k) * p.scale + p.offset;
+            float g = 0.f;
+            for (int j = 0; j < FH; ++j) {
+                const float sj = Sp[l * FH + j];
+                g = fmaf(__ldg(p.W1 + (size_t)j * KW1 + FPE + k), sj, g);
+                atomicAdd(&aW1b[j * FMAXF + k], sj * xf);
+            }
+            atomicAdd(p.d_feat + (p_first + l) * F + k, g * p.scale);
+        }
+        tc::fence_before_sync();
+        __syncthreads();
+    }
+    // ---- flush the CTA's weight-gradient partials ------------------------------------------------------------------------
+    for (int i = tid; i < FH * FPE; i += FTILE) { const int j = i / FPE, k = i % FPE; const float v = aW1a[j * 8 + k]; if (v != 0.f) atomicAdd(p.dW1 + (size_t)j * KW1 + k, v); }
+    for (int i = tid; i < FH * F; i += FTILE) { const int j = i / F, k = i % F; const float v = aW1b[j * FMAXF + k]; if (v != 0.f) atomicAdd(p.dW1 + (size_t)j * KW1 + FPE + k, v); }
+    for (int i = tid; i < FH * FH; i += FTILE) {
+        if (aW2[i] != 0.f) atomicAdd(p.dW2 + i, aW2[i]);
+        if (aW3[i] != 0.f) atomicAdd(p.dW3 + i, aW3[i]);
+    }
+    for (int i = tid; i < NST * FH; i += FTILE) if (aW4[i] != 0.f) atomicAdd(p.dW4 + i, aW4[i]);
+    for (int i = tid; i < FH; i += FTILE) {
+        if (ab1[i] != 0.f) atomicAdd(p.db1 + i, ab1[i]);
+        if (ab2[i] != 0.f) atomicAdd(p.db2 + i, ab2[i]);
+        if (ab3[i] != 0.f) atomicAdd(p.db3 + i, ab3[i]);
+    }
+    for (int i = tid; i < NST; i += FTILE) if (ab4[i] != 0.f) atomicAdd(p.db4 + i, ab4[i]);
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<256>(tmem);
+}
+
+size_t flow_tc_bwd_smem() {
+    return sizeof(float) * (size_t)(2 * FH * N4 + 4 * FH * FH + 2 * K1 * FH + FH * 8 + FH * FMAXF + 2 * FH * FH + FSTP * FH + 3 * FH + FSTP +
+                                    2 * FTILE * FLD + FMAXP * FH + 4) + 1024;
+}
+
 size_t flow_tc_smem() {
     return sizeof(float) * (size_t)(2 * FH * K1 + 4 * FH * FH + 2 * N4 * FH + 3 * FH + N4 + FMAXP * FH + 4) + 1024;
 }
@@ -214,6 +483,26 @@ int tf_internal_flow_block_fwd_tc(const float* y_in, const float* logj_in, const
     {
         TfKernelTimer timer("flow_block_fwd_tc", stream);
         flow_block_fwd_tc_kernel<<<grid, FTILE, smem, stream>>>(p);
+    }
+    tf_count_launches(1);
+    return 0;
+}
+
+// tensor-core backward of one coupling block from the activations kept by tf_internal_flow_block_fwd_tc
+int tf_internal_flow_block_bwd_tc(const float* y_in, const float* feat, int feat_dim, int sn, const float* W1, const float* W2, const float* W3,
+                                  const float* W4, float scale, float offset, int cond, int64_t M, const float* saved_h, const float* saved_st,
+                                  const float* g_y_out, const float* g_logj, float* g_y_in, float* d_feat, float* dW1, float* db1, float* dW2,
+                                  float* db2, float* dW3, float* db3, float* dW4, float* db4, cudaStream_t stream) {
+    FlowTcBwdParams p = {W1, W2, W3, W4, feat_dim, scale, offset, y_in, feat, saved_h, saved_st, sn, cond, M, g_y_out, g_logj, g_y_in, d_feat,
+                         dW1, db1, dW2, db2, dW3, db3, dW4, db4};
+    const size_t smem = flow_tc_bwd_smem();
+    if (smem > 227 * 1024) { tf_set_error("flow block backward: shared-memory budget exceeded (%zu bytes)", smem); return 1; }
+    cudaFuncSetAttribute(flow_block_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int64_t ntiles = (M + FTILE - 1) / FTILE;
+    const int grid = (int)(ntiles < tf_num_sms() ? ntiles : tf_num_sms());
+    {
+        TfKernelTimer timer("flow_block_bwd_tc", stream);
+        flow_block_bwd_tc_kernel<<<grid, FTILE, smem, stream>>>(p);
     }
     tf_count_launches(1);
     return 0;

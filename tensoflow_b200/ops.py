@@ -591,10 +591,17 @@ class FlowBlockFunction(torch.autograd.Function):
         M = yc.shape[0]
         y_out = torch.empty_like(yc)
         lj_out = torch.empty(M, device=yc.device, dtype=torch.float32)
+        # density direction with gradients: the tensor-core forward keeps h1, h2, h3 and the spline parameters (864 B per pair),
+        # so that the backward is the adjoint chain alone
+        keep = (not inverse) and any(ctx.needs_input_grad) and lib.tf_flow_block_uses_tensor_cores() == 1
+        sh = torch.empty(M, 3, 64, device=yc.device, dtype=torch.float32) if keep else None
+        sst = torch.empty(M, 24, device=yc.device, dtype=torch.float32) if keep else None
         with _timed("flow_block_fwd"):
             check(lib.tf_flow_block_fwd(ptr(yc), ptr(lc), ptr(fc), int(fc.shape[1]), int(sn), *(ptr(w) for w in ws), float(scale), float(offset),
-                                        int(cond), 1 if inverse else 0, M, ptr(y_out), ptr(lj_out), stream_ptr()), "tf_flow_block_fwd")
+                                        int(cond), 1 if inverse else 0, M, ptr(y_out), ptr(lj_out), ptr(sh), ptr(sst), stream_ptr()),
+                  "tf_flow_block_fwd")
         ctx.save_for_backward(yc, fc, *ws)
+        ctx.kept = (sh, sst)
         ctx.cfg = (int(sn), int(cond), bool(inverse), float(scale), float(offset), None if logj is None else logj.shape)
         return y_out, lj_out
 
@@ -612,7 +619,9 @@ class FlowBlockFunction(torch.autograd.Function):
         d_feat = torch.zeros_like(fc)
         dws = [_grad_zeros(w) for w in ws]
         with _timed("flow_block_bwd"):
-            check(lib.tf_flow_block_bwd(ptr(yc), ptr(fc), int(fc.shape[1]), sn, *(ptr(w) for w in ws), scale, offset, cond, M, ptr(gy), ptr(gl),
-                                        ptr(g_in), ptr(d_feat), *(ptr(d) for d in dws), stream_ptr()), "tf_flow_block_bwd")
+            check(lib.tf_flow_block_bwd(ptr(yc), ptr(fc), int(fc.shape[1]), sn, *(ptr(w) for w in ws), scale, offset, cond, M, ptr(ctx.kept[0]),
+                                        ptr(ctx.kept[1]), ptr(gy), ptr(gl), ptr(g_in), ptr(d_feat), *(ptr(d) for d in dws), stream_ptr()),
+                  "tf_flow_block_bwd")
+        ctx.kept = (None, None)
         g_logj_in = None if (logj_shape is None or gl is None) else gl.reshape(logj_shape)
         return (g_in, g_logj_in, d_feat, None, None, None, None, None, *dws)
