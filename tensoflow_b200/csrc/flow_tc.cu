@@ -216,7 +216,8 @@ struct FlowTcBwdParams {
     float *dW1, *db1, *dW2, *db2, *dW3, *db3, *dW4, *db4;
 };
 
-// acc[j][k] += sum_p D[p][j] H[p][k] over the 128 rows of a tile; every thread owns a JP x KP patch
+// acc[j][k] += sum_p D[p][j] H[p][k] over the 128 rows of a tile; every thread owns a JP x KP patch (JP, KP multiples of 4 use
+// 16-byte shared-memory loads; rows are FLD = 68 floats apart, so the patch origins must be multiples of 4)
 template <int JP, int KP>
 __device__ __forceinline__ void tile_xty(const float* __restrict__ D, int ldd, const float* __restrict__ H, int ldh, float* __restrict__ acc, int ldacc,
                                          int j0, int k0) {
@@ -225,13 +226,18 @@ __device__ __forceinline__ void tile_xty(const float* __restrict__ D, int ldd, c
     for (int x = 0; x < JP; ++x)
 #pragma unroll
         for (int y = 0; y < KP; ++y) a[x][y] = 0.f;
-#pragma unroll 2
+#pragma unroll 4
     for (int r = 0; r < FTILE; ++r) {
         float d[JP], h[KP];
+        if (JP % 4 == 0) {
 #pragma unroll
-        for (int x = 0; x < JP; ++x) d[x] = D[r * ldd + j0 + x];
+            for (int x = 0; x < JP; x += 4) { const float4 v = *reinterpret_cast<const float4*>(D + r * ldd + j0 + x); d[x] = v.x; d[x + 1] = v.y; d[x + 2] = v.z; d[x + 3] = v.w; }
+        } else {
 #pragma unroll
-        for (int y = 0; y < KP; ++y) h[y] = H[r * ldh + k0 + y];
+            for (int x = 0; x < JP; ++x) d[x] = D[r * ldd + j0 + x];
+        }
+#pragma unroll
+        for (int y = 0; y < KP; y += 4) { const float4 v = *reinterpret_cast<const float4*>(H + r * ldh + k0 + y); h[y] = v.x; h[y + 1] = v.y; h[y + 2] = v.z; h[y + 3] = v.w; }
 #pragma unroll
         for (int x = 0; x < JP; ++x)
 #pragma unroll
@@ -273,6 +279,7 @@ __global__ void __launch_bounds__(FTILE, 1) flow_block_bwd_tc_kernel(FlowTcBwdPa
     float* Th = carve(FTILE * FLD);          // kept activation of the previous layer (row-major fp32)
     float* Td = carve(FTILE * FLD);          // adjoint of the current layer's pre-activation (row-major fp32)
     float* Sp = carve(FMAXP * FH);
+    int* row_lp = reinterpret_cast<int*>(carve(FTILE));       // local point index of every row of the tile
     uint64_t* bar = reinterpret_cast<uint64_t*>(carve(2));
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(carve(2));
 
@@ -320,6 +327,7 @@ __global__ void __launch_bounds__(FTILE, 1) flow_block_bwd_tc_kernel(FlowTcBwdPa
         const int64_t i = i0 + tid;
         const bool live = i < p.M;
         float yc = 0.f, d_yt = 0.f;
+        row_lp[tid] = live ? (int)(i / p.sn - p_first) : np - 1;
         {   // ---- spline adjoint -> d_st: A operand (tensor memory) + row-major tile --------------------------------------
             float dst[N4], lo[N4];
 #pragma unroll
@@ -401,8 +409,7 @@ __global__ void __launch_bounds__(FTILE, 1) flow_block_bwd_tc_kernel(FlowTcBwdPa
                     float sacc = 0.f;
                     int cur = 0;
                     for (int r = 0; r < FTILE; ++r) {
-                        const int64_t ir = i0 + r;
-                        const int lr = ir < p.M ? (int)(ir / p.sn - p_first) : cur;
+                        const int lr = row_lp[r];
                         if (lr != cur) { Sp[cur * FH + j] = sacc; sacc = 0.f; cur = lr; }
                         sacc += Td[r * FLD + j];
                     }
@@ -459,7 +466,7 @@ __global__ void __launch_bounds__(FTILE, 1) flow_block_bwd_tc_kernel(FlowTcBwdPa
 
 size_t flow_tc_bwd_smem() {
     return sizeof(float) * (size_t)(2 * FH * N4 + 4 * FH * FH + 2 * K1 * FH + FH * 8 + FH * FMAXF + 2 * FH * FH + FSTP * FH + 3 * FH + FSTP +
-                                    2 * FTILE * FLD + FMAXP * FH + 4) + 1024;
+                                    2 * FTILE * FLD + FMAXP * FH + FTILE + 4) + 1024;
 }
 
 size_t flow_tc_smem() {
