@@ -335,11 +335,16 @@ def run_ours(args):
         l0 = _lib.launch_count()
         sampler = ClockSampler(local) if rank == 0 else None
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        prof = timers and bool(os.environ.get('TF_PROFILE_RANGE'))      # ncu --profile-from-start off: only the timed steps
+        if prof:
+            torch.cuda.profiler.start()
         a.record()
         for i in range(args.steps):
             run_step(i)
         b.record()
         torch.cuda.synchronize()
+        if prof:
+            torch.cuda.profiler.stop()
         if world > 1:
             dist.barrier()
         ms = a.elapsed_time(b)

@@ -99,10 +99,15 @@ def main():
     ops.KernelTimers.reset(True)
     l0 = _lib.launch_count()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if os.environ.get('TF_PROFILE_RANGE'):          # ncu --profile-from-start off: only the timed steps are captured
+        torch.cuda.profiler.start()
     a.record()
     for _ in range(args.steps):
         loss = one_step()
     b.record()
+    torch.cuda.synchronize()
+    if os.environ.get('TF_PROFILE_RANGE'):
+        torch.cuda.profiler.stop()
     torch.cuda.synchronize()
     ms = a.elapsed_time(b) / args.steps
     calls = {k: (round(v[0] / args.steps, 3), v[1] // args.steps) for k, v in ops.KernelTimers.totals_ms().items()}

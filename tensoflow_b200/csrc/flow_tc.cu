@@ -17,7 +17,7 @@ namespace {
 
 using namespace flowsp;
 
-constexpr int FH = 64, FPE = 7, FSTP = 24, FTILE = 128, FMAXP = 10;
+constexpr int FH = 64, FPE = 7, FSTP = 24, FTILE = 128, FMAXP = 10, FMAXF = 40;
 constexpr int K1 = 8;        // first-layer K: 7 positional-encoding inputs + one zero column
 constexpr int N4 = 32;       // last-layer N: 21 spline parameters padded to 32
 
@@ -69,11 +69,14 @@ __global__ void __launch_bounds__(FTILE, 2) flow_block_fwd_tc_kernel(FlowTcParam
     float* b4_hi = carve(N4 * FH); float* b4_lo = carve(N4 * FH);
     float* bias1 = carve(FH); float* bias2 = carve(FH); float* bias3 = carve(FH); float* bias4 = carve(N4);
     float* h1p = carve(FMAXP * FH);
+    float* w1b = carve(FMAXF * FH);          // feature part of the first layer, [k][j]
+    float* xfs = carve(FMAXP * FMAXF);       // Reshift(feature) of the tile's points
     uint64_t* bar = reinterpret_cast<uint64_t*>(carve(2));
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(carve(2));
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int F = p.F, KW1 = FPE + F;
+    for (int i = tid; i < F * FH; i += FTILE) { const int k = i / FH, j = i % FH; w1b[i] = p.W1[(size_t)j * KW1 + FPE + k]; }
     fill_b_tile(b1_hi, b1_lo, p.W1, KW1, 0, FH, K1, FH, FPE, tid, FTILE);
     fill_b_tile(b2_hi, b2_lo, p.W2, FH, 0, FH, FH, FH, FH, tid, FTILE);
     fill_b_tile(b3_hi, b3_lo, p.W3, FH, 0, FH, FH, FH, FH, tid, FTILE);
@@ -98,12 +101,12 @@ __global__ void __launch_bounds__(FTILE, 2) flow_block_fwd_tc_kernel(FlowTcParam
         const int64_t p_first = i0 / p.sn;
         const int np = (int)(i_last / p.sn - p_first) + 1;
         // per-point part of the first layer: h1p[lp][j] = b1[j] + sum_k W1[j][7 + k] (scale feat[p][k] + offset)
+        for (int e = tid; e < np * F; e += FTILE) xfs[(e / F) * FMAXF + e % F] = __ldg(p.feat + (p_first + e / F) * F + e % F) * p.scale + p.offset;
+        __syncthreads();
         for (int e = tid; e < np * FH; e += FTILE) {
             const int lp = e / FH, j = e % FH;
-            const float* f = p.feat + (p_first + lp) * F;
-            const float* wr = p.W1 + (size_t)j * KW1 + FPE;
             float acc = bias1[j];
-            for (int k = 0; k < F; ++k) acc = fmaf(__ldg(wr + k), __ldg(f + k) * p.scale + p.offset, acc);
+            for (int k = 0; k < F; ++k) acc = fmaf(w1b[k * FH + j], xfs[lp * FMAXF + k], acc);
             h1p[lp * FH + j] = acc;
         }
         const int64_t i = i0 + tid;
@@ -204,7 +207,6 @@ __global__ void __launch_bounds__(FTILE, 2) flow_block_fwd_tc_kernel(FlowTcParam
 // =====================================================================================================================
 constexpr int FLD = FH + 4;          // row stride of the fp32 tiles (bank spread for per-thread rows)
 constexpr int FLDS = FSTP + 4;
-constexpr int FMAXF = 40;
 
 struct FlowTcBwdParams {
     const float *W1, *W2, *W3, *W4;
@@ -280,6 +282,8 @@ __global__ void __launch_bounds__(FTILE, 1) flow_block_bwd_tc_kernel(FlowTcBwdPa
     float* Td = carve(FTILE * FLD);          // adjoint of the current layer's pre-activation (row-major fp32)
     float* Sp = carve(FMAXP * FH);
     int* row_lp = reinterpret_cast<int*>(carve(FTILE));       // local point index of every row of the tile
+    float* w1b = carve(FH * FMAXF);          // feature part of the first layer, [j][k]
+    float* xfs = carve(FMAXP * FMAXF);       // Reshift(feature) of the tile's points
     uint64_t* bar = reinterpret_cast<uint64_t*>(carve(2));
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(carve(2));
 
@@ -307,6 +311,7 @@ __global__ void __launch_bounds__(FTILE, 1) flow_block_bwd_tc_kernel(FlowTcBwdPa
         t1_hi[off] = h; t1_lo[off] = tc::tf32_rn(v - h);
     }
     for (int i = tid; i < FH * 8 + FH * FMAXF + 2 * FH * FH + FSTP * FH + 3 * FH + FSTP; i += FTILE) aW1a[i] = 0.f;      // contiguous accumulators
+    for (int i = tid; i < FH * F; i += FTILE) { const int j = i / F, k = i % F; w1b[j * FMAXF + k] = p.W1[(size_t)j * KW1 + FPE + k]; }
     if (warp == 0) tc::tmem_alloc<256>(tmem_slot);
     if (tid == 0) { tc::mbar_init(bar, 1); tc::mbar_fence_init(); }
     tc::fence_async_smem();
@@ -328,6 +333,7 @@ __global__ void __launch_bounds__(FTILE, 1) flow_block_bwd_tc_kernel(FlowTcBwdPa
         const bool live = i < p.M;
         float yc = 0.f, d_yt = 0.f;
         row_lp[tid] = live ? (int)(i / p.sn - p_first) : np - 1;
+        for (int e = tid; e < np * F; e += FTILE) xfs[(e / F) * FMAXF + e % F] = __ldg(p.feat + (p_first + e / F) * F + e % F) * p.scale + p.offset;
         {   // ---- spline adjoint -> d_st: A operand (tensor memory) + row-major tile --------------------------------------
             float dst[N4], lo[N4];
 #pragma unroll
@@ -431,16 +437,19 @@ __global__ void __launch_bounds__(FTILE, 1) flow_block_bwd_tc_kernel(FlowTcBwdPa
             }
         }
         __syncthreads();                                                // Sp complete
+        // feature part: d_feat[p][k] += scale sum_j W1[j][7 + k] S[lp][j] (threads <-> (point, k));  dW1[j][7 + k] += S[lp][j] xf[lp][k]
+        // (threads <-> j: every accumulator row has one owner, no atomics)
         for (int e = tid; e < np * F; e += FTILE) {
             const int l = e / F, k = e % F;
-            const float xf = __ldg(p.feat + (p_first + l) * F + k) * p.scale + p.offset;
             float g = 0.f;
-            for (int j = 0; j < FH; ++j) {
-                const float sj = Sp[l * FH + j];
-                g = fmaf(__ldg(p.W1 + (size_t)j * KW1 + FPE + k), sj, g);
-                atomicAdd(&aW1b[j * FMAXF + k], sj * xf);
-            }
+            for (int j = 0; j < FH; ++j) g = fmaf(w1b[j * FMAXF + k], Sp[l * FH + j], g);
             atomicAdd(p.d_feat + (p_first + l) * F + k, g * p.scale);
+        }
+        if (tid < FH) {
+            for (int l = 0; l < np; ++l) {
+                const float sj = Sp[l * FH + tid];
+                for (int k = 0; k < F; ++k) aW1b[tid * FMAXF + k] = fmaf(sj, xfs[l * FMAXF + k], aW1b[tid * FMAXF + k]);
+            }
         }
         tc::fence_before_sync();
         __syncthreads();
@@ -466,11 +475,11 @@ __global__ void __launch_bounds__(FTILE, 1) flow_block_bwd_tc_kernel(FlowTcBwdPa
 
 size_t flow_tc_bwd_smem() {
     return sizeof(float) * (size_t)(2 * FH * N4 + 4 * FH * FH + 2 * K1 * FH + FH * 8 + FH * FMAXF + 2 * FH * FH + FSTP * FH + 3 * FH + FSTP +
-                                    2 * FTILE * FLD + FMAXP * FH + FTILE + 4) + 1024;
+                                    2 * FTILE * FLD + FMAXP * FH + FTILE + FH * FMAXF + FMAXP * FMAXF + 4) + 1024;
 }
 
 size_t flow_tc_smem() {
-    return sizeof(float) * (size_t)(2 * FH * K1 + 4 * FH * FH + 2 * N4 * FH + 3 * FH + N4 + FMAXP * FH + 4) + 1024;
+    return sizeof(float) * (size_t)(2 * FH * K1 + 4 * FH * FH + 2 * N4 * FH + 3 * FH + N4 + FMAXP * FH + FMAXF * FH + FMAXP * FMAXF + 4) + 1024;
 }
 
 }  // namespace
