@@ -90,9 +90,15 @@ class ClockSampler:
 
 def profiled_traffic(kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the committed `ncu --set full` summary
-    (profiles/r1_<kernel>_ncu_full_summary.txt; the capture's launch is one 4 GiB-workspace slice, the same size as the bench's)."""
-    path = os.path.join(ROOT, "profiles", f"r1_{kernel.replace('sdf_', '')}_ncu_full_summary.txt")
-    if not os.path.exists(path):
+    (profiles/r<round>_<kernel>_ncu_full_summary.txt, newest round first; the capture's launch is one 4 GiB-workspace slice of
+    this same command, the same size as the bench's)."""
+    path = None
+    for rnd in ("r2", "r1"):
+        cand = os.path.join(ROOT, "profiles", f"{rnd}_{kernel.replace('sdf_', '')}_ncu_full_summary.txt")
+        if os.path.exists(cand):
+            path = cand
+            break
+    if path is None:
         return None
     tot, scale = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
     for line in open(path):

@@ -64,34 +64,40 @@ struct EncParams {
 };
 constexpr int LD_IL = 128, LD_IW = 96;
 
+constexpr int ENC_TS = 129;      // row stride of the per-warp staging tile (conflict-free row writes and row reads)
+
+// rows [base, base + 32) x ncols of the warp's staging tile -> global rows of ld floats at column col0 (coalesced: lane = column)
+__device__ __forceinline__ void warp_store_rows(const float* tile, float* __restrict__ dst, int ld, int col0, int ncols, int64_t base, int64_t n, int lane) {
+    for (int r = 0; r < 32 && base + r < n; ++r)
+        for (int c = lane; c < ncols; c += 32) dst[(base + r) * ld + col0 + c] = tile[r * ENC_TS + c];
+}
+
 __global__ void __launch_bounds__(128) shader_encode_fwd_kernel(EncParams p) {
+    extern __shared__ float enc_sm[];
     __shared__ float s_mat[IDE_NP * IDE_N];
     __shared__ float s_sig[IDE_N];
     __shared__ int s_m[IDE_N];
     for (int i = threadIdx.x; i < IDE_NP * IDE_N; i += blockDim.x) s_mat[i] = p.ide.mat[i];
     for (int i = threadIdx.x; i < IDE_N; i += blockDim.x) { s_m[i] = p.ide.m[i]; s_sig[i] = p.ide.sigma[i]; }
     __syncthreads();
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= p.n) return;
-    const Geo g = shader_geo(p.normals, p.view, p.mat, i);
-    const V3 pt = ld3(p.points, i);
-    p.nrm[i * 3] = g.n.x; p.nrm[i * 3 + 1] = g.n.y; p.nrm[i * 3 + 2] = g.n.z;
-    p.vdir[i * 3] = g.v.x; p.vdir[i * 3 + 1] = g.v.y; p.vdir[i * 3 + 2] = g.v.z;
-    p.refl[i * 3] = g.r.x; p.refl[i * 3 + 1] = g.r.y; p.refl[i * 3 + 2] = g.r.z;
-    p.nov[i] = g.nov;
-    p.rough[i] = g.rough;
-    if (p.X_rad) {                                   // [features | points | PE(view, 4) | normals | 0]
-        float* x = p.X_rad + i * p.ld_rad;
-        const float4* f4 = reinterpret_cast<const float4*>(p.feat + i * p.fd);
-        for (int c = 0; c < p.fd / 4; ++c) reinterpret_cast<float4*>(x)[c] = f4[c];
-        x += p.fd;
-        x[0] = pt.x; x[1] = pt.y; x[2] = pt.z;
-        posenc3(x + 3, g.v, PE_VIEW);
-        x[3 + 27] = g.n.x; x[3 + 28] = g.n.y; x[3 + 29] = g.n.z;
-        for (int c = p.fd + 33; c < p.ld_rad; ++c) p.X_rad[i * p.ld_rad + c] = 0.f;
-    }
-    {   // [PE(points, 8) | IDE(mirror direction, roughness) | 0]
-        float* x = p.X_il + i * LD_IL;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* tile = enc_sm + warp * 32 * ENC_TS;
+    float* x = tile + lane * ENC_TS;                 // this sample's staging row
+    const int64_t base = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) - lane;
+    const int64_t i = base + lane;
+    if (base >= p.n) return;
+    const bool live = i < p.n;
+    Geo g;
+    V3 pt = v3(0.f, 0.f, 0.f);
+    if (live) {
+        g = shader_geo(p.normals, p.view, p.mat, i);
+        pt = ld3(p.points, i);
+        p.nrm[i * 3] = g.n.x; p.nrm[i * 3 + 1] = g.n.y; p.nrm[i * 3 + 2] = g.n.z;
+        p.vdir[i * 3] = g.v.x; p.vdir[i * 3 + 1] = g.v.y; p.vdir[i * 3 + 2] = g.v.z;
+        p.refl[i * 3] = g.r.x; p.refl[i * 3 + 1] = g.r.y; p.refl[i * 3 + 2] = g.r.z;
+        p.nov[i] = g.nov;
+        p.rough[i] = g.rough;
+        // ---- [PE(points, 8) | IDE(mirror direction, roughness) | 0] into the staging row -------------------------------
         posenc3(x, pt, PE_PTS);
         float zk[IDE_NP], re[IDE_NP], im[IDE_NP];
         zk[0] = 1.f; re[0] = 1.f; im[0] = 0.f;
@@ -114,11 +120,32 @@ __global__ void __launch_bounds__(128) shader_encode_fwd_kernel(EncParams p) {
             x[51 + IDE_N + j] = imm * att;
         }
         for (int c = 51 + 2 * IDE_N; c < LD_IL; ++c) x[c] = 0.f;
-        float* w = p.X_iw + i * LD_IW;
-#pragma unroll
-        for (int c = 0; c < 51; ++c) w[c] = x[c];
-        posenc3(w + 51, g.r, PE_REFL);
-        for (int c = 51 + 39; c < LD_IW; ++c) w[c] = 0.f;
+    }
+    __syncwarp();
+    warp_store_rows(tile, p.X_il, LD_IL, 0, LD_IL, base, p.n, lane);
+    __syncwarp();
+    if (live) {                                     // [PE(points, 8) (kept) | PE(mirror direction, 6) | 0]
+        posenc3(x + 51, g.r, PE_REFL);
+        for (int c = 51 + 39; c < LD_IW; ++c) x[c] = 0.f;
+    }
+    __syncwarp();
+    warp_store_rows(tile, p.X_iw, LD_IW, 0, LD_IW, base, p.n, lane);
+    if (p.X_rad) {                                  // [features | points | PE(view, 4) | normals | 0]
+        for (int r = 0; r < 32 && base + r < p.n; ++r) {
+            const float4* src = reinterpret_cast<const float4*>(p.feat + (base + r) * p.fd);
+            float4* dst = reinterpret_cast<float4*>(p.X_rad + (base + r) * p.ld_rad);
+            for (int c = lane; c < p.fd / 4; c += 32) dst[c] = __ldg(src + c);
+        }
+        __syncwarp();
+        const int tail = p.ld_rad - p.fd;
+        if (live) {
+            x[0] = pt.x; x[1] = pt.y; x[2] = pt.z;
+            posenc3(x + 3, g.v, PE_VIEW);
+            x[30] = g.n.x; x[31] = g.n.y; x[32] = g.n.z;
+            for (int c = 33; c < tail; ++c) x[c] = 0.f;
+        }
+        __syncwarp();
+        warp_store_rows(tile, p.X_rad, p.ld_rad, p.fd, tail, base, p.n, lane);
     }
 }
 
@@ -321,7 +348,10 @@ extern "C" TF_API int tf_shader_encode_fwd(const float* points, const float* nor
     TF_REQUIRE(!X_rad || (feat && feat_dim > 0 && feat_dim % 4 == 0 && ld_rad >= feat_dim + 33 && ((uintptr_t)feat & 15) == 0 && ld_rad % 4 == 0),
                "tf_shader_encode_fwd: radiance input needs features (feat_dim %% 4 == 0, 16-byte aligned) and ld_rad >= feat_dim + 33");
     EncParams p = {points, normals, view_dirs, mat, feat, feat_dim, ld_rad, n, {ide_mat, ide_m, ide_sigma}, nrm, vdir, refl, nov, rough, X_rad, X_il, X_iw};
-    shader_encode_fwd_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(p);
+    TF_REQUIRE(!X_rad || ld_rad - feat_dim <= 128, "tf_shader_encode_fwd: ld_rad - feat_dim must be <= 128");
+    const size_t smem = (size_t)4 * 32 * ENC_TS * sizeof(float);
+    cudaFuncSetAttribute(shader_encode_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    shader_encode_fwd_kernel<<<(unsigned)((n + 127) / 128), 128, smem, (cudaStream_t)stream>>>(p);
     tf_count_launches(1);
     TF_CHECK_LAUNCH("tf_shader_encode_fwd");
     return 0;
