@@ -111,8 +111,11 @@ def main():
 
     def run(sl, allreduce):
         """fwd + bwd of the joint step over the rays / points of `sl`, micro-batched; losses normalised by GLOBAL counts."""
-        for p in params:
-            p.grad = None
+        if allreduce:
+            bucket.begin_step()        # the flat buffer is the gradient storage: the first micro-batch's kernels scatter into its views,
+        else:                          # the following ones accumulate in place
+            for p in params:
+                p.grad = None
         # pass 0: global sample count for the eikonal mean (uniform sampling: the count is known before the forward)
         n_loc = torch.zeros(1, device=dev)
         chunks = [slice(a, min(a + args.micro, sl.stop)) for a in range(sl.start, sl.stop, args.micro)]
@@ -137,7 +140,8 @@ def main():
             loss.backward()
             total += loss.detach()
         if allreduce:
-            bucket.allreduce()
+            bucket.allreduce(async_op=True)
+            bucket.finish()
             if world > 1:
                 dist.all_reduce(total)              # reported loss = the full batch's
         return total
