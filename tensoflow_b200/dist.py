@@ -50,18 +50,22 @@ class FlatGradBucket:
 
     def __init__(self, params: Iterable[torch.nn.Parameter]):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
-        self.numel = sum(p.numel() for p in self.params)
+        # every segment starts on a 256-byte boundary: the kernels scatter into the views with 16-byte vector reductions
+        align = 64
+        offs, off = [], 0
+        for p in self.params:
+            offs.append(off)
+            off += (p.numel() + align - 1) // align * align
+        self.numel = off
         dev = self.params[0].device
         self.flat = torch.zeros(self.numel, device=dev, dtype=torch.float32)
         self.views: List[torch.Tensor] = []
         self._by_ptr = {}
-        off = 0
-        for i, p in enumerate(self.params):
+        for i, (p, off) in enumerate(zip(self.params, offs)):
             n = p.numel()
             seg = self.flat[off:off + n]
             self.views.append(seg.as_strided(p.shape, p.stride()) if _dense(p) else seg.view(p.shape))
             self._by_ptr[p.data_ptr()] = i
-            off += n
         self._handed = set()
         self._work = None
         self._average = False

@@ -113,6 +113,8 @@ def _worker_untouched(rank, world, port, q):
     a = torch.nn.Parameter(torch.randn(5))
     b = torch.nn.Parameter(torch.randn(3))           # only rank 0's shard reaches it (e.g. inner_light without occluded directions)
     bucket = FlatGradBucket([a, b])
+    # 5- and 3-element parameters: every view still starts on a 256-byte boundary of the flat buffer (vector reductions of the kernels)
+    assert all((v.data_ptr() - bucket.flat.data_ptr()) % 256 == 0 for v in bucket.views)
     outs = []
     for step in range(2):                            # twice: the views of step 1 must not leak into step 2
         bucket.begin_step()

@@ -341,3 +341,122 @@ def test_material_renderer_train_step_matches_oracle():
                 close(p.grad, o32["grads"][n], o64["grads"][n], 1e-3, f"d {n}")
                 checked += 1
         assert checked > 60
+
+
+def test_bvh_trace_million_triangle_mesh():
+    """BASELINE config 3's mesh size: the 1 M-triangle bumpy sphere of scripts/bench_material.py.  Closest hits of the BVH kernel
+    against fp64 brute force over ALL triangles (Moeller-Trumbore on the device, in triangle chunks) for 1500 rays: hit / miss,
+    depth, position, and the face normal of the reported triangle."""
+    from tensoflow_b200.mc_ops import RayTracer
+    from tensoflow_b200.synthetic import bumpy_sphere as big_sphere
+    dev = _cuda()
+    verts, tris = big_sphere(1000, 501)
+    assert tris.shape[0] == 1_000_000
+    rt = RayTracer(verts, tris)
+    g = torch.Generator().manual_seed(3)
+    n = 1500
+    o = F.normalize(torch.randn(n, 3, generator=g), dim=-1) * 1.5
+    d = F.normalize(torch.randn(n, 3, generator=g) * 0.3 - o, dim=-1)
+    o[: n // 5] = F.normalize(torch.randn(n // 5, 3, generator=g), dim=-1) * 0.2            # rays starting inside the mesh
+    pos, nrm, depth = rt.trace(o.to(dev), d.to(dev))
+    # brute force in fp64 on the device, 50 k triangles at a time
+    vd, td = verts.to(dev).double(), tris.to(dev).long()
+    od, dd = o.to(dev).double(), d.to(dev).double()
+    best = torch.full((n,), float("inf"), dtype=torch.float64, device=dev)
+    for t0 in range(0, td.shape[0], 50_000):
+        tt = td[t0:t0 + 50_000]
+        v0, e1, e2 = vd[tt[:, 0]], vd[tt[:, 1]] - vd[tt[:, 0]], vd[tt[:, 2]] - vd[tt[:, 0]]
+        p = torch.cross(dd[:, None, :].expand(-1, tt.shape[0], -1), e2[None].expand(n, -1, -1), dim=-1)
+        det = (e1[None] * p).sum(-1)
+        ok = det.abs() > 1e-14
+        idet = 1.0 / torch.where(ok, det, torch.ones_like(det))
+        s = od[:, None, :] - v0[None]
+        u = (s * p).sum(-1) * idet
+        q = torch.cross(s, e1[None].expand_as(s), dim=-1)
+        v = (dd[:, None, :] * q).sum(-1) * idet
+        t = (e2[None] * q).sum(-1) * idet
+        ok = ok & (u >= 0) & (u <= 1) & (v >= 0) & (u + v <= 1) & (t > 0)
+        best = torch.minimum(best, torch.where(ok, t, torch.full_like(t, float("inf"))).min(-1).values)
+    hit = torch.isfinite(best)
+    got_hit = depth < 10
+    # a ray through a shared edge / vertex can be won or lost by an ulp of the fp32 barycentrics: allow a handful of flips
+    assert int((hit != got_hit).sum()) <= 3, int((hit != got_hit).sum())
+    both = hit & got_hit
+    assert float(both.float().mean()) > 0.3
+    assert rel_err(depth[both], best[both]) < 1e-4
+    assert rel_err(pos[both], (od + best[:, None] * dd)[both]) < 1e-4
+    assert float((depth[~got_hit] - 10.0).abs().max()) == 0.0
+
+
+def test_material_stage_parity_at_bench_scale():
+    """The configuration scripts/bench_material.py measures (BASELINE config 3: 512^2 x 36 material planes, 512^2 x 12 flow planes,
+    128^2 environment cubemap, 512 cosine + 64 + 32 flow-sampled directions, NIS losses on) against a 125 k-triangle mesh, at a point
+    count the fp64 oracle finishes in seconds: outputs, both NIS losses and every parameter gradient.  The oracle traces through the
+    SAME BVH (wrapped), so hit / miss decisions can only differ by the fp32 / fp64 ray origins."""
+    from tensoflow_b200.material import MaterialRenderer
+    from tensoflow_b200.synthetic import bumpy_sphere as big_sphere
+    dev = _cuda()
+    torch.manual_seed(7)
+    verts, tris = big_sphere(250, 251)
+    assert tris.shape[0] >= 100_000
+    pn = 192
+    cfg = dict(train_ray_num=pn, device=dev, gridSize=[512] * 3,
+               shader_cfg=dict(diffuse_sample_num=512, specular_sample_num=256, nis_diffuse_sample_num=64, nis_specular_sample_num=32,
+                               light_reso=128, gridSize=[512] * 3, mat_grid=512))
+    r = MaterialRenderer(cfg, verts, tris)
+    sh = r.shader_network
+    with torch.no_grad():
+        for p in list(sh.mat_plane) + list(sh.flow_diffuse.parameters()) + list(sh.flow_specular.parameters()):
+            if p.dim() == 4:
+                p.add_(1e-2 * torch.randn_like(p))
+        sh.outer_light.base.add_(0.5 * torch.randn_like(sh.outer_light.base))
+    step = 2000
+    sh.update_step(step)
+    sh.use_flow_diffuse_copy = sh.use_flow_specular_copy = True
+    gen = torch.Generator().manual_seed(8)
+    idx = torch.randint(0, verts.shape[0], (pn,), generator=gen)
+    pts = verts[idx] * 1.001
+    normals = F.normalize(pts, dim=-1)
+    cams = F.normalize(torch.randn(pn, 3, generator=gen) + 2 * normals, dim=-1) * 2.0
+    view = -F.normalize(pts - cams, dim=-1)
+    noise = dict(az_diffuse=torch.rand(pn, 1, 1, generator=gen), az_specular=torch.rand(pn, 1, 1, generator=gen),
+                 phi_diffuse=torch.rand(pn, 64, 1, generator=gen), phi_specular=torch.rand(pn, 32, 1, generator=gen))
+    u_rgb = torch.randn(pn, 3, generator=gen)
+
+    def cpu_tracer(o, d):
+        res = r.tracer(o.to(dev).float(), d.to(dev).float())
+        return tuple(t.cpu().to(o.dtype) if t.dtype.is_floating_point else t.cpu() for t in res)
+
+    def run_oracle(dt):
+        o = MC.MCShadingNetwork(cpu_tracer, torch.tensor([[-1., -1, -1], [1, 1, 1]]), gridSize=(512, 512, 512), flow_grid=(512, 512, 512),
+                                light_reso=128, dtype=dt)
+        res = o.load_state_dict({k: v.detach().cpu().to(dt) for k, v in sh.state_dict().items()}, strict=False)
+        assert not [k for k in res.missing_keys if "copy" not in k and "direction_samples" not in k], res.missing_keys
+        rgb, out = o(pts.to(dt), view.to(dt), normals.to(dt), {k: v.to(dt) for k, v in noise.items()}, step)
+        ((rgb * u_rgb.to(dt)).sum() + 100.0 * out["loss_nis"]).backward()
+        return rgb, out, {n: p.grad for n, p in o.named_parameters() if p.grad is not None}
+
+    rgb64, out64, g64 = run_oracle(torch.float64)
+    rgb32, out32, g32 = run_oracle(torch.float32)
+    sh.train()
+    rgb, out = sh(pts.to(dev), view.to(dev), normals.to(dev), None, step, True, noise={k: v.to(dev) for k, v in noise.items()})
+    ((rgb * u_rgb.to(dev)).sum() + 100.0 * out["loss_nis"]).backward()
+
+    def close(got, b32, b64, tol, what):
+        e, e_ref = rel_err(got, b64), rel_err(b32, b64)
+        assert e <= max(tol, 4 * e_ref), f"{what}: rel err {e:.3e} (fp32 oracle vs fp64 oracle {e_ref:.3e})"
+
+    ok = (rgb.detach().cpu().double() - rgb64).abs().max(-1).values <= 1e-3          # points whose occlusion rays agree on hit / miss
+    assert float(ok.float().mean()) > 0.95, float(ok.float().mean())
+    close(rgb.detach().cpu()[ok], rgb32[ok], rgb64[ok], 1e-4, "rgb")
+    for k in ("albedo", "roughness", "metallic", "diffuse_light", "specular_light", "visibility"):
+        close(out[k].detach().cpu()[ok], out32[k][ok], out64[k][ok], 1e-4, k)
+    if bool(ok.all()):
+        close(out["loss_nis_diffuse"], out32["loss_nis_diffuse"], out64["loss_nis_diffuse"], 1e-4, "loss_nis_diffuse")
+        close(out["loss_nis_specular"], out32["loss_nis_specular"], out64["loss_nis_specular"], 1e-4, "loss_nis_specular")
+        checked = 0
+        for n_, p in sh.named_parameters():
+            if p.requires_grad and p.grad is not None and n_ in g64:
+                close(p.grad, g32[n_], g64[n_], 1e-3, f"d {n_}")
+                checked += 1
+        assert checked > 60
