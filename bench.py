@@ -232,6 +232,32 @@ def secondary_lines():
     return out
 
 
+def config1_line(dev, steps):
+    """BASELINE.json configs[0] (the reference's CPU-runnable case): VM field 128^3, 48 feature components (C = 16), H = 128,
+    4096 rays x 128 samples, fwd + bwd, device-resident rays, CUDA events."""
+    from tensoflow_b200 import synthetic
+    cfg = dict(G=128, C=16, H=128, A=128, L=1, rays=4096, samples=128)
+    field, variance = build_shape(cfg, dev)
+    params = list(field.parameters()) + [variance]
+    rays = [synthetic.make_rays(cfg["rays"], seed=50 + b, device=dev) for b in range(2)]
+    for i in range(3):
+        for p in params:
+            p.grad = None
+        shape_step(field, variance, rays[i % 2], cfg)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(steps):
+        for p in params:
+            p.grad = None
+        shape_step(field, variance, rays[i % 2], cfg)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    return {"metric": "train rays/sec (fwd+bwd)", "value": cfg["rays"] / (ms / 1e3), "unit": "rays/s", "ms_per_step": ms,
+            "config": {"workload": workload_name(cfg)}}
+
+
 def workload_name(cfg):
     return (f"shape stage: TensoSDF VM field {cfg['G']}^3 (C={cfg['C']}, H={cfg['H']}, A={cfg['A']}, {cfg['L']} mip levels), "
             f"{cfg['rays']}-ray batch x {cfg['samples']} samples, fwd+bwd")
@@ -393,6 +419,15 @@ def run_ours(args):
 
     ms_e2e, _, _, _, _ = timed(step_e2e, False)
 
+    # ---- config 4 (joint shape + material step, strong scaling over the same ranks), so that it is in the driver's record ----
+    joint = None
+    if world > 1 and not args.no_secondary:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "scripts"))
+            import bench_joint
+            joint = bench_joint.run_joint(bench_joint.parse_args([]), own_process_group=False)
+        except Exception as e:  # noqa: BLE001
+            joint = {"metric": "joint shape+material train rays/sec (fwd+bwd)", "error": repr(e)[:300]} if rank == 0 else None
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -433,7 +468,12 @@ def run_ours(args):
                "sample": f"oracle port, {args.ref_rays} of {cfg['rays']} rays x {cfg['samples']} samples, fwd+bwd, "
                          f"{len(times)} timed step after 1 warm-up step ({times[0]:.1f} s)"}
     check = parity_check(field, variance, cfg, dev, args.check_rays) if (world == 1 and args.check_rays > 0) else None
-    secondary = secondary_lines() if (world == 1 and not args.no_secondary) else None
+    secondary = None
+    if world == 1 and not args.no_secondary:
+        secondary = secondary_lines()
+        secondary["config1_128cube_4096x128"] = config1_line(dev, args.steps)
+    if joint is not None:
+        secondary = {"joint_config4": {k: joint[k] for k in ("metric", "value", "unit", "ms_per_step", "n_gpus", "scaling", "config") if k in joint}}
     line = {
         "metric": "train rays/sec (fwd+bwd)", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",

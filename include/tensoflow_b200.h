@@ -114,6 +114,12 @@ TF_API int tf_sdf_only_fwd(const tf_vm_field_t* f, const tf_sdf_mlp_t* m, const 
                     const float* level, int64_t n, float* sdf, void* workspace, size_t ws_bytes,
                     tf_stream_t stream);
 
+/* One query per point WITH the appearance features: sdf[n], feat[n, app_dim] = TensoSDF.forward (network/fields.py:262-299)
+ * without the six finite-difference taps (forward only: inference, probes).  Workspace as tf_sdf_stencil_fwd_workspace(.., 1).
+ * Needs the tensor-core path (hidden % 32 == 0, hidden <= 256); otherwise an error is returned and tf_sdf_stencil_fwd applies. */
+TF_API int tf_sdf_point_fwd(const tf_vm_field_t* f, const tf_sdf_mlp_t* m, const float* xyz, const float* level,
+                            int64_t n, float* sdf, float* feat, void* workspace, size_t ws_bytes, tf_stream_t stream);
+
 /* Backward of tf_sdf_stencil_fwd.  g_sdf[n], g_feat[n,A], g_grad[n,3], g_hess[n] are the
  * upstream gradients (each may be NULL = zero); sdf7 is the forward output.
  * Any workspace size >= tf_sdf_stencil_bwd_workspace(.., 1) works; larger is faster

@@ -76,7 +76,7 @@ def build(args, dev):
     return cfg, field, variance, mr, verts, make_batch
 
 
-def main():
+def parse_args(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--rays", type=int, default=65536)
     ap.add_argument("--samples", type=int, default=512)
@@ -89,14 +89,25 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--check", action="store_true")
-    args = ap.parse_args()
+    return ap.parse_args(argv)
+
+
+def main():
+    line = run_joint(parse_args(), own_process_group=True)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def run_joint(args, own_process_group=True):
+    """One measurement of the joint step; returns the JSON line (a dict) on rank 0, None elsewhere.  With
+    own_process_group=False the caller (bench.py under torchrun) has initialised torch.distributed already."""
     if args.check:
         args.rays, args.samples, args.micro, args.grid, args.mat_grid = 512, 48, 128, 64, 32
         args.tris_u, args.tris_v, args.diffuse = 64, 33, 64
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
+    if world > 1 and own_process_group:
         dist.init_process_group("nccl", device_id=dev)
     from tensoflow_b200 import _lib, synthetic
     from tensoflow_b200.dist import FlatGradBucket, shard_slice
@@ -168,7 +179,7 @@ def main():
             print(json.dumps({"check": "sharded + allreduced gradients vs single-GPU full batch", "n_gpus": world, "rays": R,
                               "max_rel_err": float(t), "worst_param": name, "n_params": len(params), "tol": 1e-3,
                               "ok": bool(float(t) < 1e-3)}), flush=True)
-        if world > 1:
+        if world > 1 and own_process_group:
             dist.destroy_process_group()
         sys.exit(0 if float(t) < 1e-3 else 1)
 
@@ -191,17 +202,19 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t) / args.steps
+    line = None
     if rank == 0:
-        print(json.dumps({
+        line = ({
             "metric": "joint shape+material train rays/sec (fwd+bwd)", "value": R / (ms / 1e3), "unit": "rays/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "scaling": "strong", "higher_is_better": True,
             "config": {"workload": f"joint step: {R} rays x {cfg['samples']} samples (VM field {cfg['G']}^3, C={cfg['C']}, H={cfg['H']}) + "
                                    f"{R} surface points x ({args.diffuse}+64+32) directions vs {2 * args.tris_u * (args.tris_v - 1)} triangles, "
                                    f"{R // world} rays+points per GPU in micro-batches of {args.micro}",
                        "parallelism": f"dp{world}: ray / point slices, one flat fp32 allreduce of {bucket.numel * 4 / 1e6:.0f} MB"},
-            "gpu_launches_per_step": (_lib.launch_count() - l0) / args.steps, "loss": float(loss)}), flush=True)
-    if world > 1:
+            "gpu_launches_per_step": (_lib.launch_count() - l0) / args.steps, "loss": float(loss)})
+    if world > 1 and own_process_group:
         dist.destroy_process_group()
+    return line
 
 
 if __name__ == "__main__":

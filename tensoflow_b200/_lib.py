@@ -52,6 +52,7 @@ _SIGNATURES = {
                                      C.POINTER(C.c_float), _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "tf_sdf_only_fwd": (C.c_int, [C.POINTER(VMField), C.POINTER(SdfMlp), _P, _P, C.c_int64, _P, _P,
                                   C.c_size_t, _P]),
+    "tf_sdf_point_fwd": (C.c_int, [C.POINTER(VMField), C.POINTER(SdfMlp), _P, _P, C.c_int64, _P, _P, _P, C.c_size_t, _P]),
     "tf_sdf_stencil_bwd_workspace": (C.c_size_t, [C.POINTER(VMField), C.POINTER(SdfMlp), C.c_int64]),
     "tf_sdf_stencil_bwd": (C.c_int, [C.POINTER(VMField), C.POINTER(SdfMlp), _P, _P, C.c_int64,
                                      C.POINTER(C.c_float), _P, _P, _P, _P, _P, C.POINTER(VMMut),

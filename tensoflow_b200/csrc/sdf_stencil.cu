@@ -574,6 +574,18 @@ extern "C" TF_API int tf_sdf_only_fwd(const tf_vm_field_t* f, const tf_sdf_mlp_t
     return stencil_fwd_impl(1, f, m, xyz, level, n, nullptr, nullptr, nullptr, nullptr, nullptr, sdf, workspace, ws_bytes, stream);
 }
 
+// one query per point with the appearance features (TensoSDF.forward, network/fields.py:262-299, without the FD taps)
+extern "C" TF_API int tf_sdf_point_fwd(const tf_vm_field_t* f, const tf_sdf_mlp_t* m, const float* xyz, const float* level, int64_t n,
+                                       float* sdf, float* feat, void* workspace, size_t ws_bytes, tf_stream_t stream) {
+    Dims d;
+    if (!f || !m) { tf_set_error("tf_sdf_point_fwd: NULL descriptor"); return 1; }
+    if (int e = check_mlp(f, m, d)) return e;
+    TF_REQUIRE(feat, "tf_sdf_point_fwd: feat is NULL (use tf_sdf_only_fwd for the SDF alone)");
+    TF_REQUIRE(!use_simt_path(d), "tf_sdf_point_fwd: only the tensor-core path evaluates single queries with features "
+                                  "(hidden %% 32 == 0, hidden <= 256); use tf_sdf_stencil_fwd");
+    return stencil_fwd_impl(1, f, m, xyz, level, n, nullptr, nullptr, feat, nullptr, nullptr, sdf, workspace, ws_bytes, stream);
+}
+
 static size_t bwd_slice_floats(const Dims& d, int64_t n_slice) {
     const int64_t tiles = (n_slice + TS - 1) / TS;
     return (size_t)tiles * ((size_t)R * d.H + (size_t)R * d.KP + (size_t)TS * d.H);

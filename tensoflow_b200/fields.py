@@ -127,6 +127,12 @@ class TensoSDF(nn.Module):
 
     def forward(self, xyz_sampled, level_vol):
         """reference fields.py:262-299 -> [N, 1+app_dim]"""
+        if not (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())):
+            # no gradient wanted: one query per point (the stencil would evaluate and discard the six FD taps)
+            out = ops.sdf_point(xyz_sampled, level_vol, self.aabb, self.n_levels, self.sdf_mat[0].weight, self.sdf_mat[0].bias,
+                                self.sdf_mat[2].weight, self.sdf_mat[2].bias, list(self.sdf_plane), list(self.sdf_line))
+            if out is not None:
+                return torch.cat([out[0][:, None], out[1]], -1)
         sdf, feat, _, _ = self.stencil(xyz_sampled.reshape(-1, 3), level_vol)
         return torch.cat([sdf[:, None], feat], -1)
 

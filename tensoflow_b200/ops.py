@@ -310,6 +310,31 @@ def sdf_only(xyz, level, aabb, n_levels, W0, b0, W1, b1, planes, lines) -> torch
     return out
 
 
+def sdf_point(xyz, level, aabb, n_levels, W0, b0, W1, b1, planes, lines):
+    """TensoSDF.forward (reference network/fields.py:262-299) without autograd and without the FD taps -> (sdf [N], feat [N,A]);
+    None when the decoder shape is outside the tensor-core path (the caller then uses the stencil)."""
+    lib = _lib.load()
+    H = int(W0.shape[0])
+    if H % 32 != 0 or H > 256 or __import__('os').environ.get('TF_STENCIL_SIMT') == '1':
+        return None
+    xyz_c = _f32c(xyz.reshape(-1, 3))
+    lvl_c = None if level is None else _f32c(level.reshape(-1))
+    n = xyz_c.shape[0]
+    vm = vm_desc(planes, lines, aabb, n_levels, lvl_c is not None)
+    m, keep = _mlp_desc(W0, b0, W1, b1)
+    sdf = torch.empty(n, device=xyz_c.device, dtype=torch.float32)
+    feat = torch.empty(n, m.app_dim, device=xyz_c.device, dtype=torch.float32)
+    if n == 0:
+        return sdf, feat
+    wsb = lib.tf_sdf_stencil_fwd_workspace(C.byref(vm.c), C.byref(m), n, 1)
+    if wsb == 0:
+        check(1, "tf_sdf_stencil_fwd_workspace")
+    ws = torch.empty(wsb // 4, device=xyz_c.device, dtype=torch.float32)
+    check(lib.tf_sdf_point_fwd(C.byref(vm.c), C.byref(m), ptr(xyz_c), ptr(lvl_c), n, ptr(sdf), ptr(feat), ptr(ws), wsb, stream_ptr()),
+          "tf_sdf_point_fwd")
+    return sdf, feat
+
+
 class VMFeatureFunction(torch.autograd.Function):
     """feat[N,3C] = concat_i plane_i(x)*line_i(x) (reference network/fields.py:776-806,
     network/flow.py:709-740).  inputs: xyz, level|None, aabb, n_levels, plane0..2, line0..2."""
