@@ -6,11 +6,14 @@ raised.  The library is built in-tree by `python -m tensoflow_b200.build`.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 import torch
 
-_LIB_PATH = Path(__file__).resolve().parent / "libtensoflow_b200.so"
+# TENSOFLOW_B200_LIB: explicit path of the shared library (deployments that keep it outside the package directory;
+# scripts/stencil_phase_probe.py points it at the experiment build)
+_LIB_PATH = Path(os.environ.get("TENSOFLOW_B200_LIB") or Path(__file__).resolve().parent / "libtensoflow_b200.so")
 _lib = None
 
 

@@ -47,11 +47,20 @@ def _digest() -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
+def build(force: bool = False, verbose: bool = False, experiment: bool = False) -> Path:
+    """experiment=True builds libtensoflow_b200_exp.so with -DTF_TC_DEBUG_SWITCHES (phase-timing switches of the stencil
+    kernels; results are wrong by construction when a switch is on): only scripts/stencil_phase_probe.py loads it."""
     dig = _digest()
+    if experiment:
+        return _build_into(PKG / "libtensoflow_b200_exp.so", PKG / "build_exp", [*NVCC_FLAGS, "-DTF_TC_DEBUG_SWITCHES"], verbose)
     if not force and LIB.exists() and STAMP.exists() and STAMP.read_text().strip() == dig:
         return LIB
-    objdir = PKG / "build"
+    _build_into(LIB, PKG / "build", NVCC_FLAGS, verbose)
+    STAMP.write_text(dig)
+    return LIB
+
+
+def _build_into(LIB: Path, objdir: Path, NVCC_FLAGS, verbose: bool) -> Path:
     objdir.mkdir(exist_ok=True)
     nvcc = _nvcc()
     procs = []
@@ -73,7 +82,6 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         raise RuntimeError("nvcc failed")
     cmd = [nvcc, "-shared", "-o", str(LIB), *objs, "-lcudart"]
     subprocess.run(cmd, check=True)
-    STAMP.write_text(dig)
     return LIB
 
 
@@ -98,6 +106,6 @@ def build_probes(force: bool = False) -> Path | None:
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, experiment="--experiment" in sys.argv)
     print(path)
     print(build_probes(force="--force" in sys.argv))

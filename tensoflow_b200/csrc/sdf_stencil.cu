@@ -494,7 +494,7 @@ static bool use_simt_path(const Dims& d) {
     static int forced = -1;
     if (forced < 0) { const char* e = getenv("TF_STENCIL_SIMT"); forced = (e && e[0] == '1') ? 1 : 0; }
     const int KT = (d.K + 15) / 16 * 16;
-    return forced == 1 || tf_internal_tc_fwd_smem(KT, d.H) > 227 * 1024 || d.H > 256 || d.H % 32 != 0;
+    return forced == 1 || tf_internal_tc_fwd_smem(KT, d.H) > 227 * 1024 || KT > 128 || d.H > 256 || d.H % 32 != 0;
 }
 
 static size_t fwd_ws_floats(const Dims& d, int64_t n, bool with_feat) {

@@ -12,6 +12,7 @@
 // Hand-offs are mbarriers (A ready / GEMM1 done / dA ready / dA consumed); weight slices (W0 by 8 features for GEMM1,
 // W0^T by 16 hidden units for GEMM-dA) stream through one cp.async.bulk ring.  Weight gradients are finished by
 // X^T Y passes over the workspace (xty_tc.cu).
+#include <stdio.h>
 #include <stdlib.h>
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -22,10 +23,10 @@ namespace {
 constexpr int TM = 128;
 constexpr int NQ7 = 7;
 constexpr int KSL = 16;     // KT granularity (shared with the forward kernel)
-constexpr int KS1 = 16;     // K slice of GEMM1 streamed per ring slot
-constexpr int HHC = 32;     // hidden units of a W0^T ring slot (a whole chunk)
+constexpr int KS1 = 8;      // K slice of GEMM1 streamed per ring slot (one tf32 k-step)
+constexpr int HHC = 16;     // hidden units of a W0^T ring slot (half a chunk)
 constexpr int HCH = 32;     // hidden chunk of epilogue-1 / GEMM-dA
-constexpr int NST = 2;
+constexpr int NST = 4;      // ring stages (16 KB each) = issuing lanes
 constexpr int NGRP = 256;             // threads per group
 constexpr int NTH = 2 * NGRP;         // math group (warps 0-7) + memory group (warps 8-15)
 
@@ -46,6 +47,7 @@ struct TcBwdParams {
     float* spc;              // [n][H] centre hidden activations (NULL = not needed)
     float* dW1r0; float* db1;
 #ifdef TF_TC_DEBUG_SWITCHES
+    long long* prof;         // [3 roles][16] phase cycle totals of CTA 0 (TF_TC_BWD_PROF=1)
     int debug;               // timing experiments only (never compiled into the product library): 1 no gather, 2 no workspace stores,
                              // 4 no scatter, 8 no dW1 reduction, 16 no chunk loop
 #endif
@@ -53,8 +55,14 @@ struct TcBwdParams {
 
 #ifdef TF_TC_DEBUG_SWITCHES
 #define TF_DBG(p, bit) ((p).debug & (bit))
+#define PROF_DECL long long pt_[16] = {0}; long long pl_ = clock64();
+#define PROF(i) { const long long now_ = clock64(); pt_[i] += now_ - pl_; pl_ = now_; }
+#define PROF_DUMP(role) if (p.prof && blockIdx.x == 0) { for (int i_ = 0; i_ < 16; ++i_) p.prof[(role) * 16 + i_] = pt_[i_]; }
 #else
 #define TF_DBG(p, bit) 0
+#define PROF_DECL
+#define PROF(i)
+#define PROF_DUMP(role)
 #endif
 
 // slots 0..S-1        : W0 K-slices      [H rows x 8]   hi | lo   (GEMM1 B operand)
@@ -104,6 +112,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 
 __global__ void __launch_bounds__(NTH, 1) sdf_stencil_bwd_tc_kernel(TcBwdParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ site::LevelTab s_tab;
     const int H = p.H, KT = p.KT, S = KT / KS1, NCH = H / HCH, J = S + H / HHC;
     constexpr int SPT = site::SPT;
     const uint32_t a_part = site::a_part_bytes(KT);
@@ -143,6 +152,7 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_bwd_tc_kernel(TcBwdParams 
         *accb1 = 0.f;
     }
     for (int i = tid; i < H; i += NTH) { b0s[i] = p.b0[i]; w1s[i] = p.w1r0[i]; accw1[i] = 0.f; }
+    site::build_level_tab(p.f, &s_tab);
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
@@ -153,25 +163,31 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_bwd_tc_kernel(TcBwdParams 
         // the batched texel fetches want registers, the math group needs few: rebalance the 64K register file
         asm volatile("setmaxnreg.inc.sync.aligned.u32 160;");
         const int mtid = tid - NGRP;
+        PROF_DECL
         for (int64_t lt = 0; lt < my_tiles; ++lt) {
             const int64_t tile = blockIdx.x + lt * gridDim.x;
             if (lt > 0) tc::mbar_wait(dfull1, (uint32_t)((lt - 1) & 1));       // GEMM1 of the previous tile has consumed A
+            PROF(0)
             if (!TF_DBG(p, 1))
-                site::gather_tile_lean(p.f, p.xyz, p.level, p.n, p.units, tile * SPT, KT, a_hi, a_lo,
+                site::gather_tile_lean(p.f, s_tab, p.xyz, p.level, p.n, p.units, tile * SPT, KT, a_hi, a_lo,
                                   TF_DBG(p, 2) ? nullptr : p.arow + (size_t)tile * TM * KT, NGRP, mtid);
             tc::fence_async_smem();
             tc::mbar_arrive(aready);
+            PROF(1)
             if (lt > 0) {
                 tc::mbar_wait(daready, (uint32_t)((lt - 1) & 1));
+                PROF(2)
                 if (!TF_DBG(p, 4))
-                    site::scatter_tile_lean(p.f, p.g, p.xyz, p.level, p.n, p.units, (blockIdx.x + (lt - 1) * gridDim.x) * SPT, dAs, DAS, NGRP, mtid, true);
+                    site::scatter_tile_lean(p.f, s_tab, p.g, p.xyz, p.level, p.n, p.units, (blockIdx.x + (lt - 1) * gridDim.x) * SPT, dAs, DAS, NGRP, mtid, true);
                 tc::mbar_arrive(dafree);
+                PROF(3)
             }
         }
+        if (mtid == 0) { PROF_DUMP(2) }
         if (my_tiles > 0) {
             tc::mbar_wait(daready, (uint32_t)((my_tiles - 1) & 1));
             if (!TF_DBG(p, 4))
-                site::scatter_tile_lean(p.f, p.g, p.xyz, p.level, p.n, p.units, (blockIdx.x + (my_tiles - 1) * gridDim.x) * SPT, dAs, DAS, NGRP, mtid, true);
+                site::scatter_tile_lean(p.f, s_tab, p.g, p.xyz, p.level, p.n, p.units, (blockIdx.x + (my_tiles - 1) * gridDim.x) * SPT, dAs, DAS, NGRP, mtid, true);
         }
     } else {
         // ======================= math group: GEMM1, chunked dPre epilogue, GEMM-dA ======================================
@@ -184,72 +200,89 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_bwd_tc_kernel(TcBwdParams 
         const uint32_t a_sbo = site::a_sbo(KT), w1_sbo = (KS1 / 4) * 128, w2_sbo = (HHC / 4) * 128;
         const uint64_t a_desc_hi = tc::make_smem_desc(tc::smem_u32(a_hi), site::A_LBO, a_sbo), a_desc_lo = tc::make_smem_desc(tc::smem_u32(a_lo), site::A_LBO, a_sbo);
 
-        int64_t g_issue = 0, g_mma = 0;            // driver (thread 0): ring slot counters
+        int64_t g_mma = 0;                         // driver (thread 0): ring slot counter
         const int64_t total_slots = my_tiles * J;
         uint32_t cf_commits[2] = {0, 0};           // commits issued on cfree[buf] so far
-        auto ring_prefetch = [&]() {
-            while (g_issue < total_slots && g_issue < g_mma + NST) {
-                const int st = (int)(g_issue % NST);
-                tc::mbar_wait(&empty[st], (uint32_t)(((g_issue / NST) & 1) ^ 1));
-                mbar_expect_tx(&full[st], slot_bytes);
-                bulk_copy_g2s(wst + (size_t)st * slot_bytes, p.Wtc + (size_t)(g_issue % J) * p.slot_floats, slot_bytes, &full[st]);
-                ++g_issue;
+        // W ring refills: cp.async.bulk copies issued by ONE warp execute one after the other (~800-900 cycles each
+        // whatever their size: tests/probes/bulk_probe.cu), copies of different warps overlap.  So every ring stage has
+        // its own issuing lane (lane 0 of warps 4..7: stages 0..3) and the MMA thread only posts the byte count.  A slot is
+        // refilled NST slots ahead of the MMAs that consume it, at points where the MMAs that free its stage were issued
+        // at least one chunk earlier, so the issuing lanes (which are epilogue warps too) rarely wait.
+        const int fill_k = (lane == 0 && warp >= 4 && warp < 4 + NST) ? warp - 4 : -1;
+        int64_t g_fill = fill_k;                   // next slot of this issuer (slots g = k, k + NST, ...)
+        auto pump_to = [&](int64_t limit) {        // refill this issuer's slots below `limit`
+            if (fill_k < 0) return;
+            while (g_fill < limit && g_fill < total_slots) {
+                tc::mbar_wait(&empty[fill_k], (uint32_t)(((g_fill / NST) & 1) ^ 1));   // MMAs of slot g_fill - NST are complete
+                bulk_copy_g2s(wst + (size_t)fill_k * slot_bytes, p.Wtc + (size_t)(g_fill % J) * p.slot_floats, slot_bytes, &full[fill_k]);
+                g_fill += NST;
             }
         };
-        if (tid == 0) ring_prefetch();
+        pump_to(NST);
+        const float inv2e[3] = {1.f / (2.f * p.units[0]), 1.f / (2.f * p.units[1]), 1.f / (2.f * p.units[2])};
+        const float inve2[3] = {1.f / (p.units[0] * p.units[0]), 1.f / (p.units[1] * p.units[1]), 1.f / (p.units[2] * p.units[2])};
+        PROF_DECL
 
         for (int64_t lt = 0; lt < my_tiles; ++lt) {
             const int64_t tile = blockIdx.x + lt * gridDim.x;
             const int64_t s_base = tile * SPT;
             const int64_t tile_row0 = tile * TM;
             const uint32_t tpar = (uint32_t)(lt & 1);
-            // upstream gradients -> per-query SDF gradients of the tile's samples (adjoint of fields.py:245-256)
-            if (tid < SPT) {
-                const int64_t n = s_base + tid;
+            PROF(0)
+            // upstream gradients -> per-query SDF gradients of the tile's samples (adjoint of fields.py:245-256); done by warp 1
+            // while thread 0 (warp 0) already issues GEMM1: the HBM reads of this block are not on the MMA thread's path
+            if (tid >= 32 && tid < 32 + SPT) {
+                const int ts = tid - 32;
+                const int64_t n = s_base + ts;
                 float gq[NQ7];
 #pragma unroll
                 for (int r = 0; r < NQ7; ++r) gq[r] = 0.f;
                 if (n < p.n) {
-                    float sd[NQ7];
+                    float sd[NQ7], gg[3] = {0.f, 0.f, 0.f}, gh = 0.f, gs = 0.f;
 #pragma unroll
-                    for (int r = 0; r < NQ7; ++r) sd[r] = p.sdf7[n * NQ7 + r];
+                    for (int r = 0; r < NQ7; ++r) sd[r] = __ldg(p.sdf7 + n * NQ7 + r);      // all reads first: one round trip
+                    if (p.g_hess) gh = __ldg(p.g_hess + n);
+                    if (p.g_sdf) gs = __ldg(p.g_sdf + n);
+                    if (p.g_grad) { gg[0] = __ldg(p.g_grad + n * 3); gg[1] = __ldg(p.g_grad + n * 3 + 1); gg[2] = __ldg(p.g_grad + n * 3 + 2); }
+                    // (short on purpose: this block runs once per tile in one warp, so its instructions are fetched cold every
+                    // time; the reciprocals of the finite-difference steps are loop constants)
                     float g[3], h[3];
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
-                        const float e = p.units[k];
-                        g[k] = (sd[1 + 2 * k] - sd[2 + 2 * k]) / (2.f * e);
-                        h[k] = (sd[1 + 2 * k] + sd[2 + 2 * k] - 2.f * sd[0]) / (e * e);
+                        g[k] = (sd[1 + 2 * k] - sd[2 + 2 * k]) * inv2e[k];
+                        h[k] = (sd[1 + 2 * k] + sd[2 + 2 * k] - 2.f * sd[0]) * inve2[k];
                     }
-                    const float D = g[0] * g[0] + g[1] * g[1] + g[2] * g[2] + 1e-5f;
-                    const float nh = (g[0] * h[0] + g[1] * h[1] + g[2] * h[2]) / D;
-                    const float gh = p.g_hess ? p.g_hess[n] : 0.f;
-                    gq[0] = p.g_sdf ? p.g_sdf[n] : 0.f;
+                    const float rD = 1.f / (g[0] * g[0] + g[1] * g[1] + g[2] * g[2] + 1e-5f);
+                    const float nh = (g[0] * h[0] + g[1] * h[1] + g[2] * h[2]) * rD;
+                    gq[0] = gs;
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
-                        const float e = p.units[k];
-                        const float Gk = (p.g_grad ? p.g_grad[n * 3 + k] : 0.f) + gh * (h[k] / D - 2.f * g[k] * nh / D);
-                        const float Hk = gh * g[k] / D;
-                        gq[1 + 2 * k] = Gk / (2.f * e) + Hk / (e * e);
-                        gq[2 + 2 * k] = -Gk / (2.f * e) + Hk / (e * e);
-                        gq[0] -= 2.f * Hk / (e * e);
+                        const float Gk = gg[k] + gh * (h[k] * rD - 2.f * g[k] * nh * rD);
+                        const float Hk = gh * g[k] * rD;
+                        gq[1 + 2 * k] = Gk * inv2e[k] + Hk * inve2[k];
+                        gq[2 + 2 * k] = -Gk * inv2e[k] + Hk * inve2[k];
+                        gq[0] -= 2.f * Hk * inve2[k];
                     }
                 }
                 float tot = 0.f;
 #pragma unroll
-                for (int r = 0; r < NQ7; ++r) { gqs[tid * NQ7 + r] = gq[r]; tot += gq[r]; }
+                for (int r = 0; r < NQ7; ++r) { gqs[ts * NQ7 + r] = gq[r]; tot += gq[r]; }
                 if (tot != 0.f) atomicAdd(accb1, tot);
-            } else if (tid < SPT + 2) {
-                gqs[SPT * NQ7 + tid - SPT] = 0.f;
+            } else if (tid >= 32 + SPT && tid < 32 + SPT + 2) {
+                gqs[SPT * NQ7 + tid - 32 - SPT] = 0.f;
             }
             // ---- GEMM1 (thread 0): pre = A W0^T ----------------------------------------------------------------------
             if (tid == 0) {
+                PROF(14)
                 tc::mbar_wait(aready, tpar);
                 tc::fence_after_sync();
+                PROF(13)
                 for (int s = 0; s < S; ++s) {
-                    ring_prefetch();
                     const int st = (int)(g_mma % NST);
+                    mbar_expect_tx(&full[st], slot_bytes);
                     tc::mbar_wait(&full[st], (uint32_t)((g_mma / NST) & 1));
                     tc::fence_after_sync();
+                    PROF(11)
                     const uint32_t w_hi = tc::smem_u32(wst + (size_t)st * slot_bytes);
                     const uint64_t wdh0 = tc::make_smem_desc(w_hi, 128, w1_sbo), wdl0 = tc::make_smem_desc(w_hi + (uint32_t)H * KS1 * 4, 128, w1_sbo);
 #pragma unroll
@@ -263,9 +296,9 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_bwd_tc_kernel(TcBwdParams 
                     }
                     tc::mma_commit(&empty[st]);
                     ++g_mma;
+                    PROF(12)
                 }
                 tc::mma_commit(dfull1);
-                ring_prefetch();
             }
             const int64_t n = s_base + row_s;
             const bool centre = row_q == 0 && row_s < SPT && n < p.n;
@@ -277,17 +310,23 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_bwd_tc_kernel(TcBwdParams 
 #pragma unroll
                 for (int j = 0; j < 4; ++j) hc[j] = __ldg(src + j);
             }
+            PROF(1)
+            pump_to(lt * J + S + NST);                 // the GEMM1 slices of this tile and the slots of chunks 0 and 1
             tc::bar_sync(1, NGRP);                     // gqs visible to the group
+            PROF(2)
             tc::mbar_wait(dfull1, tpar);
             tc::fence_after_sync();
+            PROF(3)
             // ---- epilogue-1 + GEMM-dA, chunk by chunk over the hidden units -----------------------------------
             const float gq = gqs[row];
             for (int c = 0; c < (TF_DBG(p, 16) ? 0 : NCH); ++c) {
                 const int buf = c & 1;
                 if (c >= 2) { tc::mbar_wait(&cfree[buf], (cf_commits[buf] - 1) & 1); tc::fence_after_sync(); }
+                PROF(4)
                 const int col0 = c * HCH + half * 16;
                 float v[16];
                 tc::tmem_ld16(d1 + ((uint32_t)(lq * 32) << 16) + col0, v);
+                if (tid != 0) { PROF(11) }
                 float sp[16];
                 const float hcv[16] = {hc[0].x, hc[0].y, hc[0].z, hc[0].w, hc[1].x, hc[1].y, hc[1].z, hc[1].w,
                                        hc[2].x, hc[2].y, hc[2].z, hc[2].w, hc[3].x, hc[3].y, hc[3].z, hc[3].w};
@@ -302,6 +341,7 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_bwd_tc_kernel(TcBwdParams 
                     softplus100_fast_both(v[j] + b0s[col0 + j], sp[j], sg);
                     v[j] = fmaf(gq, w1s[col0 + j], hcv[j]) * sg;         // dPre = dPost * sigmoid
                 }
+                if (tid != 0) { PROF(12) }
                 float4* dst = reinterpret_cast<float4*>(p.dpre + (size_t)(tile_row0 + row) * H + col0);
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
@@ -315,11 +355,13 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_bwd_tc_kernel(TcBwdParams 
                     tc::tmem_st16(ca + 32, lo);
                     tc::tmem_st_wait();
                 }
+                if (tid != 0) { PROF(13) }
                 if (centre && p.spc) {
                     float4* sdst = reinterpret_cast<float4*>(p.spc + (size_t)n * H + col0);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) sdst[j] = make_float4(sp[4 * j], sp[4 * j + 1], sp[4 * j + 2], sp[4 * j + 3]);
                 }
+                if (tid != 0) { PROF(14) }
                 if (!TF_DBG(p, 8)) {
                     // 16 column sums over the warp's 32 rows with 16 shuffles: every exchange halves the columns a lane owns
                     float w8[8], w4[4], w2[2];
@@ -338,15 +380,18 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_bwd_tc_kernel(TcBwdParams 
                     const int col = (b16 ? 8 : 0) + (b8 ? 4 : 0) + (b4 ? 2 : 0) + (b2 ? 1 : 0);
                     if (!(lane & 1) && w1 != 0.f) atomicAdd(&accw1[col0 + col], w1);
                 }
+                PROF(5)
                 tc::fence_before_sync();
                 tc::bar_sync(1, NGRP);
                 tc::fence_after_sync();
+                PROF(6)
+                pump_to(lt * J + S + (HCH / HHC) * c + NST);   // slots of the next chunk (after the last one: first slices of the next tile)
                 if (tid == 0) {
                     const uint32_t ah = chunk_a + (uint32_t)buf * 64, al = ah + 32;
 #pragma unroll
                     for (int hh = 0; hh < HCH / HHC; ++hh) {
-                        ring_prefetch();
                         const int st = (int)(g_mma % NST);
+                        mbar_expect_tx(&full[st], slot_bytes);
                         tc::mbar_wait(&full[st], (uint32_t)((g_mma / NST) & 1));
                         tc::fence_after_sync();
                         const uint32_t w_hi = tc::smem_u32(wst + (size_t)st * slot_bytes);
@@ -364,27 +409,31 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_bwd_tc_kernel(TcBwdParams 
                     }
                     tc::mma_commit(&cfree[buf]);
                     if (c == NCH - 1) tc::mma_commit(dfull2);
-                    ring_prefetch();
                 }
                 ++cf_commits[buf];
+                PROF(7)
             }
             if (TF_DBG(p, 16)) {
-                if (tid == 0) {                         // timing experiments: the skipped slots still rotate through the ring
-                    for (int c = 0; c < H / HHC; ++c) {
-                        ring_prefetch();
-                        const int st = (int)(g_mma % NST);
-                        tc::mbar_wait(&full[st], (uint32_t)((g_mma / NST) & 1));
-                        tc::mma_commit(&empty[st]);
-                        ++g_mma;
+                for (int c = 0; c < NCH; ++c) {           // timing experiments: the skipped slots still rotate through the ring
+                    pump_to(lt * J + S + (HCH / HHC) * c + NST);
+                    if (tid == 0) {
+                        for (int hh = 0; hh < HCH / HHC; ++hh) {
+                            const int st = (int)(g_mma % NST);
+                            mbar_expect_tx(&full[st], slot_bytes);
+                            tc::mbar_wait(&full[st], (uint32_t)((g_mma / NST) & 1));
+                            tc::mma_commit(&empty[st]);
+                            ++g_mma;
+                        }
                     }
-                    ring_prefetch();
                 }
             } else {
                 tc::mbar_wait(dfull2, tpar);
             }
             tc::fence_after_sync();
+            PROF(8)
             // ---- dA: TMEM -> shared memory (fp32, row-major) once the memory group has scattered the previous tile ----
             if (lt > 0) tc::mbar_wait(dafree, (uint32_t)((lt - 1) & 1));
+            PROF(9)
             for (int c0 = half * 16; c0 < KT; c0 += 32) {
                 float v[16];
                 tc::tmem_ld16(d2 + ((uint32_t)(lq * 32) << 16) + c0, v);
@@ -394,7 +443,10 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_bwd_tc_kernel(TcBwdParams 
             }
             tc::fence_before_sync();
             tc::mbar_arrive(daready);
+            PROF(10)
         }
+        if (tid == 0) { PROF_DUMP(1) }
+        if (tid == 32) { PROF_DUMP(0) }
     }
     __syncthreads();
     for (int i = tid; i < H; i += NTH)
@@ -447,6 +499,12 @@ int tf_internal_stencil_bwd_tc(const tf_vm_field_t* f, const tf_vm_mut_t* g, con
     p.dpre = dpre; p.arow = arow; p.spc = spc; p.da_scratch = da_scratch; p.dW1r0 = dW1r0; p.db1 = db1;
 #ifdef TF_TC_DEBUG_SWITCHES
     { const char* e = getenv("TF_TC_BWD_DEBUG"); p.debug = e ? atoi(e) : 0; }
+    static long long* prof_dev = nullptr;
+    if (getenv("TF_TC_BWD_PROF")) {
+        if (!prof_dev) cudaMalloc(&prof_dev, 48 * sizeof(long long));
+        cudaMemsetAsync(prof_dev, 0, 48 * sizeof(long long), stream);
+        p.prof = prof_dev;
+    }
 #endif
     const size_t smem = tf_internal_bwd_tc_smem(KT, H);
     cudaFuncSetAttribute(sdf_stencil_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -457,5 +515,18 @@ int tf_internal_stencil_bwd_tc(const tf_vm_field_t* f, const tf_vm_mut_t* g, con
         sdf_stencil_bwd_tc_kernel<<<grid, NTH, smem, stream>>>(p);
     }
     tf_count_launches(1);
+#ifdef TF_TC_DEBUG_SWITCHES
+    if (p.prof) {
+        long long h[48];
+        cudaMemcpy(h, p.prof, sizeof(h), cudaMemcpyDeviceToHost);
+        const double tiles = (double)((ntiles + grid - 1) / grid);
+        const char* roles[3] = {"math worker (warp 1)", "math driver (thread 0)", "memory (warp 8)"};
+        for (int r = 0; r < 3; ++r) {
+            fprintf(stderr, "[bwd prof] %-22s cycles/tile:", roles[r]);
+            for (int i = 0; i < 15; ++i) fprintf(stderr, " %d:%.0f", i, (double)h[r * 16 + i] / tiles);
+            fprintf(stderr, "\n");
+        }
+    }
+#endif
     return 0;
 }

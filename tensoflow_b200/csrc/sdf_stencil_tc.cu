@@ -5,19 +5,21 @@
 // tcgen05.mma kind::tf32 with fp32-level accuracy from operand splitting
 // (x = hi + lo, D = A_hi W_hi + A_hi W_lo + A_lo W_hi: "3xTF32").
 //
-// One persistent CTA (256 threads) per SM walks MMA tiles of M = 128 rows.  In stencil mode a tile is
-// sample-major: 18 samples x 7 queries (centre, +-x, +-y, +-z) so that the queries of a sample share
+// One persistent CTA per SM (16 worker warps + a driver warp) walks MMA tiles of M = 128 rows.  In stencil mode a
+// tile is sample-major: 18 samples x 7 queries (centre, +-x, +-y, +-z) so that the queries of a sample share
 // their plane / line fetches (stencil_site.cuh); in SDF-only mode it is 128 samples:
-//   gather  : all threads; one (sample, plane, channel group) site per thread and pass, texel reads
-//             are 144-byte runs per site; values are split hi/lo and stored in the K-major no-swizzle
-//             UMMA layout with a padded K-chunk stride (conflict-free stores)
+//   gather  : workers; one (sample, plane, channel group) site per thread and pass, texel reads are 144-byte
+//             runs per site; fp32 rows go to a staging tile in shared memory (padded K-chunk stride:
+//             conflict-free stores and reads)
+//   A       : the staging tile moves to TENSOR MEMORY split into tf32 hi | lo (thread = row, tcgen05.st), so the
+//             MMAs of tile t read A from TMEM while the workers already gather tile t+1 into the staging tile
 //   W0      : pre-split / pre-tiled once per call into K-slices of 16 (prep kernel); slices stream
-//             L2 -> shared memory through a 3-stage ring with cp.async.bulk + mbarrier (one driver thread)
-//   MMA     : driver thread issues 6 tcgen05.mma per slice (2 k-steps x 3 passes), accumulator
-//             [128 x H] fp32 in TMEM, double buffered (2 x 256 columns)
-//   epilogue: overlaps the next tile's MMAs; tcgen05.ld -> +b0 -> Softplus(beta=100) -> dot with
-//             W1[0,:] (the SDF output; taps need nothing else) ; the centre tile also streams its
-//             hidden activations to HBM for the appearance head (second layer, [N,H] x [H,A])
+//             L2 -> shared memory through a 3-stage ring with cp.async.bulk + mbarrier, one issuing warp per stage
+//   MMA     : driver thread issues 6 tcgen05.mma per slice (2 k-steps x 3 passes, A from TMEM), accumulator
+//             [128 x H] fp32 in TMEM (256 columns) next to A hi | lo (2 x KT columns)
+//   epilogue: tcgen05.ld -> +b0 -> Softplus(beta=100) -> dot with W1[0,:] (the SDF output; taps need nothing
+//             else); the centre rows also stream their hidden activations to HBM for the appearance head
+//             (second layer, [N,H] x [H,A])
 //   finalize: per tile, the 7 SDF values of a sample -> sdf7, central-difference gradient, hessian term.
 #include <stdlib.h>
 #include "common.cuh"
@@ -29,9 +31,11 @@ namespace {
 constexpr int TM = 128;     // rows per MMA tile = samples per block
 constexpr int NQ7 = 7;
 constexpr int KSL = 16;     // K-slice (2 tf32 MMA k-steps)
-constexpr int NST = 2;      // W ring stages
-constexpr int NTH = 512;    // 16 warps at <= 128 registers: the gather is latency-bound, thread-level parallelism hides it
-constexpr int NCG = NTH / 128; // column groups of the epilogue (warps sharing a TMEM lane quarter)
+constexpr int NST = 3;      // W ring stages = issuing warps of the driver group (see the W ring comment in the kernel)
+constexpr int NWORK = 512;  // 16 worker warps: the gather is latency-bound, thread-level parallelism hides it
+constexpr int NTH = NWORK + 128; // + the driver warpgroup (one lane of its first warp: W ring + MMA issue); register
+                                // rebalancing (setmaxnreg) is per warpgroup, hence a whole one
+constexpr int NCG = NWORK / 128; // column groups of the epilogue (warps sharing a TMEM lane quarter)
 
 struct TcParams {
     tf_vm_field_t f;
@@ -83,15 +87,15 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar)), "r"(bytes) : "memory");
 }
 
-// SDF-only mode: gather the feature rows of 128 samples (one query each) into the A operand
-__device__ __forceinline__ void tc_gather_rows(const TcParams& p, int64_t s_base, uint8_t* a_hi, uint8_t* a_lo) {
+// SDF-only mode: gather the feature rows of 128 samples (one query each) into the fp32 staging tile
+__device__ __forceinline__ void tc_gather_rows(const TcParams& p, int64_t s_base, uint8_t* a_st) {
     const int C = p.f.n_comp, C4 = C / 4, G = p.KT / 4;
     const bool has_level = p.level != nullptr;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // unit = (8-row group, plane): lane -> (row = lane%8, channel groups lane/8, lane/8+4, ...); the
     // sampling plan of the (row, plane) pair is computed once and reused for its channel groups
     const int n_units = (TM / 8) * 3;
-    for (int u = warp; u < n_units; u += NTH / 32) {
+    for (int u = warp; u < n_units; u += NWORK / 32) {
         const int rg = u / 3, i = u % 3;
         const int row = rg * 8 + (lane & 7);
         const int64_t n = s_base + row;
@@ -108,42 +112,63 @@ __device__ __forceinline__ void tc_gather_rows(const TcParams& p, int64_t s_base
                 vm_fetch(taps, C, c4 * 4, P, L);
                 v = f4_mul(P, L);
             }
-            site::put(a_hi, a_lo, site::a_off(row, i * C4 + c4, p.KT), v);
+            site::put(a_st, nullptr, site::a_off(row, i * C4 + c4, p.KT), v);
         }
     }
     // raw xyz (fields.py:265,298) + zero padding groups
     const int tail_g = G - 3 * C4;
-    for (int it = threadIdx.x; it < TM * tail_g; it += NTH) {
+    for (int it = threadIdx.x; it < TM * tail_g; it += NWORK) {
         const int row = it % TM, g = 3 * C4 + it / TM;
         const int64_t n = s_base + row;
         float4 v = f4_zero();
         if (g == 3 * C4 && n < p.n) v = make_float4(p.xyz[n * 3 + 0], p.xyz[n * 3 + 1], p.xyz[n * 3 + 2], 0.f);
-        site::put(a_hi, a_lo, site::a_off(row, g, p.KT), v);
+        site::put(a_st, nullptr, site::a_off(row, g, p.KT), v);
     }
 }
 
-__device__ __forceinline__ void tc_gather(const TcParams& p, int64_t tile, uint8_t* a_hi, uint8_t* a_lo) {
-    if (p.nq == NQ7) site::gather_tile_lean(p.f, p.xyz, p.level, p.n, p.units, tile * site::SPT, p.KT, a_hi, a_lo, nullptr, NTH, threadIdx.x);
-    else tc_gather_rows(p, tile * TM, a_hi, a_lo);
+__device__ __forceinline__ void tc_gather(const TcParams& p, const site::LevelTab& s_tab, int64_t tile, uint8_t* a_st) {
+    if (p.nq == NQ7) site::gather_tile_lean(p.f, s_tab, p.xyz, p.level, p.n, p.units, tile * site::SPT, p.KT, a_st, nullptr, nullptr, NWORK, threadIdx.x);
+    else tc_gather_rows(p, tile * TM, a_st);
+}
+
+// staging tile (fp32, shared memory) -> A operand in tensor memory, split into tf32 hi | lo: thread = row (lane of its
+// warp's TMEM quarter), the four warps of a quarter share the 16-column units
+__device__ __forceinline__ void tc_stage_to_tmem(const uint8_t* a_st, int KT, uint32_t a_tmem, int lq, int chh, int lane) {
+    const int row = lq * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(lq * 32) << 16;
+    for (int u = chh; u < KT / 16; u += NCG) {
+        float hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4 v = *reinterpret_cast<const float4*>(a_st + site::a_off(row, u * 4 + j, KT));
+            const float4 h = site::tf32_hi(v), l = site::tf32_lo(v, h);
+            hi[4 * j] = h.x; hi[4 * j + 1] = h.y; hi[4 * j + 2] = h.z; hi[4 * j + 3] = h.w;
+            lo[4 * j] = l.x; lo[4 * j + 1] = l.y; lo[4 * j + 2] = l.z; lo[4 * j + 3] = l.w;
+        }
+        tc::tmem_st16(a_tmem + lane_sel + u * 16, hi);
+        tc::tmem_st16(a_tmem + lane_sel + KT + u * 16, lo);
+    }
+    tc::tmem_st_wait();
 }
 
 __global__ void __launch_bounds__(NTH, 1) sdf_stencil_fwd_tc_kernel(TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ site::LevelTab s_tab;
     const int H = p.H, KT = p.KT, S = KT / KSL, nq = p.nq;
     const int spt = nq == NQ7 ? site::SPT : TM;               // samples per tile
-    const uint32_t a_part = site::a_part_bytes(KT);           // bytes of one A part
+    const uint32_t a_part = site::a_part_bytes(KT);           // bytes of the fp32 staging tile
     const uint32_t w_part = (uint32_t)H * KSL * 4;            // bytes of one W slice part
-    uint8_t* a_hi = smem;
-    uint8_t* a_lo = a_hi + a_part;
-    uint8_t* wst = a_lo + a_part;                             // NST stages x (hi, lo)
+    uint8_t* a_st = smem;
+    uint8_t* wst = a_st + a_part;                             // NST stages x (hi, lo)
     float* b0s = reinterpret_cast<float*>(wst + (size_t)NST * 2 * w_part);
     float* w1s = b0s + H;
     float* sdfs = w1s + H;                                    // [2 tiles][NCG column groups][TM]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sdfs + 2 * NCG * TM);
     uint64_t* full = bars;                                    // [NST]
     uint64_t* empty = bars + NST;                             // [NST]
-    uint64_t* dfull = bars + 2 * NST;                         // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 2);
+    uint64_t* dfull = bars + 2 * NST;                         // accumulator of the tile complete (= A operand consumed)
+    uint64_t* aready = dfull + 1;                             // A operand of the tile is in tensor memory, accumulator drained
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aready + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t ntiles = (p.n + spt - 1) / spt;
@@ -153,68 +178,83 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_fwd_tc_kernel(TcParams p) 
     if (warp == 0) tc::tmem_alloc<512>(tmem_slot);
     if (tid == 0) {
         for (int i = 0; i < NST; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
-        tc::mbar_init(&dfull[0], 1); tc::mbar_init(&dfull[1], 1);
+        tc::mbar_init(dfull, 1); tc::mbar_init(aready, NWORK);
         tc::mbar_fence_init();
     }
     for (int i = tid; i < H; i += NTH) { b0s[i] = p.b0[i]; w1s[i] = p.w1r0[i]; }
-    if (my_tiles > 0) tc_gather(p, blockIdx.x, a_hi, a_lo);
-    tc::fence_async_smem();
+    site::build_level_tab(p.f, &s_tab);
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t idesc = tc::make_idesc(2, 2, TM, H);
-    const uint32_t a_sbo = site::a_sbo(KT), a_kstep = 2 * site::A_LBO;
-    const uint32_t w_sbo = (KSL / 4) * 128;
-    const uint64_t a_desc_hi = tc::make_smem_desc(tc::smem_u32(a_hi), site::A_LBO, a_sbo), a_desc_lo = tc::make_smem_desc(tc::smem_u32(a_lo), site::A_LBO, a_sbo);
+    const uint32_t d_tmem = tmem_base, a_tmem = tmem_base + 256;          // D [128 x H] | A hi [128 x KT] | A lo [128 x KT]
 
-    int64_t g_issue = 0, g_mma = 0;                           // driver-thread state (W slice counters)
-    const int64_t total_slices = my_tiles * S;
-
-    for (int64_t t = 0; t <= my_tiles; ++t) {
-        // ---- driver: stream W slices and issue the MMAs of tile t --------------------------------
-        if (tid == 0 && t < my_tiles) {
-            const uint32_t dcol = tmem_base + (uint32_t)(t & 1) * 256;
-            for (int s = 0; s < S; ++s) {
-                while (g_issue < total_slices && g_issue < g_mma + NST) {
-                    const int st = (int)(g_issue % NST);
-                    tc::mbar_wait(&empty[st], (uint32_t)(((g_issue / NST) & 1) ^ 1));
-                    mbar_expect_tx(&full[st], 2 * w_part);
-                    bulk_copy_g2s(wst + (size_t)st * 2 * w_part, p.W0tc + (size_t)(g_issue % S) * 2 * H * KSL, 2 * w_part, &full[st]);
-                    ++g_issue;
-                }
-                const int st = (int)(g_mma % NST);
-                tc::mbar_wait(&full[st], (uint32_t)((g_mma / NST) & 1));
+    if (tid >= NWORK) {
+        // ======================= driver: stream the W slices, issue the MMAs (A from tensor memory) ===================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+        const int dw = warp - NWORK / 32;                     // warp of the driver group
+        const uint32_t w_sbo = (KSL / 4) * 128;
+        const int64_t total_slices = my_tiles * S;
+        if (dw == 0 && lane == 0) {
+            // ---- MMA thread: A from tensor memory, W slices from the ring ------------------------------------------
+            const uint32_t idesc = tc::make_idesc(2, 2, TM, H);
+            int64_t g_mma = 0;
+            for (int64_t t = 0; t < my_tiles; ++t) {
+                tc::mbar_wait(aready, (uint32_t)(t & 1));
                 tc::fence_after_sync();
-                const uint32_t w_hi = tc::smem_u32(wst + (size_t)st * 2 * w_part);
-                const uint64_t wdh0 = tc::make_smem_desc(w_hi, 128, w_sbo), wdl0 = tc::make_smem_desc(w_hi + w_part, 128, w_sbo);
-                const uint64_t adh0 = tc::desc_add(a_desc_hi, s * (KSL / 8) * a_kstep), adl0 = tc::desc_add(a_desc_lo, s * (KSL / 8) * a_kstep);
+                for (int s = 0; s < S; ++s) {
+                    const int st = (int)(g_mma % NST);
+                    mbar_expect_tx(&full[st], 2 * w_part);
+                    tc::mbar_wait(&full[st], (uint32_t)((g_mma / NST) & 1));
+                    tc::fence_after_sync();
+                    const uint32_t w_hi = tc::smem_u32(wst + (size_t)st * 2 * w_part);
+                    const uint64_t wdh0 = tc::make_smem_desc(w_hi, 128, w_sbo), wdl0 = tc::make_smem_desc(w_hi + w_part, 128, w_sbo);
 #pragma unroll
-                for (int ks = 0; ks < KSL / 8; ++ks) {
-                    if (TF_DBG(p, 2)) break;
-                    const uint64_t adh = tc::desc_add(adh0, ks * a_kstep), adl = tc::desc_add(adl0, ks * a_kstep);
-                    const uint64_t wdh = tc::desc_add(wdh0, ks * 256), wdl = tc::desc_add(wdl0, ks * 256);
-                    tc::mma_tf32_ss(dcol, adh, wdh, idesc, (s | ks) != 0);
-                    tc::mma_tf32_ss(dcol, adh, wdl, idesc, 1);
-                    tc::mma_tf32_ss(dcol, adl, wdh, idesc, 1);
+                    for (int ks = 0; ks < KSL / 8; ++ks) {
+                        if (TF_DBG(p, 2)) break;
+                        const uint32_t kc = (uint32_t)(s * KSL + ks * 8);
+                        const uint64_t wdh = tc::desc_add(wdh0, ks * 256), wdl = tc::desc_add(wdl0, ks * 256);
+                        tc::mma_tf32_ts(d_tmem, a_tmem + kc, wdh, idesc, (s | ks) != 0);
+                        tc::mma_tf32_ts(d_tmem, a_tmem + kc, wdl, idesc, 1);
+                        tc::mma_tf32_ts(d_tmem, a_tmem + KT + kc, wdh, idesc, 1);
+                    }
+                    tc::mma_commit(&empty[st]);
+                    ++g_mma;
                 }
-                tc::mma_commit(&empty[st]);
-                ++g_mma;
+                tc::mma_commit(dfull);
             }
-            tc::mma_commit(&dfull[t & 1]);
+        } else if (dw >= 1 && lane == 0) {
+            // ---- W ring: cp.async.bulk copies issued by ONE warp execute one after the other (~800-900 cycles each whatever
+            // their size: tests/probes/bulk_probe.cu), copies of different warps overlap: one issuing warp per ring stage
+            const int k = dw - 1;
+            for (int64_t g = k; g < total_slices; g += NST) {
+                tc::mbar_wait(&empty[k], (uint32_t)(((g / NST) & 1) ^ 1));
+                bulk_copy_g2s(wst + (size_t)k * 2 * w_part, p.W0tc + (size_t)(g % S) * 2 * H * KSL, 2 * w_part, &full[k]);
+            }
         }
-        // ---- epilogue of tile t-1 (overlaps the MMAs of tile t) --------------------------------------
-        if (t > 0) {
-            const int64_t tp = t - 1;
-            const int64_t tile = blockIdx.x + tp * gridDim.x;
-            tc::mbar_wait(&dfull[tp & 1], (uint32_t)((tp >> 1) & 1));
+    } else {
+        // ======================= workers: gather tile t+1 while the MMAs of tile t run, then epilogue of tile t ========
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+        const int lq = warp & 3, chh = warp >> 2;
+        const int row = lq * 32 + lane;
+        const float inv2e[3] = {1.f / (2.f * p.units[0]), 1.f / (2.f * p.units[1]), 1.f / (2.f * p.units[2])};
+        const float inve2[3] = {1.f / (p.units[0] * p.units[0]), 1.f / (p.units[1] * p.units[1]), 1.f / (p.units[2] * p.units[2])};
+        tc_gather(p, s_tab, blockIdx.x, a_st);
+        tc::bar_sync(1, NWORK);
+        tc_stage_to_tmem(a_st, KT, a_tmem, lq, chh, lane);
+        tc::fence_before_sync();
+        tc::mbar_arrive(aready);
+        for (int64_t t = 0; t < my_tiles; ++t) {
+            const int64_t tile = blockIdx.x + t * gridDim.x;
+            tc::bar_sync(1, NWORK);                              // every warp has read the staging tile: it is free again
+            if (t + 1 < my_tiles && !TF_DBG(p, 1)) tc_gather(p, s_tab, blockIdx.x + (t + 1) * gridDim.x, a_st);
+            // ---- epilogue of tile t --------------------------------------------------------------------------------
+            tc::mbar_wait(dfull, (uint32_t)(t & 1));
             tc::fence_after_sync();
-            const int lq = warp & 3, chh = warp >> 2;
-            const int row = lq * 32 + lane;
             const int s = row / nq, q = row - s * nq;
             const int64_t n = tile * spt + s;
             const bool centre = q == 0 && s < spt && n < p.n;
-            const uint32_t dcol = tmem_base + (uint32_t)(tp & 1) * 256 + ((uint32_t)(lq * 32) << 16);
+            const uint32_t dcol = d_tmem + ((uint32_t)(lq * 32) << 16);
             float psum = 0.f;
             for (int c0 = chh * 32; c0 < H; c0 += 32 * NCG) {
                 if (TF_DBG(p, 4)) break;
@@ -239,54 +279,49 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_fwd_tc_kernel(TcParams p) 
                     }
                 }
             }
-            sdfs[((tp & 1) * NCG + chh) * TM + row] = psum;
+            sdfs[((t & 1) * NCG + chh) * TM + row] = psum;
             tc::fence_before_sync();
-        }
-        // ---- wait for the MMAs of tile t, then gather tile t+1 into the (now free) A buffer ---------------
-        if (t < my_tiles) {
-            tc::mbar_wait(&dfull[t & 1], (uint32_t)((t >> 1) & 1));
+            tc::bar_sync(1, NWORK);                              // staging tile of t+1 complete, partial sums of t visible
+            // ---- A operand of tile t+1 -> tensor memory (the accumulator and the A region are free: MMAs of t are done)
             if (t + 1 < my_tiles) {
-                if (!TF_DBG(p, 1)) tc_gather(p, blockIdx.x + (t + 1) * gridDim.x, a_hi, a_lo);
-                tc::fence_async_smem();
+                tc_stage_to_tmem(a_st, KT, a_tmem, lq, chh, lane);
+                tc::fence_before_sync();
+                tc::mbar_arrive(aready);
             }
-        }
-        tc::fence_before_sync();
-        __syncthreads();
-        tc::fence_after_sync();
-        // ---- finalize the samples of tile t-1 ------------------------------------------------------------
-        if (t > 0 && tid < spt) {
-            const int64_t tp = t - 1;
-            const int64_t n = (blockIdx.x + tp * gridDim.x) * spt + tid;
-            const float* sp = &sdfs[(tp & 1) * NCG * TM + tid * nq];
-            if (n < p.n) {
-                const float b1 = __ldg(p.b1);
-                if (nq == 1) {
-                    float v = b1;
-#pragma unroll
-                    for (int g = 0; g < NCG; ++g) v += sp[g * TM];
-                    p.sdf1[n] = v;
-                } else {
-                    float sd[NQ7];
-#pragma unroll
-                    for (int r = 0; r < NQ7; ++r) {
+            // ---- finalize the samples of tile t ---------------------------------------------------------------------
+            if (tid < spt) {
+                const int64_t ns = tile * spt + tid;
+                const float* sp = &sdfs[(t & 1) * NCG * TM + tid * nq];
+                if (ns < p.n) {
+                    const float b1 = __ldg(p.b1);
+                    if (nq == 1) {
                         float v = b1;
 #pragma unroll
-                        for (int g = 0; g < NCG; ++g) v += sp[g * TM + r];
-                        sd[r] = v; p.sdf7[n * NQ7 + r] = v;
-                    }
-                    float g[3], h[3];
+                        for (int g = 0; g < NCG; ++g) v += sp[g * TM];
+                        p.sdf1[ns] = v;
+                    } else {
+                        float sd[NQ7];
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        const float e = p.units[k];
-                        g[k] = (sd[1 + 2 * k] - sd[2 + 2 * k]) / (2.f * e);
-                        h[k] = (sd[1 + 2 * k] + sd[2 + 2 * k] - 2.f * sd[0]) / (e * e);
+                        for (int r = 0; r < NQ7; ++r) {
+                            float v = b1;
+#pragma unroll
+                            for (int g = 0; g < NCG; ++g) v += sp[g * TM + r];
+                            sd[r] = v; p.sdf7[ns * NQ7 + r] = v;
+                        }
+                        float g[3], h[3];              // (reciprocal FD steps: this block is fetched cold once per tile; keep it short)
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            g[k] = (sd[1 + 2 * k] - sd[2 + 2 * k]) * inv2e[k];
+                            h[k] = (sd[1 + 2 * k] + sd[2 + 2 * k] - 2.f * sd[0]) * inve2[k];
+                        }
+                        if (p.grad) { p.grad[ns * 3 + 0] = g[0]; p.grad[ns * 3 + 1] = g[1]; p.grad[ns * 3 + 2] = g[2]; }
+                        if (p.hess) p.hess[ns] = (g[0] * h[0] + g[1] * h[1] + g[2] * h[2]) / (g[0] * g[0] + g[1] * g[1] + g[2] * g[2] + 1e-5f);
                     }
-                    if (p.grad) { p.grad[n * 3 + 0] = g[0]; p.grad[n * 3 + 1] = g[1]; p.grad[n * 3 + 2] = g[2]; }
-                    if (p.hess) p.hess[n] = (g[0] * h[0] + g[1] * h[1] + g[2] * h[2]) / (g[0] * g[0] + g[1] * g[1] + g[2] * g[2] + 1e-5f);
                 }
             }
         }
     }
+    tc::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc<512>(tmem_base);
 }
@@ -294,7 +329,7 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_fwd_tc_kernel(TcParams p) 
 }  // namespace
 
 size_t tf_internal_tc_fwd_smem(int KT, int H) {
-    return (size_t)2 * 16 * (KT / 4) * site::A_LBO + (size_t)NST * 2 * H * KSL * 4 + (size_t)2 * H * 4 + (size_t)2 * NCG * TM * 4 + (2 * NST + 2) * 8 + 16;
+    return (size_t)16 * (KT / 4) * site::A_LBO + (size_t)NST * 2 * H * KSL * 4 + (size_t)2 * H * 4 + (size_t)2 * NCG * TM * 4 + (2 * NST + 2) * 8 + 16;
 }
 
 // workspace floats needed in front of spc: the pre-tiled W0
@@ -315,7 +350,7 @@ int tf_internal_stencil_fwd_tc(const tf_vm_field_t* f, const tf_sdf_mlp_t* m, co
 #endif
     tc_prep_w0_kernel<<<64, 256, 0, stream>>>(m->W0, K, KT, H, w0tc);
     const size_t smem = tf_internal_tc_fwd_smem(KT, H);
-    if (smem > 227 * 1024) { tf_set_error("tensor-core stencil: tile does not fit shared memory (KT=%d, H=%d)", KT, H); return 1; }
+    if (smem > 227 * 1024 || KT > 128 || H > 256 || f->n_levels > site::MAXL) { tf_set_error("tensor-core stencil: tile does not fit shared / tensor memory (KT=%d, H=%d)", KT, H); return 1; }
     cudaFuncSetAttribute(sdf_stencil_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int spt = nq == NQ7 ? site::SPT : TM;
     const int64_t ntiles = (n + spt - 1) / spt;

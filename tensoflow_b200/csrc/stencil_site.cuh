@@ -29,17 +29,40 @@ struct Levels {
     float fl;                           // weight of the second level (0 = single level)
 };
 
-__device__ __forceinline__ Levels levels(const tf_vm_field_t& f, float level, bool has_level, int i) {
+// per-kernel table of the mip levels (pointers / extents of every plane and line level) in shared memory: the
+// per-task level lookup is two indexed reads instead of loops over the mip chain and constant-bank indexing
+constexpr int MAXL = 8;
+struct LevelTab {
+    const float* plane[3 * MAXL]; const float* line[3 * MAXL];
+    int pw[3 * MAXL], ph[3 * MAXL], lg[3 * MAXL];
+};
+// all threads of the CTA call this before the first gather (followed by a CTA-wide barrier)
+__device__ __forceinline__ void build_level_tab(const tf_vm_field_t& f, LevelTab* t) {
+    for (int e = threadIdx.x; e < 3 * MAXL; e += blockDim.x) {
+        const int i = e / MAXL, l = e % MAXL;
+        if (l < f.n_levels) {
+            int H, W, G;
+            t->plane[e] = plane_level_ptr(f, i, l, H, W);
+            t->ph[e] = H; t->pw[e] = W;
+            t->line[e] = line_level_ptr(f, i, l, G);
+            t->lg[e] = G;
+        }
+    }
+}
+
+__device__ __forceinline__ Levels levels(const tf_vm_field_t& f, const LevelTab& tab, float level, bool has_level, int i) {
     Levels L;
     int l0 = 0, l1 = 0;
     L.fl = 0.f;
     if (has_level && f.n_levels > 1) mip_levels(level, f.n_levels, l0, l1, L.fl);
-    L.pt0 = plane_level_ptr(f, i, l0, L.H0, L.W0);
-    L.lt0 = line_level_ptr(f, i, l0, L.G0);
+    const int e0 = i * MAXL + l0;
+    L.pt0 = tab.plane[e0]; L.H0 = tab.ph[e0]; L.W0 = tab.pw[e0];
+    L.lt0 = tab.line[e0]; L.G0 = tab.lg[e0];
     L.pt1 = L.pt0; L.lt1 = L.lt0; L.W1 = L.W0; L.H1 = L.H0; L.G1 = L.G0;
     if (L.fl > 0.f) {
-        L.pt1 = plane_level_ptr(f, i, l1, L.H1, L.W1);
-        L.lt1 = line_level_ptr(f, i, l1, L.G1);
+        const int e1 = i * MAXL + l1;
+        L.pt1 = tab.plane[e1]; L.H1 = tab.ph[e1]; L.W1 = tab.pw[e1];
+        L.lt1 = tab.line[e1]; L.G1 = tab.lg[e1];
     }
     return L;
 }
@@ -66,11 +89,15 @@ __device__ __forceinline__ Tap1 tap1(float u, int N) {
 }
 // the 4 texels of a bilinear footprint / the 2 texels of a linear one (loads only, no arithmetic: callers batch
 // the loads of several positions before combining them so that many requests are in flight)
+// element offsets are 32-bit unsigned (a level holds < 2^32 floats): one IMAD.WIDE.U32 per address instead of
+// sign extensions and 64-bit multiplies (the gather / scatter are issue-bound as much as latency-bound)
+__device__ __forceinline__ uint32_t texel_off(int iy, int ix, int W, int C, int c) { return ((uint32_t)(iy * W) + (uint32_t)ix) * (uint32_t)C + (uint32_t)c; }
 __device__ __forceinline__ void bi_load(const float* T, const Tap1& tx, const Tap1& ty, int W, int C, int c, float4 t[4]) {
-    t[0] = ldg4(T + (size_t)(ty.i0 * W + tx.i0) * C + c);
-    t[1] = ldg4(T + (size_t)(ty.i0 * W + tx.i1) * C + c);
-    t[2] = ldg4(T + (size_t)(ty.i1 * W + tx.i0) * C + c);
-    t[3] = ldg4(T + (size_t)(ty.i1 * W + tx.i1) * C + c);
+    const uint32_t r0 = (uint32_t)(ty.i0 * W), r1 = (uint32_t)(ty.i1 * W), uc = (uint32_t)C, cc = (uint32_t)c;
+    t[0] = ldg4(T + ((r0 + (uint32_t)tx.i0) * uc + cc));
+    t[1] = ldg4(T + ((r0 + (uint32_t)tx.i1) * uc + cc));
+    t[2] = ldg4(T + ((r1 + (uint32_t)tx.i0) * uc + cc));
+    t[3] = ldg4(T + ((r1 + (uint32_t)tx.i1) * uc + cc));
 }
 __device__ __forceinline__ float4 bi_combine(const Tap1& tx, const Tap1& ty, const float4 t[4]) {
     float4 r = f4_scale(tx.w0 * ty.w0, t[0]);
@@ -79,17 +106,10 @@ __device__ __forceinline__ float4 bi_combine(const Tap1& tx, const Tap1& ty, con
     return f4_fma(tx.w1 * ty.w1, t[3], r);
 }
 __device__ __forceinline__ void li_load(const float* T, const Tap1& tl, int C, int c, float4 t[2]) {
-    t[0] = ldg4(T + (size_t)tl.i0 * C + c);
-    t[1] = ldg4(T + (size_t)tl.i1 * C + c);
+    t[0] = ldg4(T + ((uint32_t)tl.i0 * (uint32_t)C + (uint32_t)c));
+    t[1] = ldg4(T + ((uint32_t)tl.i1 * (uint32_t)C + (uint32_t)c));
 }
 __device__ __forceinline__ float4 li_combine(const Tap1& tl, const float4 t[2]) { return f4_fma(tl.w1, t[1], f4_scale(tl.w0, t[0])); }
-
-// 1-D plans of the 3 coordinate variants (centre, +unit, -unit) of the plane u / plane v / line axes on both levels
-template <bool TWO>
-struct SitePlan {
-    Tap1 x0[3], y0[3], l0[3];
-    Tap1 x1[3], y1[3], l1[3];
-};
 
 // normalised coordinate of value v along axis ax (same arithmetic as vm_coords)
 __device__ __forceinline__ float coord(const tf_vm_field_t& f, float v, int ax) { return (v - f.aabb_min[ax]) / (f.aabb_max[ax] - f.aabb_min[ax]); }
@@ -110,234 +130,23 @@ __device__ __forceinline__ Coords coords(const tf_vm_field_t& f, const float x[3
     return k;
 }
 
-template <bool TWO>
-__device__ __forceinline__ SitePlan<TWO> make_plan(const Levels& L, const Coords& k) {
-    SitePlan<TWO> p;
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        p.x0[j] = tap1(k.pu[j], L.W0); p.y0[j] = tap1(k.pv[j], L.H0); p.l0[j] = tap1(k.lv[j], L.G0);
-        if (TWO) { p.x1[j] = tap1(k.pu[j], L.W1); p.y1[j] = tap1(k.pv[j], L.H1); p.l1[j] = tap1(k.lv[j], L.G1); }
-    }
-    return p;
-}
-// plane value at variant (jx, jy) / line value at variant jl; the level-1 part is always fetched when TWO
-// (fl == 0 then multiplies it by zero and its texels coincide with level 0)
-template <bool TWO>
-struct PlaneFetch {
-    float4 t0[4], t1[4];
-    __device__ __forceinline__ void load(const Levels& L, const SitePlan<TWO>& p, int jx, int jy, int C, int c) {
-        bi_load(L.pt0, p.x0[jx], p.y0[jy], L.W0, C, c, t0);
-        if (TWO) bi_load(L.pt1, p.x1[jx], p.y1[jy], L.W1, C, c, t1);
-    }
-    __device__ __forceinline__ float4 value(const Levels& L, const SitePlan<TWO>& p, int jx, int jy) const {
-        float4 P = bi_combine(p.x0[jx], p.y0[jy], t0);
-        if (TWO) P = mix(L.fl, P, bi_combine(p.x1[jx], p.y1[jy], t1));
-        return P;
-    }
-};
-template <bool TWO>
-struct LineFetch {
-    float4 t0[2], t1[2];
-    __device__ __forceinline__ void load(const Levels& L, const SitePlan<TWO>& p, int jl, int C, int c) {
-        li_load(L.lt0, p.l0[jl], C, c, t0);
-        if (TWO) li_load(L.lt1, p.l1[jl], C, c, t1);
-    }
-    __device__ __forceinline__ float4 value(const Levels& L, const SitePlan<TWO>& p, int jl) const {
-        float4 V = li_combine(p.l0[jl], t0);
-        if (TWO) V = mix(L.fl, V, li_combine(p.l1[jl], t1));
-        return V;
-    }
-};
-
 __device__ __forceinline__ float4 tf32_hi(float4 v) { return make_float4(tc::tf32_rn(v.x), tc::tf32_rn(v.y), tc::tf32_rn(v.z), tc::tf32_rn(v.w)); }
 __device__ __forceinline__ float4 tf32_lo(float4 v, float4 h) {
     return make_float4(tc::tf32_rn(v.x - h.x), tc::tf32_rn(v.y - h.y), tc::tf32_rn(v.z - h.z), tc::tf32_rn(v.w - h.w));
 }
+// a_lo == nullptr: the tile is an fp32 staging buffer (the forward kernel splits when it moves the rows to tensor memory)
 __device__ __forceinline__ void put(uint8_t* a_hi, uint8_t* a_lo, uint32_t off, float4 v) {
+    if (a_lo == nullptr) { *reinterpret_cast<float4*>(a_hi + off) = v; return; }
     const float4 h = tf32_hi(v);
     *reinterpret_cast<float4*>(a_hi + off) = h;
     *reinterpret_cast<float4*>(a_lo + off) = tf32_lo(v, h);
 }
 
-// Gather the A operand of one stencil tile (samples [s_base, s_base + 18)).  When `arow` is not NULL the fp32
-// rows are also streamed to HBM ([128][KT] per tile, the constant-1 column at index 3C+3 included).
-template <bool TWO>
-__device__ __forceinline__ void gather_tile_t(const tf_vm_field_t& f, const float* __restrict__ xyz, const float* __restrict__ level, int64_t n_total,
-                                            const float units[3], int64_t s_base, int KT, uint8_t* a_hi, uint8_t* a_lo, float* arow, int nthreads, int tid0) {
-    const int C = f.n_comp, C4 = C / 4, G = KT / 4;
-    const bool has_level = level != nullptr;
-    const int n_tasks = SPT * 3 * C4;
-    for (int task = tid0; task < n_tasks; task += nthreads) {
-        const int c4 = task % C4, si = task / C4, i = si % 3, s = si / 3;
-        const int64_t n = s_base + s;
-        const int g = i * C4 + c4, r0 = s * NQ;
-        const Axes a = axes(i);
-        const int r_m0 = r0 + 1 + 2 * a.m0, r_m1 = r0 + 1 + 2 * a.m1, r_vm = r0 + 1 + 2 * a.vm;
-        float4 v[NQ];                                   // products in emission order: centre, m0+-, m1+-, vm+-
-        if (n < n_total) {
-            const float x[3] = {xyz[n * 3 + 0], xyz[n * 3 + 1], xyz[n * 3 + 2]};
-            const Levels L = levels(f, has_level ? level[n] : 0.f, has_level, i);
-            const Coords k = coords(f, x, units, a);
-            const int c = c4 * 4;
-            const SitePlan<TWO> sp = make_plan<TWO>(L, k);
-            LineFetch<TWO> fl0, fl1, fl2;
-            PlaneFetch<TWO> fp0, fpa, fpb;
-            fl0.load(L, sp, 0, C, c); fp0.load(L, sp, 0, 0, C, c);
-            fpa.load(L, sp, 1, 0, C, c); fpb.load(L, sp, 2, 0, C, c);
-            const float4 L0 = fl0.value(L, sp, 0), P0 = fp0.value(L, sp, 0, 0);
-            v[0] = f4_mul(P0, L0);
-            fl1.load(L, sp, 1, C, c); fl2.load(L, sp, 2, C, c);
-            v[1] = f4_mul(fpa.value(L, sp, 1, 0), L0);
-            v[2] = f4_mul(fpb.value(L, sp, 2, 0), L0);
-            fpa.load(L, sp, 0, 1, C, c); fpb.load(L, sp, 0, 2, C, c);
-            v[5] = f4_mul(P0, fl1.value(L, sp, 1));
-            v[6] = f4_mul(P0, fl2.value(L, sp, 2));
-            v[3] = f4_mul(fpa.value(L, sp, 0, 1), L0);
-            v[4] = f4_mul(fpb.value(L, sp, 0, 2), L0);
-        } else {
-#pragma unroll
-            for (int j = 0; j < NQ; ++j) v[j] = f4_zero();
-        }
-        const int rows[NQ] = {r0, r_m0, r_m0 + 1, r_m1, r_m1 + 1, r_vm, r_vm + 1};
-#pragma unroll
-        for (int j = 0; j < NQ; ++j) {
-            put(a_hi, a_lo, a_off(rows[j], g, KT), v[j]);
-            if (arow) *reinterpret_cast<float4*>(arow + (size_t)rows[j] * KT + g * 4) = v[j];
-        }
-    }
-    // raw stencil points (fields.py:265,298), zero padding groups and the two zero rows of the tile
-    const int tail_g = G - 3 * C4;
-    for (int it = tid0; it < 128 * tail_g; it += nthreads) {
-        const int r = it % 128, g = 3 * C4 + it / 128;
-        const int s = r / NQ, q = r - s * NQ;
-        const int64_t n = s_base + s;
-        float4 v = f4_zero(), vh = f4_zero();
-        if (g == 3 * C4 && s < SPT && n < n_total) {
-            const float x[3] = {xyz[n * 3 + 0], xyz[n * 3 + 1], xyz[n * 3 + 2]};
-            float pt[3];
-            stencil_point(x, units, q, pt);
-            v = make_float4(pt[0], pt[1], pt[2], 0.f);
-            vh = make_float4(pt[0], pt[1], pt[2], 1.f);      // ones column: dPre^T [A | 1] yields db0 next to dW0
-        }
-        put(a_hi, a_lo, a_off(r, g, KT), v);
-        if (arow) *reinterpret_cast<float4*>(arow + (size_t)r * KT + g * 4) = vh;
-    }
-    for (int it = tid0; it < 2 * 3 * C4; it += nthreads) {
-        const int r = SPT * NQ + it / (3 * C4), g = it % (3 * C4);
-        put(a_hi, a_lo, a_off(r, g, KT), f4_zero());
-        if (arow) *reinterpret_cast<float4*>(arow + (size_t)r * KT + g * 4) = f4_zero();
-    }
-}
-
-__device__ __forceinline__ void gather_tile(const tf_vm_field_t& f, const float* __restrict__ xyz, const float* __restrict__ level, int64_t n_total,
-                                            const float units[3], int64_t s_base, int KT, uint8_t* a_hi, uint8_t* a_lo, float* arow, int nthreads, int tid0 = -1) {
-    if (tid0 < 0) tid0 = threadIdx.x;      // threads tid0 = 0..nthreads-1 of the calling group share the tile
-    if (level != nullptr && f.n_levels > 1) gather_tile_t<true>(f, xyz, level, n_total, units, s_base, KT, a_hi, a_lo, arow, nthreads, tid0);
-    else gather_tile_t<false>(f, xyz, level, n_total, units, s_base, KT, a_hi, a_lo, arow, nthreads, tid0);
-}
-
 __device__ __forceinline__ float* twin(const float* p, const float* base0, float* g0, const float* basem, float* gm) {
     return p == base0 ? g0 : gm + (p - basem);
 }
-template <bool TWO>
-__device__ __forceinline__ void scatter_plane(float* t0, float* t1, const Levels& L, const SitePlan<TWO>& p, int jx, int jy, int C, int c, float4 d) {
-    {
-        const Tap1 &tx = p.x0[jx], &ty = p.y0[jy];
-        const float w0 = 1.f - L.fl;
-        red_add_v4(t0 + (size_t)(ty.i0 * L.W0 + tx.i0) * C + c, f4_scale(w0 * (tx.w0 * ty.w0), d));
-        red_add_v4(t0 + (size_t)(ty.i0 * L.W0 + tx.i1) * C + c, f4_scale(w0 * (tx.w1 * ty.w0), d));
-        red_add_v4(t0 + (size_t)(ty.i1 * L.W0 + tx.i0) * C + c, f4_scale(w0 * (tx.w0 * ty.w1), d));
-        red_add_v4(t0 + (size_t)(ty.i1 * L.W0 + tx.i1) * C + c, f4_scale(w0 * (tx.w1 * ty.w1), d));
-    }
-    if (TWO && L.fl > 0.f) {
-        const Tap1 &tx = p.x1[jx], &ty = p.y1[jy];
-        red_add_v4(t1 + (size_t)(ty.i0 * L.W1 + tx.i0) * C + c, f4_scale(L.fl * (tx.w0 * ty.w0), d));
-        red_add_v4(t1 + (size_t)(ty.i0 * L.W1 + tx.i1) * C + c, f4_scale(L.fl * (tx.w1 * ty.w0), d));
-        red_add_v4(t1 + (size_t)(ty.i1 * L.W1 + tx.i0) * C + c, f4_scale(L.fl * (tx.w0 * ty.w1), d));
-        red_add_v4(t1 + (size_t)(ty.i1 * L.W1 + tx.i1) * C + c, f4_scale(L.fl * (tx.w1 * ty.w1), d));
-    }
-}
-template <bool TWO>
-__device__ __forceinline__ void scatter_line(float* t0, float* t1, const Levels& L, const SitePlan<TWO>& p, int jl, int C, int c, float4 d) {
-    const float w0 = 1.f - L.fl;
-    red_add_v4(t0 + (size_t)p.l0[jl].i0 * C + c, f4_scale(w0 * p.l0[jl].w0, d));
-    red_add_v4(t0 + (size_t)p.l0[jl].i1 * C + c, f4_scale(w0 * p.l0[jl].w1, d));
-    if (TWO && L.fl > 0.f) {
-        red_add_v4(t1 + (size_t)p.l1[jl].i0 * C + c, f4_scale(L.fl * p.l1[jl].w0, d));
-        red_add_v4(t1 + (size_t)p.l1[jl].i1 * C + c, f4_scale(L.fl * p.l1[jl].w1, d));
-    }
-}
-
 __device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 __device__ __forceinline__ float4 f4_fma4(float4 a, float4 b, float4 c) { return make_float4(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y), fmaf(a.z, b.z, c.z), fmaf(a.w, b.w, c.w)); }
-
-// Scatter the feature gradients dA (fp32 tile in shared memory, row stride `ld` floats) of one stencil tile
-// into the plane / line gradients; shared positions are reduced in registers first.
-template <bool TWO>
-__device__ __forceinline__ void scatter_tile_t(const tf_vm_field_t& f, const tf_vm_mut_t& gm, const float* __restrict__ xyz,
-                                             const float* __restrict__ level, int64_t n_total, const float units[3], int64_t s_base,
-                                             const float* dA, int ld, int nthreads, int tid0) {
-    const int C = f.n_comp, C4 = C / 4;
-    const bool has_level = level != nullptr;
-    const int n_tasks = SPT * 3 * C4;
-    for (int task = tid0; task < n_tasks; task += nthreads) {
-        const int c4 = task % C4, si = task / C4, i = si % 3, s = si / 3;
-        const int64_t n = s_base + s;
-        if (n >= n_total) continue;
-        const int g = i * C4 + c4, r0 = s * NQ, c = c4 * 4;
-        const Axes a = axes(i);
-        const float x[3] = {xyz[n * 3 + 0], xyz[n * 3 + 1], xyz[n * 3 + 2]};
-        const Levels L = levels(f, has_level ? level[n] : 0.f, has_level, i);
-        const Coords k = coords(f, x, units, a);
-        float* pm0 = twin(L.pt0, f.plane[i], gm.plane[i], f.plane_mip[i], gm.plane_mip[i]);
-        float* pm1 = twin(L.pt1, f.plane[i], gm.plane[i], f.plane_mip[i], gm.plane_mip[i]);
-        float* lm0 = twin(L.lt0, f.line[i], gm.line[i], f.line_mip[i], gm.line_mip[i]);
-        float* lm1 = twin(L.lt1, f.line[i], gm.line[i], f.line_mip[i], gm.line_mip[i]);
-        const float* dcol = dA + g * 4;
-        auto drow = [&](int r) { return *reinterpret_cast<const float4*>(dcol + (size_t)r * ld); };
-        const int r_m0 = r0 + 1 + 2 * a.m0, r_m1 = r0 + 1 + 2 * a.m1, r_vm = r0 + 1 + 2 * a.vm;
-        const SitePlan<TWO> sp = make_plan<TWO>(L, k);
-        LineFetch<TWO> fl0, fl1, fl2;
-        PlaneFetch<TWO> fp0, fpa, fpb;
-        fl0.load(L, sp, 0, C, c); fp0.load(L, sp, 0, 0, C, c); fl1.load(L, sp, 1, C, c); fl2.load(L, sp, 2, C, c);
-        fpa.load(L, sp, 1, 0, C, c); fpb.load(L, sp, 2, 0, C, c);
-        const float4 d0 = drow(r0), dvp = drow(r_vm), dvm = drow(r_vm + 1);
-        const float4 L0 = fl0.value(L, sp, 0), P0 = fp0.value(L, sp, 0, 0);
-        // plane gradient at the centre position: centre and +-vm queries share it
-        float4 dP = f4_mul(d0, L0);
-        dP = f4_fma4(dvp, fl1.value(L, sp, 1), dP);
-        dP = f4_fma4(dvm, fl2.value(L, sp, 2), dP);
-        scatter_plane<TWO>(pm0, pm1, L, sp, 0, 0, C, c, dP);
-        scatter_line<TWO>(lm0, lm1, L, sp, 1, C, c, f4_mul(dvp, P0));
-        scatter_line<TWO>(lm0, lm1, L, sp, 2, C, c, f4_mul(dvm, P0));
-        // line gradient at the centre position: centre and the four in-plane queries share it
-        float4 dL = f4_mul(d0, P0);
-        {
-            const float4 da = drow(r_m0), db = drow(r_m0 + 1);
-            dL = f4_fma4(da, fpa.value(L, sp, 1, 0), dL);
-            dL = f4_fma4(db, fpb.value(L, sp, 2, 0), dL);
-            fpa.load(L, sp, 0, 1, C, c); fpb.load(L, sp, 0, 2, C, c);
-            scatter_plane<TWO>(pm0, pm1, L, sp, 1, 0, C, c, f4_mul(da, L0));
-            scatter_plane<TWO>(pm0, pm1, L, sp, 2, 0, C, c, f4_mul(db, L0));
-        }
-        {
-            const float4 da = drow(r_m1), db = drow(r_m1 + 1);
-            dL = f4_fma4(da, fpa.value(L, sp, 0, 1), dL);
-            dL = f4_fma4(db, fpb.value(L, sp, 0, 2), dL);
-            scatter_plane<TWO>(pm0, pm1, L, sp, 0, 1, C, c, f4_mul(da, L0));
-            scatter_plane<TWO>(pm0, pm1, L, sp, 0, 2, C, c, f4_mul(db, L0));
-        }
-        scatter_line<TWO>(lm0, lm1, L, sp, 0, C, c, dL);
-    }
-}
-
-__device__ __forceinline__ void scatter_tile(const tf_vm_field_t& f, const tf_vm_mut_t& gm, const float* __restrict__ xyz,
-                                             const float* __restrict__ level, int64_t n_total, const float units[3], int64_t s_base,
-                                             const float* dA, int ld, int nthreads, int tid0 = -1) {
-    if (tid0 < 0) tid0 = threadIdx.x;
-    if (level != nullptr && f.n_levels > 1) scatter_tile_t<true>(f, gm, xyz, level, n_total, units, s_base, dA, ld, nthreads, tid0);
-    else scatter_tile_t<false>(f, gm, xyz, level, n_total, units, s_base, dA, ld, nthreads, tid0);
-}
 
 // ---- register-lean variants (the warp-specialised backward runs its memory group next to a math group and cannot
 // ---- afford the ~200 registers of the batched fetch): sampling plans are built position by position (16 registers
@@ -380,31 +189,31 @@ template <bool TWO>
 __device__ __forceinline__ void scatter_plane_pos(float* t0, float* t1, const Levels& L, const PlanePos<TWO>& p, int C, int c, float4 d) {
     {
         const float w0 = 1.f - L.fl;
-        red_add_v4(t0 + (size_t)(p.y0.i0 * L.W0 + p.x0.i0) * C + c, f4_scale(w0 * (p.x0.w0 * p.y0.w0), d));
-        red_add_v4(t0 + (size_t)(p.y0.i0 * L.W0 + p.x0.i1) * C + c, f4_scale(w0 * (p.x0.w1 * p.y0.w0), d));
-        red_add_v4(t0 + (size_t)(p.y0.i1 * L.W0 + p.x0.i0) * C + c, f4_scale(w0 * (p.x0.w0 * p.y0.w1), d));
-        red_add_v4(t0 + (size_t)(p.y0.i1 * L.W0 + p.x0.i1) * C + c, f4_scale(w0 * (p.x0.w1 * p.y0.w1), d));
+        red_add_v4(t0 + texel_off(p.y0.i0, p.x0.i0, L.W0, C, c), f4_scale(w0 * (p.x0.w0 * p.y0.w0), d));
+        red_add_v4(t0 + texel_off(p.y0.i0, p.x0.i1, L.W0, C, c), f4_scale(w0 * (p.x0.w1 * p.y0.w0), d));
+        red_add_v4(t0 + texel_off(p.y0.i1, p.x0.i0, L.W0, C, c), f4_scale(w0 * (p.x0.w0 * p.y0.w1), d));
+        red_add_v4(t0 + texel_off(p.y0.i1, p.x0.i1, L.W0, C, c), f4_scale(w0 * (p.x0.w1 * p.y0.w1), d));
     }
     if (TWO && L.fl > 0.f) {
-        red_add_v4(t1 + (size_t)(p.y1.i0 * L.W1 + p.x1.i0) * C + c, f4_scale(L.fl * (p.x1.w0 * p.y1.w0), d));
-        red_add_v4(t1 + (size_t)(p.y1.i0 * L.W1 + p.x1.i1) * C + c, f4_scale(L.fl * (p.x1.w1 * p.y1.w0), d));
-        red_add_v4(t1 + (size_t)(p.y1.i1 * L.W1 + p.x1.i0) * C + c, f4_scale(L.fl * (p.x1.w0 * p.y1.w1), d));
-        red_add_v4(t1 + (size_t)(p.y1.i1 * L.W1 + p.x1.i1) * C + c, f4_scale(L.fl * (p.x1.w1 * p.y1.w1), d));
+        red_add_v4(t1 + texel_off(p.y1.i0, p.x1.i0, L.W1, C, c), f4_scale(L.fl * (p.x1.w0 * p.y1.w0), d));
+        red_add_v4(t1 + texel_off(p.y1.i0, p.x1.i1, L.W1, C, c), f4_scale(L.fl * (p.x1.w1 * p.y1.w0), d));
+        red_add_v4(t1 + texel_off(p.y1.i1, p.x1.i0, L.W1, C, c), f4_scale(L.fl * (p.x1.w0 * p.y1.w1), d));
+        red_add_v4(t1 + texel_off(p.y1.i1, p.x1.i1, L.W1, C, c), f4_scale(L.fl * (p.x1.w1 * p.y1.w1), d));
     }
 }
 template <bool TWO>
 __device__ __forceinline__ void scatter_line_pos(float* t0, float* t1, const Levels& L, const LinePos<TWO>& p, int C, int c, float4 d) {
     const float w0 = 1.f - L.fl;
-    red_add_v4(t0 + (size_t)p.l0.i0 * C + c, f4_scale(w0 * p.l0.w0, d));
-    red_add_v4(t0 + (size_t)p.l0.i1 * C + c, f4_scale(w0 * p.l0.w1, d));
+    red_add_v4(t0 + texel_off(0, p.l0.i0, 0, C, c), f4_scale(w0 * p.l0.w0, d));
+    red_add_v4(t0 + texel_off(0, p.l0.i1, 0, C, c), f4_scale(w0 * p.l0.w1, d));
     if (TWO && L.fl > 0.f) {
-        red_add_v4(t1 + (size_t)p.l1.i0 * C + c, f4_scale(L.fl * p.l1.w0, d));
-        red_add_v4(t1 + (size_t)p.l1.i1 * C + c, f4_scale(L.fl * p.l1.w1, d));
+        red_add_v4(t1 + texel_off(0, p.l1.i0, 0, C, c), f4_scale(L.fl * p.l1.w0, d));
+        red_add_v4(t1 + texel_off(0, p.l1.i1, 0, C, c), f4_scale(L.fl * p.l1.w1, d));
     }
 }
 
 template <bool TWO>
-__device__ __forceinline__ void gather_tile_lean_t(const tf_vm_field_t& f, const float* __restrict__ xyz, const float* __restrict__ level,
+__device__ __forceinline__ void gather_tile_lean_t(const tf_vm_field_t& f, const LevelTab& tab, const float* __restrict__ xyz, const float* __restrict__ level,
                                                    int64_t n_total, const float units[3], int64_t s_base, int KT, uint8_t* a_hi, uint8_t* a_lo,
                                                    float* arow, int nthreads, int tid0) {
     const int C = f.n_comp, C4 = C / 4, G = KT / 4;
@@ -426,7 +235,7 @@ __device__ __forceinline__ void gather_tile_lean_t(const tf_vm_field_t& f, const
             continue;
         }
         const float x[3] = {xyz[n * 3 + 0], xyz[n * 3 + 1], xyz[n * 3 + 2]};
-        const Levels L = levels(f, has_level ? level[n] : 0.f, has_level, i);
+        const Levels L = levels(f, tab, has_level ? level[n] : 0.f, has_level, i);
         const Coords k = coords(f, x, units, a);
         const float4 L0 = fetch_line<TWO>(L, line_pos<TWO>(L, k.lv[0]), C, c);
         const float4 P0 = fetch_plane<TWO>(L, plane_pos<TWO>(L, k.pu[0], k.pv[0]), C, c);
@@ -464,16 +273,16 @@ __device__ __forceinline__ void gather_tile_lean_t(const tf_vm_field_t& f, const
         if (arow) *reinterpret_cast<float4*>(arow + (size_t)r * KT + g * 4) = f4_zero();
     }
 }
-__device__ __forceinline__ void gather_tile_lean(const tf_vm_field_t& f, const float* __restrict__ xyz, const float* __restrict__ level, int64_t n_total,
+__device__ __forceinline__ void gather_tile_lean(const tf_vm_field_t& f, const LevelTab& tab, const float* __restrict__ xyz, const float* __restrict__ level, int64_t n_total,
                                                  const float units[3], int64_t s_base, int KT, uint8_t* a_hi, uint8_t* a_lo, float* arow, int nthreads,
                                                  int tid0) {
-    if (level != nullptr && f.n_levels > 1) gather_tile_lean_t<true>(f, xyz, level, n_total, units, s_base, KT, a_hi, a_lo, arow, nthreads, tid0);
-    else gather_tile_lean_t<false>(f, xyz, level, n_total, units, s_base, KT, a_hi, a_lo, arow, nthreads, tid0);
+    if (level != nullptr && f.n_levels > 1) gather_tile_lean_t<true>(f, tab, xyz, level, n_total, units, s_base, KT, a_hi, a_lo, arow, nthreads, tid0);
+    else gather_tile_lean_t<false>(f, tab, xyz, level, n_total, units, s_base, KT, a_hi, a_lo, arow, nthreads, tid0);
 }
 
 // dA may live in shared memory or in a global scratch tile written by other warps of the same CTA (read with ld.global.cg)
 template <bool TWO>
-__device__ __forceinline__ void scatter_tile_lean_t(const tf_vm_field_t& f, const tf_vm_mut_t& gm, const float* __restrict__ xyz,
+__device__ __forceinline__ void scatter_tile_lean_t(const tf_vm_field_t& f, const LevelTab& tab, const tf_vm_mut_t& gm, const float* __restrict__ xyz,
                                                     const float* __restrict__ level, int64_t n_total, const float units[3], int64_t s_base,
                                                     const float* dA, int ld, int nthreads, int tid0, bool da_global) {
     const int C = f.n_comp, C4 = C / 4;
@@ -486,7 +295,7 @@ __device__ __forceinline__ void scatter_tile_lean_t(const tf_vm_field_t& f, cons
         const int g = i * C4 + c4, r0 = s * NQ, c = c4 * 4;
         const Axes a = axes(i);
         const float x[3] = {xyz[n * 3 + 0], xyz[n * 3 + 1], xyz[n * 3 + 2]};
-        const Levels L = levels(f, has_level ? level[n] : 0.f, has_level, i);
+        const Levels L = levels(f, tab, has_level ? level[n] : 0.f, has_level, i);
         const Coords k = coords(f, x, units, a);
         float* pm0 = twin(L.pt0, f.plane[i], gm.plane[i], f.plane_mip[i], gm.plane_mip[i]);
         float* pm1 = twin(L.pt1, f.plane[i], gm.plane[i], f.plane_mip[i], gm.plane_mip[i]);
@@ -527,11 +336,11 @@ __device__ __forceinline__ void scatter_tile_lean_t(const tf_vm_field_t& f, cons
         scatter_line_pos<TWO>(lm0, lm1, L, l0, C, c, dL);
     }
 }
-__device__ __forceinline__ void scatter_tile_lean(const tf_vm_field_t& f, const tf_vm_mut_t& gm, const float* __restrict__ xyz,
+__device__ __forceinline__ void scatter_tile_lean(const tf_vm_field_t& f, const LevelTab& tab, const tf_vm_mut_t& gm, const float* __restrict__ xyz,
                                                   const float* __restrict__ level, int64_t n_total, const float units[3], int64_t s_base,
                                                   const float* dA, int ld, int nthreads, int tid0, bool da_global = false) {
-    if (level != nullptr && f.n_levels > 1) scatter_tile_lean_t<true>(f, gm, xyz, level, n_total, units, s_base, dA, ld, nthreads, tid0, da_global);
-    else scatter_tile_lean_t<false>(f, gm, xyz, level, n_total, units, s_base, dA, ld, nthreads, tid0, da_global);
+    if (level != nullptr && f.n_levels > 1) scatter_tile_lean_t<true>(f, tab, gm, xyz, level, n_total, units, s_base, dA, ld, nthreads, tid0, da_global);
+    else scatter_tile_lean_t<false>(f, tab, gm, xyz, level, n_total, units, s_base, dA, ld, nthreads, tid0, da_global);
 }
 
 }  // namespace site
