@@ -88,6 +88,47 @@ __device__ __forceinline__ void softplus100_fast_both(float x, float& sp, float&
     sg = x >= 0.f ? r : t * r;
 }
 
+// ---- packed fp32 pairs (sm_100a FFMA2 / FMUL2 / FADD2): one issue slot for two lanes of work; a pair built from the same
+// ---- register or from a constant is a free broadcast operand in SASS.  Used where the epilogues are issue-bound.
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) { uint64_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) { uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ uint64_t bcast2(float c) { return pack2(c, c); }
+// log1p_01 of a pair (same polynomial, same operation order as the scalar version: bit-identical results)
+__device__ __forceinline__ uint64_t log1p_01_2(uint64_t t) {
+    uint64_t g = bcast2(-3.176057010e-03f);
+    g = ffma2(g, t, bcast2(1.954252722e-02f));
+    g = ffma2(g, t, bcast2(-5.637361275e-02f));
+    g = ffma2(g, t, bcast2(1.054362379e-01f));
+    g = ffma2(g, t, bcast2(-1.526966707e-01f));
+    g = ffma2(g, t, bcast2(1.966327426e-01f));
+    g = ffma2(g, t, bcast2(-2.495161626e-01f));
+    g = ffma2(g, t, bcast2(3.332971050e-01f));
+    g = ffma2(g, t, bcast2(-4.999989265e-01f));
+    g = ffma2(g, t, bcast2(9.999999947e-01f));
+    return fmul2(g, t);
+}
+// softplus100_fast of two values
+__device__ __forceinline__ void softplus100_fast2(float x0, float x1, float& s0, float& s1) {
+    const float t0 = ex2_approx(-fabsf(x0) * 144.26950408889634f), t1 = ex2_approx(-fabsf(x1) * 144.26950408889634f);
+    const uint64_t r = ffma2(log1p_01_2(pack2(t0, t1)), bcast2(0.01f), pack2(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));
+    unpack2(r, s0, s1);
+}
+// softplus100_fast_both of two values
+__device__ __forceinline__ void softplus100_fast_both2(float x0, float x1, float& s0, float& s1, float& g0, float& g1) {
+    const float t0 = ex2_approx(-fabsf(x0) * 144.26950408889634f), t1 = ex2_approx(-fabsf(x1) * 144.26950408889634f);
+    const uint64_t t = pack2(t0, t1);
+    const uint64_t r = ffma2(log1p_01_2(t), bcast2(0.01f), pack2(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));
+    unpack2(r, s0, s1);
+    float d0, d1;
+    unpack2(fadd2(t, bcast2(1.f)), d0, d1);
+    const float r0 = __fdividef(1.f, d0), r1 = __fdividef(1.f, d1);
+    g0 = x0 >= 0.f ? r0 : t0 * r0;
+    g1 = x1 >= 0.f ? r1 : t1 * r1;
+}
+
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 // vector reduction into global memory (sm_90+): 4 floats, 16-byte aligned

@@ -336,10 +336,19 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_bwd_tc_kernel(TcBwdParams 
                     for (int j = 0; j < 4; ++j) hc[j] = __ldg(src + j);
                 }
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    float sg;
-                    softplus100_fast_both(v[j] + b0s[col0 + j], sp[j], sg);
-                    v[j] = fmaf(gq, w1s[col0 + j], hcv[j]) * sg;         // dPre = dPost * sigmoid
+                for (int j = 0; j < 16; j += 4) {
+                    const float4 bb = *reinterpret_cast<const float4*>(b0s + col0 + j);
+                    const float4 ww = *reinterpret_cast<const float4*>(w1s + col0 + j);
+                    float sg[4];
+                    float pre0, pre1, pre2, pre3;
+                    unpack2(fadd2(pack2(v[j], v[j + 1]), pack2(bb.x, bb.y)), pre0, pre1);
+                    unpack2(fadd2(pack2(v[j + 2], v[j + 3]), pack2(bb.z, bb.w)), pre2, pre3);
+                    softplus100_fast_both2(pre0, pre1, sp[j], sp[j + 1], sg[0], sg[1]);
+                    softplus100_fast_both2(pre2, pre3, sp[j + 2], sp[j + 3], sg[2], sg[3]);
+                    // dPre = dPost * sigmoid, dPost = gq W1[0,:] + [centre] g_feat W1[1:]
+                    const uint64_t gg = bcast2(gq);
+                    unpack2(fmul2(ffma2(gg, pack2(ww.x, ww.y), pack2(hcv[j], hcv[j + 1])), pack2(sg[0], sg[1])), v[j], v[j + 1]);
+                    unpack2(fmul2(ffma2(gg, pack2(ww.z, ww.w), pack2(hcv[j + 2], hcv[j + 3])), pack2(sg[2], sg[3])), v[j + 2], v[j + 3]);
                 }
                 if (tid != 0) { PROF(12) }
                 float4* dst = reinterpret_cast<float4*>(p.dpre + (size_t)(tile_row0 + row) * H + col0);

@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_fwd_tc_kernel(TcParams p) 
             const int64_t n = tile * spt + s;
             const bool centre = q == 0 && s < spt && n < p.n;
             const uint32_t dcol = d_tmem + ((uint32_t)(lq * 32) << 16);
-            float psum = 0.f;
+            uint64_t psum2 = pack2(0.f, 0.f);                 // two interleaved partial sums (packed FFMA2)
             for (int c0 = chh * 32; c0 < H; c0 += 32 * NCG) {
                 if (TF_DBG(p, 4)) break;
 #pragma unroll
@@ -267,10 +267,13 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_fwd_tc_kernel(TcParams p) 
                     for (int j = 0; j < 16; j += 4) {
                         const float4 bb = *reinterpret_cast<const float4*>(b0s + cc + j);
                         const float4 ww = *reinterpret_cast<const float4*>(w1s + cc + j);
-                        v[j + 0] = softplus100_fast(v[j + 0] + bb.x); psum = fmaf(v[j + 0], ww.x, psum);
-                        v[j + 1] = softplus100_fast(v[j + 1] + bb.y); psum = fmaf(v[j + 1], ww.y, psum);
-                        v[j + 2] = softplus100_fast(v[j + 2] + bb.z); psum = fmaf(v[j + 2], ww.z, psum);
-                        v[j + 3] = softplus100_fast(v[j + 3] + bb.w); psum = fmaf(v[j + 3], ww.w, psum);
+                        float pre0, pre1, pre2, pre3;
+                        unpack2(fadd2(pack2(v[j], v[j + 1]), pack2(bb.x, bb.y)), pre0, pre1);
+                        unpack2(fadd2(pack2(v[j + 2], v[j + 3]), pack2(bb.z, bb.w)), pre2, pre3);
+                        softplus100_fast2(pre0, pre1, v[j], v[j + 1]);
+                        softplus100_fast2(pre2, pre3, v[j + 2], v[j + 3]);
+                        psum2 = ffma2(pack2(v[j], v[j + 1]), pack2(ww.x, ww.y), psum2);
+                        psum2 = ffma2(pack2(v[j + 2], v[j + 3]), pack2(ww.z, ww.w), psum2);
                     }
                     if (centre && p.spc) {
                         float4* dst = reinterpret_cast<float4*>(p.spc + (size_t)n * H + cc);
@@ -279,7 +282,9 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_fwd_tc_kernel(TcParams p) 
                     }
                 }
             }
-            sdfs[((t & 1) * NCG + chh) * TM + row] = psum;
+            float psum, psum_b;
+            unpack2(psum2, psum, psum_b);
+            sdfs[((t & 1) * NCG + chh) * TM + row] = psum + psum_b;
             tc::fence_before_sync();
             tc::bar_sync(1, NWORK);                              // staging tile of t+1 complete, partial sums of t visible
             // ---- A operand of tile t+1 -> tensor memory (the accumulator and the A region are free: MMAs of t are done)
