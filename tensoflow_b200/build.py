@@ -90,17 +90,21 @@ PROBE_BIN = PKG.parent / "tests" / "probes" / "_bin" / "tc_probe"
 
 
 def build_probes(force: bool = False) -> Path | None:
-    """tests/probes/tc_probe.cu -> tests/probes/_bin/tc_probe: the tcgen05 self-test / issue-rate probe (test infrastructure,
-    a standalone executable; nothing of it is linked into libtensoflow_b200.so)."""
-    if not PROBE_SRC.exists():
+    """tests/probes/*.cu -> tests/probes/_bin/<name>: standalone probe executables (test infrastructure; nothing of them is
+    linked into libtensoflow_b200.so): tc_probe = tcgen05 operand-layout self-test / issue-rate probe, bulk_probe =
+    cp.async.bulk ring streaming probe.  Returns the tc_probe path."""
+    srcs = sorted(PROBE_SRC.parent.glob("*.cu"))
+    if not srcs:
         return None
-    h = hashlib.sha256(PROBE_SRC.read_bytes() + (CSRC / "tc_common.cuh").read_bytes()).hexdigest()
+    h = hashlib.sha256(b"".join(p.read_bytes() for p in srcs) + (CSRC / "tc_common.cuh").read_bytes()).hexdigest()
     stamp = PROBE_BIN.parent / ".stamp"
-    if not force and PROBE_BIN.exists() and stamp.exists() and stamp.read_text().strip() == h:
+    bins = [PROBE_BIN.parent / p.stem for p in srcs]
+    if not force and all(b.exists() for b in bins) and stamp.exists() and stamp.read_text().strip() == h:
         return PROBE_BIN
     PROBE_BIN.parent.mkdir(parents=True, exist_ok=True)
-    subprocess.run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-o", str(PROBE_BIN),
-                    str(PROBE_SRC)], check=True)
+    for src, out in zip(srcs, bins):
+        subprocess.run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-o", str(out),
+                        str(src)], check=True)
     stamp.write_text(h)
     return PROBE_BIN
 
