@@ -17,7 +17,9 @@ namespace {
 
 // RS = rows (GEMM K) per stage: 32, or 16 when both operands are 256 wide (shared-memory budget)
 constexpr int NTH = 512;
-constexpr int TPT = (8 * 64 + NTH - 1) / NTH;   // staging tasks per thread and operand (32 rows x 256 columns at most)
+constexpr int NWORK = NTH - 32;     // staging warps 1..15; warp 0 only issues the MMAs (a thread that issues a dozen MMAs back to back
+                                    // is blocked while the tensor queue drains: it must not be one the staging warps wait for)
+constexpr int TPT = 2;              // staging tasks per worker and stage (X and Y tasks share one list: <= 960 per stage)
 template <int RS> struct Stage { static constexpr uint32_t SBO = (RS / 4) * 128 + 16; };   // 8-row-group stride of a staged operand (padded: bank spread)
 
 __device__ __forceinline__ float4 hi4(float4 v) { return make_float4(tc::tf32_rn(v.x), tc::tf32_rn(v.y), tc::tf32_rn(v.z), tc::tf32_rn(v.w)); }
@@ -25,44 +27,51 @@ __device__ __forceinline__ float4 lo4(float4 v, float4 h) {
     return make_float4(tc::tf32_rn(v.x - h.x), tc::tf32_rn(v.y - h.y), tc::tf32_rn(v.z - h.z), tc::tf32_rn(v.w - h.w));
 }
 
-// One staging task = the 4x4 block (rows 4c..4c+3, columns 4g..4g+3) of src [rows][W]; a thread owns up to
-// 2 tasks per operand and stage.  The global loads of stage it+1 are issued into registers before stage it is
-// converted and stored, so HBM latency overlaps the staging and MMA work.
+// One staging task = the 4x4 block (rows 4c..4c+3, columns 4g..4g+3) of X [rows][M] or Y [rows][N].  The global loads
+// of stage it+2 are issued into registers before stage it+1 is converted and stored, so HBM latency overlaps the
+// staging and MMA work.
 struct Prefetch { float4 v[TPT][4]; };
-// per-thread staging plan of one operand (fixed for the whole kernel: only the row base advances)
-struct StagePlan { int src_off[TPT]; int row[TPT]; uint32_t smem_off[TPT]; bool on[TPT]; };
+// per-worker staging plan (fixed for the whole kernel: only the row base advances): task list = Y tasks then X tasks
+struct StagePlan { int src_off[TPT]; int row[TPT]; int ld[TPT]; uint32_t smem_off[TPT]; bool on[TPT], is_x[TPT]; };
 
 template <int RS>
-__device__ __forceinline__ StagePlan make_stage_plan(int W) {
+__device__ __forceinline__ StagePlan make_stage_plan(int M, int N, int wtid) {
     constexpr uint32_t SBO = Stage<RS>::SBO;
     StagePlan p;
-    const int G = W / 4, n_tasks = (RS / 4) * G;
+    const int ty = (RS / 4) * (N / 4), tx = (RS / 4) * (M / 4);
 #pragma unroll
     for (int k = 0; k < TPT; ++k) {
-        const int it = threadIdx.x + k * NTH;
+        int it = wtid + k * NWORK;
+        p.is_x[k] = it >= ty;
+        if (p.is_x[k]) it -= ty;
+        const int W = p.is_x[k] ? M : N, G = W / 4;
+        p.on[k] = wtid >= 0 && it < (p.is_x[k] ? tx : ty);
         const int g = it % G, c = it / G;
-        p.on[k] = it < n_tasks;
         p.row[k] = c * 4;
+        p.ld[k] = W;
         p.src_off[k] = c * 4 * W + g * 4;
         const int w = g * 4;                              // first of the task's 4 columns (w & 7 is 0 or 4)
         p.smem_off[k] = (uint32_t)(w >> 3) * SBO + c * 128 + (w & 7) * 16;
     }
     return p;
 }
-__device__ __forceinline__ void stage_load(const float* __restrict__ src, int64_t r0, int64_t r_end, int W, const StagePlan& sp, Prefetch& pf) {
-    const float* base = src + (size_t)r0 * W;
+__device__ __forceinline__ void stage_load(const float* __restrict__ X, const float* __restrict__ Y, int64_t r0, int64_t r_end, const StagePlan& sp,
+                                           Prefetch& pf) {
 #pragma unroll
     for (int k = 0; k < TPT; ++k) {
+        const float* base = (sp.is_x[k] ? X : Y) + (size_t)r0 * sp.ld[k] + sp.src_off[k];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-            pf.v[k][i] = (sp.on[k] && r0 + sp.row[k] + i < r_end) ? ldg4(base + sp.src_off[k] + i * W) : make_float4(0.f, 0.f, 0.f, 0.f);
+            pf.v[k][i] = (sp.on[k] && r0 + sp.row[k] + i < r_end) ? ldg4(base + i * sp.ld[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
 // transpose the 4x4 blocks in registers (four 16-byte K-major units each), split into tf32 hi / lo, store
-__device__ __forceinline__ void stage_store(const Prefetch& pf, const StagePlan& sp, uint8_t* hi, uint8_t* lo) {
+__device__ __forceinline__ void stage_store(const Prefetch& pf, const StagePlan& sp, uint8_t* xs_hi, uint8_t* xs_lo, uint8_t* ys_hi, uint8_t* ys_lo) {
 #pragma unroll
     for (int k = 0; k < TPT; ++k) {
         if (!sp.on[k]) continue;
+        uint8_t* hi = sp.is_x[k] ? xs_hi : ys_hi;
+        uint8_t* lo = sp.is_x[k] ? xs_lo : ys_lo;
         const float4* v = pf.v[k];
         const float4 t[4] = {make_float4(v[0].x, v[1].x, v[2].x, v[3].x), make_float4(v[0].y, v[1].y, v[2].y, v[3].y),
                              make_float4(v[0].z, v[1].z, v[2].z, v[3].z), make_float4(v[0].w, v[1].w, v[2].w, v[3].w)};
@@ -87,18 +96,23 @@ __global__ void __launch_bounds__(NTH, 1) xty_tc_kernel(const float* __restrict_
     const uint32_t x_part = (uint32_t)(MP / 8) * SBO, y_part = (uint32_t)(N / 8) * SBO;
     const uint32_t stage_bytes = 2 * (x_part + y_part);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * stage_bytes);
-    uint64_t* empty = bars;          // [2]
-    uint64_t* done = bars + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+    uint64_t* empty = bars;          // [2] stage consumed by its MMAs
+    uint64_t* ready = bars + 2;      // [2] stage written by the staging warps
+    uint64_t* done = bars + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int MT = MP / 128;
     const int ncol_tile = N <= 128 ? 128 : 256;      // TMEM column stride between the M tiles
 
     if (warp == 0) tc::tmem_alloc<512>(tmem_slot);
     if (tid == 0) {
-        tc::mbar_init(&empty[0], 1); tc::mbar_init(&empty[1], 1); tc::mbar_init(done, 1);
+        tc::mbar_init(&empty[0], 1); tc::mbar_init(&empty[1], 1); tc::mbar_init(&ready[0], NWORK); tc::mbar_init(&ready[1], NWORK);
+        tc::mbar_init(done, 1);
         tc::mbar_fence_init();
     }
+    // the padding rows of the M side (MP > M) are never written by a staging task: clear both stages once
+    for (uint32_t i = tid * 16; i < 2 * stage_bytes; i += NTH * 16) *reinterpret_cast<float4*>(smem + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    tc::fence_async_smem();
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
@@ -109,53 +123,61 @@ __global__ void __launch_bounds__(NTH, 1) xty_tc_kernel(const float* __restrict_
     const int64_t r_end = r_begin + rows_per_cta < rows ? r_begin + rows_per_cta : rows;
     const int64_t n_stages = r_begin < r_end ? (r_end - r_begin + RS - 1) / RS : 0;
 
-    // register prefetch two stages ahead: sets (px0, py0) / (px1, py1) alternate
-    Prefetch px0, py0, px1, py1;
-    const StagePlan spx = make_stage_plan<RS>(M), spy = make_stage_plan<RS>(N);
-    if (n_stages > 0) { stage_load(X, r_begin, r_end, M, spx, px0); stage_load(Y, r_begin, r_end, N, spy, py0); }
-    if (n_stages > 1) { stage_load(X, r_begin + RS, r_end, M, spx, px1); stage_load(Y, r_begin + RS, r_end, N, spy, py1); }
-    auto do_stage = [&](int64_t it, Prefetch& px, Prefetch& py) {
-        const int buf = (int)(it & 1);
-        uint8_t* xs_hi = smem + (size_t)buf * stage_bytes;
-        uint8_t* xs_lo = xs_hi + x_part;
-        uint8_t* ys_hi = xs_lo + x_part;
-        uint8_t* ys_lo = ys_hi + y_part;
-        if (it >= 2) tc::mbar_wait(&empty[buf], (uint32_t)(((it >> 1) - 1) & 1));
-        stage_store(px, spx, xs_hi, xs_lo);
-        stage_store(py, spy, ys_hi, ys_lo);
-        if (it + 2 < n_stages) {
-            const int64_t r2 = r_begin + (it + 2) * RS;
-            stage_load(X, r2, r_end, M, spx, px); stage_load(Y, r2, r_end, N, spy, py);
-        }
-        tc::fence_async_smem();
-        tc::fence_before_sync();
-        __syncthreads();
-        tc::fence_after_sync();
-        if (tid == 0) {
-            // one descriptor per operand part and stage; the MMAs only advance its start address
-            const uint64_t xdh = tc::make_smem_desc(tc::smem_u32(xs_hi), 128, SBO), xdl = tc::make_smem_desc(tc::smem_u32(xs_lo), 128, SBO);
-            const uint64_t ydh = tc::make_smem_desc(tc::smem_u32(ys_hi), 128, SBO), ydl = tc::make_smem_desc(tc::smem_u32(ys_lo), 128, SBO);
+    if (warp == 0) {
+        // ---- MMA warp: one lane issues the MMAs of a stage as soon as the staging warps have written it ------------------
+        if (lane == 0) {
+            for (int64_t it = 0; it < n_stages; ++it) {
+                const int buf = (int)(it & 1);
+                uint8_t* xs_hi = smem + (size_t)buf * stage_bytes;
+                uint8_t* xs_lo = xs_hi + x_part;
+                uint8_t* ys_hi = xs_lo + x_part;
+                uint8_t* ys_lo = ys_hi + y_part;
+                tc::mbar_wait(&ready[buf], (uint32_t)((it >> 1) & 1));
+                tc::fence_after_sync();
+                // one descriptor per operand part and stage; the MMAs only advance its start address
+                const uint64_t xdh = tc::make_smem_desc(tc::smem_u32(xs_hi), 128, SBO), xdl = tc::make_smem_desc(tc::smem_u32(xs_lo), 128, SBO);
+                const uint64_t ydh = tc::make_smem_desc(tc::smem_u32(ys_hi), 128, SBO), ydl = tc::make_smem_desc(tc::smem_u32(ys_lo), 128, SBO);
 #pragma unroll
-            for (int ks = 0; ks < RS / 8; ++ks) {
-                const uint64_t bdh = tc::desc_add(ydh, ks * 256), bdl = tc::desc_add(ydl, ks * 256);
+                for (int ks = 0; ks < RS / 8; ++ks) {
+                    const uint64_t bdh = tc::desc_add(ydh, ks * 256), bdl = tc::desc_add(ydl, ks * 256);
 #pragma unroll
-                for (int mt = 0; mt < 2; ++mt) {
-                    if (mt >= MT) break;
-                    const uint32_t d = tmem_base + (uint32_t)mt * ncol_tile;
-                    const uint64_t adh = tc::desc_add(xdh, mt * 16 * SBO + ks * 256), adl = tc::desc_add(xdl, mt * 16 * SBO + ks * 256);
-                    tc::mma_tf32_ss(d, adh, bdh, idesc, (it | ks) != 0);
-                    tc::mma_tf32_ss(d, adh, bdl, idesc, 1);
-                    tc::mma_tf32_ss(d, adl, bdh, idesc, 1);
+                    for (int mt = 0; mt < 2; ++mt) {
+                        if (mt >= MT) break;
+                        const uint32_t d = tmem_base + (uint32_t)mt * ncol_tile;
+                        const uint64_t adh = tc::desc_add(xdh, mt * 16 * SBO + ks * 256), adl = tc::desc_add(xdl, mt * 16 * SBO + ks * 256);
+                        tc::mma_tf32_ss(d, adh, bdh, idesc, (it | ks) != 0);
+                        tc::mma_tf32_ss(d, adh, bdl, idesc, 1);
+                        tc::mma_tf32_ss(d, adl, bdh, idesc, 1);
+                    }
                 }
+                tc::mma_commit(&empty[buf]);
+                if (it == n_stages - 1) tc::mma_commit(done);
             }
-            tc::mma_commit(&empty[buf]);
-            if (it == n_stages - 1) tc::mma_commit(done);
         }
-    };
-    for (int64_t it = 0; it < n_stages; it += 2) {
-        do_stage(it, px0, py0);
-        if (it + 1 < n_stages) do_stage(it + 1, px1, py1);
+    } else {
+        // ---- staging warps: register prefetch two stages ahead (sets p0 / p1 alternate) ------------------------------------
+        Prefetch p0, p1;
+        const StagePlan sp = make_stage_plan<RS>(M, N, tid - 32);
+        if (n_stages > 0) stage_load(X, Y, r_begin, r_end, sp, p0);
+        if (n_stages > 1) stage_load(X, Y, r_begin + RS, r_end, sp, p1);
+        auto do_stage = [&](int64_t it, Prefetch& pf) {
+            const int buf = (int)(it & 1);
+            uint8_t* xs_hi = smem + (size_t)buf * stage_bytes;
+            uint8_t* xs_lo = xs_hi + x_part;
+            uint8_t* ys_hi = xs_lo + x_part;
+            uint8_t* ys_lo = ys_hi + y_part;
+            if (it >= 2) tc::mbar_wait(&empty[buf], (uint32_t)(((it >> 1) - 1) & 1));
+            stage_store(pf, sp, xs_hi, xs_lo, ys_hi, ys_lo);
+            if (it + 2 < n_stages) stage_load(X, Y, r_begin + (it + 2) * RS, r_end, sp, pf);
+            tc::fence_async_smem();
+            tc::mbar_arrive(&ready[buf]);
+        };
+        for (int64_t it = 0; it < n_stages; it += 2) {
+            do_stage(it, p0);
+            if (it + 1 < n_stages) do_stage(it + 1, p1);
+        }
     }
+    __syncwarp();
     if (n_stages > 0) {
         tc::mbar_wait(done, 0);
         tc::fence_after_sync();
