@@ -109,6 +109,7 @@ __global__ void __launch_bounds__(NTH, 1) linear_tc_kernel(const float* __restri
     const uint32_t w_part = (uint32_t)NP * KC * 4;
     const bool vec = (K % 4 == 0) && (((uintptr_t)X & 15) == 0) && (!BWD || ((((uintptr_t)Yact | (uintptr_t)dpre) & 15) == 0));
     const bool vec_out = (N % 4 == 0) && (((uintptr_t)Y & 15) == 0);
+    const bool bias_vec = bias != nullptr && (((uintptr_t)bias & 15) == 0);
     // shared memory: NSTG X stages (hi | lo) + 2 weight-chunk buffers (hi | lo); TMEM: one accumulator per tile of a group
     uint8_t* wbuf0 = smem + (size_t)NSTG * 2 * X_PART;
     uint64_t* bars = reinterpret_cast<uint64_t*>(wbuf0 + (size_t)2 * 2 * w_part);
@@ -150,9 +151,32 @@ __global__ void __launch_bounds__(NTH, 1) linear_tc_kernel(const float* __restri
             tc::tmem_ld16(d + c0, v);
             if (m < M) {
                 if (!BWD) {
+                    // bias: four 16-byte reads per 16 columns when the row of biases allows it; the activation switch is hoisted
+                    // out of the element loop (the appearance head and the dHidden pass have none: a plain add)
+                    float b[16];
+                    if (bias_vec && c0 + 16 <= N) {
 #pragma unroll
-                    for (int jj = 0; jj < 16; ++jj)
-                        if (c0 + jj < N) v[jj] = act_fwd(v[jj] + (bias ? __ldg(bias + c0 + jj) : 0.f), act, act_p);
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const float4 t = ldg4(bias + c0 + 4 * jj);
+                            b[4 * jj] = t.x; b[4 * jj + 1] = t.y; b[4 * jj + 2] = t.z; b[4 * jj + 3] = t.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int jj = 0; jj < 16; ++jj) b[jj] = (bias && c0 + jj < N) ? __ldg(bias + c0 + jj) : 0.f;
+                    }
+                    if (act == ACT_NONE) {
+#pragma unroll
+                        for (int jj = 0; jj < 16; ++jj) v[jj] += b[jj];
+                    } else if (act == ACT_RELU) {
+#pragma unroll
+                        for (int jj = 0; jj < 16; ++jj) v[jj] = fmaxf(v[jj] + b[jj], 0.f);
+                    } else if (act == ACT_LEAKY) {
+#pragma unroll
+                        for (int jj = 0; jj < 16; ++jj) { const float x = v[jj] + b[jj]; v[jj] = x > 0.f ? x : 0.01f * x; }
+                    } else {
+#pragma unroll
+                        for (int jj = 0; jj < 16; ++jj) v[jj] = act_fwd(v[jj] + b[jj], act, act_p);
+                    }
                 }
                 if (vec_out) {
                     float4* dst = reinterpret_cast<float4*>(Y + (size_t)m * N + c0);
