@@ -21,7 +21,9 @@ constexpr int TM = 128;
 constexpr int KC = 32;                 // K chunk per pipeline stage
 constexpr int NSTG = 2;
 constexpr int NTH = 512;
-constexpr int XPT = 1024 / NTH;         // float4 loads per thread and stage (128 rows x 8 chunks)
+constexpr int NWORK = NTH - 32;        // staging warps 1..15; warp 0 streams the weight chunks and issues the MMAs (a thread that issues a
+                                       // dozen MMAs back to back is blocked while the tensor queue drains: no staging warp may wait for it)
+constexpr int XPT = (1024 + NWORK - 1) / NWORK;   // float4 loads per worker and stage (128 rows x 8 chunks = 1024)
 constexpr uint32_t X_LBO = 144;        // K-chunk (16 B) stride of the X operand, padded for bank spread
 constexpr uint32_t X_SBO = (KC / 4) * X_LBO;
 constexpr uint32_t X_PART = 16 * X_SBO;      // bytes of one X part (hi or lo) of a stage
@@ -51,7 +53,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar)), "r"(bytes) : "memory");
 }
 
-struct XRegs { float4 v[XPT]; };     // one stage of X per thread: 128 rows x 8 chunks = 1024 float4 / 256 threads
+struct XRegs { float4 v[XPT]; };     // one stage of X per worker: 128 rows x 8 chunks = 1024 float4 over 480 workers
 
 // one stage of the A operand: X[m][k0 .. k0+32) for the tile's 128 rows.  BWD: element = dY * act'(Y), also stored to dpre
 template <bool BWD>
@@ -59,12 +61,12 @@ __device__ __forceinline__ void x_load(const float* __restrict__ X, const float*
                                        float act_p, bool vec, int64_t M, int K, int64_t row0, int k0, XRegs& r) {
 #pragma unroll
     for (int j = 0; j < XPT; ++j) {
-        const int it = threadIdx.x + j * NTH;
+        const int it = (int)threadIdx.x - 32 + j * NWORK;
         const int row = it >> 3, ch = it & 7;
         const int64_t m = row0 + row;
         const int k = k0 + ch * 4;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (m < M && k < K) {
+        if (it < 1024 && m < M && k < K) {
             const size_t o = (size_t)m * K + k;
             if (vec) {
                 v = ldg4(X + o);
@@ -90,7 +92,8 @@ __device__ __forceinline__ void x_load(const float* __restrict__ X, const float*
 __device__ __forceinline__ void x_store(const XRegs& r, uint8_t* hi, uint8_t* lo) {
 #pragma unroll
     for (int j = 0; j < XPT; ++j) {
-        const int it = threadIdx.x + j * NTH;
+        const int it = (int)threadIdx.x - 32 + j * NWORK;
+        if (it >= 1024) continue;
         const int row = it >> 3, ch = it & 7;
         const uint32_t off = (uint32_t)(row >> 3) * X_SBO + ch * X_LBO + (row & 7) * 16;
         const float4 v = r.v[j];
@@ -116,8 +119,10 @@ __global__ void __launch_bounds__(NTH, 1) linear_tc_kernel(const float* __restri
     uint64_t* wfull = bars;              // [2] weight chunk landed
     uint64_t* wfree = bars + 2;          // [2] weight chunk consumed by the last MMA that reads it
     uint64_t* sfree = bars + 4;          // [NSTG] X stage consumed by its MMAs
-    uint64_t* dfull = bars + 4 + NSTG;   // accumulators of the group complete
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 + NSTG);
+    uint64_t* sready = sfree + NSTG;     // [NSTG] X stage written by the staging warps
+    uint64_t* dfull = sready + NSTG;     // accumulators of the group complete
+    uint64_t* tfree = dfull + 1;         // accumulators of the group read out by the staging warps
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfree + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nchunks = KP / KC;
     const int cstride = NP <= 128 ? 128 : 256;         // TMEM columns per accumulator
@@ -130,8 +135,8 @@ __global__ void __launch_bounds__(NTH, 1) linear_tc_kernel(const float* __restri
     if (warp == 0) tc::tmem_alloc<512>(tmem_slot);
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) { tc::mbar_init(&wfull[i], 1); tc::mbar_init(&wfree[i], 1); }
-        for (int i = 0; i < NSTG; ++i) tc::mbar_init(&sfree[i], 1);
-        tc::mbar_init(dfull, 1);
+        for (int i = 0; i < NSTG; ++i) { tc::mbar_init(&sfree[i], 1); tc::mbar_init(&sready[i], NWORK); }
+        tc::mbar_init(dfull, 1); tc::mbar_init(tfree, NWORK);
         tc::mbar_fence_init();
     }
     tc::fence_before_sync();
@@ -198,84 +203,103 @@ __global__ void __launch_bounds__(NTH, 1) linear_tc_kernel(const float* __restri
         mbar_expect_tx(&wfull[buf], 2 * w_part);
         bulk_copy_g2s(wbuf0 + (size_t)buf * 2 * w_part, Wtc + (size_t)(w % nchunks) * 2 * NP * KC, 2 * w_part, &wfull[buf]);
     };
-    if (tid == 0 && total_w > 0) issue_w(0);
-
-    // step = (group, weight chunk, tile of the group); the X rows of a step are loaded into registers PF steps ahead
+    // step = (group, weight chunk, tile of the group)
     struct Step { int64_t grp; int kc, j; };
     auto group_size = [&](int64_t grp) { return (int)(my_tiles - grp * G < G ? my_tiles - grp * G : G); };
     auto advance = [&](Step& s) {
         if (++s.j == group_size(s.grp)) { s.j = 0; if (++s.kc == nchunks) { s.kc = 0; ++s.grp; } }
     };
-    auto load_step = [&](const Step& s, XRegs& r) {
-        if (s.grp < ngroups) x_load<BWD>(X, Yact, dpre, act, act_p, vec, M, K, (blockIdx.x + (s.grp * G + s.j) * gridDim.x) * TM, s.kc * KC, r);
-    };
-    constexpr int PF = 4;
-    XRegs xr[PF];
-    Step ahead = {0, 0, 0};
+    if (warp == 0) {
+        // ======================= driver warp: weight chunks + MMAs (lane 0), then its share of the group's epilogue ==============
+        if (lane == 0 && total_w > 0) issue_w(0);
+        int64_t q = 0;
+        for (int64_t grp = 0; grp < ngroups; ++grp) {
+            const int Gc = group_size(grp);
+            if (lane == 0) {
+                if (grp > 0) { tc::mbar_wait(tfree, (uint32_t)((grp - 1) & 1)); tc::fence_after_sync(); }    // accumulators read out
+                for (int kc = 0; kc < nchunks; ++kc) {
+                    const int64_t w = grp * nchunks + kc;
+                    if (w + 1 < total_w) issue_w(w + 1);
+                    tc::mbar_wait(&wfull[w & 1], (uint32_t)((w >> 1) & 1));
+                    tc::fence_after_sync();
+                    const uint32_t wh = tc::smem_u32(wbuf0 + (size_t)(w & 1) * 2 * w_part);
+                    const uint64_t wdh0 = tc::make_smem_desc(wh, 128, w_sbo), wdl0 = tc::make_smem_desc(wh + w_part, 128, w_sbo);
+                    for (int j = 0; j < Gc; ++j, ++q) {
+                        const int st = (int)(q % NSTG);
+                        uint8_t* x_hi = smem + (size_t)st * 2 * X_PART;
+                        uint8_t* x_lo = x_hi + X_PART;
+                        tc::mbar_wait(&sready[st], (uint32_t)((q / NSTG) & 1));
+                        tc::fence_after_sync();
+                        const uint32_t d = tmem_base + (uint32_t)j * cstride;
+                        const uint64_t xdh = tc::make_smem_desc(tc::smem_u32(x_hi), X_LBO, X_SBO), xdl = tc::make_smem_desc(tc::smem_u32(x_lo), X_LBO, X_SBO);
 #pragma unroll
-    for (int i = 0; i < PF; ++i) { load_step(ahead, xr[i]); if (ahead.grp < ngroups) advance(ahead); }
-    Step cur = {0, 0, 0};
-    int64_t q = 0;                                     // X stage counter
-    auto do_step = [&](XRegs& r) {
-        const int64_t grp = cur.grp;
-        const int kc = cur.kc, j = cur.j, Gc = group_size(grp);
-        const int64_t w = grp * nchunks + kc;
-        const int st = (int)(q % NSTG);
-        uint8_t* x_hi = smem + (size_t)st * 2 * X_PART;
-        uint8_t* x_lo = x_hi + X_PART;
-        if (q >= NSTG) tc::mbar_wait(&sfree[st], (uint32_t)(((q / NSTG) - 1) & 1));
-        x_store(r, x_hi, x_lo);
-        load_step(ahead, r);
-        if (ahead.grp < ngroups) advance(ahead);
-        tc::fence_async_smem();
-        tc::fence_before_sync();
-        __syncthreads();
-        tc::fence_after_sync();
-        if (tid == 0) {
-            if (j == 0) {
-                if (w + 1 < total_w) issue_w(w + 1);
-                tc::mbar_wait(&wfull[w & 1], (uint32_t)((w >> 1) & 1));
-                tc::fence_after_sync();
+                        for (int ks = 0; ks < KC / 8; ++ks) {
+                            const uint64_t adh = tc::desc_add(xdh, ks * 2 * X_LBO), adl = tc::desc_add(xdl, ks * 2 * X_LBO);
+                            const uint64_t wdh = tc::desc_add(wdh0, ks * 256), wdl = tc::desc_add(wdl0, ks * 256);
+                            tc::mma_tf32_ss(d, adh, wdh, idesc, (kc | ks) != 0);
+                            tc::mma_tf32_ss(d, adh, wdl, idesc, 1);
+                            tc::mma_tf32_ss(d, adl, wdh, idesc, 1);
+                        }
+                        tc::mma_commit(&sfree[st]);
+                    }
+                    tc::mma_commit(&wfree[w & 1]);
+                }
+                tc::mma_commit(dfull);
             }
-            const uint32_t d = tmem_base + (uint32_t)j * cstride;
-            const uint32_t wh = tc::smem_u32(wbuf0 + (size_t)(w & 1) * 2 * w_part);
-            const uint64_t xdh = tc::make_smem_desc(tc::smem_u32(x_hi), X_LBO, X_SBO), xdl = tc::make_smem_desc(tc::smem_u32(x_lo), X_LBO, X_SBO);
-            const uint64_t wdh0 = tc::make_smem_desc(wh, 128, w_sbo), wdl0 = tc::make_smem_desc(wh + w_part, 128, w_sbo);
-#pragma unroll
-            for (int ks = 0; ks < KC / 8; ++ks) {
-                const uint64_t adh = tc::desc_add(xdh, ks * 2 * X_LBO), adl = tc::desc_add(xdl, ks * 2 * X_LBO);
-                const uint64_t wdh = tc::desc_add(wdh0, ks * 256), wdl = tc::desc_add(wdl0, ks * 256);
-                tc::mma_tf32_ss(d, adh, wdh, idesc, (kc | ks) != 0);
-                tc::mma_tf32_ss(d, adh, wdl, idesc, 1);
-                tc::mma_tf32_ss(d, adl, wdh, idesc, 1);
-            }
-            tc::mma_commit(&sfree[st]);
-            if (j == Gc - 1) {
-                tc::mma_commit(&wfree[w & 1]);
-                if (kc == nchunks - 1) tc::mma_commit(dfull);
-            }
-        }
-        ++q;
-        if (j == Gc - 1 && kc == nchunks - 1) {
-            // the group's accumulators: bias + activation + store, then TMEM is free for the next group
+            __syncwarp();
             tc::mbar_wait(dfull, (uint32_t)(grp & 1));
             tc::fence_after_sync();
             for (int jj = 0; jj < Gc; ++jj) epilogue(grp * G + jj, jj);
             tc::fence_before_sync();
+            __syncwarp();
         }
-        advance(cur);
-    };
-    while (cur.grp < ngroups) {
+    } else {
+        // ======================= staging warps: X rows -> registers PF steps ahead -> tf32 hi | lo in shared memory ================
+        auto load_step = [&](const Step& s, XRegs& r) {
+            if (s.grp < ngroups) x_load<BWD>(X, Yact, dpre, act, act_p, vec, M, K, (blockIdx.x + (s.grp * G + s.j) * gridDim.x) * TM, s.kc * KC, r);
+        };
+        constexpr int PF = 4;
+        XRegs xr[PF];
+        Step ahead = {0, 0, 0};
 #pragma unroll
-        for (int i = 0; i < PF; ++i)
-            if (cur.grp < ngroups) do_step(xr[i]);
+        for (int i = 0; i < PF; ++i) { load_step(ahead, xr[i]); if (ahead.grp < ngroups) advance(ahead); }
+        Step cur = {0, 0, 0};
+        int64_t q = 0;                                     // X stage counter
+        auto do_step = [&](XRegs& r) {
+            const int64_t grp = cur.grp;
+            const int kc = cur.kc, j = cur.j, Gc = group_size(grp);
+            const int st = (int)(q % NSTG);
+            uint8_t* x_hi = smem + (size_t)st * 2 * X_PART;
+            uint8_t* x_lo = x_hi + X_PART;
+            if (q >= NSTG) tc::mbar_wait(&sfree[st], (uint32_t)(((q / NSTG) - 1) & 1));
+            x_store(r, x_hi, x_lo);
+            load_step(ahead, r);
+            if (ahead.grp < ngroups) advance(ahead);
+            tc::fence_async_smem();
+            tc::mbar_arrive(&sready[st]);
+            ++q;
+            if (j == Gc - 1 && kc == nchunks - 1) {
+                // the group's accumulators: bias + activation + store, then TMEM is free for the next group
+                tc::mbar_wait(dfull, (uint32_t)(grp & 1));
+                tc::fence_after_sync();
+                for (int jj = 0; jj < Gc; ++jj) epilogue(grp * G + jj, jj);
+                tc::fence_before_sync();
+                tc::mbar_arrive(tfree);
+            }
+            advance(cur);
+        };
+        while (cur.grp < ngroups) {
+#pragma unroll
+            for (int i = 0; i < PF; ++i)
+                if (cur.grp < ngroups) do_step(xr[i]);
+        }
     }
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc<512>(tmem_base);
 }
 
-size_t linear_tc_smem(int NP) { return (size_t)NSTG * 2 * X_PART + (size_t)2 * 2 * NP * KC * 4 + (5 + NSTG) * 8 + 16; }
+size_t linear_tc_smem(int NP) { return (size_t)NSTG * 2 * X_PART + (size_t)2 * 2 * NP * KC * 4 + (6 + 2 * NSTG) * 8 + 16; }
 int pad16(int n) { return (n + 15) / 16 * 16; }
 
 }  // namespace
