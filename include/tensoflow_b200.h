@@ -132,6 +132,19 @@ TF_API int tf_sdf_stencil_bwd(const tf_vm_field_t* f, const tf_sdf_mlp_t* m, con
                        const tf_sdf_mlp_grad_t* g_mlp, void* workspace, size_t ws_bytes,
                        tf_stream_t stream);
 
+/* The same with the centre hidden activations KEPT from the forward call: hidden_centre[n, hidden] = the block at byte offset
+ * tf_sdf_stencil_fwd_hidden_offset(f, m) of the workspace that was passed to tf_sdf_stencil_fwd (with feat != NULL), which the
+ * caller then has to keep alive until the backward call.  The backward kernel does not recompute / store them (they feed the
+ * weight gradient of the appearance head).  hidden_centre == NULL behaves like tf_sdf_stencil_bwd; the offset is (size_t)-1
+ * when the forward path for this decoder shape does not produce the block. */
+TF_API size_t tf_sdf_stencil_fwd_hidden_offset(const tf_vm_field_t* f, const tf_sdf_mlp_t* m);
+TF_API int tf_sdf_stencil_bwd_kept(const tf_vm_field_t* f, const tf_sdf_mlp_t* m, const float* xyz,
+                       const float* level, int64_t n, const float units[3], const float* sdf7, const float* hidden_centre,
+                       const float* g_sdf, const float* g_feat, const float* g_grad,
+                       const float* g_hess, const tf_vm_mut_t* g_field,
+                       const tf_sdf_mlp_grad_t* g_mlp, void* workspace, size_t ws_bytes,
+                       tf_stream_t stream);
+
 /* ---- NeuS alpha + compositing ------------------------------------------------
  * Replaces ShapeRenderer.compute_sdf_alpha's tail (network/shapeRenderer.py:1004-1024),
  * nerfacc.render_weight_from_alpha and the nerfacc.accumulate_along_rays calls

@@ -60,6 +60,10 @@ _SIGNATURES = {
     "tf_sdf_stencil_bwd": (C.c_int, [C.POINTER(VMField), C.POINTER(SdfMlp), _P, _P, C.c_int64,
                                      C.POINTER(C.c_float), _P, _P, _P, _P, _P, C.POINTER(VMMut),
                                      C.POINTER(SdfMlpGrad), _P, C.c_size_t, _P]),
+    "tf_sdf_stencil_fwd_hidden_offset": (C.c_size_t, [C.POINTER(VMField), C.POINTER(SdfMlp)]),
+    "tf_sdf_stencil_bwd_kept": (C.c_int, [C.POINTER(VMField), C.POINTER(SdfMlp), _P, _P, C.c_int64,
+                                          C.POINTER(C.c_float), _P, _P, _P, _P, _P, _P, C.POINTER(VMMut),
+                                          C.POINTER(SdfMlpGrad), _P, C.c_size_t, _P]),
     "tf_neus_composite_fwd": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, _P, C.c_float, _P, C.c_int32,
                                         _P, _P, _P, _P, _P]),
     "tf_neus_composite_bwd": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, _P, C.c_float, _P, C.c_int32,

@@ -639,7 +639,7 @@ extern "C" TF_API size_t tf_sdf_stencil_bwd_workspace(const tf_vm_field_t* f, co
 static int stencil_bwd_tc(const tf_vm_field_t* f, const tf_sdf_mlp_t* m, const Dims& d, const float* xyz, const float* level, int64_t n,
                           const float units[3], const float* sdf7, const float* g_sdf, const float* g_feat, const float* g_grad,
                           const float* g_hess, const tf_vm_mut_t* g_field, const tf_sdf_mlp_grad_t* g_mlp, float* ws, size_t ws_floats,
-                          cudaStream_t stream) {
+                          const float* hidden_c, cudaStream_t stream) {
     const int KT = (d.K + 15) / 16 * 16, H = d.H;
     const int spt = tf_internal_bwd_tc_samples_per_tile();
     const size_t fixed = bwd_tc_fixed_floats(d), per_tile = bwd_tc_tile_floats(d);
@@ -669,15 +669,17 @@ static int stencil_bwd_tc(const tf_vm_field_t* f, const tf_sdf_mlp_t* m, const D
         }
         if (int e = tf_internal_stencil_bwd_tc(f, g_field, m, wtc, xyz + s0 * 3, level ? level + s0 : nullptr, ns, units, sdf7 + s0 * NQ,
                                                g_sdf ? g_sdf + s0 : nullptr, g_grad ? g_grad + s0 * 3 : nullptr,
-                                               g_hess ? g_hess + s0 : nullptr, gf ? dHc : nullptr, dpre, arow, gf ? spc : nullptr,
+                                               g_hess ? g_hess + s0 : nullptr, gf ? dHc : nullptr, dpre, arow, (gf && !hidden_c) ? spc : nullptr,
                                                da_scratch, g_mlp->W1, g_mlp->b1, stream))
             return e;
         // [dW0 | db0] staging += dPre^T [A | 1]
         if (tf_internal_xty_tc_ok(dpre, arow, H, KT)) tf_internal_xty_tc(dpre, arow, nt * 128, H, KT, tmp, KT, d.K + 1, stream);
         else tf_internal_xty(dpre, H, arow, KT, nt * 128, H, KT, tmp, KT, stream);
         if (gf) {
-            if (tf_internal_xty_tc_ok(gf, spc, d.A, H)) tf_internal_xty_tc(gf, spc, ns, d.A, H, g_mlp->W1 + H, H, H, stream);
-            else tf_internal_xty(gf, d.A, spc, H, ns, d.A, H, g_mlp->W1 + H, H, stream);
+            // centre hidden activations: kept from the forward call when the caller has them, else recomputed by the kernel above
+            const float* hid = hidden_c ? hidden_c + s0 * H : spc;
+            if (tf_internal_xty_tc_ok(gf, hid, d.A, H)) tf_internal_xty_tc(gf, hid, ns, d.A, H, g_mlp->W1 + H, H, H, stream);
+            else tf_internal_xty(gf, d.A, hid, H, ns, d.A, H, g_mlp->W1 + H, H, stream);
             tf_internal_colsum(gf, d.A, ns, d.A, g_mlp->b1 + 1, stream);
         }
     }
@@ -686,10 +688,27 @@ static int stencil_bwd_tc(const tf_vm_field_t* f, const tf_sdf_mlp_t* m, const D
     return 0;
 }
 
+// byte offset of the centre hidden activations [n, hidden] inside the workspace of tf_sdf_stencil_fwd(.., feat != NULL);
+// (size_t)-1 when the forward path for this shape does not produce them
+extern "C" TF_API size_t tf_sdf_stencil_fwd_hidden_offset(const tf_vm_field_t* f, const tf_sdf_mlp_t* m) {
+    Dims d;
+    if (!f || !m || check_mlp(f, m, d) || use_simt_path(d)) return (size_t)-1;
+    const int KT = (d.K + 15) / 16 * 16;
+    return tf_internal_tc_w0_floats(KT, d.H) * sizeof(float);
+}
+
 extern "C" TF_API int tf_sdf_stencil_bwd(const tf_vm_field_t* f, const tf_sdf_mlp_t* m, const float* xyz, const float* level,
                                   int64_t n, const float units[3], const float* sdf7, const float* g_sdf, const float* g_feat,
                                   const float* g_grad, const float* g_hess, const tf_vm_mut_t* g_field,
                                   const tf_sdf_mlp_grad_t* g_mlp, void* workspace, size_t ws_bytes, tf_stream_t stream_) {
+    return tf_sdf_stencil_bwd_kept(f, m, xyz, level, n, units, sdf7, nullptr, g_sdf, g_feat, g_grad, g_hess, g_field, g_mlp, workspace, ws_bytes,
+                                   stream_);
+}
+
+extern "C" TF_API int tf_sdf_stencil_bwd_kept(const tf_vm_field_t* f, const tf_sdf_mlp_t* m, const float* xyz, const float* level,
+                                       int64_t n, const float units[3], const float* sdf7, const float* hidden_centre, const float* g_sdf,
+                                       const float* g_feat, const float* g_grad, const float* g_hess, const tf_vm_mut_t* g_field,
+                                       const tf_sdf_mlp_grad_t* g_mlp, void* workspace, size_t ws_bytes, tf_stream_t stream_) {
     if (int e = tf_check_field(f, level != nullptr)) return e;
     Dims d;
     if (int e = check_mlp(f, m, d)) return e;
@@ -705,9 +724,10 @@ extern "C" TF_API int tf_sdf_stencil_bwd(const tf_vm_field_t* f, const tf_sdf_ml
     cudaStream_t stream = (cudaStream_t)stream_;
     float* ws = (float*)workspace;
     TF_REQUIRE(workspace, "workspace is NULL");
+    if (hidden_centre) TF_REQUIRE(((uintptr_t)hidden_centre & 15) == 0, "hidden_centre not 16-byte aligned");
     if (!use_simt_bwd(d))
         return stencil_bwd_tc(f, m, d, xyz, level, n, units, sdf7, g_sdf, g_feat, g_grad, g_hess, g_field, g_mlp, ws,
-                              ws_bytes / sizeof(float), stream);
+                              ws_bytes / sizeof(float), hidden_centre, stream);
     const size_t wfl = weights_ws_floats(d);
     TF_REQUIRE(ws_bytes >= (wfl + bwd_slice_floats(d, TS)) * sizeof(float), "workspace too small (%zu bytes)", ws_bytes);
     // samples per slice that fit the workspace (multiple of TS)

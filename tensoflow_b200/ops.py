@@ -228,6 +228,10 @@ def _units_arr(units) -> C.Array:
     return (C.c_float * 3)(*u)
 
 
+# keep the forward's centre hidden activations for the backward (False: the backward recomputes them, 4 n H bytes less between the two)
+KEEP_HIDDEN = True
+
+
 class SdfStencilFunction(torch.autograd.Function):
     """TensoSDF.forward at x plus the six FD taps of TensoSDF.gradient
     (reference network/fields.py:262-299, 227-260) in one fused kernel.
@@ -264,6 +268,13 @@ class SdfStencilFunction(torch.autograd.Function):
         ctx.save_for_backward(xyz_c, lvl_c, sdf7, aabb, W0, b0, W1, b1, *factors)
         ctx.units = [float(x) for x in units]
         ctx.n_levels = n_levels
+        # the centre hidden activations sit in the forward workspace: keep it for the backward (4 n H bytes) so that the backward
+        # kernel does not recompute and store them again (they feed the weight gradient of the appearance head)
+        ctx.hidden = None
+        if KEEP_HIDDEN and any(ctx.needs_input_grad):
+            off = lib.tf_sdf_stencil_fwd_hidden_offset(C.byref(vm.c), C.byref(m))
+            if off != C.c_size_t(-1).value:
+                ctx.hidden = (ws, off)
         sdf = sdf7[:, 0].contiguous()
         return sdf, feat, grad, hess
 
@@ -284,10 +295,12 @@ class SdfStencilFunction(torch.autograd.Function):
         wsb = min(need_all, max(BWD_WORKSPACE_BYTES, lib.tf_sdf_stencil_bwd_workspace(C.byref(vm.c), C.byref(m), 16)))
         ws = torch.empty(wsb // 4, device=xyz_c.device, dtype=torch.float32)
         gs, gf, gg, gh = _f32c(g_sdf), _f32c(g_feat), _f32c(g_grad), _f32c(g_hess)
+        hid = None if ctx.hidden is None else ctx.hidden[0].data_ptr() + ctx.hidden[1]
         with _timed("sdf_stencil_bwd"):
-            check(lib.tf_sdf_stencil_bwd(C.byref(vm.c), C.byref(m), ptr(xyz_c), ptr(lvl_c), n, _units_arr(ctx.units), ptr(sdf7),
-                                         ptr(gs), ptr(gf), ptr(gg), ptr(gh), C.byref(g), C.byref(mg), ptr(ws), wsb, stream_ptr()),
-                  "tf_sdf_stencil_bwd")
+            check(lib.tf_sdf_stencil_bwd_kept(C.byref(vm.c), C.byref(m), ptr(xyz_c), ptr(lvl_c), n, _units_arr(ctx.units), ptr(sdf7), hid,
+                                              ptr(gs), ptr(gf), ptr(gg), ptr(gh), C.byref(g), C.byref(mg), ptr(ws), wsb, stream_ptr()),
+                  "tf_sdf_stencil_bwd_kept")
+        ctx.hidden = None
         d_planes, d_lines = vm.finish_grads(g, gp, gl, with_mips)
         return (None, None, None, None, None, dW0, db0, dW1, db1, *d_planes, *d_lines)
 

@@ -153,6 +153,31 @@ def test_stencil_backward(C, H, A, G0, ups, N, with_level, monkeypatch):
         close_as_fp32(pc.grad, p64.grad, p32.grad, 1e-3, f"d {name}", fd=True)    # upstream gradients enter through the FD taps
 
 
+def test_stencil_backward_kept_hidden_equals_recompute(monkeypatch):
+    """tf_sdf_stencil_bwd_kept with the centre hidden activations kept from the forward workspace gives the same gradients as
+    tf_sdf_stencil_bwd, which recomputes them (sliced workspace: the kept block is indexed per slice)."""
+    from tensoflow_b200 import ops
+    C_, H, A, G0, ups, N = CONFIGS[0]
+    N = max(N, 3000)
+    _, _, cu = make_fields(C_, H, A, G0, ups)
+    dev = _cuda()
+    monkeypatch.setattr(ops, "BWD_WORKSPACE_BYTES", 48 << 20)
+    x, lv = points(N, 17, True, cu.n_levels)
+    g = torch.Generator().manual_seed(19)
+    u_sdf, u_feat = torch.randn(N, generator=g).to(dev), torch.randn(N, A, generator=g).to(dev)
+    grads = {}
+    for keep in (True, False):
+        monkeypatch.setattr(ops, "KEEP_HIDDEN", keep)
+        for p in cu.parameters():
+            p.grad = None
+        sdf, feat, grad, hess = cu.stencil(x.to(dev), lv.to(dev))
+        ((sdf * u_sdf).sum() + (feat * u_feat).sum() + grad.sum() + 1e-2 * hess.sum()).backward()
+        grads[keep] = {n: p.grad.clone() for n, p in cu.named_parameters()}
+    for n in grads[True]:
+        e = rel_err(grads[True][n], grads[False][n])
+        assert e < 2e-6, f"{n}: kept vs recomputed hidden activations differ by {e:.2e}"
+
+
 def _composite_inputs(n_rays, max_s, seed, D=7):
     g = torch.Generator().manual_seed(seed)
     counts = torch.randint(0, max_s + 1, (n_rays,), generator=g)
