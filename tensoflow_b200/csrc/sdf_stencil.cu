@@ -608,6 +608,8 @@ int tf_internal_matmul(const float* A, int lda, const float* W, int ldw, int64_t
                        cudaStream_t stream);
 bool tf_internal_xty_tc_ok(const float* X, const float* Y, int M, int N);
 int tf_internal_xty_tc(const float* X, const float* Y, int64_t rows, int M, int N, float* out, int ldo, int n_valid, cudaStream_t stream);
+int tf_internal_xty_tc_tiled(const float* X, const float* Y, int64_t rows, int M, int N, float* out, int ldo, int n_valid, int x_tiled,
+                             cudaStream_t stream);
 
 static bool use_simt_bwd(const Dims& d) {
     const int KT = (d.K + 15) / 16 * 16;
@@ -672,9 +674,10 @@ static int stencil_bwd_tc(const tf_vm_field_t* f, const tf_sdf_mlp_t* m, const D
                                                g_hess ? g_hess + s0 : nullptr, gf ? dHc : nullptr, dpre, arow, (gf && !hidden_c) ? spc : nullptr,
                                                da_scratch, g_mlp->W1, g_mlp->b1, stream))
             return e;
-        // [dW0 | db0] staging += dPre^T [A | 1]
-        if (tf_internal_xty_tc_ok(dpre, arow, H, KT)) tf_internal_xty_tc(dpre, arow, nt * 128, H, KT, tmp, KT, d.K + 1, stream);
-        else tf_internal_xty(dpre, H, arow, KT, nt * 128, H, KT, tmp, KT, stream);
+        // [dW0 | db0] staging += dPre^T [A | 1]; the kernel wrote dPre per tile as [H][128] (row fastest: coalesced stores there,
+        // no register transpose here)
+        TF_REQUIRE(tf_internal_xty_tc_ok(dpre, arow, H, KT), "tensor-core X^T Y does not take this decoder shape (H=%d, KT=%d)", H, KT);
+        if (int e = tf_internal_xty_tc_tiled(dpre, arow, nt * 128, H, KT, tmp, KT, d.K + 1, 1, stream)) return e;
         if (gf) {
             // centre hidden activations: kept from the forward call when the caller has them, else recomputed by the kernel above
             const float* hid = hidden_c ? hidden_c + s0 * H : spc;

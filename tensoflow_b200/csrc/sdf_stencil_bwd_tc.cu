@@ -42,7 +42,7 @@ struct TcBwdParams {
     int K, KT, H, slot_floats;
     float units[3];
     float* da_scratch;       // [gridDim][128][KT+4]: dA tiles handed from the math to the memory group through L2
-    float* dpre;             // [tiles*128][H]
+    float* dpre;             // [tiles][H][128] (per tile: column-major, rows fastest)
     float* arow;             // [tiles*128][KT]
     float* spc;              // [n][H] centre hidden activations (NULL = not needed)
     float* dW1r0; float* db1;
@@ -351,10 +351,12 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_bwd_tc_kernel(TcBwdParams 
                     unpack2(fmul2(ffma2(gg, pack2(ww.z, ww.w), pack2(hcv[j + 2], hcv[j + 3])), pack2(sg[2], sg[3])), v[j + 2], v[j + 3]);
                 }
                 if (tid != 0) { PROF(12) }
-                float4* dst = reinterpret_cast<float4*>(p.dpre + (size_t)(tile_row0 + row) * H + col0);
+                // dPre of the tile is stored [H][128] (row fastest): a warp's 32 rows of one column are one 128-byte store wavefront
+                // (row-major 16-byte pieces cost 8), and X^T Y reads 4 rows of a column as one K-major unit without transposing
+                float* dst = p.dpre + (size_t)tile_row0 * H + (size_t)col0 * TM + row;
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (!TF_DBG(p, 2)) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                for (int j = 0; j < 16; ++j)
+                    if (!TF_DBG(p, 2)) dst[j * TM] = v[j];
                 {   // the chunk becomes the A operand of the dA MMAs straight in tensor memory (tf32 hi | lo, lane = row)
                     float lo[16];
 #pragma unroll
