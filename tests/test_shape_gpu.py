@@ -153,6 +153,45 @@ def test_stencil_backward(C, H, A, G0, ups, N, with_level, monkeypatch):
         close_as_fp32(pc.grad, p64.grad, p32.grad, 1e-3, f"d {name}", fd=True)    # upstream gradients enter through the FD taps
 
 
+@pytest.mark.parametrize("N", [1, 5, 18, 19, 37, 2665])
+def test_stencil_tiny_and_ragged_batches(N):
+    """Edge sizes of the persistent tensor-core kernels: fewer samples than one 18-sample tile, exactly one tile, one sample into the
+    second tile, fewer tiles than CTAs, and one tile more than the 148 CTAs (2665 = 148 * 18 + 1): forward values and all parameter
+    gradients against the fp64 oracle."""
+    C_, H, A, G0, ups, _ = CONFIGS[2]
+    o32, o64, cu = make_fields(C_, H, A, G0, ups)
+    dev = _cuda()
+    x, lv = points(N, 23, True, o32.n_levels)
+    g = torch.Generator().manual_seed(29)
+    u_sdf, u_feat = torch.randn(N, generator=g), torch.randn(N, A, generator=g)
+    u_grad = torch.randn(N, 3, generator=g)
+
+    def oracle_loss(f, dt):
+        r = f(x.to(dt), lv.to(dt))
+        gr, he = f.gradient(x.to(dt), lv.to(dt), training=True, sdf=r[:, :1])
+        return r, gr, (r[:, 0] * u_sdf.to(dt)).sum() + (r[:, 1:] * u_feat.to(dt)).sum() + (gr * u_grad.to(dt)).sum()
+
+    r64, g64, l64 = oracle_loss(o64, torch.float64)
+    l64.backward()
+    r32, g32, l32 = oracle_loss(o32, torch.float32)
+    l32.backward()
+    sdf, feat, grad, hess = cu.stencil(x.to(dev), lv.to(dev))
+    ((sdf * u_sdf.to(dev)).sum() + (feat * u_feat.to(dev)).sum() + (grad * u_grad.to(dev)).sum()).backward()
+    # (max-normalised errors over a handful of samples: the denominator is the largest value of a few rows, not of thousands,
+    # so the value bars are 3e-5 here instead of the 1e-5 of the large-batch tests)
+    close_as_fp32(sdf, r64[:, 0].detach(), r32[:, 0].detach(), 3e-5, f"sdf (N={N})")
+    close_as_fp32(feat, r64[:, 1:].detach(), r32[:, 1:].detach(), 3e-5, f"features (N={N})")
+    close_as_fp32(grad, g64.detach(), g32.detach(), 1e-4, f"FD gradient (N={N})", fd=True)
+    with torch.no_grad():
+        only = cu.sdf(x.to(dev), lv.to(dev))
+        full = cu(x.to(dev), lv.to(dev))
+    close_as_fp32(only[:, 0], r64[:, 0].detach(), r32[:, 0].detach(), 3e-5, f"sdf-only kernel (N={N})")
+    close_as_fp32(full, r64.detach(), r32.detach(), 3e-5, f"single-query forward with features (N={N})")
+    for (name, p64), (_, p32), (_, pc) in zip(o64.named_parameters(), o32.named_parameters(), cu.named_parameters()):
+        assert pc.grad is not None, name
+        close_as_fp32(pc.grad, p64.grad, p32.grad, 1e-3, f"d {name} (N={N})", fd=True)
+
+
 def test_stencil_backward_kept_hidden_equals_recompute(monkeypatch):
     """tf_sdf_stencil_bwd_kept with the centre hidden activations kept from the forward workspace gives the same gradients as
     tf_sdf_stencil_bwd, which recomputes them (sliced workspace: the kept block is indexed per slice)."""
