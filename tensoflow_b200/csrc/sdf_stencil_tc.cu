@@ -51,7 +51,7 @@ struct TcParams {
     float* sdf7; float* grad; float* hess; float* sdf1;
     float* spc;          // [n][H] centre hidden activations (NULL = not needed)
 #ifdef TF_TC_DEBUG_SWITCHES
-    int debug;           // timing experiments only (never compiled into the product library): 1 skip gathers, 2 skip MMAs, 4 skip epilogue math
+    int debug;           // timing experiments only (never compiled into the product library): 1 skip gathers, 2 skip MMAs, 4 skip epilogue math, 8 skip the per-sample finalize
 #endif
 };
 
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(NTH, 1) sdf_stencil_fwd_tc_kernel(TcParams p) 
                 tc::mbar_arrive(aready);
             }
             // ---- finalize the samples of tile t ---------------------------------------------------------------------
-            if (tid < spt) {
+            if (tid < spt && !TF_DBG(p, 8)) {
                 const int64_t ns = tile * spt + tid;
                 const float* sp = &sdfs[(t & 1) * NCG * TM + tid * nq];
                 if (ns < p.n) {
