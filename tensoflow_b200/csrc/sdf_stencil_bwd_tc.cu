@@ -3,15 +3,17 @@
 // One persistent CTA per SM, 16 warps in two groups that work on different tiles at the same time
 // (MMA tile = 128 rows = 18 samples x 7 stencil queries, sample-major: stencil_site.cuh):
 //   memory group (8 warps, LSU-bound): gather of tile t+1 (features -> A operand hi/lo in shared memory + fp32 rows
-//       to the workspace) and shared-stencil scatter of tile t-1 (dA in shared memory -> RED.v4 into plane / line grads)
+//       to the workspace) and shared-stencil scatter of tile t-1 (dA from the CTA's L2 scratch tile -> RED.v4 into plane / line grads)
 //   math group (8 warps, ALU-bound) on tile t: GEMM1 pre = A W0^T (3xTF32, accumulator D1 in TMEM), then per
 //       32-column hidden chunk: tcgen05.ld -> Softplus / sigmoid -> dPre = (gq W1[0,:] + [centre] g_feat W1[1:]) * sigmoid
-//       -> workspace + TENSOR MEMORY (tcgen05.st, tf32 hi | lo), which the driver thread turns into
+//       -> workspace (per tile [H][128], row fastest: one store wavefront per warp and column; X^T Y reads it as K-major
+//       units) + TENSOR MEMORY (tcgen05.st, tf32 hi | lo), which the driver thread turns into
 //       dA += dPre[:,chunk] W0[chunk,:] MMAs with the A operand read from TMEM (no shared-memory round trip and no
-//       4 KB A read per instruction), accumulator D2; finally D2 -> shared memory for the memory group
+//       4 KB A read per instruction), accumulator D2; finally D2 -> the CTA's scratch tile in L2 for the memory group
 // Hand-offs are mbarriers (A ready / GEMM1 done / dA ready / dA consumed); weight slices (W0 by 8 features for GEMM1,
-// W0^T by 16 hidden units for GEMM-dA) stream through one cp.async.bulk ring.  Weight gradients are finished by
-// X^T Y passes over the workspace (xty_tc.cu).
+// W0^T by 16 hidden units for GEMM-dA) stream through one 4-stage cp.async.bulk ring, each stage refilled by its own
+// issuing lane (bulk copies of one warp execute one after the other).  Weight gradients are finished by X^T Y passes
+// over the workspace (xty_tc.cu); the centre hidden activations come from the forward call when the caller kept them.
 #include <stdio.h>
 #include <stdlib.h>
 #include "common.cuh"
